@@ -1,0 +1,1213 @@
+// Engine: weights, paged-KV slots, continuous-batching scheduler thread, vocoder driver and the C ABI
+// (include/xtts_b200.h).  Host orchestration that stands in for XTTSv2Engine + vLLM's engine loop
+// (XTTSv2.py:690-814); every tensor op below it is one of the kernels in this directory.
+#include "../../include/xtts_b200.h"
+#include "kernels.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+namespace xtts {
+
+static thread_local std::string t_last_error;
+static std::string g_last_error;
+static std::mutex g_err_mu;
+
+static void set_error(const std::string& s) {
+    t_last_error = s;
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    g_last_error = s;
+}
+
+static double now_s() {
+    using namespace std::chrono;
+    return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DBuf() = default;
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    ~DBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void zero(cudaStream_t st) { if (n) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void upload(const T* h, size_t count, cudaStream_t st, size_t off = 0) {
+        CUDA_CHECK(cudaMemcpyAsync(p + off, h, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+    void download(T* h, size_t count, cudaStream_t st, size_t off = 0) const {
+        CUDA_CHECK(cudaMemcpyAsync(h, p + off, count * sizeof(T), cudaMemcpyDeviceToHost, st));
+    }
+};
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+    size_t numel() const { size_t n = 1; for (auto s : shape) n *= (size_t)s; return n; }
+};
+
+// weight matrix usable as the B operand of either GEMM path
+struct Linear {
+    DBuf<float> w32;              // [N,K] fp32   (precision fp32)
+    DBuf<__nv_bfloat16> w16;      // [N,K] bf16   (precision bf16)
+    DBuf<float> b;                // [N]
+    int N = 0, K = 0;
+};
+
+struct ConvW {
+    DBuf<float> wt;               // [Cin][K][Cout]
+    DBuf<float> b;                // [Cout]
+    int Cin = 0, Cout = 0, K = 0;
+};
+
+struct Sequence {
+    uint64_t id = 0;
+    std::vector<int32_t> text_ids;
+    int speaker = 0;
+    xtts_sampling sp{};
+    int slot = -1;
+    int n_prompt = 0;
+    std::vector<int> pages;
+    double t_submit = 0, t_first = 0, t_done = 0;
+    // results
+    int status = 0;
+    std::vector<int32_t> tokens;
+    int n_samples = 0;
+    float* wav_host = nullptr;    // pinned
+    size_t wav_cap = 0;
+    DBuf<float> wav_dev;          // kept when d2h_wav == 0
+    std::vector<float> latents;   // filled on fetch request only
+    DBuf<float> lat_dev;          // [n_tokens, H] copy so the slot can be reused
+};
+
+class Engine {
+public:
+    explicit Engine(const xtts_config& c);
+    ~Engine();
+
+    void load_weight(const char* name, const float* data, const int64_t* shape, int ndim);
+    void finalize_weights();
+    void set_speaker(int slot, const float* cond, const float* g);
+    void get_speaker(int slot, float* cond, float* g);
+    void submit(uint64_t id, const int32_t* text, int n_text, int speaker, const xtts_sampling& sp);
+    int poll(xtts_result* out, int timeout_ms);
+    void fetch(uint64_t id, int32_t* tokens, float* wav, float* latents);
+    void set_option(const std::string& k, int64_t v);
+    void get_stats(xtts_stats* s);
+    void sync_idle();
+
+    void vocode_sync(const float* latents, int T, int speaker, float* wav, int* n_out, const char* stage,
+                     float* stage_out, int64_t stage_cap);
+    void gpt_prefill_sync(const int32_t* text, int n_text, int speaker, const int32_t* audio, int n_audio,
+                          float* hidden_out, float* logits_out, float* latents_out);
+    void gpt_teacher_forced_sync(const int32_t* text, int n_text, int speaker, const int32_t* forced, int n,
+                                 const xtts_sampling& sp, float* logits_out, float* latents_out, int32_t* sampled_out);
+    void debug_gemm(int mode, const float* A, const float* W, const float* bias, const float* resid, float* out, int M,
+                    int N, int K, int gelu, int iters, float* ms);
+    void debug_sample(const float* logits, const uint8_t* seen, int B, int V, const xtts_sampling& sp, int step,
+                      int32_t* out);
+
+private:
+    // ---- geometry
+    xtts_config cfg;
+    int H, L, NH, FF, V, Vpad, B, NSLOT, CAP, MAXP, max_pages, SEENW, S;
+    int prefill_rows_cap;
+    bool bf16;
+    cudaStream_t st = nullptr;
+
+    // ---- weights
+    std::map<std::string, HostTensor> raw;
+    bool finalized = false;
+    DBuf<float> text_emb, text_pos, wte, wpe;
+    struct Layer { DBuf<float> ln1w, ln1b, ln2w, ln2b; Linear qkv, o, fc, proj; };
+    std::vector<std::unique_ptr<Layer>> layers;
+    DBuf<float> lnfw, lnfb, fnw, fnb;
+    Linear mel_head;
+    ConvW conv_pre;
+    std::vector<std::unique_ptr<ConvW>> ups;
+    struct RB { std::unique_ptr<ConvW> c1[4], c2[4]; };
+    std::vector<std::unique_ptr<RB>> rbs;
+    DBuf<float> conv_post_w;
+    int post_cin = 0;
+    struct CondLin { DBuf<float> w, b; int rows = 0; };
+    CondLin cond_layer;
+    std::vector<std::unique_ptr<CondLin>> conds;
+    uint64_t weight_bytes = 0;
+
+    // ---- speakers
+    DBuf<float> spk_cond, spk_g, spk_cbias;
+    int cbias_stride = 0;
+    std::vector<int> cbias_off;
+    std::vector<char> spk_valid;
+
+    // ---- slot state (device)
+    DBuf<int> d_last_tok, d_n_gen, d_ctx_len, d_finished, d_tokens, d_sampled, d_forced, d_top_k, d_max_tokens,
+        d_stop, d_seq_seed, d_block_tables, d_active, d_rowidx, d_row_slot, d_row_pos, d_lat_pos;
+    DBuf<unsigned> d_seen;
+    DBuf<float> d_temp, d_top_p, d_pen;
+    DBuf<unsigned long long> d_seed;
+    DBuf<float> d_latents;
+    DBuf<RowDesc> d_rows;
+    DBuf<AttnSeq> d_attnseq;
+    bool use_forced = false;
+    // KV pools, one pair per layer
+    std::vector<std::unique_ptr<DBuf<float>>> k32, v32;
+    std::vector<std::unique_ptr<DBuf<__nv_bfloat16>>> k16, v16;
+    std::vector<int> free_pages;
+    // GPT workspace
+    DBuf<float> wX, wQKV, wLOG;
+    DBuf<float> wXn32, wATT32, wFF32, wY32;
+    DBuf<__nv_bfloat16> wXn16, wATT16, wFF16, wY16;
+    // pinned staging
+    int* h_finished = nullptr;
+    // vocoder workspace
+    DBuf<float> vz, vpre, vb[5], vwav;
+    int voc_max_T = 0;
+    std::vector<int> stage_ch;
+
+    // ---- scheduler
+    std::mutex mu;                      // protects queues + all GPU work issue
+    std::condition_variable cv_work, cv_done;
+    std::deque<std::shared_ptr<Sequence>> pending;
+    std::vector<std::shared_ptr<Sequence>> running;     // index = position in active list
+    std::vector<int> free_slots;
+    std::deque<std::shared_ptr<Sequence>> done_q;
+    std::unordered_map<uint64_t, std::shared_ptr<Sequence>> done_map;
+    std::thread worker;
+    std::atomic<bool> stop{false};
+    int inflight = 0;
+    bool d2h_wav = true;
+    std::vector<std::pair<float*, size_t>> pinned_pool;
+    // stats
+    uint64_t st_decode_steps = 0, st_prefill_rows = 0, st_tokens = 0, st_samples = 0;
+    double st_gpt_ms = 0, st_voc_ms = 0, st_cond_ms = 0;
+    unsigned long long launch_base = 0;
+
+    // ---- helpers
+    const HostTensor& need(const std::string& name) const;
+    void up(DBuf<float>& d, const std::vector<float>& h) { d.alloc(h.size()); d.upload(h.data(), h.size(), st); weight_bytes += h.size() * 4; }
+    void make_linear(Linear& lin, const std::string& wname, const std::string& bname, bool conv1d_layout, int pad_n = 0);
+    void make_conv(ConvW& c, const std::string& prefix, bool transposed, bool has_bias);
+    std::vector<float> folded(const std::string& prefix) const;
+    GptTables tables() const {
+        GptTables t; t.text_emb = text_emb.p; t.text_pos = text_pos.p; t.wte = wte.p; t.wpe = wpe.p;
+        t.spk_cond = spk_cond.p; t.H = H; t.n_cond = cfg.n_cond_latents; return t;
+    }
+    SampleState sample_state() const;
+    void gemm(const void* A, const Linear& lin, const float* resid, void* out, int M, int flags);
+    void layers_forward(int M, bool prefill, int nseq, int max_nq);
+    void head_and_sample(int M, const int* row_index, const int* slots_dev, const int* lat_pos, int advance_ctx, bool do_sample);
+    void init_slot(Sequence& s, const int32_t* forced, int n_forced);
+    void release_slot(Sequence& s);
+    int build_prefill(const std::vector<Sequence*>& seqs, const std::vector<std::vector<int32_t>>& audio,
+                      std::vector<int>& last_rows, int& max_nq);
+    void prefill(const std::vector<Sequence*>& seqs);
+    void decode_step(const std::vector<int>& active);
+    void run_vocoder(const float* lat_dev, int T, int speaker, float* wav_dev_out, int* n_out, const char* stage,
+                     float* stage_out, int64_t stage_cap);
+    void finish_sequence(std::shared_ptr<Sequence> s);
+    float* pinned_get(size_t n, size_t* cap);
+    void pinned_put(float* p, size_t cap);
+    void loop();
+    void require_finalized() const { if (!finalized) throw std::runtime_error("weights not finalized: call xtts_finalize_weights first"); }
+};
+
+// ================================================================================================
+// construction
+// ================================================================================================
+Engine::Engine(const xtts_config& c) : cfg(c) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        throw std::runtime_error("libxtts_b200: no CUDA device visible — this library has no CPU fallback");
+    }
+    if (c.device < 0 || c.device >= ndev) throw std::runtime_error("invalid CUDA device ordinal");
+    CUDA_CHECK(cudaSetDevice(c.device));
+    cudaDeviceProp prop{};
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major != 10) {
+        throw std::runtime_error(std::string("libxtts_b200 is built for sm_100a only; found ") + prop.name + " (sm_" +
+                                 std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    }
+    H = c.hidden; L = c.layers; NH = c.heads; FF = c.ff; V = c.n_audio_tokens;
+    if (H != NH * kHeadDim) throw std::runtime_error("hidden must equal heads * 64");
+    if (H % 64 != 0 || FF % 64 != 0) throw std::runtime_error("hidden and ff must be multiples of 64");
+    if (V > 2048) throw std::runtime_error("n_audio_tokens > 2048 unsupported");
+    Vpad = ceil_div(V, 32) * 32;
+    B = c.max_batch; NSLOT = B + 1;     // last slot is reserved for the synchronous debug entry points
+    CAP = c.max_audio_tokens;
+    MAXP = c.n_cond_latents + (c.max_text_tokens + 2) + 1;
+    max_pages = ceil_div(MAXP + CAP, kPageTokens);
+    SEENW = ceil_div(V, 32);
+    S = std::max(1, c.max_speakers);
+    bf16 = c.precision == XTTS_PRECISION_BF16;
+    if (bf16) { std::string err; if (!gemm_tc_init(&err)) throw std::runtime_error(err); }
+    CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+
+    // speakers
+    spk_cond.alloc((size_t)S * c.n_cond_latents * H);
+    spk_g.alloc((size_t)S * c.d_vector);
+    spk_valid.assign(S, 0);
+    cbias_off.clear();
+    int off = 0;
+    cbias_off.push_back(off); off += c.voc_init_ch;
+    stage_ch.clear();
+    for (int i = 0; i < c.voc_n_up; ++i) {
+        const int ch = c.voc_init_ch >> (i + 1);
+        stage_ch.push_back(ch);
+        cbias_off.push_back(off); off += ch;
+    }
+    cbias_stride = off;
+    spk_cbias.alloc((size_t)S * cbias_stride);
+
+    // slot state
+    d_last_tok.alloc(NSLOT); d_n_gen.alloc(NSLOT); d_ctx_len.alloc(NSLOT); d_finished.alloc(NSLOT);
+    d_tokens.alloc((size_t)NSLOT * CAP); d_sampled.alloc((size_t)NSLOT * CAP); d_forced.alloc((size_t)NSLOT * CAP);
+    d_top_k.alloc(NSLOT); d_max_tokens.alloc(NSLOT); d_stop.alloc(NSLOT); d_seq_seed.alloc(NSLOT);
+    d_temp.alloc(NSLOT); d_top_p.alloc(NSLOT); d_pen.alloc(NSLOT); d_seed.alloc(NSLOT);
+    d_seen.alloc((size_t)NSLOT * SEENW);
+    d_block_tables.alloc((size_t)NSLOT * max_pages);
+    d_active.alloc(NSLOT);
+    d_latents.alloc((size_t)NSLOT * CAP * H);
+    d_finished.zero(st); d_n_gen.zero(st); d_ctx_len.zero(st); d_last_tok.zero(st);
+    CUDA_CHECK(cudaMallocHost(&h_finished, NSLOT * sizeof(int)));
+
+    // prefill row budget: whole prompts of up to 8 sequences at the maximum prompt length, >= one debug pass
+    prefill_rows_cap = std::max(8 * MAXP, MAXP + CAP);
+    d_rows.alloc(prefill_rows_cap); d_row_slot.alloc(prefill_rows_cap); d_row_pos.alloc(prefill_rows_cap);
+    d_rowidx.alloc(prefill_rows_cap); d_lat_pos.alloc(prefill_rows_cap);
+    d_attnseq.alloc(NSLOT);
+    const size_t Mmax = (size_t)std::max(prefill_rows_cap, NSLOT);
+    wX.alloc(Mmax * H); wQKV.alloc(Mmax * 3 * H); wLOG.alloc((size_t)std::max(NSLOT, CAP + 1) * Vpad);
+    if (bf16) { wXn16.alloc(Mmax * H); wATT16.alloc(Mmax * H); wFF16.alloc(Mmax * FF); wY16.alloc((size_t)std::max(NSLOT, CAP + 1) * H); }
+    else { wXn32.alloc(Mmax * H); wATT32.alloc(Mmax * H); wFF32.alloc(Mmax * FF); wY32.alloc((size_t)std::max(NSLOT, CAP + 1) * H); }
+
+    // KV pools
+    const int total_pages = NSLOT * max_pages;
+    const size_t page_elems = (size_t)NH * kPageTokens * kHeadDim;
+    for (int l = 0; l < L; ++l) {
+        if (bf16) {
+            k16.emplace_back(new DBuf<__nv_bfloat16>()); v16.emplace_back(new DBuf<__nv_bfloat16>());
+            k16.back()->alloc(total_pages * page_elems); v16.back()->alloc(total_pages * page_elems);
+        } else {
+            k32.emplace_back(new DBuf<float>()); v32.emplace_back(new DBuf<float>());
+            k32.back()->alloc(total_pages * page_elems); v32.back()->alloc(total_pages * page_elems);
+        }
+    }
+    for (int p = total_pages - 1; p >= 0; --p) free_pages.push_back(p);
+    for (int s = B - 1; s >= 0; --s) free_slots.push_back(s);
+
+    // vocoder workspace for the longest chunk
+    voc_max_T = CAP;
+    {
+        const int T1 = (int)std::floor((double)voc_max_T * ((double)c.code_stride / (double)c.output_hop_length));
+        const int Tz = (int)std::floor((double)T1 * ((double)c.output_sample_rate / (double)c.input_sample_rate));
+        vz.alloc((size_t)c.voc_in_dim * Tz);
+        vpre.alloc((size_t)c.voc_init_ch * Tz);
+        size_t mx = 0; int len = Tz;
+        for (int i = 0; i < c.voc_n_up; ++i) { len *= c.voc_up_rates[i]; mx = std::max(mx, (size_t)stage_ch[i] * len); }
+        for (auto& b : vb) b.alloc(mx);
+        vwav.alloc(len);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    launch_base = g_launch_count;
+    worker = std::thread([this] { this->loop(); });
+}
+
+Engine::~Engine() {
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        stop = true;
+    }
+    cv_work.notify_all();
+    if (worker.joinable()) worker.join();
+    cudaSetDevice(cfg.device);
+    cudaStreamSynchronize(st);
+    for (auto& pr : pinned_pool) cudaFreeHost(pr.first);
+    for (auto& kv : done_map) if (kv.second->wav_host) cudaFreeHost(kv.second->wav_host);
+    if (h_finished) cudaFreeHost(h_finished);
+    if (st) cudaStreamDestroy(st);
+}
+
+// ================================================================================================
+// weights
+// ================================================================================================
+void Engine::load_weight(const char* name, const float* data, const int64_t* shape, int ndim) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (finalized) throw std::runtime_error("weights already finalized");
+    HostTensor t;
+    t.shape.assign(shape, shape + ndim);
+    const size_t n = t.numel();
+    t.data.assign(data, data + n);
+    raw[name] = std::move(t);
+}
+
+const HostTensor& Engine::need(const std::string& name) const {
+    auto it = raw.find(name);
+    if (it == raw.end()) throw std::runtime_error("missing weight: " + name);
+    return it->second;
+}
+
+// [K,N] (HF Conv1D, in x out) or [N,K] (nn.Linear) -> device [Npad,K] in the engine precision
+void Engine::make_linear(Linear& lin, const std::string& wname, const std::string& bname, bool conv1d_layout, int pad_n) {
+    const HostTensor& w = need(wname);
+    if (w.shape.size() != 2) throw std::runtime_error("expected 2-D weight: " + wname);
+    const int d0 = (int)w.shape[0], d1 = (int)w.shape[1];
+    const int N = conv1d_layout ? d1 : d0, K = conv1d_layout ? d0 : d1;
+    const int Np = pad_n > 0 ? pad_n : N;
+    std::vector<float> t((size_t)Np * K, 0.f);
+    if (conv1d_layout) {
+        const int BL = 32;                                  // blocked transpose (vllm_mm_gpt.py:723-725)
+        for (int k0 = 0; k0 < K; k0 += BL)
+            for (int n0 = 0; n0 < N; n0 += BL)
+                for (int k = k0; k < std::min(K, k0 + BL); ++k)
+                    for (int n = n0; n < std::min(N, n0 + BL); ++n) t[(size_t)n * K + k] = w.data[(size_t)k * N + n];
+    } else {
+        std::memcpy(t.data(), w.data.data(), (size_t)N * K * sizeof(float));
+    }
+    lin.N = Np; lin.K = K;
+    std::vector<float> bias(Np, 0.f);
+    if (!bname.empty()) { const HostTensor& b = need(bname); std::copy(b.data.begin(), b.data.end(), bias.begin()); }
+    lin.b.alloc(Np); lin.b.upload(bias.data(), Np, st);
+    lin.w32.alloc(t.size()); lin.w32.upload(t.data(), t.size(), st);
+    if (bf16) {
+        lin.w16.alloc(t.size());
+        launch_f32_to_bf16(lin.w32.p, lin.w16.p, t.size(), st);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        lin.w32.release();
+        weight_bytes += t.size() * 2;
+    } else {
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        weight_bytes += t.size() * 4;
+    }
+}
+
+// weight-norm fold (torch parametrizations.weight.original0/1, dim 0) — hifigan_decoder.py:44-73,189-202
+std::vector<float> Engine::folded(const std::string& prefix) const {
+    auto it = raw.find(prefix + ".weight");
+    if (it != raw.end()) return it->second.data;
+    const HostTensor& g = need(prefix + ".parametrizations.weight.original0");
+    const HostTensor& v = need(prefix + ".parametrizations.weight.original1");
+    const size_t d0 = (size_t)v.shape[0];
+    const size_t inner = v.numel() / d0;
+    std::vector<float> w(v.numel());
+    for (size_t i = 0; i < d0; ++i) {
+        double ss = 0;
+        for (size_t j = 0; j < inner; ++j) { const double x = v.data[i * inner + j]; ss += x * x; }
+        const float scale = g.data[i] / (float)std::sqrt(ss);
+        for (size_t j = 0; j < inner; ++j) w[i * inner + j] = v.data[i * inner + j] * scale;
+    }
+    return w;
+}
+
+// Conv1d weight [Cout,Cin,K] or ConvTranspose1d weight [Cin,Cout,K] -> [Cin][K][Cout]
+void Engine::make_conv(ConvW& c, const std::string& prefix, bool transposed, bool has_bias) {
+    const std::vector<float> w = folded(prefix);
+    const HostTensor& ref = raw.count(prefix + ".weight") ? need(prefix + ".weight")
+                                                          : need(prefix + ".parametrizations.weight.original1");
+    const int d0 = (int)ref.shape[0], d1 = (int)ref.shape[1], K = (int)ref.shape[2];
+    const int Cin = transposed ? d0 : d1, Cout = transposed ? d1 : d0;
+    std::vector<float> t((size_t)Cin * K * Cout);
+    for (int ci = 0; ci < Cin; ++ci)
+        for (int co = 0; co < Cout; ++co)
+            for (int j = 0; j < K; ++j) {
+                const float x = transposed ? w[((size_t)ci * Cout + co) * K + j] : w[((size_t)co * Cin + ci) * K + j];
+                t[((size_t)ci * K + j) * Cout + co] = x;
+            }
+    c.Cin = Cin; c.Cout = Cout; c.K = K;
+    up(c.wt, t);
+    if (has_bias) up(c.b, need(prefix + ".bias").data);
+}
+
+void Engine::finalize_weights() {
+    std::lock_guard<std::mutex> lk(mu);
+    if (finalized) return;
+    CUDA_CHECK(cudaSetDevice(cfg.device));
+    const auto& c = cfg;
+    // ---- GPT (names: checkpoint_converter.py:230-272)
+    up(text_emb, need("text_embedding.weight").data);
+    up(text_pos, need("text_pos_embedding.emb.weight").data);
+    up(wte, need("gpt.wte.weight").data);
+    up(wpe, need("gpt.wpe.emb.weight").data);
+    if ((int)need("gpt.wpe.emb.weight").shape[0] < c.max_audio_tokens + 1) throw std::runtime_error("wpe table too short");
+    for (int i = 0; i < L; ++i) {
+        const std::string p = "gpt.h." + std::to_string(i) + ".";
+        std::unique_ptr<Layer> ly(new Layer());
+        up(ly->ln1w, need(p + "ln_1.weight").data); up(ly->ln1b, need(p + "ln_1.bias").data);
+        up(ly->ln2w, need(p + "ln_2.weight").data); up(ly->ln2b, need(p + "ln_2.bias").data);
+        make_linear(ly->qkv, p + "attn.c_attn.weight", p + "attn.c_attn.bias", true);
+        make_linear(ly->o, p + "attn.c_proj.weight", p + "attn.c_proj.bias", true);
+        make_linear(ly->fc, p + "mlp.c_fc.weight", p + "mlp.c_fc.bias", true);
+        make_linear(ly->proj, p + "mlp.c_proj.weight", p + "mlp.c_proj.bias", true);
+        if (ly->qkv.N != 3 * H || ly->qkv.K != H || ly->fc.N != FF || ly->proj.K != FF) throw std::runtime_error("GPT weight shape mismatch at layer " + std::to_string(i));
+        layers.push_back(std::move(ly));
+        // free host copies early (1.5 GB for the full model)
+        for (const char* nm : {"attn.c_attn.weight", "attn.c_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight"}) raw.erase(p + nm);
+    }
+    up(lnfw, need("gpt.ln_f.weight").data); up(lnfb, need("gpt.ln_f.bias").data);
+    up(fnw, need("final_norm.weight").data); up(fnb, need("final_norm.bias").data);
+    make_linear(mel_head, "mel_head.weight", "mel_head.bias", false, Vpad);
+    // ---- vocoder (names: XTTSv2Engine.state_dict(), hifigan_decoder.*)
+    const std::string w = "hifigan_decoder.waveform_decoder.";
+    make_conv(conv_pre, w + "conv_pre", false, true);
+    {
+        const HostTensor& cw = need(w + "cond_layer.weight");
+        cond_layer.rows = (int)cw.shape[0];
+        up(cond_layer.w, cw.data); up(cond_layer.b, need(w + "cond_layer.bias").data);
+    }
+    const int nk = c.voc_n_rb;
+    for (int i = 0; i < c.voc_n_up; ++i) {
+        std::unique_ptr<ConvW> u(new ConvW());
+        make_conv(*u, w + "ups." + std::to_string(i), true, true);
+        ups.push_back(std::move(u));
+        std::unique_ptr<CondLin> cl(new CondLin());
+        const HostTensor& cw = need(w + "conds." + std::to_string(i) + ".weight");
+        cl->rows = (int)cw.shape[0];
+        up(cl->w, cw.data); up(cl->b, need(w + "conds." + std::to_string(i) + ".bias").data);
+        conds.push_back(std::move(cl));
+        for (int j = 0; j < nk; ++j) {
+            std::unique_ptr<RB> rb(new RB());
+            const std::string rp = w + "resblocks." + std::to_string(i * nk + j) + ".";
+            for (int t = 0; t < 3; ++t) {
+                rb->c1[t].reset(new ConvW()); rb->c2[t].reset(new ConvW());
+                make_conv(*rb->c1[t], rp + "convs1." + std::to_string(t), false, true);
+                make_conv(*rb->c2[t], rp + "convs2." + std::to_string(t), false, true);
+            }
+            rbs.push_back(std::move(rb));
+        }
+    }
+    {
+        const HostTensor& pw = need(w + "conv_post.weight");
+        post_cin = (int)pw.shape[1];
+        up(conv_post_w, pw.data);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    // keep only what xtts_condition needs later; drop the big host copies
+    for (auto it = raw.begin(); it != raw.end();) {
+        const std::string& k = it->first;
+        const bool keep = k.rfind("conditioning_", 0) == 0 || k.rfind("hifigan_decoder.speaker_encoder", 0) == 0 || k == "mel_stats";
+        if (!keep) it = raw.erase(it); else ++it;
+    }
+    finalized = true;
+}
+
+// ================================================================================================
+// speakers
+// ================================================================================================
+void Engine::set_speaker(int slot, const float* cond, const float* g) {
+    std::lock_guard<std::mutex> lk(mu);
+    require_finalized();
+    if (slot < 0 || slot >= S) throw std::runtime_error("speaker slot out of range");
+    CUDA_CHECK(cudaSetDevice(cfg.device));
+    const size_t nc = (size_t)cfg.n_cond_latents * H;
+    spk_cond.upload(cond, nc, st, (size_t)slot * nc);
+    spk_g.upload(g, cfg.d_vector, st, (size_t)slot * cfg.d_vector);
+    // speaker-conditioning biases: cond_layer(g), conds[i](g)  (hifigan_decoder.py:244-251)
+    const float* gd = spk_g.p + (size_t)slot * cfg.d_vector;
+    float* cb = spk_cbias.p + (size_t)slot * cbias_stride;
+    launch_gemv(cond_layer.w.p, cond_layer.b.p, gd, cb + cbias_off[0], cond_layer.rows, cfg.d_vector, st);
+    for (int i = 0; i < cfg.voc_n_up; ++i)
+        launch_gemv(conds[i]->w.p, conds[i]->b.p, gd, cb + cbias_off[i + 1], conds[i]->rows, cfg.d_vector, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    spk_valid[slot] = 1;
+}
+
+void Engine::get_speaker(int slot, float* cond, float* g) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (slot < 0 || slot >= S || !spk_valid[slot]) throw std::runtime_error("speaker slot not set");
+    CUDA_CHECK(cudaSetDevice(cfg.device));
+    const size_t nc = (size_t)cfg.n_cond_latents * H;
+    if (cond) spk_cond.download(cond, nc, st, (size_t)slot * nc);
+    if (g) spk_g.download(g, cfg.d_vector, st, (size_t)slot * cfg.d_vector);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+// ================================================================================================
+// GPT forward
+// ================================================================================================
+SampleState Engine::sample_state() const {
+    SampleState s;
+    s.last_tok = d_last_tok.p; s.n_gen = d_n_gen.p; s.ctx_len = d_ctx_len.p; s.finished = d_finished.p;
+    s.tokens = d_tokens.p; s.sampled = d_sampled.p; s.forced = use_forced ? d_forced.p : nullptr;
+    s.seen = d_seen.p; s.temperature = d_temp.p; s.top_p = d_top_p.p; s.top_k = d_top_k.p; s.penalty = d_pen.p;
+    s.max_tokens = d_max_tokens.p; s.stop_token = d_stop.p; s.seed = d_seed.p; s.seq_seed = d_seq_seed.p;
+    s.tokens_cap = CAP; s.seen_words = SEENW;
+    return s;
+}
+
+void Engine::gemm(const void* A, const Linear& lin, const float* resid, void* out, int M, int flags) {
+    if (bf16)
+        launch_gemm_bf16_tc(reinterpret_cast<const __nv_bfloat16*>(A), lin.w16.p, lin.b.p, resid, out, M, lin.N, lin.K, flags, st);
+    else
+        launch_gemm_f32(reinterpret_cast<const float*>(A), lin.w32.p, lin.b.p, resid, reinterpret_cast<float*>(out), M, lin.N, lin.K,
+                        flags & ~GEMM_OUT_BF16, st);
+}
+
+// X [M,H] -> X after all blocks.  prefill: causal attention inside each sequence of d_attnseq, KV written at
+// d_row_pos; decode: one row per active slot, KV appended at ctx_len, attention over the paged cache.
+void Engine::layers_forward(int M, bool prefill, int nseq, int max_nq) {
+    void* Xn = bf16 ? (void*)wXn16.p : (void*)wXn32.p;
+    void* ATT = bf16 ? (void*)wATT16.p : (void*)wATT32.p;
+    void* FFb = bf16 ? (void*)wFF16.p : (void*)wFF32.p;
+    const int oflag = bf16 ? GEMM_OUT_BF16 : 0;
+    for (int l = 0; l < L; ++l) {
+        Layer& ly = *layers[l];
+        if (bf16) launch_layernorm<__nv_bfloat16>(wX.p, ly.ln1w.p, ly.ln1b.p, wXn16.p, M, H, cfg.ln_eps, st);
+        else launch_layernorm<float>(wX.p, ly.ln1w.p, ly.ln1b.p, wXn32.p, M, H, cfg.ln_eps, st);
+        gemm(Xn, ly.qkv, nullptr, wQKV.p, M, 0);
+        if (prefill) {
+            if (bf16) launch_kv_write<__nv_bfloat16>(wQKV.p, M, d_row_slot.p, d_row_pos.p, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p, NH, st);
+            else launch_kv_write<float>(wQKV.p, M, d_row_slot.p, d_row_pos.p, d_ctx_len.p, d_block_tables.p, max_pages, k32[l]->p, v32[l]->p, NH, st);
+            AttnLayout A;
+            A.q = wQKV.p; A.k = wQKV.p + H; A.v = wQKV.p + 2 * H;
+            A.q_row_stride = 3 * H; A.kv_row_stride = 3 * H; A.q_head_stride = kHeadDim; A.kv_head_stride = kHeadDim;
+            A.heads = NH; A.scale = 0.125f; A.causal = 1;
+            if (bf16) launch_attn_generic<__nv_bfloat16>(A, d_attnseq.p, nseq, max_nq, wATT16.p, H, st);
+            else launch_attn_generic<float>(A, d_attnseq.p, nseq, max_nq, wATT32.p, H, st);
+        } else {
+            if (bf16) {
+                launch_kv_write<__nv_bfloat16>(wQKV.p, M, d_active.p, nullptr, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p, NH, st);
+                launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p, wATT16.p, NH, st);
+            } else {
+                launch_kv_write<float>(wQKV.p, M, d_active.p, nullptr, d_ctx_len.p, d_block_tables.p, max_pages, k32[l]->p, v32[l]->p, NH, st);
+                launch_attn_decode<float, float>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, k32[l]->p, v32[l]->p, wATT32.p, NH, st);
+            }
+        }
+        gemm(ATT, ly.o, wX.p, wX.p, M, GEMM_RESID);
+        if (bf16) launch_layernorm<__nv_bfloat16>(wX.p, ly.ln2w.p, ly.ln2b.p, wXn16.p, M, H, cfg.ln_eps, st);
+        else launch_layernorm<float>(wX.p, ly.ln2w.p, ly.ln2b.p, wXn32.p, M, H, cfg.ln_eps, st);
+        gemm(Xn, ly.fc, nullptr, FFb, M, GEMM_GELU | oflag);
+        gemm(FFb, ly.proj, wX.p, wX.p, M, GEMM_RESID);
+    }
+}
+
+// rows row_index[0..M) of X -> Y -> logits (wLOG[i]) ; latents captured ; optionally sample
+void Engine::head_and_sample(int M, const int* row_index, const int* slots_dev, const int* lat_pos, int advance_ctx, bool do_sample) {
+    if (bf16) launch_head_norms<__nv_bfloat16>(wX.p, row_index, lnfw.p, lnfb.p, fnw.p, fnb.p, wY16.p, d_latents.p, slots_dev, lat_pos, d_n_gen.p, CAP, M, H, cfg.ln_eps, st);
+    else launch_head_norms<float>(wX.p, row_index, lnfw.p, lnfb.p, fnw.p, fnb.p, wY32.p, d_latents.p, slots_dev, lat_pos, d_n_gen.p, CAP, M, H, cfg.ln_eps, st);
+    gemm(bf16 ? (void*)wY16.p : (void*)wY32.p, mel_head, nullptr, wLOG.p, M, 0);
+    if (do_sample) launch_sample(wLOG.p, Vpad, slots_dev, M, V, sample_state(), advance_ctx, st);
+}
+
+void Engine::init_slot(Sequence& s, const int32_t* forced, int n_forced) {
+    const int slot = s.slot;
+    const int n_text = (int)s.text_ids.size();
+    s.n_prompt = cfg.n_cond_latents + n_text + 1;
+    const int max_tok = std::min<int>(s.sp.max_tokens > 0 ? s.sp.max_tokens : CAP, CAP);
+    const int need_pages = ceil_div(s.n_prompt + max_tok, kPageTokens);
+    if ((int)free_pages.size() < need_pages) throw std::runtime_error("out of KV pages");
+    s.pages.clear();
+    std::vector<int> bt(max_pages, 0);
+    for (int i = 0; i < need_pages; ++i) { bt[i] = free_pages.back(); free_pages.pop_back(); s.pages.push_back(bt[i]); }
+    d_block_tables.upload(bt.data(), max_pages, st, (size_t)slot * max_pages);
+    const int zero = 0, ctx = s.n_prompt;
+    d_n_gen.upload(&zero, 1, st, slot); d_finished.upload(&zero, 1, st, slot); d_ctx_len.upload(&ctx, 1, st, slot);
+    d_last_tok.upload(&cfg.start_audio_token, 1, st, slot);
+    const int tk = s.sp.top_k, stopt = s.sp.stop_token, ss = s.sp.seq_seed;
+    const float T = s.sp.temperature, tp = s.sp.top_p, pen = s.sp.repetition_penalty;
+    const unsigned long long seed = s.sp.seed;
+    d_top_k.upload(&tk, 1, st, slot); d_max_tokens.upload(&max_tok, 1, st, slot); d_stop.upload(&stopt, 1, st, slot);
+    d_seq_seed.upload(&ss, 1, st, slot); d_temp.upload(&T, 1, st, slot); d_top_p.upload(&tp, 1, st, slot);
+    d_pen.upload(&pen, 1, st, slot); d_seed.upload(&seed, 1, st, slot);
+    // penalty set seed: prompt ids are [1]*(32+Lt)+[start]  (vllm_mm_gpt.py:325, App. B.7)
+    std::vector<unsigned> seen(SEENW, 0u);
+    seen[1 >> 5] |= 1u << 1;
+    seen[cfg.start_audio_token >> 5] |= 1u << (cfg.start_audio_token & 31);
+    d_seen.upload(seen.data(), SEENW, st, (size_t)slot * SEENW);
+    std::vector<int> f(CAP, -1);
+    if (forced) for (int i = 0; i < std::min(n_forced, CAP); ++i) f[i] = forced[i];
+    d_forced.upload(f.data(), CAP, st, (size_t)slot * CAP);
+    CUDA_CHECK(cudaStreamSynchronize(st));     // host staging vectors go out of scope
+}
+
+void Engine::release_slot(Sequence& s) {
+    for (int p : s.pages) free_pages.push_back(p);
+    s.pages.clear();
+    if (s.slot >= 0 && s.slot < B) free_slots.push_back(s.slot);
+    s.slot = -1;
+}
+
+// builds row descriptors for [prompt ; optional forced audio rows] of each sequence; returns total rows
+int Engine::build_prefill(const std::vector<Sequence*>& seqs, const std::vector<std::vector<int32_t>>& audio,
+                          std::vector<int>& last_rows, int& max_nq) {
+    std::vector<RowDesc> rows;
+    std::vector<int> row_slot, row_pos;
+    std::vector<AttnSeq> as;
+    last_rows.clear();
+    max_nq = 0;
+    for (size_t si = 0; si < seqs.size(); ++si) {
+        Sequence& s = *seqs[si];
+        const int start = (int)rows.size();
+        for (int i = 0; i < cfg.n_cond_latents; ++i) rows.push_back(RowDesc{0, i, 0, s.speaker});
+        for (int i = 0; i < (int)s.text_ids.size(); ++i) {
+            const int id = s.text_ids[i];
+            if (id < 0 || id >= cfg.n_text_tokens) throw std::runtime_error("text token id out of range");
+            rows.push_back(RowDesc{1, id, i, 0});
+        }
+        rows.push_back(RowDesc{2, cfg.start_audio_token, 0, 0});
+        if (si < audio.size())
+            for (int k = 0; k < (int)audio[si].size(); ++k) {
+                const int id = audio[si][k];
+                if (id < 0 || id >= V) throw std::runtime_error("audio token id out of range");
+                rows.push_back(RowDesc{2, id, k + 1, 0});
+            }
+        const int n = (int)rows.size() - start;
+        for (int i = 0; i < n; ++i) { row_slot.push_back(s.slot); row_pos.push_back(i); }
+        as.push_back(AttnSeq{start, n, start, n});
+        last_rows.push_back(start + n - 1);
+        max_nq = std::max(max_nq, n);
+    }
+    const int M = (int)rows.size();
+    if (M > prefill_rows_cap) throw std::runtime_error("prefill batch exceeds row budget");
+    d_rows.upload(rows.data(), M, st); d_row_slot.upload(row_slot.data(), M, st); d_row_pos.upload(row_pos.data(), M, st);
+    d_attnseq.upload(as.data(), as.size(), st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    return M;
+}
+
+void Engine::prefill(const std::vector<Sequence*>& seqs) {
+    std::vector<int> last_rows; int max_nq = 0;
+    const int M = build_prefill(seqs, {}, last_rows, max_nq);
+    launch_build_rows(d_rows.p, M, tables(), wX.p, st);
+    layers_forward(M, true, (int)seqs.size(), max_nq);
+    std::vector<int> slots;
+    for (auto* s : seqs) slots.push_back(s->slot);
+    d_rowidx.upload(last_rows.data(), last_rows.size(), st);
+    d_active.upload(slots.data(), slots.size(), st);
+    head_and_sample((int)seqs.size(), d_rowidx.p, d_active.p, nullptr, 0, true);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    st_prefill_rows += M;
+    const double t = now_s();
+    for (auto* s : seqs) s->t_first = t;
+}
+
+void Engine::decode_step(const std::vector<int>& active) {
+    const int M = (int)active.size();
+    d_active.upload(active.data(), M, st);
+    launch_build_decode_rows(d_active.p, M, d_last_tok.p, d_n_gen.p, tables(), wX.p, st);
+    layers_forward(M, false, 0, 0);
+    head_and_sample(M, nullptr, d_active.p, nullptr, 1, true);
+    ++st_decode_steps;
+}
+
+// ================================================================================================
+// vocoder driver  (HifiDecoder.forward, hifigan_decoder.py:776-802 + HifiganGenerator.forward :228-260)
+// ================================================================================================
+void Engine::run_vocoder(const float* lat_dev, int T, int speaker, float* wav_dev_out, int* n_out, const char* stage,
+                         float* stage_out, int64_t stage_cap) {
+    const auto& c = cfg;
+    if (T <= 0 || T > voc_max_T) throw std::runtime_error("vocoder: latent count out of range");
+    if (speaker < 0 || speaker >= S || !spk_valid[speaker]) throw std::runtime_error("vocoder: speaker slot not set");
+    const double s1 = (double)c.code_stride / (double)c.output_hop_length;
+    const double s2 = (double)c.output_sample_rate / (double)c.input_sample_rate;
+    const int T1 = (int)std::floor((double)T * s1);
+    const bool resample = c.output_sample_rate != c.input_sample_rate;
+    const int Tz = resample ? (int)std::floor((double)T1 * s2) : T1;
+    const float* cb = spk_cbias.p + (size_t)speaker * cbias_stride;
+    auto dump = [&](const char* name, const float* p, size_t n) {
+        if (stage && stage_out && std::strcmp(stage, name) == 0) {
+            const size_t m = std::min<size_t>(n, (size_t)stage_cap);
+            CUDA_CHECK(cudaMemcpyAsync(stage_out, p, m * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+    };
+    launch_interp(lat_dev, vz.p, T, c.voc_in_dim, T1, Tz, s1, resample ? s2 : 1.0, st);
+    dump("z", vz.p, (size_t)c.voc_in_dim * Tz);
+    launch_conv1d(vz.p, conv_pre.wt.p, conv_pre.b.p, cb + cbias_off[0], nullptr, vpre.p, conv_pre.Cin, conv_pre.Cout, Tz,
+                  conv_pre.K, 1, 1.0f, 1.0f, CONV_STORE, st);
+    dump("pre", vpre.p, (size_t)c.voc_init_ch * Tz);
+    const float* cur = vpre.p;
+    float in_scale = 1.0f;
+    int len = Tz;
+    const int nk = c.voc_n_rb;
+    float* X = vb[0].p; float* TMP = vb[1].p; float* R1 = vb[2].p; float* R2 = vb[3].p; float* ZS = vb[4].p;
+    for (int i = 0; i < c.voc_n_up; ++i) {
+        const ConvW& u = *ups[i];
+        launch_conv_transpose1d(cur, u.wt.p, u.b.p, cb + cbias_off[i + 1], X, u.Cin, u.Cout, len, u.K, c.voc_up_rates[i],
+                                in_scale, 0.1f, st);
+        len *= c.voc_up_rates[i];
+        const int C = u.Cout;
+        { char nm[16]; snprintf(nm, sizeof(nm), "up%d", i); dump(nm, X, (size_t)C * len); }
+        for (int j = 0; j < nk; ++j) {
+            const RB& rb = *rbs[i * nk + j];
+            const float* r_in = X;
+            for (int t = 0; t < 3; ++t) {
+                const ConvW& a = *rb.c1[t];
+                const ConvW& b = *rb.c2[t];
+                launch_conv1d(r_in, a.wt.p, a.b.p, nullptr, nullptr, TMP, C, C, len, a.K, c.voc_rb_dilations[t], 1.0f, 0.1f,
+                              CONV_STORE, st);
+                if (t < 2) {
+                    float* r_out = (t == 0) ? R1 : R2;
+                    launch_conv1d(TMP, b.wt.p, b.b.p, nullptr, r_in, r_out, C, C, len, b.K, 1, 1.0f, 0.1f, CONV_STORE, st);
+                    r_in = r_out;
+                } else {
+                    launch_conv1d(TMP, b.wt.p, b.b.p, nullptr, r_in, ZS, C, C, len, b.K, 1, 1.0f, 0.1f,
+                                  j == 0 ? CONV_STORE : CONV_ACCUM, st);
+                }
+            }
+        }
+        { char nm[16]; snprintf(nm, sizeof(nm), "mrf%d", i); dump(nm, ZS, (size_t)C * len); }   // un-normalised sum
+        // next stage reads the MRF sum scaled by 1/nk; its ConvT writes X (dead by now), and ZS is only
+        // overwritten after that ConvT has consumed it (stream order)
+        cur = ZS;
+        in_scale = 1.0f / (float)nk;
+    }
+    launch_conv_post(cur, conv_post_w.p, wav_dev_out, post_cin, len, 7, in_scale, 0.01f, st);
+    *n_out = len;
+}
+
+// ================================================================================================
+// scheduler
+// ================================================================================================
+float* Engine::pinned_get(size_t n, size_t* cap) {
+    for (size_t i = 0; i < pinned_pool.size(); ++i)
+        if (pinned_pool[i].second >= n) {
+            float* p = pinned_pool[i].first; *cap = pinned_pool[i].second;
+            pinned_pool.erase(pinned_pool.begin() + i);
+            return p;
+        }
+    float* p = nullptr;
+    CUDA_CHECK(cudaMallocHost(&p, n * sizeof(float)));
+    *cap = n;
+    return p;
+}
+void Engine::pinned_put(float* p, size_t cap) { pinned_pool.emplace_back(p, cap); }
+
+void Engine::submit(uint64_t id, const int32_t* text, int n_text, int speaker, const xtts_sampling& sp) {
+    if (n_text <= 0 || n_text > cfg.max_text_tokens + 2) throw std::runtime_error("n_text out of range (1..max_text_tokens+2)");
+    if (speaker < 0 || speaker >= S) throw std::runtime_error("speaker slot out of range");
+    std::shared_ptr<Sequence> s(new Sequence());
+    s->id = id; s->text_ids.assign(text, text + n_text); s->speaker = speaker; s->sp = sp; s->t_submit = now_s();
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        require_finalized();
+        if (!spk_valid[speaker]) throw std::runtime_error("speaker slot not set");
+        pending.push_back(s);
+        ++inflight;
+    }
+    cv_work.notify_all();
+}
+
+void Engine::finish_sequence(std::shared_ptr<Sequence> s) {
+    // tokens
+    int n = 0;
+    d_n_gen.download(&n, 1, st, s->slot);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    n = std::min(n, CAP);
+    s->tokens.resize(n);
+    d_tokens.download(s->tokens.data(), n, st, (size_t)s->slot * CAP);
+    // latents copy (device) so the slot can be recycled immediately
+    s->lat_dev.alloc((size_t)n * H);
+    CUDA_CHECK(cudaMemcpyAsync(s->lat_dev.p, d_latents.p + (size_t)s->slot * CAP * H, (size_t)n * H * sizeof(float),
+                               cudaMemcpyDeviceToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    st_tokens += n;
+    if (s->sp.vocode) {
+        const double t0 = now_s();
+        int ns = 0;
+        run_vocoder(s->lat_dev.p, n, s->speaker, vwav.p, &ns, nullptr, nullptr, 0);
+        s->n_samples = ns;
+        if (d2h_wav) {
+            s->wav_host = pinned_get(ns, &s->wav_cap);
+            CUDA_CHECK(cudaMemcpyAsync(s->wav_host, vwav.p, (size_t)ns * sizeof(float), cudaMemcpyDeviceToHost, st));
+        } else {
+            s->wav_dev.alloc(ns);
+            CUDA_CHECK(cudaMemcpyAsync(s->wav_dev.p, vwav.p, (size_t)ns * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        st_voc_ms += (now_s() - t0) * 1e3;
+        st_samples += ns;
+    }
+    s->t_done = now_s();
+    release_slot(*s);
+    done_q.push_back(s);
+    done_map[s->id] = s;
+    --inflight;
+}
+
+void Engine::loop() {
+    cudaSetDevice(cfg.device);
+    std::unique_lock<std::mutex> lk(mu);
+    while (true) {
+        cv_work.wait(lk, [&] { return stop.load() || !pending.empty() || !running.empty(); });
+        if (stop.load()) break;
+        try {
+            // ---- admission (continuous batching): fill free slots, whole prompts, within the row budget
+            std::vector<Sequence*> fresh;
+            std::vector<std::shared_ptr<Sequence>> fresh_sp;
+            int rows = 0;
+            while (!pending.empty() && !free_slots.empty()) {
+                auto s = pending.front();
+                const int p = cfg.n_cond_latents + (int)s->text_ids.size() + 1;
+                if (!fresh.empty() && rows + p > prefill_rows_cap) break;
+                pending.pop_front();
+                s->slot = free_slots.back(); free_slots.pop_back();
+                try {
+                    init_slot(*s, nullptr, 0);
+                } catch (const std::exception& ex) {
+                    s->status = XTTS_ERR_STATE; set_error(ex.what());
+                    release_slot(*s); s->t_done = now_s();
+                    done_q.push_back(s); done_map[s->id] = s; --inflight;
+                    continue;
+                }
+                rows += p;
+                fresh.push_back(s.get()); fresh_sp.push_back(s);
+            }
+            const double t0 = now_s();
+            if (!fresh.empty()) {
+                prefill(fresh);
+                for (auto& s : fresh_sp) running.push_back(s);
+                // a sequence may already be finished after its first token (max_tokens == 1 / instant stop)
+                d_finished.download(h_finished, NSLOT, st);
+                CUDA_CHECK(cudaStreamSynchronize(st));
+            }
+            if (!running.empty()) {
+                std::vector<int> active;
+                for (auto& s : running) if (!h_finished[s->slot]) active.push_back(s->slot);
+                if (!active.empty()) {
+                    decode_step(active);
+                    d_finished.download(h_finished, NSLOT, st);
+                    CUDA_CHECK(cudaStreamSynchronize(st));
+                }
+            }
+            st_gpt_ms += (now_s() - t0) * 1e3;
+            // ---- retire finished sequences: vocode, D2H, completion queue
+            std::vector<std::shared_ptr<Sequence>> keep, fin;
+            for (auto& s : running) (h_finished[s->slot] ? fin : keep).push_back(s);
+            running.swap(keep);
+            for (auto& s : fin) {
+                try { finish_sequence(s); }
+                catch (const std::exception& ex) {
+                    s->status = XTTS_ERR_CUDA; set_error(ex.what());
+                    release_slot(*s); s->t_done = now_s();
+                    done_q.push_back(s); done_map[s->id] = s; --inflight;
+                }
+            }
+            if (!fin.empty()) cv_done.notify_all();
+        } catch (const std::exception& ex) {
+            // a failure inside a batched step fails every sequence that was part of it
+            set_error(ex.what());
+            for (auto& s : running) {
+                s->status = XTTS_ERR_CUDA; s->t_done = now_s();
+                release_slot(*s);
+                done_q.push_back(s); done_map[s->id] = s; --inflight;
+            }
+            running.clear();
+            cv_done.notify_all();
+        }
+        // let submit/poll/fetch in: the wait() above does not release the mutex while work is pending
+        lk.unlock();
+        std::this_thread::yield();
+        lk.lock();
+    }
+}
+
+int Engine::poll(xtts_result* out, int timeout_ms) {
+    std::unique_lock<std::mutex> lk(mu);
+    if (!cv_done.wait_for(lk, std::chrono::milliseconds(std::max(0, timeout_ms)), [&] { return !done_q.empty(); })) return 0;
+    auto s = done_q.front(); done_q.pop_front();
+    out->seq_id = s->id; out->status = s->status; out->n_tokens = (int)s->tokens.size(); out->n_samples = s->n_samples;
+    out->n_prompt_rows = s->n_prompt; out->t_submit = s->t_submit; out->t_first_token = s->t_first; out->t_done = s->t_done;
+    return 1;
+}
+
+void Engine::fetch(uint64_t id, int32_t* tokens, float* wav, float* latents) {
+    std::shared_ptr<Sequence> s;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = done_map.find(id);
+        if (it == done_map.end()) throw std::runtime_error("fetch: unknown or unfinished sequence id");
+        s = it->second;
+        done_map.erase(it);
+        for (auto q = done_q.begin(); q != done_q.end(); ++q) if ((*q)->id == id) { done_q.erase(q); break; }
+        if (tokens) std::memcpy(tokens, s->tokens.data(), s->tokens.size() * sizeof(int32_t));
+        if (wav && s->n_samples > 0) {
+            if (s->wav_host) std::memcpy(wav, s->wav_host, (size_t)s->n_samples * sizeof(float));
+            else if (s->wav_dev.p) {
+                CUDA_CHECK(cudaSetDevice(cfg.device));
+                s->wav_dev.download(wav, s->n_samples, st);
+                CUDA_CHECK(cudaStreamSynchronize(st));
+            }
+        }
+        if (latents && s->lat_dev.p) {
+            CUDA_CHECK(cudaSetDevice(cfg.device));
+            s->lat_dev.download(latents, s->lat_dev.n, st);
+            CUDA_CHECK(cudaStreamSynchronize(st));
+        }
+        if (s->wav_host) { pinned_put(s->wav_host, s->wav_cap); s->wav_host = nullptr; }
+    }
+}
+
+void Engine::set_option(const std::string& k, int64_t v) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (k == "d2h_wav") d2h_wav = v != 0;
+    else if (k == "reset_stats") {
+        st_decode_steps = st_prefill_rows = st_tokens = st_samples = 0; st_gpt_ms = st_voc_ms = st_cond_ms = 0;
+        launch_base = g_launch_count;
+    } else throw std::runtime_error("unknown option: " + k);
+}
+
+void Engine::get_stats(xtts_stats* s) {
+    std::lock_guard<std::mutex> lk(mu);
+    s->kernel_launches = g_launch_count - launch_base; s->decode_steps = st_decode_steps; s->prefill_rows = st_prefill_rows;
+    s->tokens_generated = st_tokens; s->samples_generated = st_samples; s->gpt_ms = st_gpt_ms; s->vocoder_ms = st_voc_ms;
+    s->cond_ms = st_cond_ms; s->hbm_bytes_weights = weight_bytes;
+}
+
+void Engine::sync_idle() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv_done.wait(lk, [&] { return inflight == 0; });
+}
+
+// ================================================================================================
+// synchronous single-stage entry points
+// ================================================================================================
+void Engine::vocode_sync(const float* latents, int T, int speaker, float* wav, int* n_out, const char* stage,
+                         float* stage_out, int64_t stage_cap) {
+    std::lock_guard<std::mutex> lk(mu);
+    require_finalized();
+    CUDA_CHECK(cudaSetDevice(cfg.device));
+    DBuf<float> lat; lat.alloc((size_t)T * cfg.voc_in_dim);
+    lat.upload(latents, (size_t)T * cfg.voc_in_dim, st);
+    int ns = 0;
+    run_vocoder(lat.p, T, speaker, vwav.p, &ns, stage, stage_out, stage_cap);
+    if (wav) vwav.download(wav, ns, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (n_out) *n_out = ns;
+}
+
+void Engine::gpt_prefill_sync(const int32_t* text, int n_text, int speaker, const int32_t* audio, int n_audio,
+                              float* hidden_out, float* logits_out, float* latents_out) {
+    std::lock_guard<std::mutex> lk(mu);
+    require_finalized();
+    if (!running.empty()) throw std::runtime_error("debug entry points need an idle engine");
+    CUDA_CHECK(cudaSetDevice(cfg.device));
+    Sequence s; s.text_ids.assign(text, text + n_text); s.speaker = speaker; s.slot = B;
+    s.sp.max_tokens = CAP; s.sp.stop_token = cfg.stop_audio_token; s.sp.repetition_penalty = 1.f; s.sp.temperature = 0.f;
+    init_slot(s, nullptr, 0);
+    const int n = std::max(1, n_audio);
+    std::vector<std::vector<int32_t>> aud(1);
+    if (n_audio > 1) aud[0].assign(audio, audio + n_audio - 1);       // rows fed by t_1..t_{n-1}
+    std::vector<int> last_rows; int max_nq = 0;
+    std::vector<Sequence*> seqs{&s};
+    const int M = build_prefill(seqs, aud, last_rows, max_nq);
+    launch_build_rows(d_rows.p, M, tables(), wX.p, st);
+    layers_forward(M, true, 1, max_nq);
+    if (hidden_out) {
+        // ln_f of every row
+        launch_layernorm<float>(wX.p, lnfw.p, lnfb.p, wQKV.p, M, H, cfg.ln_eps, st);
+        CUDA_CHECK(cudaMemcpyAsync(hidden_out, wQKV.p, (size_t)M * H * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    std::vector<int> ridx(n), slots(n, B), lpos(n);
+    for (int i = 0; i < n; ++i) { ridx[i] = M - n + i; lpos[i] = i; }
+    d_rowidx.upload(ridx.data(), n, st); d_active.upload(slots.data(), 1, st);
+    DBuf<int> dslots; dslots.alloc(n); dslots.upload(slots.data(), n, st);
+    d_lat_pos.upload(lpos.data(), n, st);
+    head_and_sample(n, d_rowidx.p, dslots.p, d_lat_pos.p, 0, false);
+    if (logits_out)
+        CUDA_CHECK(cudaMemcpy2DAsync(logits_out, (size_t)V * sizeof(float), wLOG.p, (size_t)Vpad * sizeof(float),
+                                     (size_t)V * sizeof(float), n, cudaMemcpyDeviceToHost, st));
+    if (latents_out) d_latents.download(latents_out, (size_t)n * H, st, (size_t)B * CAP * H);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    release_slot(s);
+}
+
+void Engine::gpt_teacher_forced_sync(const int32_t* text, int n_text, int speaker, const int32_t* forced, int n,
+                                     const xtts_sampling& sp, float* logits_out, float* latents_out, int32_t* sampled_out) {
+    std::lock_guard<std::mutex> lk(mu);
+    require_finalized();
+    if (!running.empty()) throw std::runtime_error("debug entry points need an idle engine");
+    if (n < 1 || n > CAP) throw std::runtime_error("teacher_forced: n out of range");
+    CUDA_CHECK(cudaSetDevice(cfg.device));
+    Sequence s; s.text_ids.assign(text, text + n_text); s.speaker = speaker; s.slot = B; s.sp = sp;
+    s.sp.max_tokens = n;
+    use_forced = forced != nullptr;
+    try {
+        init_slot(s, forced, n);
+        std::vector<Sequence*> seqs{&s};
+        prefill(seqs);                                   // samples token 1 (forced -> t_1)
+        if (logits_out)
+            CUDA_CHECK(cudaMemcpyAsync(logits_out, wLOG.p, (size_t)V * sizeof(float), cudaMemcpyDeviceToHost, st));
+        std::vector<int> active{B};
+        for (int k = 1; k < n; ++k) {
+            decode_step(active);
+            if (logits_out)
+                CUDA_CHECK(cudaMemcpyAsync(logits_out + (size_t)k * V, wLOG.p, (size_t)V * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        if (latents_out) d_latents.download(latents_out, (size_t)n * H, st, (size_t)B * CAP * H);
+        if (sampled_out) d_sampled.download(sampled_out, n, st, (size_t)B * CAP);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    } catch (...) {
+        use_forced = false; release_slot(s);
+        throw;
+    }
+    use_forced = false;
+    release_slot(s);
+}
+
+void Engine::debug_gemm(int mode, const float* A, const float* W, const float* bias, const float* resid, float* out, int M,
+                        int N, int K, int gelu, int iters, float* ms) {
+    std::lock_guard<std::mutex> lk(mu);
+    CUDA_CHECK(cudaSetDevice(cfg.device));
+    DBuf<float> dA, dW, db, dr, dout;
+    dA.alloc((size_t)M * K); dW.alloc((size_t)N * K); dout.alloc((size_t)M * N);
+    dA.upload(A, (size_t)M * K, st); dW.upload(W, (size_t)N * K, st);
+    if (bias) { db.alloc(N); db.upload(bias, N, st); }
+    if (resid) { dr.alloc((size_t)M * N); dr.upload(resid, (size_t)M * N, st); }
+    const int flags = (gelu ? GEMM_GELU : 0) | (resid ? GEMM_RESID : 0);
+    DBuf<__nv_bfloat16> hA, hW;
+    if (mode == 1) {
+        std::string err;
+        if (!gemm_tc_init(&err)) throw std::runtime_error(err);
+        hA.alloc((size_t)M * K); hW.alloc((size_t)N * K);
+        launch_f32_to_bf16(dA.p, hA.p, (size_t)M * K, st); launch_f32_to_bf16(dW.p, hW.p, (size_t)N * K, st);
+    }
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    auto run = [&] {
+        if (mode == 1) launch_gemm_bf16_tc(hA.p, hW.p, db.p, dr.p, dout.p, M, N, K, flags, st);
+        else launch_gemm_f32(dA.p, dW.p, db.p, dr.p, dout.p, M, N, K, flags, st);
+    };
+    run();
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    dout.download(out, (size_t)M * N, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (iters > 0) {
+        CUDA_CHECK(cudaEventRecord(e0, st));
+        for (int i = 0; i < iters; ++i) run();
+        CUDA_CHECK(cudaEventRecord(e1, st));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float t = 0; CUDA_CHECK(cudaEventElapsedTime(&t, e0, e1));
+        if (ms) *ms = t / iters;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
+void Engine::debug_sample(const float* logits, const uint8_t* seen, int Bn, int Vn, const xtts_sampling& sp, int step,
+                          int32_t* out) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!running.empty()) throw std::runtime_error("debug entry points need an idle engine");
+    if (Bn < 1 || Bn > B || Vn != V) throw std::runtime_error("debug_sample: bad batch or vocabulary size");
+    CUDA_CHECK(cudaSetDevice(cfg.device));
+    std::vector<float> lg((size_t)Bn * Vpad, 0.f);
+    for (int b = 0; b < Bn; ++b) std::memcpy(&lg[(size_t)b * Vpad], logits + (size_t)b * V, V * sizeof(float));
+    wLOG.upload(lg.data(), lg.size(), st);
+    std::vector<int> slots(Bn), ngen(Bn, step), zeros(Bn, 0), tk(Bn, sp.top_k), mt(Bn, CAP), stp(Bn, sp.stop_token), ss(Bn);
+    std::vector<float> T(Bn, sp.temperature), tp(Bn, sp.top_p), pen(Bn, sp.repetition_penalty);
+    std::vector<unsigned long long> seed(Bn, sp.seed);
+    std::vector<unsigned> sb((size_t)Bn * SEENW, 0u);
+    for (int b = 0; b < Bn; ++b) {
+        slots[b] = b; ss[b] = sp.seq_seed + b;
+        if (seen) for (int v = 0; v < V; ++v) if (seen[(size_t)b * V + v]) sb[(size_t)b * SEENW + (v >> 5)] |= 1u << (v & 31);
+    }
+    d_active.upload(slots.data(), Bn, st); d_n_gen.upload(ngen.data(), Bn, st); d_finished.upload(zeros.data(), Bn, st);
+    d_top_k.upload(tk.data(), Bn, st); d_max_tokens.upload(mt.data(), Bn, st); d_stop.upload(stp.data(), Bn, st);
+    d_seq_seed.upload(ss.data(), Bn, st); d_temp.upload(T.data(), Bn, st); d_top_p.upload(tp.data(), Bn, st);
+    d_pen.upload(pen.data(), Bn, st); d_seed.upload(seed.data(), Bn, st); d_seen.upload(sb.data(), sb.size(), st);
+    launch_sample(wLOG.p, Vpad, d_active.p, Bn, V, sample_state(), 0, st);
+    std::vector<int> res(Bn);
+    d_last_tok.download(res.data(), Bn, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int b = 0; b < Bn; ++b) out[b] = res[b];
+    d_n_gen.upload(zeros.data(), Bn, st); d_finished.upload(zeros.data(), Bn, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+}  // namespace xtts
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using xtts::Engine;
+struct xtts_engine { Engine* impl; };
+
+#define XTTS_TRY(body)                                                  \
+    try { body; return XTTS_OK; }                                       \
+    catch (const xtts::CudaError& ex) { xtts::set_error(ex.what()); return XTTS_ERR_CUDA; } \
+    catch (const std::exception& ex) { xtts::set_error(ex.what()); return XTTS_ERR_INVALID; } \
+    catch (...) { xtts::set_error("unknown error"); return XTTS_ERR_INVALID; }
+
+extern "C" {
+
+const char* xtts_last_error(void) {
+    if (!xtts::t_last_error.empty()) return xtts::t_last_error.c_str();
+    std::lock_guard<std::mutex> lk(xtts::g_err_mu);
+    xtts::t_last_error = xtts::g_last_error;
+    return xtts::t_last_error.c_str();
+}
+const char* xtts_version(void) { return "libxtts_b200 0.1 (sm_100a)"; }
+
+int xtts_create(const xtts_config* cfg, xtts_engine** out) {
+    if (!cfg || !out) { xtts::set_error("null argument"); return XTTS_ERR_INVALID; }
+    XTTS_TRY({ Engine* e = new Engine(*cfg); *out = new xtts_engine{e}; })
+}
+int xtts_destroy(xtts_engine* e) {
+    if (!e) return XTTS_OK;
+    XTTS_TRY({ delete e->impl; delete e; })
+}
+int xtts_load_weight(xtts_engine* e, const char* name, const float* data, const int64_t* shape, int32_t ndim) {
+    XTTS_TRY(e->impl->load_weight(name, data, shape, ndim))
+}
+int xtts_finalize_weights(xtts_engine* e) { XTTS_TRY(e->impl->finalize_weights()) }
+int xtts_set_speaker(xtts_engine* e, int32_t slot, const float* cond, const float* g) { XTTS_TRY(e->impl->set_speaker(slot, cond, g)) }
+int xtts_get_speaker(xtts_engine* e, int32_t slot, float* cond, float* g) { XTTS_TRY(e->impl->get_speaker(slot, cond, g)) }
+int xtts_condition(xtts_engine*, int32_t, const float*, int64_t, const float*, int64_t, int32_t, int32_t) {
+    xtts::set_error("xtts_condition: conditioning kernels are not built yet (use xtts_set_speaker)");
+    return XTTS_ERR_STATE;
+}
+int xtts_submit(xtts_engine* e, uint64_t seq_id, const int32_t* text_ids, int32_t n_text, int32_t speaker_slot,
+                const xtts_sampling* sp) {
+    XTTS_TRY(e->impl->submit(seq_id, text_ids, n_text, speaker_slot, *sp))
+}
+int xtts_poll(xtts_engine* e, xtts_result* out, int32_t timeout_ms) {
+    try { return e->impl->poll(out, timeout_ms); }
+    catch (const std::exception& ex) { xtts::set_error(ex.what()); return XTTS_ERR_INVALID; }
+}
+int xtts_fetch(xtts_engine* e, uint64_t seq_id, int32_t* tokens, float* wav, float* latents) {
+    XTTS_TRY(e->impl->fetch(seq_id, tokens, wav, latents))
+}
+int xtts_set_option(xtts_engine* e, const char* key, int64_t value) { XTTS_TRY(e->impl->set_option(key, value)) }
+int xtts_get_stats(xtts_engine* e, xtts_stats* out) { XTTS_TRY(e->impl->get_stats(out)) }
+int xtts_sync(xtts_engine* e) { XTTS_TRY(e->impl->sync_idle()) }
+int xtts_vocode(xtts_engine* e, const float* latents, int32_t T, int32_t speaker_slot, float* wav, int32_t* n_out,
+                const char* stage, float* stage_out, int64_t stage_cap) {
+    XTTS_TRY(e->impl->vocode_sync(latents, T, speaker_slot, wav, n_out, stage, stage_out, stage_cap))
+}
+int xtts_gpt_prefill(xtts_engine* e, const int32_t* text_ids, int32_t n_text, int32_t speaker_slot,
+                     const int32_t* audio_tokens, int32_t n_audio, float* hidden_out, float* logits_out, float* latents_out) {
+    XTTS_TRY(e->impl->gpt_prefill_sync(text_ids, n_text, speaker_slot, audio_tokens, n_audio, hidden_out, logits_out, latents_out))
+}
+int xtts_gpt_teacher_forced(xtts_engine* e, const int32_t* text_ids, int32_t n_text, int32_t speaker_slot,
+                            const int32_t* forced_tokens, int32_t n, const xtts_sampling* sp, float* logits_out,
+                            float* latents_out, int32_t* sampled_out) {
+    XTTS_TRY(e->impl->gpt_teacher_forced_sync(text_ids, n_text, speaker_slot, forced_tokens, n, *sp, logits_out, latents_out, sampled_out))
+}
+int xtts_debug_gemm(xtts_engine* e, int32_t mode, const float* A, const float* W, const float* bias, const float* resid,
+                    float* out, int32_t M, int32_t N, int32_t K, int32_t gelu, int32_t iters, float* ms_per_iter) {
+    XTTS_TRY(e->impl->debug_gemm(mode, A, W, bias, resid, out, M, N, K, gelu, iters, ms_per_iter))
+}
+int xtts_debug_sample(xtts_engine* e, const float* logits, const uint8_t* seen, int32_t B, int32_t V,
+                      const xtts_sampling* sp, int32_t step, int32_t* out_tokens) {
+    XTTS_TRY(e->impl->debug_sample(logits, seen, B, V, *sp, step, out_tokens))
+}
+
+}  // extern "C"

@@ -1,0 +1,609 @@
+// GPT-2 acoustic-model kernels other than the GEMMs: embedding/prompt assembly, LayerNorm, the
+// head norm chain, paged-KV write, prefill (generic) attention, paged decode attention and the fused
+// penalty/temperature/top-k/top-p/sample kernel.
+//
+// Reference call sites these replace:
+//   K1,K2  vllm_mm_gpt.py:768-785,800-833 (wte+wpe gather, conditioning splice)      -> build_rows*
+//   K3,K8  GPT2Block ln_1/ln_2, ln_f :762,848, final_norm :671, XTTSv2.py:687          -> layernorm, head_norms
+//   K5     vLLM paged attention + reshape_and_cache (3rd party)                        -> kv_write, attn_*
+//   K10    hijack.py:49-88 LogitsRepetitionPenalizer                                    -> sample (penalty)
+//   K11    vLLM Sampler                                               -> sample
+#include "kernels.h"
+
+namespace xtts {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// prompt / input row assembly
+// ------------------------------------------------------------------------------------------------
+__global__ void build_rows_kernel(const RowDesc* __restrict__ rows, GptTables t, float* __restrict__ X) {
+    const RowDesc d = rows[blockIdx.x];
+    const int H = t.H;
+    float4* x = reinterpret_cast<float4*>(X + (size_t)blockIdx.x * H);
+    const float4* s1;
+    const float4* s2 = nullptr;
+    if (d.kind == 0) {
+        s1 = reinterpret_cast<const float4*>(t.spk_cond + ((size_t)d.c * t.n_cond + d.a) * H);
+    } else if (d.kind == 1) {
+        s1 = reinterpret_cast<const float4*>(t.text_emb + (size_t)d.a * H);
+        s2 = reinterpret_cast<const float4*>(t.text_pos + (size_t)d.b * H);
+    } else {
+        s1 = reinterpret_cast<const float4*>(t.wte + (size_t)d.a * H);
+        s2 = reinterpret_cast<const float4*>(t.wpe + (size_t)d.b * H);
+    }
+    for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
+        float4 v = s1[i];
+        if (s2) { const float4 u = s2[i]; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+        x[i] = v;
+    }
+}
+
+__global__ void build_decode_rows_kernel(const int* __restrict__ active, const int* __restrict__ last_tok,
+                                         const int* __restrict__ n_gen, GptTables t, float* __restrict__ X) {
+    const int slot = active[blockIdx.x];
+    const int H = t.H;
+    const float4* a = reinterpret_cast<const float4*>(t.wte + (size_t)last_tok[slot] * H);
+    const float4* b = reinterpret_cast<const float4*>(t.wpe + (size_t)n_gen[slot] * H);
+    float4* x = reinterpret_cast<float4*>(X + (size_t)blockIdx.x * H);
+    for (int i = threadIdx.x; i < H / 4; i += blockDim.x) {
+        float4 v = a[i]; const float4 u = b[i];
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        x[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (fp32 statistics, two-pass), one CTA per row
+// ------------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ X, const float* __restrict__ w, const float* __restrict__ b,
+                 TOut* __restrict__ Y, int H, float eps) {
+    __shared__ float red[32];
+    const float* x = X + (size_t)blockIdx.x * H;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) s += x[i];
+    const float mean = block_sum(s, red) / (float)H;
+    float v = 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) { const float d = x[i] - mean; v = fmaf(d, d, v); }
+    const float var = block_sum(v, red) / (float)H;
+    const float rstd = 1.0f / sqrtf(var + eps);
+    TOut* y = Y + (size_t)blockIdx.x * H;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) y[i] = from_f32<TOut>((x[i] - mean) * rstd * w[i] + b[i]);
+}
+
+__device__ __forceinline__ void smem_layernorm(float* buf, const float* __restrict__ w, const float* __restrict__ b,
+                                               int H, float eps, float* red) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) s += buf[i];
+    const float mean = block_sum(s, red) / (float)H;
+    float v = 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) { const float d = buf[i] - mean; v = fmaf(d, d, v); }
+    const float var = block_sum(v, red) / (float)H;
+    const float rstd = 1.0f / sqrtf(var + eps);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) buf[i] = (buf[i] - mean) * rstd * w[i] + b[i];
+    __syncthreads();
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+head_norms_kernel(const float* __restrict__ X, const int* __restrict__ row_index, const float* __restrict__ lnf_w,
+                  const float* __restrict__ lnf_b, const float* __restrict__ fn_w, const float* __restrict__ fn_b,
+                  TOut* __restrict__ Y, float* __restrict__ latents, const int* __restrict__ slots,
+                  const int* __restrict__ lat_pos, const int* __restrict__ n_gen, int lat_rows_per_slot, int H,
+                  float eps) {
+    extern __shared__ float buf[];
+    __shared__ float red[32];
+    const int i = blockIdx.x;
+    const int r = row_index ? row_index[i] : i;
+    const float* x = X + (size_t)r * H;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) buf[c] = x[c];
+    __syncthreads();
+    smem_layernorm(buf, lnf_w, lnf_b, H, eps, red);      // ln_f            (vllm_mm_gpt.py:848)
+    smem_layernorm(buf, fn_w, fn_b, H, eps, red);        // final_norm      (vllm_mm_gpt.py:671)
+    TOut* y = Y + (size_t)i * H;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) y[c] = from_f32<TOut>(buf[c]);
+    __syncthreads();
+    if (latents) {
+        smem_layernorm(buf, fn_w, fn_b, H, eps, red);    // engine final_norm (XTTSv2.py:687) — App. B.2
+        const int slot = slots[i];
+        const int pos = lat_pos ? lat_pos[i] : n_gen[slot];
+        if (pos >= 0 && pos < lat_rows_per_slot) {
+            float* l = latents + ((size_t)slot * lat_rows_per_slot + pos) * H;
+            for (int c = threadIdx.x; c < H; c += blockDim.x) l[c] = buf[c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// paged KV cache write.  grid (rows, heads), 128 threads: 0..63 -> K[d], 64..127 -> V[d]
+// ------------------------------------------------------------------------------------------------
+template <typename TKV>
+__global__ void kv_write_kernel(const float* __restrict__ QKV, const int* __restrict__ row_slot,
+                                const int* __restrict__ row_pos, const int* __restrict__ ctx_len,
+                                const int* __restrict__ block_tables, int max_pages, TKV* __restrict__ kpool,
+                                TKV* __restrict__ vpool, int heads) {
+    constexpr int X = 16 / sizeof(TKV);
+    const int r = blockIdx.x, h = blockIdx.y;
+    const int H = heads * kHeadDim;
+    const int slot = row_slot[r];
+    const int pos = row_pos ? row_pos[r] : ctx_len[slot];
+    const int page = block_tables[(size_t)slot * max_pages + pos / kPageTokens];
+    const int tk = pos % kPageTokens;
+    const int d = threadIdx.x & 63;
+    const size_t pbase = ((size_t)page * heads + h) * (kPageTokens * kHeadDim);
+    if (threadIdx.x < 64) {
+        const float k = QKV[(size_t)r * 3 * H + H + h * kHeadDim + d];
+        kpool[pbase + ((size_t)(d / X) * kPageTokens + tk) * X + (d % X)] = from_f32<TKV>(k);
+    } else {
+        const float v = QKV[(size_t)r * 3 * H + 2 * H + h * kHeadDim + d];
+        vpool[pbase + (size_t)tk * kHeadDim + d] = from_f32<TKV>(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode attention over the paged cache: one CTA per (sequence, head); 4 warps split the pages;
+// lane = token inside a page for QK^T (16-byte coalesced K reads), lane = 2 output dims for PV.
+// HBM-bound: reads 2*ctx*64*sizeof(TKV) bytes per (seq, head).
+// ------------------------------------------------------------------------------------------------
+template <typename TKV> struct KVec;
+template <> struct KVec<float> {
+    static __device__ __forceinline__ float dot(const float* p, const float* q) {
+        const float4 k = *reinterpret_cast<const float4*>(p);
+        return k.x * q[0] + k.y * q[1] + k.z * q[2] + k.w * q[3];
+    }
+    static __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+};
+template <> struct KVec<__nv_bfloat16> {
+    static __device__ __forceinline__ float dot(const __nv_bfloat16* p, const float* q) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(b[i]);
+            s = fmaf(f.x, q[2 * i], s);
+            s = fmaf(f.y, q[2 * i + 1], s);
+        }
+        return s;
+    }
+    static __device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {
+        return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+    }
+};
+
+template <typename TKV, typename TOut>
+__global__ void __launch_bounds__(128)
+attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active, const int* __restrict__ ctx_len,
+                   const int* __restrict__ block_tables, int max_pages, const TKV* __restrict__ kpool,
+                   const TKV* __restrict__ vpool, TOut* __restrict__ out, int heads) {
+    constexpr int X = 16 / sizeof(TKV);
+    constexpr int NCH = kHeadDim / X;
+    __shared__ __align__(16) float qs[kHeadDim];
+    __shared__ float pm[4], pl[4];
+    __shared__ float pacc[4][kHeadDim];
+    const int i = blockIdx.x, h = blockIdx.y;
+    const int H = heads * kHeadDim;
+    const int slot = active[i];
+    const int ctx = ctx_len[slot] + 1;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid < kHeadDim) qs[tid] = QKV[(size_t)i * 3 * H + h * kHeadDim + tid] * 0.125f;   // 64^-0.5
+    __syncthreads();
+    float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
+    const int npages = (ctx + kPageTokens - 1) / kPageTokens;
+    for (int pg = w; pg < npages; pg += 4) {
+        const int page = block_tables[(size_t)slot * max_pages + pg];
+        const size_t pbase = ((size_t)page * heads + h) * (kPageTokens * kHeadDim);
+        const int tok = pg * kPageTokens + lane;
+        const bool valid = tok < ctx;
+        float s = 0.f;
+        const TKV* kb = kpool + pbase + (size_t)lane * X;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) s += KVec<TKV>::dot(kb + (size_t)c * kPageTokens * X, qs + c * X);
+        s = valid ? s : -INFINITY;
+        const float mnew = fmaxf(m, warp_max(s));
+        const float p = valid ? expf(s - mnew) : 0.f;
+        const float corr = (m == -INFINITY) ? 0.f : expf(m - mnew);
+        l = l * corr + warp_sum(p);
+        a0 *= corr; a1 *= corr;
+        const int nvalid = min(kPageTokens, ctx - pg * kPageTokens);
+        const TKV* vb = vpool + pbase + 2 * lane;
+#pragma unroll 8
+        for (int j = 0; j < kPageTokens; ++j) {
+            if (j < nvalid) {
+                const float pj = __shfl_sync(0xffffffffu, p, j);
+                const float2 v = KVec<TKV>::ld2(vb + (size_t)j * kHeadDim);
+                a0 = fmaf(pj, v.x, a0);
+                a1 = fmaf(pj, v.y, a1);
+            }
+        }
+        m = mnew;
+    }
+    if (lane == 0) { pm[w] = m; pl[w] = l; }
+    pacc[w][2 * lane] = a0;
+    pacc[w][2 * lane + 1] = a1;
+    __syncthreads();
+    if (tid < kHeadDim) {
+        const float M = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
+        float L = 0.f, o = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float e = (pm[k] == -INFINITY) ? 0.f : expf(pm[k] - M);
+            L = fmaf(pl[k], e, L);
+            o = fmaf(pacc[k][tid], e, o);
+        }
+        out[(size_t)i * H + h * kHeadDim + tid] = from_f32<TOut>(o / L);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic fp32 attention for prefill-style work (GPT prompt, conditioning encoder, perceiver).
+// CTA = 16 queries of one (sequence, head); K/V tiles of 32 keys staged in shared memory;
+// each warp owns 4 queries; lane = key for QK^T, lane = dims {lane, lane+32} for PV.
+// ------------------------------------------------------------------------------------------------
+constexpr int AQ = 16;
+
+template <typename TOut>
+__global__ void __launch_bounds__(128)
+attn_generic_kernel(AttnLayout L, const AttnSeq* __restrict__ seqs, TOut* __restrict__ out, int out_row_stride) {
+    __shared__ __align__(16) float qT[kHeadDim][AQ];          // [d][query]
+    __shared__ float Ks[32][kHeadDim + 1];
+    __shared__ float Vs[32][kHeadDim];
+    const AttnSeq sq = seqs[blockIdx.z];
+    const int q0 = blockIdx.x * AQ;
+    if (q0 >= sq.nq) return;
+    const int h = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int shift = sq.nk - sq.nq;
+    // stage queries (pre-scaled)
+    for (int e = tid; e < AQ * kHeadDim; e += 128) {
+        const int qi = e / kHeadDim, d = e % kHeadDim;
+        const int gq = q0 + qi;
+        float v = 0.f;
+        if (gq < sq.nq) v = L.q[(size_t)(sq.q_start + gq) * L.q_row_stride + (size_t)h * L.q_head_stride + d] * L.scale;
+        qT[d][qi] = v;
+    }
+    float m[4], l[4], a0[4], a1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; l[i] = 0.f; a0[i] = 0.f; a1[i] = 0.f; }
+    const int q_last = min(q0 + AQ, sq.nq) - 1;
+    const int kmax = L.causal ? min(sq.nk, q_last + shift + 1) : sq.nk;
+    for (int k0 = 0; k0 < kmax; k0 += 32) {
+        __syncthreads();
+        for (int e = tid; e < 32 * kHeadDim; e += 128) {
+            const int j = e / kHeadDim, d = e % kHeadDim;
+            const int gk = k0 + j;
+            float kv = 0.f, vv = 0.f;
+            if (gk < sq.nk) {
+                const size_t off = (size_t)(sq.kv_start + gk) * L.kv_row_stride + (size_t)h * L.kv_head_stride + d;
+                kv = L.k[off];
+                vv = L.v[off];
+            }
+            Ks[j][d] = kv;
+            Vs[j][d] = vv;
+        }
+        __syncthreads();
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 16
+        for (int d = 0; d < kHeadDim; ++d) {
+            const float kd = Ks[lane][d];
+            const float4 q4 = *reinterpret_cast<const float4*>(&qT[d][w * 4]);
+            s[0] = fmaf(q4.x, kd, s[0]); s[1] = fmaf(q4.y, kd, s[1]);
+            s[2] = fmaf(q4.z, kd, s[2]); s[3] = fmaf(q4.w, kd, s[3]);
+        }
+        const int gk = k0 + lane;
+        float p[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int gq = q0 + w * 4 + i;
+            const bool vis = (gk < sq.nk) && (!L.causal || gk <= gq + shift);
+            const float si = vis ? s[i] : -INFINITY;
+            const float mnew = fmaxf(m[i], warp_max(si));
+            p[i] = (si == -INFINITY) ? 0.f : expf(si - mnew);
+            const float corr = (m[i] == -INFINITY) ? 0.f : expf(m[i] - mnew);
+            l[i] = l[i] * corr + warp_sum(p[i]);
+            a0[i] *= corr; a1[i] *= corr;
+            m[i] = mnew;
+        }
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const float v0 = Vs[j][lane], v1 = Vs[j][lane + 32];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float pj = __shfl_sync(0xffffffffu, p[i], j);
+                a0[i] = fmaf(pj, v0, a0[i]);
+                a1[i] = fmaf(pj, v1, a1[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gq = q0 + w * 4 + i;
+        if (gq < sq.nq) {
+            TOut* o = out + (size_t)(sq.q_start + gq) * out_row_stride + h * kHeadDim;
+            const float inv = 1.0f / l[i];
+            o[lane] = from_f32<TOut>(a0[i] * inv);
+            o[lane + 32] = from_f32<TOut>(a1[i] * inv);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused sampler: penalty -> (greedy | /T -> top-k -> top-p -> softmax -> argmax(p / Exp(1)))
+// one CTA (256 threads) per sequence; V <= 2048.
+// ------------------------------------------------------------------------------------------------
+constexpr int SV = 2048;
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct KeyIdx { float v; int i; };
+__device__ __forceinline__ bool key_less(const KeyIdx& a, const KeyIdx& b) {
+    return (a.v < b.v) || (a.v == b.v && a.i < b.i);
+}
+
+__global__ void __launch_bounds__(256)
+sample_kernel(const float* __restrict__ logits, int ld, const int* __restrict__ active, int V, SampleState S,
+              int advance_ctx) {
+    __shared__ float zs[SV];         // logits after penalty (/T), original order
+    __shared__ float sv[SV];         // sort values
+    __shared__ short si[SV];         // sort indices
+    __shared__ float red[32];
+    __shared__ int redi[32];
+    __shared__ float scan_part[256];
+    const int tid = threadIdx.x;
+    const int slot = active[blockIdx.x];
+    const int n = S.n_gen[slot];
+    const float* z = logits + (size_t)blockIdx.x * ld;
+    const float pen = S.penalty[slot];
+    const unsigned* seen = S.seen + (size_t)slot * S.seen_words;
+    const float T = S.temperature[slot];
+    const bool greedy = T < 1e-5f;
+    for (int v = tid; v < SV; v += 256) {
+        float x = -INFINITY;
+        if (v < V) {
+            x = z[v];
+            if (pen != 1.0f && ((seen[v >> 5] >> (v & 31)) & 1u)) x = (x > 0.f) ? x / pen : x * pen;
+            if (!greedy) x = x / T;
+        }
+        zs[v] = x;
+    }
+    __syncthreads();
+    int chosen = 0;
+    if (!greedy) {
+        // ---- ascending bitonic sort of (value, index); the SV-V pads (-inf, idx>=V) go to the front
+        for (int v = tid; v < SV; v += 256) { sv[v] = zs[v]; si[v] = (short)v; }
+        __syncthreads();
+        for (int k = 2; k <= SV; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < SV; t += 256) {
+                    const int ixj = t ^ j;
+                    if (ixj > t) {
+                        KeyIdx a{sv[t], si[t]}, b{sv[ixj], si[ixj]};
+                        const bool up = ((t & k) == 0);
+                        const bool sw = up ? key_less(b, a) : key_less(a, b);
+                        if (sw) { sv[t] = b.v; si[t] = (short)b.i; sv[ixj] = a.v; si[ixj] = (short)a.i; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // ---- top-k: keep >= k-th largest
+        const int tk = S.top_k[slot];
+        if (tk > 0 && tk < V) {
+            const float kth = sv[SV - tk];
+            __syncthreads();
+            for (int v = tid; v < SV; v += 256) if (sv[v] < kth) sv[v] = -INFINITY;
+            __syncthreads();
+        }
+        // ---- top-p on the ascending order: drop while cumulative softmax <= 1-p, always keep the last
+        const float tp = S.top_p[slot];
+        const float mx = sv[SV - 1];
+        if (tp < 1.0f) {
+            float e[8], loc = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float x = sv[tid * 8 + u];
+                e[u] = (x == -INFINITY) ? 0.f : expf(x - mx);
+                loc += e[u];
+            }
+            const float total = block_sum(loc, red);
+            // inclusive scan of per-thread partial sums
+            scan_part[tid] = loc;
+            __syncthreads();
+            for (int off = 1; off < 256; off <<= 1) {
+                const float add = (tid >= off) ? scan_part[tid - off] : 0.f;
+                __syncthreads();
+                scan_part[tid] += add;
+                __syncthreads();
+            }
+            float run = (tid == 0) ? 0.f : scan_part[tid - 1];
+            const float thr = 1.0f - tp;
+            const float inv = 1.0f / total;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                run += e[u];
+                const int pos = tid * 8 + u;
+                if (pos != SV - 1 && run * inv <= thr) sv[pos] = -INFINITY;
+            }
+            __syncthreads();
+        }
+        // ---- scatter the kept logits back to vocabulary order
+        for (int v = tid; v < SV; v += 256) { const int id = si[v]; if (id < V) zs[id] = sv[v]; }
+        __syncthreads();
+        // ---- softmax over kept, then argmax(p / e), e ~ Exp(1) from Philox(counter=(v/4, step, seq_seed, 0))
+        float loc = 0.f;
+        for (int v = tid; v < V; v += 256) { const float x = zs[v]; loc += (x == -INFINITY) ? 0.f : expf(x - mx); }
+        const float total = block_sum(loc, red);
+        const unsigned long long seed = S.seed[slot];
+        const uint32_t k0 = (uint32_t)(seed & 0xffffffffull), k1 = (uint32_t)(seed >> 32);
+        const uint32_t sseed = (uint32_t)S.seq_seed[slot];
+        float best = -1.f; int besti = 0x7fffffff;
+        for (int blk = tid; blk * 4 < V; blk += 256) {
+            uint32_t r[4];
+            philox4x32_10((uint32_t)blk, (uint32_t)n, sseed, 0u, k0, k1, r);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int v = blk * 4 + u;
+                if (v < V) {
+                    const float x = zs[v];
+                    const float p = (x == -INFINITY) ? 0.f : expf(x - mx) / total;
+                    const float uu = ((float)(r[u] >> 9) + 0.5f) * (1.0f / 8388608.0f);
+                    const float ee = -logf(uu);
+                    const float ratio = p / ee;
+                    if (ratio > best || (ratio == best && v < besti)) { best = ratio; besti = v; }
+                }
+            }
+        }
+        // block argmax (max ratio, lowest index on ties)
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) { red[tid >> 5] = best; redi[tid >> 5] = besti; }
+        __syncthreads();
+        if (tid < 32) {
+            best = (tid < 8) ? red[tid] : -2.f;
+            besti = (tid < 8) ? redi[tid] : 0x7fffffff;
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            }
+            chosen = besti;
+        }
+    } else {
+        float best = -INFINITY; int besti = 0x7fffffff;
+        for (int v = tid; v < V; v += 256) {
+            const float x = zs[v];
+            if (x > best || (x == best && v < besti)) { best = x; besti = v; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if ((tid & 31) == 0) { red[tid >> 5] = best; redi[tid >> 5] = besti; }
+        __syncthreads();
+        if (tid < 32) {
+            best = (tid < 8) ? red[tid] : -INFINITY;
+            besti = (tid < 8) ? redi[tid] : 0x7fffffff;
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            }
+            chosen = besti;
+        }
+    }
+    if (tid == 0) {
+        if (chosen < 0 || chosen >= V) chosen = 0;          // all -inf/NaN guard
+        int tok = chosen;
+        if (S.forced) { const int f = S.forced[(size_t)slot * S.tokens_cap + n]; if (f >= 0) tok = f; }
+        if (n < S.tokens_cap) {
+            S.tokens[(size_t)slot * S.tokens_cap + n] = tok;
+            S.sampled[(size_t)slot * S.tokens_cap + n] = chosen;
+        }
+        S.last_tok[slot] = tok;
+        S.seen[(size_t)slot * S.seen_words + (tok >> 5)] |= (1u << (tok & 31));
+        S.n_gen[slot] = n + 1;
+        if (advance_ctx) S.ctx_len[slot] += 1;
+        if (tok == S.stop_token[slot] || n + 1 >= S.max_tokens[slot]) S.finished[slot] = 1;
+    }
+}
+
+}  // namespace
+
+// ================================================================================================
+// launchers
+// ================================================================================================
+void launch_build_rows(const RowDesc* rows, int n_rows, GptTables t, float* X, cudaStream_t st) {
+    if (n_rows <= 0) return;
+    build_rows_kernel<<<n_rows, 256, 0, st>>>(rows, t, X);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+
+void launch_build_decode_rows(const int* active, int M, const int* last_tok, const int* n_gen, GptTables t,
+                              float* X, cudaStream_t st) {
+    if (M <= 0) return;
+    build_decode_rows_kernel<<<M, 256, 0, st>>>(active, last_tok, n_gen, t, X);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+
+template <typename TOut>
+void launch_layernorm(const float* X, const float* w, const float* b, TOut* Y, int M, int H, float eps,
+                      cudaStream_t st) {
+    if (M <= 0) return;
+    layernorm_kernel<TOut><<<M, 256, 0, st>>>(X, w, b, Y, H, eps);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+template void launch_layernorm<float>(const float*, const float*, const float*, float*, int, int, float, cudaStream_t);
+template void launch_layernorm<__nv_bfloat16>(const float*, const float*, const float*, __nv_bfloat16*, int, int, float, cudaStream_t);
+
+template <typename TOut>
+void launch_head_norms(const float* X, const int* row_index, const float* lnf_w, const float* lnf_b,
+                       const float* fn_w, const float* fn_b, TOut* Y, float* latents, const int* slots,
+                       const int* lat_pos, const int* n_gen, int lat_rows_per_slot, int M, int H, float eps,
+                       cudaStream_t st) {
+    if (M <= 0) return;
+    head_norms_kernel<TOut><<<M, 256, H * sizeof(float), st>>>(X, row_index, lnf_w, lnf_b, fn_w, fn_b, Y, latents,
+                                                                slots, lat_pos, n_gen, lat_rows_per_slot, H, eps);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+template void launch_head_norms<float>(const float*, const int*, const float*, const float*, const float*, const float*, float*, float*, const int*, const int*, const int*, int, int, int, float, cudaStream_t);
+template void launch_head_norms<__nv_bfloat16>(const float*, const int*, const float*, const float*, const float*, const float*, __nv_bfloat16*, float*, const int*, const int*, const int*, int, int, int, float, cudaStream_t);
+
+template <typename TKV>
+void launch_kv_write(const float* QKV, int M, const int* row_slot, const int* row_pos, const int* ctx_len,
+                     const int* block_tables, int max_pages, TKV* kpool, TKV* vpool, int heads, cudaStream_t st) {
+    if (M <= 0) return;
+    kv_write_kernel<TKV><<<dim3(M, heads), 128, 0, st>>>(QKV, row_slot, row_pos, ctx_len, block_tables, max_pages,
+                                                         kpool, vpool, heads);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+template void launch_kv_write<float>(const float*, int, const int*, const int*, const int*, const int*, int, float*, float*, int, cudaStream_t);
+template void launch_kv_write<__nv_bfloat16>(const float*, int, const int*, const int*, const int*, const int*, int, __nv_bfloat16*, __nv_bfloat16*, int, cudaStream_t);
+
+template <typename TKV, typename TOut>
+void launch_attn_decode(const float* QKV, const int* active, int M, const int* ctx_len, const int* block_tables,
+                        int max_pages, const TKV* kpool, const TKV* vpool, TOut* out, int heads, cudaStream_t st) {
+    if (M <= 0) return;
+    attn_decode_kernel<TKV, TOut><<<dim3(M, heads), 128, 0, st>>>(QKV, active, ctx_len, block_tables, max_pages,
+                                                                 kpool, vpool, out, heads);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+template void launch_attn_decode<float, float>(const float*, const int*, int, const int*, const int*, int, const float*, const float*, float*, int, cudaStream_t);
+template void launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(const float*, const int*, int, const int*, const int*, int, const __nv_bfloat16*, const __nv_bfloat16*, __nv_bfloat16*, int, cudaStream_t);
+
+template <typename TOut>
+void launch_attn_generic(AttnLayout L, const AttnSeq* seqs, int nseq, int max_nq, TOut* out, int out_row_stride,
+                         cudaStream_t st) {
+    if (nseq <= 0 || max_nq <= 0) return;
+    attn_generic_kernel<TOut><<<dim3(ceil_div(max_nq, AQ), L.heads, nseq), 128, 0, st>>>(L, seqs, out, out_row_stride);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+template void launch_attn_generic<float>(AttnLayout, const AttnSeq*, int, int, float*, int, cudaStream_t);
+template void launch_attn_generic<__nv_bfloat16>(AttnLayout, const AttnSeq*, int, int, __nv_bfloat16*, int, cudaStream_t);
+
+void launch_sample(const float* logits, int ld_logits, const int* active, int M, int V, SampleState s,
+                   int advance_ctx, cudaStream_t st) {
+    if (M <= 0) return;
+    if (V > SV) throw CudaError("sample: vocabulary larger than 2048 is not supported");
+    sample_kernel<<<M, 256, 0, st>>>(logits, ld_logits, active, V, s, advance_ctx);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+
+}  // namespace xtts

@@ -1,0 +1,124 @@
+// Host-side launchers of every sm_100a kernel in the library (one declaration per kernel family).
+// Each launcher enqueues on `st` and returns; errors surface as xtts::CudaError.
+#pragma once
+#include "common.cuh"
+
+namespace xtts {
+
+// ------------------------------------------------------------------------------------------
+// GEMM:  out[M,N] = epi(A[M,K] . W[N,K]^T + bias[N])      (W is [out,in] = K contiguous)
+//   flags: GEMM_GELU  -> gelu_new after bias
+//          GEMM_RESID -> out = resid + (...)   (resid may alias out)
+// ------------------------------------------------------------------------------------------
+enum : int { GEMM_GELU = 1, GEMM_RESID = 2, GEMM_OUT_BF16 = 4 };
+
+// fp32 CUDA-core path (parity mode; also the GPU-side reference for the tcgen05 path)
+void launch_gemm_f32(const float* A, const float* W, const float* bias, const float* resid, float* out,
+                     int M, int N, int K, int flags, cudaStream_t st);
+
+// bf16 tcgen05/TMA path (fast mode).  A [M,K] bf16 row-major, W [N,K] bf16 row-major; fp32 accum in TMEM.
+// out is fp32 unless GEMM_OUT_BF16.  K % 64 == 0, N % 16 == 0 required.
+void launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const float* resid,
+                         void* out, int M, int N, int K, int flags, cudaStream_t st);
+bool gemm_tc_init(std::string* err);   // resolves cuTensorMapEncodeTiled; false -> err filled
+
+void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------
+// GPT glue kernels
+// ------------------------------------------------------------------------------------------
+struct RowDesc {          // one prompt / teacher-forced input row
+    int kind;             // 0: cond row `a` of speaker slot `c`; 1: text id `a` at text position `b`;
+                          // 2: audio token `a` at audio position `b`
+    int a, b, c;
+};
+
+struct GptTables {        // embedding tables (device, fp32)
+    const float* text_emb;  // [n_text, H]
+    const float* text_pos;  // [n_text_pos, H]
+    const float* wte;       // [n_audio, H]
+    const float* wpe;       // [n_wpe, H]
+    const float* spk_cond;  // [n_speaker_slots, n_cond, H]
+    int H, n_cond;
+};
+
+void launch_build_rows(const RowDesc* rows, int n_rows, GptTables t, float* X, cudaStream_t st);
+// decode input rows: X[i] = wte[last_tok[slot]] + wpe[n_gen[slot]],  slot = active[i]
+void launch_build_decode_rows(const int* active, int M, const int* last_tok, const int* n_gen, GptTables t,
+                              float* X, cudaStream_t st);
+
+template <typename TOut>
+void launch_layernorm(const float* X, const float* w, const float* b, TOut* Y, int M, int H, float eps,
+                      cudaStream_t st);
+
+// y = LN_fn(LN_lnf(X[row_index[i]]));  Y[i] = y (GEMM operand);
+// latents[slots[i]][lat_pos ? lat_pos[i] : n_gen[slots[i]]] = LN_fn(y)
+template <typename TOut>
+void launch_head_norms(const float* X, const int* row_index, const float* lnf_w, const float* lnf_b,
+                       const float* fn_w, const float* fn_b, TOut* Y, float* latents, const int* slots,
+                       const int* lat_pos, const int* n_gen, int lat_rows_per_slot, int M, int H, float eps,
+                       cudaStream_t st);
+
+// KV page layout (per layer):  K: [page][head][D/X][32 tok][X]   V: [page][head][32 tok][D]
+//   X = 16 bytes / sizeof(TKV)  (so one lane = one token reads 16 B, coalesced across the warp)
+template <typename TKV>
+void launch_kv_write(const float* QKV, int M, const int* row_slot, const int* row_pos, const int* ctx_len,
+                     const int* block_tables, int max_pages, TKV* kpool, TKV* vpool, int heads,
+                     cudaStream_t st);
+
+// decode attention over the paged cache; ctx = ctx_len[slot] + 1 (new token already written)
+template <typename TKV, typename TOut>
+void launch_attn_decode(const float* QKV, const int* active, int M, const int* ctx_len,
+                        const int* block_tables, int max_pages, const TKV* kpool, const TKV* vpool,
+                        TOut* out, int heads, cudaStream_t st);
+
+struct AttnSeq { int q_start, nq, kv_start, nk; };
+struct AttnLayout {
+    const float* q; const float* k; const float* v;   // base pointers
+    int q_row_stride, kv_row_stride;                   // elements between consecutive rows
+    int q_head_stride, kv_head_stride;                 // elements between heads inside a row
+    int heads;
+    float scale;
+    int causal;                                        // key j visible to query i iff j <= i + (nk - nq)
+};
+// generic fp32 attention (GPT prefill, conditioning encoder, perceiver); head_dim 64
+template <typename TOut>
+void launch_attn_generic(AttnLayout L, const AttnSeq* seqs, int nseq, int max_nq, TOut* out, int out_row_stride,
+                         cudaStream_t st);
+
+struct SampleState {      // per-slot arrays (device)
+    int* last_tok; int* n_gen; int* ctx_len; int* finished;
+    int* tokens;          // [slot][max_tokens_cap] chosen tokens
+    int* sampled;         // [slot][max_tokens_cap] what the sampler drew (== tokens unless forced)
+    const int* forced;    // [slot][max_tokens_cap] or nullptr; entry < 0 = not forced
+    unsigned* seen;       // [slot][seen_words] bitmap of ids in prompt ∪ generated
+    const float* temperature; const float* top_p; const int* top_k; const float* penalty;
+    const int* max_tokens; const int* stop_token; const unsigned long long* seed; const int* seq_seed;
+    int tokens_cap, seen_words;
+};
+void launch_sample(const float* logits, int ld_logits, const int* active, int M, int V, SampleState s,
+                   int advance_ctx, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------
+// Vocoder kernels (fp32, channel-major activations [C][L])
+// ------------------------------------------------------------------------------------------
+void launch_interp(const float* latents, float* z, int T, int C, int T1, int Tz, double scale1, double scale2,
+                   cudaStream_t st);
+
+enum : int { CONV_STORE = 0, CONV_ACCUM = 1 };
+// out[co][t] (=|+=) bias[co] + cbias[co] + resid[co][t] + sum_{ci,j} w[ci][j][co] * act(in_scale*x[ci][t+(j-(K-1)/2)*dil])
+//   act = leaky_relu(slope) (slope==1 -> identity).  w is pre-transposed to [Cin][K][Cout].
+void launch_conv1d(const float* x, const float* w_t, const float* bias, const float* cbias, const float* resid,
+                   float* out, int Cin, int Cout, int L, int K, int dil, float in_scale, float slope, int mode,
+                   cudaStream_t st);
+// transposed conv, stride u, kernel K = 2u, padding (K-u)/2;  w pre-transposed to [Cin][K][Cout]
+void launch_conv_transpose1d(const float* x, const float* w_t, const float* bias, const float* cbias, float* out,
+                             int Cin, int Cout, int Lin, int K, int u, float in_scale, float slope,
+                             cudaStream_t st);
+// wav[t] = tanh(sum w[ci][j] * lrelu(in_scale*x[ci][t+j-3], slope))
+void launch_conv_post(const float* x, const float* w, float* wav, int Cin, int L, int K, float in_scale, float slope,
+                      cudaStream_t st);
+// y[c] = W[c,:] . g + b[c]   (speaker conditioning 1x1 convs)
+void launch_gemv(const float* W, const float* b, const float* g, float* y, int rows, int cols, cudaStream_t st);
+
+}  // namespace xtts

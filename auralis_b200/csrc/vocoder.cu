@@ -1,0 +1,302 @@
+// HiFi-GAN vocoder kernels, fp32 CUDA-core version (channel-major activations [C][L]).
+//
+// Reference call sites:
+//   hifigan_decoder.py:787-800  two F.interpolate(linear, align_corners=False)        -> interp_kernel
+//   hifigan_decoder.py:243-245  conv_pre (k7) + cond_layer(g)                          -> conv1d_kernel<7>
+//   hifigan_decoder.py:246-251  leaky_relu(0.1) -> ConvTranspose1d -> + conds[i](g)    -> conv_transpose1d_kernel
+//   hifigan_decoder.py:76-91    ResBlock1: lrelu -> conv(k,d) -> lrelu -> conv(k,1) -> +x  -> conv1d_kernel<3|7|11>
+//   hifigan_decoder.py:253-256  MRF sum / num_kernels                                  -> CONV_ACCUM + in_scale=1/3
+//   hifigan_decoder.py:257-259  leaky_relu(0.01) -> conv_post (k7, no bias) -> tanh    -> conv_post_kernel
+//
+// Dense conv C->C with kernel k is a GEMM with K-dim = C*k; here it is register-tiled on the FP32 pipe:
+// a CTA computes 64 (or 32) output channels x 128 time steps, staging 8 input channels (+halo) and
+// the matching [8][k][64] weight slab in shared memory per iteration.
+#include "kernels.h"
+
+namespace xtts {
+namespace {
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+// ------------------------------------------------------------------------------------------------
+// fused double linear interpolation + transpose:  latents [T][C]  ->  z [C][Tz]
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lin_src(int dst, float rscale, int in_len, int& i0, int& i1, float& l0, float& l1) {
+    float src = rscale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    i0 = (int)src;
+    if (i0 > in_len - 1) i0 = in_len - 1;
+    i1 = i0 + ((i0 < in_len - 1) ? 1 : 0);
+    l1 = src - (float)i0;
+    l0 = 1.0f - l1;
+}
+
+__global__ void __launch_bounds__(256)
+interp_kernel(const float* __restrict__ lat, float* __restrict__ z, int T, int C, int T1, int Tz, float r1, float r2) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;       // (32, 8)
+    for (int k = 0; k < 4; ++k) {
+        const int j = j0 + ty + 8 * k, c = c0 + tx;
+        float v = 0.f;
+        if (j < Tz && c < C) {
+            int a0, a1; float m0, m1;
+            lin_src(j, r2, T1, a0, a1, m0, m1);
+            int b0, b1; float n0, n1;
+            lin_src(a0, r1, T, b0, b1, n0, n1);
+            const float za = n0 * lat[(size_t)b0 * C + c] + n1 * lat[(size_t)b1 * C + c];
+            lin_src(a1, r1, T, b0, b1, n0, n1);
+            const float zb = n0 * lat[(size_t)b0 * C + c] + n1 * lat[(size_t)b1 * C + c];
+            v = m0 * za + m1 * zb;
+        }
+        tile[ty + 8 * k][tx] = v;
+    }
+    __syncthreads();
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k, j = j0 + tx;
+        if (c < C && j < Tz) z[(size_t)c * Tz + j] = tile[tx][ty + 8 * k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dilated Conv1d, "same" padding, fused input scale + leaky-relu, bias, speaker bias, residual, store/accumulate
+// ------------------------------------------------------------------------------------------------
+constexpr int CT_T = 128;      // time steps per CTA (4 per thread, stride 32)
+constexpr int CT_CI = 8;       // input channels staged per iteration
+constexpr int CT_TC = 8;       // output channels per thread
+
+template <int K, int NTY>
+__global__ void __launch_bounds__(32 * NTY)
+conv1d_kernel(const float* __restrict__ x, const float* __restrict__ w_t, const float* __restrict__ bias,
+              const float* __restrict__ cbias, const float* resid, float* out, int Cin, int Cout, int L, int dil,
+              float in_scale, float slope, int mode) {
+    constexpr int CO_T = CT_TC * NTY;
+    extern __shared__ __align__(16) float smem[];
+    const int halo = (K - 1) / 2 * dil;
+    const int XW = CT_T + 2 * halo;
+    float* xs = smem;                              // [CT_CI][XW]
+    float* ws = smem + CT_CI * XW + ((4 - (CT_CI * XW) % 4) % 4);   // [CT_CI][K][CO_T], 16-byte aligned
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * 32 + tx;
+    const int nthr = 32 * NTY;
+    const int t0 = blockIdx.x * CT_T, co0 = blockIdx.y * CO_T;
+
+    float acc[CT_TC][4];
+#pragma unroll
+    for (int c = 0; c < CT_TC; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
+
+    for (int ci0 = 0; ci0 < Cin; ci0 += CT_CI) {
+        __syncthreads();
+        for (int e = tid; e < CT_CI * XW; e += nthr) {
+            const int ci = e / XW, p = e - ci * XW;
+            const int gt = t0 - halo + p;
+            float v = 0.f;
+            if (gt >= 0 && gt < L && ci0 + ci < Cin) v = lrelu(in_scale * x[(size_t)(ci0 + ci) * L + gt], slope);
+            xs[e] = v;
+        }
+        for (int e = tid; e < CT_CI * K * CO_T; e += nthr) {
+            const int ci = e / (K * CO_T);
+            const int r = e - ci * (K * CO_T);
+            const int j = r / CO_T, co = r - j * CO_T;
+            float v = 0.f;
+            if (ci0 + ci < Cin && co0 + co < Cout) v = w_t[((size_t)(ci0 + ci) * K + j) * Cout + co0 + co];
+            ws[e] = v;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int ci = 0; ci < CT_CI; ++ci) {
+            const float* xr = xs + ci * XW + tx;
+            const float* wr = ws + (ci * K) * CO_T + ty * CT_TC;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                float xv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xv[i] = xr[32 * i + j * dil];
+                const float4 wa = *reinterpret_cast<const float4*>(wr + j * CO_T);
+                const float4 wb = *reinterpret_cast<const float4*>(wr + j * CO_T + 4);
+                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int c = 0; c < CT_TC; ++c)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[c][i] = fmaf(wv[c], xv[i], acc[c][i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CT_TC; ++c) {
+        const int co = co0 + ty * CT_TC + c;
+        if (co >= Cout) continue;
+        const float b = (bias ? bias[co] : 0.f) + (cbias ? cbias[co] : 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int t = t0 + tx + 32 * i;
+            if (t >= L) continue;
+            const size_t o = (size_t)co * L + t;
+            float v = acc[c][i] + b;
+            if (resid) v += resid[o];
+            if (mode == CONV_ACCUM) v += out[o];
+            out[o] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ConvTranspose1d with K == 2*stride, padding = stride/2: every output sample has exactly two taps.
+//   out[co][t] = b + sum_ci act(x[ci][s0]) w[ci][j0][co] + act(x[ci][s0-1]) w[ci][j0+u][co],
+//   q = t + u/2, j0 = q % u, s0 = q / u
+// ------------------------------------------------------------------------------------------------
+constexpr int UP_T = 128, UP_CI = 8, UP_CO = 16;
+
+__global__ void __launch_bounds__(UP_T)
+conv_transpose1d_kernel(const float* __restrict__ x, const float* __restrict__ w_t, const float* __restrict__ bias,
+                        const float* __restrict__ cbias, float* __restrict__ out, int Cin, int Cout, int Lin, int K,
+                        int u, float in_scale, float slope) {
+    extern __shared__ __align__(16) float smem[];
+    const int pad = (K - u) / 2;
+    const int XS = UP_T / u + 3;                   // source frames touched by the tile (+ slack)
+    constexpr int WROW = UP_CO + 4;
+    float* xs = smem;                              // [UP_CI][XS]
+    float* ws = smem + ((UP_CI * XS + 3) / 4) * 4; // [UP_CI][K][WROW]
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * UP_T, co0 = blockIdx.y * UP_CO;
+    const int Lout = Lin * u;
+    const int s_base = (t0 + pad) / u - 1;         // first source frame the tile may touch
+    const int t = t0 + tid;
+    const int q = t + pad;
+    const int j0 = q % u, s0 = q / u;
+    float acc[UP_CO];
+#pragma unroll
+    for (int c = 0; c < UP_CO; ++c) acc[c] = 0.f;
+    for (int ci0 = 0; ci0 < Cin; ci0 += UP_CI) {
+        __syncthreads();
+        for (int e = tid; e < UP_CI * XS; e += UP_T) {
+            const int ci = e / XS, p = e - ci * XS;
+            const int s = s_base + p;
+            float v = 0.f;
+            if (s >= 0 && s < Lin && ci0 + ci < Cin) v = lrelu(in_scale * x[(size_t)(ci0 + ci) * Lin + s], slope);
+            xs[e] = v;
+        }
+        for (int e = tid; e < UP_CI * K * UP_CO; e += UP_T) {
+            const int ci = e / (K * UP_CO);
+            const int r = e - ci * (K * UP_CO);
+            const int j = r / UP_CO, co = r - j * UP_CO;
+            float v = 0.f;
+            if (ci0 + ci < Cin && co0 + co < Cout) v = w_t[((size_t)(ci0 + ci) * K + j) * Cout + co0 + co];
+            ws[(ci * K + j) * WROW + co] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ci = 0; ci < UP_CI; ++ci) {
+            const float xa = xs[ci * XS + (s0 - s_base)];
+            const float xb = xs[ci * XS + (s0 - 1 - s_base)];
+            const float* wa = ws + (ci * K + j0) * WROW;
+            const float* wb = ws + (ci * K + j0 + u) * WROW;
+#pragma unroll
+            for (int c4 = 0; c4 < UP_CO / 4; ++c4) {
+                const float4 a = *reinterpret_cast<const float4*>(wa + 4 * c4);
+                const float4 b = *reinterpret_cast<const float4*>(wb + 4 * c4);
+                acc[4 * c4 + 0] = fmaf(xa, a.x, fmaf(xb, b.x, acc[4 * c4 + 0]));
+                acc[4 * c4 + 1] = fmaf(xa, a.y, fmaf(xb, b.y, acc[4 * c4 + 1]));
+                acc[4 * c4 + 2] = fmaf(xa, a.z, fmaf(xb, b.z, acc[4 * c4 + 2]));
+                acc[4 * c4 + 3] = fmaf(xa, a.w, fmaf(xb, b.w, acc[4 * c4 + 3]));
+            }
+        }
+    }
+    if (t < Lout) {
+#pragma unroll
+        for (int c = 0; c < UP_CO; ++c) {
+            const int co = co0 + c;
+            if (co < Cout)
+                out[(size_t)co * Lout + t] = acc[c] + (bias ? bias[co] : 0.f) + (cbias ? cbias[co] : 0.f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_post (C->1, k7, no bias) + tanh; HBM-bound (reads C*L floats, writes L)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ wav, int Cin, int L,
+                 int K, float in_scale, float slope) {
+    extern __shared__ float wsm[];                 // [Cin*K]
+    for (int e = threadIdx.x; e < Cin * K; e += blockDim.x) wsm[e] = w[e];
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= L) return;
+    const int half = (K - 1) / 2;
+    float acc = 0.f;
+    for (int ci = 0; ci < Cin; ++ci) {
+        const float* xr = x + (size_t)ci * L;
+        for (int j = 0; j < K; ++j) {
+            const int s = t + j - half;
+            if (s >= 0 && s < L) acc = fmaf(wsm[ci * K + j], lrelu(in_scale * xr[s], slope), acc);
+        }
+    }
+    wav[t] = tanhf(acc);
+}
+
+template <int K>
+void conv1d_dispatch(const float* x, const float* w_t, const float* bias, const float* cbias, const float* resid,
+                     float* out, int Cin, int Cout, int L, int dil, float in_scale, float slope, int mode,
+                     cudaStream_t st) {
+    const int halo = (K - 1) / 2 * dil;
+    const int XW = CT_T + 2 * halo;
+    const int xs_f = CT_CI * XW + ((4 - (CT_CI * XW) % 4) % 4);
+    if (Cout > 32) {
+        constexpr int NTY = 8;
+        const size_t smem = (size_t)(xs_f + CT_CI * K * CT_TC * NTY) * sizeof(float);
+        dim3 grid(ceil_div(L, CT_T), ceil_div(Cout, CT_TC * NTY));
+        conv1d_kernel<K, NTY><<<grid, dim3(32, NTY), smem, st>>>(x, w_t, bias, cbias, resid, out, Cin, Cout, L, dil,
+                                                                 in_scale, slope, mode);
+    } else {
+        constexpr int NTY = 4;
+        const size_t smem = (size_t)(xs_f + CT_CI * K * CT_TC * NTY) * sizeof(float);
+        dim3 grid(ceil_div(L, CT_T), ceil_div(Cout, CT_TC * NTY));
+        conv1d_kernel<K, NTY><<<grid, dim3(32, NTY), smem, st>>>(x, w_t, bias, cbias, resid, out, Cin, Cout, L, dil,
+                                                                 in_scale, slope, mode);
+    }
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+
+}  // namespace
+
+void launch_interp(const float* latents, float* z, int T, int C, int T1, int Tz, double scale1, double scale2,
+                   cudaStream_t st) {
+    const float r1 = (float)(1.0 / scale1), r2 = (float)(1.0 / scale2);
+    interp_kernel<<<dim3(ceil_div(Tz, 32), ceil_div(C, 32)), dim3(32, 8), 0, st>>>(latents, z, T, C, T1, Tz, r1, r2);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+
+void launch_conv1d(const float* x, const float* w_t, const float* bias, const float* cbias, const float* resid,
+                   float* out, int Cin, int Cout, int L, int K, int dil, float in_scale, float slope, int mode,
+                   cudaStream_t st) {
+    if (L <= 0) return;
+    switch (K) {
+        case 3: conv1d_dispatch<3>(x, w_t, bias, cbias, resid, out, Cin, Cout, L, dil, in_scale, slope, mode, st); break;
+        case 7: conv1d_dispatch<7>(x, w_t, bias, cbias, resid, out, Cin, Cout, L, dil, in_scale, slope, mode, st); break;
+        case 11: conv1d_dispatch<11>(x, w_t, bias, cbias, resid, out, Cin, Cout, L, dil, in_scale, slope, mode, st); break;
+        default: throw CudaError("conv1d: unsupported kernel size (3, 7, 11 only)");
+    }
+}
+
+void launch_conv_transpose1d(const float* x, const float* w_t, const float* bias, const float* cbias, float* out,
+                             int Cin, int Cout, int Lin, int K, int u, float in_scale, float slope,
+                             cudaStream_t st) {
+    if (K != 2 * u || (u & 1)) throw CudaError("conv_transpose1d: only kernel == 2*stride with even stride is supported");
+    if (UP_T % u != 0) throw CudaError("conv_transpose1d: stride must divide 128");
+    const int XS = UP_T / u + 3;
+    const size_t smem = (size_t)(((UP_CI * XS + 3) / 4) * 4 + UP_CI * K * (UP_CO + 4)) * sizeof(float);
+    dim3 grid(ceil_div(Lin * u, UP_T), ceil_div(Cout, UP_CO));
+    conv_transpose1d_kernel<<<grid, UP_T, smem, st>>>(x, w_t, bias, cbias, out, Cin, Cout, Lin, K, u, in_scale, slope);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+
+void launch_conv_post(const float* x, const float* w, float* wav, int Cin, int L, int K, float in_scale, float slope,
+                      cudaStream_t st) {
+    conv_post_kernel<<<ceil_div(L, 256), 256, Cin * K * sizeof(float), st>>>(x, w, wav, Cin, L, K, in_scale, slope);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+
+}  // namespace xtts

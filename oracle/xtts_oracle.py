@@ -208,7 +208,8 @@ def topk_topp_mask(z: torch.Tensor, top_k: int, top_p: float) -> torch.Tensor:
     if top_p < 1.0:
         probs = torch.softmax(srt, dim=-1)
         cs = torch.cumsum(probs, dim=-1)
-        m = cs <= (1.0 - top_p)
+        thr = float(np.float32(1.0) - np.float32(top_p))      # fp32 threshold, as the kernel computes it
+        m = cs <= thr
         m[-1] = False
         srt = srt.masked_fill(m, float("-inf"))
     out = torch.empty_like(z)
@@ -234,14 +235,15 @@ def philox4x32(counter: Sequence[int], key: Sequence[int]) -> np.ndarray:
 
 
 def exp_noise(seed: int, seq_seed: int, step: int, V: int) -> np.ndarray:
-    """Exp(1) variate per vocabulary entry: e = -log(u), u = (r + 0.5) * 2^-32 in (0,1).
+    """Exp(1) variate per vocabulary entry: e = -log(u), u = ((r >> 9) + 0.5) * 2^-23 — a 23-bit
+    uniform that is exact in fp32 and never rounds to 0 or 1.
     counter = (v/4, step, seq_seed, 0), key = (seed lo, seed hi)."""
     out = np.empty(((V + 3) // 4) * 4, dtype=np.float32)
     key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     for blk in range((V + 3) // 4):
         r = philox4x32((blk, step, seq_seed, 0), key)
-        u = (r.astype(np.float64) + 0.5) * (1.0 / 4294967296.0)
-        out[blk * 4: blk * 4 + 4] = (-np.log(u.astype(np.float32))).astype(np.float32)
+        u = ((r >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 8388608.0)
+        out[blk * 4: blk * 4 + 4] = (-np.log(u)).astype(np.float32)
     return out[:V]
 
 

@@ -1,0 +1,184 @@
+"""GPU: GPT-2 acoustic model — prefill, paged decode, latent capture, end-to-end chunks vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from auralis_b200.native import Sampling
+from oracle import xtts_oracle as O
+from conftest import text_ids
+
+pytestmark = pytest.mark.gpu
+
+
+def _orc(dims, state):
+    return O.GPTOracle(state[0], state[1], dims)
+
+
+def _margin_report(ref_logits, got_tokens, ref_tokens):
+    bad = []
+    for k, (a, b) in enumerate(zip(got_tokens, ref_tokens)):
+        if a != b:
+            bad.append((k, int(a), int(b), float(ref_logits[k][b] - ref_logits[k][a])))
+    return bad
+
+
+@pytest.mark.parametrize("n_text,n_audio", [(3, 0), (12, 9), (30, 33)])
+def test_prefill_small(engine_small, dims_small, state_small, speakers_small, n_text, n_audio):
+    orc = _orc(dims_small, state_small)
+    ids = text_ids(dims_small, n_text, n_text)
+    rng = np.random.RandomState(n_audio)
+    aud = rng.randint(0, dims_small.gpt.start_audio_token, size=n_audio).tolist()
+    hid, logits, lat = engine_small.gpt_prefill(ids, 2, aud, want_hidden=True)
+    rows = [orc.prompt_rows(speakers_small[2][0], ids)]
+    for k, t in enumerate(aud[:-1], start=1):
+        rows.append(orc.audio_row(t, k)[None])
+    with torch.no_grad():
+        h, _ = orc.forward_rows(torch.cat(rows, 0))
+        n = max(1, n_audio)
+        lg, lt = orc.head(h[-n:])
+    np.testing.assert_allclose(hid, h.numpy(), atol=2e-4, rtol=0)
+    np.testing.assert_allclose(logits, lg.numpy(), atol=2e-4, rtol=0)
+    np.testing.assert_allclose(lat, lt.numpy(), atol=2e-4, rtol=0)
+
+
+def test_teacher_forced_decode_small(engine_small, dims_small, state_small, speakers_small):
+    """paged-KV decode path, step by step, against the oracle's full-prefill logits (no feedback drift)."""
+    orc = _orc(dims_small, state_small)
+    g = dims_small.gpt
+    ids = text_ids(dims_small, 17, 4)
+    rng = np.random.RandomState(8)
+    forced = rng.randint(0, g.start_audio_token, size=40).tolist()      # crosses a 32-token page boundary
+    sp = Sampling(temperature=0.0, repetition_penalty=5.0, max_tokens=40, stop_token=g.stop_audio_token)
+    logits, lat, sampled = engine_small.gpt_teacher_forced(ids, 0, forced, sp)
+    lg, lt = orc.teacher_forced(speakers_small[0][0], ids, forced)
+    np.testing.assert_allclose(logits, lg.numpy(), atol=3e-4, rtol=0)
+    np.testing.assert_allclose(lat, lt.numpy(), atol=3e-4, rtol=0)
+    # sampler inside the loop: greedy + penalty over prompt ∪ forced history
+    seen = O.prompt_seen_set(g)
+    exp = []
+    for k in range(40):
+        z = O.apply_repetition_penalty(lg[k].clone(), seen, 5.0)
+        exp.append(int(torch.argmax(z)))
+        seen.add(forced[k])
+    assert _margin_report(lg.numpy(), sampled, exp) == []
+
+
+def test_e2e_greedy_small(engine_small, dims_small, state_small, speakers_small):
+    """cfg1-style: chunks of different lengths/speakers decoded concurrently (continuous batching), greedy:
+    token ids bit-exact vs the oracle, waveform within fp32 tolerance."""
+    orc = _orc(dims_small, state_small)
+    g = dims_small.gpt
+    jobs, exp = [], {}
+    for i, (n_text, spk, mt) in enumerate([(5, 0, 48), (11, 1, 20), (30, 2, 48), (2, 0, 7), (19, 1, 33), (8, 2, 48),
+                                           (14, 0, 41), (3, 1, 48), (27, 2, 5), (9, 0, 48)]):
+        ids = text_ids(dims_small, n_text, 100 + i)
+        sp = Sampling(temperature=0.0, repetition_penalty=5.0, max_tokens=mt, stop_token=g.stop_audio_token, seq_seed=i)
+        jobs.append((1000 + i, ids, spk, sp))
+        osp = O.SamplingParams(temperature=0.0, repetition_penalty=5.0, max_tokens=mt, stop_token=g.stop_audio_token)
+        toks, lats, lg = orc.generate(speakers_small[spk][0], ids, osp, return_logits=True)
+        wav = O.vocoder(lats, speakers_small[spk][1], state_small[1], dims_small)
+        exp[1000 + i] = (toks, lats.numpy(), wav.numpy(), lg.numpy())
+    res = engine_small.run_batch(jobs, timeout_s=120, want_latents=True)
+    for sid, (r, toks, wav, lat) in res.items():
+        etoks, elat, ewav, elg = exp[sid]
+        assert r.n_tokens == len(etoks)
+        bad = _margin_report(elg, toks, etoks)
+        assert bad == [], (sid, bad)
+        np.testing.assert_allclose(lat, elat, atol=5e-4, rtol=0)
+        assert wav.shape == ewav.shape
+        assert np.abs(wav - ewav).max() < 5e-4, (sid, np.abs(wav - ewav).max())
+
+
+def test_stop_token_ends_sequence(engine_small, dims_small, state_small, speakers_small):
+    orc = _orc(dims_small, state_small)
+    g = dims_small.gpt
+    ids = text_ids(dims_small, 6, 77)
+    osp = O.SamplingParams(temperature=0.0, repetition_penalty=5.0, max_tokens=30, stop_token=g.stop_audio_token)
+    toks, _ = orc.generate(speakers_small[0][0], ids, osp)
+    stop = toks[6]                                 # make the 7th greedy token the stop token
+    sp = Sampling(temperature=0.0, repetition_penalty=5.0, max_tokens=30, stop_token=stop)
+    res = engine_small.run_batch([(5, ids, 0, sp)], timeout_s=60)
+    r, got, wav, _ = res[5]
+    first = toks.index(stop)
+    assert list(got) == toks[: first + 1]
+    assert wav.shape[0] == dims_small.voc.n_samples(first + 1)
+
+
+def test_seeded_sampling_small(engine_small, dims_small, state_small, speakers_small):
+    """T=0.75/top_p=0.85/top_k=50 with the shared Philox stream: same tokens as the oracle (teacher-forced so a
+    single ulp-level flip cannot cascade)."""
+    orc = _orc(dims_small, state_small)
+    g = dims_small.gpt
+    ids = text_ids(dims_small, 10, 5)
+    osp = O.SamplingParams(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, max_tokens=48,
+                           stop_token=g.stop_audio_token, seed=99)
+    toks, _ = orc.generate(speakers_small[1][0], ids, osp, seq_seed=3)
+    sp = Sampling(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, max_tokens=len(toks),
+                  stop_token=g.stop_audio_token, seed=99, seq_seed=3)
+    _, _, sampled = engine_small.gpt_teacher_forced(ids, 1, toks, sp)
+    agree = int((np.array(toks) == sampled).sum())
+    assert agree >= len(toks) - 1, (agree, len(toks))
+
+
+def test_prefill_full_size(engine_full, dims_full, state_full, speakers_full):
+    """30 x 1024 geometry, short prompt + 6 audio rows."""
+    orc = _orc(dims_full, state_full)
+    ids = text_ids(dims_full, 10, 1)
+    aud = [17, 900, 3, 511, 42, 640]
+    _, logits, lat = engine_full.gpt_prefill(ids, 0, aud)
+    lg, lt = orc.teacher_forced(speakers_full[0][0], ids, aud)
+    np.testing.assert_allclose(logits, lg.numpy(), atol=1e-3, rtol=0)
+    np.testing.assert_allclose(lat, lt.numpy(), atol=1e-3, rtol=0)
+
+
+def test_e2e_greedy_full_size(engine_full, dims_full, state_full, speakers_full):
+    """cfg1 shape at full geometry with a bounded token budget so the CPU oracle finishes in seconds."""
+    orc = _orc(dims_full, state_full)
+    g = dims_full.gpt
+    jobs, exp = [], {}
+    for i, (n_text, spk) in enumerate([(20, 0), (7, 1)]):
+        ids = text_ids(dims_full, n_text, 300 + i)
+        sp = Sampling(temperature=0.0, repetition_penalty=5.0, max_tokens=24, stop_token=g.stop_audio_token)
+        jobs.append((i, ids, spk, sp))
+        osp = O.SamplingParams(temperature=0.0, repetition_penalty=5.0, max_tokens=24, stop_token=g.stop_audio_token)
+        toks, lats, lg = orc.generate(speakers_full[spk][0], ids, osp, return_logits=True)
+        exp[i] = (toks, O.vocoder(lats, speakers_full[spk][1], state_full[1], dims_full).numpy(), lg.numpy())
+    res = engine_full.run_batch(jobs, timeout_s=300)
+    for sid, (r, toks, wav, _) in res.items():
+        etoks, ewav, elg = exp[sid]
+        assert _margin_report(elg, toks, etoks) == [], sid
+        assert np.abs(wav - ewav).max() < 1e-3, np.abs(wav - ewav).max()
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 / tcgen05 fast mode: same graph, looser tolerance (bf16 operands, fp32 accumulate)
+# ------------------------------------------------------------------------------------------------
+def test_bf16_prefill_small(engine_small_bf16, dims_small, state_small, speakers_small):
+    orc = _orc(dims_small, state_small)
+    ids = text_ids(dims_small, 12, 12)
+    aud = [5, 100, 77, 3, 64, 9, 31, 2]
+    _, logits, lat = engine_small_bf16.gpt_prefill(ids, 2, aud)
+    lg, lt = orc.teacher_forced(speakers_small[2][0], ids, aud)
+    err = np.abs(logits - lg.numpy()).max()
+    print("bf16 logits max err", err, "logit std", float(lg.std()))
+    assert err < 0.05 * max(1.0, float(lg.abs().max()))
+    assert np.abs(lat - lt.numpy()).max() < 0.08
+
+
+def test_bf16_teacher_forced_and_e2e_small(engine_small_bf16, dims_small, state_small, speakers_small):
+    orc = _orc(dims_small, state_small)
+    g = dims_small.gpt
+    ids = text_ids(dims_small, 17, 4)
+    osp = O.SamplingParams(temperature=0.0, repetition_penalty=5.0, max_tokens=40, stop_token=g.stop_audio_token)
+    toks, lats, lg = orc.generate(speakers_small[0][0], ids, osp, return_logits=True)
+    sp = Sampling(temperature=0.0, repetition_penalty=5.0, max_tokens=40, stop_token=g.stop_audio_token)
+    logits, lat, sampled = engine_small_bf16.gpt_teacher_forced(ids, 0, toks, sp)
+    err = np.abs(logits - lg.numpy()).max()
+    agree = int((sampled == np.array(toks)).sum())
+    print("bf16 decode logits max err", err, "greedy agreement", agree, "/", len(toks))
+    assert err < 0.05 * max(1.0, float(lg.abs().max()))
+    # every disagreement must be a near-tie in the fp32 oracle
+    for k, a, b, margin in _margin_report(lg.numpy(), sampled, toks):
+        assert margin < 0.1, (k, a, b, margin)
+    res = engine_small_bf16.run_batch([(1, ids, 0, sp)], timeout_s=60)
+    assert res[1][0].n_tokens == 40 and np.isfinite(res[1][2]).all()
