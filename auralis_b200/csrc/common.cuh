@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace xtts {
 
@@ -27,6 +28,52 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 // Every kernel launch of this library goes through this counter (bench.py "gpu_launches").
 extern unsigned long long g_launch_count;
 #define COUNT_LAUNCH() (++::xtts::g_launch_count)
+
+// Optional per-kernel-family timing with CUDA events on the launching stream (bench.py "roofline").
+// Off by default; when on, every launcher records an event pair and its algorithmic FLOPs / bytes.
+enum KernelFamily : int {
+    KF_GEMM_TC = 0, KF_GEMM_F32, KF_ATTN_DECODE, KF_ATTN_PREFILL, KF_NORM, KF_SAMPLE, KF_KV_WRITE, KF_EMBED,
+    KF_CONV1D, KF_CONVT, KF_CONV_POST, KF_INTERP, KF_COND, KF_MISC, KF_COUNT
+};
+struct KernelProfiler {
+    bool enabled = false;
+    struct Rec { cudaEvent_t a, b; int fam; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    double ms[KF_COUNT] = {0}, flops[KF_COUNT] = {0}, bytes[KF_COUNT] = {0};
+    unsigned long long launches[KF_COUNT] = {0};
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    void collect() {           // call with the device idle (after a synchronize)
+        for (auto& r : recs) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) ms[r.fam] += t;
+            pool.push_back(r.a); pool.push_back(r.b);
+        }
+        recs.clear();
+    }
+    void reset() { collect(); for (int i = 0; i < KF_COUNT; ++i) { ms[i] = flops[i] = bytes[i] = 0; launches[i] = 0; } }
+};
+extern KernelProfiler g_prof;
+struct ProfScope {
+    cudaStream_t st; cudaEvent_t b; bool on;
+    ProfScope(int fam, cudaStream_t s, double fl = 0, double by = 0) : st(s), b(nullptr), on(g_prof.enabled) {
+        if (!on) return;
+        cudaEvent_t a = g_prof.get(); b = g_prof.get();
+        cudaEventRecord(a, st);
+        g_prof.recs.push_back({a, b, fam});
+        g_prof.flops[fam] += fl; g_prof.bytes[fam] += by; g_prof.launches[fam] += 1;
+    }
+    ~ProfScope() { if (on) cudaEventRecord(b, st); }
+};
+inline const char* kernel_family_name(int f) {
+    static const char* n[KF_COUNT] = {"gemm_bf16_tcgen05", "gemm_f32", "attn_decode_paged", "attn_prefill", "layernorm",
+                                      "sample", "kv_write", "embed", "conv1d", "conv_transpose1d", "conv_post_tanh",
+                                      "interp", "conditioning", "misc"};
+    return (f >= 0 && f < KF_COUNT) ? n[f] : "?";
+}
 
 constexpr int kHeadDim = 64;       // 16 heads x 64 (xttsv2_gpt_config.py:136-138); kernels specialise on it
 constexpr int kPageTokens = 32;    // KV page = one warp of tokens

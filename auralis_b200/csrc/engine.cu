@@ -3,6 +3,7 @@
 // (XTTSv2.py:690-814); every tensor op below it is one of the kernels in this directory.
 #include "../../include/xtts_b200.h"
 #include "kernels.h"
+#include "cond.h"
 
 #include <algorithm>
 #include <atomic>
@@ -108,6 +109,7 @@ public:
     void finalize_weights();
     void set_speaker(int slot, const float* cond, const float* g);
     void get_speaker(int slot, float* cond, float* g);
+    void condition(int slot, const float* w22, int64_t n22, const float* w16, int64_t n16, int cond_len, int chunk_len);
     void submit(uint64_t id, const int32_t* text, int n_text, int speaker, const xtts_sampling& sp);
     int poll(xtts_result* out, int timeout_ms);
     void fetch(uint64_t id, int32_t* tokens, float* wav, float* latents);
@@ -152,6 +154,7 @@ private:
     CondLin cond_layer;
     std::vector<std::unique_ptr<CondLin>> conds;
     uint64_t weight_bytes = 0;
+    std::unique_ptr<Conditioner> conditioner;
 
     // ---- speakers
     DBuf<float> spk_cond, spk_g, spk_cbias;
@@ -213,6 +216,7 @@ private:
         t.spk_cond = spk_cond.p; t.H = H; t.n_cond = cfg.n_cond_latents; return t;
     }
     SampleState sample_state() const;
+    void finish_speaker(int slot);
     void gemm(const void* A, const Linear& lin, const float* resid, void* out, int M, int flags);
     void layers_forward(int M, bool prefill, int nseq, int max_nq);
     void head_and_sample(int M, const int* row_index, const int* slots_dev, const int* lat_pos, int advance_ctx, bool do_sample);
@@ -502,12 +506,15 @@ void Engine::finalize_weights() {
         up(conv_post_w, pw.data);
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
-    // keep only what xtts_condition needs later; drop the big host copies
-    for (auto it = raw.begin(); it != raw.end();) {
-        const std::string& k = it->first;
-        const bool keep = k.rfind("conditioning_", 0) == 0 || k.rfind("hifigan_decoder.speaker_encoder", 0) == 0 || k == "mel_stats";
-        if (!keep) it = raw.erase(it); else ++it;
+    // ---- speaker conditioning stack (optional in a checkpoint: without it only xtts_set_speaker works)
+    if (raw.count("conditioning_encoder.init.weight") && raw.count("hifigan_decoder.speaker_encoder.conv1.weight")) {
+        auto get = [this](const std::string& n) {
+            const HostTensor& t = need(n);
+            return HostTensorView{t.data.data(), t.shape};
+        };
+        conditioner.reset(new Conditioner(cfg, get, st));
     }
+    raw.clear();
     finalized = true;
 }
 
@@ -523,6 +530,10 @@ void Engine::set_speaker(int slot, const float* cond, const float* g) {
     spk_cond.upload(cond, nc, st, (size_t)slot * nc);
     spk_g.upload(g, cfg.d_vector, st, (size_t)slot * cfg.d_vector);
     // speaker-conditioning biases: cond_layer(g), conds[i](g)  (hifigan_decoder.py:244-251)
+    finish_speaker(slot);
+}
+
+void Engine::finish_speaker(int slot) {
     const float* gd = spk_g.p + (size_t)slot * cfg.d_vector;
     float* cb = spk_cbias.p + (size_t)slot * cbias_stride;
     launch_gemv(cond_layer.w.p, cond_layer.b.p, gd, cb + cbias_off[0], cond_layer.rows, cfg.d_vector, st);
@@ -530,6 +541,21 @@ void Engine::set_speaker(int slot, const float* cond, const float* g) {
         launch_gemv(conds[i]->w.p, conds[i]->b.p, gd, cb + cbias_off[i + 1], conds[i]->rows, cfg.d_vector, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
     spk_valid[slot] = 1;
+}
+
+// get_conditioning_latents (XTTSv2.py:409-468) on the GPU
+void Engine::condition(int slot, const float* w22, int64_t n22, const float* w16, int64_t n16, int cond_len, int chunk_len) {
+    std::lock_guard<std::mutex> lk(mu);
+    require_finalized();
+    if (!conditioner) throw std::runtime_error("checkpoint has no conditioning encoder / speaker encoder weights");
+    if (slot < 0 || slot >= S) throw std::runtime_error("speaker slot out of range");
+    if (cfg.spk_proj != cfg.d_vector) throw std::runtime_error("speaker encoder projection != d_vector");
+    CUDA_CHECK(cudaSetDevice(cfg.device));
+    const double t0 = now_s();
+    conditioner->run(w22, n22, w16, n16, cond_len, chunk_len, spk_cond.p + (size_t)slot * cfg.n_cond_latents * H,
+                     spk_g.p + (size_t)slot * cfg.d_vector);
+    finish_speaker(slot);
+    st_cond_ms += (now_s() - t0) * 1e3;
 }
 
 void Engine::get_speaker(int slot, float* cond, float* g) {
@@ -1170,9 +1196,9 @@ int xtts_load_weight(xtts_engine* e, const char* name, const float* data, const 
 int xtts_finalize_weights(xtts_engine* e) { XTTS_TRY(e->impl->finalize_weights()) }
 int xtts_set_speaker(xtts_engine* e, int32_t slot, const float* cond, const float* g) { XTTS_TRY(e->impl->set_speaker(slot, cond, g)) }
 int xtts_get_speaker(xtts_engine* e, int32_t slot, float* cond, float* g) { XTTS_TRY(e->impl->get_speaker(slot, cond, g)) }
-int xtts_condition(xtts_engine*, int32_t, const float*, int64_t, const float*, int64_t, int32_t, int32_t) {
-    xtts::set_error("xtts_condition: conditioning kernels are not built yet (use xtts_set_speaker)");
-    return XTTS_ERR_STATE;
+int xtts_condition(xtts_engine* e, int32_t slot, const float* wav22k, int64_t n22, const float* wav16k, int64_t n16,
+                   int32_t gpt_cond_len_s, int32_t gpt_cond_chunk_len_s) {
+    XTTS_TRY(e->impl->condition(slot, wav22k, n22, wav16k, n16, gpt_cond_len_s, gpt_cond_chunk_len_s))
 }
 int xtts_submit(xtts_engine* e, uint64_t seq_id, const int32_t* text_ids, int32_t n_text, int32_t speaker_slot,
                 const xtts_sampling* sp) {

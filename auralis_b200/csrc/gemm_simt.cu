@@ -7,6 +7,7 @@
 namespace xtts {
 
 unsigned long long g_launch_count = 0;
+KernelProfiler g_prof;
 
 namespace {
 
@@ -110,6 +111,7 @@ void launch_gemm_f32(const float* A, const float* W, const float* bias, const fl
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
     const bool aligned = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    ProfScope ps(KF_GEMM_F32, st, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N));
     if (aligned)
         gemm_f32_nt_kernel<true><<<grid, 256, 0, st>>>(A, W, bias, resid, out, M, N, K, flags);
     else
@@ -122,6 +124,7 @@ void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStrea
     if (n == 0) return;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
+    ProfScope ps(KF_MISC, st, 0, 6.0 * n);
     f32_to_bf16_kernel<<<blocks, 256, 0, st>>>(in, out, n);
     COUNT_LAUNCH();
     KERNEL_CHECK();
@@ -129,6 +132,7 @@ void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStrea
 
 void launch_gemv(const float* W, const float* b, const float* g, float* y, int rows, int cols, cudaStream_t st) {
     const int wpb = 8;
+    ProfScope ps(KF_MISC, st, 2.0 * rows * cols, 4.0 * rows * cols);
     gemv_kernel<<<ceil_div(rows, wpb), wpb * 32, 0, st>>>(W, b, g, y, rows, cols);
     COUNT_LAUNCH();
     KERNEL_CHECK();

@@ -242,6 +242,8 @@ void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias
         attr_set = true;
     }
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+    ProfScope ps(KF_GEMM_TC, st, 2.0 * M * N * K,
+                 2.0 * ((double)M * K + (double)N * K) + ((flags & GEMM_OUT_BF16) ? 2.0 : 4.0) * M * N);
     gemm_bf16_tc_kernel<BN><<<grid, kThreads, smem, st>>>(tmA, tmB, bias, resid, out, M, N, K, flags);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }

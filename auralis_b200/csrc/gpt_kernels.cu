@@ -532,6 +532,7 @@ sample_kernel(const float* __restrict__ logits, int ld, const int* __restrict__ 
 // ================================================================================================
 void launch_build_rows(const RowDesc* rows, int n_rows, GptTables t, float* X, cudaStream_t st) {
     if (n_rows <= 0) return;
+    ProfScope ps(KF_EMBED, st, 0, 12.0 * n_rows * t.H);
     build_rows_kernel<<<n_rows, 256, 0, st>>>(rows, t, X);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
@@ -539,6 +540,7 @@ void launch_build_rows(const RowDesc* rows, int n_rows, GptTables t, float* X, c
 void launch_build_decode_rows(const int* active, int M, const int* last_tok, const int* n_gen, GptTables t,
                               float* X, cudaStream_t st) {
     if (M <= 0) return;
+    ProfScope ps(KF_EMBED, st, 0, 12.0 * M * t.H);
     build_decode_rows_kernel<<<M, 256, 0, st>>>(active, last_tok, n_gen, t, X);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
@@ -547,6 +549,7 @@ template <typename TOut>
 void launch_layernorm(const float* X, const float* w, const float* b, TOut* Y, int M, int H, float eps,
                       cudaStream_t st) {
     if (M <= 0) return;
+    ProfScope ps(KF_NORM, st, 0, (4.0 + sizeof(TOut)) * M * H);
     layernorm_kernel<TOut><<<M, 256, 0, st>>>(X, w, b, Y, H, eps);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
@@ -559,6 +562,7 @@ void launch_head_norms(const float* X, const int* row_index, const float* lnf_w,
                        const int* lat_pos, const int* n_gen, int lat_rows_per_slot, int M, int H, float eps,
                        cudaStream_t st) {
     if (M <= 0) return;
+    ProfScope ps(KF_NORM, st, 0, (8.0 + sizeof(TOut)) * M * H);
     head_norms_kernel<TOut><<<M, 256, H * sizeof(float), st>>>(X, row_index, lnf_w, lnf_b, fn_w, fn_b, Y, latents,
                                                                 slots, lat_pos, n_gen, lat_rows_per_slot, H, eps);
     COUNT_LAUNCH(); KERNEL_CHECK();
@@ -570,6 +574,7 @@ template <typename TKV>
 void launch_kv_write(const float* QKV, int M, const int* row_slot, const int* row_pos, const int* ctx_len,
                      const int* block_tables, int max_pages, TKV* kpool, TKV* vpool, int heads, cudaStream_t st) {
     if (M <= 0) return;
+    ProfScope ps(KF_KV_WRITE, st, 0, (8.0 + 2.0 * sizeof(TKV)) * M * heads * kHeadDim);
     kv_write_kernel<TKV><<<dim3(M, heads), 128, 0, st>>>(QKV, row_slot, row_pos, ctx_len, block_tables, max_pages,
                                                          kpool, vpool, heads);
     COUNT_LAUNCH(); KERNEL_CHECK();
@@ -579,19 +584,24 @@ template void launch_kv_write<__nv_bfloat16>(const float*, int, const int*, cons
 
 template <typename TKV, typename TOut>
 void launch_attn_decode(const float* QKV, const int* active, int M, const int* ctx_len, const int* block_tables,
-                        int max_pages, const TKV* kpool, const TKV* vpool, TOut* out, int heads, cudaStream_t st) {
+                        int max_pages, const TKV* kpool, const TKV* vpool, TOut* out, int heads, cudaStream_t st,
+                        double ctx_sum_hint) {
     if (M <= 0) return;
+    // algorithmic bytes: K and V of every cached token of every sequence, once
+    ProfScope ps(KF_ATTN_DECODE, st, 4.0 * ctx_sum_hint * heads * kHeadDim,
+                 2.0 * ctx_sum_hint * heads * kHeadDim * sizeof(TKV));
     attn_decode_kernel<TKV, TOut><<<dim3(M, heads), 128, 0, st>>>(QKV, active, ctx_len, block_tables, max_pages,
                                                                  kpool, vpool, out, heads);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
-template void launch_attn_decode<float, float>(const float*, const int*, int, const int*, const int*, int, const float*, const float*, float*, int, cudaStream_t);
-template void launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(const float*, const int*, int, const int*, const int*, int, const __nv_bfloat16*, const __nv_bfloat16*, __nv_bfloat16*, int, cudaStream_t);
+template void launch_attn_decode<float, float>(const float*, const int*, int, const int*, const int*, int, const float*, const float*, float*, int, cudaStream_t, double);
+template void launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(const float*, const int*, int, const int*, const int*, int, const __nv_bfloat16*, const __nv_bfloat16*, __nv_bfloat16*, int, cudaStream_t, double);
 
 template <typename TOut>
 void launch_attn_generic(AttnLayout L, const AttnSeq* seqs, int nseq, int max_nq, TOut* out, int out_row_stride,
                          cudaStream_t st) {
     if (nseq <= 0 || max_nq <= 0) return;
+    ProfScope ps(KF_ATTN_PREFILL, st);
     attn_generic_kernel<TOut><<<dim3(ceil_div(max_nq, AQ), L.heads, nseq), 128, 0, st>>>(L, seqs, out, out_row_stride);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
@@ -602,6 +612,7 @@ void launch_sample(const float* logits, int ld_logits, const int* active, int M,
                    int advance_ctx, cudaStream_t st) {
     if (M <= 0) return;
     if (V > SV) throw CudaError("sample: vocabulary larger than 2048 is not supported");
+    ProfScope ps(KF_SAMPLE, st, 0, 4.0 * M * V);
     sample_kernel<<<M, 256, 0, st>>>(logits, ld_logits, active, V, s, advance_ctx);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }

@@ -70,7 +70,7 @@ void launch_kv_write(const float* QKV, int M, const int* row_slot, const int* ro
 template <typename TKV, typename TOut>
 void launch_attn_decode(const float* QKV, const int* active, int M, const int* ctx_len,
                         const int* block_tables, int max_pages, const TKV* kpool, const TKV* vpool,
-                        TOut* out, int heads, cudaStream_t st);
+                        TOut* out, int heads, cudaStream_t st, double ctx_sum_hint = 0);
 
 struct AttnSeq { int q_start, nq, kv_start, nk; };
 struct AttnLayout {

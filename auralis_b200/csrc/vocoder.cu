@@ -244,6 +244,9 @@ void conv1d_dispatch(const float* x, const float* w_t, const float* bias, const 
     const int halo = (K - 1) / 2 * dil;
     const int XW = CT_T + 2 * halo;
     const int xs_f = CT_CI * XW + ((4 - (CT_CI * XW) % 4) % 4);
+    // algorithmic traffic: read x once, write out once (+ residual / accumulate reads), weights once
+    ProfScope ps(KF_CONV1D, st, 2.0 * Cin * Cout * K * (double)L,
+                 4.0 * ((double)L * (Cin + Cout * (1 + (resid ? 1 : 0) + (mode == CONV_ACCUM ? 1 : 0))) + (double)Cin * Cout * K));
     if (Cout > 32) {
         constexpr int NTY = 8;
         const size_t smem = (size_t)(xs_f + CT_CI * K * CT_TC * NTY) * sizeof(float);
@@ -265,6 +268,7 @@ void conv1d_dispatch(const float* x, const float* w_t, const float* bias, const 
 void launch_interp(const float* latents, float* z, int T, int C, int T1, int Tz, double scale1, double scale2,
                    cudaStream_t st) {
     const float r1 = (float)(1.0 / scale1), r2 = (float)(1.0 / scale2);
+    ProfScope ps(KF_INTERP, st, 0, 4.0 * C * ((double)T + Tz));
     interp_kernel<<<dim3(ceil_div(Tz, 32), ceil_div(C, 32)), dim3(32, 8), 0, st>>>(latents, z, T, C, T1, Tz, r1, r2);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
@@ -289,12 +293,14 @@ void launch_conv_transpose1d(const float* x, const float* w_t, const float* bias
     const int XS = UP_T / u + 3;
     const size_t smem = (size_t)(((UP_CI * XS + 3) / 4) * 4 + UP_CI * K * (UP_CO + 4)) * sizeof(float);
     dim3 grid(ceil_div(Lin * u, UP_T), ceil_div(Cout, UP_CO));
+    ProfScope ps(KF_CONVT, st, 4.0 * Cin * Cout * (double)Lin * u, 4.0 * ((double)Lin * Cin + (double)Lin * u * Cout + (double)Cin * Cout * K));
     conv_transpose1d_kernel<<<grid, UP_T, smem, st>>>(x, w_t, bias, cbias, out, Cin, Cout, Lin, K, u, in_scale, slope);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 
 void launch_conv_post(const float* x, const float* w, float* wav, int Cin, int L, int K, float in_scale, float slope,
                       cudaStream_t st) {
+    ProfScope ps(KF_CONV_POST, st, 2.0 * Cin * K * (double)L, 4.0 * (double)L * (Cin + 1));
     conv_post_kernel<<<ceil_div(L, 256), 256, Cin * K * sizeof(float), st>>>(x, w, wav, Cin, L, K, in_scale, slope);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }

@@ -1,0 +1,299 @@
+"""XTTSv2Engine — the reference's engine plugin (`/root/reference/src/auralis/models/xttsv2/XTTSv2.py`)
+re-hosted on the native B200 library.  Same public methods, argument meaning and error behaviour:
+
+* ``from_pretrained(path, gpt_model=..., max_concurrency=...)``            XTTSv2.py:235-310
+* ``await get_audio_conditioning(speaker_files, ...) -> (cond, g)``         XTTSv2.py:579-615
+* ``await get_generation_context(request, gpt_cond_latent, speaker_embeddings)
+      -> (generators, request_ids, speaker_embeddings, gpt_embed_inputs)``   XTTSv2.py:690-760
+* ``process_tokens_to_speech(generator, speaker_embeddings, multimodal_data, request)``  XTTSv2.py:762-814
+* ``await shutdown()``                                                       XTTSv2.py:818
+
+What is different underneath (SURVEY.md App. B "diverge" items): no vLLM, no second GPT pass (latents are
+captured during decode), no semaphore/sleep around the vocoder, per-sequence position counters.  All
+tensor work happens in ``libxtts_b200.so``; this file only tokenises, submits and awaits completions.
+"""
+from __future__ import annotations
+
+import asyncio
+import hashlib
+import threading
+import time
+import wave
+from pathlib import Path
+from typing import AsyncGenerator, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+
+from . import native
+from .base import BaseAsyncTTSEngine, ConditioningConfig, register_model
+from .config import XTTSDims
+from .output import TTSOutput
+from .requests import TTSRequest
+from .text import XTTSTokenizer
+from .weights import load_model_dir
+
+
+class ChunkOutput:
+    """What the reference reads off vLLM's RequestOutput (XTTSv2.py:785-799): finished flag + token ids."""
+
+    def __init__(self, request_id: str, token_ids, wav, result):
+        self.request_id = request_id
+        self.finished = True
+        self.token_ids = list(token_ids)
+        self.wav = wav
+        self.result = result
+
+
+def load_audio(source: Union[str, Path, bytes], sampling_rate: int) -> np.ndarray:
+    """Mono float32 in [-1,1] at `sampling_rate` (common/utilities.py:74-97).  RIFF/WAV via the standard
+    library (torchaudio.load needs torchcodec, absent here), polyphase resampling via scipy."""
+    import io
+    from math import gcd
+    f = io.BytesIO(source) if isinstance(source, (bytes, bytearray)) else str(source)
+    with wave.open(f, "rb") as w:
+        nch, sw, sr, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
+        raw = w.readframes(n)
+    if sw == 2:
+        a = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+    elif sw == 4:
+        a = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
+    elif sw == 1:
+        a = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+    else:
+        raise ValueError(f"unsupported WAV sample width {sw}")
+    a = a.reshape(-1, nch).mean(axis=1)
+    if sr != sampling_rate:
+        from scipy.signal import resample_poly
+        g = gcd(int(sr), int(sampling_rate))
+        a = resample_poly(a, sampling_rate // g, sr // g).astype(np.float32)
+    return np.clip(a, -1.0, 1.0).astype(np.float32)
+
+
+class XTTSv2Engine(BaseAsyncTTSEngine):
+    model_type = "xtts"
+
+    def __init__(self, dims: XTTSDims, gpt_state, core_state, *, device: int = 0, precision: str = "bf16",
+                 max_concurrency: int = 64, max_speakers: int = 32, tokenizer_file: Optional[str] = None, **_):
+        prec = {"fp32": native.PRECISION_FP32, "bf16": native.PRECISION_BF16}[precision]
+        self.dims = dims
+        self.precision = precision
+        self.max_concurrency = max_concurrency
+        self.native = native.NativeEngine(dims, device=device, precision=prec, max_batch=max_concurrency,
+                                          max_speakers=max_speakers)
+        self.native.load_state(gpt_state, core_state)
+        self.tokenizer = XTTSTokenizer(dims.gpt.n_text_tokens, dims.gpt.max_text_tokens, tokenizer_file)
+        self.mel_bos_token_id = dims.gpt.start_audio_token
+        self.mel_eos_token_id = dims.gpt.stop_audio_token
+        self.max_speakers = max_speakers
+        self._spk_slots: Dict[str, int] = {}
+        self._spk_lru: List[str] = []
+        self._spk_lock = threading.Lock()
+        self._next_id = 1
+        self._id_lock = threading.Lock()
+        self._waiters: Dict[int, Tuple[asyncio.AbstractEventLoop, asyncio.Future]] = {}
+        self._wlock = threading.Lock()
+        self._stop = False
+        self._poller = threading.Thread(target=self._poll_loop, name="xtts-poll", daemon=True)
+        self._poller.start()
+
+    # ---- plugin API -------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, gpt_model: Optional[str] = None, **kwargs):
+        dims, gpt_state, core_state = load_model_dir(pretrained_model_name_or_path, gpt_model)
+        import os
+        gdir = gpt_model if gpt_model and os.path.isdir(gpt_model) else os.path.join(pretrained_model_name_or_path, "gpt")
+        tok = os.path.join(gdir, "tokenizer.json")
+        return cls(dims, gpt_state, core_state, tokenizer_file=tok if os.path.exists(tok) else None, **kwargs)
+
+    @property
+    def conditioning_config(self) -> ConditioningConfig:
+        return ConditioningConfig(speaker_embeddings=True, gpt_like_decoder_conditioning=True)
+
+    def _alloc_speaker_slot(self, key: str) -> Tuple[int, bool]:
+        with self._spk_lock:
+            if key in self._spk_slots:
+                self._spk_lru.remove(key); self._spk_lru.append(key)
+                return self._spk_slots[key], True
+            if len(self._spk_slots) < self.max_speakers:
+                slot = len(self._spk_slots)
+            else:
+                victim = self._spk_lru.pop(0)
+                slot = self._spk_slots.pop(victim)
+            self._spk_slots[key] = slot
+            self._spk_lru.append(key)
+            return slot, False
+
+    async def get_audio_conditioning(self, audio_reference, max_ref_length=30, gpt_cond_len=6, gpt_cond_chunk_len=6,
+                                     librosa_trim_db=None, sound_norm_refs=False, load_sr=22050):
+        """XTTSv2.py:409-468,579-615: -> (gpt_cond_latents [1,32,H], speaker_embedding [1,d,1]) computed on the GPU
+        by ``xtts_condition`` and cached per reference (the per-speaker cache of SURVEY §3.4)."""
+        if not isinstance(audio_reference, (bytes, str, Path, list)):
+            raise AssertionError(f"audio_reference must be a string, byte or a list but it is {type(audio_reference)}")
+        paths = audio_reference if isinstance(audio_reference, list) else [audio_reference]
+        hk = hashlib.sha256()
+        for p in paths:
+            hk.update(p if isinstance(p, (bytes, bytearray)) else str(p).encode())
+        hk.update(f"{max_ref_length}|{gpt_cond_len}|{gpt_cond_chunk_len}|{sound_norm_refs}".encode())
+        key = hk.hexdigest()
+        slot, hit = self._alloc_speaker_slot(key)
+        if not hit:
+            def work():
+                audios22 = []
+                for p in paths:
+                    a = load_audio(p, load_sr)[: load_sr * max_ref_length]
+                    if sound_norm_refs:
+                        a = (a / np.abs(a).max()) * 0.75
+                    audios22.append(a)
+                if len(audios22) == 1:
+                    self.native.condition(slot, audios22[0], _resample(audios22[0], load_sr, 16000), gpt_cond_len,
+                                          gpt_cond_chunk_len)
+                    return
+                # several references: d-vector per file, averaged; GPT latents on the concatenation
+                # (XTTSv2.py:446-466)
+                gs = []
+                for a in audios22:
+                    self.native.condition(slot, a, _resample(a, load_sr, 16000), gpt_cond_len, gpt_cond_chunk_len)
+                    gs.append(self.native.get_speaker(slot)[1])
+                full = np.concatenate(audios22)
+                self.native.condition(slot, full, _resample(audios22[0], load_sr, 16000), gpt_cond_len, gpt_cond_chunk_len)
+                c, _ = self.native.get_speaker(slot)
+                self.native.set_speaker(slot, c, np.mean(np.stack(gs), axis=0))
+            await asyncio.to_thread(work)
+        cond, g = self.native.get_speaker(slot)
+        return _SpeakerArray(cond[None], slot), _SpeakerArray(g.reshape(1, -1, 1), slot)
+
+    def register_speaker(self, cond_latents: np.ndarray, d_vector: np.ndarray) -> Tuple["_SpeakerArray", "_SpeakerArray"]:
+        """Pre-computed conditioning (the pair `prepare_for_streaming_generation` hands back, tts.py:91-105)."""
+        c = np.ascontiguousarray(cond_latents, np.float32).reshape(self.dims.gpt.n_cond_latents, self.dims.gpt.hidden)
+        g = np.ascontiguousarray(d_vector, np.float32).reshape(-1)
+        key = hashlib.sha256(c.tobytes() + g.tobytes()).hexdigest()
+        slot, hit = self._alloc_speaker_slot(key)
+        if not hit:
+            self.native.set_speaker(slot, c, g)
+        return _SpeakerArray(c[None], slot), _SpeakerArray(g.reshape(1, -1, 1), slot)
+
+    def _slot_of(self, cond, g) -> int:
+        if isinstance(cond, _SpeakerArray):
+            return cond.slot
+        return self.register_speaker(np.asarray(cond), np.asarray(g))[0].slot
+
+    def prepare_text_tokens(self, text: str, language: str) -> List[List[int]]:
+        """XTTSv2.py:506-543: per chunk [bos] + ids + [eos]."""
+        chunks = self.tokenizer.batch_encode_with_split(text, language)
+        return [[self.tokenizer.bos_token_id] + ids + [self.tokenizer.eos_token_id] for ids in chunks]
+
+    async def get_generation_context(self, request: TTSRequest, gpt_cond_latent=None, speaker_embeddings=None):
+        if gpt_cond_latent is None or speaker_embeddings is None:
+            gpt_cond_latent, speaker_embeddings = await self.get_audio_conditioning(
+                request.speaker_files, request.max_ref_length, request.gpt_cond_len, request.gpt_cond_chunk_len)
+        slot = self._slot_of(gpt_cond_latent, speaker_embeddings)
+        token_lists = self.prepare_text_tokens(request.text, request.language)
+        generators, request_ids = [], []
+        base_seed = request.seed if request.seed is not None else int.from_bytes(hashlib.sha256(request.request_id.encode()).digest()[:6], "little")
+        for seq_index, ids in enumerate(token_lists):
+            sp = native.Sampling(temperature=request.temperature, top_p=request.top_p, top_k=request.top_k,
+                                 repetition_penalty=request.repetition_penalty,
+                                 max_tokens=self.dims.gpt.max_audio_tokens, stop_token=self.mel_eos_token_id,
+                                 seed=base_seed, seq_seed=seq_index, vocode=True)
+            rid = f"{request.request_id}_{seq_index}"
+            generators.append(self._chunk_generator(rid, ids, slot, sp))
+            request_ids.append(rid)
+        return generators, request_ids, speaker_embeddings, [gpt_cond_latent] * len(generators)
+
+    async def _chunk_generator(self, rid: str, ids: List[int], slot: int, sp: native.Sampling):
+        """Lazy like vLLM's generator (App. B.15): the chunk is submitted at the first __anext__."""
+        loop = asyncio.get_running_loop()
+        fut = loop.create_future()
+        with self._id_lock:
+            sid = self._next_id
+            self._next_id += 1
+        with self._wlock:
+            self._waiters[sid] = (loop, fut)
+        try:
+            self.native.submit(sid, ids, slot, sp)
+        except Exception:
+            with self._wlock:
+                self._waiters.pop(sid, None)
+            raise
+        result, toks, wav = await fut
+        yield ChunkOutput(rid, toks, wav, result)
+
+    async def process_tokens_to_speech(self, generator, speaker_embeddings=None, multimodal_data=None,
+                                       request: TTSRequest = None) -> AsyncGenerator[TTSOutput, None]:
+        assert speaker_embeddings is not None, "Speaker embeddings must be provided for speech generation with XTTSv2."
+        assert multimodal_data is not None, "Multimodal data must be provided for speech generation with XTTSv2."
+        async for output in generator:
+            if output.finished:
+                yield TTSOutput(array=output.wav, start_time=request.start_time if request else None,
+                                token_length=len(output.token_ids))
+
+    async def shutdown(self):
+        self._stop = True
+        self._poller.join(timeout=5)
+        self.native.close()
+
+    # ---- completion dispatch ----------------------------------------------------------------
+    def _poll_loop(self):
+        while not self._stop:
+            try:
+                r = self.native.poll(200)
+            except Exception:
+                if self._stop:
+                    return
+                time.sleep(0.05)
+                continue
+            if r is None:
+                continue
+            with self._wlock:
+                w = self._waiters.pop(r.seq_id, None)
+            try:
+                if r.status != 0:
+                    raise native.NativeError(f"chunk {r.seq_id} failed ({r.status}): "
+                                             f"{self.native.lib.xtts_last_error().decode()}")
+                toks, wav, _ = self.native.fetch(r, want_wav=True)
+                payload, err = (r, toks, wav), None
+            except Exception as e:      # noqa: BLE001 — forwarded to the awaiting coroutine
+                payload, err = None, e
+            if w is None:
+                continue
+            loop, fut = w
+
+            def deliver(fut=fut, payload=payload, err=err):
+                if fut.cancelled():
+                    return
+                if err is not None:
+                    fut.set_exception(err)
+                else:
+                    fut.set_result(payload)
+            loop.call_soon_threadsafe(deliver)
+
+
+class _SpeakerArray(np.ndarray):
+    """numpy array that remembers which native speaker slot it lives in."""
+
+    def __new__(cls, arr, slot):
+        obj = np.asarray(arr).view(cls)
+        obj.slot = slot
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.slot = getattr(obj, "slot", None)
+
+
+def _resample(a: np.ndarray, sr: int, new_sr: int) -> np.ndarray:
+    """torchaudio.functional.resample (the reference's resampler, XTTSv2.py:323,360) when importable,
+    scipy polyphase otherwise.  Host-side preprocessing of the reference wav, not part of the hot path."""
+    if sr == new_sr:
+        return a
+    try:
+        import torch
+        import torchaudio
+        return torchaudio.functional.resample(torch.from_numpy(np.ascontiguousarray(a)), sr, new_sr).numpy()
+    except Exception:
+        from math import gcd
+        from scipy.signal import resample_poly
+        g = gcd(sr, new_sr)
+        return resample_poly(a, new_sr // g, sr // g).astype(np.float32)
+
+
+register_model("xtts", XTTSv2Engine)

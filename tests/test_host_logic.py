@@ -1,0 +1,143 @@
+"""CPU: host-side mirror of the reference interface — TTSRequest/TTSOutput, text splitting, scheduler ordering,
+timeouts and error propagation, and the TTS façade driven by a fake engine (no GPU)."""
+import asyncio
+import time
+
+import numpy as np
+import pytest
+
+from auralis_b200 import TTS, TTSOutput, TTSRequest
+from auralis_b200.base import BaseAsyncTTSEngine, ConditioningConfig
+from auralis_b200.scheduler import TwoPhaseScheduler
+from auralis_b200.text import XTTSTokenizer, find_best_split_point, split_sentence
+
+
+def test_request_defaults_match_reference():
+    r = TTSRequest(text="hi", speaker_files=["a.wav"], language="en")
+    assert (r.temperature, r.top_p, r.top_k, r.repetition_penalty) == (0.75, 0.85, 50, 5.0)     # requests.py:185-188
+    assert (r.max_ref_length, r.gpt_cond_len, r.gpt_cond_chunk_len, r.load_sample_rate) == (60, 30, 4, 22050)
+    assert r.stream is False and r.enhance_speech is False and len(r.request_id) == 32
+    c = r.copy()
+    assert c.text == r.text and c.request_id == r.request_id
+    with pytest.raises(ValueError):
+        TTSRequest(text="hi", speaker_files=["a.wav"], language="xx")
+
+
+def test_output_combine_and_bytes():
+    a = TTSOutput(array=np.ones(10, np.float32) * 0.5, token_length=3)
+    b = TTSOutput(array=np.zeros(5, np.float32))
+    c = TTSOutput.combine_outputs([a, b])
+    assert c.array.shape == (15,) and c.sample_rate == 24000
+    assert len(c.to_bytes("pcm")) == 30 and c.to_bytes("wav")[:4] == b"RIFF"
+    pcm = (np.arange(200, dtype=np.int16) * 100).tobytes()
+    d = TTSOutput(array=pcm)                                   # bytes input: int16 -> float, 100-sample fade-in
+    assert d.array.dtype == np.float32 and d.array[0] == 0.0
+    assert c.resample(12000).array.shape[0] in (7, 8)
+
+
+def test_split_sentence_rules():
+    assert split_sentence("short text.", "en", 250) == ["short text."]
+    t = ("This is a sentence of some length that keeps going. " * 12).strip()
+    chunks = split_sentence(t, "en", 250)
+    assert all(len(c) <= 250 for c in chunks) and len(chunks) >= 3
+    assert all(not c.endswith(".") for c in chunks)           # trailing '.' -> ' ' (tokenizer.py:234)
+    long_one = "word " * 120                                    # one 600-char "sentence": split at whitespace
+    chunks = split_sentence(long_one, "en", 250)
+    assert all(len(c) <= 250 for c in chunks) and "".join(c.replace(" ", "") for c in chunks) == "word" * 120
+    assert find_best_split_point("aaa, bbb ccc", 5, 30) == 5   # the comma+space ends exactly at the target
+
+
+def test_tokenizer_synthetic_is_deterministic_and_bounded():
+    tok = XTTSTokenizer(6681, 402)
+    a = tok.batch_encode_with_split("Hello there. " * 40, "en")
+    b = tok.batch_encode_with_split("Hello there. " * 40, "en")
+    assert a == b and len(a) >= 2
+    assert all(0 <= i < 6681 for c in a for i in c) and all(len(c) <= 402 for c in a)
+    assert tok.batch_encode_with_split("こんにちは。" * 30, "ja") != []      # ja limit = 71 chars
+
+
+class FakeEngine(BaseAsyncTTSEngine):
+    """Yields a waveform whose values encode (chunk index) after a delay that is LONGER for earlier chunks."""
+
+    def __init__(self, fail_at=None, delay=0.02):
+        self.fail_at, self.delay, self.started = fail_at, delay, []
+
+    @property
+    def conditioning_config(self):
+        return ConditioningConfig(True, True)
+
+    async def get_audio_conditioning(self, speaker_files, *a, **k):
+        return np.zeros((1, 32, 8), np.float32), np.zeros((1, 4, 1), np.float32)
+
+    async def get_generation_context(self, request, gpt_cond_latent=None, speaker_embeddings=None):
+        n = max(1, len(request.text) // 10)
+
+        async def gen(i):
+            self.started.append(i)
+            await asyncio.sleep(self.delay * (n - i))
+            if self.fail_at == i:
+                raise RuntimeError(f"chunk {i} exploded")
+            yield i
+        return [gen(i) for i in range(n)], [f"r_{i}" for i in range(n)], np.zeros((1, 4, 1)), [np.zeros(1)] * n
+
+    async def process_tokens_to_speech(self, generator, speaker_embeddings, multimodal_data=None, request=None):
+        async for i in generator:
+            yield TTSOutput(array=np.full(4, float(i), np.float32), token_length=1, start_time=request.start_time)
+
+
+def test_generate_speech_orders_chunks_and_concatenates():
+    tts = TTS(scheduler_max_concurrency=8).from_engine(FakeEngine())
+    out = tts.generate_speech(TTSRequest(text="x" * 55, speaker_files=["s.wav"], language="en"))
+    np.testing.assert_array_equal(out.array, np.repeat(np.arange(5, dtype=np.float32), 4))
+
+
+def test_streaming_yields_in_order():
+    tts = TTS(scheduler_max_concurrency=8).from_engine(FakeEngine())
+    req = TTSRequest(text="x" * 40, speaker_files=["s.wav"], language="en", stream=True)
+    got = [int(c.array[0]) for c in tts.generate_speech(req)]
+    assert got == [0, 1, 2, 3]
+
+
+def test_async_and_batch_api():
+    tts = TTS(scheduler_max_concurrency=4).from_engine(FakeEngine(delay=0.005))
+    reqs = [TTSRequest(text="y" * (10 * (i + 1)), speaker_files=["s.wav"], language="en") for i in range(4)]
+    outs = tts.generate_speech_batch(reqs)
+    assert [o.array.shape[0] for o in outs] == [4, 8, 12, 16]
+
+    async def stream():
+        r = TTSRequest(text="z" * 30, speaker_files=["s.wav"], language="en", stream=True)
+        return [int(c.array[0]) async for c in await tts.generate_speech_async(r)]
+    assert tts.loop.run_until_complete(stream()) == [0, 1, 2]
+
+
+def test_failed_chunk_fails_the_request():
+    tts = TTS().from_engine(FakeEngine(fail_at=1))
+    with pytest.raises(RuntimeError, match="chunk 1 exploded"):
+        tts.generate_speech(TTSRequest(text="x" * 30, speaker_files=["s.wav"], language="en"))
+
+
+def test_concurrency_limit_and_timeouts():
+    eng = FakeEngine(delay=0.03)
+    tts = TTS(scheduler_max_concurrency=2).from_engine(eng)
+    tts.generate_speech(TTSRequest(text="x" * 40, speaker_files=["s.wav"], language="en"))
+    assert eng.started[:2] == [0, 1]                            # lazily started, two at a time (App. B.15)
+    sch = TwoPhaseScheduler(2, request_timeout=0.05)
+
+    async def slow_first(_):
+        await asyncio.sleep(1.0)
+
+    async def run():
+        async for _ in sch.run(None, "r", slow_first, None):
+            pass
+    with pytest.raises(TimeoutError):
+        asyncio.new_event_loop().run_until_complete(run())
+
+
+def test_split_requests_and_prepared_speaker():
+    r = TTSRequest(text="a" * 250, speaker_files=["s.wav"], language="en")
+    parts = TTS.split_requests(r, max_length=100)
+    assert [len(p.text) for p in parts] == [100, 100, 50] and len({p.request_id for p in parts}) == 3
+    tts = TTS().from_engine(FakeEngine(delay=0.001))
+    fn = tts.loop.run_until_complete(tts.prepare_for_streaming_generation(r))
+    r2 = TTSRequest(text="b" * 20, speaker_files=["s.wav"], language="en", context_partial_function=fn)
+    assert tts.generate_speech(r2).array.shape == (8,)
