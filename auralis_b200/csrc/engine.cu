@@ -87,6 +87,7 @@ struct Sequence {
     xtts_sampling sp{};
     int slot = -1;
     int n_prompt = 0;
+    int steps = 0;                // decode steps issued so far (host-side mirror of n_gen - 1)
     std::vector<int> pages;
     double t_submit = 0, t_first = 0, t_done = 0;
     // results
@@ -116,6 +117,7 @@ public:
     void set_option(const std::string& k, int64_t v);
     void get_stats(xtts_stats* s);
     void sync_idle();
+    void kernel_profile(xtts_kernel_profile* out);
 
     void vocode_sync(const float* latents, int T, int speaker, float* wav, int* n_out, const char* stage,
                      float* stage_out, int64_t stage_cap);
@@ -138,7 +140,7 @@ private:
 
     // ---- weights
     std::map<std::string, HostTensor> raw;
-    bool finalized = false;
+    std::atomic<bool> finalized{false};
     DBuf<float> text_emb, text_pos, wte, wpe;
     struct Layer { DBuf<float> ln1w, ln1b, ln2w, ln2b; Linear qkv, o, fc, proj; };
     std::vector<std::unique_ptr<Layer>> layers;
@@ -188,9 +190,14 @@ private:
     std::vector<int> stage_ch;
 
     // ---- scheduler
-    std::mutex mu;                      // protects queues + all GPU work issue
+    // Two locks so that submit/poll never wait behind a GPU step:
+    //   q_mu   — pending / done queues, inflight counter (short critical sections)
+    //   mu     — all GPU state and work issue: held by the scheduler thread for one iteration at a time and by
+    //            the synchronous entry points (weights, speakers, debug calls)
+    std::mutex mu, q_mu, pin_mu;
     std::condition_variable cv_work, cv_done;
-    std::deque<std::shared_ptr<Sequence>> pending;
+    std::deque<std::shared_ptr<Sequence>> pending;      // q_mu
+    std::deque<std::shared_ptr<Sequence>> waiting;      // scheduler thread only: accepted, not yet admitted
     std::vector<std::shared_ptr<Sequence>> running;     // index = position in active list
     std::vector<int> free_slots;
     std::deque<std::shared_ptr<Sequence>> done_q;
@@ -201,6 +208,7 @@ private:
     bool d2h_wav = true;
     std::vector<std::pair<float*, size_t>> pinned_pool;
     // stats
+    double decode_ctx_sum = 0;
     uint64_t st_decode_steps = 0, st_prefill_rows = 0, st_tokens = 0, st_samples = 0;
     double st_gpt_ms = 0, st_voc_ms = 0, st_cond_ms = 0;
     unsigned long long launch_base = 0;
@@ -229,6 +237,7 @@ private:
     void run_vocoder(const float* lat_dev, int T, int speaker, float* wav_dev_out, int* n_out, const char* stage,
                      float* stage_out, int64_t stage_cap);
     void finish_sequence(std::shared_ptr<Sequence> s);
+    void retire(std::shared_ptr<Sequence> s);
     float* pinned_get(size_t n, size_t* cap);
     void pinned_put(float* p, size_t cap);
     void loop();
@@ -340,7 +349,7 @@ Engine::Engine(const xtts_config& c) : cfg(c) {
 
 Engine::~Engine() {
     {
-        std::lock_guard<std::mutex> lk(mu);
+        std::lock_guard<std::mutex> lk(q_mu);
         stop = true;
     }
     cv_work.notify_all();
@@ -613,10 +622,10 @@ void Engine::layers_forward(int M, bool prefill, int nseq, int max_nq) {
         } else {
             if (bf16) {
                 launch_kv_write<__nv_bfloat16>(wQKV.p, M, d_active.p, nullptr, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p, NH, st);
-                launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p, wATT16.p, NH, st);
+                launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p, wATT16.p, NH, st, decode_ctx_sum);
             } else {
                 launch_kv_write<float>(wQKV.p, M, d_active.p, nullptr, d_ctx_len.p, d_block_tables.p, max_pages, k32[l]->p, v32[l]->p, NH, st);
-                launch_attn_decode<float, float>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, k32[l]->p, v32[l]->p, wATT32.p, NH, st);
+                launch_attn_decode<float, float>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, k32[l]->p, v32[l]->p, wATT32.p, NH, st, decode_ctx_sum);
             }
         }
         gemm(ATT, ly.o, wX.p, wX.p, M, GEMM_RESID);
@@ -805,6 +814,7 @@ void Engine::run_vocoder(const float* lat_dev, int T, int speaker, float* wav_de
 // scheduler
 // ================================================================================================
 float* Engine::pinned_get(size_t n, size_t* cap) {
+    std::lock_guard<std::mutex> lk(pin_mu);
     for (size_t i = 0; i < pinned_pool.size(); ++i)
         if (pinned_pool[i].second >= n) {
             float* p = pinned_pool[i].first; *cap = pinned_pool[i].second;
@@ -816,17 +826,17 @@ float* Engine::pinned_get(size_t n, size_t* cap) {
     *cap = n;
     return p;
 }
-void Engine::pinned_put(float* p, size_t cap) { pinned_pool.emplace_back(p, cap); }
+void Engine::pinned_put(float* p, size_t cap) { std::lock_guard<std::mutex> lk(pin_mu); pinned_pool.emplace_back(p, cap); }
 
 void Engine::submit(uint64_t id, const int32_t* text, int n_text, int speaker, const xtts_sampling& sp) {
     if (n_text <= 0 || n_text > cfg.max_text_tokens + 2) throw std::runtime_error("n_text out of range (1..max_text_tokens+2)");
     if (speaker < 0 || speaker >= S) throw std::runtime_error("speaker slot out of range");
     std::shared_ptr<Sequence> s(new Sequence());
     s->id = id; s->text_ids.assign(text, text + n_text); s->speaker = speaker; s->sp = sp; s->t_submit = now_s();
+    require_finalized();
+    if (!spk_valid[speaker]) throw std::runtime_error("speaker slot not set");
     {
-        std::lock_guard<std::mutex> lk(mu);
-        require_finalized();
-        if (!spk_valid[speaker]) throw std::runtime_error("speaker slot not set");
+        std::lock_guard<std::mutex> lk(q_mu);
         pending.push_back(s);
         ++inflight;
     }
@@ -865,34 +875,50 @@ void Engine::finish_sequence(std::shared_ptr<Sequence> s) {
     }
     s->t_done = now_s();
     release_slot(*s);
-    done_q.push_back(s);
-    done_map[s->id] = s;
-    --inflight;
+    retire(s);
+}
+
+void Engine::retire(std::shared_ptr<Sequence> s) {
+    {
+        std::lock_guard<std::mutex> lk(q_mu);
+        done_q.push_back(s);
+        done_map[s->id] = s;
+        --inflight;
+    }
+    cv_done.notify_all();
 }
 
 void Engine::loop() {
     cudaSetDevice(cfg.device);
-    std::unique_lock<std::mutex> lk(mu);
     while (true) {
-        cv_work.wait(lk, [&] { return stop.load() || !pending.empty() || !running.empty(); });
-        if (stop.load()) break;
+        {
+            std::unique_lock<std::mutex> q(q_mu);
+            cv_work.wait(q, [&] { return stop.load() || !pending.empty() || !waiting.empty() || !running.empty(); });
+            if (stop.load()) break;
+            while (!pending.empty()) { waiting.push_back(pending.front()); pending.pop_front(); }
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        auto fail = [&](std::shared_ptr<Sequence>& s, int code, const char* what) {
+            s->status = code; set_error(what);
+            release_slot(*s); s->t_done = now_s();
+            retire(s);
+        };
         try {
             // ---- admission (continuous batching): fill free slots, whole prompts, within the row budget
             std::vector<Sequence*> fresh;
             std::vector<std::shared_ptr<Sequence>> fresh_sp;
             int rows = 0;
-            while (!pending.empty() && !free_slots.empty()) {
-                auto s = pending.front();
+            while (!waiting.empty() && !free_slots.empty()) {
+                auto s = waiting.front();
                 const int p = cfg.n_cond_latents + (int)s->text_ids.size() + 1;
                 if (!fresh.empty() && rows + p > prefill_rows_cap) break;
-                pending.pop_front();
+                waiting.pop_front();
                 s->slot = free_slots.back(); free_slots.pop_back();
                 try {
+                    if (!spk_valid[s->speaker]) throw std::runtime_error("speaker slot not set");
                     init_slot(*s, nullptr, 0);
                 } catch (const std::exception& ex) {
-                    s->status = XTTS_ERR_STATE; set_error(ex.what());
-                    release_slot(*s); s->t_done = now_s();
-                    done_q.push_back(s); done_map[s->id] = s; --inflight;
+                    fail(s, XTTS_ERR_STATE, ex.what());
                     continue;
                 }
                 rows += p;
@@ -908,8 +934,10 @@ void Engine::loop() {
             }
             if (!running.empty()) {
                 std::vector<int> active;
-                for (auto& s : running) if (!h_finished[s->slot]) active.push_back(s->slot);
+                double ctx_sum = 0;
+                for (auto& s : running) if (!h_finished[s->slot]) { active.push_back(s->slot); ctx_sum += s->n_prompt + s->steps + 1; ++s->steps; }
                 if (!active.empty()) {
+                    decode_ctx_sum = ctx_sum;
                     decode_step(active);
                     d_finished.download(h_finished, NSLOT, st);
                     CUDA_CHECK(cudaStreamSynchronize(st));
@@ -922,33 +950,18 @@ void Engine::loop() {
             running.swap(keep);
             for (auto& s : fin) {
                 try { finish_sequence(s); }
-                catch (const std::exception& ex) {
-                    s->status = XTTS_ERR_CUDA; set_error(ex.what());
-                    release_slot(*s); s->t_done = now_s();
-                    done_q.push_back(s); done_map[s->id] = s; --inflight;
-                }
+                catch (const std::exception& ex) { fail(s, XTTS_ERR_CUDA, ex.what()); }
             }
-            if (!fin.empty()) cv_done.notify_all();
         } catch (const std::exception& ex) {
             // a failure inside a batched step fails every sequence that was part of it
-            set_error(ex.what());
-            for (auto& s : running) {
-                s->status = XTTS_ERR_CUDA; s->t_done = now_s();
-                release_slot(*s);
-                done_q.push_back(s); done_map[s->id] = s; --inflight;
-            }
+            for (auto& s : running) fail(s, XTTS_ERR_CUDA, ex.what());
             running.clear();
-            cv_done.notify_all();
         }
-        // let submit/poll/fetch in: the wait() above does not release the mutex while work is pending
-        lk.unlock();
-        std::this_thread::yield();
-        lk.lock();
     }
 }
 
 int Engine::poll(xtts_result* out, int timeout_ms) {
-    std::unique_lock<std::mutex> lk(mu);
+    std::unique_lock<std::mutex> lk(q_mu);
     if (!cv_done.wait_for(lk, std::chrono::milliseconds(std::max(0, timeout_ms)), [&] { return !done_q.empty(); })) return 0;
     auto s = done_q.front(); done_q.pop_front();
     out->seq_id = s->id; out->status = s->status; out->n_tokens = (int)s->tokens.size(); out->n_samples = s->n_samples;
@@ -959,33 +972,35 @@ int Engine::poll(xtts_result* out, int timeout_ms) {
 void Engine::fetch(uint64_t id, int32_t* tokens, float* wav, float* latents) {
     std::shared_ptr<Sequence> s;
     {
-        std::lock_guard<std::mutex> lk(mu);
+        std::lock_guard<std::mutex> lk(q_mu);
         auto it = done_map.find(id);
         if (it == done_map.end()) throw std::runtime_error("fetch: unknown or unfinished sequence id");
         s = it->second;
         done_map.erase(it);
         for (auto q = done_q.begin(); q != done_q.end(); ++q) if ((*q)->id == id) { done_q.erase(q); break; }
-        if (tokens) std::memcpy(tokens, s->tokens.data(), s->tokens.size() * sizeof(int32_t));
-        if (wav && s->n_samples > 0) {
-            if (s->wav_host) std::memcpy(wav, s->wav_host, (size_t)s->n_samples * sizeof(float));
-            else if (s->wav_dev.p) {
-                CUDA_CHECK(cudaSetDevice(cfg.device));
-                s->wav_dev.download(wav, s->n_samples, st);
-                CUDA_CHECK(cudaStreamSynchronize(st));
-            }
-        }
-        if (latents && s->lat_dev.p) {
-            CUDA_CHECK(cudaSetDevice(cfg.device));
-            s->lat_dev.download(latents, s->lat_dev.n, st);
-            CUDA_CHECK(cudaStreamSynchronize(st));
-        }
-        if (s->wav_host) { pinned_put(s->wav_host, s->wav_cap); s->wav_host = nullptr; }
+    }
+    if (tokens) std::memcpy(tokens, s->tokens.data(), s->tokens.size() * sizeof(int32_t));
+    if (wav && s->n_samples > 0 && s->wav_host) std::memcpy(wav, s->wav_host, (size_t)s->n_samples * sizeof(float));
+    const bool dev_wav = wav && s->n_samples > 0 && !s->wav_host && s->wav_dev.p;
+    const bool dev_lat = latents && s->lat_dev.p;
+    if (dev_wav || dev_lat) {
+        std::lock_guard<std::mutex> lk(mu);          // device copies go through the engine stream
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        if (dev_wav) s->wav_dev.download(wav, s->n_samples, st);
+        if (dev_lat) s->lat_dev.download(latents, s->lat_dev.n, st);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    if (s->wav_host) { pinned_put(s->wav_host, s->wav_cap); s->wav_host = nullptr; }
+    if (s->wav_dev.p || s->lat_dev.p) {               // cudaFree under the GPU lock
+        std::lock_guard<std::mutex> lk(mu);
+        s->wav_dev.release(); s->lat_dev.release();
     }
 }
 
 void Engine::set_option(const std::string& k, int64_t v) {
     std::lock_guard<std::mutex> lk(mu);
     if (k == "d2h_wav") d2h_wav = v != 0;
+    else if (k == "profile") { CUDA_CHECK(cudaSetDevice(cfg.device)); CUDA_CHECK(cudaStreamSynchronize(st)); g_prof.reset(); g_prof.enabled = v != 0; }
     else if (k == "reset_stats") {
         st_decode_steps = st_prefill_rows = st_tokens = st_samples = 0; st_gpt_ms = st_voc_ms = st_cond_ms = 0;
         launch_base = g_launch_count;
@@ -999,8 +1014,22 @@ void Engine::get_stats(xtts_stats* s) {
     s->cond_ms = st_cond_ms; s->hbm_bytes_weights = weight_bytes;
 }
 
+void Engine::kernel_profile(xtts_kernel_profile* out) {
+    std::lock_guard<std::mutex> lk(mu);
+    CUDA_CHECK(cudaSetDevice(cfg.device));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    g_prof.collect();
+    std::memset(out, 0, sizeof(*out));
+    out->n = KF_COUNT;
+    for (int i = 0; i < KF_COUNT && i < 16; ++i) {
+        std::snprintf(out->name[i], sizeof(out->name[i]), "%s", kernel_family_name(i));
+        out->ms[i] = g_prof.ms[i]; out->flops[i] = g_prof.flops[i]; out->bytes[i] = g_prof.bytes[i];
+        out->launches[i] = g_prof.launches[i];
+    }
+}
+
 void Engine::sync_idle() {
-    std::unique_lock<std::mutex> lk(mu);
+    std::unique_lock<std::mutex> lk(q_mu);
     cv_done.wait(lk, [&] { return inflight == 0; });
 }
 
@@ -1025,7 +1054,7 @@ void Engine::gpt_prefill_sync(const int32_t* text, int n_text, int speaker, cons
                               float* hidden_out, float* logits_out, float* latents_out) {
     std::lock_guard<std::mutex> lk(mu);
     require_finalized();
-    if (!running.empty()) throw std::runtime_error("debug entry points need an idle engine");
+    if (!running.empty() || !waiting.empty()) throw std::runtime_error("debug entry points need an idle engine");
     CUDA_CHECK(cudaSetDevice(cfg.device));
     Sequence s; s.text_ids.assign(text, text + n_text); s.speaker = speaker; s.slot = B;
     s.sp.max_tokens = CAP; s.sp.stop_token = cfg.stop_audio_token; s.sp.repetition_penalty = 1.f; s.sp.temperature = 0.f;
@@ -1061,7 +1090,7 @@ void Engine::gpt_teacher_forced_sync(const int32_t* text, int n_text, int speake
                                      const xtts_sampling& sp, float* logits_out, float* latents_out, int32_t* sampled_out) {
     std::lock_guard<std::mutex> lk(mu);
     require_finalized();
-    if (!running.empty()) throw std::runtime_error("debug entry points need an idle engine");
+    if (!running.empty() || !waiting.empty()) throw std::runtime_error("debug entry points need an idle engine");
     if (n < 1 || n > CAP) throw std::runtime_error("teacher_forced: n out of range");
     CUDA_CHECK(cudaSetDevice(cfg.device));
     Sequence s; s.text_ids.assign(text, text + n_text); s.speaker = speaker; s.slot = B; s.sp = sp;
@@ -1131,7 +1160,7 @@ void Engine::debug_gemm(int mode, const float* A, const float* W, const float* b
 void Engine::debug_sample(const float* logits, const uint8_t* seen, int Bn, int Vn, const xtts_sampling& sp, int step,
                           int32_t* out) {
     std::lock_guard<std::mutex> lk(mu);
-    if (!running.empty()) throw std::runtime_error("debug entry points need an idle engine");
+    if (!running.empty() || !waiting.empty()) throw std::runtime_error("debug entry points need an idle engine");
     if (Bn < 1 || Bn > B || Vn != V) throw std::runtime_error("debug_sample: bad batch or vocabulary size");
     CUDA_CHECK(cudaSetDevice(cfg.device));
     std::vector<float> lg((size_t)Bn * Vpad, 0.f);
@@ -1214,6 +1243,7 @@ int xtts_fetch(xtts_engine* e, uint64_t seq_id, int32_t* tokens, float* wav, flo
 int xtts_set_option(xtts_engine* e, const char* key, int64_t value) { XTTS_TRY(e->impl->set_option(key, value)) }
 int xtts_get_stats(xtts_engine* e, xtts_stats* out) { XTTS_TRY(e->impl->get_stats(out)) }
 int xtts_sync(xtts_engine* e) { XTTS_TRY(e->impl->sync_idle()) }
+int xtts_get_kernel_profile(xtts_engine* e, xtts_kernel_profile* out) { XTTS_TRY(e->impl->kernel_profile(out)) }
 int xtts_vocode(xtts_engine* e, const float* latents, int32_t T, int32_t speaker_slot, float* wav, int32_t* n_out,
                 const char* stage, float* stage_out, int64_t stage_cap) {
     XTTS_TRY(e->impl->vocode_sync(latents, T, speaker_slot, wav, n_out, stage, stage_out, stage_cap))

@@ -63,11 +63,16 @@ class XttsStats(C.Structure):
                 ("hbm_bytes_weights", C.c_uint64)]
 
 
+class XttsKernelProfile(C.Structure):
+    _fields_ = [("n", C.c_int32), ("name", (C.c_char * 32) * 16), ("ms", C.c_double * 16), ("flops", C.c_double * 16),
+                ("bytes", C.c_double * 16), ("launches", C.c_uint64 * 16)]
+
+
 # every symbol include/xtts_b200.h declares (checked by tests/test_abi.py against the header text)
 ABI_SYMBOLS = [
     "xtts_last_error", "xtts_version", "xtts_create", "xtts_destroy", "xtts_load_weight", "xtts_finalize_weights",
     "xtts_set_speaker", "xtts_get_speaker", "xtts_condition", "xtts_submit", "xtts_poll", "xtts_fetch",
-    "xtts_set_option", "xtts_get_stats", "xtts_sync", "xtts_vocode", "xtts_gpt_prefill", "xtts_gpt_teacher_forced",
+    "xtts_set_option", "xtts_get_stats", "xtts_sync", "xtts_get_kernel_profile", "xtts_vocode", "xtts_gpt_prefill", "xtts_gpt_teacher_forced",
     "xtts_debug_gemm", "xtts_debug_sample",
 ]
 
@@ -99,6 +104,7 @@ def load_library(path: Optional[str] = None):
     lib.xtts_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.xtts_get_stats.argtypes = [vp, C.POINTER(XttsStats)]
     lib.xtts_sync.argtypes = [vp]
+    lib.xtts_get_kernel_profile.argtypes = [vp, C.POINTER(XttsKernelProfile)]
     lib.xtts_vocode.argtypes = [vp, f32p, i32, i32, f32p, i32p, C.c_char_p, f32p, i64]
     lib.xtts_gpt_prefill.argtypes = [vp, i32p, i32, i32, i32p, i32, f32p, f32p, f32p]
     lib.xtts_gpt_teacher_forced.argtypes = [vp, i32p, i32, i32, i32p, i32, C.POINTER(XttsSampling), f32p, f32p, i32p]
@@ -265,6 +271,17 @@ class NativeEngine:
 
     def sync(self):
         self._chk(self.lib.xtts_sync(self.h), "sync")
+
+    def kernel_profile(self) -> Dict[str, dict]:
+        """{family: {ms, flops, bytes, launches}} accumulated since option "profile" was switched on."""
+        p = XttsKernelProfile()
+        self._chk(self.lib.xtts_get_kernel_profile(self.h, C.byref(p)), "get_kernel_profile")
+        out = {}
+        for i in range(p.n):
+            if p.launches[i]:
+                out[bytes(p.name[i]).split(b"\0")[0].decode()] = dict(ms=p.ms[i], flops=p.flops[i], bytes=p.bytes[i],
+                                                                    launches=int(p.launches[i]))
+        return out
 
     def run_batch(self, jobs, timeout_s: float = 600.0, want_wav: bool = True, want_latents: bool = False):
         """jobs: iterable of (seq_id, text_ids, speaker_slot, Sampling).  Returns {seq_id: (result, tokens, wav, lat)}."""

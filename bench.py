@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline metric on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                      (CPU arm: the oracle port on the host cores)
+
+Workload (BASELINE.json configs[1]): per GPU, 32 requests x 1 000 chars of synthetic English, 4 shared
+speakers, temperature 0.75 / top_p 0.85 / top_k 50 / repetition penalty 5.0, random-init XTTSv2 weights of
+the full geometry (30 x 1024 GPT-2, HiFi-GAN 512->32 ch).  With random weights the stop token never wins, so
+every <=250-char chunk runs the full 605 tokens = 28.096 s of 24 kHz audio — a fixed unit of
+work.  Weak scaling: the per-GPU request count is fixed as N grows.
+
+One "step" = one pass of the hot path over the batch: text chunks -> GPT prefill + 605 decode steps with
+continuous batching -> latents -> vocoder -> waveforms.
+  * `value`  : audio-seconds per wall-second with inputs resident on the device (token ids uploaded before the
+               timed region, waveforms left in HBM).
+  * `e2e`    : the same metric through the public API (`TTS.generate_speech_batch(TTSRequest...)`): host text in,
+               host float32 waveforms out, tokenisation, H2D and D2H inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 1234
+WORDS = ("the of and to in is that it was for on are as with his they at be this from have or by one had not but what "
+         "all were when we there can an your which their said if do will each about how up out them then she many some "
+         "so these would other into has more her two like him see time could no make than first been its who now people "
+         "my made over did down only way find use may water long little very after words called just where most know "
+         "get through back much before go good new write our used me man too any day same right look think also around "
+         "another came come work three word must because does part even place well such here take why things help put "
+         "years different away again off went old number great tell men say small every found still between name should "
+         "home big give air line set own under read last never us left end along while might next sound below saw "
+         "something thought both few those always looked show large often together asked house world going want").split()
+
+
+def make_text(n_chars: int, seed: int) -> str:
+    """Synthetic English: sentences of 60-120 chars from a fixed word list."""
+    rng = np.random.RandomState(seed)
+    out, total = [], 0
+    while total < n_chars:
+        target = rng.randint(60, 121)
+        s = []
+        n = 0
+        while n < target:
+            w = WORDS[rng.randint(len(WORDS))]
+            s.append(w)
+            n += len(w) + 1
+        sent = " ".join(s).capitalize() + "."
+        out.append(sent)
+        total += len(sent) + 1
+    return " ".join(out)[:n_chars]
+
+
+def synthetic_wav_bytes(seconds: float, f0: float, seed: int, sr: int = 22050) -> bytes:
+    """RIFF bytes of the synthetic speaker reference."""
+    import io
+    import wave
+    t = np.arange(int(seconds * sr), dtype=np.float64) / sr
+    rng = np.random.RandomState(seed)
+    x = 0.3 * np.sin(2 * np.pi * (f0 + 40.0 * np.sin(2 * np.pi * 3.0 * t)) * t) + 0.01 * rng.randn(t.size)
+    buf = io.BytesIO()
+    with wave.open(buf, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(sr)
+        w.writeframes((np.clip(x, -1, 1) * 32767).astype(np.int16).tobytes())
+    return buf.getvalue()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for (_, r) in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[0]) for r in rows]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
+
+
+# =====================================================================================================
+def cpu_reference_sample(dims, state, n_threads: int, decode_tokens: int = 12, voc_latents: int = 24) -> dict:
+    """Times the reference's CPU path (the oracle port, fp32 torch ops, all host threads) on a bounded sample of
+    the same workload: one 250-char chunk's prompt prefill + `decode_tokens` KV-cached decode steps, and the
+    vocoder on `voc_latents` latents; scaled to the workload's unit (605 tokens + 605 latents per chunk)."""
+    import torch
+    from oracle import xtts_oracle as O
+    torch.set_num_threads(n_threads)
+    gs, cs = state
+    orc = O.GPTOracle(gs, cs, dims)
+    g = torch.Generator().manual_seed(500)
+    cond = torch.randn(dims.gpt.n_cond_latents, dims.gpt.hidden, generator=g)
+    dv = torch.nn.functional.normalize(torch.randn(dims.voc.d_vector, generator=g), dim=0)
+    ids = [0] + np.random.RandomState(0).randint(2, dims.gpt.n_text_tokens, size=78).tolist() + [1]   # ~250 chars
+    sp = O.SamplingParams(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, max_tokens=decode_tokens,
+                          stop_token=dims.gpt.stop_audio_token, seed=1)
+    with torch.no_grad():
+        rows = orc.prompt_rows(cond, ids)
+        orc.forward_rows(rows[:8])                              # warm the allocator / thread pool
+        t0 = time.perf_counter()
+        h, cache = orc.forward_rows(rows)
+        t_prefill = time.perf_counter() - t0
+        # KV-cached decode steps, timed on their own (teacher-forced ids: the arithmetic is the same)
+        h_last = h[-1:]
+        t0 = time.perf_counter()
+        for k in range(1, decode_tokens + 1):
+            logits, _ = orc.head(h_last)
+            tok = O.sample_token(logits[0].clone(), {1, dims.gpt.start_audio_token}, sp, 0, k - 1)
+            h_last, cache = orc.forward_rows(orc.audio_row(tok, k)[None], cache)
+        t_per_tok = (time.perf_counter() - t0) / decode_tokens
+        lat = torch.randn(voc_latents, dims.voc.in_dim, generator=g)
+        O.vocoder(lat[:4], dv, cs, dims)
+        t0 = time.perf_counter()
+        wav = O.vocoder(lat, dv, cs, dims)
+        t_voc = time.perf_counter() - t0
+    n_tok = dims.gpt.max_audio_tokens
+    voc_audio_s = wav.numel() / 24000.0
+    chunk_audio_s = dims.voc.n_samples(n_tok) / 24000.0
+    t_chunk = t_prefill + n_tok * t_per_tok + t_voc * (chunk_audio_s / voc_audio_s)
+    return {"value": chunk_audio_s / t_chunk, "unit": "audio-s/s", "cores": n_threads, "kind": "port",
+            "sample": f"1 chunk: prefill {rows.shape[0]} rows {t_prefill:.2f}s + {decode_tokens} decode steps "
+                      f"({1.0 / t_per_tok:.1f} tok/s) + vocoder on {voc_latents} latents ({voc_audio_s / t_voc:.2f} audio-s/s), "
+                      f"extrapolated linearly to 605 tokens / 28.1 s per chunk",
+            "gpt_tokens_per_s": 1.0 / t_per_tok, "vocoder_audio_s_per_s": voc_audio_s / t_voc}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--requests", type=int, default=32, help="requests per GPU")
+    ap.add_argument("--chars", type=int, default=1000)
+    ap.add_argument("--max-tokens", type=int, default=605)
+    ap.add_argument("--small", action="store_true", help="tiny geometry (plumbing check only; not a valid bench number)")
+    args = ap.parse_args()
+
+    import torch
+    from auralis_b200.config import XTTSDims
+    from auralis_b200.weights import synth_state
+    from auralis_b200 import parallel
+
+    rank, world, local = parallel.init_from_env()
+    dims = XTTSDims.small() if args.small else XTTSDims.full()
+    n_threads = os.cpu_count() or 1
+    workload = f"cfg2: {args.requests} x {args.chars}-char English requests per GPU, 4 speakers, T=0.75 top_p=0.85 top_k=50 rep=5.0"
+
+    # ------------------------------------------------------------------------------- reference (CPU) arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        torch.set_num_threads(n_threads)
+        state = synth_state(dims, SEED)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            r = cpu_reference_sample(dims, state, n_threads, decode_tokens=8, voc_latents=16)
+            if i >= args.warmup:
+                vals.append(r)
+        v = statistics.mean(x["value"] for x in vals)
+        r = vals[-1]; r["value"] = v
+        chunk_audio = dims.voc.n_samples(dims.gpt.max_audio_tokens) / 24000.0
+        line = {"metric": "audio_seconds_per_second", "value": v, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * chunk_audio / v, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+                "config": {"workload": workload, "sample": r["sample"], "note": "reference CPU path = oracle port "
+                           "(the reference cannot run without CUDA + vLLM 0.6.4, SURVEY.md §8c)"},
+                "cpu_baseline": r, "gpu_launches": 0,
+                "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------------------- B200 arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference)")
+    from auralis_b200 import TTS, TTSRequest, native
+    from auralis_b200.engine import XTTSv2Engine
+    torch.cuda.set_device(local)
+    state = synth_state(dims, SEED)
+    n_chunks_est = args.requests * (args.chars // 200 + 2)
+    eng = XTTSv2Engine(dims, state[0], state[1], device=local, precision=args.precision,
+                       max_concurrency=min(256, max(8, n_chunks_est)), max_speakers=8)
+    ne = eng.native
+    tts = TTS(scheduler_max_concurrency=4096).from_engine(eng)
+
+    # speakers: 4 synthetic references, conditioned on the GPU once (cached per speaker)
+    spk_bytes = [synthetic_wav_bytes(6.0, 100.0 + 25.0 * i, 7 + i) for i in range(4)]
+    loop = tts.loop
+    spk = [loop.run_until_complete(eng.get_audio_conditioning(b, 60, 30, 4)) for b in spk_bytes]
+    spk_slots = [c.slot for c, _ in spk]
+
+    texts = [make_text(args.chars, 1000 * rank + i) for i in range(args.requests)]
+    reqs_chunks = [eng.prepare_text_tokens(t, "en") for t in texts]
+    n_chunks = sum(len(c) for c in reqs_chunks)
+    max_tok = min(args.max_tokens, dims.gpt.max_audio_tokens)
+
+    def device_step(step_idx: int):
+        jobs, sid = [], 0
+        for ri, chunks in enumerate(reqs_chunks):
+            for ci, ids in enumerate(chunks):
+                sp = native.Sampling(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, max_tokens=max_tok,
+                                     stop_token=dims.gpt.stop_audio_token, seed=SEED + step_idx, seq_seed=sid, vocode=True)
+                jobs.append((sid, ids, spk_slots[ri % 4], sp))
+                sid += 1
+        res = ne.run_batch(jobs, timeout_s=3600, want_wav=False)
+        return sum(r.n_samples for (r, _, _, _) in res.values()), sum(r.n_tokens for (r, _, _, _) in res.values())
+
+    def e2e_step(step_idx: int):
+        reqs = [TTSRequest(text=t, speaker_files=spk_bytes[i % 4], language="en", temperature=0.75, top_p=0.85, top_k=50,
+                           repetition_penalty=5.0, seed=SEED + 100 + step_idx) for i, t in enumerate(texts)]
+        if max_tok != dims.gpt.max_audio_tokens:
+            eng.dims.gpt.max_audio_tokens = max_tok          # reduced runs only (flagged in config)
+        outs = tts.generate_speech_batch(reqs)
+        # DP epilogue: gather every rank's waveforms on all ranks (rank 0 is the consumer) over NCCL
+        if world > 1:
+            local_w = {rank * len(outs) + i: o.array for i, o in enumerate(outs)}
+            parallel.gather_waveforms(local_w, world * len(outs), torch.device("cuda", local))
+        return sum(o.array.shape[0] for o in outs), sum(len(t) for t in texts)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, warm, steps):
+        for i in range(warm):
+            fn(i)
+        barrier()
+        t0w = time.time(); t0 = time.perf_counter()
+        acc = [fn(warm + i) for i in range(steps)]
+        barrier()
+        dt = time.perf_counter() - t0
+        return dt, acc, (t0w, time.time())
+
+    # ---- device-resident arm
+    ne.set_option("d2h_wav", 0)
+    ne.set_option("profile", 1)
+    sampler = ClockSampler(local) if rank == 0 else None
+    for i in range(args.warmup):
+        device_step(i)
+    ne.set_option("reset_stats", 0)
+    ne.set_option("profile", 1)          # resets the per-family accumulators
+    if sampler:
+        sampler.start()
+    dt_dev, acc_dev, span = timed(device_step, 0, args.steps)
+    clocks = sampler.stop(*span) if sampler else None
+    prof = ne.kernel_profile()
+    st = ne.stats()
+    ne.set_option("profile", 0)
+    samples_dev = sum(a[0] for a in acc_dev)
+    tokens_dev = sum(a[1] for a in acc_dev)
+
+    # ---- end-to-end arm (public API, host buffers)
+    ne.set_option("d2h_wav", 1)
+    dt_e2e, acc_e2e, _ = timed(e2e_step, 1, args.steps)
+    samples_e2e = sum(a[0] for a in acc_e2e)
+    h2d = sum(len(ids) * 4 for chunks in reqs_chunks for ids in chunks)
+    d2h = samples_e2e // max(1, args.steps) * 4 + n_chunks * max_tok * 4
+
+    # ---- max over ranks, aggregate over ranks
+    if world > 1:
+        t = torch.tensor([dt_dev, dt_e2e], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        dt_dev, dt_e2e = float(t[0]), float(t[1])
+        s = torch.tensor([samples_dev, tokens_dev, samples_e2e], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(s, op=torch.distributed.ReduceOp.SUM)
+        samples_dev, tokens_dev, samples_e2e = float(s[0]), float(s[1]), float(s[2])
+    if rank != 0:
+        return
+
+    audio_s_dev = samples_dev / 24000.0
+    value = audio_s_dev / dt_dev
+    e2e_value = (samples_e2e / 24000.0) / dt_e2e
+
+    # ---- roofline of the dominant kernel family (device time by CUDA events inside the timed region)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    total_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    dom_name, dom = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else ("none", {"ms": 1, "flops": 0, "bytes": 0, "launches": 1})
+    fams = {k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / total_ms, 4), "launches": v["launches"],
+                "GB/s": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] else None,
+                "TFLOP/s": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] else None}
+            for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    tensor_bound = dom_name.startswith("gemm_bf16") or dom_name.startswith("conv1d_tc")
+    if tensor_bound:
+        ach = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak}
+    else:
+        ach = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}
+    roof.update({"kernel": dom_name, "avg_launch_us": 1e3 * dom["ms"] / max(1, dom["launches"]), "launches": dom["launches"],
+                 "share_of_device_time": dom["ms"] / total_ms, "peak_source": peak_src, "traffic": None,
+                 "fp32_tflops": dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] else None,
+                 "families": fams})
+
+    cpu = cpu_reference_sample(dims, state, n_threads) if args.gpus == 1 else None
+
+    line = {
+        "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": workload, "chunks_per_gpu": n_chunks, "tokens_per_chunk": max_tok,
+                   "audio_s_per_step": audio_s_dev / args.steps, "geometry": "small (INVALID as a bench number)" if args.small else "XTTSv2 full: GPT-2 30x1024x16h, HiFi-GAN 512ch, random-init",
+                   "parallelism": f"dp{args.gpus} (requests sharded, waveform all-gather only)",
+                   "gpt_compute": "bf16 tcgen05 GEMM operands + bf16 KV, fp32 accumulate/residual/LN/softmax" if args.precision == "bf16" else "fp32",
+                   "vocoder_compute": "fp32",
+                   "l2": "no explicit flush: per-step working set (0.76 GB weights + >5 GB KV + 0.4 GB vocoder activations) >> 126 MB L2",
+                   "timing": "host perf_counter bracketed by barrier + cuda synchronize (device idle on both sides); max over ranks",
+                   "e2e_speakers": "4 reference wavs conditioned on the GPU before the timed region (per-speaker cache, as prepare_for_streaming_generation)"},
+        "gpt_tokens_per_s": tokens_dev / dt_dev, "rtf": 1.0 / value,
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "api": "TTS.generate_speech_batch([TTSRequest(text, speaker_files=wav bytes)])", "ms_per_step": 1e3 * dt_e2e / args.steps},
+        "gpu_launches": int(st.kernel_launches),
+        "clocks": clocks, "roofline": roof,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    loop.run_until_complete(tts.shutdown())
+
+
+if __name__ == "__main__":
+    main()

@@ -79,6 +79,15 @@ typedef struct xtts_stats {
     uint64_t hbm_bytes_weights;
 } xtts_stats;
 
+/* Per-kernel-family device time (CUDA events on the engine's stream) and algorithmic FLOPs / bytes, collected
+ * while option "profile" is 1 — what bench.py's `roofline` object is computed from. */
+typedef struct xtts_kernel_profile {
+    int32_t n;
+    char name[16][32];
+    double ms[16], flops[16], bytes[16];
+    uint64_t launches[16];
+} xtts_kernel_profile;
+
 const char* xtts_last_error(void);
 const char* xtts_version(void);
 
@@ -115,6 +124,7 @@ int xtts_fetch(xtts_engine* e, uint64_t seq_id, int32_t* tokens, float* wav, flo
 int xtts_set_option(xtts_engine* e, const char* key, int64_t value);
 int xtts_get_stats(xtts_engine* e, xtts_stats* out);
 int xtts_sync(xtts_engine* e);   /* waits until no submitted work is pending */
+int xtts_get_kernel_profile(xtts_engine* e, xtts_kernel_profile* out);
 
 /* ---- synchronous single-stage entry points (parity tests; they serialise with the scheduler) ---- */
 /* HifiDecoder.forward (hifigan_decoder.py:776-802): latents [T,in_dim] -> wav [n_samples]. Returns n_samples
