@@ -75,7 +75,10 @@ struct Linear {
 };
 
 struct ConvW {
-    DBuf<float> wt;               // [Cin][K][Cout]
+    DBuf<float> wt;               // [Cin][K][Cout]      (CUDA-core path)
+    DBuf<__half> blob;            // tcgen05 tile blob   (fast mode, Conv1d only)
+    ConvTcPlan plan{};
+    bool tc = false;
     DBuf<float> b;                // [Cout]
     int Cin = 0, Cout = 0, K = 0;
 };
@@ -185,8 +188,8 @@ private:
     // pinned staging
     int* h_finished = nullptr;
     // vocoder workspace
-    DBuf<float> vz, vpre, vb[5], vwav;
-    int voc_max_T = 0;
+    DBuf<float> vz, vpre, vb[5], vwav, vlat, vcb;
+    int voc_max_T = 0, VB = 1;
     std::vector<int> stage_ch;
 
     // ---- scheduler
@@ -206,6 +209,11 @@ private:
     std::atomic<bool> stop{false};
     int inflight = 0;
     bool d2h_wav = true;
+    bool use_graphs = true;       // option "cuda_graphs"
+    int eager_steps_done = 0;
+    std::map<int, cudaGraphExec_t> decode_graphs;
+    std::map<int, unsigned long long> graph_kernels;
+    bool use_tc_vocoder = true;   // fast mode only; option "tc_vocoder" switches back to the fp32 CUDA-core convs
     std::vector<std::pair<float*, size_t>> pinned_pool;
     // stats
     double decode_ctx_sum = 0;
@@ -218,6 +226,8 @@ private:
     void up(DBuf<float>& d, const std::vector<float>& h) { d.alloc(h.size()); d.upload(h.data(), h.size(), st); weight_bytes += h.size() * 4; }
     void make_linear(Linear& lin, const std::string& wname, const std::string& bname, bool conv1d_layout, int pad_n = 0);
     void make_conv(ConvW& c, const std::string& prefix, bool transposed, bool has_bias);
+    void conv1d(const ConvW& c, const float* x, const float* cbias, const float* resid, float* out, int L, int dil,
+                float in_scale, float slope, int mode, int nb);
     std::vector<float> folded(const std::string& prefix) const;
     GptTables tables() const {
         GptTables t; t.text_emb = text_emb.p; t.text_pos = text_pos.p; t.wte = wte.p; t.wpe = wpe.p;
@@ -234,8 +244,9 @@ private:
                       std::vector<int>& last_rows, int& max_nq);
     void prefill(const std::vector<Sequence*>& seqs);
     void decode_step(const std::vector<int>& active);
-    void run_vocoder(const float* lat_dev, int T, int speaker, float* wav_dev_out, int* n_out, const char* stage,
-                     float* stage_out, int64_t stage_cap);
+    void run_vocoder(const float* lat_dev, int T, const int* speakers, int nb, float* wav_dev_out, int* n_out,
+                     const char* stage, float* stage_out, int64_t stage_cap);
+    void finish_group(std::vector<std::shared_ptr<Sequence>>& grp);
     void finish_sequence(std::shared_ptr<Sequence> s);
     void retire(std::shared_ptr<Sequence> s);
     float* pinned_get(size_t n, size_t* cap);
@@ -335,12 +346,15 @@ Engine::Engine(const xtts_config& c) : cfg(c) {
     {
         const int T1 = (int)std::floor((double)voc_max_T * ((double)c.code_stride / (double)c.output_hop_length));
         const int Tz = (int)std::floor((double)T1 * ((double)c.output_sample_rate / (double)c.input_sample_rate));
-        vz.alloc((size_t)c.voc_in_dim * Tz);
-        vpre.alloc((size_t)c.voc_init_ch * Tz);
+        VB = std::max(1, std::min(8, B));       // chunks vocoded per launch (fills the SMs at the short early stages)
+        vz.alloc((size_t)VB * c.voc_in_dim * Tz);
+        vpre.alloc((size_t)VB * c.voc_init_ch * Tz);
         size_t mx = 0; int len = Tz;
         for (int i = 0; i < c.voc_n_up; ++i) { len *= c.voc_up_rates[i]; mx = std::max(mx, (size_t)stage_ch[i] * len); }
-        for (auto& b : vb) b.alloc(mx);
-        vwav.alloc(len);
+        for (auto& b : vb) b.alloc((size_t)VB * mx);
+        vwav.alloc((size_t)VB * len);
+        vlat.alloc((size_t)VB * voc_max_T * c.voc_in_dim);
+        vcb.alloc((size_t)VB * cbias_stride);
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
     launch_base = g_launch_count;
@@ -356,6 +370,7 @@ Engine::~Engine() {
     if (worker.joinable()) worker.join();
     cudaSetDevice(cfg.device);
     cudaStreamSynchronize(st);
+    for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second);
     for (auto& pr : pinned_pool) cudaFreeHost(pr.first);
     for (auto& kv : done_map) if (kv.second->wav_host) cudaFreeHost(kv.second->wav_host);
     if (h_finished) cudaFreeHost(h_finished);
@@ -450,6 +465,27 @@ void Engine::make_conv(ConvW& c, const std::string& prefix, bool transposed, boo
     c.Cin = Cin; c.Cout = Cout; c.K = K;
     up(c.wt, t);
     if (has_bias) up(c.b, need(prefix + ".bias").data);
+    if (bf16 && !transposed) {               // fast mode: fp16 tensor-core tiles for every Conv1d that fits the plan
+        c.plan = conv1d_tc_plan(Cin, Cout, K);
+        if (c.plan.ok) {
+            std::vector<__half> blob(c.plan.blob_halves);
+            conv1d_tc_pack(w.data(), Cin, Cout, K, c.plan, blob.data());
+            c.blob.alloc(blob.size());
+            c.blob.upload(blob.data(), blob.size(), st);
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            c.tc = true;
+            weight_bytes += blob.size() * 2;
+        }
+    }
+}
+
+// Conv1d through whichever path the weights were prepared for
+void Engine::conv1d(const ConvW& c, const float* x, const float* cbias, const float* resid, float* out, int L, int dil,
+                    float in_scale, float slope, int mode, int nb) {
+    if (c.tc && use_tc_vocoder)
+        launch_conv1d_tc(x, c.blob.p, c.plan, c.b.p, cbias, resid, out, c.Cin, c.Cout, L, c.K, dil, in_scale, slope, mode, nb, cbias_stride, st);
+    else
+        launch_conv1d(x, c.wt.p, c.b.p, cbias, resid, out, c.Cin, c.Cout, L, c.K, dil, in_scale, slope, mode, nb, cbias_stride, st);
 }
 
 void Engine::finalize_weights() {
@@ -739,36 +775,69 @@ void Engine::prefill(const std::vector<Sequence*>& seqs) {
 void Engine::decode_step(const std::vector<int>& active) {
     const int M = (int)active.size();
     d_active.upload(active.data(), M, st);
-    launch_build_decode_rows(d_active.p, M, d_last_tok.p, d_n_gen.p, tables(), wX.p, st);
-    layers_forward(M, false, 0, 0);
-    head_and_sample(M, nullptr, d_active.p, nullptr, 1, true);
+    auto enqueue = [&] {
+        launch_build_decode_rows(d_active.p, M, d_last_tok.p, d_n_gen.p, tables(), wX.p, st);
+        layers_forward(M, false, 0, 0);
+        head_and_sample(M, nullptr, d_active.p, nullptr, 1, true);
+    };
+    // The decode step is ~250 small launches whose arguments depend only on M (slot lists, positions and
+    // lengths live in device memory), so it is captured once per batch size into a CUDA graph and replayed.
+    // Kernel-family profiling and teacher forcing use the eager path.
+    const bool graphable = use_graphs && !g_prof.enabled && !use_forced && eager_steps_done >= 2;
+    if (!graphable) {
+        enqueue();
+        ++eager_steps_done;
+    } else {
+        auto it = decode_graphs.find(M);
+        if (it == decode_graphs.end()) {
+            cudaGraph_t g = nullptr; cudaGraphExec_t ge = nullptr;
+            const unsigned long long lc = g_launch_count;
+            CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            try { enqueue(); }
+            catch (...) { cudaStreamEndCapture(st, &g); if (g) cudaGraphDestroy(g); throw; }
+            CUDA_CHECK(cudaStreamEndCapture(st, &g));
+            CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
+            cudaGraphDestroy(g);
+            graph_kernels[M] = g_launch_count - lc;
+            g_launch_count = lc;                       // capture enqueued nothing on the device
+            it = decode_graphs.emplace(M, ge).first;
+        }
+        CUDA_CHECK(cudaGraphLaunch(it->second, st));
+        g_launch_count += graph_kernels[M];            // kernels executed by the replay
+    }
     ++st_decode_steps;
 }
 
 // ================================================================================================
 // vocoder driver  (HifiDecoder.forward, hifigan_decoder.py:776-802 + HifiganGenerator.forward :228-260)
 // ================================================================================================
-void Engine::run_vocoder(const float* lat_dev, int T, int speaker, float* wav_dev_out, int* n_out, const char* stage,
-                         float* stage_out, int64_t stage_cap) {
+// `nb` equal-length chunks at once: latents [nb][T][in_dim] (contiguous, device) -> wav_dev_out [nb][n_samples]
+void Engine::run_vocoder(const float* lat_dev, int T, const int* speakers, int nb, float* wav_dev_out, int* n_out,
+                         const char* stage, float* stage_out, int64_t stage_cap) {
     const auto& c = cfg;
     if (T <= 0 || T > voc_max_T) throw std::runtime_error("vocoder: latent count out of range");
-    if (speaker < 0 || speaker >= S || !spk_valid[speaker]) throw std::runtime_error("vocoder: speaker slot not set");
+    if (nb < 1 || nb > VB) throw std::runtime_error("vocoder: batch out of range");
+    for (int i = 0; i < nb; ++i) {
+        const int sp = speakers[i];
+        if (sp < 0 || sp >= S || !spk_valid[sp]) throw std::runtime_error("vocoder: speaker slot not set");
+        CUDA_CHECK(cudaMemcpyAsync(vcb.p + (size_t)i * cbias_stride, spk_cbias.p + (size_t)sp * cbias_stride,
+                                   (size_t)cbias_stride * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
     const double s1 = (double)c.code_stride / (double)c.output_hop_length;
     const double s2 = (double)c.output_sample_rate / (double)c.input_sample_rate;
     const int T1 = (int)std::floor((double)T * s1);
     const bool resample = c.output_sample_rate != c.input_sample_rate;
     const int Tz = resample ? (int)std::floor((double)T1 * s2) : T1;
-    const float* cb = spk_cbias.p + (size_t)speaker * cbias_stride;
-    auto dump = [&](const char* name, const float* p, size_t n) {
+    const float* cb = vcb.p;
+    auto dump = [&](const char* name, const float* p, size_t n) {           // first batch item only
         if (stage && stage_out && std::strcmp(stage, name) == 0) {
             const size_t m = std::min<size_t>(n, (size_t)stage_cap);
             CUDA_CHECK(cudaMemcpyAsync(stage_out, p, m * sizeof(float), cudaMemcpyDeviceToHost, st));
         }
     };
-    launch_interp(lat_dev, vz.p, T, c.voc_in_dim, T1, Tz, s1, resample ? s2 : 1.0, st);
+    launch_interp(lat_dev, vz.p, T, c.voc_in_dim, T1, Tz, s1, resample ? s2 : 1.0, nb, st);
     dump("z", vz.p, (size_t)c.voc_in_dim * Tz);
-    launch_conv1d(vz.p, conv_pre.wt.p, conv_pre.b.p, cb + cbias_off[0], nullptr, vpre.p, conv_pre.Cin, conv_pre.Cout, Tz,
-                  conv_pre.K, 1, 1.0f, 1.0f, CONV_STORE, st);
+    conv1d(conv_pre, vz.p, cb + cbias_off[0], nullptr, vpre.p, Tz, 1, 1.0f, 1.0f, CONV_STORE, nb);
     dump("pre", vpre.p, (size_t)c.voc_init_ch * Tz);
     const float* cur = vpre.p;
     float in_scale = 1.0f;
@@ -778,7 +847,7 @@ void Engine::run_vocoder(const float* lat_dev, int T, int speaker, float* wav_de
     for (int i = 0; i < c.voc_n_up; ++i) {
         const ConvW& u = *ups[i];
         launch_conv_transpose1d(cur, u.wt.p, u.b.p, cb + cbias_off[i + 1], X, u.Cin, u.Cout, len, u.K, c.voc_up_rates[i],
-                                in_scale, 0.1f, st);
+                                in_scale, 0.1f, nb, cbias_stride, st);
         len *= c.voc_up_rates[i];
         const int C = u.Cout;
         { char nm[16]; snprintf(nm, sizeof(nm), "up%d", i); dump(nm, X, (size_t)C * len); }
@@ -788,15 +857,13 @@ void Engine::run_vocoder(const float* lat_dev, int T, int speaker, float* wav_de
             for (int t = 0; t < 3; ++t) {
                 const ConvW& a = *rb.c1[t];
                 const ConvW& b = *rb.c2[t];
-                launch_conv1d(r_in, a.wt.p, a.b.p, nullptr, nullptr, TMP, C, C, len, a.K, c.voc_rb_dilations[t], 1.0f, 0.1f,
-                              CONV_STORE, st);
+                conv1d(a, r_in, nullptr, nullptr, TMP, len, c.voc_rb_dilations[t], 1.0f, 0.1f, CONV_STORE, nb);
                 if (t < 2) {
                     float* r_out = (t == 0) ? R1 : R2;
-                    launch_conv1d(TMP, b.wt.p, b.b.p, nullptr, r_in, r_out, C, C, len, b.K, 1, 1.0f, 0.1f, CONV_STORE, st);
+                    conv1d(b, TMP, nullptr, r_in, r_out, len, 1, 1.0f, 0.1f, CONV_STORE, nb);
                     r_in = r_out;
                 } else {
-                    launch_conv1d(TMP, b.wt.p, b.b.p, nullptr, r_in, ZS, C, C, len, b.K, 1, 1.0f, 0.1f,
-                                  j == 0 ? CONV_STORE : CONV_ACCUM, st);
+                    conv1d(b, TMP, nullptr, r_in, ZS, len, 1, 1.0f, 0.1f, j == 0 ? CONV_STORE : CONV_ACCUM, nb);
                 }
             }
         }
@@ -806,7 +873,7 @@ void Engine::run_vocoder(const float* lat_dev, int T, int speaker, float* wav_de
         cur = ZS;
         in_scale = 1.0f / (float)nk;
     }
-    launch_conv_post(cur, conv_post_w.p, wav_dev_out, post_cin, len, 7, in_scale, 0.01f, st);
+    launch_conv_post(cur, conv_post_w.p, wav_dev_out, post_cin, len, 7, in_scale, 0.01f, nb, st);
     *n_out = len;
 }
 
@@ -843,8 +910,8 @@ void Engine::submit(uint64_t id, const int32_t* text, int n_text, int speaker, c
     cv_work.notify_all();
 }
 
+// tokens + latent snapshot of one finished sequence; frees its slot
 void Engine::finish_sequence(std::shared_ptr<Sequence> s) {
-    // tokens
     int n = 0;
     d_n_gen.download(&n, 1, st, s->slot);
     CUDA_CHECK(cudaStreamSynchronize(st));
@@ -857,25 +924,40 @@ void Engine::finish_sequence(std::shared_ptr<Sequence> s) {
                                cudaMemcpyDeviceToDevice, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     st_tokens += n;
-    if (s->sp.vocode) {
-        const double t0 = now_s();
+    release_slot(*s);
+}
+
+// vocode a group of finished sequences that have the same token count, VB at a time, then retire them
+void Engine::finish_group(std::vector<std::shared_ptr<Sequence>>& grp) {
+    const double t0 = now_s();
+    for (size_t b0 = 0; b0 < grp.size(); b0 += VB) {
+        const int nb = (int)std::min<size_t>(VB, grp.size() - b0);
+        const int n = (int)grp[b0]->tokens.size();
+        std::vector<int> spk(nb);
+        for (int i = 0; i < nb; ++i) {
+            spk[i] = grp[b0 + i]->speaker;
+            CUDA_CHECK(cudaMemcpyAsync(vlat.p + (size_t)i * n * H, grp[b0 + i]->lat_dev.p, (size_t)n * H * sizeof(float),
+                                       cudaMemcpyDeviceToDevice, st));
+        }
         int ns = 0;
-        run_vocoder(s->lat_dev.p, n, s->speaker, vwav.p, &ns, nullptr, nullptr, 0);
-        s->n_samples = ns;
-        if (d2h_wav) {
-            s->wav_host = pinned_get(ns, &s->wav_cap);
-            CUDA_CHECK(cudaMemcpyAsync(s->wav_host, vwav.p, (size_t)ns * sizeof(float), cudaMemcpyDeviceToHost, st));
-        } else {
-            s->wav_dev.alloc(ns);
-            CUDA_CHECK(cudaMemcpyAsync(s->wav_dev.p, vwav.p, (size_t)ns * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        run_vocoder(vlat.p, n, spk.data(), nb, vwav.p, &ns, nullptr, nullptr, 0);
+        for (int i = 0; i < nb; ++i) {
+            auto& s = grp[b0 + i];
+            s->n_samples = ns;
+            if (d2h_wav) {
+                s->wav_host = pinned_get(ns, &s->wav_cap);
+                CUDA_CHECK(cudaMemcpyAsync(s->wav_host, vwav.p + (size_t)i * ns, (size_t)ns * sizeof(float), cudaMemcpyDeviceToHost, st));
+            } else {
+                s->wav_dev.alloc(ns);
+                CUDA_CHECK(cudaMemcpyAsync(s->wav_dev.p, vwav.p + (size_t)i * ns, (size_t)ns * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            }
+            st_samples += ns;
         }
         CUDA_CHECK(cudaStreamSynchronize(st));
-        st_voc_ms += (now_s() - t0) * 1e3;
-        st_samples += ns;
+        const double t = now_s();
+        for (int i = 0; i < nb; ++i) { grp[b0 + i]->t_done = t; retire(grp[b0 + i]); }
     }
-    s->t_done = now_s();
-    release_slot(*s);
-    retire(s);
+    st_voc_ms += (now_s() - t0) * 1e3;
 }
 
 void Engine::retire(std::shared_ptr<Sequence> s) {
@@ -948,9 +1030,19 @@ void Engine::loop() {
             std::vector<std::shared_ptr<Sequence>> keep, fin;
             for (auto& s : running) (h_finished[s->slot] ? fin : keep).push_back(s);
             running.swap(keep);
+            std::map<int, std::vector<std::shared_ptr<Sequence>>> groups;     // token count -> sequences to vocode
             for (auto& s : fin) {
-                try { finish_sequence(s); }
-                catch (const std::exception& ex) { fail(s, XTTS_ERR_CUDA, ex.what()); }
+                try {
+                    finish_sequence(s);
+                    if (s->sp.vocode) groups[(int)s->tokens.size()].push_back(s);
+                    else { s->t_done = now_s(); retire(s); }
+                } catch (const std::exception& ex) { fail(s, XTTS_ERR_CUDA, ex.what()); }
+            }
+            for (auto& kv : groups) {
+                try { finish_group(kv.second); }
+                catch (const std::exception& ex) {
+                    for (auto& s : kv.second) if (s->t_done == 0) fail(s, XTTS_ERR_CUDA, ex.what());
+                }
             }
         } catch (const std::exception& ex) {
             // a failure inside a batched step fails every sequence that was part of it
@@ -1000,6 +1092,8 @@ void Engine::fetch(uint64_t id, int32_t* tokens, float* wav, float* latents) {
 void Engine::set_option(const std::string& k, int64_t v) {
     std::lock_guard<std::mutex> lk(mu);
     if (k == "d2h_wav") d2h_wav = v != 0;
+    else if (k == "tc_vocoder") use_tc_vocoder = v != 0;
+    else if (k == "cuda_graphs") use_graphs = v != 0;
     else if (k == "profile") { CUDA_CHECK(cudaSetDevice(cfg.device)); CUDA_CHECK(cudaStreamSynchronize(st)); g_prof.reset(); g_prof.enabled = v != 0; }
     else if (k == "reset_stats") {
         st_decode_steps = st_prefill_rows = st_tokens = st_samples = 0; st_gpt_ms = st_voc_ms = st_cond_ms = 0;
@@ -1044,7 +1138,7 @@ void Engine::vocode_sync(const float* latents, int T, int speaker, float* wav, i
     DBuf<float> lat; lat.alloc((size_t)T * cfg.voc_in_dim);
     lat.upload(latents, (size_t)T * cfg.voc_in_dim, st);
     int ns = 0;
-    run_vocoder(lat.p, T, speaker, vwav.p, &ns, stage, stage_out, stage_cap);
+    run_vocoder(lat.p, T, &speaker, 1, vwav.p, &ns, stage, stage_out, stage_cap);
     if (wav) vwav.download(wav, ns, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
     if (n_out) *n_out = ns;

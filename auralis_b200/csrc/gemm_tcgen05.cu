@@ -261,6 +261,12 @@ bool gemm_tc_init(std::string* err) {
         return false;
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    // opt every instantiation into its dynamic shared memory now (never inside a stream capture)
+    auto smem_of = [](int bn) { return (int)(STAGES * (BM * BK * 2 + bn * BK * 2) + 1024); };
+    cudaFuncSetAttribute(gemm_bf16_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(128));
+    cudaFuncSetAttribute(gemm_bf16_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(64));
+    cudaFuncSetAttribute(gemm_bf16_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(32));
+    (void)cudaGetLastError();
     return true;
 }
 

@@ -102,22 +102,30 @@ void launch_sample(const float* logits, int ld_logits, const int* active, int M,
 // ------------------------------------------------------------------------------------------
 // Vocoder kernels (fp32, channel-major activations [C][L])
 // ------------------------------------------------------------------------------------------
+// every vocoder launcher takes `batch` equal-length items laid out back to back ([batch][C][L])
 void launch_interp(const float* latents, float* z, int T, int C, int T1, int Tz, double scale1, double scale2,
-                   cudaStream_t st);
+                   int batch, cudaStream_t st);
 
 enum : int { CONV_STORE = 0, CONV_ACCUM = 1 };
 // out[co][t] (=|+=) bias[co] + cbias[co] + resid[co][t] + sum_{ci,j} w[ci][j][co] * act(in_scale*x[ci][t+(j-(K-1)/2)*dil])
 //   act = leaky_relu(slope) (slope==1 -> identity).  w is pre-transposed to [Cin][K][Cout].
 void launch_conv1d(const float* x, const float* w_t, const float* bias, const float* cbias, const float* resid,
                    float* out, int Cin, int Cout, int L, int K, int dil, float in_scale, float slope, int mode,
-                   cudaStream_t st);
+                   int batch, int cbias_batch_stride, cudaStream_t st);
+// tensor-core (tcgen05, fp16 operands / fp32 accumulate) version of launch_conv1d; weights pre-packed by conv1d_tc_pack
+struct ConvTcPlan { int N, CK, n_tiles, nacc; bool ok; size_t tile_halves, blob_halves; };
+ConvTcPlan conv1d_tc_plan(int Cin, int Cout, int K);
+void conv1d_tc_pack(const float* w /*[Cout][Cin][K]*/, int Cin, int Cout, int K, const ConvTcPlan& pl, __half* blob);
+void launch_conv1d_tc(const float* x, const __half* wblob, const ConvTcPlan& pl, const float* bias, const float* cbias,
+                      const float* resid, float* out, int Cin, int Cout, int L, int K, int dil, float in_scale, float slope,
+                      int mode, int batch, int cbias_batch_stride, cudaStream_t st);
 // transposed conv, stride u, kernel K = 2u, padding (K-u)/2;  w pre-transposed to [Cin][K][Cout]
 void launch_conv_transpose1d(const float* x, const float* w_t, const float* bias, const float* cbias, float* out,
-                             int Cin, int Cout, int Lin, int K, int u, float in_scale, float slope,
-                             cudaStream_t st);
+                             int Cin, int Cout, int Lin, int K, int u, float in_scale, float slope, int batch,
+                             int cbias_batch_stride, cudaStream_t st);
 // wav[t] = tanh(sum w[ci][j] * lrelu(in_scale*x[ci][t+j-3], slope))
 void launch_conv_post(const float* x, const float* w, float* wav, int Cin, int L, int K, float in_scale, float slope,
-                      cudaStream_t st);
+                      int batch, cudaStream_t st);
 // y[c] = W[c,:] . g + b[c]   (speaker conditioning 1x1 convs)
 void launch_gemv(const float* W, const float* b, const float* g, float* y, int rows, int cols, cudaStream_t st);
 

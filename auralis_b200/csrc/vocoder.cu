@@ -32,8 +32,10 @@ __device__ __forceinline__ void lin_src(int dst, float rscale, int in_len, int& 
 }
 
 __global__ void __launch_bounds__(256)
-interp_kernel(const float* __restrict__ lat, float* __restrict__ z, int T, int C, int T1, int Tz, float r1, float r2) {
+interp_kernel(const float* __restrict__ lat_, float* __restrict__ z_, int T, int C, int T1, int Tz, float r1, float r2) {
     __shared__ float tile[32][33];
+    const float* lat = lat_ + (size_t)blockIdx.z * T * C;
+    float* z = z_ + (size_t)blockIdx.z * C * Tz;
     const int c0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;       // (32, 8)
     for (int k = 0; k < 4; ++k) {
@@ -67,10 +69,14 @@ constexpr int CT_TC = 8;       // output channels per thread
 
 template <int K, int NTY>
 __global__ void __launch_bounds__(32 * NTY)
-conv1d_kernel(const float* __restrict__ x, const float* __restrict__ w_t, const float* __restrict__ bias,
-              const float* __restrict__ cbias, const float* resid, float* out, int Cin, int Cout, int L, int dil,
-              float in_scale, float slope, int mode) {
+conv1d_kernel(const float* __restrict__ x_, const float* __restrict__ w_t, const float* __restrict__ bias,
+              const float* __restrict__ cbias_, const float* resid_, float* out_, int Cin, int Cout, int L, int dil,
+              float in_scale, float slope, int mode, int cbias_bs) {
     constexpr int CO_T = CT_TC * NTY;
+    const float* x = x_ + (size_t)blockIdx.z * Cin * L;
+    float* out = out_ + (size_t)blockIdx.z * Cout * L;
+    const float* resid = resid_ ? resid_ + (size_t)blockIdx.z * Cout * L : nullptr;
+    const float* cbias = cbias_ ? cbias_ + (size_t)blockIdx.z * cbias_bs : nullptr;
     extern __shared__ __align__(16) float smem[];
     const int halo = (K - 1) / 2 * dil;
     const int XW = CT_T + 2 * halo;
@@ -150,10 +156,13 @@ conv1d_kernel(const float* __restrict__ x, const float* __restrict__ w_t, const 
 constexpr int UP_T = 128, UP_CI = 8, UP_CO = 16;
 
 __global__ void __launch_bounds__(UP_T)
-conv_transpose1d_kernel(const float* __restrict__ x, const float* __restrict__ w_t, const float* __restrict__ bias,
-                        const float* __restrict__ cbias, float* __restrict__ out, int Cin, int Cout, int Lin, int K,
-                        int u, float in_scale, float slope) {
+conv_transpose1d_kernel(const float* __restrict__ x_, const float* __restrict__ w_t, const float* __restrict__ bias,
+                        const float* __restrict__ cbias_, float* __restrict__ out_, int Cin, int Cout, int Lin, int K,
+                        int u, float in_scale, float slope, int cbias_bs) {
     extern __shared__ __align__(16) float smem[];
+    const float* x = x_ + (size_t)blockIdx.z * Cin * Lin;
+    float* out = out_ + (size_t)blockIdx.z * Cout * Lin * u;
+    const float* cbias = cbias_ ? cbias_ + (size_t)blockIdx.z * cbias_bs : nullptr;
     const int pad = (K - u) / 2;
     const int XS = UP_T / u + 3;                   // source frames touched by the tile (+ slack)
     constexpr int WROW = UP_CO + 4;
@@ -218,9 +227,11 @@ conv_transpose1d_kernel(const float* __restrict__ x, const float* __restrict__ w
 // conv_post (C->1, k7, no bias) + tanh; HBM-bound (reads C*L floats, writes L)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ wav, int Cin, int L,
+conv_post_kernel(const float* __restrict__ x_, const float* __restrict__ w, float* __restrict__ wav_, int Cin, int L,
                  int K, float in_scale, float slope) {
     extern __shared__ float wsm[];                 // [Cin*K]
+    const float* x = x_ + (size_t)blockIdx.y * Cin * L;
+    float* wav = wav_ + (size_t)blockIdx.y * L;
     for (int e = threadIdx.x; e < Cin * K; e += blockDim.x) wsm[e] = w[e];
     __syncthreads();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -239,26 +250,26 @@ conv_post_kernel(const float* __restrict__ x, const float* __restrict__ w, float
 
 template <int K>
 void conv1d_dispatch(const float* x, const float* w_t, const float* bias, const float* cbias, const float* resid,
-                     float* out, int Cin, int Cout, int L, int dil, float in_scale, float slope, int mode,
-                     cudaStream_t st) {
+                     float* out, int Cin, int Cout, int L, int dil, float in_scale, float slope, int mode, int batch,
+                     int cbias_bs, cudaStream_t st) {
     const int halo = (K - 1) / 2 * dil;
     const int XW = CT_T + 2 * halo;
     const int xs_f = CT_CI * XW + ((4 - (CT_CI * XW) % 4) % 4);
     // algorithmic traffic: read x once, write out once (+ residual / accumulate reads), weights once
-    ProfScope ps(KF_CONV1D, st, 2.0 * Cin * Cout * K * (double)L,
-                 4.0 * ((double)L * (Cin + Cout * (1 + (resid ? 1 : 0) + (mode == CONV_ACCUM ? 1 : 0))) + (double)Cin * Cout * K));
+    ProfScope ps(KF_CONV1D, st, 2.0 * Cin * Cout * K * (double)L * batch,
+                 4.0 * (batch * (double)L * (Cin + Cout * (1 + (resid ? 1 : 0) + (mode == CONV_ACCUM ? 1 : 0))) + (double)Cin * Cout * K));
     if (Cout > 32) {
         constexpr int NTY = 8;
         const size_t smem = (size_t)(xs_f + CT_CI * K * CT_TC * NTY) * sizeof(float);
-        dim3 grid(ceil_div(L, CT_T), ceil_div(Cout, CT_TC * NTY));
+        dim3 grid(ceil_div(L, CT_T), ceil_div(Cout, CT_TC * NTY), batch);
         conv1d_kernel<K, NTY><<<grid, dim3(32, NTY), smem, st>>>(x, w_t, bias, cbias, resid, out, Cin, Cout, L, dil,
-                                                                 in_scale, slope, mode);
+                                                                 in_scale, slope, mode, cbias_bs);
     } else {
         constexpr int NTY = 4;
         const size_t smem = (size_t)(xs_f + CT_CI * K * CT_TC * NTY) * sizeof(float);
-        dim3 grid(ceil_div(L, CT_T), ceil_div(Cout, CT_TC * NTY));
+        dim3 grid(ceil_div(L, CT_T), ceil_div(Cout, CT_TC * NTY), batch);
         conv1d_kernel<K, NTY><<<grid, dim3(32, NTY), smem, st>>>(x, w_t, bias, cbias, resid, out, Cin, Cout, L, dil,
-                                                                 in_scale, slope, mode);
+                                                                 in_scale, slope, mode, cbias_bs);
     }
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
@@ -266,42 +277,42 @@ void conv1d_dispatch(const float* x, const float* w_t, const float* bias, const 
 }  // namespace
 
 void launch_interp(const float* latents, float* z, int T, int C, int T1, int Tz, double scale1, double scale2,
-                   cudaStream_t st) {
+                   int batch, cudaStream_t st) {
     const float r1 = (float)(1.0 / scale1), r2 = (float)(1.0 / scale2);
-    ProfScope ps(KF_INTERP, st, 0, 4.0 * C * ((double)T + Tz));
-    interp_kernel<<<dim3(ceil_div(Tz, 32), ceil_div(C, 32)), dim3(32, 8), 0, st>>>(latents, z, T, C, T1, Tz, r1, r2);
+    ProfScope ps(KF_INTERP, st, 0, 4.0 * C * ((double)T + Tz) * batch);
+    interp_kernel<<<dim3(ceil_div(Tz, 32), ceil_div(C, 32), batch), dim3(32, 8), 0, st>>>(latents, z, T, C, T1, Tz, r1, r2);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 
 void launch_conv1d(const float* x, const float* w_t, const float* bias, const float* cbias, const float* resid,
                    float* out, int Cin, int Cout, int L, int K, int dil, float in_scale, float slope, int mode,
-                   cudaStream_t st) {
-    if (L <= 0) return;
+                   int batch, int cbias_bs, cudaStream_t st) {
+    if (L <= 0 || batch <= 0) return;
     switch (K) {
-        case 3: conv1d_dispatch<3>(x, w_t, bias, cbias, resid, out, Cin, Cout, L, dil, in_scale, slope, mode, st); break;
-        case 7: conv1d_dispatch<7>(x, w_t, bias, cbias, resid, out, Cin, Cout, L, dil, in_scale, slope, mode, st); break;
-        case 11: conv1d_dispatch<11>(x, w_t, bias, cbias, resid, out, Cin, Cout, L, dil, in_scale, slope, mode, st); break;
+        case 3: conv1d_dispatch<3>(x, w_t, bias, cbias, resid, out, Cin, Cout, L, dil, in_scale, slope, mode, batch, cbias_bs, st); break;
+        case 7: conv1d_dispatch<7>(x, w_t, bias, cbias, resid, out, Cin, Cout, L, dil, in_scale, slope, mode, batch, cbias_bs, st); break;
+        case 11: conv1d_dispatch<11>(x, w_t, bias, cbias, resid, out, Cin, Cout, L, dil, in_scale, slope, mode, batch, cbias_bs, st); break;
         default: throw CudaError("conv1d: unsupported kernel size (3, 7, 11 only)");
     }
 }
 
 void launch_conv_transpose1d(const float* x, const float* w_t, const float* bias, const float* cbias, float* out,
-                             int Cin, int Cout, int Lin, int K, int u, float in_scale, float slope,
-                             cudaStream_t st) {
+                             int Cin, int Cout, int Lin, int K, int u, float in_scale, float slope, int batch,
+                             int cbias_bs, cudaStream_t st) {
     if (K != 2 * u || (u & 1)) throw CudaError("conv_transpose1d: only kernel == 2*stride with even stride is supported");
     if (UP_T % u != 0) throw CudaError("conv_transpose1d: stride must divide 128");
     const int XS = UP_T / u + 3;
     const size_t smem = (size_t)(((UP_CI * XS + 3) / 4) * 4 + UP_CI * K * (UP_CO + 4)) * sizeof(float);
-    dim3 grid(ceil_div(Lin * u, UP_T), ceil_div(Cout, UP_CO));
-    ProfScope ps(KF_CONVT, st, 4.0 * Cin * Cout * (double)Lin * u, 4.0 * ((double)Lin * Cin + (double)Lin * u * Cout + (double)Cin * Cout * K));
-    conv_transpose1d_kernel<<<grid, UP_T, smem, st>>>(x, w_t, bias, cbias, out, Cin, Cout, Lin, K, u, in_scale, slope);
+    dim3 grid(ceil_div(Lin * u, UP_T), ceil_div(Cout, UP_CO), batch);
+    ProfScope ps(KF_CONVT, st, 4.0 * Cin * Cout * (double)Lin * u * batch, 4.0 * (batch * ((double)Lin * Cin + (double)Lin * u * Cout) + (double)Cin * Cout * K));
+    conv_transpose1d_kernel<<<grid, UP_T, smem, st>>>(x, w_t, bias, cbias, out, Cin, Cout, Lin, K, u, in_scale, slope, cbias_bs);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 
 void launch_conv_post(const float* x, const float* w, float* wav, int Cin, int L, int K, float in_scale, float slope,
-                      cudaStream_t st) {
-    ProfScope ps(KF_CONV_POST, st, 2.0 * Cin * K * (double)L, 4.0 * (double)L * (Cin + 1));
-    conv_post_kernel<<<ceil_div(L, 256), 256, Cin * K * sizeof(float), st>>>(x, w, wav, Cin, L, K, in_scale, slope);
+                      int batch, cudaStream_t st) {
+    ProfScope ps(KF_CONV_POST, st, 2.0 * Cin * K * (double)L * batch, 4.0 * (double)L * (Cin + 1) * batch);
+    conv_post_kernel<<<dim3(ceil_div(L, 256), batch), 256, Cin * K * sizeof(float), st>>>(x, w, wav, Cin, L, K, in_scale, slope);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 

@@ -93,6 +93,7 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
         self._waiters: Dict[int, Tuple[asyncio.AbstractEventLoop, asyncio.Future]] = {}
         self._wlock = threading.Lock()
         self._stop = False
+        self._paused = False       # set while a caller drives the native completion queue itself (bench device arm)
         self._poller = threading.Thread(target=self._poll_loop, name="xtts-poll", daemon=True)
         self._poller.start()
 
@@ -227,6 +228,15 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
                 yield TTSOutput(array=output.wav, start_time=request.start_time if request else None,
                                 token_length=len(output.token_ids))
 
+    def run_batch_direct(self, jobs, **kw):
+        """Drive the native engine synchronously (no asyncio): the poller thread is parked for the duration."""
+        self._paused = True
+        time.sleep(0.12)                      # let an in-flight poll() time out
+        try:
+            return self.native.run_batch(jobs, **kw)
+        finally:
+            self._paused = False
+
     async def shutdown(self):
         self._stop = True
         self._poller.join(timeout=5)
@@ -235,8 +245,11 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
     # ---- completion dispatch ----------------------------------------------------------------
     def _poll_loop(self):
         while not self._stop:
+            if self._paused:
+                time.sleep(0.01)
+                continue
             try:
-                r = self.native.poll(200)
+                r = self.native.poll(50)
             except Exception:
                 if self._stop:
                     return

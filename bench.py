@@ -242,7 +242,7 @@ def main():
                                      stop_token=dims.gpt.stop_audio_token, seed=SEED + step_idx, seq_seed=sid, vocode=True)
                 jobs.append((sid, ids, spk_slots[ri % 4], sp))
                 sid += 1
-        res = ne.run_batch(jobs, timeout_s=3600, want_wav=False)
+        res = eng.run_batch_direct(jobs, timeout_s=900, want_wav=False)
         return sum(r.n_samples for (r, _, _, _) in res.values()), sum(r.n_tokens for (r, _, _, _) in res.values())
 
     def e2e_step(step_idx: int):
@@ -256,6 +256,10 @@ def main():
             local_w = {rank * len(outs) + i: o.array for i, o in enumerate(outs)}
             parallel.gather_waveforms(local_w, world * len(outs), torch.device("cuda", local))
         return sum(o.array.shape[0] for o in outs), sum(len(t) for t in texts)
+
+    def log(msg):
+        if rank == 0:
+            print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
     def barrier():
         if world > 1:
@@ -273,27 +277,35 @@ def main():
         return dt, acc, (t0w, time.time())
 
     # ---- device-resident arm
+    log(f"engine up: {n_chunks} chunks/GPU, {max_tok} tokens/chunk, precision {args.precision}")
     ne.set_option("d2h_wav", 0)
-    ne.set_option("profile", 1)
     sampler = ClockSampler(local) if rank == 0 else None
     for i in range(args.warmup):
+        t_w = time.perf_counter()
         device_step(i)
+        log(f"warm-up step {i}: {time.perf_counter() - t_w:.2f}s")
     ne.set_option("reset_stats", 0)
-    ne.set_option("profile", 1)          # resets the per-family accumulators
     if sampler:
         sampler.start()
     dt_dev, acc_dev, span = timed(device_step, 0, args.steps)
     clocks = sampler.stop(*span) if sampler else None
-    prof = ne.kernel_profile()
     st = ne.stats()
-    ne.set_option("profile", 0)
     samples_dev = sum(a[0] for a in acc_dev)
     tokens_dev = sum(a[1] for a in acc_dev)
+    log(f"device arm: {dt_dev:.2f}s for {args.steps} step(s)")
+    # ---- kernel-family profile: one more identical step with CUDA events around every launch (eager launches; the
+    # timed steps replay the decode step as a CUDA graph, which event pairs cannot bracket kernel by kernel)
+    ne.set_option("profile", 1)
+    device_step(args.warmup + args.steps)
+    prof = ne.kernel_profile()
+    ne.set_option("profile", 0)
+    log("profile step done")
 
     # ---- end-to-end arm (public API, host buffers)
     ne.set_option("d2h_wav", 1)
     dt_e2e, acc_e2e, _ = timed(e2e_step, 1, args.steps)
     samples_e2e = sum(a[0] for a in acc_e2e)
+    log(f"e2e arm: {dt_e2e:.2f}s for {args.steps} step(s)")
     h2d = sum(len(ids) * 4 for chunks in reqs_chunks for ids in chunks)
     d2h = samples_e2e // max(1, args.steps) * 4 + n_chunks * max_tok * 4
 
@@ -353,6 +365,7 @@ def main():
                    "vocoder_compute": "fp32",
                    "l2": "no explicit flush: per-step working set (0.76 GB weights + >5 GB KV + 0.4 GB vocoder activations) >> 126 MB L2",
                    "timing": "host perf_counter bracketed by barrier + cuda synchronize (device idle on both sides); max over ranks",
+                   "roofline_timing": "CUDA events around every launch on the engine stream, in one extra identical step right after the timed ones (eager launches)",
                    "e2e_speakers": "4 reference wavs conditioned on the GPU before the timed region (per-speaker cache, as prepare_for_streaming_generation)"},
         "gpt_tokens_per_s": tokens_dev / dt_dev, "rtf": 1.0 / value,
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
