@@ -281,16 +281,17 @@ void launch_conv1d_tc(const float* x, const __half* wblob, const ConvTcPlan& pl,
     P.cbias_bs = cbias_batch_stride;
     const size_t a_stage = (size_t)P.rows * 16 * (pl.CK / 8), b_stage = (size_t)pl.N * 16 * (pl.CK / 8);
     const size_t smem = ((SA * a_stage + 127) & ~(size_t)127) + SB * b_stage + 128;
-    if (smem > 227 * 1024) throw CudaError("conv1d_tc: shared memory budget exceeded");
+    constexpr int kMaxDyn = 227 * 1024 - 2048;      // opt-in limit minus this kernel's static shared memory
+    if (smem > (size_t)kMaxDyn) throw CudaError("conv1d_tc: shared memory budget exceeded");
     dim3 grid(ceil_div(L, 128 * pl.nacc), pl.n_tiles, batch);
     ProfScope ps(KF_CONV1D_TC, st, 2.0 * Cin * Cout * K * (double)L * batch,
                  batch * 4.0 * ((double)L * (Cin + Cout * (1 + (resid ? 1 : 0) + (mode == CONV_ACCUM ? 1 : 0)))) + 2.0 * Cin * Cout * K);
     static bool attr2 = false, attr4 = false;
     if (pl.nacc == 2) {
-        if (!attr2) { CUDA_CHECK(cudaFuncSetAttribute(conv1d_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr2 = true; }
+        if (!attr2) { CUDA_CHECK(cudaFuncSetAttribute(conv1d_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn)); attr2 = true; }
         conv1d_tc_kernel<2><<<grid, kThreadsTC, smem, st>>>(P);
     } else {
-        if (!attr4) { CUDA_CHECK(cudaFuncSetAttribute(conv1d_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr4 = true; }
+        if (!attr4) { CUDA_CHECK(cudaFuncSetAttribute(conv1d_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn)); attr4 = true; }
         conv1d_tc_kernel<4><<<grid, kThreadsTC, smem, st>>>(P);
     }
     COUNT_LAUNCH(); KERNEL_CHECK();

@@ -182,7 +182,7 @@ private:
     std::vector<std::unique_ptr<DBuf<__nv_bfloat16>>> k16, v16;
     std::vector<int> free_pages;
     // GPT workspace
-    DBuf<float> wX, wQKV, wLOG;
+    DBuf<float> wX, wQKV, wLOG, wPART;
     DBuf<float> wXn32, wATT32, wFF32, wY32;
     DBuf<__nv_bfloat16> wXn16, wATT16, wFF16, wY16;
     // pinned staging
@@ -209,6 +209,7 @@ private:
     std::atomic<bool> stop{false};
     int inflight = 0;
     bool d2h_wav = true;
+    bool use_splitk = true;       // option "splitk"
     bool use_graphs = true;       // option "cuda_graphs"
     int eager_steps_done = 0;
     std::map<int, cudaGraphExec_t> decode_graphs;
@@ -323,6 +324,7 @@ Engine::Engine(const xtts_config& c) : cfg(c) {
     d_attnseq.alloc(NSLOT);
     const size_t Mmax = (size_t)std::max(prefill_rows_cap, NSLOT);
     wX.alloc(Mmax * H); wQKV.alloc(Mmax * 3 * H); wLOG.alloc((size_t)std::max(NSLOT, CAP + 1) * Vpad);
+    if (bf16) wPART.alloc((size_t)8 * NSLOT * H);
     if (bf16) { wXn16.alloc(Mmax * H); wATT16.alloc(Mmax * H); wFF16.alloc(Mmax * FF); wY16.alloc((size_t)std::max(NSLOT, CAP + 1) * H); }
     else { wXn32.alloc(Mmax * H); wATT32.alloc(Mmax * H); wFF32.alloc(Mmax * FF); wY32.alloc((size_t)std::max(NSLOT, CAP + 1) * H); }
 
@@ -641,10 +643,18 @@ void Engine::layers_forward(int M, bool prefill, int nseq, int max_nq) {
     void* ATT = bf16 ? (void*)wATT16.p : (void*)wATT32.p;
     void* FFb = bf16 ? (void*)wFF16.p : (void*)wFF32.p;
     const int oflag = bf16 ? GEMM_OUT_BF16 : 0;
+    // Decode-shaped steps in fast mode: the two N = hidden GEMMs (attention out-proj, MLP down-proj) expose only
+    // N/BN CTAs, so they run split-K into fp32 partials and the reduction is fused with the residual add and the
+    // following LayerNorm (fixed summation order => deterministic).
+    const bool splitk = bf16 && !prefill && use_splitk && M <= NSLOT && (H / 64) % 4 == 0 && (FF / 64) % 8 == 0;
+    auto ln = [&](const float* w, const float* b) {
+        if (bf16) launch_layernorm<__nv_bfloat16>(wX.p, w, b, wXn16.p, M, H, cfg.ln_eps, st);
+        else launch_layernorm<float>(wX.p, w, b, wXn32.p, M, H, cfg.ln_eps, st);
+    };
+    if (splitk) ln(layers[0]->ln1w.p, layers[0]->ln1b.p);
     for (int l = 0; l < L; ++l) {
         Layer& ly = *layers[l];
-        if (bf16) launch_layernorm<__nv_bfloat16>(wX.p, ly.ln1w.p, ly.ln1b.p, wXn16.p, M, H, cfg.ln_eps, st);
-        else launch_layernorm<float>(wX.p, ly.ln1w.p, ly.ln1b.p, wXn32.p, M, H, cfg.ln_eps, st);
+        if (!splitk) ln(ly.ln1w.p, ly.ln1b.p);
         gemm(Xn, ly.qkv, nullptr, wQKV.p, M, 0);
         if (prefill) {
             if (bf16) launch_kv_write<__nv_bfloat16>(wQKV.p, M, d_row_slot.p, d_row_pos.p, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p, NH, st);
@@ -664,11 +674,21 @@ void Engine::layers_forward(int M, bool prefill, int nseq, int max_nq) {
                 launch_attn_decode<float, float>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, k32[l]->p, v32[l]->p, wATT32.p, NH, st, decode_ctx_sum);
             }
         }
-        gemm(ATT, ly.o, wX.p, wX.p, M, GEMM_RESID);
-        if (bf16) launch_layernorm<__nv_bfloat16>(wX.p, ly.ln2w.p, ly.ln2b.p, wXn16.p, M, H, cfg.ln_eps, st);
-        else launch_layernorm<float>(wX.p, ly.ln2w.p, ly.ln2b.p, wXn32.p, M, H, cfg.ln_eps, st);
-        gemm(Xn, ly.fc, nullptr, FFb, M, GEMM_GELU | oflag);
-        gemm(FFb, ly.proj, wX.p, wX.p, M, GEMM_RESID);
+        if (splitk) {
+            launch_gemm_bf16_tc_splitk(wATT16.p, ly.o.w16.p, wPART.p, M, H, H, 4, st);
+            launch_residual_reduce_layernorm<__nv_bfloat16>(wX.p, wPART.p, 4, ly.o.b.p, ly.ln2w.p, ly.ln2b.p, wXn16.p, M, H, cfg.ln_eps, st);
+            gemm(Xn, ly.fc, nullptr, FFb, M, GEMM_GELU | oflag);
+            launch_gemm_bf16_tc_splitk(wFF16.p, ly.proj.w16.p, wPART.p, M, H, FF, 8, st);
+            const bool last = (l + 1 == L);
+            launch_residual_reduce_layernorm<__nv_bfloat16>(wX.p, wPART.p, 8, ly.proj.b.p, last ? nullptr : layers[l + 1]->ln1w.p,
+                                                            last ? nullptr : layers[l + 1]->ln1b.p, last ? nullptr : wXn16.p, M, H,
+                                                            cfg.ln_eps, st);
+        } else {
+            gemm(ATT, ly.o, wX.p, wX.p, M, GEMM_RESID);
+            ln(ly.ln2w.p, ly.ln2b.p);
+            gemm(Xn, ly.fc, nullptr, FFb, M, GEMM_GELU | oflag);
+            gemm(FFb, ly.proj, wX.p, wX.p, M, GEMM_RESID);
+        }
     }
 }
 
@@ -1094,6 +1114,7 @@ void Engine::set_option(const std::string& k, int64_t v) {
     if (k == "d2h_wav") d2h_wav = v != 0;
     else if (k == "tc_vocoder") use_tc_vocoder = v != 0;
     else if (k == "cuda_graphs") use_graphs = v != 0;
+    else if (k == "splitk") { use_splitk = v != 0; for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second); decode_graphs.clear(); }
     else if (k == "profile") { CUDA_CHECK(cudaSetDevice(cfg.device)); CUDA_CHECK(cudaStreamSynchronize(st)); g_prof.reset(); g_prof.enabled = v != 0; }
     else if (k == "reset_stats") {
         st_decode_steps = st_prefill_rows = st_tokens = st_samples = 0; st_gpt_ms = st_voc_ms = st_cond_ms = 0;

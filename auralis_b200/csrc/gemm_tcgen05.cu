@@ -87,6 +87,7 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const float* __restrict__ bias, const float* resid, void* out, int M, int N, int K, int flags) {
+    // (bias / out / flags are re-pointed below for split-K launches)
     constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ uint8_t smem_raw[];
@@ -101,7 +102,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-    const int num_kb = K / BK;
+    // split-K: gridDim.z CTAs share one output tile, each owning a contiguous range of k-blocks and writing its raw
+    // fp32 partial tile to out + z*M*N (bias/activation/residual are applied by the consumer, deterministically)
+    const int total_kb = K / BK;
+    const int kb_per = (total_kb + gridDim.z - 1) / gridDim.z;
+    const int kb_begin = blockIdx.z * kb_per;
+    const int num_kb = max(0, min(total_kb, kb_begin + kb_per) - kb_begin);
+    if (gridDim.z > 1) {
+        out = reinterpret_cast<float*>(out) + (size_t)blockIdx.z * M * N;
+        bias = nullptr; flags = 0;
+    }
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -127,8 +137,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1, 1);
                 mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
-                tma_load_2d(sA + s * A_BYTES, &tmA, &full_bar[s], kb * BK, m0);
-                tma_load_2d(sB + s * B_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+                tma_load_2d(sA + s * A_BYTES, &tmA, &full_bar[s], (kb_begin + kb) * BK, m0);
+                tma_load_2d(sB + s * B_BYTES, &tmB, &full_bar[s], (kb_begin + kb) * BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -234,14 +244,14 @@ void encode_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, u
 
 template <int BN>
 void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, const float* resid, void* out, int M,
-               int N, int K, int flags, cudaStream_t st) {
+               int N, int K, int flags, cudaStream_t st, int splits = 1) {
     constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+    dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
     ProfScope ps(KF_GEMM_TC, st, 2.0 * M * N * K,
                  2.0 * ((double)M * K + (double)N * K) + ((flags & GEMM_OUT_BF16) ? 2.0 : 4.0) * M * N);
     gemm_bf16_tc_kernel<BN><<<grid, kThreads, smem, st>>>(tmA, tmB, bias, resid, out, M, N, K, flags);
@@ -290,6 +300,25 @@ void launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const f
     if (bn == 128) launch_bn<128>(tmA, tmB, bias, resid, out, M, N, K, flags, st);
     else if (bn == 64) launch_bn<64>(tmA, tmB, bias, resid, out, M, N, K, flags, st);
     else launch_bn<32>(tmA, tmB, bias, resid, out, M, N, K, flags, st);
+}
+
+
+// split-K variant for the skinny decode GEMMs (N = hidden): partials[z][M][N] = A[:, kz] . W[:, kz]^T, fp32, no epilogue
+void launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, float* partials, int M, int N, int K,
+                                int splits, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return;
+    if (K % BK != 0 || N % 32 != 0 || splits < 1 || (K / BK) % splits != 0) throw CudaError("gemm_bf16_tc_splitk: bad shape");
+    if (!g_encode) { std::string err; if (!gemm_tc_init(&err)) throw CudaError(err); }
+    const int mt = ceil_div(M, BM);
+    int bn = 128;
+    if (N % 128 != 0 || mt * (N / 128) * splits < 148) bn = 64;
+    if (bn == 64 && (N % 64 != 0 || mt * (N / 64) * splits < 148)) bn = 32;
+    CUtensorMap tmA, tmB;
+    encode_2d(&tmA, A, (uint64_t)M, (uint64_t)K, BM);
+    encode_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint32_t)bn);
+    if (bn == 128) launch_bn<128>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits);
+    else if (bn == 64) launch_bn<64>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits);
+    else launch_bn<32>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits);
 }
 
 }  // namespace xtts

@@ -87,6 +87,28 @@ __device__ __forceinline__ void smem_layernorm(float* buf, const float* __restri
 
 template <typename TOut>
 __global__ void __launch_bounds__(256)
+residual_reduce_ln_kernel(float* __restrict__ X, const float* __restrict__ P, int splits, size_t split_stride,
+                          const float* __restrict__ bias, const float* __restrict__ w, const float* __restrict__ b,
+                          TOut* __restrict__ Y, int H, float eps) {
+    extern __shared__ float buf[];
+    __shared__ float red[32];
+    float* x = X + (size_t)blockIdx.x * H;
+    const float* p = P + (size_t)blockIdx.x * H;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        float v = x[c] + bias[c];
+        for (int z = 0; z < splits; ++z) v += p[(size_t)z * split_stride + c];      // fixed order: deterministic
+        x[c] = v;
+        buf[c] = v;
+    }
+    __syncthreads();
+    if (Y == nullptr) return;
+    smem_layernorm(buf, w, b, H, eps, red);
+    TOut* y = Y + (size_t)blockIdx.x * H;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) y[c] = from_f32<TOut>(buf[c]);
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(256)
 head_norms_kernel(const float* __restrict__ X, const int* __restrict__ row_index, const float* __restrict__ lnf_w,
                   const float* __restrict__ lnf_b, const float* __restrict__ fn_w, const float* __restrict__ fn_b,
                   TOut* __restrict__ Y, float* __restrict__ latents, const int* __restrict__ slots,
@@ -555,6 +577,17 @@ void launch_layernorm(const float* X, const float* w, const float* b, TOut* Y, i
 }
 template void launch_layernorm<float>(const float*, const float*, const float*, float*, int, int, float, cudaStream_t);
 template void launch_layernorm<__nv_bfloat16>(const float*, const float*, const float*, __nv_bfloat16*, int, int, float, cudaStream_t);
+
+template <typename TOut>
+void launch_residual_reduce_layernorm(float* X, const float* partials, int splits, const float* bias, const float* w,
+                                      const float* b, TOut* Y, int M, int H, float eps, cudaStream_t st) {
+    if (M <= 0) return;
+    ProfScope ps(KF_NORM, st, 0, (8.0 + 4.0 * splits + sizeof(TOut)) * M * H);
+    residual_reduce_ln_kernel<TOut><<<M, 256, H * sizeof(float), st>>>(X, partials, splits, (size_t)M * H, bias, w, b, Y, H, eps);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+template void launch_residual_reduce_layernorm<float>(float*, const float*, int, const float*, const float*, const float*, float*, int, int, float, cudaStream_t);
+template void launch_residual_reduce_layernorm<__nv_bfloat16>(float*, const float*, int, const float*, const float*, const float*, __nv_bfloat16*, int, int, float, cudaStream_t);
 
 template <typename TOut>
 void launch_head_norms(const float* X, const int* row_index, const float* lnf_w, const float* lnf_b,

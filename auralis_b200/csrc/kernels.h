@@ -20,6 +20,8 @@ void launch_gemm_f32(const float* A, const float* W, const float* bias, const fl
 // out is fp32 unless GEMM_OUT_BF16.  K % 64 == 0, N % 16 == 0 required.
 void launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const float* resid,
                          void* out, int M, int N, int K, int flags, cudaStream_t st);
+void launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, float* partials, int M, int N, int K,
+                                int splits, cudaStream_t st);
 bool gemm_tc_init(std::string* err);   // resolves cuTensorMapEncodeTiled; false -> err filled
 
 void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st);
@@ -50,6 +52,12 @@ void launch_build_decode_rows(const int* active, int M, const int* last_tok, con
 template <typename TOut>
 void launch_layernorm(const float* X, const float* w, const float* b, TOut* Y, int M, int H, float eps,
                       cudaStream_t st);
+
+// X[m] += bias + sum_z partials[z][m]  (deterministic split-K reduction fused with the residual add), then
+// Y[m] = LN(X[m]) when Y != nullptr  (the following block's LayerNorm)
+template <typename TOut>
+void launch_residual_reduce_layernorm(float* X, const float* partials, int splits, const float* bias, const float* w,
+                                      const float* b, TOut* Y, int M, int H, float eps, cudaStream_t st);
 
 // y = LN_fn(LN_lnf(X[row_index[i]]));  Y[i] = y (GEMM operand);
 // latents[slots[i]][lat_pos ? lat_pos[i] : n_gen[slots[i]]] = LN_fn(y)

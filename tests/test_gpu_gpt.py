@@ -182,3 +182,36 @@ def test_bf16_teacher_forced_and_e2e_small(engine_small_bf16, dims_small, state_
         assert margin < 0.1, (k, a, b, margin)
     res = engine_small_bf16.run_batch([(1, ids, 0, sp)], timeout_s=60)
     assert res[1][0].n_tokens == 40 and np.isfinite(res[1][2]).all()
+
+
+def test_bf16_full_size_decode_paths(engine_full_bf16, dims_full, state_full, speakers_full):
+    """full geometry in fast mode: exercises the split-K out-proj/down-proj GEMMs + fused reduce-LayerNorm and the
+    CUDA-graph replay of the decode step (graphs kick in after two eager steps)."""
+    orc = _orc(dims_full, state_full)
+    g = dims_full.gpt
+    ids = text_ids(dims_full, 14, 9)
+    osp = O.SamplingParams(temperature=0.0, repetition_penalty=5.0, max_tokens=20, stop_token=g.stop_audio_token)
+    toks, lats, lg = orc.generate(speakers_full[1][0], ids, osp, return_logits=True)
+    sp = Sampling(temperature=0.0, repetition_penalty=5.0, max_tokens=20, stop_token=g.stop_audio_token)
+    logits, lat, sampled = engine_full_bf16.gpt_teacher_forced(ids, 1, toks, sp)          # eager path
+    err = np.abs(logits - lg.numpy()).max()
+    print("bf16 full teacher-forced logits max err", err, "logit abs max", float(lg.abs().max()))
+    assert err < 0.05 * max(1.0, float(lg.abs().max()))
+    for k, a, b, margin in _margin_report(lg.numpy(), sampled, toks):
+        assert margin < 0.15, (k, a, b, margin)
+    # free-running batch (graph path): same tokens as the eager teacher-forced run unless a near-tie flips
+    res = engine_full_bf16.run_batch([(i, ids, 1, sp) for i in range(3)], timeout_s=120, want_latents=True)
+    for i in range(3):
+        r, got, wav, glat = res[i]
+        assert r.n_tokens == 20 and np.isfinite(wav).all()
+        np.testing.assert_array_equal(got, res[0][1])                        # deterministic across batch slots
+        bad = _margin_report(lg.numpy(), got, toks)
+        assert all(m < 0.15 for (_, _, _, m) in bad), bad
+    engine_full_bf16.set_option("splitk", 0)
+    engine_full_bf16.set_option("cuda_graphs", 0)
+    res2 = engine_full_bf16.run_batch([(7, ids, 1, sp)], timeout_s=120)
+    engine_full_bf16.set_option("splitk", 1)
+    engine_full_bf16.set_option("cuda_graphs", 1)
+    agree = int((res2[7][1] == res[0][1]).sum())
+    print("split-K+graphs vs plain bf16 token agreement", agree, "/ 20")
+    assert agree >= 17
