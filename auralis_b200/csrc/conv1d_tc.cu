@@ -1,17 +1,18 @@
 // Dilated Conv1d ("same" padding) as an implicit GEMM on the 5th-gen tensor cores (fast mode of the vocoder).
 //
-//   out[co][t] (=|+=) bias[co] + cbias[co] + resid[co][t] + sum_j sum_ci W_j[co][ci] * act(s * x[ci][t + (j-c)*d])
+//   y[co][t] = bias[co] + cbias[co] + resid[co][t] + sum_j sum_ci W_j[co][ci] * a[ci][t + (j-c)*d]
 //
-// Mapping (per CTA):  D[M = 128*NACC time steps, N = C_out tile] += A[M, K=16 ci] * B[N, K=16 ci]^T per tap and ci-step
-//   * A (activations): loader warps read fp32 x[ci][t] coalesced along t, apply scale + leaky-relu, convert to fp16 and
-//     store 16-byte atoms into the UMMA *no-swizzle K-major* layout  [ci/8 plane][time row][8 ci]  (SBO = 128 B, so
-//     rows are linear in time and a tap is just a start-address shift of j*d rows — no im2col copy);
-//     staged per 64-channel chunk in a ring, reused by every tap.
-//   * B (weights): pre-packed on the host into the same atom layout per (ci-chunk, tap); each tile is ONE contiguous
-//     cp.async.bulk (TMA 1-D) into a second ring.
-//   * tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM (NACC accumulators of N columns share each B tile),
-//     epilogue warps read TMEM (lane = time step) and store channel-major fp32, coalesced along t.
-// Warp roles: warps 0-3 A-loaders then epilogue (TMEM lane quarter = warp), warp 4 TMA producer, warp 5 MMA issuer.
+// where `a` is the ALREADY ACTIVATED fp16 input kept in HBM in the tensor-core operand layout
+//   "atoms":  [C/8 plane][PADL + L + PADR time rows][8 channels]   (16-byte atoms, zero pads)
+// which is byte-for-byte the UMMA no-swizzle K-major image (SBO = 128 B => rows linear in time), so
+//   * the A tile of a ci-chunk is `CK/8` contiguous cp.async.bulk copies (one per plane), a tap is a start-address
+//     shift of j*d rows inside the staged tile (no im2col, no conversion work in this kernel);
+//   * weights are pre-packed per (ci-chunk, tap) into the same layout: one bulk copy per tile.
+// tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM: NACC accumulators (128 time rows each) share every
+// weight tile.  The epilogue (lane = time step) can emit
+//   * out32: fp32 channel-major [C][L]  (store or accumulate)  — the residual stream / MRF sum
+//   * out16: lrelu(y, slope_out) as fp16 atoms                 — the next conv's operand, written once, read once.
+// Warp roles: warps 0-3 epilogue (TMEM lane quarter = warp), warp 4 bulk-copy producer, warp 5 MMA issuer.
 //
 // Replaces the cuDNN fp16-autocast Conv1d calls of HifiganGenerator.forward / ResBlock1.forward
 // (hifigan_decoder.py:76-91,241-259; the reference runs them in fp16 under torch.amp.autocast on GPU, App. B.8).
@@ -26,9 +27,6 @@ constexpr int SA = 2, SB = 3;          // ring depths (activation chunks, weight
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(uint64_t* b, uint32_t c) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(c) : "memory");
-}
-__device__ __forceinline__ void bar_arrive(uint64_t* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory");
 }
 __device__ __forceinline__ void bar_expect_tx(uint64_t* b, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory");
@@ -48,6 +46,10 @@ __device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity, int tag) 
             __trap();
         }
     }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
 }
 // no-swizzle K-major descriptor: rows 16 B apart (SBO = 128 B per 8 rows), the two 8-element K halves `lbo` bytes apart
 __device__ __forceinline__ uint64_t desc_nosw(uint32_t addr, uint32_t lbo_bytes) {
@@ -69,10 +71,14 @@ __device__ __forceinline__ void mma_commit(uint64_t* b) {
 __device__ __forceinline__ float lrelu_s(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 struct ConvTcParams {
-    const float* x; const __half* wblob; const float* bias; const float* cbias; const float* resid; float* out;
-    int Cin, Cout, L, K, dil, mode;
-    float in_scale, slope;
-    int N;          // output channels per CTA (<= 256, multiple of 16)
+    const __half* a16;       // input atoms  [batch][Cin/8][lpad][8]
+    const __half* wblob;
+    const float* bias; const float* cbias; const float* resid;
+    float* out32;            // [batch][Cout][L] or nullptr
+    __half* out16;           // output atoms [batch][Cout/8][lpad][8] or nullptr
+    int Cin, Cout, L, lpad, K, dil, mode;
+    float slope_out;
+    int N;          // output channels per CTA (<= 256, multiple of 32)
     int CK;         // input channels per chunk (<= 64, multiple of 16)
     int rows;       // time rows staged per chunk = 128*NACC + (K-1)*dil
     int cbias_bs;   // elements between the speaker-bias vectors of consecutive batch items
@@ -96,17 +102,11 @@ conv1d_tc_kernel(const ConvTcParams P) {
     const uint32_t b_stage = b_plane * planes;
     uint8_t* sA = smem;
     uint8_t* sB = smem + ((SA * a_stage + 127) & ~127u);
-    const float* x = P.x + (size_t)blockIdx.z * P.Cin * P.L;
-    float* out = P.out + (size_t)blockIdx.z * P.Cout * P.L;
-    const float* resid = P.resid ? P.resid + (size_t)blockIdx.z * P.Cout * P.L : nullptr;
-    const float* cbias = P.cbias ? P.cbias + (size_t)blockIdx.z * P.cbias_bs : nullptr;
-    constexpr uint32_t TM_COLS_MAX = 512;
     uint32_t tm_cols = 32;
     while (tm_cols < (uint32_t)(NACC * P.N)) tm_cols <<= 1;
-    if (tm_cols > TM_COLS_MAX) tm_cols = TM_COLS_MAX;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < SA; ++i) { bar_init(&a_full[i], 128); bar_init(&a_empty[i], 1); }
+        for (int i = 0; i < SA; ++i) { bar_init(&a_full[i], 1); bar_init(&a_empty[i], 1); }
         for (int i = 0; i < SB; ++i) { bar_init(&b_full[i], 1); bar_init(&b_empty[i], 1); }
         bar_init(&tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -121,34 +121,13 @@ conv1d_tc_kernel(const ConvTcParams P) {
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp < 4) {
-        // ------------------------------------------------ activation loaders (128 threads)
-        const int tid = threadIdx.x;
-        const int items = planes * P.rows;
-        for (int c = 0; c < nch; ++c) {
-            const int s = c % SA;
-            bar_wait(&a_empty[s], ((c / SA) & 1) ^ 1, 1);
-            uint8_t* dst = sA + (size_t)s * a_stage;
-            for (int it = tid; it < items; it += 128) {
-                const int p = it / P.rows, r = it - p * P.rows;
-                const int gt = T0 - halo + r;
-                uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-                if (gt >= 0 && gt < P.L) {
-                    const float* src = x + (size_t)(c * P.CK + p * 8) * P.L + gt;
-                    float v[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = lrelu_s(P.in_scale * __ldg(src + (size_t)e * P.L), P.slope);
-                    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-                    __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
-                    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                }
-                *reinterpret_cast<uint4*>(dst + (size_t)p * a_plane + (size_t)r * 16) = pk;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (UMMA)
-            bar_arrive(&a_full[s]);
-        }
         // ------------------------------------------------ epilogue: warp q owns TMEM lanes [32q, 32q+32) = time rows
         const int q = warp;
+        const size_t zo = (size_t)blockIdx.z;
+        float* out32 = P.out32 ? P.out32 + zo * P.Cout * P.L : nullptr;
+        const float* resid = P.resid ? P.resid + zo * P.Cout * P.L : nullptr;
+        const float* cbias = P.cbias ? P.cbias + zo * P.cbias_bs : nullptr;
+        uint4* out16 = P.out16 ? reinterpret_cast<uint4*>(P.out16) + zo * (size_t)(P.Cout / 8) * P.lpad : nullptr;
         bar_wait(&tmem_full, 0, 4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -169,34 +148,59 @@ conv1d_tc_kernel(const ConvTcParams P) {
                     : "r"(taddr) : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (t < P.L) {
+                    const int cb = n0 + nc * 32;
+                    float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const int co = n0 + nc * 32 + i;
-                        if (co < P.Cout) {
-                            const size_t o = (size_t)co * P.L + t;
-                            float v = __uint_as_float(r[i]) + (P.bias ? __ldg(P.bias + co) : 0.f) + (cbias ? __ldg(cbias + co) : 0.f);
-                            if (resid) v += resid[o];
-                            if (P.mode == CONV_ACCUM) v += out[o];
-                            out[o] = v;
+                        const int co = cb + i;
+                        float x = __uint_as_float(r[i]) + (P.bias ? __ldg(P.bias + co) : 0.f) + (cbias ? __ldg(cbias + co) : 0.f);
+                        if (resid) x += resid[(size_t)co * P.L + t];
+                        v[i] = x;
+                    }
+                    if (out32) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const size_t o = (size_t)(cb + i) * P.L + t;
+                            out32[o] = (P.mode == CONV_ACCUM) ? out32[o] + v[i] : v[i];
+                        }
+                    }
+                    if (out16) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            __half2 h0 = __floats2half2_rn(lrelu_s(v[8 * g + 0], P.slope_out), lrelu_s(v[8 * g + 1], P.slope_out));
+                            __half2 h1 = __floats2half2_rn(lrelu_s(v[8 * g + 2], P.slope_out), lrelu_s(v[8 * g + 3], P.slope_out));
+                            __half2 h2 = __floats2half2_rn(lrelu_s(v[8 * g + 4], P.slope_out), lrelu_s(v[8 * g + 5], P.slope_out));
+                            __half2 h3 = __floats2half2_rn(lrelu_s(v[8 * g + 6], P.slope_out), lrelu_s(v[8 * g + 7], P.slope_out));
+                            uint4 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            out16[(size_t)(cb / 8 + g) * P.lpad + (t + kAtomPadL)] = pk;
                         }
                     }
                 }
             }
         }
     } else if (warp == 4) {
-        // ------------------------------------------------ weight tiles: one bulk copy per (ci-chunk, tap)
+        // ------------------------------------------------ producer: activation planes + weight tiles, all bulk copies
         if (lane == 0) {
             const __half* wsrc = P.wblob + (size_t)blockIdx.y * nch * P.K * (b_stage / 2);
+            const __half* asrc = P.a16 + (size_t)blockIdx.z * (size_t)(P.Cin / 8) * P.lpad * 8;
+            const int row0 = T0 - halo + kAtomPadL;                 // first staged time row inside the padded plane
             int it = 0;
-            for (int c = 0; c < nch; ++c)
+            for (int c = 0; c < nch; ++c) {
+                const int sa = c % SA;
+                bar_wait(&a_empty[sa], ((c / SA) & 1) ^ 1, 1);
+                bar_expect_tx(&a_full[sa], a_stage);
+                for (int p = 0; p < planes; ++p)
+                    bulk_g2s(sA + (size_t)sa * a_stage + (size_t)p * a_plane,
+                             asrc + ((size_t)(c * planes + p) * P.lpad + row0) * 8, a_plane, &a_full[sa]);
                 for (int j = 0; j < P.K; ++j, ++it) {
                     const int s = it % SB;
                     bar_wait(&b_empty[s], ((it / SB) & 1) ^ 1, 2);
                     bar_expect_tx(&b_full[s], b_stage);
-                    const __half* src = wsrc + (size_t)it * (b_stage / 2);
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(s_u32(sB + (size_t)s * b_stage)), "l"(src), "r"(b_stage), "r"(s_u32(&b_full[s])) : "memory");
+                    bulk_g2s(sB + (size_t)s * b_stage, wsrc + (size_t)it * (b_stage / 2), b_stage, &b_full[s]);
                 }
+            }
         }
     } else {
         // ------------------------------------------------ MMA issuer
@@ -235,6 +239,19 @@ conv1d_tc_kernel(const ConvTcParams P) {
     }
 }
 
+// zero the head pad and everything from row PADL+L on, for every plane of every batch item
+__global__ void atoms_zero_pads_kernel(uint4* __restrict__ buf, int planes_total, int lpad, int L) {
+    const int pl = blockIdx.y;
+    if (pl >= planes_total) return;
+    uint4* p = buf + (size_t)pl * lpad;
+    const int tail0 = kAtomPadL + L;
+    const int n = kAtomPadL + (lpad - tail0);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int row = (i < kAtomPadL) ? i : tail0 + (i - kAtomPadL);
+        p[row] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -268,24 +285,30 @@ void conv1d_tc_pack(const float* w, int Cin, int Cout, int K, const ConvTcPlan& 
             }
 }
 
-void launch_conv1d_tc(const float* x, const __half* wblob, const ConvTcPlan& pl, const float* bias, const float* cbias,
-                      const float* resid, float* out, int Cin, int Cout, int L, int K, int dil, float in_scale, float slope,
-                      int mode, int batch, int cbias_batch_stride, cudaStream_t st) {
+int atoms_lpad(int L) { return kAtomPadL + ceil_div(L, 512) * 512 + kAtomPadR; }
+
+void launch_conv1d_tc(const __half* a16, const __half* wblob, const ConvTcPlan& pl, const float* bias, const float* cbias,
+                      const float* resid, float* out32, __half* out16, int Cin, int Cout, int L, int lpad, int K, int dil,
+                      float slope_out, int mode, int batch, int cbias_batch_stride, cudaStream_t st) {
     if (L <= 0 || batch <= 0) return;
     if (!pl.ok) throw CudaError("conv1d_tc: unsupported channel geometry");
+    const int tile = 128 * pl.nacc;
+    if (lpad < kAtomPadL + ceil_div(L, tile) * tile + (K - 1) / 2 * dil) throw CudaError("conv1d_tc: atom buffer pad too small");
     ConvTcParams P{};
-    P.x = x; P.wblob = wblob; P.bias = bias; P.cbias = cbias; P.resid = resid; P.out = out;
-    P.Cin = Cin; P.Cout = Cout; P.L = L; P.K = K; P.dil = dil; P.mode = mode; P.in_scale = in_scale; P.slope = slope;
+    P.a16 = a16; P.wblob = wblob; P.bias = bias; P.cbias = cbias; P.resid = resid; P.out32 = out32; P.out16 = out16;
+    P.Cin = Cin; P.Cout = Cout; P.L = L; P.lpad = lpad; P.K = K; P.dil = dil; P.mode = mode; P.slope_out = slope_out;
     P.N = pl.N; P.CK = pl.CK;
-    P.rows = 128 * pl.nacc + (K - 1) * dil;
+    P.rows = tile + (K - 1) * dil;
     P.cbias_bs = cbias_batch_stride;
     const size_t a_stage = (size_t)P.rows * 16 * (pl.CK / 8), b_stage = (size_t)pl.N * 16 * (pl.CK / 8);
     const size_t smem = ((SA * a_stage + 127) & ~(size_t)127) + SB * b_stage + 128;
     constexpr int kMaxDyn = 227 * 1024 - 2048;      // opt-in limit minus this kernel's static shared memory
     if (smem > (size_t)kMaxDyn) throw CudaError("conv1d_tc: shared memory budget exceeded");
-    dim3 grid(ceil_div(L, 128 * pl.nacc), pl.n_tiles, batch);
-    ProfScope ps(KF_CONV1D_TC, st, 2.0 * Cin * Cout * K * (double)L * batch,
-                 batch * 4.0 * ((double)L * (Cin + Cout * (1 + (resid ? 1 : 0) + (mode == CONV_ACCUM ? 1 : 0)))) + 2.0 * Cin * Cout * K);
+    dim3 grid(ceil_div(L, tile), pl.n_tiles, batch);
+    // algorithmic traffic: fp16 atoms in, fp32 residual in, fp32 and/or fp16 out, weights once
+    const double by = batch * (double)L * (2.0 * Cin + (resid ? 4.0 * Cout : 0) + (out32 ? (mode == CONV_ACCUM ? 8.0 : 4.0) * Cout : 0) +
+                                           (out16 ? 2.0 * Cout : 0)) + 2.0 * Cin * Cout * K;
+    ProfScope ps(KF_CONV1D_TC, st, 2.0 * Cin * Cout * K * (double)L * batch, by);
     static bool attr2 = false, attr4 = false;
     if (pl.nacc == 2) {
         if (!attr2) { CUDA_CHECK(cudaFuncSetAttribute(conv1d_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn)); attr2 = true; }
@@ -294,6 +317,13 @@ void launch_conv1d_tc(const float* x, const __half* wblob, const ConvTcPlan& pl,
         if (!attr4) { CUDA_CHECK(cudaFuncSetAttribute(conv1d_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn)); attr4 = true; }
         conv1d_tc_kernel<4><<<grid, kThreadsTC, smem, st>>>(P);
     }
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+
+void launch_atoms_zero_pads(__half* buf, int planes_total, int lpad, int L, cudaStream_t st) {
+    if (planes_total <= 0) return;
+    ProfScope ps(KF_MISC, st, 0, 16.0 * planes_total * (lpad - L));
+    atoms_zero_pads_kernel<<<dim3(2, planes_total), 256, 0, st>>>(reinterpret_cast<uint4*>(buf), planes_total, lpad, L);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 

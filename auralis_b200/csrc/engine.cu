@@ -189,6 +189,8 @@ private:
     int* h_finished = nullptr;
     // vocoder workspace
     DBuf<float> vz, vpre, vb[5], vwav, vlat, vcb;
+    DBuf<__half> vz16, va16[4];   // fp16 operand atoms of the tensor-core vocoder path
+    bool tc_vocoder_ready = false;
     int voc_max_T = 0, VB = 1;
     std::vector<int> stage_ch;
 
@@ -229,6 +231,10 @@ private:
     void make_conv(ConvW& c, const std::string& prefix, bool transposed, bool has_bias);
     void conv1d(const ConvW& c, const float* x, const float* cbias, const float* resid, float* out, int L, int dil,
                 float in_scale, float slope, int mode, int nb);
+    void conv1d_tc(const ConvW& c, const __half* a16, const float* cbias, const float* resid, float* out32, __half* out16,
+                   int L, int lpad, int dil, int mode, int nb);
+    void run_vocoder_tc(const float* lat_dev, int T, int nb, float* wav_dev_out, int* n_out, const char* stage,
+                        float* stage_out, int64_t stage_cap);
     std::vector<float> folded(const std::string& prefix) const;
     GptTables tables() const {
         GptTables t; t.text_emb = text_emb.p; t.text_pos = text_pos.p; t.wte = wte.p; t.wpe = wpe.p;
@@ -484,10 +490,13 @@ void Engine::make_conv(ConvW& c, const std::string& prefix, bool transposed, boo
 // Conv1d through whichever path the weights were prepared for
 void Engine::conv1d(const ConvW& c, const float* x, const float* cbias, const float* resid, float* out, int L, int dil,
                     float in_scale, float slope, int mode, int nb) {
-    if (c.tc && use_tc_vocoder)
-        launch_conv1d_tc(x, c.blob.p, c.plan, c.b.p, cbias, resid, out, c.Cin, c.Cout, L, c.K, dil, in_scale, slope, mode, nb, cbias_stride, st);
-    else
-        launch_conv1d(x, c.wt.p, c.b.p, cbias, resid, out, c.Cin, c.Cout, L, c.K, dil, in_scale, slope, mode, nb, cbias_stride, st);
+    launch_conv1d(x, c.wt.p, c.b.p, cbias, resid, out, c.Cin, c.Cout, L, c.K, dil, in_scale, slope, mode, nb, cbias_stride, st);
+}
+
+void Engine::conv1d_tc(const ConvW& c, const __half* a16, const float* cbias, const float* resid, float* out32, __half* out16,
+                       int L, int lpad, int dil, int mode, int nb) {
+    launch_conv1d_tc(a16, c.blob.p, c.plan, c.b.p, cbias, resid, out32, out16, c.Cin, c.Cout, L, lpad, c.K, dil, 0.1f, mode, nb,
+                     cbias_stride, st);
 }
 
 void Engine::finalize_weights() {
@@ -551,6 +560,20 @@ void Engine::finalize_weights() {
         const HostTensor& pw = need(w + "conv_post.weight");
         post_cin = (int)pw.shape[1];
         up(conv_post_w, pw.data);
+    }
+    if (bf16) {
+        bool all_tc = conv_pre.tc;
+        for (auto& rb : rbs) for (int t = 0; t < 3; ++t) all_tc = all_tc && rb->c1[t]->tc && rb->c2[t]->tc;
+        for (int ch : stage_ch) all_tc = all_tc && (ch % 16 == 0);
+        if (all_tc) {
+            const int T1 = (int)std::floor((double)voc_max_T * ((double)c.code_stride / (double)c.output_hop_length));
+            const int Tz = (int)std::floor((double)T1 * ((double)c.output_sample_rate / (double)c.input_sample_rate));
+            vz16.alloc((size_t)VB * c.voc_in_dim * atoms_lpad(Tz));
+            size_t mx = 0; int len = Tz;
+            for (int i = 0; i < c.voc_n_up; ++i) { len *= c.voc_up_rates[i]; mx = std::max(mx, (size_t)stage_ch[i] * atoms_lpad(len)); }
+            for (auto& b : va16) b.alloc((size_t)VB * mx);
+            tc_vocoder_ready = true;
+        }
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
     // ---- speaker conditioning stack (optional in a checkpoint: without it only xtts_set_speaker works)
@@ -843,6 +866,7 @@ void Engine::run_vocoder(const float* lat_dev, int T, const int* speakers, int n
         CUDA_CHECK(cudaMemcpyAsync(vcb.p + (size_t)i * cbias_stride, spk_cbias.p + (size_t)sp * cbias_stride,
                                    (size_t)cbias_stride * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
+    if (tc_vocoder_ready && use_tc_vocoder) { run_vocoder_tc(lat_dev, T, nb, wav_dev_out, n_out, stage, stage_out, stage_cap); return; }
     const double s1 = (double)c.code_stride / (double)c.output_hop_length;
     const double s2 = (double)c.output_sample_rate / (double)c.input_sample_rate;
     const int T1 = (int)std::floor((double)T * s1);
@@ -855,7 +879,7 @@ void Engine::run_vocoder(const float* lat_dev, int T, const int* speakers, int n
             CUDA_CHECK(cudaMemcpyAsync(stage_out, p, m * sizeof(float), cudaMemcpyDeviceToHost, st));
         }
     };
-    launch_interp(lat_dev, vz.p, T, c.voc_in_dim, T1, Tz, s1, resample ? s2 : 1.0, nb, st);
+    launch_interp(lat_dev, vz.p, nullptr, 0, T, c.voc_in_dim, T1, Tz, s1, resample ? s2 : 1.0, nb, st);
     dump("z", vz.p, (size_t)c.voc_in_dim * Tz);
     conv1d(conv_pre, vz.p, cb + cbias_off[0], nullptr, vpre.p, Tz, 1, 1.0f, 1.0f, CONV_STORE, nb);
     dump("pre", vpre.p, (size_t)c.voc_init_ch * Tz);
@@ -866,8 +890,8 @@ void Engine::run_vocoder(const float* lat_dev, int T, const int* speakers, int n
     float* X = vb[0].p; float* TMP = vb[1].p; float* R1 = vb[2].p; float* R2 = vb[3].p; float* ZS = vb[4].p;
     for (int i = 0; i < c.voc_n_up; ++i) {
         const ConvW& u = *ups[i];
-        launch_conv_transpose1d(cur, u.wt.p, u.b.p, cb + cbias_off[i + 1], X, u.Cin, u.Cout, len, u.K, c.voc_up_rates[i],
-                                in_scale, 0.1f, nb, cbias_stride, st);
+        launch_conv_transpose1d(cur, u.wt.p, u.b.p, cb + cbias_off[i + 1], X, nullptr, 0, 0.f, u.Cin, u.Cout, len, u.K,
+                                c.voc_up_rates[i], in_scale, 0.1f, nb, cbias_stride, st);
         len *= c.voc_up_rates[i];
         const int C = u.Cout;
         { char nm[16]; snprintf(nm, sizeof(nm), "up%d", i); dump(nm, X, (size_t)C * len); }
@@ -890,6 +914,68 @@ void Engine::run_vocoder(const float* lat_dev, int T, const int* speakers, int n
         { char nm[16]; snprintf(nm, sizeof(nm), "mrf%d", i); dump(nm, ZS, (size_t)C * len); }   // un-normalised sum
         // next stage reads the MRF sum scaled by 1/nk; its ConvT writes X (dead by now), and ZS is only
         // overwritten after that ConvT has consumed it (stream order)
+        cur = ZS;
+        in_scale = 1.0f / (float)nk;
+    }
+    launch_conv_post(cur, conv_post_w.p, wav_dev_out, post_cin, len, 7, in_scale, 0.01f, nb, st);
+    *n_out = len;
+}
+
+// Tensor-core vocoder: every Conv1d operand is kept as activated fp16 atoms written by its producer's epilogue
+// (ConvT / previous conv), so the conv kernels are pure bulk-copy + tcgen05; fp32 is kept for the residual stream
+// (x, r1, r2), the MRF sum and the final waveform.  (speaker biases were gathered into vcb by run_vocoder)
+void Engine::run_vocoder_tc(const float* lat_dev, int T, int nb, float* wav_dev_out, int* n_out, const char* stage,
+                            float* stage_out, int64_t stage_cap) {
+    const auto& c = cfg;
+    const double s1 = (double)c.code_stride / (double)c.output_hop_length;
+    const double s2 = (double)c.output_sample_rate / (double)c.input_sample_rate;
+    const int T1 = (int)std::floor((double)T * s1);
+    const bool resample = c.output_sample_rate != c.input_sample_rate;
+    const int Tz = resample ? (int)std::floor((double)T1 * s2) : T1;
+    const float* cb = vcb.p;
+    auto dump = [&](const char* name, const float* p, size_t n) {
+        if (stage && stage_out && std::strcmp(stage, name) == 0) {
+            const size_t m = std::min<size_t>(n, (size_t)stage_cap);
+            CUDA_CHECK(cudaMemcpyAsync(stage_out, p, m * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+    };
+    int lpad = atoms_lpad(Tz);
+    launch_atoms_zero_pads(vz16.p, nb * c.voc_in_dim / 8, lpad, Tz, st);
+    launch_interp(lat_dev, stage ? vz.p : nullptr, vz16.p, lpad, T, c.voc_in_dim, T1, Tz, s1, resample ? s2 : 1.0, nb, st);
+    if (stage) dump("z", vz.p, (size_t)c.voc_in_dim * Tz);
+    conv1d_tc(conv_pre, vz16.p, cb + cbias_off[0], nullptr, vpre.p, nullptr, Tz, lpad, 1, CONV_STORE, nb);
+    dump("pre", vpre.p, (size_t)c.voc_init_ch * Tz);
+    const float* cur = vpre.p;
+    float in_scale = 1.0f;
+    int len = Tz;
+    const int nk = c.voc_n_rb;
+    float* X = vb[0].p; float* R[2] = {vb[2].p, vb[3].p}; float* ZS = vb[4].p;
+    __half* XA = va16[0].p; __half* TA = va16[1].p; __half* RA[2] = {va16[2].p, va16[3].p};
+    for (int i = 0; i < c.voc_n_up; ++i) {
+        const ConvW& u = *ups[i];
+        const int C = u.Cout;
+        const int lout = len * c.voc_up_rates[i];
+        lpad = atoms_lpad(lout);
+        for (__half* b : {XA, TA, RA[0], RA[1]}) launch_atoms_zero_pads(b, nb * C / 8, lpad, lout, st);
+        launch_conv_transpose1d(cur, u.wt.p, u.b.p, cb + cbias_off[i + 1], X, XA, lpad, 0.1f, u.Cin, u.Cout, len, u.K,
+                                c.voc_up_rates[i], in_scale, 0.1f, nb, cbias_stride, st);
+        len = lout;
+        { char nm[16]; snprintf(nm, sizeof(nm), "up%d", i); dump(nm, X, (size_t)C * len); }
+        for (int j = 0; j < nk; ++j) {
+            const RB& rb = *rbs[i * nk + j];
+            const __half* in16 = XA;
+            const float* resid = X;
+            for (int t = 0; t < 3; ++t) {
+                conv1d_tc(*rb.c1[t], in16, nullptr, nullptr, nullptr, TA, len, lpad, c.voc_rb_dilations[t], CONV_STORE, nb);
+                if (t < 2) {
+                    conv1d_tc(*rb.c2[t], TA, nullptr, resid, R[t], RA[t], len, lpad, 1, CONV_STORE, nb);
+                    in16 = RA[t]; resid = R[t];
+                } else {
+                    conv1d_tc(*rb.c2[t], TA, nullptr, resid, ZS, nullptr, len, lpad, 1, j == 0 ? CONV_STORE : CONV_ACCUM, nb);
+                }
+            }
+        }
+        { char nm[16]; snprintf(nm, sizeof(nm), "mrf%d", i); dump(nm, ZS, (size_t)C * len); }
         cur = ZS;
         in_scale = 1.0f / (float)nk;
     }

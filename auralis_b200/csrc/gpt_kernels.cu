@@ -170,37 +170,40 @@ __global__ void kv_write_kernel(const float* __restrict__ QKV, const int* __rest
 // ------------------------------------------------------------------------------------------------
 template <typename TKV> struct KVec;
 template <> struct KVec<float> {
-    static __device__ __forceinline__ float dot(const float* p, const float* q) {
-        const float4 k = *reinterpret_cast<const float4*>(p);
-        return k.x * q[0] + k.y * q[1] + k.z * q[2] + k.w * q[3];
+    static constexpr int X = 4;                       // elements per 16-byte atom
+    static __device__ __forceinline__ void unpack(const uint4& raw, float* f) {
+        f[0] = __uint_as_float(raw.x); f[1] = __uint_as_float(raw.y); f[2] = __uint_as_float(raw.z); f[3] = __uint_as_float(raw.w);
     }
-    static __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 };
 template <> struct KVec<__nv_bfloat16> {
-    static __device__ __forceinline__ float dot(const __nv_bfloat16* p, const float* q) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(p);
+    static constexpr int X = 8;
+    static __device__ __forceinline__ void unpack(const uint4& raw, float* f) {
         const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&raw);
-        float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 f = __bfloat1622float2(b[i]);
-            s = fmaf(f.x, q[2 * i], s);
-            s = fmaf(f.y, q[2 * i + 1], s);
-        }
-        return s;
-    }
-    static __device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {
-        return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+        for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(b[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
     }
 };
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {          // streaming 16-byte load: KV is read once per step
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
 
+// One CTA per (sequence, head); the 4 warps take pages round-robin.  Per 32-token page a warp issues
+//   QK^T : lane = token, 64/X independent 16-byte loads (K atoms of one token are 32*16 B apart, a warp-load is 512 B)
+//   PV   : lane = (token group, 16-byte dim chunk), 32*X/64... independent 16-byte loads, p broadcast by shuffle
+// so ~16 wide loads are in flight per warp and page (the first version issued 32 dependent 4-byte V loads).
+// HBM-bound: algorithmic bytes = 2 * ctx * 64 * sizeof(TKV) per (sequence, head).
 template <typename TKV, typename TOut>
 __global__ void __launch_bounds__(128)
 attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active, const int* __restrict__ ctx_len,
                    const int* __restrict__ block_tables, int max_pages, const TKV* __restrict__ kpool,
                    const TKV* __restrict__ vpool, TOut* __restrict__ out, int heads) {
-    constexpr int X = 16 / sizeof(TKV);
-    constexpr int NCH = kHeadDim / X;
+    constexpr int X = KVec<TKV>::X;
+    constexpr int NCH = kHeadDim / X;                 // 16-byte atoms per token row (8 bf16 / 16 fp32)
+    constexpr int TPI = 32 / NCH;                     // tokens covered by one warp-wide V load (4 / 2)
+    constexpr int VIT = kPageTokens / TPI;            // V loads per page (8 / 16)
     __shared__ __align__(16) float qs[kHeadDim];
     __shared__ float pm[4], pl[4];
     __shared__ float pacc[4][kHeadDim];
@@ -211,39 +214,66 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid < kHeadDim) qs[tid] = QKV[(size_t)i * 3 * H + h * kHeadDim + tid] * 0.125f;   // 64^-0.5
     __syncthreads();
-    float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
+    const int tg = lane / NCH, dc = lane % NCH;       // PV role of this lane: token group, dim chunk
+    float m = -INFINITY, l = 0.f;
+    float acc[X];
+#pragma unroll
+    for (int e = 0; e < X; ++e) acc[e] = 0.f;
     const int npages = (ctx + kPageTokens - 1) / kPageTokens;
+    const int* bt = block_tables + (size_t)slot * max_pages;
     for (int pg = w; pg < npages; pg += 4) {
-        const int page = block_tables[(size_t)slot * max_pages + pg];
+        const int page = bt[pg];
         const size_t pbase = ((size_t)page * heads + h) * (kPageTokens * kHeadDim);
-        const int tok = pg * kPageTokens + lane;
-        const bool valid = tok < ctx;
-        float s = 0.f;
+        const int nvalid = min(kPageTokens, ctx - pg * kPageTokens);
+        // ---- issue every load of the page up front
+        uint4 kraw[NCH], vraw[VIT];
         const TKV* kb = kpool + pbase + (size_t)lane * X;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) s += KVec<TKV>::dot(kb + (size_t)c * kPageTokens * X, qs + c * X);
+        for (int c = 0; c < NCH; ++c) kraw[c] = ldg_stream(kb + (size_t)c * kPageTokens * X);
+        const TKV* vb = vpool + pbase + (size_t)tg * kHeadDim + (size_t)dc * X;
+#pragma unroll
+        for (int it = 0; it < VIT; ++it) vraw[it] = ldg_stream(vb + (size_t)it * TPI * kHeadDim);
+        // ---- scores
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            float kf[X];
+            KVec<TKV>::unpack(kraw[c], kf);
+#pragma unroll
+            for (int e = 0; e < X; ++e) s = fmaf(kf[e], qs[c * X + e], s);
+        }
+        const bool valid = lane < nvalid;
         s = valid ? s : -INFINITY;
         const float mnew = fmaxf(m, warp_max(s));
         const float p = valid ? expf(s - mnew) : 0.f;
         const float corr = (m == -INFINITY) ? 0.f : expf(m - mnew);
         l = l * corr + warp_sum(p);
-        a0 *= corr; a1 *= corr;
-        const int nvalid = min(kPageTokens, ctx - pg * kPageTokens);
-        const TKV* vb = vpool + pbase + 2 * lane;
-#pragma unroll 8
-        for (int j = 0; j < kPageTokens; ++j) {
-            if (j < nvalid) {
-                const float pj = __shfl_sync(0xffffffffu, p, j);
-                const float2 v = KVec<TKV>::ld2(vb + (size_t)j * kHeadDim);
-                a0 = fmaf(pj, v.x, a0);
-                a1 = fmaf(pj, v.y, a1);
+#pragma unroll
+        for (int e = 0; e < X; ++e) acc[e] *= corr;
+        // ---- PV
+#pragma unroll
+        for (int it = 0; it < VIT; ++it) {
+            const int j = it * TPI + tg;
+            const float pj = __shfl_sync(0xffffffffu, p, j);
+            if (j < nvalid) {                           // stale page tails are never multiplied in
+                float vf[X];
+                KVec<TKV>::unpack(vraw[it], vf);
+#pragma unroll
+                for (int e = 0; e < X; ++e) acc[e] = fmaf(pj, vf[e], acc[e]);
             }
         }
         m = mnew;
     }
+    // ---- fold the token groups of the warp (lanes with equal dc), then the 4 warps
+#pragma unroll
+    for (int o = NCH; o < 32; o <<= 1)
+#pragma unroll
+        for (int e = 0; e < X; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
     if (lane == 0) { pm[w] = m; pl[w] = l; }
-    pacc[w][2 * lane] = a0;
-    pacc[w][2 * lane + 1] = a1;
+    if (lane < NCH) {
+#pragma unroll
+        for (int e = 0; e < X; ++e) pacc[w][dc * X + e] = acc[e];
+    }
     __syncthreads();
     if (tid < kHeadDim) {
         const float M = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));

@@ -111,8 +111,9 @@ void launch_sample(const float* logits, int ld_logits, const int* active, int M,
 // Vocoder kernels (fp32, channel-major activations [C][L])
 // ------------------------------------------------------------------------------------------
 // every vocoder launcher takes `batch` equal-length items laid out back to back ([batch][C][L])
-void launch_interp(const float* latents, float* z, int T, int C, int T1, int Tz, double scale1, double scale2,
-                   int batch, cudaStream_t st);
+// z32 (fp32 [C][Tz]) and/or z16 (fp16 atoms, lpad rows per plane) — either may be null
+void launch_interp(const float* latents, float* z32, __half* z16, int lpad, int T, int C, int T1, int Tz, double scale1,
+                   double scale2, int batch, cudaStream_t st);
 
 enum : int { CONV_STORE = 0, CONV_ACCUM = 1 };
 // out[co][t] (=|+=) bias[co] + cbias[co] + resid[co][t] + sum_{ci,j} w[ci][j][co] * act(in_scale*x[ci][t+(j-(K-1)/2)*dil])
@@ -120,17 +121,23 @@ enum : int { CONV_STORE = 0, CONV_ACCUM = 1 };
 void launch_conv1d(const float* x, const float* w_t, const float* bias, const float* cbias, const float* resid,
                    float* out, int Cin, int Cout, int L, int K, int dil, float in_scale, float slope, int mode,
                    int batch, int cbias_batch_stride, cudaStream_t st);
-// tensor-core (tcgen05, fp16 operands / fp32 accumulate) version of launch_conv1d; weights pre-packed by conv1d_tc_pack
+// ---- tensor-core vocoder path (fast mode).  Activations that feed a Conv1d live in HBM as fp16 "atoms":
+//   [C/8 plane][kAtomPadL + L + tail][8 channels], zero pads — the UMMA no-swizzle K-major operand image.
+constexpr int kAtomPadL = 64, kAtomPadR = 64;
+int atoms_lpad(int L);                                   // padded rows per plane for a signal of L steps
 struct ConvTcPlan { int N, CK, n_tiles, nacc; bool ok; size_t tile_halves, blob_halves; };
 ConvTcPlan conv1d_tc_plan(int Cin, int Cout, int K);
 void conv1d_tc_pack(const float* w /*[Cout][Cin][K]*/, int Cin, int Cout, int K, const ConvTcPlan& pl, __half* blob);
-void launch_conv1d_tc(const float* x, const __half* wblob, const ConvTcPlan& pl, const float* bias, const float* cbias,
-                      const float* resid, float* out, int Cin, int Cout, int L, int K, int dil, float in_scale, float slope,
-                      int mode, int batch, int cbias_batch_stride, cudaStream_t st);
+// y = bias + cbias + resid + conv(a16);  out32 (fp32 [C][L], store/accumulate) and/or out16 (lrelu(y, slope_out) atoms)
+void launch_conv1d_tc(const __half* a16, const __half* wblob, const ConvTcPlan& pl, const float* bias, const float* cbias,
+                      const float* resid, float* out32, __half* out16, int Cin, int Cout, int L, int lpad, int K, int dil,
+                      float slope_out, int mode, int batch, int cbias_batch_stride, cudaStream_t st);
+void launch_atoms_zero_pads(__half* buf, int planes_total, int lpad, int L, cudaStream_t st);
 // transposed conv, stride u, kernel K = 2u, padding (K-u)/2;  w pre-transposed to [Cin][K][Cout]
+// out16 (optional): lrelu(out, slope16) as fp16 atoms with lpad16 rows per plane
 void launch_conv_transpose1d(const float* x, const float* w_t, const float* bias, const float* cbias, float* out,
-                             int Cin, int Cout, int Lin, int K, int u, float in_scale, float slope, int batch,
-                             int cbias_batch_stride, cudaStream_t st);
+                             __half* out16, int lpad16, float slope16, int Cin, int Cout, int Lin, int K, int u,
+                             float in_scale, float slope, int batch, int cbias_batch_stride, cudaStream_t st);
 // wav[t] = tanh(sum w[ci][j] * lrelu(in_scale*x[ci][t+j-3], slope))
 void launch_conv_post(const float* x, const float* w, float* wav, int Cin, int L, int K, float in_scale, float slope,
                       int batch, cudaStream_t st);

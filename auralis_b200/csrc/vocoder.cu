@@ -32,10 +32,10 @@ __device__ __forceinline__ void lin_src(int dst, float rscale, int in_len, int& 
 }
 
 __global__ void __launch_bounds__(256)
-interp_kernel(const float* __restrict__ lat_, float* __restrict__ z_, int T, int C, int T1, int Tz, float r1, float r2) {
+interp_kernel(const float* __restrict__ lat_, float* __restrict__ z_, uint4* __restrict__ z16_, int lpad, int T, int C,
+              int T1, int Tz, float r1, float r2) {
     __shared__ float tile[32][33];
     const float* lat = lat_ + (size_t)blockIdx.z * T * C;
-    float* z = z_ + (size_t)blockIdx.z * C * Tz;
     const int c0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;       // (32, 8)
     for (int k = 0; k < 4; ++k) {
@@ -51,12 +51,27 @@ interp_kernel(const float* __restrict__ lat_, float* __restrict__ z_, int T, int
             const float zb = n0 * lat[(size_t)b0 * C + c] + n1 * lat[(size_t)b1 * C + c];
             v = m0 * za + m1 * zb;
         }
-        tile[ty + 8 * k][tx] = v;
+        tile[ty + 8 * k][tx] = v;                       // tile[j][c]
     }
     __syncthreads();
-    for (int k = 0; k < 4; ++k) {
-        const int c = c0 + ty + 8 * k, j = j0 + tx;
-        if (c < C && j < Tz) z[(size_t)c * Tz + j] = tile[tx][ty + 8 * k];
+    if (z_) {
+        float* z = z_ + (size_t)blockIdx.z * C * Tz;
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + ty + 8 * k, j = j0 + tx;
+            if (c < C && j < Tz) z[(size_t)c * Tz + j] = tile[tx][ty + 8 * k];
+        }
+    }
+    if (z16_ && ty < 4) {                               // 32 time steps x 4 atoms of 8 channels
+        const int j = j0 + tx, cg = c0 / 8 + ty;
+        if (j < Tz && c0 + ty * 8 < C) {
+            const float* r = &tile[tx][ty * 8];
+            __half2 h0 = __floats2half2_rn(r[0], r[1]), h1 = __floats2half2_rn(r[2], r[3]);
+            __half2 h2 = __floats2half2_rn(r[4], r[5]), h3 = __floats2half2_rn(r[6], r[7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            z16_[((size_t)blockIdx.z * (C / 8) + cg) * lpad + kAtomPadL + j] = pk;
+        }
     }
 }
 
@@ -157,8 +172,8 @@ constexpr int UP_T = 128, UP_CI = 8, UP_CO = 16;
 
 __global__ void __launch_bounds__(UP_T)
 conv_transpose1d_kernel(const float* __restrict__ x_, const float* __restrict__ w_t, const float* __restrict__ bias,
-                        const float* __restrict__ cbias_, float* __restrict__ out_, int Cin, int Cout, int Lin, int K,
-                        int u, float in_scale, float slope, int cbias_bs) {
+                        const float* __restrict__ cbias_, float* __restrict__ out_, uint4* __restrict__ out16_, int lpad16,
+                        float slope16, int Cin, int Cout, int Lin, int K, int u, float in_scale, float slope, int cbias_bs) {
     extern __shared__ __align__(16) float smem[];
     const float* x = x_ + (size_t)blockIdx.z * Cin * Lin;
     float* out = out_ + (size_t)blockIdx.z * Cout * Lin * u;
@@ -217,8 +232,26 @@ conv_transpose1d_kernel(const float* __restrict__ x_, const float* __restrict__ 
 #pragma unroll
         for (int c = 0; c < UP_CO; ++c) {
             const int co = co0 + c;
-            if (co < Cout)
-                out[(size_t)co * Lout + t] = acc[c] + (bias ? bias[co] : 0.f) + (cbias ? cbias[co] : 0.f);
+            if (co < Cout) {
+                acc[c] += (bias ? bias[co] : 0.f) + (cbias ? cbias[co] : 0.f);
+                out[(size_t)co * Lout + t] = acc[c];
+            }
+        }
+        if (out16_) {                                   // activated fp16 copy for the tensor-core resblocks
+#pragma unroll
+            for (int g = 0; g < UP_CO / 8; ++g) {
+                if (co0 + 8 * g < Cout) {
+                    const float* a = acc + 8 * g;
+                    __half2 h0 = __floats2half2_rn(lrelu(a[0], slope16), lrelu(a[1], slope16));
+                    __half2 h1 = __floats2half2_rn(lrelu(a[2], slope16), lrelu(a[3], slope16));
+                    __half2 h2 = __floats2half2_rn(lrelu(a[4], slope16), lrelu(a[5], slope16));
+                    __half2 h3 = __floats2half2_rn(lrelu(a[6], slope16), lrelu(a[7], slope16));
+                    uint4 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                    out16_[((size_t)blockIdx.z * (Cout / 8) + (co0 / 8 + g)) * lpad16 + kAtomPadL + t] = pk;
+                }
+            }
         }
     }
 }
@@ -276,11 +309,12 @@ void conv1d_dispatch(const float* x, const float* w_t, const float* bias, const 
 
 }  // namespace
 
-void launch_interp(const float* latents, float* z, int T, int C, int T1, int Tz, double scale1, double scale2,
-                   int batch, cudaStream_t st) {
+void launch_interp(const float* latents, float* z32, __half* z16, int lpad, int T, int C, int T1, int Tz, double scale1,
+                   double scale2, int batch, cudaStream_t st) {
     const float r1 = (float)(1.0 / scale1), r2 = (float)(1.0 / scale2);
-    ProfScope ps(KF_INTERP, st, 0, 4.0 * C * ((double)T + Tz) * batch);
-    interp_kernel<<<dim3(ceil_div(Tz, 32), ceil_div(C, 32), batch), dim3(32, 8), 0, st>>>(latents, z, T, C, T1, Tz, r1, r2);
+    ProfScope ps(KF_INTERP, st, 0, C * (4.0 * T + (z32 ? 4.0 : 0.0) * Tz + (z16 ? 2.0 : 0.0) * Tz) * batch);
+    interp_kernel<<<dim3(ceil_div(Tz, 32), ceil_div(C, 32), batch), dim3(32, 8), 0, st>>>(
+        latents, z32, reinterpret_cast<uint4*>(z16), lpad, T, C, T1, Tz, r1, r2);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 
@@ -297,15 +331,16 @@ void launch_conv1d(const float* x, const float* w_t, const float* bias, const fl
 }
 
 void launch_conv_transpose1d(const float* x, const float* w_t, const float* bias, const float* cbias, float* out,
-                             int Cin, int Cout, int Lin, int K, int u, float in_scale, float slope, int batch,
-                             int cbias_bs, cudaStream_t st) {
+                             __half* out16, int lpad16, float slope16, int Cin, int Cout, int Lin, int K, int u,
+                             float in_scale, float slope, int batch, int cbias_bs, cudaStream_t st) {
     if (K != 2 * u || (u & 1)) throw CudaError("conv_transpose1d: only kernel == 2*stride with even stride is supported");
     if (UP_T % u != 0) throw CudaError("conv_transpose1d: stride must divide 128");
     const int XS = UP_T / u + 3;
     const size_t smem = (size_t)(((UP_CI * XS + 3) / 4) * 4 + UP_CI * K * (UP_CO + 4)) * sizeof(float);
     dim3 grid(ceil_div(Lin * u, UP_T), ceil_div(Cout, UP_CO), batch);
     ProfScope ps(KF_CONVT, st, 4.0 * Cin * Cout * (double)Lin * u * batch, 4.0 * (batch * ((double)Lin * Cin + (double)Lin * u * Cout) + (double)Cin * Cout * K));
-    conv_transpose1d_kernel<<<grid, UP_T, smem, st>>>(x, w_t, bias, cbias, out, Cin, Cout, Lin, K, u, in_scale, slope, cbias_bs);
+    if (out16 && (Cout % 8 != 0)) throw CudaError("conv_transpose1d: atoms output needs Cout % 8 == 0");
+    conv_transpose1d_kernel<<<grid, UP_T, smem, st>>>(x, w_t, bias, cbias, out, reinterpret_cast<uint4*>(out16), lpad16, slope16, Cin, Cout, Lin, K, u, in_scale, slope, cbias_bs);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 
