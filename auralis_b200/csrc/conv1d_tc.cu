@@ -16,6 +16,8 @@
 //
 // Replaces the cuDNN fp16-autocast Conv1d calls of HifiganGenerator.forward / ResBlock1.forward
 // (hifigan_decoder.py:76-91,241-259; the reference runs them in fp16 under torch.amp.autocast on GPU, App. B.8).
+#include <vector>
+
 #include "kernels.h"
 
 namespace xtts {
@@ -77,7 +79,11 @@ struct ConvTcParams {
     float* out32;            // [batch][Cout][L] or nullptr
     __half* out16;           // output atoms [batch][Cout/8][lpad][8] or nullptr
     int Cin, Cout, L, lpad, K, dil, mode;
-    float slope_out;
+    float slope_out, scale16;   // out16 = lrelu(y * scale16, slope_out)
+    int center;              // tap j reads a[t + (j - center) * dil]
+    int up;                  // 0: Conv1d.  u > 0: ConvTranspose1d(stride u, kernel 2u, pad u/2) as u two-tap phases:
+                             //    GEMM channel n' = phase * Cr + co, GEMM row s -> output step s*u + phase - u/2
+    int Cr, Lout, lpad_out;  // real output channels, output length, padded rows of the output atoms
     int N;          // output channels per CTA (<= 256, multiple of 32)
     int CK;         // input channels per chunk (<= 64, multiple of 16)
     int rows;       // time rows staged per chunk = 128*NACC + (K-1)*dil
@@ -92,7 +98,7 @@ conv1d_tc_kernel(const ConvTcParams P) {
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int halo = (P.K - 1) / 2 * P.dil;
+    const int halo = P.center * P.dil;
     const int T0 = blockIdx.x * (128 * NACC);
     const int n0 = blockIdx.y * P.N;
     const int planes = P.CK / 8, ksteps = P.CK / 16, nch = P.Cin / P.CK;
@@ -124,15 +130,16 @@ conv1d_tc_kernel(const ConvTcParams P) {
         // ------------------------------------------------ epilogue: warp q owns TMEM lanes [32q, 32q+32) = time rows
         const int q = warp;
         const size_t zo = (size_t)blockIdx.z;
-        float* out32 = P.out32 ? P.out32 + zo * P.Cout * P.L : nullptr;
-        const float* resid = P.resid ? P.resid + zo * P.Cout * P.L : nullptr;
+        float* out32 = P.out32 ? P.out32 + zo * P.Cr * P.Lout : nullptr;
+        const float* resid = P.resid ? P.resid + zo * P.Cr * P.Lout : nullptr;
         const float* cbias = P.cbias ? P.cbias + zo * P.cbias_bs : nullptr;
-        uint4* out16 = P.out16 ? reinterpret_cast<uint4*>(P.out16) + zo * (size_t)(P.Cout / 8) * P.lpad : nullptr;
+        uint4* out16 = P.out16 ? reinterpret_cast<uint4*>(P.out16) + zo * (size_t)(P.Cr / 8) * P.lpad_out : nullptr;
+        const int row_limit = P.up ? P.L + 1 : P.L;      // a transposed conv also consumes the zero row x[L]
         bar_wait(&tmem_full, 0, 4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
         for (int a = 0; a < NACC; ++a) {
-            const int t = T0 + a * 128 + q * 32 + lane;
+            const int srow = T0 + a * 128 + q * 32 + lane;
 #pragma unroll 1
             for (int nc = 0; nc < P.N / 32; ++nc) {
                 uint32_t r[32];
@@ -147,34 +154,40 @@ conv1d_tc_kernel(const ConvTcParams P) {
                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr) : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (t < P.L) {
-                    const int cb = n0 + nc * 32;
+                // GEMM channels [cb, cb+32) of this chunk all belong to one phase (Cr % 32 == 0)
+                const int cbg = n0 + nc * 32;
+                const int phase = P.up ? cbg / P.Cr : 0;
+                const int cb = cbg - phase * P.Cr;                   // first real output channel of the chunk
+                const int t = P.up ? srow * P.up + phase - P.up / 2 : srow;
+                if (srow < row_limit && t >= 0 && t < P.Lout) {
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const int co = cb + i;
                         float x = __uint_as_float(r[i]) + (P.bias ? __ldg(P.bias + co) : 0.f) + (cbias ? __ldg(cbias + co) : 0.f);
-                        if (resid) x += resid[(size_t)co * P.L + t];
+                        if (resid) x += resid[(size_t)co * P.Lout + t];
                         v[i] = x;
                     }
                     if (out32) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const size_t o = (size_t)(cb + i) * P.L + t;
-                            out32[o] = (P.mode == CONV_ACCUM) ? out32[o] + v[i] : v[i];
+                            const size_t o = (size_t)(cb + i) * P.Lout + t;
+                            if (P.mode == CONV_ACCUM) v[i] += out32[o];
+                            out32[o] = v[i];
                         }
                     }
-                    if (out16) {
+                    if (out16) {                                     // (after an accumulate: the activated SUM)
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
-                            __half2 h0 = __floats2half2_rn(lrelu_s(v[8 * g + 0], P.slope_out), lrelu_s(v[8 * g + 1], P.slope_out));
-                            __half2 h1 = __floats2half2_rn(lrelu_s(v[8 * g + 2], P.slope_out), lrelu_s(v[8 * g + 3], P.slope_out));
-                            __half2 h2 = __floats2half2_rn(lrelu_s(v[8 * g + 4], P.slope_out), lrelu_s(v[8 * g + 5], P.slope_out));
-                            __half2 h3 = __floats2half2_rn(lrelu_s(v[8 * g + 6], P.slope_out), lrelu_s(v[8 * g + 7], P.slope_out));
+                            float w8[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) w8[e] = lrelu_s(v[8 * g + e] * P.scale16, P.slope_out);
+                            __half2 h0 = __floats2half2_rn(w8[0], w8[1]), h1 = __floats2half2_rn(w8[2], w8[3]);
+                            __half2 h2 = __floats2half2_rn(w8[4], w8[5]), h3 = __floats2half2_rn(w8[6], w8[7]);
                             uint4 pk;
                             pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
                             pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                            out16[(size_t)(cb / 8 + g) * P.lpad + (t + kAtomPadL)] = pk;
+                            out16[(size_t)(cb / 8 + g) * P.lpad_out + (t + kAtomPadL)] = pk;
                         }
                     }
                 }
@@ -263,7 +276,7 @@ ConvTcPlan conv1d_tc_plan(int Cin, int Cout, int K) {
     pl.CK = Cin >= 64 ? 64 : Cin;
     pl.n_tiles = ceil_div(Cout, pl.N);
     pl.nacc = pl.N >= 256 ? 2 : 4;
-    pl.ok = (Cin % pl.CK == 0) && (pl.CK % 16 == 0) && (pl.N % 32 == 0) && (Cout % pl.N == 0) && (K % 2 == 1);
+    pl.ok = (Cin % pl.CK == 0) && (pl.CK % 16 == 0) && (pl.N % 32 == 0) && (Cout % pl.N == 0) && K >= 1;
     pl.tile_halves = (size_t)(pl.CK / 8) * pl.N * 8;
     pl.blob_halves = (size_t)pl.n_tiles * (Cin / pl.CK) * K * pl.tile_halves;
     return pl;
@@ -285,30 +298,21 @@ void conv1d_tc_pack(const float* w, int Cin, int Cout, int K, const ConvTcPlan& 
             }
 }
 
-int atoms_lpad(int L) { return kAtomPadL + ceil_div(L, 512) * 512 + kAtomPadR; }
+int atoms_lpad(int L) { return kAtomPadL + ceil_div(L + 1, 512) * 512 + kAtomPadR; }
 
-void launch_conv1d_tc(const __half* a16, const __half* wblob, const ConvTcPlan& pl, const float* bias, const float* cbias,
-                      const float* resid, float* out32, __half* out16, int Cin, int Cout, int L, int lpad, int K, int dil,
-                      float slope_out, int mode, int batch, int cbias_batch_stride, cudaStream_t st) {
-    if (L <= 0 || batch <= 0) return;
-    if (!pl.ok) throw CudaError("conv1d_tc: unsupported channel geometry");
+static void launch_tc_common(ConvTcParams& P, const ConvTcPlan& pl, int rows_to_cover, int batch, double flops, double bytes,
+                             cudaStream_t st) {
     const int tile = 128 * pl.nacc;
-    if (lpad < kAtomPadL + ceil_div(L, tile) * tile + (K - 1) / 2 * dil) throw CudaError("conv1d_tc: atom buffer pad too small");
-    ConvTcParams P{};
-    P.a16 = a16; P.wblob = wblob; P.bias = bias; P.cbias = cbias; P.resid = resid; P.out32 = out32; P.out16 = out16;
-    P.Cin = Cin; P.Cout = Cout; P.L = L; P.lpad = lpad; P.K = K; P.dil = dil; P.mode = mode; P.slope_out = slope_out;
     P.N = pl.N; P.CK = pl.CK;
-    P.rows = tile + (K - 1) * dil;
-    P.cbias_bs = cbias_batch_stride;
+    P.rows = tile + (P.K - 1) * P.dil;
+    if (P.lpad < kAtomPadL + ceil_div(rows_to_cover, tile) * tile + (P.K - 1 - P.center) * P.dil || P.center * P.dil > kAtomPadL)
+        throw CudaError("conv1d_tc: atom buffer pad too small");
     const size_t a_stage = (size_t)P.rows * 16 * (pl.CK / 8), b_stage = (size_t)pl.N * 16 * (pl.CK / 8);
     const size_t smem = ((SA * a_stage + 127) & ~(size_t)127) + SB * b_stage + 128;
     constexpr int kMaxDyn = 227 * 1024 - 2048;      // opt-in limit minus this kernel's static shared memory
     if (smem > (size_t)kMaxDyn) throw CudaError("conv1d_tc: shared memory budget exceeded");
-    dim3 grid(ceil_div(L, tile), pl.n_tiles, batch);
-    // algorithmic traffic: fp16 atoms in, fp32 residual in, fp32 and/or fp16 out, weights once
-    const double by = batch * (double)L * (2.0 * Cin + (resid ? 4.0 * Cout : 0) + (out32 ? (mode == CONV_ACCUM ? 8.0 : 4.0) * Cout : 0) +
-                                           (out16 ? 2.0 * Cout : 0)) + 2.0 * Cin * Cout * K;
-    ProfScope ps(KF_CONV1D_TC, st, 2.0 * Cin * Cout * K * (double)L * batch, by);
+    dim3 grid(ceil_div(rows_to_cover, tile), pl.n_tiles, batch);
+    ProfScope ps(KF_CONV1D_TC, st, flops, bytes);
     static bool attr2 = false, attr4 = false;
     if (pl.nacc == 2) {
         if (!attr2) { CUDA_CHECK(cudaFuncSetAttribute(conv1d_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn)); attr2 = true; }
@@ -318,6 +322,52 @@ void launch_conv1d_tc(const __half* a16, const __half* wblob, const ConvTcPlan& 
         conv1d_tc_kernel<4><<<grid, kThreadsTC, smem, st>>>(P);
     }
     COUNT_LAUNCH(); KERNEL_CHECK();
+}
+
+void launch_conv1d_tc(const __half* a16, const __half* wblob, const ConvTcPlan& pl, const float* bias, const float* cbias,
+                      const float* resid, float* out32, __half* out16, int Cin, int Cout, int L, int lpad, int K, int dil,
+                      float slope_out, float scale16, int mode, int batch, int cbias_batch_stride, cudaStream_t st) {
+    if (L <= 0 || batch <= 0) return;
+    if (!pl.ok || K % 2 != 1) throw CudaError("conv1d_tc: unsupported geometry");
+    ConvTcParams P{};
+    P.a16 = a16; P.wblob = wblob; P.bias = bias; P.cbias = cbias; P.resid = resid; P.out32 = out32; P.out16 = out16;
+    P.Cin = Cin; P.Cout = Cout; P.L = L; P.lpad = lpad; P.K = K; P.dil = dil; P.mode = mode; P.slope_out = slope_out;
+    P.scale16 = scale16; P.center = (K - 1) / 2; P.up = 0; P.Cr = Cout; P.Lout = L; P.lpad_out = lpad;
+    P.cbias_bs = cbias_batch_stride;
+    // algorithmic traffic: fp16 atoms in, fp32 residual in, fp32 and/or fp16 out, weights once
+    const double by = batch * (double)L * (2.0 * Cin + (resid ? 4.0 * Cout : 0) + (out32 ? (mode == CONV_ACCUM ? 8.0 : 4.0) * Cout : 0) +
+                                           (out16 ? 2.0 * Cout : 0)) + 2.0 * Cin * Cout * K;
+    launch_tc_common(P, pl, L, batch, 2.0 * Cin * Cout * K * (double)L * batch, by, st);
+}
+
+// ConvTranspose1d(Cin -> Cr, kernel 2u, stride u, padding u/2) on the same kernel: u phases x 2 taps.
+// `pl`/`wblob` come from conv1d_tc_plan(Cin, u*Cr, 2) / convT_tc_pack.
+void launch_convT_tc(const __half* a16, const __half* wblob, const ConvTcPlan& pl, const float* bias, const float* cbias,
+                     float* out32, __half* out16, int Cin, int Cr, int Lin, int lpad_in, int lpad_out, int u, float slope_out,
+                     int batch, int cbias_batch_stride, cudaStream_t st) {
+    if (Lin <= 0 || batch <= 0) return;
+    if (!pl.ok || (u & 1) || Cr % 32 != 0) throw CudaError("convT_tc: unsupported geometry");
+    ConvTcParams P{};
+    P.a16 = a16; P.wblob = wblob; P.bias = bias; P.cbias = cbias; P.resid = nullptr; P.out32 = out32; P.out16 = out16;
+    P.Cin = Cin; P.Cout = u * Cr; P.L = Lin; P.lpad = lpad_in; P.K = 2; P.dil = 1; P.mode = CONV_STORE; P.slope_out = slope_out;
+    P.scale16 = 1.0f; P.center = 1; P.up = u; P.Cr = Cr; P.Lout = Lin * u; P.lpad_out = lpad_out;
+    P.cbias_bs = cbias_batch_stride;
+    const double by = batch * ((double)Lin * 2.0 * Cin + (double)Lin * u * Cr * ((out32 ? 4.0 : 0) + (out16 ? 2.0 : 0))) + 4.0 * Cin * Cr * u;
+    launch_tc_common(P, pl, Lin + 1, batch, 4.0 * Cin * Cr * (double)Lin * u * batch, by, st);
+}
+
+// ConvTranspose1d weight [Cin][Cr][2u] fp32 -> two-tap phase blob: W'[p*Cr+co][ci][0] = w[ci][co][p+u] (x[s-1]),
+//                                                                     W'[p*Cr+co][ci][1] = w[ci][co][p]   (x[s])
+void convT_tc_pack(const float* w, int Cin, int Cr, int u, const ConvTcPlan& pl, __half* blob) {
+    std::vector<float> tmp((size_t)u * Cr * Cin * 2);
+    for (int p = 0; p < u; ++p)
+        for (int co = 0; co < Cr; ++co)
+            for (int ci = 0; ci < Cin; ++ci) {
+                const size_t o = (((size_t)p * Cr + co) * Cin + ci) * 2;
+                tmp[o + 0] = w[((size_t)ci * Cr + co) * (2 * u) + p + u];
+                tmp[o + 1] = w[((size_t)ci * Cr + co) * (2 * u) + p];
+            }
+    conv1d_tc_pack(tmp.data(), Cin, u * Cr, 2, pl, blob);
 }
 
 void launch_atoms_zero_pads(__half* buf, int planes_total, int lpad, int L, cudaStream_t st) {

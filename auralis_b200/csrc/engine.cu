@@ -189,7 +189,7 @@ private:
     int* h_finished = nullptr;
     // vocoder workspace
     DBuf<float> vz, vpre, vb[5], vwav, vlat, vcb;
-    DBuf<__half> vz16, va16[4];   // fp16 operand atoms of the tensor-core vocoder path
+    DBuf<__half> vz16, va16[5];   // fp16 operand atoms of the tensor-core vocoder path
     bool tc_vocoder_ready = false;
     int voc_max_T = 0, VB = 1;
     std::vector<int> stage_ch;
@@ -232,7 +232,7 @@ private:
     void conv1d(const ConvW& c, const float* x, const float* cbias, const float* resid, float* out, int L, int dil,
                 float in_scale, float slope, int mode, int nb);
     void conv1d_tc(const ConvW& c, const __half* a16, const float* cbias, const float* resid, float* out32, __half* out16,
-                   int L, int lpad, int dil, int mode, int nb);
+                   int L, int lpad, int dil, int mode, int nb, float scale16 = 1.0f);
     void run_vocoder_tc(const float* lat_dev, int T, int nb, float* wav_dev_out, int* n_out, const char* stage,
                         float* stage_out, int64_t stage_cap);
     std::vector<float> folded(const std::string& prefix) const;
@@ -473,6 +473,19 @@ void Engine::make_conv(ConvW& c, const std::string& prefix, bool transposed, boo
     c.Cin = Cin; c.Cout = Cout; c.K = K;
     up(c.wt, t);
     if (has_bias) up(c.b, need(prefix + ".bias").data);
+    if (bf16 && transposed && K % 2 == 0 && Cout % 32 == 0) {      // fast mode: ConvTranspose1d as u two-tap phases
+        const int u = K / 2;
+        c.plan = conv1d_tc_plan(Cin, u * Cout, 2);
+        if (c.plan.ok) {
+            std::vector<__half> blob(c.plan.blob_halves);
+            convT_tc_pack(w.data(), Cin, Cout, u, c.plan, blob.data());
+            c.blob.alloc(blob.size());
+            c.blob.upload(blob.data(), blob.size(), st);
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            c.tc = true;
+            weight_bytes += blob.size() * 2;
+        }
+    }
     if (bf16 && !transposed) {               // fast mode: fp16 tensor-core tiles for every Conv1d that fits the plan
         c.plan = conv1d_tc_plan(Cin, Cout, K);
         if (c.plan.ok) {
@@ -494,9 +507,9 @@ void Engine::conv1d(const ConvW& c, const float* x, const float* cbias, const fl
 }
 
 void Engine::conv1d_tc(const ConvW& c, const __half* a16, const float* cbias, const float* resid, float* out32, __half* out16,
-                       int L, int lpad, int dil, int mode, int nb) {
-    launch_conv1d_tc(a16, c.blob.p, c.plan, c.b.p, cbias, resid, out32, out16, c.Cin, c.Cout, L, lpad, c.K, dil, 0.1f, mode, nb,
-                     cbias_stride, st);
+                       int L, int lpad, int dil, int mode, int nb, float scale16) {
+    launch_conv1d_tc(a16, c.blob.p, c.plan, c.b.p, cbias, resid, out32, out16, c.Cin, c.Cout, L, lpad, c.K, dil, 0.1f, scale16,
+                     mode, nb, cbias_stride, st);
 }
 
 void Engine::finalize_weights() {
@@ -563,13 +576,14 @@ void Engine::finalize_weights() {
     }
     if (bf16) {
         bool all_tc = conv_pre.tc;
+        for (auto& u : ups) all_tc = all_tc && u->tc && (u->K == 2 * c.voc_up_rates[&u - &ups[0]]);
         for (auto& rb : rbs) for (int t = 0; t < 3; ++t) all_tc = all_tc && rb->c1[t]->tc && rb->c2[t]->tc;
         for (int ch : stage_ch) all_tc = all_tc && (ch % 16 == 0);
         if (all_tc) {
             const int T1 = (int)std::floor((double)voc_max_T * ((double)c.code_stride / (double)c.output_hop_length));
             const int Tz = (int)std::floor((double)T1 * ((double)c.output_sample_rate / (double)c.input_sample_rate));
             vz16.alloc((size_t)VB * c.voc_in_dim * atoms_lpad(Tz));
-            size_t mx = 0; int len = Tz;
+            size_t mx = (size_t)c.voc_init_ch * atoms_lpad(Tz); int len = Tz;
             for (int i = 0; i < c.voc_n_up; ++i) { len *= c.voc_up_rates[i]; mx = std::max(mx, (size_t)stage_ch[i] * atoms_lpad(len)); }
             for (auto& b : va16) b.alloc((size_t)VB * mx);
             tc_vocoder_ready = true;
@@ -940,27 +954,31 @@ void Engine::run_vocoder_tc(const float* lat_dev, int T, int nb, float* wav_dev_
         }
     };
     int lpad = atoms_lpad(Tz);
+    __half* XA = va16[0].p; __half* TA = va16[1].p; __half* RA[2] = {va16[2].p, va16[3].p}; __half* PA = va16[4].p;
     launch_atoms_zero_pads(vz16.p, nb * c.voc_in_dim / 8, lpad, Tz, st);
+    launch_atoms_zero_pads(PA, nb * c.voc_init_ch / 8, lpad, Tz, st);
     launch_interp(lat_dev, stage ? vz.p : nullptr, vz16.p, lpad, T, c.voc_in_dim, T1, Tz, s1, resample ? s2 : 1.0, nb, st);
     if (stage) dump("z", vz.p, (size_t)c.voc_in_dim * Tz);
-    conv1d_tc(conv_pre, vz16.p, cb + cbias_off[0], nullptr, vpre.p, nullptr, Tz, lpad, 1, CONV_STORE, nb);
-    dump("pre", vpre.p, (size_t)c.voc_init_ch * Tz);
-    const float* cur = vpre.p;
-    float in_scale = 1.0f;
+    // conv_pre: fp32 copy only for the stage tap; its activated fp16 atoms feed the first transposed conv
+    conv1d_tc(conv_pre, vz16.p, cb + cbias_off[0], nullptr, stage ? vpre.p : nullptr, PA, Tz, lpad, 1, CONV_STORE, nb);
+    if (stage) dump("pre", vpre.p, (size_t)c.voc_init_ch * Tz);
     int len = Tz;
     const int nk = c.voc_n_rb;
     float* X = vb[0].p; float* R[2] = {vb[2].p, vb[3].p}; float* ZS = vb[4].p;
-    __half* XA = va16[0].p; __half* TA = va16[1].p; __half* RA[2] = {va16[2].p, va16[3].p};
     for (int i = 0; i < c.voc_n_up; ++i) {
         const ConvW& u = *ups[i];
         const int C = u.Cout;
-        const int lout = len * c.voc_up_rates[i];
+        const int up = c.voc_up_rates[i];
+        const int lout = len * up;
+        const int lpad_in = lpad;
         lpad = atoms_lpad(lout);
         for (__half* b : {XA, TA, RA[0], RA[1]}) launch_atoms_zero_pads(b, nb * C / 8, lpad, lout, st);
-        launch_conv_transpose1d(cur, u.wt.p, u.b.p, cb + cbias_off[i + 1], X, XA, lpad, 0.1f, u.Cin, u.Cout, len, u.K,
-                                c.voc_up_rates[i], in_scale, 0.1f, nb, cbias_stride, st);
+        launch_convT_tc(PA, u.blob.p, u.plan, u.b.p, cb + cbias_off[i + 1], X, XA, u.Cin, C, len, lpad_in, lpad, up, 0.1f, nb,
+                        cbias_stride, st);
         len = lout;
         { char nm[16]; snprintf(nm, sizeof(nm), "up%d", i); dump(nm, X, (size_t)C * len); }
+        const bool more = (i + 1 < c.voc_n_up);
+        if (more) launch_atoms_zero_pads(PA, nb * C / 8, lpad, len, st);     // PA is re-shaped for the next stage's input
         for (int j = 0; j < nk; ++j) {
             const RB& rb = *rbs[i * nk + j];
             const __half* in16 = XA;
@@ -971,14 +989,17 @@ void Engine::run_vocoder_tc(const float* lat_dev, int T, int nb, float* wav_dev_
                     conv1d_tc(*rb.c2[t], TA, nullptr, resid, R[t], RA[t], len, lpad, 1, CONV_STORE, nb);
                     in16 = RA[t]; resid = R[t];
                 } else {
-                    conv1d_tc(*rb.c2[t], TA, nullptr, resid, ZS, nullptr, len, lpad, 1, j == 0 ? CONV_STORE : CONV_ACCUM, nb);
+                    // MRF sum; the last resblock also emits lrelu(sum / nk) as the next transposed conv's operand
+                    const bool emit = more && (j == nk - 1);
+                    conv1d_tc(*rb.c2[t], TA, nullptr, resid, ZS, emit ? PA : nullptr, len, lpad, 1,
+                              j == 0 ? CONV_STORE : CONV_ACCUM, nb, 1.0f / (float)nk);
                 }
             }
         }
         { char nm[16]; snprintf(nm, sizeof(nm), "mrf%d", i); dump(nm, ZS, (size_t)C * len); }
-        cur = ZS;
-        in_scale = 1.0f / (float)nk;
     }
+    const float* cur = ZS;
+    const float in_scale = 1.0f / (float)nk;
     launch_conv_post(cur, conv_post_w.p, wav_dev_out, post_cin, len, 7, in_scale, 0.01f, nb, st);
     *n_out = len;
 }

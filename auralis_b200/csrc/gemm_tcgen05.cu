@@ -12,7 +12,9 @@
 namespace xtts {
 namespace {
 
-constexpr int BM = 128, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+// ring depth per tile width: ~190 KB of operands in flight per CTA (the skinny decode GEMMs are latency-bound)
+__host__ __device__ constexpr int stages_for(int bn) { return bn >= 128 ? 6 : (bn >= 64 ? 8 : 10); }
 constexpr int kThreads = 192;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -86,8 +88,10 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const float* __restrict__ bias, const float* resid, void* out, int M, int N, int K, int flags) {
+                    const float* __restrict__ bias, const float* resid, void* out, int M, int N, int K, int flags,
+                    int a_box_rows) {
     // (bias / out / flags are re-pointed below for split-K launches)
+    constexpr int STAGES = stages_for(BN);
     constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ uint8_t smem_raw[];
@@ -136,7 +140,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1, 1);
-                mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+                mbar_expect_tx(&full_bar[s], (uint32_t)a_box_rows * BK * 2 + B_BYTES);
                 tma_load_2d(sA + s * A_BYTES, &tmA, &full_bar[s], (kb_begin + kb) * BK, m0);
                 tma_load_2d(sB + s * B_BYTES, &tmB, &full_bar[s], (kb_begin + kb) * BK, n0);
             }
@@ -226,6 +230,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
+// rows of the A box: the whole 128-row tile, or (single m-tile problems) just the valid rows rounded up to 8 —
+// the rest of the smem tile keeps stale data whose accumulator rows are never stored
+inline int a_box_rows_for(int M) { return M >= BM ? BM : ((M + 7) / 8) * 8; }
+
 void encode_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     const cuuint64_t dims[2] = {cols, rows};
     const cuuint64_t strides[1] = {cols * 2};
@@ -244,7 +252,8 @@ void encode_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, u
 
 template <int BN>
 void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, const float* resid, void* out, int M,
-               int N, int K, int flags, cudaStream_t st, int splits = 1) {
+               int N, int K, int flags, cudaStream_t st, int splits, int a_box_rows) {
+    constexpr int STAGES = stages_for(BN);
     constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
@@ -254,7 +263,7 @@ void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
     ProfScope ps(KF_GEMM_TC, st, 2.0 * M * N * K,
                  2.0 * ((double)M * K + (double)N * K) + ((flags & GEMM_OUT_BF16) ? 2.0 : 4.0) * M * N);
-    gemm_bf16_tc_kernel<BN><<<grid, kThreads, smem, st>>>(tmA, tmB, bias, resid, out, M, N, K, flags);
+    gemm_bf16_tc_kernel<BN><<<grid, kThreads, smem, st>>>(tmA, tmB, bias, resid, out, M, N, K, flags, a_box_rows);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 
@@ -272,7 +281,7 @@ bool gemm_tc_init(std::string* err) {
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     // opt every instantiation into its dynamic shared memory now (never inside a stream capture)
-    auto smem_of = [](int bn) { return (int)(STAGES * (BM * BK * 2 + bn * BK * 2) + 1024); };
+    auto smem_of = [](int bn) { return (int)(stages_for(bn) * (BM * BK * 2 + bn * BK * 2) + 1024); };
     cudaFuncSetAttribute(gemm_bf16_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(128));
     cudaFuncSetAttribute(gemm_bf16_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(64));
     cudaFuncSetAttribute(gemm_bf16_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(32));
@@ -295,11 +304,12 @@ void launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const f
     if (N % 128 != 0 || mt * (N / 128) < 148) bn = 64;
     if (bn == 64 && (N % 64 != 0 || mt * (N / 64) < 148)) bn = 32;
     CUtensorMap tmA, tmB;
-    encode_2d(&tmA, A, (uint64_t)M, (uint64_t)K, BM);
+    const int abox = a_box_rows_for(M);
+    encode_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint32_t)abox);
     encode_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint32_t)bn);
-    if (bn == 128) launch_bn<128>(tmA, tmB, bias, resid, out, M, N, K, flags, st);
-    else if (bn == 64) launch_bn<64>(tmA, tmB, bias, resid, out, M, N, K, flags, st);
-    else launch_bn<32>(tmA, tmB, bias, resid, out, M, N, K, flags, st);
+    if (bn == 128) launch_bn<128>(tmA, tmB, bias, resid, out, M, N, K, flags, st, 1, abox);
+    else if (bn == 64) launch_bn<64>(tmA, tmB, bias, resid, out, M, N, K, flags, st, 1, abox);
+    else launch_bn<32>(tmA, tmB, bias, resid, out, M, N, K, flags, st, 1, abox);
 }
 
 
@@ -314,11 +324,12 @@ void launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, 
     if (N % 128 != 0 || mt * (N / 128) * splits < 148) bn = 64;
     if (bn == 64 && (N % 64 != 0 || mt * (N / 64) * splits < 148)) bn = 32;
     CUtensorMap tmA, tmB;
-    encode_2d(&tmA, A, (uint64_t)M, (uint64_t)K, BM);
+    const int abox = a_box_rows_for(M);
+    encode_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint32_t)abox);
     encode_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint32_t)bn);
-    if (bn == 128) launch_bn<128>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits);
-    else if (bn == 64) launch_bn<64>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits);
-    else launch_bn<32>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits);
+    if (bn == 128) launch_bn<128>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox);
+    else if (bn == 64) launch_bn<64>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox);
+    else launch_bn<32>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox);
 }
 
 }  // namespace xtts

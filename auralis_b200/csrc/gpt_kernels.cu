@@ -95,8 +95,12 @@ residual_reduce_ln_kernel(float* __restrict__ X, const float* __restrict__ P, in
     float* x = X + (size_t)blockIdx.x * H;
     const float* p = P + (size_t)blockIdx.x * H;
     for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        float pv[8];
+#pragma unroll
+        for (int z = 0; z < 8; ++z) pv[z] = (z < splits) ? p[(size_t)z * split_stride + c] : 0.f;   // all loads in flight
         float v = x[c] + bias[c];
-        for (int z = 0; z < splits; ++z) v += p[(size_t)z * split_stride + c];      // fixed order: deterministic
+#pragma unroll
+        for (int z = 0; z < 8; ++z) v += pv[z];                                                      // fixed order: deterministic
         x[c] = v;
         buf[c] = v;
     }

@@ -129,9 +129,15 @@ struct ConvTcPlan { int N, CK, n_tiles, nacc; bool ok; size_t tile_halves, blob_
 ConvTcPlan conv1d_tc_plan(int Cin, int Cout, int K);
 void conv1d_tc_pack(const float* w /*[Cout][Cin][K]*/, int Cin, int Cout, int K, const ConvTcPlan& pl, __half* blob);
 // y = bias + cbias + resid + conv(a16);  out32 (fp32 [C][L], store/accumulate) and/or out16 (lrelu(y, slope_out) atoms)
+// out16 = lrelu(y * scale16, slope_out)
 void launch_conv1d_tc(const __half* a16, const __half* wblob, const ConvTcPlan& pl, const float* bias, const float* cbias,
                       const float* resid, float* out32, __half* out16, int Cin, int Cout, int L, int lpad, int K, int dil,
-                      float slope_out, int mode, int batch, int cbias_batch_stride, cudaStream_t st);
+                      float slope_out, float scale16, int mode, int batch, int cbias_batch_stride, cudaStream_t st);
+// ConvTranspose1d(kernel 2u, stride u, padding u/2) on the same kernel (u phases x 2 taps); plan = conv1d_tc_plan(Cin, u*Cr, 2)
+void convT_tc_pack(const float* w /*[Cin][Cr][2u]*/, int Cin, int Cr, int u, const ConvTcPlan& pl, __half* blob);
+void launch_convT_tc(const __half* a16, const __half* wblob, const ConvTcPlan& pl, const float* bias, const float* cbias,
+                     float* out32, __half* out16, int Cin, int Cr, int Lin, int lpad_in, int lpad_out, int u, float slope_out,
+                     int batch, int cbias_batch_stride, cudaStream_t st);
 void launch_atoms_zero_pads(__half* buf, int planes_total, int lpad, int L, cudaStream_t st);
 // transposed conv, stride u, kernel K = 2u, padding (K-u)/2;  w pre-transposed to [Cin][K][Cout]
 // out16 (optional): lrelu(out, slope16) as fp16 atoms with lpad16 rows per plane

