@@ -75,6 +75,26 @@ inline const char* kernel_family_name(int f) {
     return (f >= 0 && f < KF_COUNT) ? n[f] : "?";
 }
 
+// ---- programmatic dependent launch (PDL): the decode step is a chain of ~200 short dependent kernels; with the
+// programmatic-serialization attribute kernel N+1 is launched while kernel N still runs, does its prologue (barrier
+// init, TMEM alloc, weight-tile prefetch) and only blocks at griddepcontrol.wait before touching N's outputs.
+extern bool g_use_pdl;
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (pdl && g_use_pdl) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    cuda_check(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...), "cudaLaunchKernelEx", __FILE__, __LINE__);
+}
+
 constexpr int kHeadDim = 64;       // 16 heads x 64 (xttsv2_gpt_config.py:136-138); kernels specialise on it
 constexpr int kPageTokens = 32;    // KV page = one warp of tokens
 

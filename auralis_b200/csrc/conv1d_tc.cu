@@ -16,6 +16,7 @@
 //
 // Replaces the cuDNN fp16-autocast Conv1d calls of HifiganGenerator.forward / ResBlock1.forward
 // (hifigan_decoder.py:76-91,241-259; the reference runs them in fp16 under torch.amp.autocast on GPU, App. B.8).
+#include <algorithm>
 #include <vector>
 
 #include "kernels.h"
@@ -29,6 +30,9 @@ constexpr int SA = 2, SB = 3;          // ring depths (activation chunks, weight
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(uint64_t* b, uint32_t c) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(c) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory");
 }
 __device__ __forceinline__ void bar_expect_tx(uint64_t* b, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory");
@@ -88,19 +92,18 @@ struct ConvTcParams {
     int CK;         // input channels per chunk (<= 64, multiple of 16)
     int rows;       // time rows staged per chunk = 128*NACC + (K-1)*dil
     int cbias_bs;   // elements between the speaker-bias vectors of consecutive batch items
+    int tiles_t, tiles_n, batch;   // persistent-CTA tile space
 };
 
 template <int NACC>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 conv1d_tc_kernel(const ConvTcParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], tmem_full;
+    __shared__ __align__(8) uint64_t a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int halo = P.center * P.dil;
-    const int T0 = blockIdx.x * (128 * NACC);
-    const int n0 = blockIdx.y * P.N;
     const int planes = P.CK / 8, ksteps = P.CK / 16, nch = P.Cin / P.CK;
     const uint32_t a_plane = (uint32_t)P.rows * 16u;               // bytes per ci-plane of a staged chunk
     const uint32_t a_stage = a_plane * planes;
@@ -108,13 +111,19 @@ conv1d_tc_kernel(const ConvTcParams P) {
     const uint32_t b_stage = b_plane * planes;
     uint8_t* sA = smem;
     uint8_t* sB = smem + ((SA * a_stage + 127) & ~127u);
+    // persistent CTA: tiles = (batch item, C_out tile, time tile), strided by the grid; accumulators are double
+    // buffered in TMEM when two sets fit (NACC*N <= 256 columns), so the epilogue of tile i overlaps the MMAs of tile i+1
+    const int acc_cols = NACC * P.N;
+    const int nbuf = (2 * acc_cols <= 512) ? 2 : 1;
     uint32_t tm_cols = 32;
-    while (tm_cols < (uint32_t)(NACC * P.N)) tm_cols <<= 1;
+    while (tm_cols < (uint32_t)(nbuf * acc_cols)) tm_cols <<= 1;
+    const int tiles_t = P.tiles_t, tiles_n = P.tiles_n;
+    const int total_tiles = tiles_t * tiles_n * P.batch;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < SA; ++i) { bar_init(&a_full[i], 1); bar_init(&a_empty[i], 1); }
         for (int i = 0; i < SB; ++i) { bar_init(&b_full[i], 1); bar_init(&b_empty[i], 1); }
-        bar_init(&tmem_full, 1);
+        for (int i = 0; i < 2; ++i) { bar_init(&tmem_full[i], 1); bar_init(&tmem_empty[i], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
@@ -129,89 +138,108 @@ conv1d_tc_kernel(const ConvTcParams P) {
     if (warp < 4) {
         // ------------------------------------------------ epilogue: warp q owns TMEM lanes [32q, 32q+32) = time rows
         const int q = warp;
-        const size_t zo = (size_t)blockIdx.z;
-        float* out32 = P.out32 ? P.out32 + zo * P.Cr * P.Lout : nullptr;
-        const float* resid = P.resid ? P.resid + zo * P.Cr * P.Lout : nullptr;
-        const float* cbias = P.cbias ? P.cbias + zo * P.cbias_bs : nullptr;
-        uint4* out16 = P.out16 ? reinterpret_cast<uint4*>(P.out16) + zo * (size_t)(P.Cr / 8) * P.lpad_out : nullptr;
         const int row_limit = P.up ? P.L + 1 : P.L;      // a transposed conv also consumes the zero row x[L]
-        bar_wait(&tmem_full, 0, 4);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            const int tx = tile % tiles_t, ty = (tile / tiles_t) % tiles_n;
+            const size_t zo = (size_t)(tile / (tiles_t * tiles_n));
+            const int T0 = tx * (128 * NACC), n0 = ty * P.N;
+            float* out32 = P.out32 ? P.out32 + zo * P.Cr * P.Lout : nullptr;
+            const float* resid = P.resid ? P.resid + zo * P.Cr * P.Lout : nullptr;
+            const float* cbias = P.cbias ? P.cbias + zo * P.cbias_bs : nullptr;
+            uint4* out16 = P.out16 ? reinterpret_cast<uint4*>(P.out16) + zo * (size_t)(P.Cr / 8) * P.lpad_out : nullptr;
+            const int ab = lt % nbuf;
+            bar_wait(&tmem_full[ab], (uint32_t)((lt / nbuf) & 1), 4);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int a = 0; a < NACC; ++a) {
-            const int srow = T0 + a * 128 + q * 32 + lane;
+            for (int a = 0; a < NACC; ++a) {
+                const int srow = T0 + a * 128 + q * 32 + lane;
 #pragma unroll 1
-            for (int nc = 0; nc < P.N / 32; ++nc) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * P.N + nc * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr) : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // GEMM channels [cb, cb+32) of this chunk all belong to one phase (Cr % 32 == 0)
-                const int cbg = n0 + nc * 32;
-                const int phase = P.up ? cbg / P.Cr : 0;
-                const int cb = cbg - phase * P.Cr;                   // first real output channel of the chunk
-                const int t = P.up ? srow * P.up + phase - P.up / 2 : srow;
-                if (srow < row_limit && t >= 0 && t < P.Lout) {
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int co = cb + i;
-                        float x = __uint_as_float(r[i]) + (P.bias ? __ldg(P.bias + co) : 0.f) + (cbias ? __ldg(cbias + co) : 0.f);
-                        if (resid) x += resid[(size_t)co * P.Lout + t];
-                        v[i] = x;
-                    }
-                    if (out32) {
+                for (int nc = 0; nc < P.N / 32; ++nc) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols + a * P.N + nc * 32);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // GEMM channels [cbg, cbg+32) of this chunk all belong to one phase (Cr % 32 == 0)
+                    const int cbg = n0 + nc * 32;
+                    const int phase = P.up ? cbg / P.Cr : 0;
+                    const int cb = cbg - phase * P.Cr;               // first real output channel of the chunk
+                    const int t = P.up ? srow * P.up + phase - P.up / 2 : srow;
+                    if (srow < row_limit && t >= 0 && t < P.Lout) {
+                        float v[32];
+                        // every load of the chunk is issued before the first store (the accumulate used to alternate
+                        // dependent load/store pairs: 32 serialized round trips)
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const size_t o = (size_t)(cb + i) * P.Lout + t;
-                            if (P.mode == CONV_ACCUM) v[i] += out32[o];
-                            out32[o] = v[i];
+                            float x = __uint_as_float(r[i]);
+                            if (resid) x += resid[o];
+                            if (out32 && P.mode == CONV_ACCUM) x += out32[o];
+                            v[i] = x;
                         }
-                    }
-                    if (out16) {                                     // (after an accumulate: the activated SUM)
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            float w8[8];
+                        for (int i = 0; i < 32; ++i) {
+                            const int co = cb + i;
+                            v[i] += (P.bias ? __ldg(P.bias + co) : 0.f) + (cbias ? __ldg(cbias + co) : 0.f);
+                        }
+                        if (out32) {
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) w8[e] = lrelu_s(v[8 * g + e] * P.scale16, P.slope_out);
-                            __half2 h0 = __floats2half2_rn(w8[0], w8[1]), h1 = __floats2half2_rn(w8[2], w8[3]);
-                            __half2 h2 = __floats2half2_rn(w8[4], w8[5]), h3 = __floats2half2_rn(w8[6], w8[7]);
-                            uint4 pk;
-                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                            out16[(size_t)(cb / 8 + g) * P.lpad_out + (t + kAtomPadL)] = pk;
+                            for (int i = 0; i < 32; ++i) out32[(size_t)(cb + i) * P.Lout + t] = v[i];
+                        }
+                        if (out16) {                                 // (after an accumulate: the activated SUM)
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                float w8[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) w8[e] = lrelu_s(v[8 * g + e] * P.scale16, P.slope_out);
+                                __half2 h0 = __floats2half2_rn(w8[0], w8[1]), h1 = __floats2half2_rn(w8[2], w8[3]);
+                                __half2 h2 = __floats2half2_rn(w8[4], w8[5]), h3 = __floats2half2_rn(w8[6], w8[7]);
+                                uint4 pk;
+                                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                                out16[(size_t)(cb / 8 + g) * P.lpad_out + (t + kAtomPadL)] = pk;
+                            }
                         }
                     }
                 }
             }
+            // this accumulator set is drained: hand it back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            bar_arrive(&tmem_empty[ab]);
         }
     } else if (warp == 4) {
         // ------------------------------------------------ producer: activation planes + weight tiles, all bulk copies
         if (lane == 0) {
-            const __half* wsrc = P.wblob + (size_t)blockIdx.y * nch * P.K * (b_stage / 2);
-            const __half* asrc = P.a16 + (size_t)blockIdx.z * (size_t)(P.Cin / 8) * P.lpad * 8;
-            const int row0 = T0 - halo + kAtomPadL;                 // first staged time row inside the padded plane
-            int it = 0;
-            for (int c = 0; c < nch; ++c) {
-                const int sa = c % SA;
-                bar_wait(&a_empty[sa], ((c / SA) & 1) ^ 1, 1);
-                bar_expect_tx(&a_full[sa], a_stage);
-                for (int p = 0; p < planes; ++p)
-                    bulk_g2s(sA + (size_t)sa * a_stage + (size_t)p * a_plane,
-                             asrc + ((size_t)(c * planes + p) * P.lpad + row0) * 8, a_plane, &a_full[sa]);
-                for (int j = 0; j < P.K; ++j, ++it) {
-                    const int s = it % SB;
-                    bar_wait(&b_empty[s], ((it / SB) & 1) ^ 1, 2);
-                    bar_expect_tx(&b_full[s], b_stage);
-                    bulk_g2s(sB + (size_t)s * b_stage, wsrc + (size_t)it * (b_stage / 2), b_stage, &b_full[s]);
+            int ita = 0, itb = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int tx = tile % tiles_t, ty = (tile / tiles_t) % tiles_n;
+                const size_t zo = (size_t)(tile / (tiles_t * tiles_n));
+                const int T0 = tx * (128 * NACC);
+                const __half* wsrc = P.wblob + (size_t)ty * nch * P.K * (b_stage / 2);
+                const __half* asrc = P.a16 + zo * (size_t)(P.Cin / 8) * P.lpad * 8;
+                const int row0 = T0 - halo + kAtomPadL;             // first staged time row inside the padded plane
+                int wt = 0;
+                for (int c = 0; c < nch; ++c, ++ita) {
+                    const int sa = ita % SA;
+                    bar_wait(&a_empty[sa], ((ita / SA) & 1) ^ 1, 1);
+                    bar_expect_tx(&a_full[sa], a_stage);
+                    for (int p = 0; p < planes; ++p)
+                        bulk_g2s(sA + (size_t)sa * a_stage + (size_t)p * a_plane,
+                                 asrc + ((size_t)(c * planes + p) * P.lpad + row0) * 8, a_plane, &a_full[sa]);
+                    for (int j = 0; j < P.K; ++j, ++itb, ++wt) {
+                        const int s = itb % SB;
+                        bar_wait(&b_empty[s], ((itb / SB) & 1) ^ 1, 2);
+                        bar_expect_tx(&b_full[s], b_stage);
+                        bulk_g2s(sB + (size_t)s * b_stage, wsrc + (size_t)wt * (b_stage / 2), b_stage, &b_full[s]);
+                    }
                 }
             }
         }
@@ -219,30 +247,36 @@ conv1d_tc_kernel(const ConvTcParams P) {
         // ------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | ((uint32_t)(P.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f16 x f16 -> f32
-            int it = 0;
-            for (int c = 0; c < nch; ++c) {
-                const int sa = c % SA;
-                bar_wait(&a_full[sa], (c / SA) & 1, 3);
+            int ita = 0, itb = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+                const int ab = lt % nbuf;
+                bar_wait(&tmem_empty[ab], (uint32_t)(((lt / nbuf) & 1) ^ 1), 6);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = s_u32(sA + (size_t)sa * a_stage);
-                for (int j = 0; j < P.K; ++j, ++it) {
-                    const int sb = it % SB;
-                    bar_wait(&b_full[sb], (it / SB) & 1, 5);
+                const uint32_t acc0 = tmem_base + (uint32_t)(ab * acc_cols);
+                for (int c = 0; c < nch; ++c, ++ita) {
+                    const int sa = ita % SA;
+                    bar_wait(&a_full[sa], (ita / SA) & 1, 3);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t b_addr = s_u32(sB + (size_t)sb * b_stage);
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint64_t bd = desc_nosw(b_addr + (uint32_t)(2 * k) * b_plane, b_plane);
+                    const uint32_t a_addr = s_u32(sA + (size_t)sa * a_stage);
+                    for (int j = 0; j < P.K; ++j, ++itb) {
+                        const int sb = itb % SB;
+                        bar_wait(&b_full[sb], (itb / SB) & 1, 5);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t b_addr = s_u32(sB + (size_t)sb * b_stage);
+                        for (int k = 0; k < ksteps; ++k) {
+                            const uint64_t bd = desc_nosw(b_addr + (uint32_t)(2 * k) * b_plane, b_plane);
 #pragma unroll
-                        for (int a = 0; a < NACC; ++a) {
-                            const uint64_t ad = desc_nosw(a_addr + (uint32_t)(2 * k) * a_plane + (uint32_t)(a * 128 + j * P.dil) * 16u, a_plane);
-                            mma_f16(tmem_base + (uint32_t)(a * P.N), ad, bd, idesc, (c | j | k) != 0 ? 1u : 0u);
+                            for (int a = 0; a < NACC; ++a) {
+                                const uint64_t ad = desc_nosw(a_addr + (uint32_t)(2 * k) * a_plane + (uint32_t)(a * 128 + j * P.dil) * 16u, a_plane);
+                                mma_f16(acc0 + (uint32_t)(a * P.N), ad, bd, idesc, (c | j | k) != 0 ? 1u : 0u);
+                            }
                         }
+                        mma_commit(&b_empty[sb]);
                     }
-                    mma_commit(&b_empty[sb]);
+                    mma_commit(&a_empty[sa]);
                 }
-                mma_commit(&a_empty[sa]);
+                mma_commit(&tmem_full[ab]);
             }
-            mma_commit(&tmem_full);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -275,7 +309,7 @@ ConvTcPlan conv1d_tc_plan(int Cin, int Cout, int K) {
     pl.N = Cout > 256 ? 256 : Cout;
     pl.CK = Cin >= 64 ? 64 : Cin;
     pl.n_tiles = ceil_div(Cout, pl.N);
-    pl.nacc = pl.N >= 256 ? 2 : 4;
+    pl.nacc = pl.N >= 128 ? 2 : 4;     // N = 128: two 256-column accumulator sets (double buffered); N = 256: one
     pl.ok = (Cin % pl.CK == 0) && (pl.CK % 16 == 0) && (pl.N % 32 == 0) && (Cout % pl.N == 0) && K >= 1;
     pl.tile_halves = (size_t)(pl.CK / 8) * pl.N * 8;
     pl.blob_halves = (size_t)pl.n_tiles * (Cin / pl.CK) * K * pl.tile_halves;
@@ -311,7 +345,11 @@ static void launch_tc_common(ConvTcParams& P, const ConvTcPlan& pl, int rows_to_
     const size_t smem = ((SA * a_stage + 127) & ~(size_t)127) + SB * b_stage + 128;
     constexpr int kMaxDyn = 227 * 1024 - 2048;      // opt-in limit minus this kernel's static shared memory
     if (smem > (size_t)kMaxDyn) throw CudaError("conv1d_tc: shared memory budget exceeded");
-    dim3 grid(ceil_div(rows_to_cover, tile), pl.n_tiles, batch);
+    P.tiles_t = ceil_div(rows_to_cover, tile); P.tiles_n = pl.n_tiles; P.batch = batch;
+    const int total_tiles = P.tiles_t * P.tiles_n * batch;
+    static int n_sm = 0;
+    if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+    dim3 grid(std::min(total_tiles, n_sm));          // one persistent CTA per SM
     ProfScope ps(KF_CONV1D_TC, st, flops, bytes);
     static bool attr2 = false, attr4 = false;
     if (pl.nacc == 2) {

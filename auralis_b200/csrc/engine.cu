@@ -99,9 +99,10 @@ struct Sequence {
     int n_samples = 0;
     float* wav_host = nullptr;    // pinned
     size_t wav_cap = 0;
-    DBuf<float> wav_dev;          // kept when d2h_wav == 0
-    std::vector<float> latents;   // filled on fetch request only
-    DBuf<float> lat_dev;          // [n_tokens, H] copy so the slot can be reused
+    float* wav_dev = nullptr;     // kept when d2h_wav == 0 (pooled device buffer)
+    size_t wav_dev_cap = 0;
+    float* lat_dev = nullptr;     // [n_tokens, H] copy so the slot can be reused (pooled device buffer)
+    size_t lat_dev_cap = 0;
 };
 
 class Engine {
@@ -212,6 +213,7 @@ private:
     int inflight = 0;
     bool d2h_wav = true;
     bool use_splitk = true;       // option "splitk"
+    bool use_pdl = true;          // option "pdl" (programmatic dependent launch along the decode chain)
     bool use_graphs = true;       // option "cuda_graphs"
     int eager_steps_done = 0;
     std::map<int, cudaGraphExec_t> decode_graphs;
@@ -242,7 +244,7 @@ private:
     }
     SampleState sample_state() const;
     void finish_speaker(int slot);
-    void gemm(const void* A, const Linear& lin, const float* resid, void* out, int M, int flags);
+    void gemm(const void* A, const Linear& lin, const float* resid, void* out, int M, int flags, bool pdl = false);
     void layers_forward(int M, bool prefill, int nseq, int max_nq);
     void head_and_sample(int M, const int* row_index, const int* slots_dev, const int* lat_pos, int advance_ctx, bool do_sample);
     void init_slot(Sequence& s, const int32_t* forced, int n_forced);
@@ -258,6 +260,9 @@ private:
     void retire(std::shared_ptr<Sequence> s);
     float* pinned_get(size_t n, size_t* cap);
     void pinned_put(float* p, size_t cap);
+    float* dev_get(size_t n, size_t* cap);           // device buffer pool (no cudaMalloc/cudaFree per chunk)
+    void dev_put(float* p, size_t cap);
+    std::vector<std::pair<float*, size_t>> dev_pool;
     void loop();
     void require_finalized() const { if (!finalized) throw std::runtime_error("weights not finalized: call xtts_finalize_weights first"); }
 };
@@ -380,6 +385,7 @@ Engine::~Engine() {
     cudaStreamSynchronize(st);
     for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second);
     for (auto& pr : pinned_pool) cudaFreeHost(pr.first);
+    for (auto& pr : dev_pool) cudaFree(pr.first);
     for (auto& kv : done_map) if (kv.second->wav_host) cudaFreeHost(kv.second->wav_host);
     if (h_finished) cudaFreeHost(h_finished);
     if (st) cudaStreamDestroy(st);
@@ -665,9 +671,9 @@ SampleState Engine::sample_state() const {
     return s;
 }
 
-void Engine::gemm(const void* A, const Linear& lin, const float* resid, void* out, int M, int flags) {
+void Engine::gemm(const void* A, const Linear& lin, const float* resid, void* out, int M, int flags, bool pdl) {
     if (bf16)
-        launch_gemm_bf16_tc(reinterpret_cast<const __nv_bfloat16*>(A), lin.w16.p, lin.b.p, resid, out, M, lin.N, lin.K, flags, st);
+        launch_gemm_bf16_tc(reinterpret_cast<const __nv_bfloat16*>(A), lin.w16.p, lin.b.p, resid, out, M, lin.N, lin.K, flags, st, pdl);
     else
         launch_gemm_f32(reinterpret_cast<const float*>(A), lin.w32.p, lin.b.p, resid, reinterpret_cast<float*>(out), M, lin.N, lin.K,
                         flags & ~GEMM_OUT_BF16, st);
@@ -684,15 +690,16 @@ void Engine::layers_forward(int M, bool prefill, int nseq, int max_nq) {
     // N/BN CTAs, so they run split-K into fp32 partials and the reduction is fused with the residual add and the
     // following LayerNorm (fixed summation order => deterministic).
     const bool splitk = bf16 && !prefill && use_splitk && M <= NSLOT && (H / 64) % 4 == 0 && (FF / 64) % 8 == 0;
+    const bool pdl = !prefill && use_pdl;            // decode chain: programmatic dependent launch
     auto ln = [&](const float* w, const float* b) {
-        if (bf16) launch_layernorm<__nv_bfloat16>(wX.p, w, b, wXn16.p, M, H, cfg.ln_eps, st);
-        else launch_layernorm<float>(wX.p, w, b, wXn32.p, M, H, cfg.ln_eps, st);
+        if (bf16) launch_layernorm<__nv_bfloat16>(wX.p, w, b, wXn16.p, M, H, cfg.ln_eps, st, pdl);
+        else launch_layernorm<float>(wX.p, w, b, wXn32.p, M, H, cfg.ln_eps, st, pdl);
     };
     if (splitk) ln(layers[0]->ln1w.p, layers[0]->ln1b.p);
     for (int l = 0; l < L; ++l) {
         Layer& ly = *layers[l];
         if (!splitk) ln(ly.ln1w.p, ly.ln1b.p);
-        gemm(Xn, ly.qkv, nullptr, wQKV.p, M, 0);
+        gemm(Xn, ly.qkv, nullptr, wQKV.p, M, 0, pdl);
         if (prefill) {
             if (bf16) launch_kv_write<__nv_bfloat16>(wQKV.p, M, d_row_slot.p, d_row_pos.p, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p, NH, st);
             else launch_kv_write<float>(wQKV.p, M, d_row_slot.p, d_row_pos.p, d_ctx_len.p, d_block_tables.p, max_pages, k32[l]->p, v32[l]->p, NH, st);
@@ -703,38 +710,35 @@ void Engine::layers_forward(int M, bool prefill, int nseq, int max_nq) {
             if (bf16) launch_attn_generic<__nv_bfloat16>(A, d_attnseq.p, nseq, max_nq, wATT16.p, H, st);
             else launch_attn_generic<float>(A, d_attnseq.p, nseq, max_nq, wATT32.p, H, st);
         } else {
-            if (bf16) {
-                launch_kv_write<__nv_bfloat16>(wQKV.p, M, d_active.p, nullptr, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p, NH, st);
-                launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p, wATT16.p, NH, st, decode_ctx_sum);
-            } else {
-                launch_kv_write<float>(wQKV.p, M, d_active.p, nullptr, d_ctx_len.p, d_block_tables.p, max_pages, k32[l]->p, v32[l]->p, NH, st);
-                launch_attn_decode<float, float>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, k32[l]->p, v32[l]->p, wATT32.p, NH, st, decode_ctx_sum);
-            }
+            // (the attention kernel appends this step's K/V to the cache itself)
+            if (bf16) launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p, wATT16.p, NH, st, decode_ctx_sum, pdl);
+            else launch_attn_decode<float, float>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, k32[l]->p, v32[l]->p, wATT32.p, NH, st, decode_ctx_sum, pdl);
         }
         if (splitk) {
-            launch_gemm_bf16_tc_splitk(wATT16.p, ly.o.w16.p, wPART.p, M, H, H, 4, st);
-            launch_residual_reduce_layernorm<__nv_bfloat16>(wX.p, wPART.p, 4, ly.o.b.p, ly.ln2w.p, ly.ln2b.p, wXn16.p, M, H, cfg.ln_eps, st);
-            gemm(Xn, ly.fc, nullptr, FFb, M, GEMM_GELU | oflag);
-            launch_gemm_bf16_tc_splitk(wFF16.p, ly.proj.w16.p, wPART.p, M, H, FF, 8, st);
+            launch_gemm_bf16_tc_splitk(wATT16.p, ly.o.w16.p, wPART.p, M, H, H, 4, st, pdl);
+            launch_residual_reduce_layernorm<__nv_bfloat16>(wX.p, wPART.p, 4, ly.o.b.p, ly.ln2w.p, ly.ln2b.p, wXn16.p, M, H, cfg.ln_eps, st, pdl);
+            gemm(Xn, ly.fc, nullptr, FFb, M, GEMM_GELU | oflag, pdl);
+            launch_gemm_bf16_tc_splitk(wFF16.p, ly.proj.w16.p, wPART.p, M, H, FF, 8, st, pdl);
             const bool last = (l + 1 == L);
             launch_residual_reduce_layernorm<__nv_bfloat16>(wX.p, wPART.p, 8, ly.proj.b.p, last ? nullptr : layers[l + 1]->ln1w.p,
                                                             last ? nullptr : layers[l + 1]->ln1b.p, last ? nullptr : wXn16.p, M, H,
-                                                            cfg.ln_eps, st);
+                                                            cfg.ln_eps, st, pdl);
         } else {
-            gemm(ATT, ly.o, wX.p, wX.p, M, GEMM_RESID);
+            gemm(ATT, ly.o, wX.p, wX.p, M, GEMM_RESID, pdl);
             ln(ly.ln2w.p, ly.ln2b.p);
-            gemm(Xn, ly.fc, nullptr, FFb, M, GEMM_GELU | oflag);
-            gemm(FFb, ly.proj, wX.p, wX.p, M, GEMM_RESID);
+            gemm(Xn, ly.fc, nullptr, FFb, M, GEMM_GELU | oflag, pdl);
+            gemm(FFb, ly.proj, wX.p, wX.p, M, GEMM_RESID, pdl);
         }
     }
 }
 
 // rows row_index[0..M) of X -> Y -> logits (wLOG[i]) ; latents captured ; optionally sample
 void Engine::head_and_sample(int M, const int* row_index, const int* slots_dev, const int* lat_pos, int advance_ctx, bool do_sample) {
-    if (bf16) launch_head_norms<__nv_bfloat16>(wX.p, row_index, lnfw.p, lnfb.p, fnw.p, fnb.p, wY16.p, d_latents.p, slots_dev, lat_pos, d_n_gen.p, CAP, M, H, cfg.ln_eps, st);
-    else launch_head_norms<float>(wX.p, row_index, lnfw.p, lnfb.p, fnw.p, fnb.p, wY32.p, d_latents.p, slots_dev, lat_pos, d_n_gen.p, CAP, M, H, cfg.ln_eps, st);
-    gemm(bf16 ? (void*)wY16.p : (void*)wY32.p, mel_head, nullptr, wLOG.p, M, 0);
-    if (do_sample) launch_sample(wLOG.p, Vpad, slots_dev, M, V, sample_state(), advance_ctx, st);
+    const bool pdl = advance_ctx && use_pdl;         // decode step only
+    if (bf16) launch_head_norms<__nv_bfloat16>(wX.p, row_index, lnfw.p, lnfb.p, fnw.p, fnb.p, wY16.p, d_latents.p, slots_dev, lat_pos, d_n_gen.p, CAP, M, H, cfg.ln_eps, st, pdl);
+    else launch_head_norms<float>(wX.p, row_index, lnfw.p, lnfb.p, fnw.p, fnb.p, wY32.p, d_latents.p, slots_dev, lat_pos, d_n_gen.p, CAP, M, H, cfg.ln_eps, st, pdl);
+    gemm(bf16 ? (void*)wY16.p : (void*)wY32.p, mel_head, nullptr, wLOG.p, M, 0, pdl);
+    if (do_sample) launch_sample(wLOG.p, Vpad, slots_dev, M, V, sample_state(), advance_ctx, st, pdl);
 }
 
 void Engine::init_slot(Sequence& s, const int32_t* forced, int n_forced) {
@@ -833,7 +837,7 @@ void Engine::decode_step(const std::vector<int>& active) {
     const int M = (int)active.size();
     d_active.upload(active.data(), M, st);
     auto enqueue = [&] {
-        launch_build_decode_rows(d_active.p, M, d_last_tok.p, d_n_gen.p, tables(), wX.p, st);
+        launch_build_decode_rows(d_active.p, M, d_last_tok.p, d_n_gen.p, tables(), wX.p, st, use_pdl);
         layers_forward(M, false, 0, 0);
         head_and_sample(M, nullptr, d_active.p, nullptr, 1, true);
     };
@@ -1020,6 +1024,23 @@ float* Engine::pinned_get(size_t n, size_t* cap) {
     *cap = n;
     return p;
 }
+float* Engine::dev_get(size_t n, size_t* cap) {
+    std::lock_guard<std::mutex> lk(pin_mu);
+    size_t best = dev_pool.size();
+    for (size_t i = 0; i < dev_pool.size(); ++i)
+        if (dev_pool[i].second >= n && (best == dev_pool.size() || dev_pool[i].second < dev_pool[best].second)) best = i;
+    if (best != dev_pool.size()) {
+        float* p = dev_pool[best].first; *cap = dev_pool[best].second;
+        dev_pool.erase(dev_pool.begin() + best);
+        return p;
+    }
+    float* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, n * sizeof(float)));
+    *cap = n;
+    return p;
+}
+void Engine::dev_put(float* p, size_t cap) { std::lock_guard<std::mutex> lk(pin_mu); dev_pool.emplace_back(p, cap); }
+
 void Engine::pinned_put(float* p, size_t cap) { std::lock_guard<std::mutex> lk(pin_mu); pinned_pool.emplace_back(p, cap); }
 
 void Engine::submit(uint64_t id, const int32_t* text, int n_text, int speaker, const xtts_sampling& sp) {
@@ -1046,8 +1067,8 @@ void Engine::finish_sequence(std::shared_ptr<Sequence> s) {
     s->tokens.resize(n);
     d_tokens.download(s->tokens.data(), n, st, (size_t)s->slot * CAP);
     // latents copy (device) so the slot can be recycled immediately
-    s->lat_dev.alloc((size_t)n * H);
-    CUDA_CHECK(cudaMemcpyAsync(s->lat_dev.p, d_latents.p + (size_t)s->slot * CAP * H, (size_t)n * H * sizeof(float),
+    s->lat_dev = dev_get((size_t)std::max(1, n) * H, &s->lat_dev_cap);
+    CUDA_CHECK(cudaMemcpyAsync(s->lat_dev, d_latents.p + (size_t)s->slot * CAP * H, (size_t)n * H * sizeof(float),
                                cudaMemcpyDeviceToDevice, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     st_tokens += n;
@@ -1063,7 +1084,7 @@ void Engine::finish_group(std::vector<std::shared_ptr<Sequence>>& grp) {
         std::vector<int> spk(nb);
         for (int i = 0; i < nb; ++i) {
             spk[i] = grp[b0 + i]->speaker;
-            CUDA_CHECK(cudaMemcpyAsync(vlat.p + (size_t)i * n * H, grp[b0 + i]->lat_dev.p, (size_t)n * H * sizeof(float),
+            CUDA_CHECK(cudaMemcpyAsync(vlat.p + (size_t)i * n * H, grp[b0 + i]->lat_dev, (size_t)n * H * sizeof(float),
                                        cudaMemcpyDeviceToDevice, st));
         }
         int ns = 0;
@@ -1075,8 +1096,8 @@ void Engine::finish_group(std::vector<std::shared_ptr<Sequence>>& grp) {
                 s->wav_host = pinned_get(ns, &s->wav_cap);
                 CUDA_CHECK(cudaMemcpyAsync(s->wav_host, vwav.p + (size_t)i * ns, (size_t)ns * sizeof(float), cudaMemcpyDeviceToHost, st));
             } else {
-                s->wav_dev.alloc(ns);
-                CUDA_CHECK(cudaMemcpyAsync(s->wav_dev.p, vwav.p + (size_t)i * ns, (size_t)ns * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                s->wav_dev = dev_get(ns, &s->wav_dev_cap);
+                CUDA_CHECK(cudaMemcpyAsync(s->wav_dev, vwav.p + (size_t)i * ns, (size_t)ns * sizeof(float), cudaMemcpyDeviceToDevice, st));
             }
             st_samples += ns;
         }
@@ -1200,20 +1221,18 @@ void Engine::fetch(uint64_t id, int32_t* tokens, float* wav, float* latents) {
     }
     if (tokens) std::memcpy(tokens, s->tokens.data(), s->tokens.size() * sizeof(int32_t));
     if (wav && s->n_samples > 0 && s->wav_host) std::memcpy(wav, s->wav_host, (size_t)s->n_samples * sizeof(float));
-    const bool dev_wav = wav && s->n_samples > 0 && !s->wav_host && s->wav_dev.p;
-    const bool dev_lat = latents && s->lat_dev.p;
+    const bool dev_wav = wav && s->n_samples > 0 && !s->wav_host && s->wav_dev;
+    const bool dev_lat = latents && s->lat_dev;
     if (dev_wav || dev_lat) {
         std::lock_guard<std::mutex> lk(mu);          // device copies go through the engine stream
         CUDA_CHECK(cudaSetDevice(cfg.device));
-        if (dev_wav) s->wav_dev.download(wav, s->n_samples, st);
-        if (dev_lat) s->lat_dev.download(latents, s->lat_dev.n, st);
+        if (dev_wav) CUDA_CHECK(cudaMemcpyAsync(wav, s->wav_dev, (size_t)s->n_samples * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (dev_lat) CUDA_CHECK(cudaMemcpyAsync(latents, s->lat_dev, s->tokens.size() * (size_t)H * sizeof(float), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
     }
     if (s->wav_host) { pinned_put(s->wav_host, s->wav_cap); s->wav_host = nullptr; }
-    if (s->wav_dev.p || s->lat_dev.p) {               // cudaFree under the GPU lock
-        std::lock_guard<std::mutex> lk(mu);
-        s->wav_dev.release(); s->lat_dev.release();
-    }
+    if (s->wav_dev) { dev_put(s->wav_dev, s->wav_dev_cap); s->wav_dev = nullptr; }
+    if (s->lat_dev) { dev_put(s->lat_dev, s->lat_dev_cap); s->lat_dev = nullptr; }
 }
 
 void Engine::set_option(const std::string& k, int64_t v) {
@@ -1221,6 +1240,7 @@ void Engine::set_option(const std::string& k, int64_t v) {
     if (k == "d2h_wav") d2h_wav = v != 0;
     else if (k == "tc_vocoder") use_tc_vocoder = v != 0;
     else if (k == "cuda_graphs") use_graphs = v != 0;
+    else if (k == "pdl") { use_pdl = v != 0; for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second); decode_graphs.clear(); }
     else if (k == "splitk") { use_splitk = v != 0; for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second); decode_graphs.clear(); }
     else if (k == "profile") { CUDA_CHECK(cudaSetDevice(cfg.device)); CUDA_CHECK(cudaStreamSynchronize(st)); g_prof.reset(); g_prof.enabled = v != 0; }
     else if (k == "reset_stats") {

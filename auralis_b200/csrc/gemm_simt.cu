@@ -8,6 +8,7 @@ namespace xtts {
 
 unsigned long long g_launch_count = 0;
 KernelProfiler g_prof;
+bool g_use_pdl = true;
 
 namespace {
 

@@ -13,8 +13,9 @@ namespace xtts {
 namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
-// ring depth per tile width: ~190 KB of operands in flight per CTA (the skinny decode GEMMs are latency-bound)
-__host__ __device__ constexpr int stages_for(int bn) { return bn >= 128 ? 6 : (bn >= 64 ? 8 : 10); }
+// ring depth per tile width
+// (BN <= 64 rings stay <= 100 KB so that, under PDL, the next GEMM's CTA can sit on the same SM and prefetch its weight tiles)
+__host__ __device__ constexpr int stages_for(int bn) { return bn >= 128 ? 6 : (bn >= 64 ? 4 : 5); }
 constexpr int kThreads = 192;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -134,9 +135,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
 
+    pdl_trigger();                                   // dependents may start their prologue now
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
+            // weights never depend on the previous kernel: their tiles for the first ring pass are requested BEFORE the
+            // dependency wait, the activation tiles right after it
+            const int pre = min(num_kb, STAGES);
+            for (int kb = 0; kb < pre; ++kb) {
+                mbar_expect_tx(&full_bar[kb], (uint32_t)a_box_rows * BK * 2 + B_BYTES);
+                tma_load_2d(sB + kb * B_BYTES, &tmB, &full_bar[kb], (kb_begin + kb) * BK, n0);
+            }
+            pdl_wait();
+            for (int kb = 0; kb < pre; ++kb)
+                tma_load_2d(sA + kb * A_BYTES, &tmA, &full_bar[kb], (kb_begin + kb) * BK, m0);
+            for (int kb = pre; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1, 1);
@@ -167,6 +179,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else {
         // ---------------- epilogue: warp (2..5) owns TMEM lanes [32*(warp%4), +32) = tile rows
         const int q = warp & 3;
+        pdl_wait();                                  // this warp reads `resid` and overwrites `out`
         mbar_wait(&tmem_full_bar, 0, 3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = m0 + q * 32 + lane;
@@ -252,7 +265,7 @@ void encode_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, u
 
 template <int BN>
 void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, const float* resid, void* out, int M,
-               int N, int K, int flags, cudaStream_t st, int splits, int a_box_rows) {
+               int N, int K, int flags, cudaStream_t st, int splits, int a_box_rows, bool pdl) {
     constexpr int STAGES = stages_for(BN);
     constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
     static bool attr_set = false;
@@ -263,7 +276,7 @@ void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
     ProfScope ps(KF_GEMM_TC, st, 2.0 * M * N * K,
                  2.0 * ((double)M * K + (double)N * K) + ((flags & GEMM_OUT_BF16) ? 2.0 : 4.0) * M * N);
-    gemm_bf16_tc_kernel<BN><<<grid, kThreads, smem, st>>>(tmA, tmB, bias, resid, out, M, N, K, flags, a_box_rows);
+    launch_k(gemm_bf16_tc_kernel<BN>, grid, dim3(kThreads), smem, st, pdl, tmA, tmB, bias, resid, out, M, N, K, flags, a_box_rows);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 
@@ -290,7 +303,7 @@ bool gemm_tc_init(std::string* err) {
 }
 
 void launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const float* resid,
-                         void* out, int M, int N, int K, int flags, cudaStream_t st) {
+                         void* out, int M, int N, int K, int flags, cudaStream_t st, bool pdl) {
     if (M <= 0 || N <= 0) return;
     if (K % BK != 0 || N % 32 != 0) throw CudaError("gemm_bf16_tc: need K % 64 == 0 and N % 32 == 0");
     if (!g_encode) {
@@ -307,15 +320,15 @@ void launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const f
     const int abox = a_box_rows_for(M);
     encode_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint32_t)abox);
     encode_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint32_t)bn);
-    if (bn == 128) launch_bn<128>(tmA, tmB, bias, resid, out, M, N, K, flags, st, 1, abox);
-    else if (bn == 64) launch_bn<64>(tmA, tmB, bias, resid, out, M, N, K, flags, st, 1, abox);
-    else launch_bn<32>(tmA, tmB, bias, resid, out, M, N, K, flags, st, 1, abox);
+    if (bn == 128) launch_bn<128>(tmA, tmB, bias, resid, out, M, N, K, flags, st, 1, abox, pdl);
+    else if (bn == 64) launch_bn<64>(tmA, tmB, bias, resid, out, M, N, K, flags, st, 1, abox, pdl);
+    else launch_bn<32>(tmA, tmB, bias, resid, out, M, N, K, flags, st, 1, abox, pdl);
 }
 
 
 // split-K variant for the skinny decode GEMMs (N = hidden): partials[z][M][N] = A[:, kz] . W[:, kz]^T, fp32, no epilogue
 void launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, float* partials, int M, int N, int K,
-                                int splits, cudaStream_t st) {
+                                int splits, cudaStream_t st, bool pdl) {
     if (M <= 0 || N <= 0) return;
     if (K % BK != 0 || N % 32 != 0 || splits < 1 || (K / BK) % splits != 0) throw CudaError("gemm_bf16_tc_splitk: bad shape");
     if (!g_encode) { std::string err; if (!gemm_tc_init(&err)) throw CudaError(err); }
@@ -327,9 +340,9 @@ void launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, 
     const int abox = a_box_rows_for(M);
     encode_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint32_t)abox);
     encode_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint32_t)bn);
-    if (bn == 128) launch_bn<128>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox);
-    else if (bn == 64) launch_bn<64>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox);
-    else launch_bn<32>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox);
+    if (bn == 128) launch_bn<128>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox, pdl);
+    else if (bn == 64) launch_bn<64>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox, pdl);
+    else launch_bn<32>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox, pdl);
 }
 
 }  // namespace xtts

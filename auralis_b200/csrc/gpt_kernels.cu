@@ -40,6 +40,7 @@ __global__ void build_rows_kernel(const RowDesc* __restrict__ rows, GptTables t,
 
 __global__ void build_decode_rows_kernel(const int* __restrict__ active, const int* __restrict__ last_tok,
                                          const int* __restrict__ n_gen, GptTables t, float* __restrict__ X) {
+    pdl_trigger(); pdl_wait();
     const int slot = active[blockIdx.x];
     const int H = t.H;
     const float4* a = reinterpret_cast<const float4*>(t.wte + (size_t)last_tok[slot] * H);
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ X, const float* __restrict__ w, const float* __restrict__ b,
                  TOut* __restrict__ Y, int H, float eps) {
     __shared__ float red[32];
+    pdl_trigger(); pdl_wait();
     const float* x = X + (size_t)blockIdx.x * H;
     float s = 0.f;
     for (int i = threadIdx.x; i < H; i += blockDim.x) s += x[i];
@@ -92,6 +94,7 @@ residual_reduce_ln_kernel(float* __restrict__ X, const float* __restrict__ P, in
                           TOut* __restrict__ Y, int H, float eps) {
     extern __shared__ float buf[];
     __shared__ float red[32];
+    pdl_trigger(); pdl_wait();
     float* x = X + (size_t)blockIdx.x * H;
     const float* p = P + (size_t)blockIdx.x * H;
     for (int c = threadIdx.x; c < H; c += blockDim.x) {
@@ -120,6 +123,7 @@ head_norms_kernel(const float* __restrict__ X, const int* __restrict__ row_index
                   float eps) {
     extern __shared__ float buf[];
     __shared__ float red[32];
+    pdl_trigger(); pdl_wait();
     const int i = blockIdx.x;
     const int r = row_index ? row_index[i] : i;
     const float* x = X + (size_t)r * H;
@@ -196,39 +200,57 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {          // streami
 
 // One CTA per (sequence, head); the 4 warps take pages round-robin.  Per 32-token page a warp issues
 //   QK^T : lane = token, 64/X independent 16-byte loads (K atoms of one token are 32*16 B apart, a warp-load is 512 B)
-//   PV   : lane = (token group, 16-byte dim chunk), 32*X/64... independent 16-byte loads, p broadcast by shuffle
-// so ~16 wide loads are in flight per warp and page (the first version issued 32 dependent 4-byte V loads).
+//   PV   : lane = (token group, 16-byte dim chunk), independent 16-byte loads, p broadcast by shuffle
+// so ~16 wide loads are in flight per warp and page.  The step's own token is appended to the cache here (what
+// reshape_and_cache does in vLLM) and attended to straight from shared memory, rounded to the cache type first so the
+// result is identical to reading it back.
 // HBM-bound: algorithmic bytes = 2 * ctx * 64 * sizeof(TKV) per (sequence, head).
 template <typename TKV, typename TOut>
 __global__ void __launch_bounds__(128)
 attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active, const int* __restrict__ ctx_len,
-                   const int* __restrict__ block_tables, int max_pages, const TKV* __restrict__ kpool,
-                   const TKV* __restrict__ vpool, TOut* __restrict__ out, int heads) {
+                   const int* __restrict__ block_tables, int max_pages, TKV* __restrict__ kpool, TKV* __restrict__ vpool,
+                   TOut* __restrict__ out, int heads) {
     constexpr int X = KVec<TKV>::X;
     constexpr int NCH = kHeadDim / X;                 // 16-byte atoms per token row (8 bf16 / 16 fp32)
     constexpr int TPI = 32 / NCH;                     // tokens covered by one warp-wide V load (4 / 2)
     constexpr int VIT = kPageTokens / TPI;            // V loads per page (8 / 16)
-    __shared__ __align__(16) float qs[kHeadDim];
+    __shared__ __align__(16) float qs[kHeadDim], ks[kHeadDim], vs[kHeadDim];
     __shared__ float pm[4], pl[4];
     __shared__ float pacc[4][kHeadDim];
+    pdl_trigger(); pdl_wait();
     const int i = blockIdx.x, h = blockIdx.y;
     const int H = heads * kHeadDim;
     const int slot = active[i];
-    const int ctx = ctx_len[slot] + 1;
+    const int past = ctx_len[slot];                   // tokens already cached; the new one goes to position `past`
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid < kHeadDim) qs[tid] = QKV[(size_t)i * 3 * H + h * kHeadDim + tid] * 0.125f;   // 64^-0.5
+    const int* bt = block_tables + (size_t)slot * max_pages;
+    {
+        const float* row = QKV + (size_t)i * 3 * H + h * kHeadDim;
+        const int d = tid & 63;
+        const int page = bt[past / kPageTokens], tk = past % kPageTokens;
+        const size_t pbase = ((size_t)page * heads + h) * (kPageTokens * kHeadDim);
+        if (tid < 64) {
+            qs[d] = row[d] * 0.125f;                                                 // 64^-0.5
+            const TKV k = from_f32<TKV>(row[H + d]);
+            ks[d] = to_f32<TKV>(k);
+            kpool[pbase + ((size_t)(d / X) * kPageTokens + tk) * X + (d % X)] = k;
+        } else {
+            const TKV v = from_f32<TKV>(row[2 * H + d]);
+            vs[d] = to_f32<TKV>(v);
+            vpool[pbase + (size_t)tk * kHeadDim + d] = v;
+        }
+    }
     __syncthreads();
     const int tg = lane / NCH, dc = lane % NCH;       // PV role of this lane: token group, dim chunk
     float m = -INFINITY, l = 0.f;
     float acc[X];
 #pragma unroll
     for (int e = 0; e < X; ++e) acc[e] = 0.f;
-    const int npages = (ctx + kPageTokens - 1) / kPageTokens;
-    const int* bt = block_tables + (size_t)slot * max_pages;
+    const int npages = (past + kPageTokens - 1) / kPageTokens;
     for (int pg = w; pg < npages; pg += 4) {
         const int page = bt[pg];
         const size_t pbase = ((size_t)page * heads + h) * (kPageTokens * kHeadDim);
-        const int nvalid = min(kPageTokens, ctx - pg * kPageTokens);
+        const int nvalid = min(kPageTokens, past - pg * kPageTokens);
         // ---- issue every load of the page up front
         uint4 kraw[NCH], vraw[VIT];
         const TKV* kb = kpool + pbase + (size_t)lane * X;
@@ -266,6 +288,18 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
                 for (int e = 0; e < X; ++e) acc[e] = fmaf(pj, vf[e], acc[e]);
             }
         }
+        m = mnew;
+    }
+    if (w == 0) {
+        // ---- the step's own token, from shared memory
+        float s = qs[lane] * ks[lane] + qs[lane + 32] * ks[lane + 32];
+        s = warp_sum(s);
+        const float mnew = fmaxf(m, s);
+        const float p = expf(s - mnew);
+        const float corr = (m == -INFINITY) ? 0.f : expf(m - mnew);
+        l = l * corr + p;
+#pragma unroll
+        for (int e = 0; e < X; ++e) acc[e] = acc[e] * corr + ((tg == 0) ? p * vs[dc * X + e] : 0.f);
         m = mnew;
     }
     // ---- fold the token groups of the warp (lanes with equal dc), then the 4 warps
@@ -418,6 +452,7 @@ sample_kernel(const float* __restrict__ logits, int ld, const int* __restrict__ 
     __shared__ float red[32];
     __shared__ int redi[32];
     __shared__ float scan_part[256];
+    pdl_trigger(); pdl_wait();
     const int tid = threadIdx.x;
     const int slot = active[blockIdx.x];
     const int n = S.n_gen[slot];
@@ -594,48 +629,48 @@ void launch_build_rows(const RowDesc* rows, int n_rows, GptTables t, float* X, c
 }
 
 void launch_build_decode_rows(const int* active, int M, const int* last_tok, const int* n_gen, GptTables t,
-                              float* X, cudaStream_t st) {
+                              float* X, cudaStream_t st, bool pdl) {
     if (M <= 0) return;
     ProfScope ps(KF_EMBED, st, 0, 12.0 * M * t.H);
-    build_decode_rows_kernel<<<M, 256, 0, st>>>(active, last_tok, n_gen, t, X);
+    launch_k(build_decode_rows_kernel, dim3(M), dim3(256), 0, st, pdl, active, last_tok, n_gen, t, X);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 
 template <typename TOut>
 void launch_layernorm(const float* X, const float* w, const float* b, TOut* Y, int M, int H, float eps,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool pdl) {
     if (M <= 0) return;
     ProfScope ps(KF_NORM, st, 0, (4.0 + sizeof(TOut)) * M * H);
-    layernorm_kernel<TOut><<<M, 256, 0, st>>>(X, w, b, Y, H, eps);
+    launch_k(layernorm_kernel<TOut>, dim3(M), dim3(256), 0, st, pdl, X, w, b, Y, H, eps);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
-template void launch_layernorm<float>(const float*, const float*, const float*, float*, int, int, float, cudaStream_t);
-template void launch_layernorm<__nv_bfloat16>(const float*, const float*, const float*, __nv_bfloat16*, int, int, float, cudaStream_t);
+template void launch_layernorm<float>(const float*, const float*, const float*, float*, int, int, float, cudaStream_t, bool);
+template void launch_layernorm<__nv_bfloat16>(const float*, const float*, const float*, __nv_bfloat16*, int, int, float, cudaStream_t, bool);
 
 template <typename TOut>
 void launch_residual_reduce_layernorm(float* X, const float* partials, int splits, const float* bias, const float* w,
-                                      const float* b, TOut* Y, int M, int H, float eps, cudaStream_t st) {
+                                      const float* b, TOut* Y, int M, int H, float eps, cudaStream_t st, bool pdl) {
     if (M <= 0) return;
     ProfScope ps(KF_NORM, st, 0, (8.0 + 4.0 * splits + sizeof(TOut)) * M * H);
-    residual_reduce_ln_kernel<TOut><<<M, 256, H * sizeof(float), st>>>(X, partials, splits, (size_t)M * H, bias, w, b, Y, H, eps);
+    launch_k(residual_reduce_ln_kernel<TOut>, dim3(M), dim3(256), H * sizeof(float), st, pdl, X, partials, splits, (size_t)M * H, bias, w, b, Y, H, eps);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
-template void launch_residual_reduce_layernorm<float>(float*, const float*, int, const float*, const float*, const float*, float*, int, int, float, cudaStream_t);
-template void launch_residual_reduce_layernorm<__nv_bfloat16>(float*, const float*, int, const float*, const float*, const float*, __nv_bfloat16*, int, int, float, cudaStream_t);
+template void launch_residual_reduce_layernorm<float>(float*, const float*, int, const float*, const float*, const float*, float*, int, int, float, cudaStream_t, bool);
+template void launch_residual_reduce_layernorm<__nv_bfloat16>(float*, const float*, int, const float*, const float*, const float*, __nv_bfloat16*, int, int, float, cudaStream_t, bool);
 
 template <typename TOut>
 void launch_head_norms(const float* X, const int* row_index, const float* lnf_w, const float* lnf_b,
                        const float* fn_w, const float* fn_b, TOut* Y, float* latents, const int* slots,
                        const int* lat_pos, const int* n_gen, int lat_rows_per_slot, int M, int H, float eps,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool pdl) {
     if (M <= 0) return;
     ProfScope ps(KF_NORM, st, 0, (8.0 + sizeof(TOut)) * M * H);
-    head_norms_kernel<TOut><<<M, 256, H * sizeof(float), st>>>(X, row_index, lnf_w, lnf_b, fn_w, fn_b, Y, latents,
-                                                                slots, lat_pos, n_gen, lat_rows_per_slot, H, eps);
+    launch_k(head_norms_kernel<TOut>, dim3(M), dim3(256), H * sizeof(float), st, pdl, X, row_index, lnf_w, lnf_b, fn_w, fn_b, Y,
+             latents, slots, lat_pos, n_gen, lat_rows_per_slot, H, eps);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
-template void launch_head_norms<float>(const float*, const int*, const float*, const float*, const float*, const float*, float*, float*, const int*, const int*, const int*, int, int, int, float, cudaStream_t);
-template void launch_head_norms<__nv_bfloat16>(const float*, const int*, const float*, const float*, const float*, const float*, __nv_bfloat16*, float*, const int*, const int*, const int*, int, int, int, float, cudaStream_t);
+template void launch_head_norms<float>(const float*, const int*, const float*, const float*, const float*, const float*, float*, float*, const int*, const int*, const int*, int, int, int, float, cudaStream_t, bool);
+template void launch_head_norms<__nv_bfloat16>(const float*, const int*, const float*, const float*, const float*, const float*, __nv_bfloat16*, float*, const int*, const int*, const int*, int, int, int, float, cudaStream_t, bool);
 
 template <typename TKV>
 void launch_kv_write(const float* QKV, int M, const int* row_slot, const int* row_pos, const int* ctx_len,
@@ -651,18 +686,18 @@ template void launch_kv_write<__nv_bfloat16>(const float*, int, const int*, cons
 
 template <typename TKV, typename TOut>
 void launch_attn_decode(const float* QKV, const int* active, int M, const int* ctx_len, const int* block_tables,
-                        int max_pages, const TKV* kpool, const TKV* vpool, TOut* out, int heads, cudaStream_t st,
-                        double ctx_sum_hint) {
+                        int max_pages, TKV* kpool, TKV* vpool, TOut* out, int heads, cudaStream_t st,
+                        double ctx_sum_hint, bool pdl) {
     if (M <= 0) return;
     // algorithmic bytes: K and V of every cached token of every sequence, once
     ProfScope ps(KF_ATTN_DECODE, st, 4.0 * ctx_sum_hint * heads * kHeadDim,
                  2.0 * ctx_sum_hint * heads * kHeadDim * sizeof(TKV));
-    attn_decode_kernel<TKV, TOut><<<dim3(M, heads), 128, 0, st>>>(QKV, active, ctx_len, block_tables, max_pages,
-                                                                 kpool, vpool, out, heads);
+    launch_k(attn_decode_kernel<TKV, TOut>, dim3(M, heads), dim3(128), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
+             kpool, vpool, out, heads);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
-template void launch_attn_decode<float, float>(const float*, const int*, int, const int*, const int*, int, const float*, const float*, float*, int, cudaStream_t, double);
-template void launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(const float*, const int*, int, const int*, const int*, int, const __nv_bfloat16*, const __nv_bfloat16*, __nv_bfloat16*, int, cudaStream_t, double);
+template void launch_attn_decode<float, float>(const float*, const int*, int, const int*, const int*, int, float*, float*, float*, int, cudaStream_t, double, bool);
+template void launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(const float*, const int*, int, const int*, const int*, int, __nv_bfloat16*, __nv_bfloat16*, __nv_bfloat16*, int, cudaStream_t, double, bool);
 
 template <typename TOut>
 void launch_attn_generic(AttnLayout L, const AttnSeq* seqs, int nseq, int max_nq, TOut* out, int out_row_stride,
@@ -676,11 +711,11 @@ template void launch_attn_generic<float>(AttnLayout, const AttnSeq*, int, int, f
 template void launch_attn_generic<__nv_bfloat16>(AttnLayout, const AttnSeq*, int, int, __nv_bfloat16*, int, cudaStream_t);
 
 void launch_sample(const float* logits, int ld_logits, const int* active, int M, int V, SampleState s,
-                   int advance_ctx, cudaStream_t st) {
+                   int advance_ctx, cudaStream_t st, bool pdl) {
     if (M <= 0) return;
     if (V > SV) throw CudaError("sample: vocabulary larger than 2048 is not supported");
     ProfScope ps(KF_SAMPLE, st, 0, 4.0 * M * V);
-    sample_kernel<<<M, 256, 0, st>>>(logits, ld_logits, active, V, s, advance_ctx);
+    launch_k(sample_kernel, dim3(M), dim3(256), 0, st, pdl, logits, ld_logits, active, V, s, advance_ctx);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 

@@ -18,10 +18,12 @@ void launch_gemm_f32(const float* A, const float* W, const float* bias, const fl
 
 // bf16 tcgen05/TMA path (fast mode).  A [M,K] bf16 row-major, W [N,K] bf16 row-major; fp32 accum in TMEM.
 // out is fp32 unless GEMM_OUT_BF16.  K % 64 == 0, N % 16 == 0 required.
+// `pdl`: launch with the programmatic-dependent-launch attribute (decode chain); every kernel that can be launched
+// that way executes griddepcontrol.wait before touching its predecessor's outputs
 void launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const float* resid,
-                         void* out, int M, int N, int K, int flags, cudaStream_t st);
+                         void* out, int M, int N, int K, int flags, cudaStream_t st, bool pdl = false);
 void launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, float* partials, int M, int N, int K,
-                                int splits, cudaStream_t st);
+                                int splits, cudaStream_t st, bool pdl = false);
 bool gemm_tc_init(std::string* err);   // resolves cuTensorMapEncodeTiled; false -> err filled
 
 void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st);
@@ -47,17 +49,17 @@ struct GptTables {        // embedding tables (device, fp32)
 void launch_build_rows(const RowDesc* rows, int n_rows, GptTables t, float* X, cudaStream_t st);
 // decode input rows: X[i] = wte[last_tok[slot]] + wpe[n_gen[slot]],  slot = active[i]
 void launch_build_decode_rows(const int* active, int M, const int* last_tok, const int* n_gen, GptTables t,
-                              float* X, cudaStream_t st);
+                              float* X, cudaStream_t st, bool pdl = false);
 
 template <typename TOut>
 void launch_layernorm(const float* X, const float* w, const float* b, TOut* Y, int M, int H, float eps,
-                      cudaStream_t st);
+                      cudaStream_t st, bool pdl = false);
 
 // X[m] += bias + sum_z partials[z][m]  (deterministic split-K reduction fused with the residual add), then
 // Y[m] = LN(X[m]) when Y != nullptr  (the following block's LayerNorm)
 template <typename TOut>
 void launch_residual_reduce_layernorm(float* X, const float* partials, int splits, const float* bias, const float* w,
-                                      const float* b, TOut* Y, int M, int H, float eps, cudaStream_t st);
+                                      const float* b, TOut* Y, int M, int H, float eps, cudaStream_t st, bool pdl = false);
 
 // y = LN_fn(LN_lnf(X[row_index[i]]));  Y[i] = y (GEMM operand);
 // latents[slots[i]][lat_pos ? lat_pos[i] : n_gen[slots[i]]] = LN_fn(y)
@@ -65,7 +67,7 @@ template <typename TOut>
 void launch_head_norms(const float* X, const int* row_index, const float* lnf_w, const float* lnf_b,
                        const float* fn_w, const float* fn_b, TOut* Y, float* latents, const int* slots,
                        const int* lat_pos, const int* n_gen, int lat_rows_per_slot, int M, int H, float eps,
-                       cudaStream_t st);
+                       cudaStream_t st, bool pdl = false);
 
 // KV page layout (per layer):  K: [page][head][D/X][32 tok][X]   V: [page][head][32 tok][D]
 //   X = 16 bytes / sizeof(TKV)  (so one lane = one token reads 16 B, coalesced across the warp)
@@ -74,11 +76,12 @@ void launch_kv_write(const float* QKV, int M, const int* row_slot, const int* ro
                      const int* block_tables, int max_pages, TKV* kpool, TKV* vpool, int heads,
                      cudaStream_t st);
 
-// decode attention over the paged cache; ctx = ctx_len[slot] + 1 (new token already written)
+// decode attention over the paged cache, ctx = ctx_len[slot] + 1.  The kernel also appends the new token's K/V
+// (read from the QKV row) to the cache — the reshape_and_cache step — so no separate kv_write launch is needed.
 template <typename TKV, typename TOut>
 void launch_attn_decode(const float* QKV, const int* active, int M, const int* ctx_len,
-                        const int* block_tables, int max_pages, const TKV* kpool, const TKV* vpool,
-                        TOut* out, int heads, cudaStream_t st, double ctx_sum_hint = 0);
+                        const int* block_tables, int max_pages, TKV* kpool, TKV* vpool,
+                        TOut* out, int heads, cudaStream_t st, double ctx_sum_hint = 0, bool pdl = false);
 
 struct AttnSeq { int q_start, nq, kv_start, nk; };
 struct AttnLayout {
@@ -105,7 +108,7 @@ struct SampleState {      // per-slot arrays (device)
     int tokens_cap, seen_words;
 };
 void launch_sample(const float* logits, int ld_logits, const int* active, int M, int V, SampleState s,
-                   int advance_ctx, cudaStream_t st);
+                   int advance_ctx, cudaStream_t st, bool pdl = false);
 
 // ------------------------------------------------------------------------------------------
 // Vocoder kernels (fp32, channel-major activations [C][L])

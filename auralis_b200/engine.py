@@ -93,6 +93,7 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
         self._waiters: Dict[int, Tuple[asyncio.AbstractEventLoop, asyncio.Future]] = {}
         self._wlock = threading.Lock()
         self._stop = False
+        self._parked = False
         self._paused = False       # set while a caller drives the native completion queue itself (bench device arm)
         self._poller = threading.Thread(target=self._poll_loop, name="xtts-poll", daemon=True)
         self._poller.start()
@@ -228,14 +229,21 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
                 yield TTSOutput(array=output.wav, start_time=request.start_time if request else None,
                                 token_length=len(output.token_ids))
 
+    def park_poller(self, parked: bool = True):
+        """Park / resume the completion poller (a caller that drives `native.run_batch` itself must own the queue)."""
+        self._paused = parked
+        while parked and not self._parked:    # acknowledged between two poll() calls (<= 50 ms)
+            time.sleep(0.002)
+
     def run_batch_direct(self, jobs, **kw):
         """Drive the native engine synchronously (no asyncio): the poller thread is parked for the duration."""
-        self._paused = True
-        time.sleep(0.12)                      # let an in-flight poll() time out
+        was = self._paused
+        self.park_poller(True)
         try:
             return self.native.run_batch(jobs, **kw)
         finally:
-            self._paused = False
+            if not was:
+                self.park_poller(False)
 
     async def shutdown(self):
         self._stop = True
@@ -246,8 +254,10 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
     def _poll_loop(self):
         while not self._stop:
             if self._paused:
-                time.sleep(0.01)
+                self._parked = True
+                time.sleep(0.002)
                 continue
+            self._parked = False
             try:
                 r = self.native.poll(50)
             except Exception:
