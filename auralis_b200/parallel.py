@@ -47,12 +47,13 @@ def lpt_partition(costs: Sequence[float], world: int) -> List[List[int]]:
 
 
 def gather_waveforms(local: Dict[int, np.ndarray], n_items: int, device: torch.device | None = None,
-                     group=None) -> List[np.ndarray] | None:
+                     group=None, dst: int | None = None) -> List[np.ndarray] | None:
     """All-gather {item index -> waveform} from every rank; returns the list in item order on every rank.
 
     Wire format: int64 [2*k] (index, length) table, then one flat fp32 payload per rank, both max-padded so a
     single `all_gather_into_tensor` moves each.  With NCCL the payload lives in HBM (`device`), so the
-    transfer is GPU->NVSwitch->GPU; with gloo (CPU tests) it stays on the host."""
+    transfer is GPU->NVSwitch->GPU; with gloo (CPU tests) it stays on the host.
+    `dst`: only that rank copies the gathered payload back to the host and returns the list (others return None)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return [local[i] for i in range(n_items)]
@@ -76,6 +77,8 @@ def gather_waveforms(local: Dict[int, np.ndarray], n_items: int, device: torch.d
         off += w.numel()
     allp = torch.empty(world * payload.numel(), dtype=torch.float32, device=dev)
     dist.all_gather_into_tensor(allp, payload, group=group)
+    if dst is not None and dist.get_rank(group) != dst:
+        return None
     tables = tables.cpu().view(world, -1)
     allp = allp.cpu().view(world, -1).numpy()
     out: List[np.ndarray | None] = [None] * n_items

@@ -255,7 +255,7 @@ def main():
         # DP epilogue: gather every rank's waveforms on all ranks (rank 0 is the consumer) over NCCL
         if world > 1:
             local_w = {rank * len(outs) + i: o.array for i, o in enumerate(outs)}
-            parallel.gather_waveforms(local_w, world * len(outs), torch.device("cuda", local))
+            parallel.gather_waveforms(local_w, world * len(outs), torch.device("cuda", local), dst=0)
         return sum(o.array.shape[0] for o in outs), sum(len(t) for t in texts)
 
     def log(msg):
