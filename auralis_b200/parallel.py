@@ -27,7 +27,9 @@ def init_from_env(backend: str | None = None) -> Tuple[int, int, int]:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+            dist.init_process_group(backend=backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, world, local
 
 
@@ -44,6 +46,18 @@ def lpt_partition(costs: Sequence[float], world: int) -> List[List[int]]:
     for lst in out:
         lst.sort()
     return out
+
+
+_HOST_BUFFERS: Dict[str, torch.Tensor] = {}
+
+
+def _host_buffer(tag: str, n: int, pinned: bool) -> torch.Tensor:
+    """Cached host staging buffer (pinned when a GPU is in play) — the gather runs every step with the same sizes."""
+    b = _HOST_BUFFERS.get(tag)
+    if b is None or b.numel() < n or b.is_pinned() != pinned:
+        b = torch.empty(n, dtype=torch.float32, pin_memory=pinned)
+        _HOST_BUFFERS[tag] = b
+    return b[:n]
 
 
 def gather_waveforms(local: Dict[int, np.ndarray], n_items: int, device: torch.device | None = None,
@@ -69,24 +83,32 @@ def gather_waveforms(local: Dict[int, np.ndarray], n_items: int, device: torch.d
     tpad[: table.numel()] = table.to(dev)
     tables = torch.empty(world * tpad.numel(), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(tables, tpad, group=group)
-    payload = torch.zeros(max(1, max_n), dtype=torch.float32, device=dev)
+    on_gpu = dev.type == "cuda"
+    # stage this rank's audio in one (cached, pinned) host buffer -> a single H2D copy
+    stage = _host_buffer("send", max(1, max_n), on_gpu)
     off = 0
     for i in idx:
-        w = torch.from_numpy(np.ascontiguousarray(local[i], dtype=np.float32))
-        payload[off: off + w.numel()] = w.to(dev, non_blocking=True)
-        off += w.numel()
+        n = int(local[i].shape[0])
+        stage[off: off + n] = torch.from_numpy(np.ascontiguousarray(local[i], dtype=np.float32))
+        off += n
+    payload = stage.to(dev, non_blocking=True) if on_gpu else stage
     allp = torch.empty(world * payload.numel(), dtype=torch.float32, device=dev)
     dist.all_gather_into_tensor(allp, payload, group=group)
     if dst is not None and dist.get_rank(group) != dst:
         return None
     tables = tables.cpu().view(world, -1)
-    allp = allp.cpu().view(world, -1).numpy()
+    if on_gpu:                                    # one D2H into a cached pinned buffer; the results are views into it
+        recv = _host_buffer("recv", allp.numel(), True)
+        recv.copy_(allp, non_blocking=False)
+        allp_h = recv.view(world, -1).numpy()
+    else:
+        allp_h = allp.view(world, -1).numpy()
     out: List[np.ndarray | None] = [None] * n_items
     for r in range(world):
         off = 0
         for j in range(int(metas[r, 0])):
             i, n = int(tables[r, 2 * j]), int(tables[r, 2 * j + 1])
-            out[i] = allp[r, off: off + n].copy()
+            out[i] = allp_h[r, off: off + n] if on_gpu else allp_h[r, off: off + n].copy()
             off += n
     missing = [i for i, w in enumerate(out) if w is None]
     if missing:

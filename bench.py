@@ -322,6 +322,9 @@ def main():
         torch.distributed.all_reduce(s, op=torch.distributed.ReduceOp.SUM)
         samples_dev, tokens_dev, samples_e2e = float(s[0]), float(s[1]), float(s[2])
     if rank != 0:
+        loop.run_until_complete(tts.shutdown())
+        if world > 1:
+            torch.distributed.destroy_process_group()
         return
 
     audio_s_dev = samples_dev / 24000.0
@@ -379,8 +382,10 @@ def main():
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     loop.run_until_complete(tts.shutdown())
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
