@@ -1125,7 +1125,13 @@ void Engine::loop() {
             std::unique_lock<std::mutex> q(q_mu);
             cv_work.wait(q, [&] { return stop.load() || !pending.empty() || !waiting.empty() || !running.empty(); });
             if (stop.load()) break;
-            while (!pending.empty()) { waiting.push_back(pending.front()); pending.pop_front(); }
+            while (!pending.empty()) {
+                // stable priority insert: lower `priority` (chunk index) first, FIFO among equals
+                auto s = pending.front(); pending.pop_front();
+                auto it = waiting.end();
+                while (it != waiting.begin() && (*(it - 1))->sp.priority > s->sp.priority) --it;
+                waiting.insert(it, s);
+            }
         }
         std::lock_guard<std::mutex> lk(mu);
         auto fail = [&](std::shared_ptr<Sequence>& s, int code, const char* what) {

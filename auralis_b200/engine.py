@@ -196,7 +196,7 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
             sp = native.Sampling(temperature=request.temperature, top_p=request.top_p, top_k=request.top_k,
                                  repetition_penalty=request.repetition_penalty,
                                  max_tokens=self.dims.gpt.max_audio_tokens, stop_token=self.mel_eos_token_id,
-                                 seed=base_seed, seq_seed=seq_index, vocode=True)
+                                 seed=base_seed, seq_seed=seq_index, vocode=True, priority=seq_index)
             rid = f"{request.request_id}_{seq_index}"
             generators.append(self._chunk_generator(rid, ids, slot, sp))
             request_ids.append(rid)

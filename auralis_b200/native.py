@@ -47,7 +47,8 @@ class XttsConfig(C.Structure):
 class XttsSampling(C.Structure):
     _fields_ = [("temperature", C.c_float), ("top_p", C.c_float), ("repetition_penalty", C.c_float),
                 ("top_k", C.c_int32), ("max_tokens", C.c_int32), ("stop_token", C.c_int32),
-                ("seed", C.c_uint64), ("seq_seed", C.c_int32), ("vocode", C.c_int32)]
+                ("seed", C.c_uint64), ("seq_seed", C.c_int32), ("vocode", C.c_int32), ("priority", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class XttsResult(C.Structure):
@@ -173,12 +174,14 @@ class Sampling:
     seed: int = 0
     seq_seed: int = 0
     vocode: bool = True
+    priority: int = 0
 
     def c(self) -> XttsSampling:
         s = XttsSampling()
         s.temperature, s.top_p, s.repetition_penalty = self.temperature, self.top_p, self.repetition_penalty
         s.top_k, s.max_tokens, s.stop_token = self.top_k, self.max_tokens, self.stop_token
         s.seed, s.seq_seed, s.vocode = self.seed, self.seq_seed, 1 if self.vocode else 0
+        s.priority = self.priority
         return s
 
 

@@ -342,10 +342,13 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     total_ms = sum(v["ms"] for v in prof.values()) or 1.0
     dom_name, dom = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else ("none", {"ms": 1, "flops": 0, "bytes": 0, "launches": 1})
-    fams = {k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / total_ms, 4), "launches": v["launches"],
-                "GB/s": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] else None,
-                "TFLOP/s": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] else None}
-            for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    fams = {}
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        gbs = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else 0.0
+        tfs = v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] else 0.0
+        fams[k] = {"ms": round(v["ms"], 3), "share": round(v["ms"] / total_ms, 4), "launches": v["launches"],
+                   "GB/s": round(gbs, 1), "TFLOP/s": round(tfs, 2),
+                   "frac_of_hbm_peak": round(gbs / hbm_peak, 4), "frac_of_tensor_peak": round(tfs / tc_peak, 4)}
     tensor_bound = dom_name.startswith("gemm_bf16") or dom_name.startswith("conv1d_tc")
     if tensor_bound:
         ach = dom["flops"] / (dom["ms"] * 1e-3) / 1e12

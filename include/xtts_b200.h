@@ -62,6 +62,9 @@ typedef struct xtts_sampling {
     uint64_t seed;             /* Philox key; the reference is unseeded                        */
     int32_t seq_seed;          /* per-sequence stream id                                       */
     int32_t vocode;            /* 1: run the vocoder on completion; 0: tokens + latents only   */
+    int32_t priority;          /* admission order: lower first (the engine passes the chunk index,
+                                  so every request's first chunk is decoded before any second chunk) */
+    int32_t reserved;
 } xtts_sampling;
 
 typedef struct xtts_result {

@@ -31,7 +31,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_struct_layouts_match_header():
     # sizes implied by the header (all 4-byte fields except the 8-byte ones noted there)
-    assert ctypes.sizeof(native.XttsSampling) == 40
+    assert ctypes.sizeof(native.XttsSampling) == 48
     assert ctypes.sizeof(native.XttsResult) == 48
     assert ctypes.sizeof(native.XttsStats) == 9 * 8
     assert ctypes.sizeof(native.XttsConfig) == 4 * (4 + 12 + 3 + 8 + 1 + 8 + 1 + 4 + 6 + 8 + 2)

@@ -17,3 +17,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm
     python tools/profile_kernels.py 160 12 8 > gpurun_out/prof_gemm.log 2>&1
 echo "gemm capture exit $?"
 timeout 300 python -m pytest tests -q -m gpu --durations=12 -k "full" --no-header > gpurun_out/full_durations.log 2>&1; tail -n 20 gpurun_out/full_durations.log
+echo "=== cfg3 streaming bench"
+timeout 600 python tools/bench_stream.py 256 256 > gpurun_out/bench_stream.json 2> gpurun_out/bench_stream.err; echo "exit $?"; tail -n 3 gpurun_out/bench_stream.err; cat gpurun_out/bench_stream.json
+timeout 300 python -m pytest tests/test_gpu_gpt.py tests/test_gpu_api.py -q -m gpu -k "small or api or speech or streaming or prepared" --no-header -x > gpurun_out/t_small_after_priority.log 2>&1; tail -n 3 gpurun_out/t_small_after_priority.log
