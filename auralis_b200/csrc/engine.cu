@@ -141,6 +141,9 @@ private:
     int prefill_rows_cap;
     bool bf16;
     cudaStream_t st = nullptr;
+    static constexpr int kMaxMicro = 4;
+    cudaStream_t st_mb[kMaxMicro] = {nullptr, nullptr, nullptr, nullptr};   // [0] == st; decode micro-batch branches
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxMicro] = {nullptr, nullptr, nullptr, nullptr};
 
     // ---- weights
     std::map<std::string, HostTensor> raw;
@@ -215,6 +218,8 @@ private:
     bool use_splitk = true;       // option "splitk"
     bool use_pdl = true;          // option "pdl" (programmatic dependent launch along the decode chain)
     bool use_graphs = true;       // option "cuda_graphs"
+    int n_micro = 2;              // option "microbatches": decode rows are split into this many concurrent branches
+    int micro_min_rows = 48;      // option "microbatch_min_rows": below this many active rows the step stays single-branch
     int eager_steps_done = 0;
     std::map<int, cudaGraphExec_t> decode_graphs;
     std::map<int, unsigned long long> graph_kernels;
@@ -246,7 +251,9 @@ private:
     void finish_speaker(int slot);
     void gemm(const void* A, const Linear& lin, const float* resid, void* out, int M, int flags, bool pdl = false);
     void layers_forward(int M, bool prefill, int nseq, int max_nq);
-    void head_and_sample(int M, const int* row_index, const int* slots_dev, const int* lat_pos, int advance_ctx, bool do_sample);
+    void head_and_sample(int M, const int* row_index, const int* slots_dev, const int* lat_pos, int advance_ctx, bool do_sample,
+                         bool pdl_first = true);
+    void decode_layers_rows(int r0, int Mi, cudaStream_t s, bool pdl_first, double ctx_sum);
     void init_slot(Sequence& s, const int32_t* forced, int n_forced);
     void release_slot(Sequence& s);
     int build_prefill(const std::vector<Sequence*>& seqs, const std::vector<std::vector<int32_t>>& audio,
@@ -299,6 +306,10 @@ Engine::Engine(const xtts_config& c) : cfg(c) {
     bf16 = c.precision == XTTS_PRECISION_BF16;
     if (bf16) { std::string err; if (!gemm_tc_init(&err)) throw std::runtime_error(err); }
     CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    st_mb[0] = st;
+    for (int i = 1; i < kMaxMicro; ++i) CUDA_CHECK(cudaStreamCreateWithFlags(&st_mb[i], cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    for (int i = 1; i < kMaxMicro; ++i) CUDA_CHECK(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
 
     // speakers
     spk_cond.alloc((size_t)S * c.n_cond_latents * H);
@@ -388,6 +399,8 @@ Engine::~Engine() {
     for (auto& pr : dev_pool) cudaFree(pr.first);
     for (auto& kv : done_map) if (kv.second->wav_host) cudaFreeHost(kv.second->wav_host);
     if (h_finished) cudaFreeHost(h_finished);
+    for (int i = 1; i < kMaxMicro; ++i) { if (st_mb[i]) cudaStreamDestroy(st_mb[i]); if (ev_join[i]) cudaEventDestroy(ev_join[i]); }
+    if (ev_fork) cudaEventDestroy(ev_fork);
     if (st) cudaStreamDestroy(st);
 }
 
@@ -733,10 +746,12 @@ void Engine::layers_forward(int M, bool prefill, int nseq, int max_nq) {
 }
 
 // rows row_index[0..M) of X -> Y -> logits (wLOG[i]) ; latents captured ; optionally sample
-void Engine::head_and_sample(int M, const int* row_index, const int* slots_dev, const int* lat_pos, int advance_ctx, bool do_sample) {
+void Engine::head_and_sample(int M, const int* row_index, const int* slots_dev, const int* lat_pos, int advance_ctx, bool do_sample,
+                             bool pdl_first) {
     const bool pdl = advance_ctx && use_pdl;         // decode step only
-    if (bf16) launch_head_norms<__nv_bfloat16>(wX.p, row_index, lnfw.p, lnfb.p, fnw.p, fnb.p, wY16.p, d_latents.p, slots_dev, lat_pos, d_n_gen.p, CAP, M, H, cfg.ln_eps, st, pdl);
-    else launch_head_norms<float>(wX.p, row_index, lnfw.p, lnfb.p, fnw.p, fnb.p, wY32.p, d_latents.p, slots_dev, lat_pos, d_n_gen.p, CAP, M, H, cfg.ln_eps, st, pdl);
+    const bool pdl0 = pdl && pdl_first;              // (the first kernel after a stream join takes a full dependency)
+    if (bf16) launch_head_norms<__nv_bfloat16>(wX.p, row_index, lnfw.p, lnfb.p, fnw.p, fnb.p, wY16.p, d_latents.p, slots_dev, lat_pos, d_n_gen.p, CAP, M, H, cfg.ln_eps, st, pdl0);
+    else launch_head_norms<float>(wX.p, row_index, lnfw.p, lnfb.p, fnw.p, fnb.p, wY32.p, d_latents.p, slots_dev, lat_pos, d_n_gen.p, CAP, M, H, cfg.ln_eps, st, pdl0);
     gemm(bf16 ? (void*)wY16.p : (void*)wY32.p, mel_head, nullptr, wLOG.p, M, 0, pdl);
     if (do_sample) launch_sample(wLOG.p, Vpad, slots_dev, M, V, sample_state(), advance_ctx, st, pdl);
 }
@@ -833,13 +848,60 @@ void Engine::prefill(const std::vector<Sequence*>& seqs) {
     for (auto* s : seqs) s->t_first = t;
 }
 
+// Fast-mode decode layers for rows [r0, r0 + Mi) of the step on stream `s`.  Every work buffer is row-major and the
+// KV cache is per slot, so disjoint row ranges are independent: decode_step runs several of these as concurrent
+// branches (micro-batches), which lets one branch's HBM-bound attention overlap another's latency-bound GEMM chain.
+void Engine::decode_layers_rows(int r0, int Mi, cudaStream_t s, bool pdl_first, double ctx_sum) {
+    float* X = wX.p + (size_t)r0 * H;
+    __nv_bfloat16* Xn = wXn16.p + (size_t)r0 * H;
+    float* QKV = wQKV.p + (size_t)r0 * 3 * H;
+    __nv_bfloat16* ATT = wATT16.p + (size_t)r0 * H;
+    __nv_bfloat16* FFb = wFF16.p + (size_t)r0 * FF;
+    float* PART = wPART.p + (size_t)r0 * 8 * H;          // [splits <= 8][Mi][H] inside this branch's own region
+    const int* act = d_active.p + r0;
+    const bool pdl = use_pdl;
+    launch_layernorm<__nv_bfloat16>(X, layers[0]->ln1w.p, layers[0]->ln1b.p, Xn, Mi, H, cfg.ln_eps, s, pdl && pdl_first);
+    for (int l = 0; l < L; ++l) {
+        Layer& ly = *layers[l];
+        launch_gemm_bf16_tc(Xn, ly.qkv.w16.p, ly.qkv.b.p, nullptr, QKV, Mi, ly.qkv.N, ly.qkv.K, 0, s, pdl);
+        launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(QKV, act, Mi, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p,
+                                                         ATT, NH, s, ctx_sum, pdl);
+        launch_gemm_bf16_tc_splitk(ATT, ly.o.w16.p, PART, Mi, H, H, 4, s, pdl);
+        launch_residual_reduce_layernorm<__nv_bfloat16>(X, PART, 4, ly.o.b.p, ly.ln2w.p, ly.ln2b.p, Xn, Mi, H, cfg.ln_eps, s, pdl);
+        launch_gemm_bf16_tc(Xn, ly.fc.w16.p, ly.fc.b.p, nullptr, FFb, Mi, ly.fc.N, ly.fc.K, GEMM_GELU | GEMM_OUT_BF16, s, pdl);
+        launch_gemm_bf16_tc_splitk(FFb, ly.proj.w16.p, PART, Mi, H, FF, 8, s, pdl);
+        const bool last = (l + 1 == L);
+        launch_residual_reduce_layernorm<__nv_bfloat16>(X, PART, 8, ly.proj.b.p, last ? nullptr : layers[l + 1]->ln1w.p,
+                                                        last ? nullptr : layers[l + 1]->ln1b.p, last ? nullptr : Xn, Mi, H,
+                                                        cfg.ln_eps, s, pdl);
+    }
+}
+
 void Engine::decode_step(const std::vector<int>& active) {
     const int M = (int)active.size();
     d_active.upload(active.data(), M, st);
+    const bool fast = bf16 && use_splitk && M <= NSLOT && (H / 64) % 4 == 0 && (FF / 64) % 8 == 0;
+    const int nmb = (fast && n_micro > 1 && M >= micro_min_rows) ? std::min(n_micro, (int)kMaxMicro) : 1;
     auto enqueue = [&] {
         launch_build_decode_rows(d_active.p, M, d_last_tok.p, d_n_gen.p, tables(), wX.p, st, use_pdl);
-        layers_forward(M, false, 0, 0);
-        head_and_sample(M, nullptr, d_active.p, nullptr, 1, true);
+        if (nmb > 1) {
+            // fork: every branch starts after the row build; join: head + sampler run once over all rows
+            CUDA_CHECK(cudaEventRecord(ev_fork, st));
+            for (int i = 1; i < nmb; ++i) CUDA_CHECK(cudaStreamWaitEvent(st_mb[i], ev_fork, 0));
+            for (int i = 0, r0 = 0; i < nmb; ++i) {
+                const int Mi = M / nmb + (i < M % nmb ? 1 : 0);
+                decode_layers_rows(r0, Mi, st_mb[i], i == 0, decode_ctx_sum * (double)Mi / (double)M);
+                r0 += Mi;
+            }
+            for (int i = 1; i < nmb; ++i) {
+                CUDA_CHECK(cudaEventRecord(ev_join[i], st_mb[i]));
+                CUDA_CHECK(cudaStreamWaitEvent(st, ev_join[i], 0));
+            }
+            head_and_sample(M, nullptr, d_active.p, nullptr, 1, true, false);
+        } else {
+            layers_forward(M, false, 0, 0);
+            head_and_sample(M, nullptr, d_active.p, nullptr, 1, true);
+        }
     };
     // The decode step is ~250 small launches whose arguments depend only on M (slot lists, positions and
     // lengths live in device memory), so it is captured once per batch size into a CUDA graph and replayed.
@@ -1248,6 +1310,11 @@ void Engine::set_option(const std::string& k, int64_t v) {
     else if (k == "cuda_graphs") use_graphs = v != 0;
     else if (k == "pdl") { use_pdl = v != 0; for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second); decode_graphs.clear(); }
     else if (k == "splitk") { use_splitk = v != 0; for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second); decode_graphs.clear(); }
+    else if (k == "microbatches" || k == "microbatch_min_rows") {
+        if (k == "microbatches") n_micro = std::max<int>(1, std::min<int64_t>(v, kMaxMicro)); else micro_min_rows = (int)std::max<int64_t>(2, v);
+        for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second);
+        decode_graphs.clear();
+    }
     else if (k == "profile") { CUDA_CHECK(cudaSetDevice(cfg.device)); CUDA_CHECK(cudaStreamSynchronize(st)); g_prof.reset(); g_prof.enabled = v != 0; }
     else if (k == "reset_stats") {
         st_decode_steps = st_prefill_rows = st_tokens = st_samples = 0; st_gpt_ms = st_voc_ms = st_cond_ms = 0;

@@ -472,7 +472,118 @@ sample_kernel(const float* __restrict__ logits, int ld, const int* __restrict__ 
     }
     __syncthreads();
     int chosen = 0;
-    if (!greedy) {
+    const int tk_fast = S.top_k[slot];
+    bool fast_done = false;
+    if (!greedy && tk_fast > 0 && tk_fast <= 64 && tk_fast < V) {
+        // ---- fast path (the usual top_k = 50): radix-select the k-th largest logit, compact the <= 128 survivors,
+        //      sort just those, then top-p / softmax / Exp(1) race on the short list.  Same kept set and same
+        //      arithmetic as the full-sort path below, which remains the fallback (top_k off, > 64, or > 128 ties).
+        __shared__ unsigned hist[256];
+        __shared__ unsigned sel_prefix, sel_k, ncand;
+        __shared__ float cv[128];
+        __shared__ short ci[128];
+        __shared__ float cum[128];
+        auto fkey = [](float x) { unsigned b = __float_as_uint(x); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); };
+        if (tid == 0) { sel_prefix = 0u; sel_k = (unsigned)tk_fast; ncand = 0u; }
+        for (int pass = 3; pass >= 0; --pass) {
+            hist[tid] = 0u;
+            __syncthreads();
+            const unsigned pfx = sel_prefix;
+            const unsigned himask = (pass == 3) ? 0u : (0xFFFFFFFFu << ((pass + 1) * 8));
+            for (int v = tid; v < V; v += 256) {
+                const unsigned k = fkey(zs[v]);
+                if ((k & himask) == pfx) atomicAdd(&hist[(k >> (pass * 8)) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned need = sel_k, d = 255;
+                for (;; --d) {                                   // from the top digit down: where does the k-th largest live?
+                    if (hist[d] >= need) break;
+                    need -= hist[d];
+                    if (d == 0) break;
+                }
+                sel_k = need;
+                sel_prefix = pfx | (d << (pass * 8));
+            }
+            __syncthreads();
+        }
+        const unsigned kth_key = sel_prefix;
+        for (int v = tid; v < V; v += 256) {
+            if (fkey(zs[v]) >= kth_key) {
+                const unsigned pos = atomicAdd(&ncand, 1u);
+                if (pos < 128u) { cv[pos] = zs[v]; ci[pos] = (short)v; }
+            }
+        }
+        __syncthreads();
+        const int nc = (int)ncand;
+        if (nc <= 128) {
+            if (tid < 128 && tid >= nc) { cv[tid] = -INFINITY; ci[tid] = (short)(SV + tid); }    // pads sort to the front
+            __syncthreads();
+            for (int k = 2; k <= 128; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    if (tid < 128) {
+                        const int ixj = tid ^ j;
+                        if (ixj > tid) {
+                            KeyIdx a{cv[tid], ci[tid]}, b{cv[ixj], ci[ixj]};
+                            const bool up = ((tid & k) == 0);
+                            const bool sw = up ? key_less(b, a) : key_less(a, b);
+                            if (sw) { cv[tid] = b.v; ci[tid] = (short)b.i; cv[ixj] = a.v; ci[ixj] = (short)a.i; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            const float mx = cv[127];
+            const float tp = S.top_p[slot];
+            if (tid == 0) {                                      // <= 128 entries: a serial ascending scan is the cheapest
+                float run = 0.f;
+                for (int i = 0; i < 128; ++i) { run += (cv[i] == -INFINITY) ? 0.f : expf(cv[i] - mx); cum[i] = run; }
+            }
+            __syncthreads();
+            const float total_k = cum[127];
+            if (tp < 1.0f && tid < 127) {
+                if (cum[tid] * (1.0f / total_k) <= 1.0f - tp) cv[tid] = -INFINITY;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float run = 0.f;
+                for (int i = 0; i < 128; ++i) run += (cv[i] == -INFINITY) ? 0.f : expf(cv[i] - mx);
+                cum[0] = run;                                    // softmax denominator over the kept set
+            }
+            __syncthreads();
+            const float total = cum[0];
+            const unsigned long long seed = S.seed[slot];
+            const uint32_t k0 = (uint32_t)(seed & 0xffffffffull), k1 = (uint32_t)(seed >> 32);
+            float best = -1.f; int besti = 0x7fffffff;
+            if (tid < 128 && cv[tid] != -INFINITY) {
+                const int v = ci[tid];
+                uint32_t r[4];
+                philox4x32_10((uint32_t)(v >> 2), (uint32_t)n, (uint32_t)S.seq_seed[slot], 0u, k0, k1, r);
+                const float p = expf(cv[tid] - mx) / total;
+                const float uu = ((float)(r[v & 3] >> 9) + 0.5f) * (1.0f / 8388608.0f);
+                best = p / (-logf(uu)); besti = v;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            }
+            if ((tid & 31) == 0) { red[tid >> 5] = best; redi[tid >> 5] = besti; }
+            __syncthreads();
+            if (tid < 32) {
+                best = (tid < 8) ? red[tid] : -2.f;
+                besti = (tid < 8) ? redi[tid] : 0x7fffffff;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+                    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+                }
+                chosen = besti;
+            }
+            fast_done = true;
+        }
+        __syncthreads();
+    }
+    if (!greedy && !fast_done) {
         // ---- ascending bitonic sort of (value, index); the SV-V pads (-inf, idx>=V) go to the front
         for (int v = tid; v < SV; v += 256) { sv[v] = zs[v]; si[v] = (short)v; }
         __syncthreads();
@@ -576,7 +687,7 @@ sample_kernel(const float* __restrict__ logits, int ld, const int* __restrict__ 
             }
             chosen = besti;
         }
-    } else {
+    } else if (greedy) {
         float best = -INFINITY; int besti = 0x7fffffff;
         for (int v = tid; v < V; v += 256) {
             const float x = zs[v];

@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--requests", type=int, default=32, help="requests per GPU")
     ap.add_argument("--chars", type=int, default=1000)
     ap.add_argument("--max-tokens", type=int, default=605)
+    ap.add_argument("--microbatches", type=int, default=2, help="concurrent decode branches per step (engine option)")
     ap.add_argument("--small", action="store_true", help="tiny geometry (plumbing check only; not a valid bench number)")
     args = ap.parse_args()
 
@@ -280,6 +281,7 @@ def main():
     # ---- device-resident arm
     log(f"engine up: {n_chunks} chunks/GPU, {max_tok} tokens/chunk, precision {args.precision}")
     ne.set_option("d2h_wav", 0)
+    ne.set_option("microbatches", args.microbatches)
     eng.park_poller(True)                 # the device arm drives the native completion queue directly
     sampler = ClockSampler(local) if rank == 0 else None
     for i in range(args.warmup):
@@ -298,10 +300,14 @@ def main():
         f"{st.decode_steps} decode steps, {st.kernel_launches} kernels")
     # ---- kernel-family profile: one more identical step with CUDA events around every launch (eager launches; the
     # timed steps replay the decode step as a CUDA graph, which event pairs cannot bracket kernel by kernel)
+    # The profile step also runs the decode rows as ONE branch: concurrent micro-batch branches overlap kernels of
+    # different families, which would smear each family's own duration.
+    ne.set_option("microbatches", 1)
     ne.set_option("profile", 1)
     device_step(args.warmup + args.steps)
     prof = ne.kernel_profile()
     ne.set_option("profile", 0)
+    ne.set_option("microbatches", args.microbatches)
     eng.park_poller(False)
     log("profile step done")
 
@@ -375,7 +381,8 @@ def main():
                    "vocoder_compute": "fp16 tcgen05 implicit-GEMM convs (fp32 accumulate, fp32 residual stream)" if args.precision == "bf16" else "fp32",
                    "l2": "no explicit flush: per-step working set (0.76 GB weights + >5 GB KV + 0.4 GB vocoder activations) >> 126 MB L2",
                    "timing": "host perf_counter bracketed by barrier + cuda synchronize (device idle on both sides); max over ranks",
-                   "roofline_timing": "CUDA events around every launch on the engine stream, in one extra identical step right after the timed ones (eager launches)",
+                   "decode_microbatches": args.microbatches,
+                   "roofline_timing": "CUDA events around every launch on the engine stream, in one extra identical step right after the timed ones (eager launches, single decode branch so families do not overlap)",
                    "e2e_speakers": "4 reference wavs conditioned on the GPU before the timed region (per-speaker cache, as prepare_for_streaming_generation)"},
         "gpt_tokens_per_s": tokens_dev / dt_dev, "rtf": 1.0 / value,
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

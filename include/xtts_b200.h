@@ -123,7 +123,12 @@ int xtts_submit(xtts_engine* e, uint64_t seq_id, const int32_t* text_ids, int32_
 int xtts_poll(xtts_engine* e, xtts_result* out, int32_t timeout_ms);
 /* copies out and releases a finished chunk; any of tokens / wav / latents may be NULL */
 int xtts_fetch(xtts_engine* e, uint64_t seq_id, int32_t* tokens, float* wav, float* latents);
-/* bench knob: 0 = leave waveforms in HBM (kernel-only timing), 1 = D2H into pinned memory (default) */
+/* engine knobs (key, value):
+ *   "d2h_wav"             0 = leave waveforms in HBM (kernel-only timing), 1 = D2H into pinned memory (default)
+ *   "cuda_graphs" / "pdl" / "splitk" / "tc_vocoder"   0/1, fast-mode execution features (all default 1)
+ *   "microbatches"        1..4 concurrent branches the decode step's rows are split into (default 2)
+ *   "microbatch_min_rows" steps with fewer active rows stay single-branch (default 48)
+ *   "profile"             1 = CUDA events around every launch (xtts_get_kernel_profile), "reset_stats" = zero the counters */
 int xtts_set_option(xtts_engine* e, const char* key, int64_t value);
 int xtts_get_stats(xtts_engine* e, xtts_stats* out);
 int xtts_sync(xtts_engine* e);   /* waits until no submitted work is pending */

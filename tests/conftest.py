@@ -15,6 +15,11 @@ from auralis_b200.weights import synth_state           # noqa: E402
 SEED = 1234
 
 
+# The CPU oracle is small-tensor torch work: on a many-core GPU host the default (one thread per core) spends
+# its time in thread wake-ups, so the checker is pinned to a modest pool.
+torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
     config.addinivalue_line("markers", "slow: long-running")
@@ -41,7 +46,6 @@ def state_small(dims_small):
 
 @pytest.fixture(scope="session")
 def state_full(dims_full):
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
     return synth_state(dims_full, SEED)
 
 

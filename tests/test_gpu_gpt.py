@@ -150,6 +150,26 @@ def test_e2e_greedy_full_size(engine_full, dims_full, state_full, speakers_full)
         assert np.abs(wav - ewav).max() < 1e-3, np.abs(wav - ewav).max()
 
 
+@pytest.mark.parametrize("top_k", [50, 0])
+def test_sampler_full_vocab(engine_full, dims_full, top_k):
+    """V = 1026 at the reference's default sampling (top_k 50 -> radix-select path; 0 -> full 2048-wide sort)."""
+    V = dims_full.gpt.n_audio_tokens
+    rng = np.random.RandomState(11)
+    agree = total = 0
+    for step in range(4):
+        logits = (rng.randn(4, V) * 3.0).astype(np.float32)
+        seen = (rng.rand(4, V) < 0.05).astype(np.uint8)
+        sp = Sampling(temperature=0.75, top_p=0.85, top_k=top_k, repetition_penalty=5.0, seed=99 + step, seq_seed=3,
+                      stop_token=dims_full.gpt.stop_audio_token)
+        got = engine_full.debug_sample(logits, seen, sp, step=step)
+        osp = O.SamplingParams(temperature=sp.temperature, top_p=sp.top_p, top_k=sp.top_k,
+                               repetition_penalty=sp.repetition_penalty, seed=sp.seed)
+        exp = np.array([O.sample_token(torch.from_numpy(logits[b].copy()), set(np.nonzero(seen[b])[0].tolist()),
+                                       osp, sp.seq_seed + b, step) for b in range(4)])
+        agree += int((got == exp).sum()); total += got.size
+    assert agree >= total - 1, (agree, total)
+
+
 # ------------------------------------------------------------------------------------------------
 # bf16 / tcgen05 fast mode: same graph, looser tolerance (bf16 operands, fp32 accumulate)
 # ------------------------------------------------------------------------------------------------
@@ -218,3 +238,28 @@ def test_bf16_full_size_decode_paths(engine_full_bf16, dims_full, state_full, sp
     print("split-K+graphs vs plain bf16 token agreement", agree, "/ 20")
     first = next((k for k in range(20) if res2[7][1][k] != res[0][1][k]), 20)
     assert first >= 5 or _margin_report(lg.numpy(), res2[7][1][: first + 1], toks[: first + 1])[-1][3] < 0.15
+
+
+def test_bf16_decode_microbatch_branches_match_single_branch(engine_full_bf16, dims_full):
+    """The decode step may run its rows as concurrent branches on forked streams (engine option "microbatches").
+    Rows are independent, so tokens and waveforms must not depend on how the step was split."""
+    g = dims_full.gpt
+    jobs = []
+    for i in range(4):
+        sp = Sampling(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, max_tokens=14, seed=77, seq_seed=i,
+                      stop_token=g.stop_audio_token)
+        jobs.append((i, text_ids(dims_full, 9 + 3 * i, 40 + i), i % 3, sp))
+    out = {}
+    try:
+        engine_full_bf16.set_option("microbatch_min_rows", 2)
+        for nmb in (1, 2, 3):
+            engine_full_bf16.set_option("microbatches", nmb)
+            res = engine_full_bf16.run_batch(jobs, timeout_s=120)
+            out[nmb] = {sid: (list(toks), wav) for sid, (_, toks, wav, _) in res.items()}
+    finally:
+        engine_full_bf16.set_option("microbatches", 2)
+        engine_full_bf16.set_option("microbatch_min_rows", 48)
+    for nmb in (2, 3):
+        for sid in out[1]:
+            assert out[nmb][sid][0] == out[1][sid][0], (nmb, sid)
+            np.testing.assert_allclose(out[nmb][sid][1], out[1][sid][1], rtol=0, atol=1e-6)

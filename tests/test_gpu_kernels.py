@@ -88,15 +88,19 @@ def test_sampler_greedy_with_penalty(engine_small, dims_small):
     np.testing.assert_array_equal(got, _oracle_tokens(logits, seen, sp, 4))
 
 
-def test_sampler_topk_topp_seeded(engine_small, dims_small):
-    """Same Philox stream, same kept set -> same token (a few near-ties may flip on exp/log ulps)."""
+@pytest.mark.parametrize("top_k,quantised", [(50, False), (0, False), (100, False), (50, True)])
+def test_sampler_topk_topp_seeded(engine_small, dims_small, top_k, quantised):
+    """Same Philox stream, same kept set -> same token (a few near-ties may flip on exp/log ulps).
+    top_k=50 takes the radix-select fast path; 0 / 100 and the heavily tied (quantised) logits take the full sort."""
     V = dims_small.gpt.n_audio_tokens
     rng = np.random.RandomState(5)
     agree = total = 0
     for step in range(6):
         logits = (rng.randn(8, V) * 2.0).astype(np.float32)
+        if quantised:
+            logits = np.round(logits)                # many exact ties at the k-th value
         seen = (rng.rand(8, V) < 0.1).astype(np.uint8)
-        sp = Sampling(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, seed=1234 + step, seq_seed=7,
+        sp = Sampling(temperature=0.75, top_p=0.85, top_k=top_k, repetition_penalty=5.0, seed=1234 + step, seq_seed=7,
                       stop_token=dims_small.gpt.stop_audio_token)
         got = engine_small.debug_sample(logits, seen, sp, step=step)
         exp = _oracle_tokens(logits, seen, sp, step)

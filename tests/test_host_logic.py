@@ -141,3 +141,20 @@ def test_split_requests_and_prepared_speaker():
     fn = tts.loop.run_until_complete(tts.prepare_for_streaming_generation(r))
     r2 = TTSRequest(text="b" * 20, speaker_files=["s.wav"], language="en", context_partial_function=fn)
     assert tts.generate_speech(r2).array.shape == (8,)
+
+
+def test_tokenizer_with_real_vocab_file(tmp_path):
+    """the HF-`tokenizers` path (what XTTSTokenizerFast wraps, tokenizer.py:742-942): [lang] prefix, [SPACE] for blanks,
+    [START]/[STOP] ids come from the vocab."""
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    vocab = {"[STOP]": 0, "[UNK]": 1, "[SPACE]": 2, "[START]": 3, "[en]": 4, "h": 5, "e": 6, "l": 7, "o": 8, "w": 9, "r": 10, "d": 11}
+    tok = Tokenizer(models.BPE(vocab=vocab, merges=[], unk_token="[UNK]"))
+    tok.pre_tokenizer = pre_tokenizers.WhitespaceSplit()
+    tok.add_special_tokens(["[STOP]", "[UNK]", "[SPACE]", "[START]", "[en]"])     # matched whole, as in the real vocab
+    f = tmp_path / "tokenizer.json"
+    tok.save(str(f))
+    t = XTTSTokenizer(6681, 402, str(f))
+    assert not t.synthetic and (t.bos_token_id, t.eos_token_id) == (3, 0)
+    ids = t.encode_chunk("Hello World", "en")
+    assert ids[0] == 4 and 2 in ids and ids.count(7) == 3          # [en] h e l l o [SPACE] w o r l d
+    assert t.batch_encode_with_split("hello world", "en") == [ids]

@@ -28,11 +28,14 @@ def run(label, **opts):
         t0 = time.time(); eng.run_batch(jobs(nt), timeout_s=600, want_wav=False); t.append(time.time() - t0)
     st = eng.stats()
     print(f"{label:34s} batch {NB}: {1e3 * (t[1] - t[0]) / (NT - NT // 2):6.3f} ms/decode-step  (runs {t[0]*1e3:.0f} / {t[1]*1e3:.0f} ms; engine gpt_ms {st.gpt_ms:.0f})", flush=True)
-run("graphs + split-K", cuda_graphs=1, splitk=1)
-run("eager  + split-K", cuda_graphs=0, splitk=1)
-run("graphs, no split-K", cuda_graphs=1, splitk=0)
-run("eager, no split-K", cuda_graphs=0, splitk=0)
-eng.set_option("cuda_graphs", 1); eng.set_option("splitk", 1)
+eng.set_option("microbatch_min_rows", 8)
+for nmb in (1, 2, 3, 4):
+    run(f"graphs + split-K, {nmb} branch(es)", cuda_graphs=1, splitk=1, microbatches=nmb)
+run("eager  + split-K, 1 branch", cuda_graphs=0, splitk=1, microbatches=1)
+run("eager  + split-K, 2 branches", cuda_graphs=0, splitk=1, microbatches=2)
+if os.environ.get("STEP_PROBE_NOSPLITK"):
+    run("graphs, no split-K", cuda_graphs=1, splitk=0, microbatches=1)
+eng.set_option("cuda_graphs", 1); eng.set_option("splitk", 1); eng.set_option("microbatches", 1)
 eng.set_option("profile", 1)
 eng.run_batch(jobs(NT // 2), timeout_s=600, want_wav=False)
 prof = eng.kernel_profile(); eng.set_option("profile", 0)
