@@ -12,7 +12,8 @@
 // weight tile.  The epilogue (lane = time step) can emit
 //   * out32: fp32 channel-major [C][L]  (store or accumulate)  — the residual stream / MRF sum
 //   * out16: lrelu(y, slope_out) as fp16 atoms                 — the next conv's operand, written once, read once.
-// Warp roles: warps 0-3 epilogue (TMEM lane quarter = warp), warp 4 bulk-copy producer, warp 5 MMA issuer.
+// Warp roles: 4*EG epilogue warps (TMEM lane quarter = warp % 4; EG = 1 or 2 warpgroups), then one bulk-copy producer
+// warp and one MMA-issuer warp.
 //
 // Replaces the cuDNN fp16-autocast Conv1d calls of HifiganGenerator.forward / ResBlock1.forward
 // (hifigan_decoder.py:76-91,241-259; the reference runs them in fp16 under torch.amp.autocast on GPU, App. B.8).
@@ -22,9 +23,11 @@
 #include "kernels.h"
 
 namespace xtts {
+int g_conv_epi_groups = 2;        // engine option "conv_epi_groups" (1 or 2 epilogue warpgroups per CTA)
 namespace {
 
-constexpr int kThreadsTC = 192;
+// warps [0, 4*EG) epilogue (EG warpgroups share a tile's accumulator chunks), warp 4*EG producer, warp 4*EG+1 MMA issuer
+constexpr int threads_tc(int eg) { return (4 * eg + 2) * 32; }
 constexpr int SA = 2, SB = 3;          // ring depths (activation chunks, weight tiles)
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -95,9 +98,10 @@ struct ConvTcParams {
     int tiles_t, tiles_n, batch;   // persistent-CTA tile space
 };
 
-template <int NACC>
-__global__ void __launch_bounds__(kThreadsTC, 1)
+template <int NACC, int EG>
+__global__ void __launch_bounds__(threads_tc(EG), 1)
 conv1d_tc_kernel(const ConvTcParams P) {
+    constexpr int kProducerWarp = 4 * EG, kMmaWarp = 4 * EG + 1;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
@@ -123,10 +127,10 @@ conv1d_tc_kernel(const ConvTcParams P) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < SA; ++i) { bar_init(&a_full[i], 1); bar_init(&a_empty[i], 1); }
         for (int i = 0; i < SB; ++i) { bar_init(&b_full[i], 1); bar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { bar_init(&tmem_full[i], 1); bar_init(&tmem_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { bar_init(&tmem_full[i], 1); bar_init(&tmem_empty[i], 128 * EG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_s)), "r"(tm_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -135,9 +139,10 @@ conv1d_tc_kernel(const ConvTcParams P) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp < 4) {
-        // ------------------------------------------------ epilogue: warp q owns TMEM lanes [32q, 32q+32) = time rows
-        const int q = warp;
+    if (warp < 4 * EG) {
+        // ------------------------------------------------ epilogue: warp q owns TMEM lanes [32q, 32q+32) = time rows;
+        // the EG warpgroups take alternate 32-column chunks of the tile (more loads/stores in flight per SM)
+        const int q = warp & 3, grp = warp >> 2;
         const int row_limit = P.up ? P.L + 1 : P.L;      // a transposed conv also consumes the zero row x[L]
         int lt = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
@@ -151,11 +156,12 @@ conv1d_tc_kernel(const ConvTcParams P) {
             const int ab = lt % nbuf;
             bar_wait(&tmem_full[ab], (uint32_t)((lt / nbuf) & 1), 4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int ncn = P.N / 32;
 #pragma unroll 1
-            for (int a = 0; a < NACC; ++a) {
+            for (int item = grp; item < NACC * ncn; item += EG) {
+                const int a = item / ncn, nc = item - a * ncn;
                 const int srow = T0 + a * 128 + q * 32 + lane;
-#pragma unroll 1
-                for (int nc = 0; nc < P.N / 32; ++nc) {
+                {
                     uint32_t r[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols + a * P.N + nc * 32);
                     asm volatile(
@@ -215,7 +221,7 @@ conv1d_tc_kernel(const ConvTcParams P) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             bar_arrive(&tmem_empty[ab]);
         }
-    } else if (warp == 4) {
+    } else if (warp == kProducerWarp) {
         // ------------------------------------------------ producer: activation planes + weight tiles, all bulk copies
         if (lane == 0) {
             int ita = 0, itb = 0;
@@ -281,7 +287,7 @@ conv1d_tc_kernel(const ConvTcParams P) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tm_cols) : "memory");
     }
 }
@@ -334,6 +340,14 @@ void conv1d_tc_pack(const float* w, int Cin, int Cout, int K, const ConvTcPlan& 
 
 int atoms_lpad(int L) { return kAtomPadL + ceil_div(L + 1, 512) * 512 + kAtomPadR; }
 
+constexpr int kMaxDynTc = 227 * 1024 - 2048;      // opt-in limit minus the kernel's static shared memory
+template <int NACC, int EG>
+static void launch_inst(const ConvTcParams& P, dim3 grid, size_t smem, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(conv1d_tc_kernel<NACC, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynTc)); attr = true; }
+    conv1d_tc_kernel<NACC, EG><<<grid, threads_tc(EG), smem, st>>>(P);
+}
+
 static void launch_tc_common(ConvTcParams& P, const ConvTcPlan& pl, int rows_to_cover, int batch, double flops, double bytes,
                              cudaStream_t st) {
     const int tile = 128 * pl.nacc;
@@ -343,7 +357,7 @@ static void launch_tc_common(ConvTcParams& P, const ConvTcPlan& pl, int rows_to_
         throw CudaError("conv1d_tc: atom buffer pad too small");
     const size_t a_stage = (size_t)P.rows * 16 * (pl.CK / 8), b_stage = (size_t)pl.N * 16 * (pl.CK / 8);
     const size_t smem = ((SA * a_stage + 127) & ~(size_t)127) + SB * b_stage + 128;
-    constexpr int kMaxDyn = 227 * 1024 - 2048;      // opt-in limit minus this kernel's static shared memory
+    constexpr int kMaxDyn = kMaxDynTc;
     if (smem > (size_t)kMaxDyn) throw CudaError("conv1d_tc: shared memory budget exceeded");
     P.tiles_t = ceil_div(rows_to_cover, tile); P.tiles_n = pl.n_tiles; P.batch = batch;
     const int total_tiles = P.tiles_t * P.tiles_n * batch;
@@ -351,14 +365,9 @@ static void launch_tc_common(ConvTcParams& P, const ConvTcPlan& pl, int rows_to_
     if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
     dim3 grid(std::min(total_tiles, n_sm));          // one persistent CTA per SM
     ProfScope ps(KF_CONV1D_TC, st, flops, bytes);
-    static bool attr2 = false, attr4 = false;
-    if (pl.nacc == 2) {
-        if (!attr2) { CUDA_CHECK(cudaFuncSetAttribute(conv1d_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn)); attr2 = true; }
-        conv1d_tc_kernel<2><<<grid, kThreadsTC, smem, st>>>(P);
-    } else {
-        if (!attr4) { CUDA_CHECK(cudaFuncSetAttribute(conv1d_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn)); attr4 = true; }
-        conv1d_tc_kernel<4><<<grid, kThreadsTC, smem, st>>>(P);
-    }
+    const int eg = g_conv_epi_groups >= 2 ? 2 : 1;
+    if (pl.nacc == 2) { if (eg == 2) launch_inst<2, 2>(P, grid, smem, st); else launch_inst<2, 1>(P, grid, smem, st); }
+    else              { if (eg == 2) launch_inst<4, 2>(P, grid, smem, st); else launch_inst<4, 1>(P, grid, smem, st); }
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 

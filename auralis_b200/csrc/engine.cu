@@ -218,6 +218,7 @@ private:
     bool use_splitk = true;       // option "splitk"
     bool use_pdl = true;          // option "pdl" (programmatic dependent launch along the decode chain)
     bool use_graphs = true;       // option "cuda_graphs"
+    std::atomic<bool> hold_admission{false};   // option "hold_admission": queue submissions, admit nothing (batch submit)
     int n_micro = 2;              // option "microbatches": decode rows are split into this many concurrent branches
     int micro_min_rows = 48;      // option "microbatch_min_rows": below this many active rows the step stays single-branch
     int eager_steps_done = 0;
@@ -1185,7 +1186,9 @@ void Engine::loop() {
     while (true) {
         {
             std::unique_lock<std::mutex> q(q_mu);
-            cv_work.wait(q, [&] { return stop.load() || !pending.empty() || !waiting.empty() || !running.empty(); });
+            cv_work.wait(q, [&] {
+                return stop.load() || !pending.empty() || (!waiting.empty() && !hold_admission.load()) || !running.empty();
+            });
             if (stop.load()) break;
             while (!pending.empty()) {
                 // stable priority insert: lower `priority` (chunk index) first, FIFO among equals
@@ -1206,7 +1209,7 @@ void Engine::loop() {
             std::vector<Sequence*> fresh;
             std::vector<std::shared_ptr<Sequence>> fresh_sp;
             int rows = 0;
-            while (!waiting.empty() && !free_slots.empty()) {
+            while (!hold_admission.load() && !waiting.empty() && !free_slots.empty()) {
                 auto s = waiting.front();
                 const int p = cfg.n_cond_latents + (int)s->text_ids.size() + 1;
                 if (!fresh.empty() && rows + p > prefill_rows_cap) break;
@@ -1304,9 +1307,16 @@ void Engine::fetch(uint64_t id, int32_t* tokens, float* wav, float* latents) {
 }
 
 void Engine::set_option(const std::string& k, int64_t v) {
+    if (k == "hold_admission") {       // no GPU state involved: must not wait for a running step
+        hold_admission.store(v != 0);
+        { std::lock_guard<std::mutex> q(q_mu); }
+        cv_work.notify_all();
+        return;
+    }
     std::lock_guard<std::mutex> lk(mu);
     if (k == "d2h_wav") d2h_wav = v != 0;
     else if (k == "tc_vocoder") use_tc_vocoder = v != 0;
+    else if (k == "conv_epi_groups") g_conv_epi_groups = v >= 2 ? 2 : 1;
     else if (k == "cuda_graphs") use_graphs = v != 0;
     else if (k == "pdl") { use_pdl = v != 0; for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second); decode_graphs.clear(); }
     else if (k == "splitk") { use_splitk = v != 0; for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second); decode_graphs.clear(); }

@@ -290,9 +290,15 @@ class NativeEngine:
         """jobs: iterable of (seq_id, text_ids, speaker_slot, Sampling).  Returns {seq_id: (result, tokens, wav, lat)}."""
         import time
         n = 0
-        for sid, ids, spk, sp in jobs:
-            self.submit(sid, ids, spk, sp)
-            n += 1
+        # batch submit: the scheduler admits nothing until the whole batch is queued, so admission waves (and with
+        # them which chunks finish together and share a vocoder launch) do not depend on host timing
+        self.set_option("hold_admission", 1)
+        try:
+            for sid, ids, spk, sp in jobs:
+                self.submit(sid, ids, spk, sp)
+                n += 1
+        finally:
+            self.set_option("hold_admission", 0)
         out = {}
         t_end = time.time() + timeout_s
         while len(out) < n:

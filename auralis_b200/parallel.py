@@ -117,10 +117,11 @@ def gather_waveforms(local: Dict[int, np.ndarray], n_items: int, device: torch.d
 
 
 def run_sharded(items: Sequence, costs: Sequence[float], synth: Callable[[List[int]], Dict[int, np.ndarray]],
-                device: torch.device | None = None, group=None) -> List[np.ndarray]:
-    """Shard `items` by LPT, run `synth(indices)` on this rank's share, all-gather the audio."""
+                device: torch.device | None = None, group=None, dst: int | None = None) -> List[np.ndarray] | None:
+    """Shard `items` by LPT, run `synth(indices)` on this rank's share, all-gather the audio
+    (`dst`: only that rank materialises the gathered list on the host; the others return None)."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     mine = lpt_partition(costs, world)[rank]
     local = synth(mine) if mine else {}
-    return gather_waveforms(local, len(items), device, group)
+    return gather_waveforms(local, len(items), device, group, dst)
