@@ -219,6 +219,8 @@ private:
     bool use_pdl = true;          // option "pdl" (programmatic dependent launch along the decode chain)
     bool use_graphs = true;       // option "cuda_graphs"
     std::atomic<bool> hold_admission{false};   // option "hold_admission": queue submissions, admit nothing (batch submit)
+    bool use_chain = true;        // option "decode_chain": fused persistent per-layer GEMM/LayerNorm chain kernel
+    DBuf<unsigned> d_chain_sync;  // device-wide barrier words of the chain kernel
     int n_micro = 2;              // option "microbatches": decode rows are split into this many concurrent branches
     int micro_min_rows = 48;      // option "microbatch_min_rows": below this many active rows the step stays single-branch
     int eager_steps_done = 0;
@@ -255,6 +257,7 @@ private:
     void head_and_sample(int M, const int* row_index, const int* slots_dev, const int* lat_pos, int advance_ctx, bool do_sample,
                          bool pdl_first = true);
     void decode_layers_rows(int r0, int Mi, cudaStream_t s, bool pdl_first, double ctx_sum);
+    void decode_layers_chain(int M);
     void init_slot(Sequence& s, const int32_t* forced, int n_forced);
     void release_slot(Sequence& s);
     int build_prefill(const std::vector<Sequence*>& seqs, const std::vector<std::vector<int32_t>>& audio,
@@ -348,6 +351,7 @@ Engine::Engine(const xtts_config& c) : cfg(c) {
     const size_t Mmax = (size_t)std::max(prefill_rows_cap, NSLOT);
     wX.alloc(Mmax * H); wQKV.alloc(Mmax * 3 * H); wLOG.alloc((size_t)std::max(NSLOT, CAP + 1) * Vpad);
     if (bf16) wPART.alloc((size_t)8 * NSLOT * H);
+    d_chain_sync.alloc(2); d_chain_sync.zero(st);
     if (bf16) { wXn16.alloc(Mmax * H); wATT16.alloc(Mmax * H); wFF16.alloc(Mmax * FF); wY16.alloc((size_t)std::max(NSLOT, CAP + 1) * H); }
     else { wXn32.alloc(Mmax * H); wATT32.alloc(Mmax * H); wFF32.alloc(Mmax * FF); wY32.alloc((size_t)std::max(NSLOT, CAP + 1) * H); }
 
@@ -878,11 +882,34 @@ void Engine::decode_layers_rows(int r0, int Mi, cudaStream_t s, bool pdl_first, 
     }
 }
 
+// Fast-mode decode layers with the fused chain kernel: per layer one attention launch and one persistent launch that
+// runs out-proj, residual+LN2, fc+gelu, down-proj, residual+LN1(next) and the next layer's QKV projection.
+void Engine::decode_layers_chain(int M) {
+    const bool pdl = use_pdl;
+    launch_layernorm<__nv_bfloat16>(wX.p, layers[0]->ln1w.p, layers[0]->ln1b.p, wXn16.p, M, H, cfg.ln_eps, st, pdl);
+    launch_gemm_bf16_tc(wXn16.p, layers[0]->qkv.w16.p, layers[0]->qkv.b.p, nullptr, wQKV.p, M, layers[0]->qkv.N, layers[0]->qkv.K, 0, st, pdl);
+    for (int l = 0; l < L; ++l) {
+        Layer& ly = *layers[l];
+        Layer* nx = (l + 1 < L) ? layers[l + 1].get() : nullptr;
+        launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p,
+                                                         wATT16.p, NH, st, decode_ctx_sum, pdl);
+        DecodeChainArgs a{};
+        a.phases = DC_PROJ | DC_LN2 | DC_FC | DC_FC2 | DC_LN1 | (nx ? DC_QKV : 0);
+        a.M = M; a.H = H; a.FF = FF; a.eps = cfg.ln_eps;
+        a.ATT = wATT16.p; a.Wo = ly.o.w16.p; a.Wfc = ly.fc.w16.p; a.Wproj = ly.proj.w16.p; a.Wqkv = nx ? nx->qkv.w16.p : nullptr;
+        a.proj_bias = ly.o.b.p; a.ln2_w = ly.ln2w.p; a.ln2_b = ly.ln2b.p; a.fc_bias = ly.fc.b.p; a.fc2_bias = ly.proj.b.p;
+        a.ln1_w = nx ? nx->ln1w.p : nullptr; a.ln1_b = nx ? nx->ln1b.p : nullptr; a.qkv_bias = nx ? nx->qkv.b.p : nullptr;
+        a.X = wX.p; a.Xn = wXn16.p; a.FFb = wFF16.p; a.QKV = wQKV.p; a.PART = wPART.p; a.sync = d_chain_sync.p;
+        launch_decode_chain(a, st, pdl);
+    }
+}
+
 void Engine::decode_step(const std::vector<int>& active) {
     const int M = (int)active.size();
     d_active.upload(active.data(), M, st);
     const bool fast = bf16 && use_splitk && M <= NSLOT && (H / 64) % 4 == 0 && (FF / 64) % 8 == 0;
-    const int nmb = (fast && n_micro > 1 && M >= micro_min_rows) ? std::min(n_micro, (int)kMaxMicro) : 1;
+    const bool chain = fast && use_chain && decode_chain_supported(M, H, FF);
+    const int nmb = (fast && !chain && n_micro > 1 && M >= micro_min_rows) ? std::min(n_micro, (int)kMaxMicro) : 1;
     auto enqueue = [&] {
         launch_build_decode_rows(d_active.p, M, d_last_tok.p, d_n_gen.p, tables(), wX.p, st, use_pdl);
         if (nmb > 1) {
@@ -900,7 +927,7 @@ void Engine::decode_step(const std::vector<int>& active) {
             }
             head_and_sample(M, nullptr, d_active.p, nullptr, 1, true, false);
         } else {
-            layers_forward(M, false, 0, 0);
+            if (chain) decode_layers_chain(M); else layers_forward(M, false, 0, 0);
             head_and_sample(M, nullptr, d_active.p, nullptr, 1, true);
         }
     };
@@ -1320,6 +1347,7 @@ void Engine::set_option(const std::string& k, int64_t v) {
     else if (k == "cuda_graphs") use_graphs = v != 0;
     else if (k == "pdl") { use_pdl = v != 0; for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second); decode_graphs.clear(); }
     else if (k == "splitk") { use_splitk = v != 0; for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second); decode_graphs.clear(); }
+    else if (k == "decode_chain") { use_chain = v != 0; for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second); decode_graphs.clear(); }
     else if (k == "microbatches" || k == "microbatch_min_rows") {
         if (k == "microbatches") n_micro = std::max<int>(1, std::min<int64_t>(v, kMaxMicro)); else micro_min_rows = (int)std::max<int64_t>(2, v);
         for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second);

@@ -31,6 +31,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -280,6 +283,296 @@ void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 
+
+// =================================================================================================================
+// Fused decode "chain" kernel: everything between two attention calls of the decode step in ONE persistent launch
+//
+//   proj (split-K) -> residual + LayerNorm2 -> fc + gelu -> fc2 (split-K) -> residual + LayerNorm1(next) -> qkv(next)
+//
+// At decode shapes (M <= 256 rows) every one of those six launches is latency-bound (a 16-k-block main loop between a
+// launch, a TMEM/barrier prologue and an epilogue); here the CTAs stay resident, keep their barriers, smem ring and TMEM
+// accumulator, and separate the phases with a device-wide barrier (one atomic + one acquire-poll per CTA).
+// One CTA per SM, 192 threads: GEMM phases use the roles of gemm_bf16_tc_kernel (warp 0 TMA producer, warp 1 MMA issuer,
+// warps 2-5 epilogue); the reduce + LayerNorm phases use all 6 warps, one row per warp.
+// Data written by generic stores in one phase is read by TMA (async proxy) in the next: the barrier is followed by a
+// cross-proxy fence.  Co-residency: the grid is <= the SM count, one CTA per SM, and griddepcontrol.launch_dependents is
+// only issued after the last device-wide barrier, so no dependent grid can take an SM one of our CTAs still needs.
+// =================================================================================================================
+constexpr int CH_BN = 64, CH_STAGES = 6, CH_SPLITS = 4;
+enum { EPI_PARTIAL = 0, EPI_BIAS_F32 = 1, EPI_BIAS_GELU_BF16 = 2 };
+
+struct ChainParams {
+    int phases, M, H, FF, abox;
+    float eps;
+    const float* proj_bias; const float* ln2_w; const float* ln2_b;
+    const float* fc_bias;
+    const float* fc2_bias; const float* ln1_w; const float* ln1_b;     // LayerNorm1 of the NEXT layer (null: residual only)
+    const float* qkv_bias;                                              // next layer
+    float* X; __nv_bfloat16* Xn; __nv_bfloat16* FFb; float* QKV; float* PART;
+    unsigned* sync;                                                     // [0] arrival count, [1] generation
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// self-resetting device-wide barrier (all CTAs of the grid are resident: grid <= #SMs, 1 CTA/SM)
+__device__ __forceinline__ void chain_grid_sync(unsigned* sync) {
+    asm volatile("fence.proxy.async;" ::: "memory");          // generic writes of this phase -> later async-proxy (TMA) reads
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned gen = ld_acquire_u32(sync + 1);
+        __threadfence();
+        if (atomicAdd(sync, 1u) == gridDim.x - 1) {
+            sync[0] = 0u;
+            __threadfence();
+            atomicAdd(sync + 1, 1u);
+        } else {
+            const long long t0 = clock64();
+            while (ld_acquire_u32(sync + 1) == gen) {
+                if (clock64() - t0 > 4000000000LL) {
+                    printf("decode_chain: grid barrier watchdog (block %d)\n", blockIdx.x);
+                    __trap();
+                }
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+struct ChainSmem {
+    uint8_t* sA; uint8_t* sB;
+    uint64_t* full_bar; uint64_t* empty_bar; uint64_t* tmem_full; uint64_t* tmem_empty;
+    uint32_t tmem_base;
+};
+
+// one GEMM phase: out = epi(A[M,K] . W[N,K]^T); tiles (n-tile, m-tile, k-split) strided over the grid
+__device__ __forceinline__ void chain_gemm(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, int splits,
+                                           int epi, const float* __restrict__ bias, void* out, int abox, const ChainSmem& S,
+                                           int warp, int lane, int& it, int& lt) {
+    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = CH_BN * BK * 2;
+    const int tiles_n = N / CH_BN, mt = (M + BM - 1) / BM;
+    const int kb_per = (K / BK) / splits;
+    const int total = tiles_n * mt * splits;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int nt = tile % tiles_n, mi = (tile / tiles_n) % mt, z = tile / (tiles_n * mt);
+        const int n0 = nt * CH_BN, m0 = mi * BM, kb0 = z * kb_per;
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int kb = 0; kb < kb_per; ++kb, ++it) {
+                    const int s = it % CH_STAGES;
+                    mbar_wait(&S.empty_bar[s], (uint32_t)(((it / CH_STAGES) & 1) ^ 1), 11);
+                    mbar_expect_tx(&S.full_bar[s], (uint32_t)abox * BK * 2 + B_BYTES);
+                    tma_load_2d(S.sB + s * B_BYTES, tmB, &S.full_bar[s], (kb0 + kb) * BK, n0);
+                    tma_load_2d(S.sA + s * A_BYTES, tmA, &S.full_bar[s], (kb0 + kb) * BK, m0);
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                constexpr uint32_t idesc = make_idesc(CH_BN);
+                mbar_wait(S.tmem_empty, (uint32_t)((lt & 1) ^ 1), 16);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < kb_per; ++kb, ++it) {
+                    const int s = it % CH_STAGES;
+                    mbar_wait(&S.full_bar[s], (uint32_t)((it / CH_STAGES) & 1), 12);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_u32(S.sA + s * A_BYTES), b_addr = smem_u32(S.sB + s * B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16(S.tmem_base, make_sw128_desc(a_addr + k * UMMA_K * 2), make_sw128_desc(b_addr + k * UMMA_K * 2),
+                                  idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(&S.empty_bar[s]);
+                }
+                umma_commit(S.tmem_full);
+            }
+            ++lt;
+        } else {
+            const int q = warp & 3;
+            mbar_wait(S.tmem_full, (uint32_t)(lt & 1), 13);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+            for (int c = 0; c < CH_BN / 32; ++c) {
+                uint32_t r[32];
+                const uint32_t taddr = S.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int nb = n0 + c * 32;
+                if (row < M) {
+                    if (epi == EPI_BIAS_GELU_BF16) {
+                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)row * N + nb;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float v[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = gelu_new(__uint_as_float(r[8 * i + e]) + __ldg(bias + nb + 8 * i + e));
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+                            uint4 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            reinterpret_cast<uint4*>(op)[i] = pk;
+                        }
+                    } else {
+                        float* base = reinterpret_cast<float*>(out) + (epi == EPI_PARTIAL ? (size_t)z * M * N : (size_t)0);
+                        float4* op = reinterpret_cast<float4*>(base + (size_t)row * N + nb);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                            if (epi == EPI_BIAS_F32) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb) + i);
+                                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+                            }
+                            op[i] = v;
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(S.tmem_empty);
+            ++lt;
+        }
+    }
+}
+
+// X[r] += bias + sum_z PART[z][r] (fixed order: deterministic); optional LayerNorm -> bf16 Xn[r].  One row per warp.
+__device__ __forceinline__ void chain_reduce_ln(const ChainParams& P, const float* __restrict__ bias, const float* __restrict__ w,
+                                                const float* __restrict__ b, int warp, int lane) {
+    const int H = P.H, nj = H / 128;                 // H <= 1024: up to 8 float4 per lane
+    const size_t zs = (size_t)P.M * H;
+    for (int r = blockIdx.x * 6 + warp; r < P.M; r += gridDim.x * 6) {
+        float4 v[8];
+        float* x = P.X + (size_t)r * H;
+        const float* p = P.PART + (size_t)r * H;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < nj) {
+                const int c = j * 128 + lane * 4;
+                float4 acc = __ldcg(reinterpret_cast<const float4*>(x + c));
+                float4 pz[CH_SPLITS];
+#pragma unroll
+                for (int z = 0; z < CH_SPLITS; ++z) pz[z] = __ldcg(reinterpret_cast<const float4*>(p + (size_t)z * zs + c));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
+                acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
+#pragma unroll
+                for (int z = 0; z < CH_SPLITS; ++z) { acc.x += pz[z].x; acc.y += pz[z].y; acc.z += pz[z].z; acc.w += pz[z].w; }
+                v[j] = acc;
+                *reinterpret_cast<float4*>(x + c) = acc;
+            }
+        }
+        if (w == nullptr) continue;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < nj) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        const float mean = warp_sum(s) / (float)H;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < nj) {
+                const float d0 = v[j].x - mean, d1 = v[j].y - mean, d2 = v[j].z - mean, d3 = v[j].w - mean;
+                q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
+            }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + P.eps);
+        __nv_bfloat16* y = P.Xn + (size_t)r * H;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < nj) {
+                const int c = j * 128 + lane * 4;
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c)), b4 = __ldg(reinterpret_cast<const float4*>(b + c));
+                __nv_bfloat162 h0 = __floats2bfloat162_rn((v[j].x - mean) * rstd * w4.x + b4.x, (v[j].y - mean) * rstd * w4.y + b4.y);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn((v[j].z - mean) * rstd * w4.z + b4.z, (v[j].w - mean) * rstd * w4.w + b4.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(y + c) = pk;
+            }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+decode_chain_kernel(const __grid_constant__ CUtensorMap tmATT, const __grid_constant__ CUtensorMap tmWo,
+                    const __grid_constant__ CUtensorMap tmXn, const __grid_constant__ CUtensorMap tmWfc,
+                    const __grid_constant__ CUtensorMap tmFF, const __grid_constant__ CUtensorMap tmWproj,
+                    const __grid_constant__ CUtensorMap tmWqkv, const ChainParams P) {
+    constexpr uint32_t A_BYTES = BM * BK * 2;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[CH_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[CH_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar, tmem_empty_bar;
+    __shared__ uint32_t tmem_base_smem;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmATT) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmXn) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWfc) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmFF) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWproj) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWqkv) : "memory");
+        for (int s = 0; s < CH_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        mbar_init(&tmem_empty_bar, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)CH_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    ChainSmem S;
+    S.sA = smem; S.sB = smem + CH_STAGES * A_BYTES;
+    S.full_bar = full_bar; S.empty_bar = empty_bar; S.tmem_full = &tmem_full_bar; S.tmem_empty = &tmem_empty_bar;
+    S.tmem_base = tmem_base_smem;
+
+    pdl_wait();                                    // the attention output (and everything before it) is complete
+    int it = 0, lt = 0;
+    const int last = 31 - __clz(P.phases);         // index of the last enabled phase
+    auto boundary = [&](int bit) {                 // device-wide barrier after every phase but the last; dependents may
+        if ((1 << last) == bit) return;            // start launching once the final barrier is behind us
+        chain_grid_sync(P.sync);
+        if ((P.phases & ~(2 * bit - 1)) == (1 << last)) pdl_trigger();
+    };
+    if (P.phases == (1 << last)) pdl_trigger();    // single-phase launch: nothing to wait for
+    if (P.phases & DC_PROJ) {
+        chain_gemm(&tmATT, &tmWo, P.M, P.H, P.H, CH_SPLITS, EPI_PARTIAL, nullptr, P.PART, P.abox, S, warp, lane, it, lt);
+        boundary(DC_PROJ);
+    }
+    if (P.phases & DC_LN2) { chain_reduce_ln(P, P.proj_bias, P.ln2_w, P.ln2_b, warp, lane); boundary(DC_LN2); }
+    if (P.phases & DC_FC) {
+        chain_gemm(&tmXn, &tmWfc, P.M, P.FF, P.H, 1, EPI_BIAS_GELU_BF16, P.fc_bias, P.FFb, P.abox, S, warp, lane, it, lt);
+        boundary(DC_FC);
+    }
+    if (P.phases & DC_FC2) {
+        chain_gemm(&tmFF, &tmWproj, P.M, P.H, P.FF, CH_SPLITS, EPI_PARTIAL, nullptr, P.PART, P.abox, S, warp, lane, it, lt);
+        boundary(DC_FC2);
+    }
+    if (P.phases & DC_LN1) { chain_reduce_ln(P, P.fc2_bias, P.ln1_w, P.ln1_b, warp, lane); boundary(DC_LN1); }
+    if (P.phases & DC_QKV)
+        chain_gemm(&tmXn, &tmWqkv, P.M, 3 * P.H, P.H, 1, EPI_BIAS_F32, P.qkv_bias, P.QKV, P.abox, S, warp, lane, it, lt);
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base), "r"((uint32_t)CH_BN) : "memory");
+    }
+}
+
 }  // namespace
 
 bool gemm_tc_init(std::string* err) {
@@ -343,6 +636,52 @@ void launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, 
     if (bn == 128) launch_bn<128>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox, pdl);
     else if (bn == 64) launch_bn<64>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox, pdl);
     else launch_bn<32>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox, pdl);
+}
+
+
+bool decode_chain_supported(int M, int H, int FF) {
+    return M >= 1 && H % 128 == 0 && H <= 1024 && (H / BK) % CH_SPLITS == 0 && FF % CH_BN == 0 && (FF / BK) % CH_SPLITS == 0;
+}
+
+// one launch = the phases of `a.phases` (DC_* bits) for one layer boundary of the decode step
+void launch_decode_chain(const DecodeChainArgs& a, cudaStream_t st, bool pdl) {
+    if (a.M <= 0 || a.phases == 0) return;
+    if (!decode_chain_supported(a.M, a.H, a.FF)) throw CudaError("decode_chain: unsupported geometry");
+    if (!g_encode) { std::string err; if (!gemm_tc_init(&err)) throw CudaError(err); }
+    static int n_sm = 0;
+    static bool attr_set = false;
+    constexpr size_t smem = CH_STAGES * (BM * BK * 2 + CH_BN * BK * 2) + 1024;
+    if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(decode_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int abox = a_box_rows_for(a.M);
+    const int H = a.H, FF = a.FF;
+    CUtensorMap tATT, tWo, tXn, tWfc, tFF, tWproj, tWqkv;
+    encode_2d(&tATT, a.ATT, (uint64_t)a.M, (uint64_t)H, (uint32_t)abox);
+    encode_2d(&tXn, a.Xn, (uint64_t)a.M, (uint64_t)H, (uint32_t)abox);
+    encode_2d(&tFF, a.FFb, (uint64_t)a.M, (uint64_t)FF, (uint32_t)abox);
+    encode_2d(&tWo, a.Wo, (uint64_t)H, (uint64_t)H, CH_BN);
+    encode_2d(&tWfc, a.Wfc, (uint64_t)FF, (uint64_t)H, CH_BN);
+    encode_2d(&tWproj, a.Wproj, (uint64_t)H, (uint64_t)FF, CH_BN);
+    encode_2d(&tWqkv, a.Wqkv ? a.Wqkv : a.Wo, (uint64_t)(a.Wqkv ? 3 * H : H), (uint64_t)H, CH_BN);
+    ChainParams P{};
+    P.phases = a.phases; P.M = a.M; P.H = H; P.FF = FF; P.abox = abox; P.eps = a.eps;
+    P.proj_bias = a.proj_bias; P.ln2_w = a.ln2_w; P.ln2_b = a.ln2_b; P.fc_bias = a.fc_bias; P.fc2_bias = a.fc2_bias;
+    P.ln1_w = a.ln1_w; P.ln1_b = a.ln1_b; P.qkv_bias = a.qkv_bias;
+    P.X = a.X; P.Xn = a.Xn; P.FFb = a.FFb; P.QKV = a.QKV; P.PART = a.PART; P.sync = a.sync;
+    double fl = 0, by = 0;
+    const double M = a.M;
+    if (a.phases & DC_PROJ) { fl += 2.0 * M * H * H; by += 2.0 * (M * H + (double)H * H) + 4.0 * CH_SPLITS * M * H; }
+    if (a.phases & DC_LN2) by += (8.0 + 4.0 * CH_SPLITS + 2.0) * M * H;
+    if (a.phases & DC_FC) { fl += 2.0 * M * H * FF; by += 2.0 * (M * H + (double)H * FF) + 2.0 * M * FF; }
+    if (a.phases & DC_FC2) { fl += 2.0 * M * H * FF; by += 2.0 * (M * FF + (double)H * FF) + 4.0 * CH_SPLITS * M * H; }
+    if (a.phases & DC_LN1) by += (8.0 + 4.0 * CH_SPLITS + 2.0) * M * H;
+    if (a.phases & DC_QKV) { fl += 6.0 * M * H * H; by += 2.0 * (M * H + 3.0 * H * H) + 12.0 * M * H; }
+    ProfScope ps(KF_DECODE_CHAIN, st, fl, by);
+    launch_k(decode_chain_kernel, dim3(n_sm), dim3(kThreads), smem, st, pdl, tATT, tWo, tXn, tWfc, tFF, tWproj, tWqkv, P);
+    COUNT_LAUNCH(); KERNEL_CHECK();
 }
 
 }  // namespace xtts

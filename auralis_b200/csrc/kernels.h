@@ -24,6 +24,22 @@ void launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const f
                          void* out, int M, int N, int K, int flags, cudaStream_t st, bool pdl = false);
 void launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, float* partials, int M, int N, int K,
                                 int splits, cudaStream_t st, bool pdl = false);
+
+// Fused decode chain (gemm_tcgen05.cu): one persistent launch runs, for one layer boundary of the decode step,
+//   proj (split-K) -> residual+LN2 -> fc+gelu -> fc2 (split-K) -> residual+LN1(next layer) -> qkv(next layer)
+// with device-wide barriers between the phases.  `phases` selects a contiguous subset (DC_* bits).
+enum { DC_PROJ = 1, DC_LN2 = 2, DC_FC = 4, DC_FC2 = 8, DC_LN1 = 16, DC_QKV = 32 };
+struct DecodeChainArgs {
+    int phases, M, H, FF;
+    float eps;
+    const __nv_bfloat16* ATT; const __nv_bfloat16* Wo; const __nv_bfloat16* Wfc; const __nv_bfloat16* Wproj; const __nv_bfloat16* Wqkv;
+    const float* proj_bias; const float* ln2_w; const float* ln2_b; const float* fc_bias; const float* fc2_bias;
+    const float* ln1_w; const float* ln1_b; const float* qkv_bias;
+    float* X; __nv_bfloat16* Xn; __nv_bfloat16* FFb; float* QKV; float* PART;
+    unsigned* sync;          // 2 words, zero-initialised once, owned by the chain kernel (self-resetting barrier)
+};
+bool decode_chain_supported(int M, int H, int FF);
+void launch_decode_chain(const DecodeChainArgs& a, cudaStream_t st, bool pdl);
 bool gemm_tc_init(std::string* err);   // resolves cuTensorMapEncodeTiled; false -> err filled
 
 void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st);

@@ -251,6 +251,7 @@ def test_bf16_decode_microbatch_branches_match_single_branch(engine_full_bf16, d
         jobs.append((i, text_ids(dims_full, 9 + 3 * i, 40 + i), i % 3, sp))
     out = {}
     try:
+        engine_full_bf16.set_option("decode_chain", 0)         # the fused chain kernel always runs the rows as one branch
         engine_full_bf16.set_option("microbatch_min_rows", 2)
         for nmb in (1, 2, 3):
             engine_full_bf16.set_option("microbatches", nmb)
@@ -259,7 +260,41 @@ def test_bf16_decode_microbatch_branches_match_single_branch(engine_full_bf16, d
     finally:
         engine_full_bf16.set_option("microbatches", 2)
         engine_full_bf16.set_option("microbatch_min_rows", 48)
+        engine_full_bf16.set_option("decode_chain", 1)
     for nmb in (2, 3):
         for sid in out[1]:
             assert out[nmb][sid][0] == out[1][sid][0], (nmb, sid)
             np.testing.assert_allclose(out[nmb][sid][1], out[1][sid][1], rtol=0, atol=1e-6)
+
+
+def test_bf16_decode_chain_matches_unfused(engine_full_bf16, dims_full, state_full, speakers_full):
+    """Engine option "decode_chain": the persistent kernel that fuses out-proj, residual+LN2, fc+gelu, down-proj,
+    residual+LN1 and the next QKV projection must reproduce the one-launch-per-op decode step (same bf16 operands, same
+    split-K order; only the LayerNorm reduction tree differs) and stay within the fast-mode tolerance of the oracle."""
+    orc = _orc(dims_full, state_full)
+    g = dims_full.gpt
+    ids = text_ids(dims_full, 21, 77)
+    osp = O.SamplingParams(temperature=0.0, repetition_penalty=5.0, max_tokens=16, stop_token=g.stop_audio_token)
+    toks, lats, lg = orc.generate(speakers_full[2][0], ids, osp, return_logits=True)
+    sp = Sampling(temperature=0.0, repetition_penalty=5.0, max_tokens=16, stop_token=g.stop_audio_token)
+    got = {}
+    try:
+        for chain in (1, 0):
+            engine_full_bf16.set_option("decode_chain", chain)
+            logits, lat, sampled = engine_full_bf16.gpt_teacher_forced(ids, 2, toks, sp)
+            jobs = [(i, text_ids(dims_full, 8 + 5 * i, 60 + i), i % 3,
+                     Sampling(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, max_tokens=12, seed=5, seq_seed=i,
+                              stop_token=g.stop_audio_token)) for i in range(4)]
+            res = engine_full_bf16.run_batch(jobs, timeout_s=120, want_latents=True)
+            got[chain] = (logits, lat, {sid: (list(t), l) for sid, (_, t, _, l) in res.items()})
+    finally:
+        engine_full_bf16.set_option("decode_chain", 1)
+    err = np.abs(got[1][0] - lg.numpy()).max()
+    d_logits = np.abs(got[1][0] - got[0][0]).max()
+    d_lat = np.abs(got[1][1] - got[0][1]).max()
+    print("chain vs oracle logits max err", err, "| chain vs unfused: logits", d_logits, "latents", d_lat)
+    assert err < 0.05 * max(1.0, float(lg.abs().max()))
+    assert d_logits < 0.03 and d_lat < 0.05
+    same = sum(got[1][2][sid][0] == got[0][2][sid][0] for sid in got[1][2])
+    print("sampled sequences identical with / without the chain kernel:", same, "/ 4")
+    assert same >= 3
