@@ -48,8 +48,9 @@ __device__ __forceinline__ bool bar_try(uint64_t* b, uint32_t parity) {
 }
 __device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity, int tag) {
     const long long t0 = clock64();
+    int polls = 0;
     while (!bar_try(b, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
+        if ((++polls & 1023) == 0 && clock64() - t0 > 4000000000LL) {
             printf("conv1d_tc: mbarrier watchdog (tag %d, block %d,%d,%d thread %d)\n", tag, blockIdx.x, blockIdx.y, blockIdx.z,
                    threadIdx.x);
             __trap();
@@ -105,6 +106,7 @@ conv1d_tc_kernel(const ConvTcParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float sbias[2][256];     // per-tile bias + speaker bias (double buffered across tiles)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int halo = P.center * P.dil;
@@ -141,78 +143,110 @@ conv1d_tc_kernel(const ConvTcParams P) {
 
     if (warp < 4 * EG) {
         // ------------------------------------------------ epilogue: warp q owns TMEM lanes [32q, 32q+32) = time rows;
-        // the EG warpgroups take alternate 32-column chunks of the tile (more loads/stores in flight per SM)
-        const int q = warp & 3, grp = warp >> 2;
+        // the EG warpgroups take alternate 32-column chunks of the tile.  Per tile the per-channel bias (+ speaker bias)
+        // is staged once in shared memory; the residual of the NEXT chunk is requested before the current chunk is
+        // stored (and the first chunk's before the tile's MMAs have finished), so its latency is off the critical path.
+        const int q = warp & 3, grp = warp >> 2, etid = warp * 32 + lane;
         const int row_limit = P.up ? P.L + 1 : P.L;      // a transposed conv also consumes the zero row x[L]
+        const int ncn = P.N / 32, nitems = NACC * ncn;
+        const bool has_res = P.resid != nullptr, accum = (P.mode == CONV_ACCUM);
+        const size_t Ls = (size_t)P.Lout;
+        float rs[32];
         int lt = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
             const int tx = tile % tiles_t, ty = (tile / tiles_t) % tiles_n;
             const size_t zo = (size_t)(tile / (tiles_t * tiles_n));
             const int T0 = tx * (128 * NACC), n0 = ty * P.N;
             float* out32 = P.out32 ? P.out32 + zo * P.Cr * P.Lout : nullptr;
-            const float* resid = P.resid ? P.resid + zo * P.Cr * P.Lout : nullptr;
+            const float* resid = has_res ? P.resid + zo * P.Cr * P.Lout : nullptr;
             const float* cbias = P.cbias ? P.cbias + zo * P.cbias_bs : nullptr;
             uint4* out16 = P.out16 ? reinterpret_cast<uint4*>(P.out16) + zo * (size_t)(P.Cr / 8) * P.lpad_out : nullptr;
+            float* sb = sbias[lt & 1];
+            for (int j = etid; j < P.N; j += EG * 128) {
+                const int co = (n0 + j) % P.Cr;          // GEMM channel -> real output channel (phases of a transposed conv)
+                sb[j] = (P.bias ? __ldg(P.bias + co) : 0.f) + (cbias ? __ldg(cbias + co) : 0.f);
+            }
+            // geometry of a 32-column chunk: all its GEMM channels belong to one phase (Cr % 32 == 0)
+            auto geom = [&](int item, int& a, int& nc, int& cb, int& t, bool& valid) {
+                a = item / ncn; nc = item - a * ncn;
+                const int srow = T0 + a * 128 + q * 32 + lane;
+                const int cbg = n0 + nc * 32;
+                const int phase = P.up ? cbg / P.Cr : 0;
+                cb = cbg - phase * P.Cr;
+                t = P.up ? srow * P.up + phase - P.up / 2 : srow;
+                valid = srow < row_limit && t >= 0 && t < P.Lout;
+            };
+            int a, nc, cb, t; bool valid;
+            geom(grp, a, nc, cb, t, valid);
+            if (has_res && valid) {
+                const float* rp = resid + (size_t)cb * Ls + t;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) rs[i] = rp[i * Ls];
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(EG * 128) : "memory");      // bias table visible to every epilogue warp
             const int ab = lt % nbuf;
             bar_wait(&tmem_full[ab], (uint32_t)((lt / nbuf) & 1), 4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int ncn = P.N / 32;
 #pragma unroll 1
-            for (int item = grp; item < NACC * ncn; item += EG) {
-                const int a = item / ncn, nc = item - a * ncn;
-                const int srow = T0 + a * 128 + q * 32 + lane;
-                {
-                    uint32_t r[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols + a * P.N + nc * 32);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                        : "r"(taddr) : "memory");
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    // GEMM channels [cbg, cbg+32) of this chunk all belong to one phase (Cr % 32 == 0)
-                    const int cbg = n0 + nc * 32;
-                    const int phase = P.up ? cbg / P.Cr : 0;
-                    const int cb = cbg - phase * P.Cr;               // first real output channel of the chunk
-                    const int t = P.up ? srow * P.up + phase - P.up / 2 : srow;
-                    if (srow < row_limit && t >= 0 && t < P.Lout) {
-                        float v[32];
-                        // every load of the chunk is issued before the first store (the accumulate used to alternate
-                        // dependent load/store pairs: 32 serialized round trips)
+            for (int item = grp; item < nitems; item += EG) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols + a * P.N + nc * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float v[32];
+                const float4* sb4 = reinterpret_cast<const float4*>(sb + nc * 32);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const size_t o = (size_t)(cb + i) * P.Lout + t;
-                            float x = __uint_as_float(r[i]);
-                            if (resid) x += resid[o];
-                            if (out32 && P.mode == CONV_ACCUM) x += out32[o];
-                            v[i] = x;
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b4 = sb4[i];
+                    v[4 * i] = __uint_as_float(r[4 * i]) + b4.x;         v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
+                    v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
+                }
+                if (has_res) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += rs[i];          // (rows outside the signal carry garbage: never stored)
+                }
+                // next chunk: geometry + residual request, in flight while this chunk is stored
+                const bool cur_valid = valid;
+                const int cur_cb = cb, cur_t = t;
+                if (item + EG < nitems) {
+                    geom(item + EG, a, nc, cb, t, valid);
+                    if (has_res && valid) {
+                        const float* rp = resid + (size_t)cb * Ls + t;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) rs[i] = rp[i * Ls];
+                    }
+                }
+                if (cur_valid) {
+                    if (out32) {
+                        float* op = out32 + (size_t)cur_cb * Ls + cur_t;
+                        if (accum) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] += op[i * Ls];     // all loads before the first store
                         }
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int co = cb + i;
-                            v[i] += (P.bias ? __ldg(P.bias + co) : 0.f) + (cbias ? __ldg(cbias + co) : 0.f);
-                        }
-                        if (out32) {
+                        for (int i = 0; i < 32; ++i) op[i * Ls] = v[i];
+                    }
+                    if (out16) {                                     // (after an accumulate: the activated SUM)
+                        uint4* ap = out16 + (size_t)(cur_cb / 8) * P.lpad_out + (cur_t + kAtomPadL);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) out32[(size_t)(cb + i) * P.Lout + t] = v[i];
-                        }
-                        if (out16) {                                 // (after an accumulate: the activated SUM)
+                        for (int g = 0; g < 4; ++g) {
+                            float w8[8];
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                float w8[8];
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) w8[e] = lrelu_s(v[8 * g + e] * P.scale16, P.slope_out);
-                                __half2 h0 = __floats2half2_rn(w8[0], w8[1]), h1 = __floats2half2_rn(w8[2], w8[3]);
-                                __half2 h2 = __floats2half2_rn(w8[4], w8[5]), h3 = __floats2half2_rn(w8[6], w8[7]);
-                                uint4 pk;
-                                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                                out16[(size_t)(cb / 8 + g) * P.lpad_out + (t + kAtomPadL)] = pk;
-                            }
+                            for (int e = 0; e < 8; ++e) w8[e] = lrelu_s(v[8 * g + e] * P.scale16, P.slope_out);
+                            __half2 h0 = __floats2half2_rn(w8[0], w8[1]), h1 = __floats2half2_rn(w8[2], w8[3]);
+                            __half2 h2 = __floats2half2_rn(w8[4], w8[5]), h3 = __floats2half2_rn(w8[6], w8[7]);
+                            uint4 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            ap[(size_t)g * P.lpad_out] = pk;
                         }
                     }
                 }
@@ -340,7 +374,7 @@ void conv1d_tc_pack(const float* w, int Cin, int Cout, int K, const ConvTcPlan& 
 
 int atoms_lpad(int L) { return kAtomPadL + ceil_div(L + 1, 512) * 512 + kAtomPadR; }
 
-constexpr int kMaxDynTc = 227 * 1024 - 2048;      // opt-in limit minus the kernel's static shared memory
+constexpr int kMaxDynTc = 227 * 1024 - 4096;      // opt-in limit minus the kernel's static shared memory
 template <int NACC, int EG>
 static void launch_inst(const ConvTcParams& P, dim3 grid, size_t smem, cudaStream_t st) {
     static bool attr = false;

@@ -45,8 +45,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
     const long long t0 = clock64();
+    int polls = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {      // ~2 s at 2 GHz: a protocol bug, not a slow tile
+        if ((++polls & 1023) == 0 && clock64() - t0 > 4000000000LL) {      // ~2 s at 2 GHz: a protocol bug, not a slow tile
             printf("gemm_tcgen05: mbarrier watchdog (tag %d, block %d,%d, thread %d)\n", tag, blockIdx.x, blockIdx.y,
                    threadIdx.x);
             __trap();
