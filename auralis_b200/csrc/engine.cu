@@ -219,7 +219,7 @@ private:
     bool use_pdl = true;          // option "pdl" (programmatic dependent launch along the decode chain)
     bool use_graphs = true;       // option "cuda_graphs"
     std::atomic<bool> hold_admission{false};   // option "hold_admission": queue submissions, admit nothing (batch submit)
-    bool use_chain = true;        // option "decode_chain": fused persistent per-layer GEMM/LayerNorm chain kernel
+    bool use_chain = false;       // option "decode_chain": fused persistent per-layer GEMM/LayerNorm chain kernel (measured slower)
     DBuf<unsigned> d_chain_sync;  // device-wide barrier words of the chain kernel
     int n_micro = 2;              // option "microbatches": decode rows are split into this many concurrent branches
     int micro_min_rows = 48;      // option "microbatch_min_rows": below this many active rows the step stays single-branch
@@ -351,7 +351,7 @@ Engine::Engine(const xtts_config& c) : cfg(c) {
     const size_t Mmax = (size_t)std::max(prefill_rows_cap, NSLOT);
     wX.alloc(Mmax * H); wQKV.alloc(Mmax * 3 * H); wLOG.alloc((size_t)std::max(NSLOT, CAP + 1) * Vpad);
     if (bf16) wPART.alloc((size_t)8 * NSLOT * H);
-    d_chain_sync.alloc(2); d_chain_sync.zero(st);
+    d_chain_sync.alloc(64); d_chain_sync.zero(st);
     if (bf16) { wXn16.alloc(Mmax * H); wATT16.alloc(Mmax * H); wFF16.alloc(Mmax * FF); wY16.alloc((size_t)std::max(NSLOT, CAP + 1) * H); }
     else { wXn32.alloc(Mmax * H); wATT32.alloc(Mmax * H); wFF32.alloc(Mmax * FF); wY32.alloc((size_t)std::max(NSLOT, CAP + 1) * H); }
 

@@ -310,7 +310,7 @@ struct ChainParams {
     const float* fc2_bias; const float* ln1_w; const float* ln1_b;     // LayerNorm1 of the NEXT layer (null: residual only)
     const float* qkv_bias;                                              // next layer
     float* X; __nv_bfloat16* Xn; __nv_bfloat16* FFb; float* QKV; float* PART;
-    unsigned* sync;                                                     // [0] arrival count, [1] generation
+    unsigned* sync;                                                     // [0] arrival count, [32] generation (64 words)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -318,21 +318,25 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// self-resetting device-wide barrier (all CTAs of the grid are resident: grid <= #SMs, 1 CTA/SM)
+// self-resetting device-wide barrier (all CTAs of the grid are resident: grid <= #SMs, 1 CTA/SM).
+// sync[0] = arrival count, sync[32] = generation: separate 128-byte lines, so the pollers do not queue behind the arrivals.
 __device__ __forceinline__ void chain_grid_sync(unsigned* sync) {
     asm volatile("fence.proxy.async;" ::: "memory");          // generic writes of this phase -> later async-proxy (TMA) reads
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned gen = ld_acquire_u32(sync + 1);
+        unsigned* gen_p = sync + 32;
+        const unsigned gen = ld_acquire_u32(gen_p);
         __threadfence();
         if (atomicAdd(sync, 1u) == gridDim.x - 1) {
             sync[0] = 0u;
             __threadfence();
-            atomicAdd(sync + 1, 1u);
+            atomicAdd(gen_p, 1u);
         } else {
             const long long t0 = clock64();
-            while (ld_acquire_u32(sync + 1) == gen) {
-                if (clock64() - t0 > 4000000000LL) {
+            int polls = 0;
+            while (ld_acquire_u32(gen_p) == gen) {
+                __nanosleep(40);
+                if ((++polls & 1023) == 0 && clock64() - t0 > 4000000000LL) {
                     printf("decode_chain: grid barrier watchdog (block %d)\n", blockIdx.x);
                     __trap();
                 }

@@ -36,7 +36,7 @@ struct DecodeChainArgs {
     const float* proj_bias; const float* ln2_w; const float* ln2_b; const float* fc_bias; const float* fc2_bias;
     const float* ln1_w; const float* ln1_b; const float* qkv_bias;
     float* X; __nv_bfloat16* Xn; __nv_bfloat16* FFb; float* QKV; float* PART;
-    unsigned* sync;          // 2 words, zero-initialised once, owned by the chain kernel (self-resetting barrier)
+    unsigned* sync;          // 64 words, zero-initialised once, owned by the chain kernel (self-resetting barrier)
 };
 bool decode_chain_supported(int M, int H, int FF);
 void launch_decode_chain(const DecodeChainArgs& a, cudaStream_t st, bool pdl);

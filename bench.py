@@ -174,7 +174,7 @@ def main():
     ap.add_argument("--chars", type=int, default=1000)
     ap.add_argument("--max-tokens", type=int, default=605)
     ap.add_argument("--microbatches", type=int, default=2, help="concurrent decode branches per step (engine option; unfused decode only)")
-    ap.add_argument("--decode-chain", type=int, default=1, help="1 = fused persistent per-layer chain kernel in the decode step")
+    ap.add_argument("--decode-chain", type=int, default=0, help="1 = fused persistent per-layer chain kernel in the decode step")
     ap.add_argument("--small", action="store_true", help="tiny geometry (plumbing check only; not a valid bench number)")
     args = ap.parse_args()
 

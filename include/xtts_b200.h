@@ -128,8 +128,8 @@ int xtts_fetch(xtts_engine* e, uint64_t seq_id, int32_t* tokens, float* wav, flo
  *   "cuda_graphs" / "pdl" / "splitk" / "tc_vocoder"   0/1, fast-mode execution features (all default 1)
  *   "hold_admission"      1 = queue submissions without admitting them, 0 = release (atomic batch submit)
  *   "conv_epi_groups"     1 or 2 epilogue warpgroups in the tensor-core conv kernel (default 2)
- *   "decode_chain"        1 = fused persistent per-layer GEMM/LayerNorm chain kernel in the decode step (default), 0 = one
- *                         launch per GEMM / LayerNorm (then "microbatches" applies)
+ *   "decode_chain"        1 = fused persistent per-layer GEMM/LayerNorm chain kernel in the decode step, 0 = one launch per
+ *                         GEMM / LayerNorm with "microbatches" concurrent row branches (default: measured faster)
  *   "microbatches"        1..4 concurrent branches the decode step's rows are split into (default 2)
  *   "microbatch_min_rows" steps with fewer active rows stay single-branch (default 48)
  *   "profile"             1 = CUDA events around every launch (xtts_get_kernel_profile), "reset_stats" = zero the counters */

@@ -260,7 +260,6 @@ def test_bf16_decode_microbatch_branches_match_single_branch(engine_full_bf16, d
     finally:
         engine_full_bf16.set_option("microbatches", 2)
         engine_full_bf16.set_option("microbatch_min_rows", 48)
-        engine_full_bf16.set_option("decode_chain", 1)
     for nmb in (2, 3):
         for sid in out[1]:
             assert out[nmb][sid][0] == out[1][sid][0], (nmb, sid)
@@ -288,7 +287,7 @@ def test_bf16_decode_chain_matches_unfused(engine_full_bf16, dims_full, state_fu
             res = engine_full_bf16.run_batch(jobs, timeout_s=120, want_latents=True)
             got[chain] = (logits, lat, {sid: (list(t), l) for sid, (_, t, _, l) in res.items()})
     finally:
-        engine_full_bf16.set_option("decode_chain", 1)
+        engine_full_bf16.set_option("decode_chain", 0)
     err = np.abs(got[1][0] - lg.numpy()).max()
     d_logits = np.abs(got[1][0] - got[0][0]).max()
     d_lat = np.abs(got[1][1] - got[0][1]).max()

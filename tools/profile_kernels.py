@@ -17,7 +17,10 @@ g = torch.Generator().manual_seed(500)
 cond = torch.randn(32, 1024, generator=g); dv = torch.nn.functional.normalize(torch.randn(512, generator=g), dim=0)
 eng = native.NativeEngine(dims, precision=1, max_batch=max(nb, 8), max_speakers=2)
 eng.load_state(gs, cs); eng.set_speaker(0, cond.numpy(), dv.numpy())
-eng.set_option("cuda_graphs", 0)          # ncu attributes kernels per launch either way; eager keeps names simple
+eng.set_option("cuda_graphs", 0)
+for kv in os.environ.get("XTTS_OPTS", "").split(","):      # e.g. XTTS_OPTS=decode_chain=1,microbatches=1
+    if "=" in kv: eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+          # ncu attributes kernels per launch either way; eager keeps names simple
 rng = np.random.RandomState(1)
 jobs = [(i, [0] + rng.randint(2, 6000, size=78).tolist() + [1], 0,
          native.Sampling(temperature=0.75, top_p=0.85, top_k=50, max_tokens=nt, seed=1, seq_seed=i, vocode=False)) for i in range(nb)]
