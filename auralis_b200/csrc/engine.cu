@@ -1344,6 +1344,12 @@ void Engine::set_option(const std::string& k, int64_t v) {
     if (k == "d2h_wav") d2h_wav = v != 0;
     else if (k == "tc_vocoder") use_tc_vocoder = v != 0;
     else if (k == "conv_epi_groups") g_conv_epi_groups = v >= 2 ? 2 : 1;
+    else if (k == "attn_ctas_per_sm" || k == "gemm_bn") {
+        if (k == "gemm_bn") { if (v != 0 && v != 32 && v != 64 && v != 128) throw std::runtime_error("gemm_bn: 0, 32, 64 or 128"); g_gemm_decode_bn = (int)v; }
+        else g_attn_ctas_per_sm = (int)v;                        // < 0: absolute grid size (tests)
+        for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second);
+        decode_graphs.clear();
+    }
     else if (k == "cuda_graphs") use_graphs = v != 0;
     else if (k == "pdl") { use_pdl = v != 0; for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second); decode_graphs.clear(); }
     else if (k == "splitk") { use_splitk = v != 0; for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second); decode_graphs.clear(); }

@@ -10,6 +10,7 @@
 #include "kernels.h"
 
 namespace xtts {
+int g_gemm_decode_bn = 0;
 namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
@@ -614,6 +615,7 @@ void launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const f
     int bn = 128;
     if (N % 128 != 0 || mt * (N / 128) < 148) bn = 64;
     if (bn == 64 && (N % 64 != 0 || mt * (N / 64) < 148)) bn = 32;
+    if (g_gemm_decode_bn && M <= 256 && N % g_gemm_decode_bn == 0) bn = g_gemm_decode_bn;
     CUtensorMap tmA, tmB;
     const int abox = a_box_rows_for(M);
     encode_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint32_t)abox);
@@ -634,6 +636,7 @@ void launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, 
     int bn = 128;
     if (N % 128 != 0 || mt * (N / 128) * splits < 148) bn = 64;
     if (bn == 64 && (N % 64 != 0 || mt * (N / 64) * splits < 148)) bn = 32;
+    if (g_gemm_decode_bn && M <= 256 && N % g_gemm_decode_bn == 0) bn = g_gemm_decode_bn;
     CUtensorMap tmA, tmB;
     const int abox = a_box_rows_for(M);
     encode_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint32_t)abox);

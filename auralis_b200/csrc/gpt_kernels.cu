@@ -8,9 +8,11 @@
 //   K5     vLLM paged attention + reshape_and_cache (3rd party)                        -> kv_write, attn_*
 //   K10    hijack.py:49-88 LogitsRepetitionPenalizer                                    -> sample (penalty)
 //   K11    vLLM Sampler                                               -> sample
+#include <algorithm>
 #include "kernels.h"
 
 namespace xtts {
+int g_attn_ctas_per_sm = 0;       // engine option "attn_ctas_per_sm": 0 = one CTA per (row, head); > 0 caps the decode-attention grid
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -209,7 +211,7 @@ template <typename TKV, typename TOut>
 __global__ void __launch_bounds__(128)
 attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active, const int* __restrict__ ctx_len,
                    const int* __restrict__ block_tables, int max_pages, TKV* __restrict__ kpool, TKV* __restrict__ vpool,
-                   TOut* __restrict__ out, int heads) {
+                   TOut* __restrict__ out, int heads, int n_items) {
     constexpr int X = KVec<TKV>::X;
     constexpr int NCH = kHeadDim / X;                 // 16-byte atoms per token row (8 bf16 / 16 fp32)
     constexpr int TPI = 32 / NCH;                     // tokens covered by one warp-wide V load (4 / 2)
@@ -218,8 +220,11 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
     __shared__ float pm[4], pl[4];
     __shared__ float pacc[4][kHeadDim];
     pdl_trigger(); pdl_wait();
-    const int i = blockIdx.x, h = blockIdx.y;
     const int H = heads * kHeadDim;
+    // work items = (active row, head); the grid may be capped below M*heads (engine option "attn_ctas_per_sm") so that the
+    // kernel leaves registers free for GEMM CTAs of a concurrent decode branch: then each CTA walks several items
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int i = item / heads, h = item - i * heads;
     const int slot = active[i];
     const int past = ctx_len[slot];                   // tokens already cached; the new one goes to position `past`
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -323,6 +328,8 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
             o = fmaf(pacc[k][tid], e, o);
         }
         out[(size_t)i * H + h * kHeadDim + tid] = from_f32<TOut>(o / L);
+    }
+    __syncthreads();                                  // qs/ks/vs/pacc are reused by the next item
     }
 }
 
@@ -803,8 +810,17 @@ void launch_attn_decode(const float* QKV, const int* active, int M, const int* c
     // algorithmic bytes: K and V of every cached token of every sequence, once
     ProfScope ps(KF_ATTN_DECODE, st, 4.0 * ctx_sum_hint * heads * kHeadDim,
                  2.0 * ctx_sum_hint * heads * kHeadDim * sizeof(TKV));
-    launch_k(attn_decode_kernel<TKV, TOut>, dim3(M, heads), dim3(128), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
-             kpool, vpool, out, heads);
+    const int n_items = M * heads;
+    int grid = n_items;
+    if (g_attn_ctas_per_sm > 0) {
+        static int n_sm = 0;
+        if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+        grid = std::min(n_items, n_sm * g_attn_ctas_per_sm);
+    } else if (g_attn_ctas_per_sm < 0) {
+        grid = std::min(n_items, -g_attn_ctas_per_sm);          // test hook: an absolute grid size
+    }
+    launch_k(attn_decode_kernel<TKV, TOut>, dim3(grid), dim3(128), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
+             kpool, vpool, out, heads, n_items);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 template void launch_attn_decode<float, float>(const float*, const int*, int, const int*, const int*, int, float*, float*, float*, int, cudaStream_t, double, bool);

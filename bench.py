@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--chars", type=int, default=1000)
     ap.add_argument("--max-tokens", type=int, default=605)
     ap.add_argument("--microbatches", type=int, default=2, help="concurrent decode branches per step (engine option; unfused decode only)")
+    ap.add_argument("--engine-opt", action="append", default=[], help="extra engine option key=value (repeatable)")
     ap.add_argument("--decode-chain", type=int, default=0, help="1 = fused persistent per-layer chain kernel in the decode step")
     ap.add_argument("--small", action="store_true", help="tiny geometry (plumbing check only; not a valid bench number)")
     args = ap.parse_args()
@@ -284,6 +285,8 @@ def main():
     ne.set_option("d2h_wav", 0)
     ne.set_option("microbatches", args.microbatches)
     ne.set_option("decode_chain", args.decode_chain)
+    for kv in args.engine_opt:
+        ne.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     eng.park_poller(True)                 # the device arm drives the native completion queue directly
     sampler = ClockSampler(local) if rank == 0 else None
     for i in range(args.warmup):
@@ -383,6 +386,7 @@ def main():
                    "vocoder_compute": "fp16 tcgen05 implicit-GEMM convs (fp32 accumulate, fp32 residual stream)" if args.precision == "bf16" else "fp32",
                    "l2": "no explicit flush: per-step working set (0.76 GB weights + >5 GB KV + 0.4 GB vocoder activations) >> 126 MB L2",
                    "timing": "host perf_counter bracketed by barrier + cuda synchronize (device idle on both sides); max over ranks",
+                   "engine_opts": args.engine_opt,
                    "decode_step": ("per layer: paged attention + one persistent chain kernel (out-proj, LN2, fc+gelu, down-proj, LN1, next QKV)"
                                    if args.decode_chain else f"one launch per GEMM/LayerNorm, {args.microbatches} concurrent row branches"),
                    "roofline_timing": "CUDA events around every launch on the engine stream, in one extra identical step right after the timed ones (eager launches, single decode branch so families do not overlap)",

@@ -298,3 +298,27 @@ def test_bf16_decode_chain_matches_unfused(engine_full_bf16, dims_full, state_fu
     same = sum(got[1][2][sid][0] == got[0][2][sid][0] for sid in got[1][2])
     print("sampled sequences identical with / without the chain kernel:", same, "/ 4")
     assert same >= 2          # seeded sampling at T=0.75: a bf16 near-tie may flip one chain and everything after it
+
+
+def test_capped_attention_grid_and_forced_gemm_tile(engine_small, engine_full_bf16, dims_small, dims_full):
+    """Engine options "attn_ctas_per_sm" (decode attention walks several (row, head) items per CTA) and "gemm_bn" (tile
+    width of the decode GEMMs) change scheduling only: tokens and waveforms must be unchanged."""
+    for eng, dims, opts in ((engine_small, dims_small, [("attn_ctas_per_sm", -3)]),
+                            (engine_full_bf16, dims_full, [("attn_ctas_per_sm", -5), ("gemm_bn", 64)])):
+        g = dims.gpt
+        jobs = [(i, text_ids(dims, 6 + 4 * i, 90 + i), i % 3,
+                 Sampling(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, max_tokens=10, seed=3, seq_seed=i,
+                          stop_token=g.stop_audio_token)) for i in range(4)]
+        ref = eng.run_batch(jobs, timeout_s=120)
+        for key, val in opts:
+            try:
+                eng.set_option(key, val)
+                got = eng.run_batch(jobs, timeout_s=120)
+            finally:
+                eng.set_option(key, 0)
+            for sid in ref:
+                if key == "attn_ctas_per_sm":
+                    assert list(got[sid][1]) == list(ref[sid][1]), (key, sid)
+                    np.testing.assert_allclose(got[sid][2], ref[sid][2], rtol=0, atol=1e-6)
+                else:                                   # another tile width = another bf16 summation order inside the MMA? no:
+                    assert list(got[sid][1]) == list(ref[sid][1]), (key, sid)     # K order per output is unchanged
