@@ -38,6 +38,15 @@ enum KernelFamily : int {
 struct KernelProfiler {
     bool enabled = false;
     struct Rec { cudaEvent_t a, b; int fam; };
+    // Events bracketing the kernels of ONE captured graph (cudaEventRecordExternal nodes): re-recorded by every replay and
+    // read back after the replay's synchronize.  Inside a graph there is no host launch gap between the event and the
+    // kernel, so these are true device durations even for 5-us kernels (eager event pairs include the CPU launch latency).
+    struct GraphRecs {
+        std::vector<Rec> recs;
+        double flops[KF_COUNT] = {0}, bytes[KF_COUNT] = {0};
+        unsigned long long launches[KF_COUNT] = {0};
+    };
+    GraphRecs* cap = nullptr;          // non-null while a profiled graph is being captured
     std::vector<Rec> recs;
     std::vector<cudaEvent_t> pool;
     double ms[KF_COUNT] = {0}, flops[KF_COUNT] = {0}, bytes[KF_COUNT] = {0};
@@ -54,19 +63,38 @@ struct KernelProfiler {
         }
         recs.clear();
     }
+    void collect_graph(const GraphRecs& g) {       // after the replay has been synchronized
+        for (auto& r : g.recs) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) ms[r.fam] += t;
+        }
+        for (int i = 0; i < KF_COUNT; ++i) { flops[i] += g.flops[i]; bytes[i] += g.bytes[i]; launches[i] += g.launches[i]; }
+        (void)cudaGetLastError();
+    }
     void reset() { collect(); for (int i = 0; i < KF_COUNT; ++i) { ms[i] = flops[i] = bytes[i] = 0; launches[i] = 0; } }
 };
 extern KernelProfiler g_prof;
 struct ProfScope {
-    cudaStream_t st; cudaEvent_t b; bool on;
-    ProfScope(int fam, cudaStream_t s, double fl = 0, double by = 0) : st(s), b(nullptr), on(g_prof.enabled) {
+    cudaStream_t st; cudaEvent_t b; bool on; bool ext;
+    ProfScope(int fam, cudaStream_t s, double fl = 0, double by = 0) : st(s), b(nullptr), on(g_prof.enabled), ext(false) {
         if (!on) return;
+        if (g_prof.cap) {                          // capturing a profiled graph: event-record nodes owned by that graph
+            ext = true;
+            cudaEvent_t a; cudaEventCreate(&a); cudaEventCreate(&b);
+            cudaEventRecordWithFlags(a, st, cudaEventRecordExternal);
+            g_prof.cap->recs.push_back({a, b, fam});
+            g_prof.cap->flops[fam] += fl; g_prof.cap->bytes[fam] += by; g_prof.cap->launches[fam] += 1;
+            return;
+        }
         cudaEvent_t a = g_prof.get(); b = g_prof.get();
         cudaEventRecord(a, st);
         g_prof.recs.push_back({a, b, fam});
         g_prof.flops[fam] += fl; g_prof.bytes[fam] += by; g_prof.launches[fam] += 1;
     }
-    ~ProfScope() { if (on) cudaEventRecord(b, st); }
+    ~ProfScope() {
+        if (!on) return;
+        if (ext) cudaEventRecordWithFlags(b, st, cudaEventRecordExternal); else cudaEventRecord(b, st);
+    }
 };
 inline const char* kernel_family_name(int f) {
     static const char* n[KF_COUNT] = {"gemm_bf16_tcgen05", "gemm_f32", "attn_decode_paged", "attn_prefill", "layernorm",

@@ -219,6 +219,9 @@ private:
     bool use_pdl = true;          // option "pdl" (programmatic dependent launch along the decode chain)
     bool use_graphs = true;       // option "cuda_graphs"
     std::atomic<bool> hold_admission{false};   // option "hold_admission": queue submissions, admit nothing (batch submit)
+    std::map<int, std::pair<cudaGraphExec_t, KernelProfiler::GraphRecs*>> prof_graphs;   // decode graphs with event-record nodes (option "profile")
+    KernelProfiler::GraphRecs* last_prof = nullptr;     // recs of the profiled graph launched by the current step
+    void drop_graphs();
     bool use_chain = false;       // option "decode_chain": fused persistent per-layer GEMM/LayerNorm chain kernel (measured slower)
     DBuf<unsigned> d_chain_sync;  // device-wide barrier words of the chain kernel
     int n_micro = 2;              // option "microbatches": decode rows are split into this many concurrent branches
@@ -399,7 +402,7 @@ Engine::~Engine() {
     if (worker.joinable()) worker.join();
     cudaSetDevice(cfg.device);
     cudaStreamSynchronize(st);
-    for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second);
+    drop_graphs();
     for (auto& pr : pinned_pool) cudaFreeHost(pr.first);
     for (auto& pr : dev_pool) cudaFree(pr.first);
     for (auto& kv : done_map) if (kv.second->wav_host) cudaFreeHost(kv.second->wav_host);
@@ -904,6 +907,18 @@ void Engine::decode_layers_chain(int M) {
     }
 }
 
+void Engine::drop_graphs() {
+    for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second);
+    decode_graphs.clear();
+    for (auto& kv : prof_graphs) {
+        cudaGraphExecDestroy(kv.second.first);
+        for (auto& r : kv.second.second->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        delete kv.second.second;
+    }
+    prof_graphs.clear();
+    last_prof = nullptr;
+}
+
 void Engine::decode_step(const std::vector<int>& active) {
     const int M = (int)active.size();
     d_active.upload(active.data(), M, st);
@@ -934,10 +949,34 @@ void Engine::decode_step(const std::vector<int>& active) {
     // The decode step is ~250 small launches whose arguments depend only on M (slot lists, positions and
     // lengths live in device memory), so it is captured once per batch size into a CUDA graph and replayed.
     // Kernel-family profiling and teacher forcing use the eager path.
-    const bool graphable = use_graphs && !g_prof.enabled && !use_forced && eager_steps_done >= 2;
+    const bool graphable = use_graphs && !use_forced && eager_steps_done >= 2;
     if (!graphable) {
         enqueue();
         ++eager_steps_done;
+    } else if (g_prof.enabled) {
+        // kernel-family profiling: the same step captured with an event-record node on either side of every kernel
+        // (full dependencies instead of PDL edges), replayed, and read back after the step's synchronize
+        auto it = prof_graphs.find(M);
+        if (it == prof_graphs.end()) {
+            cudaGraph_t g = nullptr; cudaGraphExec_t ge = nullptr;
+            auto* recs = new KernelProfiler::GraphRecs();
+            const unsigned long long lc = g_launch_count;
+            const bool pdl_was = g_use_pdl;
+            g_use_pdl = false; g_prof.cap = recs;
+            CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            try { enqueue(); }
+            catch (...) { g_prof.cap = nullptr; g_use_pdl = pdl_was; cudaStreamEndCapture(st, &g); if (g) cudaGraphDestroy(g); delete recs; throw; }
+            g_prof.cap = nullptr; g_use_pdl = pdl_was;
+            CUDA_CHECK(cudaStreamEndCapture(st, &g));
+            CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
+            cudaGraphDestroy(g);
+            graph_kernels[M] = g_launch_count - lc;
+            g_launch_count = lc;
+            it = prof_graphs.emplace(M, std::make_pair(ge, recs)).first;
+        }
+        CUDA_CHECK(cudaGraphLaunch(it->second.first, st));
+        g_launch_count += graph_kernels[M];
+        last_prof = it->second.second;
     } else {
         auto it = decode_graphs.find(M);
         if (it == decode_graphs.end()) {
@@ -1269,6 +1308,7 @@ void Engine::loop() {
                     decode_step(active);
                     d_finished.download(h_finished, NSLOT, st);
                     CUDA_CHECK(cudaStreamSynchronize(st));
+                    if (last_prof) { g_prof.collect_graph(*last_prof); last_prof = nullptr; }
                 }
             }
             st_gpt_ms += (now_s() - t0) * 1e3;
@@ -1347,17 +1387,15 @@ void Engine::set_option(const std::string& k, int64_t v) {
     else if (k == "attn_ctas_per_sm" || k == "gemm_bn") {
         if (k == "gemm_bn") { if (v != 0 && v != 32 && v != 64 && v != 128) throw std::runtime_error("gemm_bn: 0, 32, 64 or 128"); g_gemm_decode_bn = (int)v; }
         else g_attn_ctas_per_sm = (int)v;                        // < 0: absolute grid size (tests)
-        for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second);
-        decode_graphs.clear();
+        drop_graphs();
     }
     else if (k == "cuda_graphs") use_graphs = v != 0;
-    else if (k == "pdl") { use_pdl = v != 0; for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second); decode_graphs.clear(); }
-    else if (k == "splitk") { use_splitk = v != 0; for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second); decode_graphs.clear(); }
-    else if (k == "decode_chain") { use_chain = v != 0; for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second); decode_graphs.clear(); }
+    else if (k == "pdl") { use_pdl = v != 0; drop_graphs(); }
+    else if (k == "splitk") { use_splitk = v != 0; drop_graphs(); }
+    else if (k == "decode_chain") { use_chain = v != 0; drop_graphs(); }
     else if (k == "microbatches" || k == "microbatch_min_rows") {
         if (k == "microbatches") n_micro = std::max<int>(1, std::min<int64_t>(v, kMaxMicro)); else micro_min_rows = (int)std::max<int64_t>(2, v);
-        for (auto& kv : decode_graphs) cudaGraphExecDestroy(kv.second);
-        decode_graphs.clear();
+        drop_graphs();
     }
     else if (k == "profile") { CUDA_CHECK(cudaSetDevice(cfg.device)); CUDA_CHECK(cudaStreamSynchronize(st)); g_prof.reset(); g_prof.enabled = v != 0; }
     else if (k == "reset_stats") {

@@ -303,8 +303,9 @@ def main():
     tokens_dev = sum(a[1] for a in acc_dev)
     log(f"device arm: {dt_dev:.2f}s for {args.steps} step(s); engine clocks: gpt {st.gpt_ms:.0f} ms, vocoder {st.vocoder_ms:.0f} ms, "
         f"{st.decode_steps} decode steps, {st.kernel_launches} kernels")
-    # ---- kernel-family profile: one more identical step with CUDA events around every launch (eager launches; the
-    # timed steps replay the decode step as a CUDA graph, which event pairs cannot bracket kernel by kernel)
+    # ---- kernel-family profile: one more identical step with a CUDA event on either side of every launch.  The decode
+    # step is replayed from a graph that carries the events as event-record nodes (no host launch gap inside the bracket,
+    # full dependencies instead of PDL edges); prefill and vocoder launches are bracketed eagerly (long kernels).
     # The profile step also runs the decode rows as ONE branch: concurrent micro-batch branches overlap kernels of
     # different families, which would smear each family's own duration.
     ne.set_option("microbatches", 1)
@@ -360,14 +361,17 @@ def main():
         fams[k] = {"ms": round(v["ms"], 3), "share": round(v["ms"] / total_ms, 4), "launches": v["launches"],
                    "GB/s": round(gbs, 1), "TFLOP/s": round(tfs, 2),
                    "frac_of_hbm_peak": round(gbs / hbm_peak, 4), "frac_of_tensor_peak": round(tfs / tc_peak, 4)}
-    tensor_bound = dom_name.startswith("gemm_bf16") or dom_name.startswith("conv1d_tc")
+    # which roof binds the dominant family: its algorithmic FLOP/byte against the machine's ridge point
+    ridge = tc_peak * 1e12 / (hbm_peak * 1e9)
+    ai = dom["flops"] / dom["bytes"] if dom.get("bytes") else 0.0
+    tensor_bound = ai >= ridge
     if tensor_bound:
         ach = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak}
     else:
         ach = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}
-    roof.update({"kernel": dom_name, "avg_launch_us": 1e3 * dom["ms"] / max(1, dom["launches"]), "launches": dom["launches"],
+    roof.update({"kernel": dom_name, "flop_per_byte": ai, "ridge_flop_per_byte": ridge, "avg_launch_us": 1e3 * dom["ms"] / max(1, dom["launches"]), "launches": dom["launches"],
                  "share_of_device_time": dom["ms"] / total_ms, "peak_source": peak_src, "traffic": None,
                  "fp32_tflops": dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] else None,
                  "families": fams})
@@ -389,7 +393,7 @@ def main():
                    "engine_opts": args.engine_opt,
                    "decode_step": ("per layer: paged attention + one persistent chain kernel (out-proj, LN2, fc+gelu, down-proj, LN1, next QKV)"
                                    if args.decode_chain else f"one launch per GEMM/LayerNorm, {args.microbatches} concurrent row branches"),
-                   "roofline_timing": "CUDA events around every launch on the engine stream, in one extra identical step right after the timed ones (eager launches, single decode branch so families do not overlap)",
+                   "roofline_timing": "CUDA events around every launch on the engine stream, in one extra identical step right after the timed ones (decode step: event-record nodes inside the replayed graph, single row branch, no PDL overlap; prefill/vocoder: eager)",
                    "e2e_speakers": "4 reference wavs conditioned on the GPU before the timed region (per-speaker cache, as prepare_for_streaming_generation)"},
         "gpt_tokens_per_s": tokens_dev / dt_dev, "rtf": 1.0 / value,
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

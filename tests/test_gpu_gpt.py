@@ -322,3 +322,25 @@ def test_capped_attention_grid_and_forced_gemm_tile(engine_small, engine_full_bf
                     np.testing.assert_allclose(got[sid][2], ref[sid][2], rtol=0, atol=1e-6)
                 else:                                   # another tile width = another bf16 summation order inside the MMA? no:
                     assert list(got[sid][1]) == list(ref[sid][1]), (key, sid)     # K order per output is unchanged
+
+
+def test_kernel_profile_graph_events(engine_small_bf16, dims_small):
+    """Option "profile": the decode step is replayed from a graph that carries an event-record node on either side of
+    every kernel; the family table must account for every decode launch and the tokens must not change."""
+    g = dims_small.gpt
+    jobs = [(i, text_ids(dims_small, 7 + i, 30 + i), i % 3,
+             Sampling(temperature=0.0, repetition_penalty=5.0, max_tokens=12, stop_token=g.stop_audio_token, vocode=False))
+            for i in range(3)]
+    ref = engine_small_bf16.run_batch(jobs, timeout_s=60, want_wav=False)
+    engine_small_bf16.set_option("profile", 1)
+    try:
+        got = engine_small_bf16.run_batch(jobs, timeout_s=60, want_wav=False)
+        prof = engine_small_bf16.kernel_profile()
+    finally:
+        engine_small_bf16.set_option("profile", 0)
+    for sid in ref:
+        assert list(got[sid][1]) == list(ref[sid][1])
+    L = g.layers
+    att = prof["attn_decode_paged"]
+    assert att["launches"] >= 9 * L and att["ms"] > 0 and att["bytes"] > 0, att
+    assert prof["sample"]["launches"] >= 10 and prof["gemm_bf16_tcgen05"]["ms"] > 0
