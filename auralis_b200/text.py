@@ -6,8 +6,8 @@ Restates the splitting rules of `/root/reference/src/auralis/models/xttsv2/confi
 sentencizer equivalent to spaCy's rule-based ``sentencizer`` for the scripts XTTS supports.
 
 Token ids: with a real ``tokenizer.json`` (HF `tokenizers`) in the GPT model directory the BPE of the
-reference is used (`XTTSTokenizerFast`, tokenizer.py:742-942, basic cleaners only — the per-language
-number/abbreviation expansion is the SURVEY §8f-1 "next" row).  Without one (this build has no network)
+reference is used (`XTTSTokenizerFast`, tokenizer.py:742-942) behind the per-language cleaners of `textnorm.py`
+(English numbers / abbreviations / symbols restated; other languages keep their digits — SURVEY §8f-1).  Without one (this build has no network)
 ids are synthetic: ceil(chars/3.2) ids drawn uniformly from the text vocabulary, seeded by the chunk's
 hash — deterministic, same chunk -> same ids.
 """
@@ -20,6 +20,8 @@ import re
 from typing import List, Optional
 
 import numpy as np
+
+from .textnorm import basic_cleaners, format_for_bpe, preprocess_text  # noqa: F401  (re-exported)
 
 CHAR_LIMITS = {"en": 250, "de": 253, "fr": 273, "es": 239, "it": 213, "pt": 203, "pl": 224, "zh": 82, "ar": 166,
                "cs": 186, "ru": 182, "nl": 251, "tr": 226, "ja": 71, "hu": 224, "ko": 95}
@@ -93,10 +95,6 @@ def split_sentence(text: str, lang: str, text_split_length: int = 250) -> List[s
 _WS = re.compile(r"\s+")
 
 
-def basic_cleaners(text: str) -> str:
-    return _WS.sub(" ", text.lower()).strip()
-
-
 class XTTSTokenizer:
     """Chunk -> ids.  ``bos``/``eos`` are added by the engine (XTTSv2.py:519-522)."""
 
@@ -120,7 +118,7 @@ class XTTSTokenizer:
     def encode_chunk(self, chunk: str, lang: str) -> List[int]:
         base = lang.split("-")[0]
         if self.tok is not None:
-            txt = f"[{base}]{basic_cleaners(chunk)}".replace(" ", "[SPACE]")     # tokenizer.py:871-942
+            txt = format_for_bpe(chunk, lang)                                    # tokenizer.py:871-942
             ids = self.tok.encode(txt, add_special_tokens=False).ids
         else:
             n = max(1, int(math.ceil(len(chunk) / 3.2)))
