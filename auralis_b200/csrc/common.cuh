@@ -45,6 +45,7 @@ struct KernelProfiler {
         std::vector<Rec> recs;
         double flops[KF_COUNT] = {0}, bytes[KF_COUNT] = {0};
         unsigned long long launches[KF_COUNT] = {0};
+        double ctx_sum = 0;            // cached tokens summed over the step's rows when the graph was captured
     };
     GraphRecs* cap = nullptr;          // non-null while a profiled graph is being captured
     std::vector<Rec> recs;
@@ -63,12 +64,18 @@ struct KernelProfiler {
         }
         recs.clear();
     }
-    void collect_graph(const GraphRecs& g) {       // after the replay has been synchronized
+    // after the replay has been synchronized.  The paged-attention work of a replay scales with the tokens cached NOW,
+    // not with those cached when the graph was captured: `ctx_sum_now` rescales that family's algorithmic bytes / FLOPs.
+    void collect_graph(const GraphRecs& g, double ctx_sum_now) {
         for (auto& r : g.recs) {
             float t = 0.f;
             if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) ms[r.fam] += t;
         }
-        for (int i = 0; i < KF_COUNT; ++i) { flops[i] += g.flops[i]; bytes[i] += g.bytes[i]; launches[i] += g.launches[i]; }
+        const double attn_scale = (g.ctx_sum > 0 && ctx_sum_now > 0) ? ctx_sum_now / g.ctx_sum : 1.0;
+        for (int i = 0; i < KF_COUNT; ++i) {
+            const double sc = (i == KF_ATTN_DECODE) ? attn_scale : 1.0;
+            flops[i] += sc * g.flops[i]; bytes[i] += sc * g.bytes[i]; launches[i] += g.launches[i];
+        }
         (void)cudaGetLastError();
     }
     void reset() { collect(); for (int i = 0; i < KF_COUNT; ++i) { ms[i] = flops[i] = bytes[i] = 0; launches[i] = 0; } }

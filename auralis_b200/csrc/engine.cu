@@ -122,6 +122,7 @@ public:
     void get_stats(xtts_stats* s);
     void sync_idle();
     void kernel_profile(xtts_kernel_profile* out);
+    void device_timer(int op, double* ms);
 
     void vocode_sync(const float* latents, int T, int speaker, float* wav, int* n_out, const char* stage,
                      float* stage_out, int64_t stage_cap);
@@ -143,6 +144,8 @@ private:
     cudaStream_t st = nullptr;
     static constexpr int kMaxMicro = 4;
     cudaStream_t st_mb[kMaxMicro] = {nullptr, nullptr, nullptr, nullptr};   // [0] == st; decode micro-batch branches
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;       // xtts_device_timer
+    bool timer_armed = false;
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxMicro] = {nullptr, nullptr, nullptr, nullptr};
 
     // ---- weights
@@ -409,6 +412,8 @@ Engine::~Engine() {
     if (h_finished) cudaFreeHost(h_finished);
     for (int i = 1; i < kMaxMicro; ++i) { if (st_mb[i]) cudaStreamDestroy(st_mb[i]); if (ev_join[i]) cudaEventDestroy(ev_join[i]); }
     if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_t0) cudaEventDestroy(ev_t0);
+    if (ev_t1) cudaEventDestroy(ev_t1);
     if (st) cudaStreamDestroy(st);
 }
 
@@ -960,6 +965,7 @@ void Engine::decode_step(const std::vector<int>& active) {
         if (it == prof_graphs.end()) {
             cudaGraph_t g = nullptr; cudaGraphExec_t ge = nullptr;
             auto* recs = new KernelProfiler::GraphRecs();
+            recs->ctx_sum = decode_ctx_sum;
             const unsigned long long lc = g_launch_count;
             const bool pdl_was = g_use_pdl;
             g_use_pdl = false; g_prof.cap = recs;
@@ -1308,7 +1314,7 @@ void Engine::loop() {
                     decode_step(active);
                     d_finished.download(h_finished, NSLOT, st);
                     CUDA_CHECK(cudaStreamSynchronize(st));
-                    if (last_prof) { g_prof.collect_graph(*last_prof); last_prof = nullptr; }
+                    if (last_prof) { g_prof.collect_graph(*last_prof, decode_ctx_sum); last_prof = nullptr; }
                 }
             }
             st_gpt_ms += (now_s() - t0) * 1e3;
@@ -1423,6 +1429,25 @@ void Engine::kernel_profile(xtts_kernel_profile* out) {
         out->ms[i] = g_prof.ms[i]; out->flops[i] = g_prof.flops[i]; out->bytes[i] = g_prof.bytes[i];
         out->launches[i] = g_prof.launches[i];
     }
+}
+
+// Stopwatch on the engine stream.  Every other stream the engine uses (decode branches) forks from and joins back into
+// `st` inside a step, so an event recorded on `st` behind a step completes after all of that step's device work.
+void Engine::device_timer(int op, double* ms) {
+    std::lock_guard<std::mutex> lk(mu);
+    CUDA_CHECK(cudaSetDevice(cfg.device));
+    if (!ev_t0) { CUDA_CHECK(cudaEventCreate(&ev_t0)); CUDA_CHECK(cudaEventCreate(&ev_t1)); }
+    if (op == 0) {
+        CUDA_CHECK(cudaEventRecord(ev_t0, st));
+        timer_armed = true;
+    } else if (op == 1) {
+        if (!timer_armed) throw std::runtime_error("device_timer: stop without start");
+        CUDA_CHECK(cudaEventRecord(ev_t1, st));
+        CUDA_CHECK(cudaEventSynchronize(ev_t1));
+        float t = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&t, ev_t0, ev_t1));
+        if (ms) *ms = (double)t;
+    } else throw std::runtime_error("device_timer: op must be 0 (start) or 1 (stop)");
 }
 
 void Engine::sync_idle() {
@@ -1641,6 +1666,7 @@ int xtts_set_option(xtts_engine* e, const char* key, int64_t value) { XTTS_TRY(e
 int xtts_get_stats(xtts_engine* e, xtts_stats* out) { XTTS_TRY(e->impl->get_stats(out)) }
 int xtts_sync(xtts_engine* e) { XTTS_TRY(e->impl->sync_idle()) }
 int xtts_get_kernel_profile(xtts_engine* e, xtts_kernel_profile* out) { XTTS_TRY(e->impl->kernel_profile(out)) }
+int xtts_device_timer(xtts_engine* e, int32_t op, double* ms) { XTTS_TRY(e->impl->device_timer(op, ms)) }
 int xtts_vocode(xtts_engine* e, const float* latents, int32_t T, int32_t speaker_slot, float* wav, int32_t* n_out,
                 const char* stage, float* stage_out, int64_t stage_cap) {
     XTTS_TRY(e->impl->vocode_sync(latents, T, speaker_slot, wav, n_out, stage, stage_out, stage_cap))

@@ -73,7 +73,7 @@ class XttsKernelProfile(C.Structure):
 ABI_SYMBOLS = [
     "xtts_last_error", "xtts_version", "xtts_create", "xtts_destroy", "xtts_load_weight", "xtts_finalize_weights",
     "xtts_set_speaker", "xtts_get_speaker", "xtts_condition", "xtts_submit", "xtts_poll", "xtts_fetch",
-    "xtts_set_option", "xtts_get_stats", "xtts_sync", "xtts_get_kernel_profile", "xtts_vocode", "xtts_gpt_prefill", "xtts_gpt_teacher_forced",
+    "xtts_set_option", "xtts_get_stats", "xtts_sync", "xtts_get_kernel_profile", "xtts_device_timer", "xtts_vocode", "xtts_gpt_prefill", "xtts_gpt_teacher_forced",
     "xtts_debug_gemm", "xtts_debug_sample",
 ]
 
@@ -106,6 +106,7 @@ def load_library(path: Optional[str] = None):
     lib.xtts_get_stats.argtypes = [vp, C.POINTER(XttsStats)]
     lib.xtts_sync.argtypes = [vp]
     lib.xtts_get_kernel_profile.argtypes = [vp, C.POINTER(XttsKernelProfile)]
+    lib.xtts_device_timer.argtypes = [vp, i32, C.POINTER(C.c_double)]
     lib.xtts_vocode.argtypes = [vp, f32p, i32, i32, f32p, i32p, C.c_char_p, f32p, i64]
     lib.xtts_gpt_prefill.argtypes = [vp, i32p, i32, i32, i32p, i32, f32p, f32p, f32p]
     lib.xtts_gpt_teacher_forced.argtypes = [vp, i32p, i32, i32, i32p, i32, C.POINTER(XttsSampling), f32p, f32p, i32p]
@@ -274,6 +275,16 @@ class NativeEngine:
 
     def sync(self):
         self._chk(self.lib.xtts_sync(self.h), "sync")
+
+    def timer_start(self):
+        """CUDA event on the engine stream (call with the engine idle)."""
+        self._chk(self.lib.xtts_device_timer(self.h, 0, None), "device_timer(start)")
+
+    def timer_stop_ms(self) -> float:
+        """Second event behind everything submitted so far; milliseconds on the device clock since timer_start()."""
+        ms = C.c_double(0.0)
+        self._chk(self.lib.xtts_device_timer(self.h, 1, C.byref(ms)), "device_timer(stop)")
+        return float(ms.value)
 
     def kernel_profile(self) -> Dict[str, dict]:
         """{family: {ms, flops, bytes, launches}} accumulated since option "profile" was switched on."""

@@ -271,14 +271,19 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, warm, steps):
+        """-> (seconds on the device clock, seconds of host wall clock, per-step results, wall span).  The device figure is
+        the distance between two CUDA events recorded on the engine's own stream: the first with the device idle (after the
+        barrier + synchronize), the second behind the last step's work."""
         for i in range(warm):
             fn(i)
         barrier()
         t0w = time.time(); t0 = time.perf_counter()
+        ne.timer_start()
         acc = [fn(warm + i) for i in range(steps)]
+        dt_ev = ne.timer_stop_ms() * 1e-3
         barrier()
         dt = time.perf_counter() - t0
-        return dt, acc, (t0w, time.time())
+        return dt_ev, dt, acc, (t0w, time.time())
 
     # ---- device-resident arm
     log(f"engine up: {n_chunks} chunks/GPU, {max_tok} tokens/chunk, precision {args.precision}")
@@ -296,12 +301,12 @@ def main():
     ne.set_option("reset_stats", 0)
     if sampler:
         sampler.start()
-    dt_dev, acc_dev, span = timed(device_step, 0, args.steps)
+    dt_dev, wall_dev, acc_dev, span = timed(device_step, 0, args.steps)
     clocks = sampler.stop(*span) if sampler else None
     st = ne.stats()
     samples_dev = sum(a[0] for a in acc_dev)
     tokens_dev = sum(a[1] for a in acc_dev)
-    log(f"device arm: {dt_dev:.2f}s for {args.steps} step(s); engine clocks: gpt {st.gpt_ms:.0f} ms, vocoder {st.vocoder_ms:.0f} ms, "
+    log(f"device arm: {dt_dev:.2f}s (CUDA events; host wall {wall_dev:.2f}s) for {args.steps} step(s); engine clocks: gpt {st.gpt_ms:.0f} ms, vocoder {st.vocoder_ms:.0f} ms, "
         f"{st.decode_steps} decode steps, {st.kernel_launches} kernels")
     # ---- kernel-family profile: one more identical step with a CUDA event on either side of every launch.  The decode
     # step is replayed from a graph that carries the events as event-record nodes (no host launch gap inside the bracket,
@@ -319,7 +324,7 @@ def main():
 
     # ---- end-to-end arm (public API, host buffers)
     ne.set_option("d2h_wav", 1)
-    dt_e2e, acc_e2e, _ = timed(e2e_step, 1, args.steps)
+    ev_e2e, dt_e2e, acc_e2e, _ = timed(e2e_step, 1, args.steps)      # e2e = host wall clock: tokenisation and the host copies count
     samples_e2e = sum(a[0] for a in acc_e2e)
     log(f"e2e arm: {dt_e2e:.2f}s for {args.steps} step(s)")
     h2d = sum(len(ids) * 4 for chunks in reqs_chunks for ids in chunks)
@@ -327,9 +332,9 @@ def main():
 
     # ---- max over ranks, aggregate over ranks
     if world > 1:
-        t = torch.tensor([dt_dev, dt_e2e], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dt_dev, dt_e2e, wall_dev], dtype=torch.float64, device="cuda")
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        dt_dev, dt_e2e = float(t[0]), float(t[1])
+        dt_dev, dt_e2e, wall_dev = float(t[0]), float(t[1]), float(t[2])
         s = torch.tensor([samples_dev, tokens_dev, samples_e2e], dtype=torch.float64, device="cuda")
         torch.distributed.all_reduce(s, op=torch.distributed.ReduceOp.SUM)
         samples_dev, tokens_dev, samples_e2e = float(s[0]), float(s[1]), float(s[2])
@@ -376,6 +381,17 @@ def main():
                  "fp32_tflops": dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] else None,
                  "families": fams})
 
+    # DRAM traffic of the dominant family, per launch, from the committed ncu capture (profiles/ncu_traffic.json)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom_name)
+    except Exception:
+        tr = None
+    if tr:
+        roof["traffic"] = tr["dram_bytes_per_launch"]
+        roof["traffic_detail"] = {"unit": "bytes per launch", "algorithmic_bytes_per_launch_at_capture": tr["algorithmic_bytes_per_launch_at_capture"],
+                                  "algorithmic_bytes_per_launch_this_run": dom["bytes"] / max(1, dom["launches"]),
+                                  "shape": tr["shape"], "note": tr["note"], "source": tr["source"]}
+
     cpu = cpu_reference_sample(dims, state, n_threads) if args.gpus == 1 else None
 
     line = {
@@ -389,7 +405,9 @@ def main():
                    "gpt_compute": "bf16 tcgen05 GEMM operands + bf16 KV, fp32 accumulate/residual/LN/softmax" if args.precision == "bf16" else "fp32",
                    "vocoder_compute": "fp16 tcgen05 implicit-GEMM convs (fp32 accumulate, fp32 residual stream)" if args.precision == "bf16" else "fp32",
                    "l2": "no explicit flush: per-step working set (0.76 GB weights + >5 GB KV + 0.4 GB vocoder activations) >> 126 MB L2",
-                   "timing": "host perf_counter bracketed by barrier + cuda synchronize (device idle on both sides); max over ranks",
+                   "timing": "CUDA events on the engine stream (first recorded with the device idle after barrier + synchronize, second "
+                             "behind the last step's work); max over ranks; e2e: host wall clock around the public API calls",
+                   "host_wall_ms_per_step": 1e3 * wall_dev / args.steps,
                    "engine_opts": args.engine_opt,
                    "decode_step": ("per layer: paged attention + one persistent chain kernel (out-proj, LN2, fc+gelu, down-proj, LN1, next QKV)"
                                    if args.decode_chain else f"one launch per GEMM/LayerNorm, {args.microbatches} concurrent row branches"),

@@ -137,6 +137,10 @@ int xtts_set_option(xtts_engine* e, const char* key, int64_t value);
 int xtts_get_stats(xtts_engine* e, xtts_stats* out);
 int xtts_sync(xtts_engine* e);   /* waits until no submitted work is pending */
 int xtts_get_kernel_profile(xtts_engine* e, xtts_kernel_profile* out);
+/* device-side stopwatch for bench.py: op 0 records a CUDA event on the engine's stream (call with the engine idle);
+ * op 1 records a second one behind all work submitted so far, waits for it and returns the elapsed milliseconds
+ * between the two in *ms.  No reference counterpart (the reference times with time.time(), two_phase_scheduler.py:139). */
+int xtts_device_timer(xtts_engine* e, int32_t op, double* ms);
 
 /* ---- synchronous single-stage entry points (parity tests; they serialise with the scheduler) ---- */
 /* HifiDecoder.forward (hifigan_decoder.py:776-802): latents [T,in_dim] -> wav [n_samples]. Returns n_samples
