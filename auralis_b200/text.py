@@ -7,7 +7,8 @@ sentencizer equivalent to spaCy's rule-based ``sentencizer`` for the scripts XTT
 
 Token ids: with a real ``tokenizer.json`` (HF `tokenizers`) in the GPT model directory the BPE of the
 reference is used (`XTTSTokenizerFast`, tokenizer.py:742-942) behind the per-language cleaners of `textnorm.py`
-(English numbers / abbreviations / symbols restated; other languages keep their digits — SURVEY §8f-1).  Without one (this build has no network)
+(abbreviation / symbol / number passes of all 15 cleaned languages pinned against the reference's functions; number
+words restated for en/es/fr/de/it/pt, digits kept elsewhere — SURVEY §8f-1).  Without one (this build has no network)
 ids are synthetic: ceil(chars/3.2) ids drawn uniformly from the text vocabulary, seeded by the chunk's
 hash — deterministic, same chunk -> same ids.
 """
@@ -106,7 +107,9 @@ class XTTSTokenizer:
         self.bos_token_id, self.eos_token_id = 0, 1          # synthetic stand-ins for [START]/[STOP]
         if tokenizer_file and os.path.exists(tokenizer_file):
             from tokenizers import Tokenizer
+            from tokenizers.pre_tokenizers import WhitespaceSplit
             self.tok = Tokenizer.from_file(tokenizer_file)
+            self.tok.pre_tokenizer = WhitespaceSplit()                           # tokenizer.py:763
             b, e = self.tok.token_to_id("[START]"), self.tok.token_to_id("[STOP]")
             if b is not None and e is not None:
                 self.bos_token_id, self.eos_token_id = b, e

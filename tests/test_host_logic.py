@@ -158,27 +158,3 @@ def test_tokenizer_with_real_vocab_file(tmp_path):
     ids = t.encode_chunk("Hello World", "en")
     assert ids[0] == 4 and 2 in ids and ids.count(7) == 3          # [en] h e l l o [SPACE] w o r l d
     assert t.batch_encode_with_split("hello world", "en") == [ids]
-
-
-def test_english_text_cleaners():
-    """textnorm.py restates the reference's multilingual_cleaners for English (tokenizer.py:681-719); number words
-    follow num2words' English conventions."""
-    from auralis_b200 import textnorm as T
-    assert T.cardinal_en(0) == "zero" and T.cardinal_en(21) == "twenty-one" and T.cardinal_en(110) == "one hundred and ten"
-    assert T.cardinal_en(1001) == "one thousand and one"
-    assert T.cardinal_en(1234) == "one thousand, two hundred and thirty-four"
-    assert T.cardinal_en(1200000) == "one million, two hundred thousand"
-    assert T.cardinal_en(1000001) == "one million and one"
-    assert T.ordinal_en(1) == "first" and T.ordinal_en(12) == "twelfth" and T.ordinal_en(20) == "twentieth"
-    assert T.ordinal_en(21) == "twenty-first" and T.ordinal_en(100) == "one hundredth" and T.ordinal_en(43) == "forty-third"
-    assert T.decimal_en("3.05") == "three point zero five"
-    assert T.currency_en(5.5, "USD") == "five dollars, fifty cents" and T.currency_en(1.0, "USD") == "one dollar"
-    assert T.currency_en(2.01, "GBP") == "two pounds, one penny" and T.currency_en(20.0, "EUR") == "twenty euros"
-    c = T.preprocess_text('Dr. Smith paid $5.50 for the 21st "copy", 1,234 in all & 3.5% more.', "en")
-    assert c == ("doctor smith paid five dollars, fifty cents for the twenty-first copy, one thousand, two hundred and "
-                 "thirty-four in all and three point five percent more.")
-    assert T.preprocess_text("Das  kostet 1.234 Euro", "de") == "das kostet 1234 euro"          # digits kept (open part of the row)
-    assert T.preprocess_text("ÇOK  İYİ", "tr") == "çok iyi"                                    # dotted capital İ mapped before lower()
-    assert T.format_for_bpe("Hello there", "en") == "[en]hello[SPACE]there"
-    assert T.format_for_bpe("你好", "zh-cn").startswith("[zh-cn]")
-    assert T.preprocess_text("MiXed   Case", "xx") == "mixed case"
