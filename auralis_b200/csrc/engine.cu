@@ -408,7 +408,11 @@ Engine::~Engine() {
     drop_graphs();
     for (auto& pr : pinned_pool) cudaFreeHost(pr.first);
     for (auto& pr : dev_pool) cudaFree(pr.first);
-    for (auto& kv : done_map) if (kv.second->wav_host) cudaFreeHost(kv.second->wav_host);
+    for (auto& kv : done_map) {                     // finished chunks nobody fetched
+        if (kv.second->wav_host) cudaFreeHost(kv.second->wav_host);
+        if (kv.second->wav_dev) cudaFree(kv.second->wav_dev);
+        if (kv.second->lat_dev) cudaFree(kv.second->lat_dev);
+    }
     if (h_finished) cudaFreeHost(h_finished);
     for (int i = 1; i < kMaxMicro; ++i) { if (st_mb[i]) cudaStreamDestroy(st_mb[i]); if (ev_join[i]) cudaEventDestroy(ev_join[i]); }
     if (ev_fork) cudaEventDestroy(ev_fork);

@@ -29,6 +29,7 @@ from .base import BaseAsyncTTSEngine, ConditioningConfig, register_model
 from .config import XTTSDims
 from .output import TTSOutput
 from .requests import TTSRequest
+from .speakers import SpeakerSlots, SpeakerSlotsFull
 from .text import XTTSTokenizer
 from .weights import load_model_dir
 
@@ -85,12 +86,10 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
         self.mel_bos_token_id = dims.gpt.start_audio_token
         self.mel_eos_token_id = dims.gpt.stop_audio_token
         self.max_speakers = max_speakers
-        self._spk_slots: Dict[str, int] = {}
-        self._spk_lru: List[str] = []
-        self._spk_lock = threading.Lock()
+        self._spk = SpeakerSlots(max_speakers)        # key -> native slot; pins slots referenced by chunks in flight
         self._next_id = 1
         self._id_lock = threading.Lock()
-        self._waiters: Dict[int, Tuple[asyncio.AbstractEventLoop, asyncio.Future]] = {}
+        self._waiters: Dict[int, Tuple[asyncio.AbstractEventLoop, asyncio.Future, int]] = {}
         self._wlock = threading.Lock()
         self._stop = False
         self._parked = False
@@ -111,19 +110,16 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
     def conditioning_config(self) -> ConditioningConfig:
         return ConditioningConfig(speaker_embeddings=True, gpt_like_decoder_conditioning=True)
 
-    def _alloc_speaker_slot(self, key: str) -> Tuple[int, bool]:
-        with self._spk_lock:
-            if key in self._spk_slots:
-                self._spk_lru.remove(key); self._spk_lru.append(key)
-                return self._spk_slots[key], True
-            if len(self._spk_slots) < self.max_speakers:
-                slot = len(self._spk_slots)
-            else:
-                victim = self._spk_lru.pop(0)
-                slot = self._spk_slots.pop(victim)
-            self._spk_slots[key] = slot
-            self._spk_lru.append(key)
-            return slot, False
+    async def _acquire_speaker(self, key: str, timeout_s: float = 120.0):
+        """SpeakerSlots.acquire, waiting (not failing) while every slot is pinned by chunks in flight."""
+        t0 = time.monotonic()
+        while True:
+            try:
+                return self._spk.acquire(key)
+            except SpeakerSlotsFull:
+                if time.monotonic() - t0 > timeout_s:
+                    raise
+                await asyncio.sleep(0.005)
 
     async def get_audio_conditioning(self, audio_reference, max_ref_length=30, gpt_cond_len=6, gpt_cond_chunk_len=6,
                                      librosa_trim_db=None, sound_norm_refs=False, load_sr=22050):
@@ -137,8 +133,8 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
             hk.update(p if isinstance(p, (bytes, bytearray)) else str(p).encode())
         hk.update(f"{max_ref_length}|{gpt_cond_len}|{gpt_cond_chunk_len}|{sound_norm_refs}".encode())
         key = hk.hexdigest()
-        slot, hit = self._alloc_speaker_slot(key)
-        if not hit:
+        slot, pending, owner = await self._acquire_speaker(key)
+        if owner:
             def work():
                 audios22 = []
                 for p in paths:
@@ -160,24 +156,49 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
                 self.native.condition(slot, full, _resample(audios22[0], load_sr, 16000), gpt_cond_len, gpt_cond_chunk_len)
                 c, _ = self.native.get_speaker(slot)
                 self.native.set_speaker(slot, c, np.mean(np.stack(gs), axis=0))
-            await asyncio.to_thread(work)
+            try:
+                await asyncio.to_thread(work)
+            except BaseException as e:
+                self._spk.failed(key, e if isinstance(e, Exception) else RuntimeError("conditioning cancelled"))
+                raise
+            self._spk.ready(key)
+        elif pending is not None:                      # another request is computing this speaker right now
+            await asyncio.wrap_future(pending)
         cond, g = self.native.get_speaker(slot)
-        return _SpeakerArray(cond[None], slot), _SpeakerArray(g.reshape(1, -1, 1), slot)
+        return _SpeakerArray(cond[None], slot, key), _SpeakerArray(g.reshape(1, -1, 1), slot, key)
 
     def register_speaker(self, cond_latents: np.ndarray, d_vector: np.ndarray) -> Tuple["_SpeakerArray", "_SpeakerArray"]:
-        """Pre-computed conditioning (the pair `prepare_for_streaming_generation` hands back, tts.py:91-105)."""
+        """Pre-computed conditioning (the pair `prepare_for_streaming_generation` hands back, tts.py:91-105).
+        Raises SpeakerSlotsFull when every slot is pinned by chunks in flight."""
         c = np.ascontiguousarray(cond_latents, np.float32).reshape(self.dims.gpt.n_cond_latents, self.dims.gpt.hidden)
         g = np.ascontiguousarray(d_vector, np.float32).reshape(-1)
         key = hashlib.sha256(c.tobytes() + g.tobytes()).hexdigest()
-        slot, hit = self._alloc_speaker_slot(key)
-        if not hit:
-            self.native.set_speaker(slot, c, g)
-        return _SpeakerArray(c[None], slot), _SpeakerArray(g.reshape(1, -1, 1), slot)
+        slot, pending, owner = self._spk.acquire(key)
+        if owner:
+            try:
+                self.native.set_speaker(slot, c, g)
+            except BaseException as e:
+                self._spk.failed(key, e if isinstance(e, Exception) else RuntimeError("set_speaker interrupted"))
+                raise
+            self._spk.ready(key)
+        elif pending is not None:
+            pending.result(timeout=120)
+        return _SpeakerArray(c[None], slot, key), _SpeakerArray(g.reshape(1, -1, 1), slot, key)
 
-    def _slot_of(self, cond, g) -> int:
-        if isinstance(cond, _SpeakerArray):
-            return cond.slot
-        return self.register_speaker(np.asarray(cond), np.asarray(g))[0].slot
+    async def _pin_speaker(self, cond, g, timeout_s: float = 120.0) -> int:
+        """Slot holding this conditioning pair, pinned for one chunk.  A pair whose slot was recycled since it was
+        handed out (LRU eviction) is uploaded again from the arrays instead of selecting another speaker's voice."""
+        t0 = time.monotonic()
+        while True:
+            key, slot = getattr(cond, "key", None), getattr(cond, "slot", None)
+            if key is not None and slot is not None and self._spk.pin(key, slot):
+                return slot
+            try:
+                cond, g = self.register_speaker(np.asarray(cond), np.asarray(g))
+            except SpeakerSlotsFull:
+                if time.monotonic() - t0 > timeout_s:
+                    raise
+                await asyncio.sleep(0.005)
 
     def prepare_text_tokens(self, text: str, language: str) -> List[List[int]]:
         """XTTSv2.py:506-543: per chunk [bos] + ids + [eos]."""
@@ -188,7 +209,6 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
         if gpt_cond_latent is None or speaker_embeddings is None:
             gpt_cond_latent, speaker_embeddings = await self.get_audio_conditioning(
                 request.speaker_files, request.max_ref_length, request.gpt_cond_len, request.gpt_cond_chunk_len)
-        slot = self._slot_of(gpt_cond_latent, speaker_embeddings)
         token_lists = self.prepare_text_tokens(request.text, request.language)
         generators, request_ids = [], []
         base_seed = request.seed if request.seed is not None else int.from_bytes(hashlib.sha256(request.request_id.encode()).digest()[:6], "little")
@@ -198,24 +218,28 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
                                  max_tokens=self.dims.gpt.max_audio_tokens, stop_token=self.mel_eos_token_id,
                                  seed=base_seed, seq_seed=seq_index, vocode=True, priority=seq_index)
             rid = f"{request.request_id}_{seq_index}"
-            generators.append(self._chunk_generator(rid, ids, slot, sp))
+            generators.append(self._chunk_generator(rid, ids, gpt_cond_latent, speaker_embeddings, sp))
             request_ids.append(rid)
         return generators, request_ids, speaker_embeddings, [gpt_cond_latent] * len(generators)
 
-    async def _chunk_generator(self, rid: str, ids: List[int], slot: int, sp: native.Sampling):
-        """Lazy like vLLM's generator (App. B.15): the chunk is submitted at the first __anext__."""
+    async def _chunk_generator(self, rid: str, ids: List[int], cond, g, sp: native.Sampling):
+        """Lazy like vLLM's generator (App. B.15): the chunk is submitted at the first __anext__.  The speaker slot is
+        pinned from submission until the native completion arrives (released by the poller thread), so it cannot be
+        recycled under a queued or running chunk even if the awaiting coroutine is cancelled."""
         loop = asyncio.get_running_loop()
         fut = loop.create_future()
+        slot = await self._pin_speaker(cond, g)
         with self._id_lock:
             sid = self._next_id
             self._next_id += 1
         with self._wlock:
-            self._waiters[sid] = (loop, fut)
+            self._waiters[sid] = (loop, fut, slot)
         try:
             self.native.submit(sid, ids, slot, sp)
-        except Exception:
+        except BaseException:
             with self._wlock:
                 self._waiters.pop(sid, None)
+            self._spk.unpin(slot)
             raise
         result, toks, wav = await fut
         yield ChunkOutput(rid, toks, wav, result)
@@ -279,7 +303,8 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
                 payload, err = None, e
             if w is None:
                 continue
-            loop, fut = w
+            loop, fut, slot = w
+            self._spk.unpin(slot)                   # the native engine is done with this chunk's speaker slot
 
             def deliver(fut=fut, payload=payload, err=err):
                 if fut.cancelled():
@@ -292,15 +317,18 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
 
 
 class _SpeakerArray(np.ndarray):
-    """numpy array that remembers which native speaker slot it lives in."""
+    """numpy array that remembers which native speaker slot it was uploaded to and under which cache key (the pair is
+    re-validated before every use: a recycled slot is detected and the array uploaded again)."""
 
-    def __new__(cls, arr, slot):
+    def __new__(cls, arr, slot, key=None):
         obj = np.asarray(arr).view(cls)
         obj.slot = slot
+        obj.key = key
         return obj
 
     def __array_finalize__(self, obj):
         self.slot = getattr(obj, "slot", None)
+        self.key = getattr(obj, "key", None)
 
 
 def _resample(a: np.ndarray, sr: int, new_sr: int) -> np.ndarray:

@@ -158,3 +158,72 @@ def test_tokenizer_with_real_vocab_file(tmp_path):
     ids = t.encode_chunk("Hello World", "en")
     assert ids[0] == 4 and 2 in ids and ids.count(7) == 3          # [en] h e l l o [SPACE] w o r l d
     assert t.batch_encode_with_split("hello world", "en") == [ids]
+
+
+def test_speaker_slots_pin_evict_and_pending():
+    """speakers.py: LRU eviction never takes a pinned or still-computing slot; stale (key, slot) pairs are detected."""
+    from auralis_b200.speakers import SpeakerSlots, SpeakerSlotsFull
+    t = SpeakerSlots(2)
+    s_a, f_a, own = t.acquire("a")
+    assert own and f_a is not None and not t.holds("a", s_a)          # not valid until the owner says so
+    s_a2, f_a2, own2 = t.acquire("a")
+    assert (s_a2, own2) == (s_a, False) and f_a2 is f_a                # a second request waits on the same future
+    t.ready("a")
+    assert f_a.result(timeout=1) is True and t.holds("a", s_a)
+    assert t.acquire("a") == (s_a, None, False)                       # plain hit
+    s_b, _, _ = t.acquire("b"); t.ready("b")
+    assert s_b != s_a and t.pin("a", s_a) and t.pinned(s_a) == 1
+    s_c, _, own_c = t.acquire("c"); t.ready("c")                       # evicts b (a is pinned although older)
+    assert own_c and s_c == s_b and not t.holds("b", s_b) and t.holds("a", s_a)
+    assert not t.pin("b", s_b)                                         # stale pair: caller must re-register
+    assert t.pin("c", s_c)
+    with pytest.raises(SpeakerSlotsFull):
+        t.acquire("d")                                                 # both slots pinned
+    t.unpin(s_c)
+    s_d, f_d, _ = t.acquire("d")                                       # c evicted; d is still being computed ...
+    assert s_d == s_c
+    t.unpin(s_a)
+    s_e, _, _ = t.acquire("e")                                         # ... so the only candidate is a
+    assert s_e == s_a
+    t.failed("d", RuntimeError("boom"))                                # owner failed: entry forgotten, waiters see the error
+    with pytest.raises(RuntimeError):
+        f_d.result(timeout=1)
+    assert len(t) == 1 and t.acquire("d")[2] is True
+
+
+def test_engine_repins_recycled_speaker_slot():
+    """engine.py: a conditioning pair whose native slot was recycled is uploaded again instead of selecting the other
+    speaker's voice; the slot stays pinned until the native completion is seen."""
+    import asyncio
+    from auralis_b200.config import XTTSDims
+    from auralis_b200.engine import XTTSv2Engine
+    from auralis_b200.speakers import SpeakerSlots
+
+    class FakeNative:
+        def __init__(self):
+            self.slots = {}
+
+        def set_speaker(self, slot, c, g):
+            self.slots[slot] = (c.copy(), g.copy())
+
+    dims = XTTSDims.small()
+    eng = object.__new__(XTTSv2Engine)
+    eng.dims, eng.native, eng._spk = dims, FakeNative(), SpeakerSlots(1)
+    n, h, d = dims.gpt.n_cond_latents, dims.gpt.hidden, dims.voc.d_vector
+    ca, ga = np.full((1, n, h), 1.0, np.float32), np.full((1, d, 1), 1.0, np.float32)
+    cb, gb = np.full((1, n, h), 2.0, np.float32), np.full((1, d, 1), 2.0, np.float32)
+    A = eng.register_speaker(ca, ga)
+    assert A[0].slot == 0 and A[0].key == A[1].key
+    B = eng.register_speaker(cb, gb)                                   # one slot only: A is evicted
+    assert B[0].slot == 0 and eng.native.slots[0][0].flat[0] == 2.0
+
+    async def go():
+        slot = await eng._pin_speaker(*A)                              # stale pair -> uploaded again
+        assert slot == 0 and eng.native.slots[0][0].flat[0] == 1.0 and eng._spk.pinned(0) == 1
+        # B cannot take the slot while A's chunk is in flight; it gets it once the completion unpins
+        task = asyncio.ensure_future(eng._pin_speaker(*B, timeout_s=5))
+        await asyncio.sleep(0.05)
+        assert not task.done() and eng.native.slots[0][0].flat[0] == 1.0
+        eng._spk.unpin(0)
+        assert await task == 0 and eng.native.slots[0][0].flat[0] == 2.0
+    asyncio.new_event_loop().run_until_complete(go())
