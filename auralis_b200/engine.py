@@ -133,38 +133,41 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
             hk.update(p if isinstance(p, (bytes, bytearray)) else str(p).encode())
         hk.update(f"{max_ref_length}|{gpt_cond_len}|{gpt_cond_chunk_len}|{sound_norm_refs}".encode())
         key = hk.hexdigest()
-        slot, pending, owner = await self._acquire_speaker(key)
-        if owner:
-            def work():
-                audios22 = []
-                for p in paths:
-                    a = load_audio(p, load_sr)[: load_sr * max_ref_length]
-                    if sound_norm_refs:
-                        a = (a / np.abs(a).max()) * 0.75
-                    audios22.append(a)
-                if len(audios22) == 1:
-                    self.native.condition(slot, audios22[0], _resample(audios22[0], load_sr, 16000), gpt_cond_len,
-                                          gpt_cond_chunk_len)
-                    return
-                # several references: d-vector per file, averaged; GPT latents on the concatenation
-                # (XTTSv2.py:446-466)
-                gs = []
-                for a in audios22:
-                    self.native.condition(slot, a, _resample(a, load_sr, 16000), gpt_cond_len, gpt_cond_chunk_len)
-                    gs.append(self.native.get_speaker(slot)[1])
-                full = np.concatenate(audios22)
-                self.native.condition(slot, full, _resample(audios22[0], load_sr, 16000), gpt_cond_len, gpt_cond_chunk_len)
-                c, _ = self.native.get_speaker(slot)
-                self.native.set_speaker(slot, c, np.mean(np.stack(gs), axis=0))
-            try:
-                await asyncio.to_thread(work)
-            except BaseException as e:
-                self._spk.failed(key, e if isinstance(e, Exception) else RuntimeError("conditioning cancelled"))
-                raise
-            self._spk.ready(key)
-        elif pending is not None:                      # another request is computing this speaker right now
-            await asyncio.wrap_future(pending)
-        cond, g = self.native.get_speaker(slot)
+        while True:
+            slot, pending, owner = await self._acquire_speaker(key)
+            if owner:
+                def work():
+                    audios22 = []
+                    for p in paths:
+                        a = load_audio(p, load_sr)[: load_sr * max_ref_length]
+                        if sound_norm_refs:
+                            a = (a / np.abs(a).max()) * 0.75
+                        audios22.append(a)
+                    if len(audios22) == 1:
+                        self.native.condition(slot, audios22[0], _resample(audios22[0], load_sr, 16000), gpt_cond_len,
+                                              gpt_cond_chunk_len)
+                        return
+                    # several references: d-vector per file, averaged; GPT latents on the concatenation
+                    # (XTTSv2.py:446-466)
+                    gs = []
+                    for a in audios22:
+                        self.native.condition(slot, a, _resample(a, load_sr, 16000), gpt_cond_len, gpt_cond_chunk_len)
+                        gs.append(self.native.get_speaker(slot)[1])
+                    full = np.concatenate(audios22)
+                    self.native.condition(slot, full, _resample(audios22[0], load_sr, 16000), gpt_cond_len, gpt_cond_chunk_len)
+                    c, _ = self.native.get_speaker(slot)
+                    self.native.set_speaker(slot, c, np.mean(np.stack(gs), axis=0))
+                try:
+                    await asyncio.to_thread(work)
+                except BaseException as e:
+                    self._spk.failed(key, e if isinstance(e, Exception) else RuntimeError("conditioning cancelled"))
+                    raise
+                self._spk.ready(key)
+            elif pending is not None:                      # another request is computing this speaker right now
+                await asyncio.wrap_future(pending)
+            cond, g = self.native.get_speaker(slot)
+            if self._spk.holds(key, slot):              # not recycled between the wake-up and the read-back
+                break
         return _SpeakerArray(cond[None], slot, key), _SpeakerArray(g.reshape(1, -1, 1), slot, key)
 
     def register_speaker(self, cond_latents: np.ndarray, d_vector: np.ndarray) -> Tuple["_SpeakerArray", "_SpeakerArray"]:

@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--microbatches", type=int, default=2, help="concurrent decode branches per step (engine option; unfused decode only)")
     ap.add_argument("--engine-opt", action="append", default=[], help="extra engine option key=value (repeatable)")
     ap.add_argument("--decode-chain", type=int, default=0, help="1 = fused persistent per-layer chain kernel in the decode step")
+    ap.add_argument("--sweep", action="store_true", help="option sweeps only: skip the e2e arm and the CPU baseline (the line says so; not a headline run)")
     ap.add_argument("--small", action="store_true", help="tiny geometry (plumbing check only; not a valid bench number)")
     args = ap.parse_args()
 
@@ -324,9 +325,12 @@ def main():
 
     # ---- end-to-end arm (public API, host buffers)
     ne.set_option("d2h_wav", 1)
-    ev_e2e, dt_e2e, acc_e2e, _ = timed(e2e_step, 1, args.steps)      # e2e = host wall clock: tokenisation and the host copies count
-    samples_e2e = sum(a[0] for a in acc_e2e)
-    log(f"e2e arm: {dt_e2e:.2f}s for {args.steps} step(s)")
+    if args.sweep:
+        ev_e2e, dt_e2e, acc_e2e, samples_e2e = 0.0, float("nan"), [], 0
+    else:
+        ev_e2e, dt_e2e, acc_e2e, _ = timed(e2e_step, 1, args.steps)      # e2e = host wall clock: tokenisation and the host copies count
+        samples_e2e = sum(a[0] for a in acc_e2e)
+        log(f"e2e arm: {dt_e2e:.2f}s for {args.steps} step(s)")
     h2d = sum(len(ids) * 4 for chunks in reqs_chunks for ids in chunks)
     d2h = samples_e2e // max(1, args.steps) * 4 + n_chunks * max_tok * 4
 
@@ -346,7 +350,7 @@ def main():
 
     audio_s_dev = samples_dev / 24000.0
     value = audio_s_dev / dt_dev
-    e2e_value = (samples_e2e / 24000.0) / dt_e2e
+    e2e_value = None if args.sweep else (samples_e2e / 24000.0) / dt_e2e
 
     # ---- roofline of the dominant kernel family (device time by CUDA events inside the timed region)
     peaks = {}
@@ -392,7 +396,7 @@ def main():
                                   "algorithmic_bytes_per_launch_this_run": dom["bytes"] / max(1, dom["launches"]),
                                   "shape": tr["shape"], "note": tr["note"], "source": tr["source"]}
 
-    cpu = cpu_reference_sample(dims, state, n_threads) if args.gpus == 1 else None
+    cpu = cpu_reference_sample(dims, state, n_threads) if (args.gpus == 1 and not args.sweep) else None
 
     line = {
         "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
@@ -415,12 +419,15 @@ def main():
                    "e2e_speakers": "4 reference wavs conditioned on the GPU before the timed region (per-speaker cache, as prepare_for_streaming_generation)"},
         "gpt_tokens_per_s": tokens_dev / dt_dev, "rtf": 1.0 / value,
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "api": "TTS.generate_speech_batch([TTSRequest(text, speaker_files=wav bytes)])", "ms_per_step": 1e3 * dt_e2e / args.steps},
+                "api": "TTS.generate_speech_batch([TTSRequest(text, speaker_files=wav bytes)])",
+                "ms_per_step": None if args.sweep else 1e3 * dt_e2e / args.steps},
         "gpu_launches": int(st.kernel_launches),
         "clocks": clocks, "roofline": roof,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if args.sweep:
+        line["sweep"] = "option sweep: e2e arm and CPU baseline skipped — not a headline run"
     print(json.dumps(line), flush=True)
     loop.run_until_complete(tts.shutdown())
     if world > 1:

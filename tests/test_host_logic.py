@@ -227,3 +227,142 @@ def test_engine_repins_recycled_speaker_slot():
         eng._spk.unpin(0)
         assert await task == 0 and eng.native.slots[0][0].flat[0] == 2.0
     asyncio.new_event_loop().run_until_complete(go())
+
+
+class _FakeNativeEngine:
+    """Stands in for native.NativeEngine: same methods, a worker thread that 'synthesises' each chunk as a waveform
+    filled with (speaker value at submission time) — so a voice swap or an unpinned slot shows up in the audio."""
+
+    def __init__(self, dims, max_speakers, delay=0.01, fail_ids=()):
+        import queue
+        import threading
+        self.dims, self.delay, self.fail_ids = dims, delay, set(fail_ids)
+        self.spk, self.q, self.done = {}, queue.Queue(), queue.Queue()
+        self.results, self.closed, self.cond_calls = {}, False, 0
+        self.lock = threading.Lock()
+        self.lib = type("L", (), {"xtts_last_error": staticmethod(lambda: b"fake failure")})()
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        while not self.closed:
+            try:
+                sid, ids, slot = self.q.get(timeout=0.05)
+            except Exception:
+                continue
+            time.sleep(self.delay)
+            with self.lock:
+                v = float(self.spk[slot][1].flat[0])          # the slot's CURRENT contents, like the real engine
+            self.results[sid] = (np.arange(len(ids), dtype=np.int32), np.full(8, v, np.float32))
+            from auralis_b200.native import XttsResult
+            r = XttsResult()
+            r.seq_id, r.status, r.n_tokens, r.n_samples = sid, (-2 if sid in self.fail_ids else 0), len(ids), 8
+            self.done.put(r)
+
+    def condition(self, slot, wav22, wav16, cond_len=30, chunk_len=4):
+        time.sleep(0.02)
+        self.cond_calls += 1
+        v = float(np.round(np.abs(wav22).mean() * 1000))
+        n, h, d = self.dims.gpt.n_cond_latents, self.dims.gpt.hidden, self.dims.voc.d_vector
+        with self.lock:
+            self.spk[slot] = (np.full((n, h), v, np.float32), np.full((d,), v, np.float32))
+
+    def set_speaker(self, slot, c, g):
+        with self.lock:
+            self.spk[slot] = (np.array(c, np.float32).reshape(self.dims.gpt.n_cond_latents, -1), np.array(g, np.float32).reshape(-1))
+
+    def get_speaker(self, slot):
+        with self.lock:
+            c, g = self.spk[slot]
+            return c.copy(), g.copy()
+
+    def submit(self, sid, ids, slot, sp):
+        self.q.put((sid, list(ids), slot))
+
+    def poll(self, timeout_ms=50):
+        try:
+            return self.done.get(timeout=timeout_ms / 1000.0)
+        except Exception:
+            return None
+
+    def fetch(self, r, want_wav=True, want_latents=False):
+        toks, wav = self.results.pop(r.seq_id)
+        return toks, wav, None
+
+    def close(self):
+        self.closed = True
+
+
+def _host_engine(max_speakers=2, **kw):
+    """The real XTTSv2Engine host code (engine.py) over the fake native layer."""
+    import threading
+    from auralis_b200.config import XTTSDims
+    from auralis_b200.engine import XTTSv2Engine
+    from auralis_b200.speakers import SpeakerSlots
+    dims = XTTSDims.small()
+    eng = object.__new__(XTTSv2Engine)
+    eng.dims, eng.precision, eng.max_concurrency, eng.max_speakers = dims, "fp32", 8, max_speakers
+    eng.native = _FakeNativeEngine(dims, max_speakers, **kw)
+    eng.tokenizer = XTTSTokenizer(dims.gpt.n_text_tokens, dims.gpt.max_text_tokens)
+    eng.mel_bos_token_id, eng.mel_eos_token_id = dims.gpt.start_audio_token, dims.gpt.stop_audio_token
+    eng._spk = SpeakerSlots(max_speakers)
+    eng._next_id, eng._id_lock, eng._waiters, eng._wlock = 1, threading.Lock(), {}, threading.Lock()
+    eng._stop = eng._parked = eng._paused = False
+    eng._poller = threading.Thread(target=eng._poll_loop, daemon=True)
+    eng._poller.start()
+    return eng
+
+
+def _wav(level):
+    import io
+    import wave
+    buf = io.BytesIO()
+    with wave.open(buf, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(22050)
+        w.writeframes((np.full(2205, level * 32767.0)).astype(np.int16).tobytes())
+    return buf.getvalue()
+
+
+def test_engine_host_path_many_speakers_few_slots():
+    """6 requests x 3 speakers through TTS -> XTTSv2Engine -> (fake) native with only 2 speaker slots: every request
+    must come back in its own speaker's voice, the same reference is conditioned once even when requested concurrently,
+    and no slot stays pinned afterwards."""
+    eng = _host_engine(max_speakers=2)
+    tts = TTS(scheduler_max_concurrency=8).from_engine(eng)
+    levels = [0.1, 0.2, 0.3]
+    spk = [_wav(v) for v in levels]
+    text = ("Sentence number one is here. " * 12).strip()              # several chunks per request
+    reqs = [TTSRequest(text=text, speaker_files=spk[i % 3], language="en") for i in range(6)]
+    outs = tts.generate_speech_batch(reqs)
+    for i, o in enumerate(outs):
+        want = float(np.round(levels[i % 3] * 1000))
+        assert o.array.size >= 16 and np.all(np.abs(o.array - want) <= 1.0), (i, o.array[:4], want)
+    assert eng.native.cond_calls <= 5                                   # 3 speakers (+ re-conditioning after eviction), not 6
+    assert all(eng._spk.pinned(s) == 0 for s in range(2)) and not eng._waiters
+    # a pair handed out earlier keeps working after its slot was recycled by two other speakers
+    c0, g0 = tts.loop.run_until_complete(eng.get_audio_conditioning(spk[0]))
+    for k in (1, 2):
+        tts.loop.run_until_complete(eng.get_audio_conditioning(spk[k]))
+    assert not eng._spk.holds(c0.key, c0.slot)
+    fn = partial_ctx(eng, c0, g0)
+    out = tts.generate_speech(TTSRequest(text="short one", speaker_files=spk[0], language="en", context_partial_function=fn))
+    assert np.all(np.abs(out.array - 100.0) <= 1.0)
+    tts.loop.run_until_complete(tts.shutdown())
+
+
+def partial_ctx(eng, cond, g):
+    from functools import partial
+    return partial(eng.get_generation_context, gpt_cond_latent=cond, speaker_embeddings=g)
+
+
+def test_engine_host_path_native_failure_propagates_and_unpins():
+    eng = _host_engine(max_speakers=2, fail_ids={2})
+    tts = TTS(scheduler_max_concurrency=8).from_engine(eng)
+    text = ("Sentence number one is here. " * 12).strip()
+    with pytest.raises(Exception, match="failed"):
+        tts.generate_speech(TTSRequest(text=text, speaker_files=_wav(0.5), language="en"))
+    deadline = time.time() + 2.0
+    while time.time() < deadline and (eng._waiters or any(eng._spk.pinned(s) for s in range(2))):
+        time.sleep(0.01)                                                # the other chunks finish in the background
+    assert not eng._waiters and all(eng._spk.pinned(s) == 0 for s in range(2))
+    tts.loop.run_until_complete(tts.shutdown())
