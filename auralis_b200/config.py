@@ -117,6 +117,40 @@ class XTTSDims:
                      cond_blocks=2, perceiver_depth=1, perceiver_heads=2)
         return XTTSDims(g, v, c)
 
+    @staticmethod
+    def from_reference_configs(core_cfg: dict, gpt_cfg: dict | None = None) -> "XTTSDims":
+        """Geometry from the two config.json files the reference's converter writes
+        (`utils/checkpoint_converter.py:117-223`: `core_xttsv2/config.json` and `gpt/config.json`; the core file also
+        embeds the GPT one under "gpt_config").  Keys the files do not carry keep the class defaults, exactly like the
+        reference's XTTSConfig / XTTSGPTConfig (`config/xttsv2_config.py:237-301`, `config/xttsv2_gpt_config.py:133-229`);
+        the HiFi-GAN layout is not configurable there either (`hifigan_decoder.py:698-723`)."""
+        g = dict(core_cfg.get("gpt_config") or {})
+        g.update(gpt_cfg or {})
+        d = GPTDims()
+        gd = GPTDims(
+            hidden=int(g.get("hidden_size", d.hidden)), layers=int(g.get("num_hidden_layers", d.layers)),
+            heads=int(g.get("num_attention_heads", d.heads)), ff=int(g.get("n_inner", 4 * int(g.get("hidden_size", d.hidden)))),
+            n_text_tokens=int(g.get("number_text_tokens", g.get("vocab_size", d.n_text_tokens))),
+            n_audio_tokens=int(g.get("num_audio_tokens", d.n_audio_tokens)),
+            start_audio_token=int(g.get("start_audio_token", d.start_audio_token)),
+            stop_audio_token=int(g.get("stop_audio_token", d.stop_audio_token)),
+            max_audio_tokens=int(g.get("max_audio_tokens", d.max_audio_tokens)),
+            max_text_tokens=int(g.get("max_text_tokens", d.max_text_tokens)),
+            ln_eps=float(g.get("layer_norm_epsilon", d.ln_eps)), activation=str(g.get("activation_function", d.activation)))
+        if gd.hidden != gd.heads * 64:
+            raise ValueError(f"hidden_size {gd.hidden} / num_attention_heads {gd.heads}: the kernels need 64-wide heads")
+        if gd.activation != "gelu_new":
+            raise ValueError(f"activation_function {gd.activation!r} is not supported (gelu_new only)")
+        v = VocoderDims()
+        ac = core_cfg.get("audio_config") or {}
+        vd = VocoderDims(
+            in_dim=int(core_cfg.get("decoder_input_dim", gd.hidden)), d_vector=int(core_cfg.get("d_vector_dim", v.d_vector)),
+            input_sample_rate=int(core_cfg.get("input_sample_rate", ac.get("sample_rate", v.input_sample_rate))),
+            output_sample_rate=int(core_cfg.get("output_sample_rate", ac.get("output_sample_rate", v.output_sample_rate))),
+            output_hop_length=int(core_cfg.get("output_hop_length", ac.get("hop_length", v.output_hop_length))),
+            code_stride=int(core_cfg.get("gpt_code_stride_len", v.code_stride)))
+        return XTTSDims(gd, vd, CondDims(spk_proj=vd.d_vector))
+
     def to_json(self) -> dict:
         return asdict(self)
 

@@ -248,12 +248,53 @@ def save_model_dir(path: str, dims: XTTSDims, gpt_state: State, core_state: Stat
 
 
 def load_model_dir(path: str, gpt_model: str | None = None) -> Tuple[XTTSDims, State, State]:
+    """Reads a model directory in either layout:
+      * the reference converter's (`utils/checkpoint_converter.py:286-334`): `path` = `.../core_xttsv2` holding
+        `config.json` + `xtts-v2.safetensors`, `gpt_model` = `.../gpt` holding `config.json` + `gpt2_model.safetensors`
+        (what `TTS().from_pretrained("AstraMindAI/xttsv2", gpt_model="AstraMindAI/xtts2-gpt")` resolves to);
+      * this package's own (`save_model_dir`): one directory with a `gpt/` sub-directory and the geometry under "b200_dims".
+    Tensor names are the converter's in both (`checkpoint_converter.py:225-284`); shapes are checked against the geometry."""
     from safetensors.torch import load_file
     with open(os.path.join(path, "config.json")) as f:
         cfg = json.load(f)
-    dims = XTTSDims.from_json(cfg["b200_dims"]) if "b200_dims" in cfg else XTTSDims.full()
-    core = load_file(os.path.join(path, "xtts-v2.safetensors"))
     gdir = gpt_model if gpt_model is not None else os.path.join(path, "gpt")
     gfile = gdir if gdir.endswith(".safetensors") else os.path.join(gdir, "gpt2_model.safetensors")
-    gpt = load_file(gfile)
-    return dims, {k: v.float() for k, v in gpt.items()}, {k: v.float() for k, v in core.items()}
+    if "b200_dims" in cfg:
+        dims = XTTSDims.from_json(cfg["b200_dims"])
+    else:
+        gcfg = None
+        gcfg_path = os.path.join(os.path.dirname(gfile), "config.json")
+        if os.path.exists(gcfg_path):
+            with open(gcfg_path) as f:
+                gcfg = json.load(f)
+        dims = XTTSDims.from_reference_configs(cfg, gcfg)
+    core = {k: v.float() for k, v in load_file(os.path.join(path, "xtts-v2.safetensors")).items()}
+    gpt = {k: v.float() for k, v in load_file(gfile).items()}
+    check_state_shapes(dims, gpt, core)
+    return dims, gpt, core
+
+
+def check_state_shapes(dims: XTTSDims, gpt: State, core: State) -> None:
+    """Fails with the offending tensor's name when a checkpoint does not match the geometry of its config
+    (the native loader would otherwise report a bare shape mismatch much later)."""
+    g = dims.gpt
+    want = {
+        ("gpt", "gpt.wte.weight"): (g.n_audio_tokens, g.hidden),
+        ("gpt", "mel_head.weight"): (g.n_audio_tokens, g.hidden),
+        ("gpt", "gpt.h.0.attn.c_attn.weight"): (g.hidden, 3 * g.hidden),
+        ("gpt", f"gpt.h.{g.layers - 1}.mlp.c_fc.weight"): (g.hidden, g.ff),
+        ("gpt", "final_norm.weight"): (g.hidden,),
+        ("core", "text_embedding.weight"): (g.n_text_tokens, g.hidden),
+    }
+    for (which, name), shape in want.items():
+        st = gpt if which == "gpt" else core
+        if name not in st:
+            raise KeyError(f"{which} checkpoint has no tensor {name!r}")
+        if tuple(st[name].shape) != tuple(shape):
+            raise ValueError(f"{name}: checkpoint shape {tuple(st[name].shape)} != {tuple(shape)} implied by config.json")
+    if f"gpt.h.{g.layers}.ln_1.weight" in gpt:
+        raise ValueError(f"checkpoint has more than num_hidden_layers = {g.layers} GPT layers")
+    if gpt["gpt.wpe.emb.weight"].shape[0] < g.max_audio_tokens + 1:
+        raise ValueError("gpt.wpe.emb.weight has fewer rows than max_audio_tokens + 1")
+    if core["text_pos_embedding.emb.weight"].shape[0] < g.max_text_tokens + 2:
+        raise ValueError("text_pos_embedding.emb.weight has fewer rows than max_text_tokens + 2")
