@@ -1280,10 +1280,10 @@ void Engine::loop() {
             release_slot(*s); s->t_done = now_s();
             retire(s);
         };
+        std::vector<std::shared_ptr<Sequence>> fresh_sp;      // admitted this iteration (outside the try: see the catch)
         try {
             // ---- admission (continuous batching): fill free slots, whole prompts, within the row budget
             std::vector<Sequence*> fresh;
-            std::vector<std::shared_ptr<Sequence>> fresh_sp;
             int rows = 0;
             while (!hold_admission.load() && !waiting.empty() && !free_slots.empty()) {
                 auto s = waiting.front();
@@ -1305,6 +1305,7 @@ void Engine::loop() {
             if (!fresh.empty()) {
                 prefill(fresh);
                 for (auto& s : fresh_sp) running.push_back(s);
+                fresh_sp.clear();
                 // a sequence may already be finished after its first token (max_tokens == 1 / instant stop)
                 d_finished.download(h_finished, NSLOT, st);
                 CUDA_CHECK(cudaStreamSynchronize(st));
@@ -1341,7 +1342,9 @@ void Engine::loop() {
                 }
             }
         } catch (const std::exception& ex) {
-            // a failure inside a batched step fails every sequence that was part of it
+            // a failure inside a batched step fails every sequence that was part of it — including the ones admitted
+            // in this iteration whose prefill threw before they reached `running`
+            for (auto& s : fresh_sp) fail(s, XTTS_ERR_CUDA, ex.what());
             for (auto& s : running) fail(s, XTTS_ERR_CUDA, ex.what());
             running.clear();
         }
