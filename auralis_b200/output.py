@@ -106,6 +106,68 @@ class TTSOutput:
         y = librosa.istft(librosa.phase_vocoder(D, rate=speed_factor, hop_length=512), hop_length=512)
         return TTSOutput(array=librosa.util.normalize(y, norm=np.inf), sample_rate=self.sample_rate)
 
+    def get_info(self):
+        """output.py:248-256: (number of samples, sample rate, duration in seconds)."""
+        n = len(self.array)
+        return n, self.sample_rate, n / self.sample_rate
+
+    @classmethod
+    def from_tensor(cls, tensor, sample_rate: int = 24000) -> "TTSOutput":
+        """output.py:258-272."""
+        return cls(array=tensor.squeeze().cpu().numpy(), sample_rate=sample_rate)
+
+    @classmethod
+    def from_file(cls, filename: Union[str, Path]) -> "TTSOutput":
+        """output.py:274-285.  RIFF/WAV through the standard library (the reference's torchaudio.load needs a codec
+        backend that this image does not ship); other containers go through torchaudio when it can load them."""
+        try:
+            with wave.open(str(filename), "rb") as w:
+                nch, sw, sr, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
+                raw = w.readframes(n)
+        except wave.Error:
+            import torchaudio
+            wav, sr = torchaudio.load(str(filename))
+            return cls.from_tensor(wav, sr)
+        if sw == 2:
+            a = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+        elif sw == 4:
+            a = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
+        elif sw == 1:
+            a = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+        else:
+            raise ValueError(f"unsupported WAV sample width {sw}")
+        a = a.reshape(-1, nch)
+        return cls(array=(a[:, 0] if nch == 1 else a.T).copy(), sample_rate=sr)
+
+    def play(self) -> None:
+        """output.py:287-303 (needs the optional `sounddevice` package, like the reference)."""
+        try:
+            import sounddevice as sd
+        except ImportError as e:
+            raise RuntimeError("play() needs the optional sounddevice package") from e
+        sd.play(np.clip(np.asarray(self.array, np.float32), -1.0, 1.0), self.sample_rate, blocksize=2048)
+        sd.wait()
+
+    def display(self):
+        """output.py:305-319: IPython audio widget, None outside a notebook."""
+        try:
+            from IPython.display import Audio, display
+            widget = Audio(self.to_bytes(format="wav"), rate=self.sample_rate, autoplay=False)
+            display(widget)
+            return widget
+        except Exception as e:      # noqa: BLE001 — same behaviour as the reference: report and fall back
+            print(f"Could not display audio widget: {e}")
+            print("Try using .play() method instead")
+            return None
+
+    def preview(self) -> None:
+        """output.py:321-330."""
+        try:
+            if self.display() is None:
+                self.play()
+        except Exception as e:      # noqa: BLE001
+            print(f"Error playing audio: {e}")
+
     @property
     def duration_s(self) -> float:
         return len(self.array) / float(self.sample_rate)

@@ -33,6 +33,21 @@ def test_output_combine_and_bytes():
     d = TTSOutput(array=pcm)                                   # bytes input: int16 -> float, 100-sample fade-in
     assert d.array.dtype == np.float32 and d.array[0] == 0.0
     assert c.resample(12000).array.shape[0] in (7, 8)
+    assert c.get_info() == (15, 24000, 15 / 24000)                 # output.py:248-256
+
+
+def test_output_file_and_tensor_round_trip(tmp_path):
+    import torch
+    x = (np.sin(np.arange(480) * 0.05) * 0.5).astype(np.float32)
+    o = TTSOutput(array=x)
+    f = tmp_path / "a.wav"
+    o.save(f)
+    back = TTSOutput.from_file(f)
+    assert back.sample_rate == 24000 and back.array.shape == x.shape and np.abs(back.array - x).max() < 1.0 / 32767 + 1e-6
+    o.save(tmp_path / "b.wav", sample_rate=12000)
+    assert TTSOutput.from_file(tmp_path / "b.wav").get_info()[:2] == (240, 12000)
+    t = TTSOutput.from_tensor(torch.from_numpy(x)[None], 16000)
+    assert t.sample_rate == 16000 and np.array_equal(t.array, x) and torch.equal(t.to_tensor(), torch.from_numpy(x))
 
 
 def test_split_sentence_rules():
