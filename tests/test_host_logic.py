@@ -43,7 +43,7 @@ def test_output_file_and_tensor_round_trip(tmp_path):
     f = tmp_path / "a.wav"
     o.save(f)
     back = TTSOutput.from_file(f)
-    assert back.sample_rate == 24000 and back.array.shape == x.shape and np.abs(back.array - x).max() < 1.0 / 32767 + 1e-6
+    assert back.sample_rate == 24000 and back.array.shape == x.shape and np.abs(back.array - x).max() < 1e-4      # int16 quantisation
     o.save(tmp_path / "b.wav", sample_rate=12000)
     assert TTSOutput.from_file(tmp_path / "b.wav").get_info()[:2] == (240, 12000)
     t = TTSOutput.from_tensor(torch.from_numpy(x)[None], 16000)
