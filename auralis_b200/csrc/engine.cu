@@ -103,7 +103,17 @@ struct Sequence {
     size_t wav_dev_cap = 0;
     float* lat_dev = nullptr;     // [n_tokens, H] copy so the slot can be reused (pooled device buffer)
     size_t lat_dev_cap = 0;
+    // first-audio early emit (xtts_sampling.early_tokens; 0 = off)
+    int early_tokens = 0;         // audio of this many leading tokens goes out as a partial result
+    bool early_done = false;
+    int early_samples = 0;        // samples already delivered by the partial result
 };
+
+// a partial (first-audio) piece lives in done_map under its sequence id with this bit set; user ids must not use it
+static constexpr uint64_t kPartialBit = 1ull << 63;
+// latent frames decoded beyond `early_tokens` before the prefix is vocoded: the vocoder's receptive field reaches
+// ~3 latent frames ahead (conv_pre + the k = 11, d = 5 resblock of the first stage; measured with the oracle), 6 leaves margin
+static constexpr int kEarlyLookahead = 6;
 
 class Engine {
 public:
@@ -273,6 +283,8 @@ private:
     void run_vocoder(const float* lat_dev, int T, const int* speakers, int nb, float* wav_dev_out, int* n_out,
                      const char* stage, float* stage_out, int64_t stage_cap);
     void finish_group(std::vector<std::shared_ptr<Sequence>>& grp);
+    void emit_early(std::vector<std::shared_ptr<Sequence>>& grp);
+    int samples_for(int T) const;
     void finish_sequence(std::shared_ptr<Sequence> s);
     void retire(std::shared_ptr<Sequence> s);
     float* pinned_get(size_t n, size_t* cap);
@@ -1187,6 +1199,8 @@ void Engine::submit(uint64_t id, const int32_t* text, int n_text, int speaker, c
     if (speaker < 0 || speaker >= S) throw std::runtime_error("speaker slot out of range");
     std::shared_ptr<Sequence> s(new Sequence());
     s->id = id; s->text_ids.assign(text, text + n_text); s->speaker = speaker; s->sp = sp; s->t_submit = now_s();
+    if (id & kPartialBit) throw std::runtime_error("seq_id must be < 2^63");
+    if (sp.early_tokens > 0 && sp.vocode) s->early_tokens = sp.early_tokens;
     require_finalized();
     if (!spk_valid[speaker]) throw std::runtime_error("speaker slot not set");
     {
@@ -1230,19 +1244,89 @@ void Engine::finish_group(std::vector<std::shared_ptr<Sequence>>& grp) {
         run_vocoder(vlat.p, n, spk.data(), nb, vwav.p, &ns, nullptr, nullptr, 0);
         for (int i = 0; i < nb; ++i) {
             auto& s = grp[b0 + i];
-            s->n_samples = ns;
+            const int skip = std::min(s->early_samples, ns);       // 0 unless a partial first-audio piece went out already
+            const int nrem = ns - skip;
+            const float* src = vwav.p + (size_t)i * ns + skip;
+            s->n_samples = nrem;
             if (d2h_wav) {
-                s->wav_host = pinned_get(ns, &s->wav_cap);
-                CUDA_CHECK(cudaMemcpyAsync(s->wav_host, vwav.p + (size_t)i * ns, (size_t)ns * sizeof(float), cudaMemcpyDeviceToHost, st));
+                s->wav_host = pinned_get(std::max(1, nrem), &s->wav_cap);
+                if (nrem > 0) CUDA_CHECK(cudaMemcpyAsync(s->wav_host, src, (size_t)nrem * sizeof(float), cudaMemcpyDeviceToHost, st));
             } else {
-                s->wav_dev = dev_get(ns, &s->wav_dev_cap);
-                CUDA_CHECK(cudaMemcpyAsync(s->wav_dev, vwav.p + (size_t)i * ns, (size_t)ns * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                s->wav_dev = dev_get(std::max(1, nrem), &s->wav_dev_cap);
+                if (nrem > 0) CUDA_CHECK(cudaMemcpyAsync(s->wav_dev, src, (size_t)nrem * sizeof(float), cudaMemcpyDeviceToDevice, st));
             }
-            st_samples += ns;
+            st_samples += nrem;
         }
         CUDA_CHECK(cudaStreamSynchronize(st));
         const double t = now_s();
         for (int i = 0; i < nb; ++i) { grp[b0 + i]->t_done = t; retire(grp[b0 + i]); }
+    }
+    st_voc_ms += (now_s() - t0) * 1e3;
+}
+
+// samples the vocoder produces for T latent frames (the two interpolations of HifiDecoder.forward, then the upsampling)
+int Engine::samples_for(int T) const {
+    const double s1 = (double)cfg.code_stride / (double)cfg.output_hop_length;
+    const double s2 = (double)cfg.output_sample_rate / (double)cfg.input_sample_rate;
+    const int T1 = (int)std::floor((double)T * s1);
+    int len = cfg.output_sample_rate != cfg.input_sample_rate ? (int)std::floor((double)T1 * s2) : T1;
+    for (int i = 0; i < cfg.voc_n_up; ++i) len *= cfg.voc_up_rates[i];
+    return len;
+}
+
+// First audio early (xtts_sampling.early_tokens; not in the reference, which returns whole chunks):
+// every sequence of `grp` is still decoding and has early_tokens + kEarlyLookahead latent frames.  Vocode that prefix
+// straight from the latent ring and deliver the samples of the first early_tokens frames as a PARTIAL result (status 1);
+// the lookahead frames cover the vocoder's receptive field, so these samples equal the ones the whole chunk will give.
+void Engine::emit_early(std::vector<std::shared_ptr<Sequence>>& grp) {
+    const double t0 = now_s();
+    std::map<int, std::vector<std::shared_ptr<Sequence>>> by_len;
+    for (auto& s : grp) by_len[s->early_tokens].push_back(s);
+    for (auto& kv : by_len) {
+        const int n_early = kv.first, T = n_early + kEarlyLookahead;
+        const int keep = samples_for(n_early);
+        auto& v = kv.second;
+        for (size_t b0 = 0; b0 < v.size(); b0 += VB) {
+            const int nb = (int)std::min<size_t>(VB, v.size() - b0);
+            std::vector<int> spk(nb);
+            for (int i = 0; i < nb; ++i) {
+                spk[i] = v[b0 + i]->speaker;
+                CUDA_CHECK(cudaMemcpyAsync(vlat.p + (size_t)i * T * H, d_latents.p + (size_t)v[b0 + i]->slot * CAP * H,
+                                           (size_t)T * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            }
+            int ns = 0;
+            run_vocoder(vlat.p, T, spk.data(), nb, vwav.p, &ns, nullptr, nullptr, 0);
+            if (keep <= 0 || keep > ns) throw std::runtime_error("early emit: sample count out of range");
+            std::vector<std::shared_ptr<Sequence>> parts;
+            for (int i = 0; i < nb; ++i) {
+                auto& s = v[b0 + i];
+                std::shared_ptr<Sequence> p(new Sequence());
+                p->id = s->id; p->speaker = s->speaker; p->status = 1; p->n_prompt = s->n_prompt;
+                p->t_submit = s->t_submit; p->t_first = s->t_first;
+                p->tokens.resize(n_early);
+                d_tokens.download(p->tokens.data(), n_early, st, (size_t)s->slot * CAP);
+                p->n_samples = keep;
+                if (d2h_wav) {
+                    p->wav_host = pinned_get(keep, &p->wav_cap);
+                    CUDA_CHECK(cudaMemcpyAsync(p->wav_host, vwav.p + (size_t)i * ns, (size_t)keep * sizeof(float), cudaMemcpyDeviceToHost, st));
+                } else {
+                    p->wav_dev = dev_get(keep, &p->wav_dev_cap);
+                    CUDA_CHECK(cudaMemcpyAsync(p->wav_dev, vwav.p + (size_t)i * ns, (size_t)keep * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                }
+                st_samples += keep;
+                parts.push_back(p);
+            }
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            const double t = now_s();
+            for (int i = 0; i < nb; ++i) {
+                v[b0 + i]->early_done = true; v[b0 + i]->early_samples = keep;
+                parts[i]->t_done = t;
+                std::lock_guard<std::mutex> lk(q_mu);          // a partial piece does not end the sequence: inflight unchanged
+                done_q.push_back(parts[i]);
+                done_map[parts[i]->id | kPartialBit] = parts[i];
+            }
+            cv_done.notify_all();
+        }
     }
     st_voc_ms += (now_s() - t0) * 1e3;
 }
@@ -1323,6 +1407,15 @@ void Engine::loop() {
                 }
             }
             st_gpt_ms += (now_s() - t0) * 1e3;
+            // ---- first audio early (off unless a chunk asked for it): sequences that just reached their prefix length
+            {
+                std::vector<std::shared_ptr<Sequence>> early;
+                for (auto& s : running)
+                    if (s->early_tokens > 0 && !s->early_done && !h_finished[s->slot] &&
+                        s->steps + 1 >= s->early_tokens + kEarlyLookahead && s->early_tokens + kEarlyLookahead <= voc_max_T)
+                        early.push_back(s);
+                if (!early.empty()) emit_early(early);
+            }
             // ---- retire finished sequences: vocode, D2H, completion queue
             std::vector<std::shared_ptr<Sequence>> keep, fin;
             for (auto& s : running) (h_finished[s->slot] ? fin : keep).push_back(s);
@@ -1364,11 +1457,12 @@ void Engine::fetch(uint64_t id, int32_t* tokens, float* wav, float* latents) {
     std::shared_ptr<Sequence> s;
     {
         std::lock_guard<std::mutex> lk(q_mu);
-        auto it = done_map.find(id);
+        auto it = done_map.find(id | kPartialBit);          // an unfetched first-audio piece of this id is older than its final
+        if (it == done_map.end()) it = done_map.find(id);
         if (it == done_map.end()) throw std::runtime_error("fetch: unknown or unfinished sequence id");
         s = it->second;
         done_map.erase(it);
-        for (auto q = done_q.begin(); q != done_q.end(); ++q) if ((*q)->id == id) { done_q.erase(q); break; }
+        for (auto q = done_q.begin(); q != done_q.end(); ++q) if (*q == s) { done_q.erase(q); break; }
     }
     if (tokens) std::memcpy(tokens, s->tokens.data(), s->tokens.size() * sizeof(int32_t));
     if (wav && s->n_samples > 0 && s->wav_host) std::memcpy(wav, s->wav_host, (size_t)s->n_samples * sizeof(float));

@@ -35,11 +35,14 @@ from .weights import load_model_dir
 
 
 class ChunkOutput:
-    """What the reference reads off vLLM's RequestOutput (XTTSv2.py:785-799): finished flag + token ids."""
+    """What the reference reads off vLLM's RequestOutput (XTTSv2.py:785-799): finished flag + token ids.
+    `partial`: a first-audio piece (engine option `early_emit_tokens`) — the audio of the chunk's leading tokens, delivered
+    while the rest of the chunk is still decoding; the final piece then carries only the remaining samples."""
 
-    def __init__(self, request_id: str, token_ids, wav, result):
+    def __init__(self, request_id: str, token_ids, wav, result, partial: bool = False):
         self.request_id = request_id
         self.finished = True
+        self.partial = partial
         self.token_ids = list(token_ids)
         self.wav = wav
         self.result = result
@@ -74,7 +77,8 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
     model_type = "xtts"
 
     def __init__(self, dims: XTTSDims, gpt_state, core_state, *, device: int = 0, precision: str = "bf16",
-                 max_concurrency: int = 64, max_speakers: int = 32, tokenizer_file: Optional[str] = None, **_):
+                 max_concurrency: int = 64, max_speakers: int = 32, tokenizer_file: Optional[str] = None,
+                 early_emit_tokens: int = 0, **_):
         prec = {"fp32": native.PRECISION_FP32, "bf16": native.PRECISION_BF16}[precision]
         self.dims = dims
         self.precision = precision
@@ -86,10 +90,13 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
         self.mel_bos_token_id = dims.gpt.start_audio_token
         self.mel_eos_token_id = dims.gpt.stop_audio_token
         self.max_speakers = max_speakers
+        # > 0: streaming requests get the audio of their first chunk's leading tokens as soon as those are decoded
+        # (time-to-first-audio); 0 = one TTSOutput per chunk, exactly like the reference
+        self.early_emit_tokens = int(early_emit_tokens)
         self._spk = SpeakerSlots(max_speakers)        # key -> native slot; pins slots referenced by chunks in flight
         self._next_id = 1
         self._id_lock = threading.Lock()
-        self._waiters: Dict[int, Tuple[asyncio.AbstractEventLoop, asyncio.Future, int]] = {}
+        self._waiters: Dict[int, Tuple[asyncio.AbstractEventLoop, asyncio.Queue, int]] = {}
         self._wlock = threading.Lock()
         self._stop = False
         self._parked = False
@@ -219,7 +226,8 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
             sp = native.Sampling(temperature=request.temperature, top_p=request.top_p, top_k=request.top_k,
                                  repetition_penalty=request.repetition_penalty,
                                  max_tokens=self.dims.gpt.max_audio_tokens, stop_token=self.mel_eos_token_id,
-                                 seed=base_seed, seq_seed=seq_index, vocode=True, priority=seq_index)
+                                 seed=base_seed, seq_seed=seq_index, vocode=True, priority=seq_index,
+                                 early_tokens=self.early_emit_tokens if (request.stream and seq_index == 0) else 0)
             rid = f"{request.request_id}_{seq_index}"
             generators.append(self._chunk_generator(rid, ids, gpt_cond_latent, speaker_embeddings, sp))
             request_ids.append(rid)
@@ -230,13 +238,13 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
         pinned from submission until the native completion arrives (released by the poller thread), so it cannot be
         recycled under a queued or running chunk even if the awaiting coroutine is cancelled."""
         loop = asyncio.get_running_loop()
-        fut = loop.create_future()
+        box: asyncio.Queue = asyncio.Queue()            # completions of this chunk: an optional partial piece, then the final one
         slot = await self._pin_speaker(cond, g)
         with self._id_lock:
             sid = self._next_id
             self._next_id += 1
         with self._wlock:
-            self._waiters[sid] = (loop, fut, slot)
+            self._waiters[sid] = (loop, box, slot)
         try:
             self.native.submit(sid, ids, slot, sp)
         except BaseException:
@@ -244,8 +252,19 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
                 self._waiters.pop(sid, None)
             self._spk.unpin(slot)
             raise
-        result, toks, wav = await fut
-        yield ChunkOutput(rid, toks, wav, result)
+        n_before = 0
+        while True:
+            payload, err = await box.get()
+            if err is not None:
+                raise err
+            result, toks, wav = payload
+            if result.status > 0:                       # first-audio piece: leading tokens only
+                n_before = len(toks)
+                yield ChunkOutput(rid, toks, wav, result, partial=True)
+                continue
+            # the final result lists every token; report only the ones whose audio this piece carries
+            yield ChunkOutput(rid, toks[n_before:], wav, result)
+            return
 
     async def process_tokens_to_speech(self, generator, speaker_embeddings=None, multimodal_data=None,
                                        request: TTSRequest = None) -> AsyncGenerator[TTSOutput, None]:
@@ -294,10 +313,11 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
                 continue
             if r is None:
                 continue
+            final = r.status <= 0
             with self._wlock:
-                w = self._waiters.pop(r.seq_id, None)
+                w = self._waiters.pop(r.seq_id, None) if final else self._waiters.get(r.seq_id)
             try:
-                if r.status != 0:
+                if r.status < 0:
                     raise native.NativeError(f"chunk {r.seq_id} failed ({r.status}): "
                                              f"{self.native.lib.xtts_last_error().decode()}")
                 toks, wav, _ = self.native.fetch(r, want_wav=True)
@@ -306,17 +326,10 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
                 payload, err = None, e
             if w is None:
                 continue
-            loop, fut, slot = w
-            self._spk.unpin(slot)                   # the native engine is done with this chunk's speaker slot
-
-            def deliver(fut=fut, payload=payload, err=err):
-                if fut.cancelled():
-                    return
-                if err is not None:
-                    fut.set_exception(err)
-                else:
-                    fut.set_result(payload)
-            loop.call_soon_threadsafe(deliver)
+            loop, box, slot = w
+            if final:
+                self._spk.unpin(slot)               # the native engine is done with this chunk's speaker slot
+            loop.call_soon_threadsafe(box.put_nowait, (payload, err))
 
 
 class _SpeakerArray(np.ndarray):

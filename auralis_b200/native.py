@@ -48,7 +48,7 @@ class XttsSampling(C.Structure):
     _fields_ = [("temperature", C.c_float), ("top_p", C.c_float), ("repetition_penalty", C.c_float),
                 ("top_k", C.c_int32), ("max_tokens", C.c_int32), ("stop_token", C.c_int32),
                 ("seed", C.c_uint64), ("seq_seed", C.c_int32), ("vocode", C.c_int32), ("priority", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("early_tokens", C.c_int32)]
 
 
 class XttsResult(C.Structure):
@@ -176,6 +176,7 @@ class Sampling:
     seq_seed: int = 0
     vocode: bool = True
     priority: int = 0
+    early_tokens: int = 0          # > 0: deliver the audio of the first n tokens as a partial result (include/xtts_b200.h)
 
     def c(self) -> XttsSampling:
         s = XttsSampling()
@@ -183,6 +184,7 @@ class Sampling:
         s.top_k, s.max_tokens, s.stop_token = self.top_k, self.max_tokens, self.stop_token
         s.seed, s.seq_seed, s.vocode = self.seed, self.seq_seed, 1 if self.vocode else 0
         s.priority = self.priority
+        s.early_tokens = max(0, int(self.early_tokens))
         return s
 
 
@@ -310,7 +312,7 @@ class NativeEngine:
                 n += 1
         finally:
             self.set_option("hold_admission", 0)
-        out = {}
+        out, partials = {}, {}
         t_end = time.time() + timeout_s
         while len(out) < n:
             r = self.poll(1000)
@@ -318,11 +320,17 @@ class NativeEngine:
                 if time.time() > t_end:
                     raise NativeError("run_batch timed out")
                 continue
-            if r.status != 0:
+            if r.status < 0:
                 raise NativeError(f"sequence {r.seq_id} failed ({r.status}): {self.lib.xtts_last_error().decode()}")
+            if r.status > 0:                 # partial first-audio piece (Sampling.early_tokens): kept next to the final result
+                ptoks, pwav, _ = self.fetch(r, want_wav, False)
+                partials[r.seq_id] = (r, ptoks, pwav)
+                continue
             toks, wav, lat = self.fetch(r, want_wav, want_latents)
             out[r.seq_id] = (r, toks, wav, lat)
+        self.last_partials = partials        # {seq_id: (result, tokens, wav)} of the batch just run
         return out
+
 
     # ---- synchronous single-stage entry points (parity tests)
     def vocode(self, latents, speaker_slot: int, stage: Optional[str] = None, stage_shape: Optional[Tuple[int, ...]] = None):

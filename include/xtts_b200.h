@@ -64,12 +64,19 @@ typedef struct xtts_sampling {
     int32_t vocode;            /* 1: run the vocoder on completion; 0: tokens + latents only   */
     int32_t priority;          /* admission order: lower first (the engine passes the chunk index,
                                   so every request's first chunk is decoded before any second chunk) */
-    int32_t reserved;
+    int32_t early_tokens;      /* 0 (default): one result per chunk, as the reference (FINAL_ONLY, XTTSv2.py:738).
+                                  n > 0: "first audio early" — as soon as n + 6 tokens are decoded the engine vocodes that
+                                  prefix and delivers the samples of the first n tokens as a PARTIAL result (status 1);
+                                  the final result then carries all tokens and only the remaining samples.  The 6-token
+                                  lookahead covers the vocoder's receptive field (~3 latent frames), so partial + final
+                                  concatenate to exactly the waveform of the unsplit chunk.  SURVEY.md §8f-3.            */
 } xtts_sampling;
 
 typedef struct xtts_result {
     uint64_t seq_id;
-    int32_t status;            /* 0 ok, <0 failed                                              */
+    int32_t status;            /* 0 ok (final result), <0 failed, 1 = partial first-audio piece (see early_tokens):
+                                  fetch it before polling further; xtts_fetch(seq_id) hands out the partial piece of an
+                                  id before its final one                                        */
     int32_t n_tokens;          /* = TTSOutput.token_length (XTTSv2.py:813); stop token included */
     int32_t n_samples;         /* 24 kHz samples                                               */
     int32_t n_prompt_rows;
@@ -121,7 +128,8 @@ int xtts_submit(xtts_engine* e, uint64_t seq_id, const int32_t* text_ids, int32_
 /* completion queue (replaces `async for output in generator` + get_model_logits + hifigan_decoder,
  * XTTSv2.py:785-814).  Returns 1 and fills *out when a chunk finished, 0 on timeout. */
 int xtts_poll(xtts_engine* e, xtts_result* out, int32_t timeout_ms);
-/* copies out and releases a finished chunk; any of tokens / wav / latents may be NULL */
+/* copies out and releases a finished chunk (or its partial first-audio piece, whichever is older); any of tokens / wav /
+ * latents may be NULL (a partial piece has no latents).  seq_id must be < 2^63. */
 int xtts_fetch(xtts_engine* e, uint64_t seq_id, int32_t* tokens, float* wav, float* latents);
 /* engine knobs (key, value):
  *   "d2h_wav"             0 = leave waveforms in HBM (kernel-only timing), 1 = D2H into pinned memory (default)

@@ -260,18 +260,28 @@ class _FakeNativeEngine:
         self.t.start()
 
     def _run(self):
+        from auralis_b200.native import XttsResult
         while not self.closed:
             try:
-                sid, ids, slot = self.q.get(timeout=0.05)
+                sid, ids, slot, early = self.q.get(timeout=0.05)
             except Exception:
                 continue
             time.sleep(self.delay)
             with self.lock:
                 v = float(self.spk[slot][1].flat[0])          # the slot's CURRENT contents, like the real engine
-            self.results[sid] = (np.arange(len(ids), dtype=np.int32), np.full(8, v, np.float32))
-            from auralis_b200.native import XttsResult
+            toks = np.arange(len(ids), dtype=np.int32)
+            wav = np.full(8, v, np.float32) + np.arange(8, dtype=np.float32) * 1e-3
+            skip = 0
+            if early > 0 and len(ids) > early:                # first-audio piece, then the remainder (include/xtts_b200.h)
+                skip = 3
+                self.results.setdefault(sid, []).append((toks[:early], wav[:skip]))
+                p = XttsResult()
+                p.seq_id, p.status, p.n_tokens, p.n_samples = sid, 1, early, skip
+                self.done.put(p)
+                time.sleep(self.delay)
+            self.results.setdefault(sid, []).append((toks, wav[skip:]))
             r = XttsResult()
-            r.seq_id, r.status, r.n_tokens, r.n_samples = sid, (-2 if sid in self.fail_ids else 0), len(ids), 8
+            r.seq_id, r.status, r.n_tokens, r.n_samples = sid, (-2 if sid in self.fail_ids else 0), len(ids), 8 - skip
             self.done.put(r)
 
     def condition(self, slot, wav22, wav16, cond_len=30, chunk_len=4):
@@ -292,7 +302,7 @@ class _FakeNativeEngine:
             return c.copy(), g.copy()
 
     def submit(self, sid, ids, slot, sp):
-        self.q.put((sid, list(ids), slot))
+        self.q.put((sid, list(ids), slot, int(getattr(sp, "early_tokens", 0))))
 
     def poll(self, timeout_ms=50):
         try:
@@ -301,7 +311,7 @@ class _FakeNativeEngine:
             return None
 
     def fetch(self, r, want_wav=True, want_latents=False):
-        toks, wav = self.results.pop(r.seq_id)
+        toks, wav = self.results[r.seq_id].pop(0)             # oldest piece of that id first, like xtts_fetch
         return toks, wav, None
 
     def close(self):
@@ -321,6 +331,7 @@ def _host_engine(max_speakers=2, **kw):
     eng.tokenizer = XTTSTokenizer(dims.gpt.n_text_tokens, dims.gpt.max_text_tokens)
     eng.mel_bos_token_id, eng.mel_eos_token_id = dims.gpt.start_audio_token, dims.gpt.stop_audio_token
     eng._spk = SpeakerSlots(max_speakers)
+    eng.early_emit_tokens = 0
     eng._next_id, eng._id_lock, eng._waiters, eng._wlock = 1, threading.Lock(), {}, threading.Lock()
     eng._stop = eng._parked = eng._paused = False
     eng._poller = threading.Thread(target=eng._poll_loop, daemon=True)
@@ -379,5 +390,25 @@ def test_engine_host_path_native_failure_propagates_and_unpins():
     deadline = time.time() + 2.0
     while time.time() < deadline and (eng._waiters or any(eng._spk.pinned(s) for s in range(2))):
         time.sleep(0.01)                                                # the other chunks finish in the background
+    assert not eng._waiters and all(eng._spk.pinned(s) == 0 for s in range(2))
+    tts.loop.run_until_complete(tts.shutdown())
+
+
+def test_engine_early_first_audio_piece():
+    """engine option early_emit_tokens: a streaming request gets its first chunk in two pieces (leading tokens first);
+    the pieces concatenate to the unsplit audio, token counts add up, later chunks and non-streaming requests are not split."""
+    eng = _host_engine(max_speakers=2)
+    tts = TTS(scheduler_max_concurrency=8).from_engine(eng)
+    text = ("Sentence number one is here. " * 12).strip()
+    spk = _wav(0.4)
+    plain = list(tts.generate_speech(TTSRequest(text=text, speaker_files=spk, language="en", stream=True)))
+    eng.early_emit_tokens = 4
+    early = list(tts.generate_speech(TTSRequest(text=text, speaker_files=spk, language="en", stream=True)))
+    assert len(early) == len(plain) + 1                                 # only the first chunk is split
+    assert early[0].array.size == 3 and early[0].token_length == 4     # the fake's partial piece
+    assert early[0].token_length + early[1].token_length == plain[0].token_length
+    np.testing.assert_array_equal(np.concatenate([c.array for c in early]), np.concatenate([c.array for c in plain]))
+    whole = tts.generate_speech(TTSRequest(text=text, speaker_files=spk, language="en"))        # stream=False: never split
+    np.testing.assert_array_equal(whole.array, np.concatenate([c.array for c in plain]))
     assert not eng._waiters and all(eng._spk.pinned(s) == 0 for s in range(2))
     tts.loop.run_until_complete(tts.shutdown())
