@@ -185,7 +185,11 @@ def main():
     from auralis_b200.weights import synth_state
     from auralis_b200 import parallel
 
-    rank, world, local = parallel.init_from_env()
+    if args.impl == "reference":
+        # CPU arm: no process group, no CUDA context — ranks other than 0 leave immediately (nothing to tear down)
+        rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), 0
+    else:
+        rank, world, local = parallel.init_from_env()
     dims = XTTSDims.small() if args.small else XTTSDims.full()
     # torch CPU ops on these shapes stop scaling (and regress) beyond ~32 threads: use the best of what the host has
     n_threads = min(os.cpu_count() or 1, 32)
