@@ -8,9 +8,8 @@ No transformers dependency: the native library only needs the integers.
 """
 from __future__ import annotations
 
-import ctypes
 from dataclasses import dataclass, field, asdict
-from typing import List, Tuple
+from typing import Tuple
 
 
 @dataclass

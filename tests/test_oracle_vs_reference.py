@@ -1,0 +1,81 @@
+"""CPU, container only (needs /root/reference): the oracle restatement against the REFERENCE's own modules, imported
+unmodified (oracle/ref_import.py), on inputs OTHER than the committed golden vectors — ragged lengths, a one-frame
+chunk, several speakers, reference audio that is cut into more than one conditioning chunk.  The golden files
+(tests/golden/*.npz) carry the same pin to machines without the reference tree."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from auralis_b200.config import XTTSDims
+from oracle import ref_import
+from oracle import xtts_oracle as O
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+
+
+def _golden_tools():
+    spec = importlib.util.spec_from_file_location(
+        "make_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_import.load()
+
+
+@pytest.mark.parametrize("T", [1, 2, 7, 33])
+def test_vocoder_live(ref, dims_small, state_small, T):
+    mg = _golden_tools()
+    hd = mg.ref_vocoder(ref, dims_small, state_small[1])
+    g = torch.Generator().manual_seed(1000 + T)
+    for spk in range(2):
+        lat = torch.randn(T, dims_small.voc.in_dim, generator=g)
+        gv = torch.nn.functional.normalize(torch.randn(dims_small.voc.d_vector, generator=g), dim=0)
+        with torch.no_grad():
+            want = ref.HifiDecoder.forward(hd, lat[None], g=gv.reshape(1, -1, 1)).reshape(-1)
+        got = O.vocoder(lat, gv, state_small[1], dims_small)
+        assert got.shape == want.shape == (dims_small.voc.n_samples(T),)
+        np.testing.assert_allclose(got.numpy(), want.numpy(), atol=2e-6, rtol=0)
+
+
+@pytest.mark.parametrize("seconds,f0", [(0.4, 95.0), (1.3, 180.0)])
+def test_conditioning_live(ref, dims_small, state_small, seconds, f0):
+    cs, dims = state_small[1], dims_small
+    wav22 = O.synthetic_reference_wav(seconds, 22050, f0, 21)
+    mel = ref.wav_to_mel_cloning(wav22[None], mel_norms=cs["mel_stats"], n_fft=2048, hop_length=256, win_length=1024, power=2,
+                                 normalized=False, sample_rate=22050, f_min=0, f_max=8000, n_mels=80)
+    np.testing.assert_allclose(O.mel_cloning(wav22, cs["mel_stats"], dims.cond.n_mels).numpy(), mel[0].numpy(), atol=2e-5, rtol=0)
+    ce = ref.ConditioningEncoder(dims.cond.n_mels, dims.gpt.hidden, attn_blocks=dims.cond.cond_blocks, num_attn_heads=dims.gpt.heads)
+    ce.load_state_dict({k[len("conditioning_encoder."):]: t for k, t in cs.items() if k.startswith("conditioning_encoder.")})
+    pr = ref.PerceiverResampler(dim=dims.gpt.hidden, depth=dims.cond.perceiver_depth, dim_context=dims.gpt.hidden,
+                                num_latents=dims.gpt.n_cond_latents, dim_head=dims.cond.perceiver_dim_head,
+                                heads=dims.cond.perceiver_heads, ff_mult=dims.cond.perceiver_ff_mult, use_flash_attn=False)
+    pr.load_state_dict({k[len("conditioning_perceiver."):]: t for k, t in cs.items() if k.startswith("conditioning_perceiver.")})
+    with torch.no_grad():
+        h = ce(mel)
+        want = pr(h.permute(0, 2, 1))[0]
+    got_h = O.cond_encoder(mel[0], cs, dims)
+    np.testing.assert_allclose(got_h.numpy(), h[0].numpy(), atol=2e-5, rtol=0)
+    np.testing.assert_allclose(O.perceiver(got_h.t(), cs, dims).numpy(), want.numpy(), atol=5e-5, rtol=0)
+
+
+def test_speaker_encoder_live(ref, dims_small, state_small):
+    cs, dims = state_small[1], dims_small
+    se = ref.ResNetSpeakerEncoder(input_dim=dims.cond.spk_mels, proj_dim=dims.cond.spk_proj, layers=list(dims.cond.spk_layers),
+                                  num_filters=list(dims.cond.spk_filters), log_input=True, use_torch_spec=True,
+                                  audio_config={"fft_size": 512, "win_length": 400, "hop_length": 160, "sample_rate": 16000,
+                                                "preemphasis": 0.97, "num_mels": 64})
+    pre = "hifigan_decoder.speaker_encoder."
+    se.load_state_dict({k[len(pre):]: t for k, t in cs.items() if k.startswith(pre)})
+    se.eval()
+    for seconds, f0 in ((0.35, 110.0), (0.9, 210.0)):
+        wav16 = O.synthetic_reference_wav(seconds, 16000, f0, 5)
+        with torch.no_grad():
+            want = se.forward(wav16[None].clone(), l2_norm=True)[0]
+        np.testing.assert_allclose(O.speaker_embedding(wav16, cs, dims).numpy(), want.numpy(), atol=2e-6, rtol=0)
