@@ -16,7 +16,9 @@ Parity pin status
   (requirements.txt:31), not vendored under /root/reference and not installable here
   (SURVEY.md §8c).  They are restated from the reference's call sites and checked
   against HF ``transformers.GPT2Model`` (same arithmetic: Conv1D, gelu_new, pre-LN)
-  in ``tests/test_oracle_gpt.py``.  The reference holds no golden vector for this
+  in ``tests/test_oracle_gpt.py``; the top-k / top-p mask is additionally compared (ties included) with
+  ``apply_top_k_top_p_pytorch`` lifted by source from the vLLM that IS installed (0.22, v1 sampler — same
+  published algorithm, different version).  The reference holds no golden vector for this
   path -> **parity unpinned** for the GPT/sampler beyond that.
 
 Every function cites the reference lines it restates.

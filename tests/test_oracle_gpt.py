@@ -1,5 +1,7 @@
 """CPU: the GPT restatement against HF transformers.GPT2Model (the arithmetic-equivalent stand-in for the
 un-vendored vLLM GPT2Block), plus the loop semantics of SURVEY App. A.2-A.4."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -92,3 +94,42 @@ def test_sampling_distribution_matches_softmax():
     n = 3000
     c = np.bincount([O.sample_token(z.clone(), set(), sp, s, 0) for s in range(n)], minlength=3) / n
     assert np.abs(c - [0.6, 0.3, 0.1]).max() < 0.03
+
+
+def _installed_vllm_topk_topp():
+    """`apply_top_k_top_p_pytorch` lifted out of the INSTALLED vLLM (0.22, v1 sampler) by source — importing the package
+    needs libcuda.  It is a stand-in for the pinned, un-vendored vLLM 0.6.4.post1 sampler: same published
+    algorithm (ascending sort, k-th value threshold, cumulative-softmax <= 1-p with the maximum always kept)."""
+    import ast
+    import importlib.util
+    spec = importlib.util.find_spec("vllm")
+    if spec is None or not spec.submodule_search_locations:
+        return None
+    path = os.path.join(list(spec.submodule_search_locations)[0], "v1", "sample", "ops", "topk_topp_sampler.py")
+    if not os.path.exists(path):
+        return None
+    tree = ast.parse(open(path).read())
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("apply_top_k_top_p_pytorch", "apply_top_k_only")]
+    if len(fns) != 2:
+        return None
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), path, "exec"), ns)
+    return ns["apply_top_k_top_p_pytorch"]
+
+
+def test_topk_topp_mask_matches_installed_vllm_sampler():
+    fn = _installed_vllm_topk_topp()
+    if fn is None:
+        pytest.skip("no installed vLLM sampler source to compare with")
+    g = torch.Generator().manual_seed(3)
+    for trial in range(40):
+        V = [130, 1026, 7][trial % 3]
+        z = torch.randn(V, generator=g) * (1.0 + trial % 5)
+        if trial % 4 == 0:
+            z[torch.randint(0, V, (V // 3,), generator=g)] = float(z[0])            # ties at and around the thresholds
+        k = [1, 5, 50, V - 1, V][trial % 5]
+        p = [0.05, 0.5, 0.85, 0.999][trial % 4]
+        want = fn(z.clone()[None], torch.tensor([min(k, V)]), torch.tensor([p], dtype=torch.float32))[0]
+        got = O.topk_topp_mask(z.clone(), k, p)
+        assert torch.equal(torch.isinf(got), torch.isinf(want)), (trial, V, k, p)
+        assert torch.equal(got[~torch.isinf(got)], want[~torch.isinf(want)])
