@@ -92,19 +92,20 @@ class TTS:
         self._ensure_event_loop()
 
         async def process_chunks():
-            chunks = []
+            acc = TTSOutput.Accumulator()               # = combine_outputs(chunks), copied chunk by chunk as they arrive
             try:
                 async for chunk in self.scheduler.run(inputs=request, request_id=request.request_id,
                                                       first_phase_fn=self._prepare_generation_context,
                                                       second_phase_fn=self._second_phase_fn):
                     if request.stream:
                         yield chunk
-                    chunks.append(chunk)
+                    else:
+                        acc.add(chunk)
             except Exception as e:
                 logger.error(f"Error during speech generation: {e}")
                 raise
             if not request.stream:
-                yield TTSOutput.combine_outputs(chunks)
+                yield acc.result()
 
         if request.stream:
             return process_chunks()
@@ -127,14 +128,14 @@ class TTS:
     async def _process_multiple_requests(self, requests: List[TTSRequest]) -> TTSOutput:
         """tts.py:257-308: sub-requests run concurrently, audio is concatenated in order."""
         async def one(sub):
-            chunks = []
+            acc = TTSOutput.Accumulator()
             async for chunk in self.scheduler.run(inputs=sub, request_id=sub.request_id,
                                                   first_phase_fn=self._prepare_generation_context,
                                                   second_phase_fn=self._second_phase_fn):
-                chunks.append(chunk)
-            return chunks
-        all_chunks = await asyncio.gather(*[asyncio.ensure_future(one(r)) for r in requests])
-        return TTSOutput.combine_outputs([c for chunks in all_chunks for c in chunks])
+                acc.add(chunk)
+            return acc.result()
+        parts = await asyncio.gather(*[asyncio.ensure_future(one(r)) for r in requests])
+        return parts[0] if len(parts) == 1 else TTSOutput.combine_outputs(list(parts))
 
     def generate_speech(self, request: TTSRequest) -> Union[Generator[TTSOutput, None, None], TTSOutput]:
         """tts.py:310-355."""

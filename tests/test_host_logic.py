@@ -36,6 +36,21 @@ def test_output_combine_and_bytes():
     assert c.get_info() == (15, 24000, 15 / 24000)                 # output.py:248-256
 
 
+def test_accumulator_equals_combine_outputs():
+    rng = np.random.RandomState(0)
+    for sizes in ([5], [3, 0, 7], [1000] * 5, [10] * 20, [7, 900, 2, 5000, 1, 1, 1, 1, 1, 64]):
+        outs = [TTSOutput(array=rng.randn(n).astype(np.float32)) for n in sizes]
+        acc = TTSOutput.Accumulator()
+        for o in outs:
+            acc.add(o)
+        want = TTSOutput.combine_outputs(outs)
+        got = acc.result()
+        assert got.sample_rate == want.sample_rate and got.array.dtype == want.array.dtype
+        np.testing.assert_array_equal(got.array, want.array)
+    with pytest.raises(ValueError):
+        TTSOutput.Accumulator().result()
+
+
 def test_output_file_and_tensor_round_trip(tmp_path):
     import torch
     x = (np.sin(np.arange(480) * 0.05) * 0.5).astype(np.float32)
