@@ -13,8 +13,9 @@ What is pinned and how (tests/test_text_golden.py, vectors in tests/golden/text_
     reference).  `verbalise()` restates its conventions for en / es / fr / de / it / pt (the languages of
     BASELINE.json's multilingual config that use digits); there is no copy of num2words to check against, so the
     word lists are "parity unpinned" (DESIGN.md §7).  For ar / cs / hu / ko / nl / pl / ru / tr digits are kept.
-  * zh number normalisation (the reference's `zh_num2words.TextNorm`) and the zh / ja / ko transliteration
-    (pypinyin, cutlet, hangul_romanize: third-party, absent) are not restated: such text passes through unchanged.
+  * zh number normalisation (the reference's `zh_num2words.TextNorm`) is not restated.  The zh / ja / ko romanisation is
+    third-party (pypinyin, cutlet, hangul_romanize): it is called exactly as the reference calls it when the package is
+    installed, otherwise the text passes through unromanised with a one-time warning.
 """
 from __future__ import annotations
 
@@ -610,11 +611,57 @@ def basic_cleaners(text: str) -> str:
     return _WS.sub(" ", text.lower())
 
 
+_TRANSLIT_CACHE: Dict[str, object] = {}
+_TRANSLIT_WARNED = set()
+
+
+def _transliterator(lang: str):
+    """zh / ko / ja romanisation exactly as the reference wires it (tokenizer.py:727-739,797-803) when the third-party
+    package it uses is installed: pypinyin (TONE3, neutral tone 5), hangul_romanize (academic rule), cutlet (romaji, then
+    lowercase).  None when the package is absent — the text then passes through unromanised and a warning says so once."""
+    if lang in _TRANSLIT_CACHE:
+        return _TRANSLIT_CACHE[lang]
+    fn = None
+    try:
+        if lang == "zh":
+            import pypinyin
+            fn = lambda t: "".join(p[0] for p in pypinyin.pinyin(t, style=pypinyin.Style.TONE3, heteronym=False,      # noqa: E731
+                                                                  neutral_tone_with_five=True))
+        elif lang == "ko":
+            from hangul_romanize import Transliter
+            from hangul_romanize.rule import academic
+            tr = Transliter(academic)
+            fn = tr.translit
+        elif lang == "ja":
+            import cutlet
+            katsu = cutlet.Cutlet()
+            fn = lambda t: katsu.romaji(t).lower()                                                                     # noqa: E731
+    except ImportError:
+        fn = None
+    if fn is None and lang not in _TRANSLIT_WARNED:
+        _TRANSLIT_WARNED.add(lang)
+        import warnings
+        pkg = {"zh": "pypinyin", "ko": "hangul_romanize", "ja": "cutlet"}[lang]
+        warnings.warn(f"text front-end: {pkg} is not installed, '{lang}' text is passed to the BPE without romanisation "
+                      f"(the reference romanises it, tokenizer.py:805-819)", RuntimeWarning, stacklevel=3)
+    _TRANSLIT_CACHE[lang] = fn
+    return fn
+
+
 def preprocess_text(text: str, lang: str, n2w: Optional[Verbaliser] = None) -> str:
-    """tokenizer.py:805-819 (without the zh/ko/ja transliteration step)."""
+    """tokenizer.py:805-819.  zh / ko / ja romanisation runs when its third-party package is importable (`_transliterator`)."""
     base = lang.split("-")[0]
     if base in _CLEANED_LANGS:
-        return multilingual_cleaners(text, base, n2w)
+        text = multilingual_cleaners(text, base, n2w)
+        if base in ("zh", "ko"):
+            fn = _transliterator(base)
+            if fn is not None:
+                text = fn(text)
+        return text
+    if base == "ja":
+        fn = _transliterator("ja")
+        if fn is not None:
+            return fn(text)                       # japanese_cleaners: romaji, then lowercase (tokenizer.py:732-735)
     return basic_cleaners(text)
 
 

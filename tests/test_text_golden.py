@@ -129,3 +129,32 @@ def test_cleaners_end_to_end_with_number_words():
     assert T.format_for_bpe("Hello there", "en") == "[en]hello[SPACE]there"
     assert T.format_for_bpe("你好", "zh-cn").startswith("[zh-cn]")
     assert T.preprocess_text("MiXed   Case", "xx") == "mixed case"
+
+
+def test_romanisation_hooks_follow_the_reference_wiring(monkeypatch):
+    """zh/ko/ja: the third-party romanisers are called the way tokenizer.py:727-739 calls them when present; absent -> warning."""
+    import sys
+    import types
+    import warnings
+    T._TRANSLIT_CACHE.clear(); T._TRANSLIT_WARNED.clear()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert T.preprocess_text("你好 20%", "zh-cn") == "你好 20 百分之"              # cleaners still run; no pypinyin here
+        assert T.preprocess_text("こんにちは", "ja") == "こんにちは"
+    assert any("pypinyin" in str(x.message) for x in w) and any("cutlet" in str(x.message) for x in w)
+    calls = {}
+    pyp = types.ModuleType("pypinyin")
+    pyp.Style = types.SimpleNamespace(TONE3="T3")
+
+    def pinyin(text, style=None, heteronym=None, neutral_tone_with_five=None):
+        calls["zh"] = (style, heteronym, neutral_tone_with_five)
+        return [[f"<{ch}>"] for ch in text]
+    pyp.pinyin = pinyin
+    cut = types.ModuleType("cutlet")
+    cut.Cutlet = lambda: types.SimpleNamespace(romaji=lambda t: "Konnichiwa")
+    monkeypatch.setitem(sys.modules, "pypinyin", pyp)
+    monkeypatch.setitem(sys.modules, "cutlet", cut)
+    T._TRANSLIT_CACHE.clear()
+    assert T.preprocess_text("你好", "zh") == "<你><好>" and calls["zh"] == ("T3", False, True)
+    assert T.preprocess_text("こんにちは", "ja") == "konnichiwa"
+    T._TRANSLIT_CACHE.clear(); T._TRANSLIT_WARNED.clear()
