@@ -118,7 +118,7 @@ class ClockSampler:
 
 
 # =====================================================================================================
-def cpu_reference_sample(dims, state, n_threads: int, decode_tokens: int = 12, voc_latents: int = 24) -> dict:
+def cpu_reference_sample(dims, state, n_threads: int, decode_tokens: int = 32, voc_latents: int = 64) -> dict:
     """Times the reference's CPU path (the oracle port, fp32 torch ops, all host threads) on a bounded sample of
     the same workload: one 250-char chunk's prompt prefill + `decode_tokens` KV-cached decode steps, and the
     vocoder on `voc_latents` latents; scaled to the workload's unit (605 tokens + 605 latents per chunk)."""
@@ -203,7 +203,7 @@ def main():
         state = synth_state(dims, SEED)
         vals = []
         for i in range(args.warmup + args.steps):
-            r = cpu_reference_sample(dims, state, n_threads, decode_tokens=6, voc_latents=12)
+            r = cpu_reference_sample(dims, state, n_threads)
             if i >= args.warmup:
                 vals.append(r)
         v = statistics.mean(x["value"] for x in vals)
