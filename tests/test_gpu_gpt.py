@@ -344,3 +344,19 @@ def test_kernel_profile_graph_events(engine_small_bf16, dims_small):
     att = prof["attn_decode_paged"]
     assert att["launches"] >= 9 * L and att["ms"] > 0 and att["bytes"] > 0, att
     assert prof["sample"]["launches"] >= 10 and prof["gemm_bf16_tcgen05"]["ms"] > 0
+
+
+def test_device_timer_brackets_a_batch(engine_small, dims_small):
+    """xtts_device_timer (bench.py's stopwatch): two CUDA events on the engine stream; the device-clock span of a batch is
+    positive and does not exceed the host wall clock around the same calls by more than scheduling noise."""
+    import time
+    g = dims_small.gpt
+    jobs = [(i, text_ids(dims_small, 6 + i, 40 + i), i % 3,
+             Sampling(temperature=0.0, repetition_penalty=5.0, max_tokens=10, stop_token=g.stop_audio_token)) for i in range(3)]
+    engine_small.run_batch(jobs, timeout_s=60)                       # warm
+    t0 = time.perf_counter()
+    engine_small.timer_start()
+    engine_small.run_batch(jobs, timeout_s=60)
+    ms = engine_small.timer_stop_ms()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    assert 0.0 < ms <= wall_ms + 5.0, (ms, wall_ms)
