@@ -94,6 +94,7 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
         # (time-to-first-audio); 0 = one TTSOutput per chunk, exactly like the reference
         self.early_emit_tokens = int(early_emit_tokens)
         self._spk = SpeakerSlots(max_speakers)        # key -> native slot; pins slots referenced by chunks in flight
+        self._spk_arrays: Dict[str, Tuple["_SpeakerArray", "_SpeakerArray"]] = {}    # reference key -> host (cond, g) pair
         self._next_id = 1
         self._id_lock = threading.Lock()
         self._waiters: Dict[int, Tuple[asyncio.AbstractEventLoop, asyncio.Queue, int]] = {}
@@ -140,6 +141,12 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
             hk.update(p if isinstance(p, (bytes, bytearray)) else str(p).encode())
         hk.update(f"{max_ref_length}|{gpt_cond_len}|{gpt_cond_chunk_len}|{sound_norm_refs}".encode())
         key = hk.hexdigest()
+        cached = self._spk_arrays.get(key)
+        if cached is not None:
+            # no native call on a hit: xtts_get_speaker would wait for the scheduler thread's current iteration and stall
+            # every other coroutine of this loop behind it.  Whether the slot still holds this speaker is checked (and the
+            # pair uploaded again if not) when a chunk pins it.
+            return cached
         while True:
             slot, pending, owner = await self._acquire_speaker(key)
             if owner:
@@ -175,7 +182,11 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
             cond, g = self.native.get_speaker(slot)
             if self._spk.holds(key, slot):              # not recycled between the wake-up and the read-back
                 break
-        return _SpeakerArray(cond[None], slot, key), _SpeakerArray(g.reshape(1, -1, 1), slot, key)
+        pair = (_SpeakerArray(cond[None], slot, key), _SpeakerArray(g.reshape(1, -1, 1), slot, key))
+        if len(self._spk_arrays) >= 4 * self.max_speakers:           # host copies are 130 KB each: a small bounded cache
+            self._spk_arrays.pop(next(iter(self._spk_arrays)))
+        self._spk_arrays[key] = pair
+        return pair
 
     def register_speaker(self, cond_latents: np.ndarray, d_vector: np.ndarray) -> Tuple["_SpeakerArray", "_SpeakerArray"]:
         """Pre-computed conditioning (the pair `prepare_for_streaming_generation` hands back, tts.py:91-105).
