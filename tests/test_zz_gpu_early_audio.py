@@ -49,3 +49,19 @@ def test_short_sequences_never_split(engine_small, dims_small):
     """a chunk that ends before early_tokens + lookahead frames exist is delivered whole"""
     got, parts = _run(engine_small, dims_small, early=10, max_tokens=12)
     assert not parts and all(got[s][0].n_tokens == 12 for s in got)
+
+
+@pytest.mark.parametrize("which,dims_name,T,n", [("engine_small", "dims_small", 40, 20), ("engine_small_bf16", "dims_small", 40, 20),
+                                                   ("engine_full_bf16", "dims_full", 605, 58)])
+def test_vocoder_prefix_property(request, which, dims_name, T, n):
+    """Size-independent property the early emit rests on, checked through xtts_vocode alone: the waveform of the first n
+    latent frames does not depend on frames more than 6 ahead — vocode(lat[:n+6])[:samples(n)] == vocode(lat)[:samples(n)]."""
+    import torch
+    eng, dims = request.getfixturevalue(which), request.getfixturevalue(dims_name)
+    g = torch.Generator().manual_seed(77)
+    lat = torch.randn(T, dims.voc.in_dim, generator=g).numpy()
+    full = eng.vocode(lat, 0)
+    part = eng.vocode(lat[: n + 6], 0)
+    keep = dims.voc.n_samples(n)
+    assert part.shape[0] == dims.voc.n_samples(n + 6) and keep < part.shape[0]
+    np.testing.assert_array_equal(part[:keep], full[:keep])
