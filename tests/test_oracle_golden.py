@@ -50,3 +50,24 @@ def test_interpolate_length_rule():
     for T in (1, 2, 7, 64, 320):
         lat = torch.zeros(T, 8)
         assert O.interp_latents(lat, v).shape[1] == v.z_frames(T)
+
+
+def test_vocoder_lookahead_covers_receptive_field(state_small):
+    """The engine's first-audio early emit vocodes a chunk's first n + 6 latent frames and keeps the samples of the first n
+    (kEarlyLookahead in engine.cu).  With the oracle: prefix and whole-chunk waveforms agree to 1e-6 on those samples — the
+    vocoder's receptive field (conv_pre + the k = 11, d = 5 resblock of the first stage) reaches ~3 frames ahead, so 3 frames
+    are the minimum that passes and 6 leave margin.  Same kernels and dilations as the full geometry."""
+    dims = XTTSDims.small()
+    cs = state_small[1]
+    g = torch.Generator().manual_seed(3)
+    lat = torch.randn(60, dims.voc.in_dim, generator=g)
+    dv = torch.nn.functional.normalize(torch.randn(dims.voc.d_vector, generator=g), dim=0)
+    full = O.vocoder(lat, dv, cs, dims).numpy()
+    for n in (10, 16, 24):
+        keep = dims.voc.n_samples(n)
+        part6 = O.vocoder(lat[: n + 6], dv, cs, dims).numpy()
+        np.testing.assert_allclose(part6[:keep], full[:keep], atol=1e-6, rtol=0)
+        part3 = O.vocoder(lat[: n + 3], dv, cs, dims).numpy()
+        np.testing.assert_allclose(part3[:keep], full[:keep], atol=1e-6, rtol=0)
+        part1 = O.vocoder(lat[: n + 1], dv, cs, dims).numpy()
+        assert np.abs(part1[:keep] - full[:keep]).max() > 1e-4          # one frame of lookahead is NOT enough
