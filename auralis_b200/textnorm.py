@@ -13,7 +13,8 @@ What is pinned and how (tests/test_text_golden.py, vectors in tests/golden/text_
     reference).  `verbalise()` restates its conventions for en / es / fr / de / it / pt (the languages of
     BASELINE.json's multilingual config that use digits); there is no copy of num2words to check against, so the
     word lists are "parity unpinned" (DESIGN.md §7).  For ar / cs / hu / ko / nl / pl / ru / tr digits are kept.
-  * zh number normalisation (the reference's `zh_num2words.TextNorm`) is not restated.  The zh / ja / ko romanisation is
+  * zh number normalisation is the reference's own `zh_num2words.TextNorm`: restated in `zh_textnorm.py` and pinned against
+    that module (golden records + live fuzz, tests/test_zh_textnorm.py).  The zh / ja / ko romanisation is
     third-party (pypinyin, cutlet, hangul_romanize): it is called exactly as the reference calls it when the package is
     installed, otherwise the text passes through unromanised with a one-time warning.
 """
@@ -576,7 +577,8 @@ def _expand_currency(m, lang: str, code: str, n2w: Verbaliser) -> str:
 def expand_numbers_multilingual(text: str, lang: str = "en", n2w: Optional[Verbaliser] = None) -> str:
     """tokenizer.py:681-700.  `n2w` defaults to `verbalise`; tests inject the marker function shared with the reference."""
     if lang == "zh":
-        return text                     # zh_num2words.TextNorm is not restated (module docstring)
+        from .zh_textnorm import normalize as zh_normalize
+        return zh_normalize(text)       # the reference's own zh_num2words.TextNorm, restated and pinned (zh_textnorm.py)
     n2w = n2w or verbalise
     n2w_lang = lang if lang != "cs" else "cz"
     if lang in ("en", "ru"):

@@ -76,11 +76,11 @@ def main():
                          "out": ref.expand_abbreviations_multilingual(s.lower(), lang)})
             recs.append({"fn": "expand_symbols_multilingual", "lang": lang, "in": s.lower(),
                          "out": ref.expand_symbols_multilingual(s.lower(), lang)})
-            if lang != "zh":                                                 # zh numbers: zh_num2words.TextNorm (not restated)
-                recs.append({"fn": "expand_numbers_multilingual", "lang": lang, "in": s.lower(),
-                             "out": ref.expand_numbers_multilingual(s.lower(), lang)})
-                recs.append({"fn": "multilingual_cleaners", "lang": lang, "in": s,
-                             "out": ref.multilingual_cleaners(s, lang)})
+            # (zh numbers go through the reference's own zh_num2words.TextNorm, not num2words)
+            recs.append({"fn": "expand_numbers_multilingual", "lang": lang, "in": s.lower(),
+                         "out": ref.expand_numbers_multilingual(s.lower(), lang)})
+            recs.append({"fn": "multilingual_cleaners", "lang": lang, "in": s,
+                         "out": ref.multilingual_cleaners(s, lang)})
     recs.append({"fn": "basic_cleaners", "lang": "xx", "in": "MiXed   Case\n\tText", "out": ref.basic_cleaners("MiXed   Case\n\tText")})
     rng = random.Random(20240917)
     for i, (lang, limit) in enumerate([("en", 250), ("en", 120), ("de", 253), ("it", 213), ("pt", 203), ("ar", 166), ("ja", 71),

@@ -43,6 +43,7 @@ def test_golden_vectors_from_the_reference():
     # every cleaned language is covered by every table-driven stage
     for lang in ["en", "es", "fr", "de", "it", "pt", "pl", "ar", "zh", "cs", "ru", "nl", "tr", "hu", "ko"]:
         assert ("expand_abbreviations_multilingual", lang) in seen and ("expand_symbols_multilingual", lang) in seen
+        assert ("expand_numbers_multilingual", lang) in seen and ("multilingual_cleaners", lang) in seen
 
 
 @pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
@@ -51,7 +52,7 @@ def test_live_against_the_reference_module():
     ref = ref_text.load()
     rng = random.Random(7)
     alphabet = "abc dr. mr. sr. st. co. 1 2 3 12 1.234 5,50 $ £ € % & # @ ° º ª th st er e . , ; ! ?".split(" ")
-    for lang in ["en", "es", "fr", "de", "it", "pt", "pl", "ar", "cs", "ru", "nl", "tr", "hu", "ko"]:
+    for lang in ["en", "es", "fr", "de", "it", "pt", "pl", "ar", "zh", "cs", "ru", "nl", "tr", "hu", "ko"]:
         for _ in range(60):
             s = " ".join(rng.choice(alphabet) for _ in range(rng.randint(1, 14)))
             if rng.random() < 0.5:
@@ -139,7 +140,7 @@ def test_romanisation_hooks_follow_the_reference_wiring(monkeypatch):
     T._TRANSLIT_CACHE.clear(); T._TRANSLIT_WARNED.clear()
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
-        assert T.preprocess_text("你好 20%", "zh-cn") == "你好 20 百分之"              # cleaners still run; no pypinyin here
+        assert T.preprocess_text("你好 20%", "zh-cn") == "你好 百分之二十"              # cleaners still run; no pypinyin here
         assert T.preprocess_text("こんにちは", "ja") == "こんにちは"
     assert any("pypinyin" in str(x.message) for x in w) and any("cutlet" in str(x.message) for x in w)
     calls = {}
