@@ -1,0 +1,143 @@
+"""CPU, container only: the public façade (`auralis_b200.TTS` / `TTSRequest` / `TTSOutput`) against the REFERENCE's own
+classes (`auralis.core.tts.TTS` etc., imported unmodified by oracle/ref_facade.py).  Both are driven by the same fake engine
+— per chunk one waveform whose values encode (request text length, chunk index), earlier chunks finishing LATER — and must
+return the same audio in the same order for: one-shot generation, streaming, several chunks, the 100 000-character request
+split (`split_requests`), a prepared speaker (`prepare_for_streaming_generation`), the async API, and a failing chunk."""
+import asyncio
+
+import numpy as np
+import pytest
+
+import auralis_b200 as ours
+from oracle import ref_import
+
+pytestmark = [pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted"), pytest.mark.timeout(120)]
+
+
+def make_engine(ns_output, cond_config, fail_at=None):
+    """A fake engine speaking the plugin API (`models/base.py:57-224`); `ns_output` is the TTSOutput class of the side under
+    test, so each façade receives its own output type."""
+
+    class Engine:
+        def __init__(self):
+            self.cond_calls = 0
+
+        @property
+        def conditioning_config(self):
+            return cond_config
+
+        async def get_audio_conditioning(self, speaker_files, *a, **k):
+            self.cond_calls += 1
+            return np.full((1, 32, 8), 0.5, np.float32), np.full((1, 4, 1), 0.25, np.float32)
+
+        async def get_generation_context(self, request, gpt_cond_latent=None, speaker_embeddings=None):
+            if gpt_cond_latent is None:
+                gpt_cond_latent, speaker_embeddings = await self.get_audio_conditioning(request.speaker_files)
+            n = max(1, len(request.text) // 10)
+
+            async def gen(i):
+                await asyncio.sleep(0.003 * (n - i))
+                if fail_at == i:
+                    raise RuntimeError(f"chunk {i} exploded")
+                yield (len(request.text), i)
+            return [gen(i) for i in range(n)], [f"{request.request_id}_{i}" for i in range(n)], speaker_embeddings, [gpt_cond_latent] * n
+
+        async def process_tokens_to_speech(self, generator, speaker_embeddings, multimodal_data=None, request=None):
+            assert speaker_embeddings is not None and multimodal_data is not None
+            async for (L, i) in generator:
+                yield ns_output(array=np.full(3 + i, float(1000 * L + i), np.float32), token_length=i + 1,
+                                start_time=getattr(request, "start_time", None))
+
+        async def shutdown(self):
+            pass
+    return Engine()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_facade
+    return ref_facade.load()
+
+
+def _sides(ref, **kw):
+    from auralis_b200.base import ConditioningConfig as OursCC
+    import importlib
+    RefCC = importlib.import_module("auralis.models.base").ConditioningConfig
+    r = ref.TTS(scheduler_max_concurrency=4)
+    r._ensure_event_loop()
+    r.tts_engine = make_engine(ref.TTSOutput, RefCC(speaker_embeddings=True, gpt_like_decoder_conditioning=True), **kw)
+    o = ours.TTS(scheduler_max_concurrency=4).from_engine(make_engine(ours.TTSOutput, OursCC(True, True), **kw))
+    return (r, ref.TTSRequest), (o, ours.TTSRequest)
+
+
+@pytest.mark.parametrize("n_chars", [5, 55, 200])
+def test_generate_speech_same_audio(ref, n_chars):
+    res = []
+    for tts, Req in _sides(ref):
+        out = tts.generate_speech(Req(text="x" * n_chars, speaker_files=["s.wav"], language="en"))
+        res.append((np.asarray(out.array), out.sample_rate))
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    assert res[0][1] == res[1][1] == 24000
+
+
+def test_streaming_same_chunks_in_same_order(ref):
+    res = []
+    for tts, Req in _sides(ref):
+        chunks = list(tts.generate_speech(Req(text="y" * 64, speaker_files=["s.wav"], language="en", stream=True)))
+        res.append([(np.asarray(c.array).tolist(), c.token_length) for c in chunks])
+    assert res[0] == res[1] and len(res[0]) == 6
+
+
+def test_long_request_is_split_like_the_reference(ref):
+    res = []
+    for tts, Req in _sides(ref):
+        req = Req(text="z" * 250_035, speaker_files=["s.wav"], language="en")
+        parts = tts.split_requests(req, max_length=100_000)
+        res.append([len(p.text) for p in parts])
+        assert len({p.request_id for p in parts}) == len(parts)
+    assert res[0] == res[1] == [100_000, 100_000, 50_035]
+    # and the audio of a (smaller) split request is the concatenation of its parts, in order
+    res = []
+    for tts, Req in _sides(ref):
+        tts.split_requests = lambda request, max_length=100000, _f=type(tts).split_requests: _f(request, 30)
+        out = tts.generate_speech(Req(text="w" * 75, speaker_files=["s.wav"], language="en"))
+        res.append(np.asarray(out.array))
+    np.testing.assert_array_equal(res[0], res[1])
+
+
+def test_prepared_speaker_and_async_api(ref):
+    res = []
+    for tts, Req in _sides(ref):
+        base = Req(text="q" * 40, speaker_files=["s.wav"], language="en")
+        fn = tts.loop.run_until_complete(tts.prepare_for_streaming_generation(base))
+        calls = tts.tts_engine.cond_calls
+
+        async def go():
+            a = await tts.generate_speech_async(Req(text="q" * 40, speaker_files=["s.wav"], language="en", context_partial_function=fn))
+            gen = await tts.generate_speech_async(Req(text="q" * 30, speaker_files=["s.wav"], language="en", stream=True,
+                                                      context_partial_function=fn))
+            b = [np.asarray(c.array).tolist() async for c in gen]
+            return np.asarray(a.array).tolist(), b
+        res.append(tts.loop.run_until_complete(go()))
+        assert tts.tts_engine.cond_calls == calls                  # the prepared conditioning is reused, not recomputed
+    assert res[0] == res[1]
+
+
+def test_failing_chunk_raises_the_same_error(ref):
+    errs = []
+    for tts, Req in _sides(ref, fail_at=1):
+        with pytest.raises(Exception) as ei:
+            tts.generate_speech(Req(text="x" * 30, speaker_files=["s.wav"], language="en"))
+        errs.append((type(ei.value).__name__, str(ei.value)))
+    assert errs[0] == errs[1] == ("RuntimeError", "chunk 1 exploded")
+
+
+def test_request_defaults_and_validation_match(ref):
+    a = ref.TTSRequest(text="hi", speaker_files=["a.wav"])
+    b = ours.TTSRequest(text="hi", speaker_files=["a.wav"])
+    for f in ("temperature", "top_p", "top_k", "repetition_penalty", "length_penalty", "do_sample", "max_ref_length", "gpt_cond_len",
+              "gpt_cond_chunk_len", "stream", "enhance_speech", "load_sample_rate", "sound_norm_refs", "language"):
+        assert getattr(a, f) == getattr(b, f), f
+    for cls in (ref.TTSRequest, ours.TTSRequest):
+        with pytest.raises(ValueError):
+            cls(text="hi", speaker_files=["a.wav"], language="klingon")
