@@ -87,8 +87,8 @@ class TTSOutput:
         if format == "pcm":
             if sample_width == 2:
                 return (wav * 32767).astype(np.int16).tobytes()
-            if sample_width == 4:
-                return (wav.astype(np.float64) * 2147483647).astype(np.int32).tobytes()
+            if sample_width == 4:       # float32 arithmetic, as the reference's torch expression (output.py:177-178)
+                return (wav * np.float32(2147483647)).astype(np.int32).tobytes()
             return (wav * 127).astype(np.int8).tobytes()
         if format == "wav":
             buf = io.BytesIO()
@@ -117,13 +117,21 @@ class TTSOutput:
             f.write(out.to_bytes(fmt))
 
     def resample(self, new_sample_rate: int) -> "TTSOutput":
-        if new_sample_rate == self.sample_rate:
-            return self
-        from math import gcd
-        from scipy.signal import resample_poly
-        g = gcd(int(new_sample_rate), int(self.sample_rate))
-        y = resample_poly(np.asarray(self.array, np.float32), new_sample_rate // g, self.sample_rate // g)
-        return TTSOutput(array=y.astype(np.float32), sample_rate=new_sample_rate)
+        """output.py:224-246: torchaudio's windowed-sinc resampler, like the reference; scipy's polyphase filter only when
+        torchaudio cannot be imported."""
+        try:
+            import torch
+            import torchaudio
+            y = torchaudio.functional.resample(torch.from_numpy(np.ascontiguousarray(self.array, np.float32))[None],
+                                               orig_freq=self.sample_rate, new_freq=new_sample_rate).squeeze().numpy()
+        except ImportError:
+            if new_sample_rate == self.sample_rate:
+                return self
+            from math import gcd
+            from scipy.signal import resample_poly
+            g = gcd(int(new_sample_rate), int(self.sample_rate))
+            y = resample_poly(np.asarray(self.array, np.float32), new_sample_rate // g, self.sample_rate // g).astype(np.float32)
+        return TTSOutput(array=y, sample_rate=new_sample_rate)
 
     def change_speed(self, speed_factor: float) -> "TTSOutput":
         if speed_factor <= 0:

@@ -141,3 +141,29 @@ def test_request_defaults_and_validation_match(ref):
     for cls in (ref.TTSRequest, ours.TTSRequest):
         with pytest.raises(ValueError):
             cls(text="hi", speaker_files=["a.wav"], language="klingon")
+
+
+def test_output_helpers_match(ref):
+    """TTSOutput: bytes constructor (int16 + fade-in), combine_outputs, pcm encodings, resample, get_info, from_tensor."""
+    import torch
+    rng = np.random.RandomState(1)
+    x = (rng.rand(4800).astype(np.float32) * 1.9 - 0.95)
+    pcm = (rng.randint(-30000, 30000, size=600)).astype(np.int16).tobytes()
+    sides = []
+    for Out in (ref.TTSOutput, ours.TTSOutput):
+        a, b, c = Out(array=x.copy()), Out(array=x[::-1].copy()), Out(array=pcm)
+        comb = Out.combine_outputs([a, b, c])
+        rs = a.resample(16000)
+        sides.append(dict(
+            from_bytes=np.asarray(c.array), comb=np.asarray(comb.array), comb_sr=comb.sample_rate,
+            pcm2=a.to_bytes("pcm", 2), pcm4=a.to_bytes("pcm", 4), pcm1=a.to_bytes("pcm", 1),
+            rs=np.asarray(rs.array), rs_sr=rs.sample_rate, info=a.get_info(),
+            ft=np.asarray(Out.from_tensor(torch.from_numpy(x)[None], 22050).array), tensor=a.to_tensor().numpy()))
+        with pytest.raises(ValueError):
+            a.to_bytes("ogg")
+    r, o = sides
+    for k in r:
+        if isinstance(r[k], np.ndarray):
+            np.testing.assert_array_equal(o[k], r[k], err_msg=k)
+        else:
+            assert o[k] == r[k], k
