@@ -133,3 +133,39 @@ def test_topk_topp_mask_matches_installed_vllm_sampler():
         got = O.topk_topp_mask(z.clone(), k, p)
         assert torch.equal(torch.isinf(got), torch.isinf(want)), (trial, V, k, p)
         assert torch.equal(got[~torch.isinf(got)], want[~torch.isinf(want)])
+
+
+def _reference_penalizer():
+    """`LogitsRepetitionPenalizer` lifted by source out of the reference's hijack.py (the module itself imports vLLM 0.6.4)."""
+    import ast
+    path = "/root/reference/src/auralis/models/xttsv2/components/vllm/hijack.py"
+    if not os.path.exists(path):
+        return None
+    tree = ast.parse(open(path).read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "LogitsRepetitionPenalizer"]
+    from typing import List
+    ns = {"torch": torch, "List": List}
+    exec(compile(ast.Module(body=cls, type_ignores=[]), path, "exec"), ns)
+    return ns["LogitsRepetitionPenalizer"]
+
+
+def test_repetition_penalty_matches_the_reference_class(dims_small):
+    """hijack.py:49-88 — the reference's OWN penaliser, run as-is on the prompt the reference builds
+    (`[1]*(32+Lt)+[start]`, vllm_mm_gpt.py:325) plus a generated history with repeats."""
+    Pen = _reference_penalizer()
+    if Pen is None:
+        pytest.skip("reference tree not mounted")
+    g = dims_small.gpt
+    rng = np.random.RandomState(4)
+    for trial in range(20):
+        V = g.n_audio_tokens
+        z = torch.from_numpy(rng.randn(V).astype(np.float32) * 3)
+        n_text = int(rng.randint(3, 20))
+        prompt = [1] * (g.n_cond_latents + n_text) + [g.start_audio_token]
+        gen = rng.randint(0, V, size=int(rng.randint(0, 30))).tolist()
+        gen = gen + gen[:3]                                              # repeats must be penalised once
+        p = [5.0, 1.0, 2.5, 0.5][trial % 4]
+        want = Pen(p)(prompt, gen, z.clone())
+        seen = O.prompt_seen_set(g) | set(gen)
+        got = O.apply_repetition_penalty(z.clone(), seen, p)
+        assert torch.equal(got, want), (trial, p)
