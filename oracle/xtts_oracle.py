@@ -12,6 +12,10 @@ Parity pin status
   by ``tests/test_oracle_vs_reference.py`` (container only) and against the golden
   vectors those modules produced (``tests/golden/*.npz``, generator
   ``tests/golden/make_golden.py``) everywhere else.  -> pinned to reference outputs.
+  The reference-audio chunking around them (``XTTSv2Engine.get_gpt_cond_latents``: truncation, pieces, the 0.33 s drop,
+  the mean) and the repetition penaliser (``LogitsRepetitionPenalizer``) are the reference's own code inside modules
+  that import vLLM 0.6.4: those two are lifted BY SOURCE and executed as written against the restatement
+  (``tests/test_oracle_vs_reference.py``, ``tests/test_oracle_gpt.py``).
 * GPT block arithmetic + sampler live in third-party vLLM 0.6.4.post1
   (requirements.txt:31), not vendored under /root/reference and not installable here
   (SURVEY.md §8c).  They are restated from the reference's call sites and checked

@@ -79,3 +79,43 @@ def test_speaker_encoder_live(ref, dims_small, state_small):
         with torch.no_grad():
             want = se.forward(wav16[None].clone(), l2_norm=True)[0]
         np.testing.assert_allclose(O.speaker_embedding(wav16, cs, dims).numpy(), want.numpy(), atol=2e-6, rtol=0)
+
+
+def _lift_methods(path, cls_name, names):
+    """Methods of a reference class lifted by source into plain functions (the module itself imports vLLM 0.6.4)."""
+    import ast
+    tree = ast.parse(open(path).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls_name)
+    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert len(fns) == len(names)
+    return fns
+
+
+def test_gpt_cond_latents_chunking_live(ref, dims_small, state_small):
+    """XTTSv2Engine.get_gpt_cond_latents (XTTSv2.py:349-407) run AS WRITTEN — truncation to `length` seconds, `chunk_length`
+    pieces, pieces under 0.33 s dropped, mean over pieces — on the reference's own encoder modules, against the oracle."""
+    import ast
+    import types
+    from typing import Optional
+    import torchaudio
+    cs, dims = state_small[1], dims_small
+    path = os.path.join(ref_import.REF_SRC, "auralis", "models", "xttsv2", "XTTSv2.py")
+    fns = _lift_methods(path, "XTTSv2Engine", ("get_gpt_cond_latents", "get_style_emb"))
+    ns = {"torch": torch, "torchaudio": torchaudio, "wav_to_mel_cloning": ref.wav_to_mel_cloning, "Optional": Optional}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), path, "exec"), ns)
+    ce = ref.ConditioningEncoder(dims.cond.n_mels, dims.gpt.hidden, attn_blocks=dims.cond.cond_blocks, num_attn_heads=dims.gpt.heads)
+    ce.load_state_dict({k[len("conditioning_encoder."):]: t for k, t in cs.items() if k.startswith("conditioning_encoder.")})
+    pr = ref.PerceiverResampler(dim=dims.gpt.hidden, depth=dims.cond.perceiver_depth, dim_context=dims.gpt.hidden,
+                                num_latents=dims.gpt.n_cond_latents, dim_head=dims.cond.perceiver_dim_head,
+                                heads=dims.cond.perceiver_heads, ff_mult=dims.cond.perceiver_ff_mult, use_flash_attn=False)
+    pr.load_state_dict({k[len("conditioning_perceiver."):]: t for k, t in cs.items() if k.startswith("conditioning_perceiver.")})
+    me = types.SimpleNamespace(gpt_config=types.SimpleNamespace(use_perceiver_resampler=True), mel_stats=cs["mel_stats"],
+                               device=torch.device("cpu"), conditioning_encoder=ce, conditioning_perceiver=pr)
+    me.get_style_emb = lambda mel, rl=False: ns["get_style_emb"](me, mel, rl)
+    for seconds, length, chunk in ((2.6, 30, 1), (2.6, 2, 1), (1.2, 30, 4), (2.2, 30, 1)):     # 2.2 s / 1 s: last piece 0.2 s is dropped
+        wav = O.synthetic_reference_wav(seconds, 22050, 140.0, 31)
+        with torch.no_grad():
+            want = ns["get_gpt_cond_latents"](me, wav[None], 22050, length=length, chunk_length=chunk)[0]      # [32, H]
+        got = O.gpt_cond_latents(wav, cs, dims, length=length, chunk_length=chunk)
+        assert got.shape == want.shape == (dims.gpt.n_cond_latents, dims.gpt.hidden)
+        np.testing.assert_allclose(got.numpy(), want.numpy(), atol=5e-5, rtol=0)
