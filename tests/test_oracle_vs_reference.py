@@ -86,7 +86,7 @@ def _lift_methods(path, cls_name, names):
     import ast
     tree = ast.parse(open(path).read())
     cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls_name)
-    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    fns = [n for n in cls.body if isinstance(n, (ast.FunctionDef, ast.AsyncFunctionDef)) and n.name in names]
     assert len(fns) == len(names)
     return fns
 
@@ -119,3 +119,50 @@ def test_gpt_cond_latents_chunking_live(ref, dims_small, state_small):
         got = O.gpt_cond_latents(wav, cs, dims, length=length, chunk_length=chunk)
         assert got.shape == want.shape == (dims.gpt.n_cond_latents, dims.gpt.hidden)
         np.testing.assert_allclose(got.numpy(), want.numpy(), atol=5e-5, rtol=0)
+
+
+def test_prompt_construction_live(dims_small, state_small, speakers_small):
+    """Rows a1-a2 of the hot path: XTTSv2Engine.prepare_text_tokens_async + _merge_conditioning (XTTSv2.py:506-543,330-347)
+    and LearnedPositionEmbeddings (vllm_mm_gpt.py:165-214), lifted by source and executed as written with the synthetic
+    embedding tables, against the oracle's prompt rows ([cond latents ; text_emb + text_pos] — the audio-bos row is added by
+    the GPT wrapper, vllm_mm_gpt.py:806-813)."""
+    import ast
+    import asyncio
+    import logging
+    import random
+    import types
+    from typing import List, Tuple, Union
+    gs, cs = state_small
+    g = dims_small.gpt
+    base = os.path.join(ref_import.REF_SRC, "auralis", "models", "xttsv2")
+    fns = _lift_methods(os.path.join(base, "XTTSv2.py"), "XTTSv2Engine", ("prepare_text_tokens_async", "_merge_conditioning"))
+    tree = ast.parse(open(os.path.join(base, "components", "vllm_mm_gpt.py")).read())
+    lpe = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "LearnedPositionEmbeddings"]
+    ns = {"torch": torch, "nn": torch.nn, "random": random, "List": List, "Tuple": Tuple, "Union": Union}
+    exec(compile(ast.Module(body=lpe + fns, type_ignores=[]), "lifted", "exec"), ns)
+    text_emb = torch.nn.Embedding(g.n_text_tokens, g.hidden)
+    text_emb.weight.data.copy_(cs["text_embedding.weight"])
+    text_pos = ns["LearnedPositionEmbeddings"](g.max_text_tokens + 2, g.hidden)
+    text_pos.emb.weight.data.copy_(cs["text_pos_embedding.emb.weight"])
+    orc = O.GPTOracle(gs, cs, dims_small)
+    for n_chunks, seed in ((1, 0), (3, 1)):
+        rng = np.random.RandomState(seed)
+        chunks = [rng.randint(2, g.n_text_tokens, size=int(rng.randint(1, g.max_text_tokens - 1))).tolist() for _ in range(n_chunks)]
+        tok = types.SimpleNamespace(bos_token_id=0, eos_token_id=1,
+                                    batch_encode_with_split=lambda text, lang, _c=chunks: [list(c) for c in _c])
+        me = types.SimpleNamespace(tokenizer=tok, text_embedding=text_emb, text_pos_embedding=text_pos, logger=logging.getLogger("x"),
+                                   llm_engine=types.SimpleNamespace(engine=types.SimpleNamespace(model_config=types.SimpleNamespace(dtype=torch.float32))))
+        cond = speakers_small[0][0]                                        # [32, H]
+
+        async def go():
+            fake, embeds = await ns["prepare_text_tokens_async"](me, "ignored", "en", split_text=True)
+            merged = await ns["_merge_conditioning"](me, embeds, cond[None])
+            return fake, merged
+        with torch.no_grad():
+            fake, merged = asyncio.new_event_loop().run_until_complete(go())
+        assert [len(f) for f in fake] == [len(c) + 2 for c in chunks]       # placeholder ids [1]*(L+2) (App. A.2)
+        for c, m in zip(chunks, merged):
+            ids = [0] + c + [1]
+            rows = orc.prompt_rows(cond, ids)
+            assert rows.shape[0] == g.n_cond_latents + len(ids) + 1
+            np.testing.assert_allclose(rows[:-1].numpy(), m.numpy(), atol=1e-6, rtol=0)
