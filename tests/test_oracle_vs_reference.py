@@ -166,3 +166,49 @@ def test_prompt_construction_live(dims_small, state_small, speakers_small):
             rows = orc.prompt_rows(cond, ids)
             assert rows.shape[0] == g.n_cond_latents + len(ids) + 1
             np.testing.assert_allclose(rows[:-1].numpy(), m.numpy(), atol=1e-6, rtol=0)
+
+
+def test_gpt_wrapper_embedding_and_splice_live(dims_small, state_small, speakers_small):
+    """Row a5: the embedding / conditioning-splice part of the reference's GPT2Model.forward (vllm_mm_gpt.py:768-833) lifted by
+    source and executed as written with zero transformer layers: prefill rows = [prefix ; wte[start] + wpe[0]], decode row k =
+    wte[t_k] + wpe[k], and a mixed prefill + decode batch — against the oracle's prompt_rows / audio_row."""
+    import __future__
+    import ast
+    import random
+    import types
+    gs, cs = state_small
+    g = dims_small.gpt
+    path = os.path.join(ref_import.REF_SRC, "auralis", "models", "xttsv2", "components", "vllm_mm_gpt.py")
+    tree = ast.parse(open(path).read())
+    lpe = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "LearnedPositionEmbeddings"]
+    fns = _lift_methods(path, "GPT2Model", ("forward", "_insert_conditioning_into_hidden_states"))
+    for f in fns:
+        f.decorator_list = []
+    ns = {"torch": torch, "nn": torch.nn, "random": random,
+          "get_pp_group": lambda: types.SimpleNamespace(is_first_rank=True, is_last_rank=True)}
+    exec(compile(ast.Module(body=lpe + fns, type_ignores=[]), "lifted", "exec", flags=__future__.annotations.compiler_flag), ns)
+    wte = torch.nn.Embedding(g.n_audio_tokens, g.hidden)
+    wte.weight.data.copy_(gs["gpt.wte.weight"])
+    wpe = ns["LearnedPositionEmbeddings"](g.max_audio_tokens + 3, g.hidden)
+    wpe.emb.weight.data.copy_(gs["gpt.wpe.emb.weight"])
+    me = types.SimpleNamespace(wte=wte, wpe=wpe, audio_start_generation_token=g.start_audio_token, embed_dim=g.hidden,
+                               start_layer=0, end_layer=0, h=[], ln_f=lambda x: x,
+                               _insert_conditioning_into_hidden_states=ns["_insert_conditioning_into_hidden_states"])
+    orc = O.GPTOracle(gs, cs, dims_small)
+    cond = speakers_small[1][0]
+    ids = [0, 17, 5, 44, 9, 1]
+    rows = orc.prompt_rows(cond, ids)
+    prefix = rows[:-1]                                                         # what _merge_conditioning hands to vLLM
+    empty = torch.empty(0, dtype=torch.long)
+    with torch.no_grad():
+        got = ns["forward"](me, empty, empty, [], None, None, input_embeds=[prefix[None]], starting_sequence_start_ids=[0],
+                            is_logit_only=torch.tensor([False]))
+        np.testing.assert_allclose(got.numpy(), rows.numpy(), atol=1e-6, rtol=0)
+        for tok, k in ((3, 1), (g.start_audio_token - 1, 7), (60, g.max_audio_tokens)):
+            got = ns["forward"](me, torch.tensor([tok]), torch.tensor([k]), [], None, None)
+            np.testing.assert_allclose(got[0].numpy(), orc.audio_row(tok, k).numpy(), atol=1e-6, rtol=0)
+        # one sequence decoding (row first), another one starting in the same step (spliced after it)
+        got = ns["forward"](me, torch.tensor([9]), torch.tensor([4]), [], None, None, input_embeds=[prefix[None]],
+                            starting_sequence_start_ids=[1], is_logit_only=torch.tensor([False]))
+        want = torch.cat([orc.audio_row(9, 4)[None], rows], dim=0)
+        np.testing.assert_allclose(got.numpy(), want.numpy(), atol=1e-6, rtol=0)
