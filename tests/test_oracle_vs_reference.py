@@ -212,3 +212,24 @@ def test_gpt_wrapper_embedding_and_splice_live(dims_small, state_small, speakers
                             starting_sequence_start_ids=[1], is_logit_only=torch.tensor([False]))
         want = torch.cat([orc.audio_row(9, 4)[None], rows], dim=0)
         np.testing.assert_allclose(got.numpy(), want.numpy(), atol=1e-6, rtol=0)
+
+
+def test_placeholder_prompt_and_penalty_seed_live(dims_small):
+    """Row a3: input_processor_for_xtts2_gpt (vllm_mm_gpt.py:296-334) executed as written — the prompt vLLM sees is
+    [1]*(32+Lt) + [start_audio_token], so the repetition penaliser's prompt set is {1, start} (App. B.7), which is what the
+    oracle and the CUDA sampler seed their 'seen' set with."""
+    import __future__
+    import ast
+    import types
+    path = os.path.join(ref_import.REF_SRC, "auralis", "models", "xttsv2", "components", "vllm_mm_gpt.py")
+    tree = ast.parse(open(path).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "input_processor_for_xtts2_gpt"]
+    ns = {"token_inputs": lambda **kw: kw, "PlaceholderRange": lambda **kw: kw}
+    exec(compile(ast.Module(body=fn, type_ignores=[]), "lifted", "exec", flags=__future__.annotations.compiler_flag), ns)
+    g = dims_small.gpt
+    ctx = types.SimpleNamespace(model_config=types.SimpleNamespace(hf_config=types.SimpleNamespace(start_audio_token=g.start_audio_token)))
+    for n_text in (3, 17):
+        embeds = torch.zeros(g.n_cond_latents + n_text, g.hidden)
+        out = ns["input_processor_for_xtts2_gpt"](ctx, {"multi_modal_data": {"audio": {"embeds": embeds}}, "prompt_token_ids": [1] * n_text})
+        assert out["prompt_token_ids"] == [1] * (g.n_cond_latents + n_text) + [g.start_audio_token]
+        assert set(out["prompt_token_ids"]) == O.prompt_seen_set(g)
