@@ -13,7 +13,7 @@ import os
 import sys
 import types
 
-REF_SRC = "/root/reference/src"
+REF_SRC = os.environ.get("XTTS_REFERENCE_SRC", "/root/reference/src")     # override to test without the tree
 
 
 def available() -> bool:

@@ -138,7 +138,8 @@ def test_topk_topp_mask_matches_installed_vllm_sampler():
 def _reference_penalizer():
     """`LogitsRepetitionPenalizer` lifted by source out of the reference's hijack.py (the module itself imports vLLM 0.6.4)."""
     import ast
-    path = "/root/reference/src/auralis/models/xttsv2/components/vllm/hijack.py"
+    from oracle import ref_import
+    path = os.path.join(ref_import.REF_SRC, "auralis", "models", "xttsv2", "components", "vllm", "hijack.py")
     if not os.path.exists(path):
         return None
     tree = ast.parse(open(path).read())
