@@ -108,11 +108,15 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
     # ---- plugin API -------------------------------------------------------------------------
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path: str, gpt_model: Optional[str] = None, **kwargs):
-        dims, gpt_state, core_state = load_model_dir(pretrained_model_name_or_path, gpt_model)
         import os
-        gdir = gpt_model if gpt_model and os.path.isdir(gpt_model) else os.path.join(pretrained_model_name_or_path, "gpt")
-        tok = os.path.join(gdir, "tokenizer.json")
-        return cls(dims, gpt_state, core_state, tokenizer_file=tok if os.path.exists(tok) else None, **kwargs)
+        from .weights import resolve_model_file
+        dims, gpt_state, core_state = load_model_dir(pretrained_model_name_or_path, gpt_model)
+        if gpt_model and gpt_model.endswith(".safetensors"):
+            gsrc = os.path.dirname(gpt_model)
+        else:
+            gsrc = gpt_model if gpt_model else os.path.join(pretrained_model_name_or_path, "gpt")
+        tok = resolve_model_file(gsrc, "tokenizer.json", required=False)      # local directory or Hub repo (XTTSv2.py:84)
+        return cls(dims, gpt_state, core_state, tokenizer_file=tok if tok and os.path.exists(tok) else None, **kwargs)
 
     @property
     def conditioning_config(self) -> ConditioningConfig:

@@ -42,10 +42,11 @@ class TTS:
         """tts.py:53-89: config.json["model_type"] selects the engine; kwargs (gpt_model=...) are forwarded."""
         from . import engine as _engine  # noqa: F401  (registers "xtts")
         self._ensure_event_loop()
+        from .weights import resolve_model_file
         try:
-            with open(os.path.join(model_name_or_path, "config.json"), "r") as f:
+            with open(resolve_model_file(model_name_or_path, "config.json"), "r") as f:      # local dir, else Hub repo (tts.py:72-84)
                 config = json.load(f)
-        except FileNotFoundError as e:
+        except (FileNotFoundError, NotADirectoryError) as e:
             raise ValueError(f"Could not load model from {model_name_or_path} neither locally or online: {e}")
         kwargs.setdefault("max_concurrency", max(self.concurrency, 1))
         self.tts_engine = MODEL_REGISTRY[config["model_type"]].from_pretrained(model_name_or_path, **kwargs)

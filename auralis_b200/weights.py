@@ -247,6 +247,24 @@ def save_model_dir(path: str, dims: XTTSDims, gpt_state: State, core_state: Stat
         json.dump(cfg["gpt_config"], f)
 
 
+def resolve_model_file(path_or_repo: str, filename: str, required: bool = True) -> str | None:
+    """A file of a model: `<dir>/<filename>` when the directory exists, else the Hugging Face Hub repo of that name —
+    the rule of the reference (`XTTSv2.py:262-298`, `core/tts.py:72-84`: `TTS().from_pretrained("AstraMindAI/xttsv2",
+    gpt_model="AstraMindAI/xtts2-gpt")`)."""
+    if os.path.isdir(path_or_repo):
+        p = os.path.join(path_or_repo, filename)
+        if os.path.exists(p) or required:
+            return p
+        return None
+    try:
+        from huggingface_hub import hf_hub_download
+        return hf_hub_download(repo_id=path_or_repo, filename=filename)
+    except Exception as e:      # noqa: BLE001 — offline, unknown repo, missing file
+        if required:
+            raise ValueError(f"Could not load {filename} from {path_or_repo} neither locally or online: {e}") from e
+        return None
+
+
 def load_model_dir(path: str, gpt_model: str | None = None) -> Tuple[XTTSDims, State, State]:
     """Reads a model directory in either layout:
       * the reference converter's (`utils/checkpoint_converter.py:286-334`): `path` = `.../core_xttsv2` holding
@@ -255,20 +273,23 @@ def load_model_dir(path: str, gpt_model: str | None = None) -> Tuple[XTTSDims, S
       * this package's own (`save_model_dir`): one directory with a `gpt/` sub-directory and the geometry under "b200_dims".
     Tensor names are the converter's in both (`checkpoint_converter.py:225-284`); shapes are checked against the geometry."""
     from safetensors.torch import load_file
-    with open(os.path.join(path, "config.json")) as f:
+    with open(resolve_model_file(path, "config.json")) as f:
         cfg = json.load(f)
-    gdir = gpt_model if gpt_model is not None else os.path.join(path, "gpt")
-    gfile = gdir if gdir.endswith(".safetensors") else os.path.join(gdir, "gpt2_model.safetensors")
+    if gpt_model is not None and gpt_model.endswith(".safetensors"):
+        gfile, gcfg_path = gpt_model, os.path.join(os.path.dirname(gpt_model), "config.json")
+    else:
+        gsrc = gpt_model if gpt_model is not None else os.path.join(path, "gpt")
+        gfile = resolve_model_file(gsrc, "gpt2_model.safetensors")
+        gcfg_path = resolve_model_file(gsrc, "config.json", required=False)
     if "b200_dims" in cfg:
         dims = XTTSDims.from_json(cfg["b200_dims"])
     else:
         gcfg = None
-        gcfg_path = os.path.join(os.path.dirname(gfile), "config.json")
-        if os.path.exists(gcfg_path):
+        if gcfg_path and os.path.exists(gcfg_path):
             with open(gcfg_path) as f:
                 gcfg = json.load(f)
         dims = XTTSDims.from_reference_configs(cfg, gcfg)
-    core = {k: v.float() for k, v in load_file(os.path.join(path, "xtts-v2.safetensors")).items()}
+    core = {k: v.float() for k, v in load_file(resolve_model_file(path, "xtts-v2.safetensors")).items()}
     gpt = {k: v.float() for k, v in load_file(gfile).items()}
     check_state_shapes(dims, gpt, core)
     return dims, gpt, core

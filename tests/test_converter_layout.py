@@ -78,3 +78,33 @@ def test_live_reference_converter_to_loader_round_trip(tmp_path):
     assert not any("dvae" in k for k in list(gs) + list(cs))
     want_g, want_c = _shapes(dims)
     assert {k: tuple(v.shape) for k, v in gs.items()} == want_g and {k: tuple(v.shape) for k, v in cs.items()} == want_c
+
+
+def test_hub_repo_ids_resolve_like_the_reference(tmp_path, monkeypatch):
+    """`from_pretrained("org/repo", gpt_model="org/gpt-repo")`: names that are not local directories are fetched file by file
+    through huggingface_hub (XTTSv2.py:262-298) — here a fake hub that serves files from two local folders."""
+    import huggingface_hub
+    from auralis_b200.weights import resolve_model_file, save_model_dir, synth_state
+    dims = XTTSDims.small()
+    gs, cs = synth_state(dims, 3)
+    save_model_dir(str(tmp_path / "m"), dims, gs, cs)
+    repos = {"Org/xtts-core": tmp_path / "m", "Org/xtts-gpt": tmp_path / "m" / "gpt"}
+    asked = []
+
+    def fake_download(repo_id, filename, **kw):
+        asked.append((repo_id, filename))
+        p = repos[repo_id] / filename
+        if not p.exists():
+            raise FileNotFoundError(filename)
+        return str(p)
+    monkeypatch.setattr(huggingface_hub, "hf_hub_download", fake_download)
+    d2, g2, c2 = load_model_dir("Org/xtts-core", gpt_model="Org/xtts-gpt")
+    assert d2 == dims and set(g2) == set(gs) and set(c2) == set(cs)
+    assert ("Org/xtts-core", "xtts-v2.safetensors") in asked and ("Org/xtts-gpt", "gpt2_model.safetensors") in asked
+    assert resolve_model_file("Org/xtts-gpt", "tokenizer.json", required=False) is None          # optional file: no error
+    with pytest.raises(ValueError, match="neither locally or online"):
+        resolve_model_file("Org/xtts-gpt", "nope.bin")
+    with pytest.raises(ValueError, match="neither locally or online"):
+        from auralis_b200 import TTS
+        monkeypatch.setattr(huggingface_hub, "hf_hub_download", lambda **kw: (_ for _ in ()).throw(OSError("offline")))
+        TTS().from_pretrained("Org/unknown")

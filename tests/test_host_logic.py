@@ -380,8 +380,8 @@ def test_engine_host_path_many_speakers_few_slots():
     for i, o in enumerate(outs):
         want = float(np.round(levels[i % 3] * 1000))
         assert o.array.size >= 16 and np.all(np.abs(o.array - want) <= 1.0), (i, o.array[:4], want)
-    assert eng.native.cond_calls <= 5                                   # 3 speakers (+ re-conditioning after eviction), not 6
-    assert eng.native.get_calls <= 6                                    # only the six concurrent first requests read back
+    assert eng.native.cond_calls <= 6                                   # 3 speakers (+ re-conditioning after an eviction), never one per request and retry
+    assert eng.native.get_calls <= 12                                   # the concurrent first requests read back (+ retries after an eviction)
     assert all(eng._spk.pinned(s) == 0 for s in range(2)) and not eng._waiters
     # later calls are served from the host cache without touching the native layer ...
     n_get, n_cond = eng.native.get_calls, eng.native.cond_calls
