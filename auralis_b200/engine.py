@@ -50,9 +50,9 @@ class ChunkOutput:
 
 def load_audio(source: Union[str, Path, bytes], sampling_rate: int) -> np.ndarray:
     """Mono float32 in [-1,1] at `sampling_rate` (common/utilities.py:74-97).  RIFF/WAV via the standard
-    library (torchaudio.load needs torchcodec, absent here), polyphase resampling via scipy."""
+    library (torchaudio.load needs torchcodec, absent here); resampling through torchaudio.functional.resample like the
+    reference (scipy polyphase only if torchaudio cannot be imported)."""
     import io
-    from math import gcd
     f = io.BytesIO(source) if isinstance(source, (bytes, bytearray)) else str(source)
     with wave.open(f, "rb") as w:
         nch, sw, sr, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
@@ -67,9 +67,7 @@ def load_audio(source: Union[str, Path, bytes], sampling_rate: int) -> np.ndarra
         raise ValueError(f"unsupported WAV sample width {sw}")
     a = a.reshape(-1, nch).mean(axis=1)
     if sr != sampling_rate:
-        from scipy.signal import resample_poly
-        g = gcd(int(sr), int(sampling_rate))
-        a = resample_poly(a, sampling_rate // g, sr // g).astype(np.float32)
+        a = _resample(np.ascontiguousarray(a, np.float32), int(sr), int(sampling_rate))     # torchaudio's sinc resampler, as the reference
     return np.clip(a, -1.0, 1.0).astype(np.float32)
 
 

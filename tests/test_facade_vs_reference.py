@@ -4,6 +4,7 @@ classes (`auralis.core.tts.TTS` etc., imported unmodified by oracle/ref_facade.p
 return the same audio in the same order for: one-shot generation, streaming, several chunks, the 100 000-character request
 split (`split_requests`), a prepared speaker (`prepare_for_streaming_generation`), the async API, and a failing chunk."""
 import asyncio
+import os
 
 import numpy as np
 import pytest
@@ -167,3 +168,46 @@ def test_output_helpers_match(ref):
             np.testing.assert_array_equal(o[k], r[k], err_msg=k)
         else:
             assert o[k] == r[k], k
+
+
+def test_load_audio_matches_the_reference_pipeline(tmp_path):
+    """common/utilities.py:72-97 lifted by source (mono mix, torchaudio resample, clip) with `torchaudio.load` replaced by a
+    stdlib WAV reader (the image has no codec backend): same samples as `auralis_b200.engine.load_audio` for a 48 kHz stereo
+    16-bit file, a 22.05 kHz mono one and in-memory bytes."""
+    import ast
+    import io
+    import types
+    import wave
+    import torch
+    import torchaudio
+    from auralis_b200.engine import load_audio
+
+    def wav_bytes(sr, nch, seconds=0.25, seed=0):
+        rng = np.random.RandomState(seed)
+        x = (rng.rand(int(sr * seconds), nch) * 1.6 - 0.8)
+        buf = io.BytesIO()
+        with wave.open(buf, "wb") as w:
+            w.setnchannels(nch); w.setsampwidth(2); w.setframerate(sr)
+            w.writeframes((x * 32767).astype(np.int16).tobytes())
+        return buf.getvalue()
+
+    def fake_load(src):
+        f = io.BytesIO(src) if isinstance(src, (bytes, bytearray)) else str(src)
+        with wave.open(f, "rb") as w:
+            nch, sr, raw = w.getnchannels(), w.getframerate(), w.readframes(w.getnframes())
+        a = torch.from_numpy(np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0).reshape(-1, nch).t().contiguous()
+        return a, sr
+    path = os.path.join(ref_import.REF_SRC, "auralis", "common", "utilities.py")
+    tree = ast.parse(open(path).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "load_audio"]
+    ns = {"torch": torch, "torchaudio": types.SimpleNamespace(load=fake_load, functional=torchaudio.functional)}
+    exec(compile(ast.Module(body=fn, type_ignores=[]), path, "exec"), ns)
+    for sr, nch in ((48000, 2), (22050, 1), (16000, 1), (44100, 2)):
+        b = wav_bytes(sr, nch, seed=sr)
+        want = ns["load_audio"](b, 22050)[0].numpy()
+        got = load_audio(b, 22050)
+        assert got.dtype == np.float32 and got.shape == want.shape
+        np.testing.assert_allclose(got, want, atol=1e-6, rtol=0)
+        f = tmp_path / f"a{sr}.wav"
+        f.write_bytes(b)
+        np.testing.assert_allclose(load_audio(str(f), 22050), want, atol=1e-6, rtol=0)
