@@ -76,9 +76,12 @@ class TTSRequest:
         if self.language == "auto" and len(self.text) > 0:
             self.language = get_language(self.text if isinstance(self.text, str) else " ".join(self.text))
         validate_language(self.language)
-        if self.enhance_speech:
-            raise NotImplementedError("enhance_speech (reference-audio clean-up, enhancer.py) is CPU DSP outside "
-                                      "the hot path and is not provided")
+        if self.enhance_speech and isinstance(self.speaker_files, list):
+            # requests.py:199-203 + 214-247: the reference cleans the reference audio on the CPU (librosa / pyloudnorm) and
+            # falls back to the original file when that fails.  That DSP is outside the hot path and not provided here:
+            # same fallback, said once.
+            warnings.warn("enhance_speech: reference-audio enhancement is not provided, the original speaker files are used",
+                          RuntimeWarning, stacklevel=2)
 
     def infer_language(self):
         if self.language == "auto":
