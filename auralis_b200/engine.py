@@ -18,7 +18,6 @@ import asyncio
 import hashlib
 import threading
 import time
-import wave
 from pathlib import Path
 from typing import AsyncGenerator, Dict, List, Optional, Tuple, Union
 
@@ -49,23 +48,24 @@ class ChunkOutput:
 
 
 def load_audio(source: Union[str, Path, bytes], sampling_rate: int) -> np.ndarray:
-    """Mono float32 in [-1,1] at `sampling_rate` (common/utilities.py:74-97).  RIFF/WAV via the standard
-    library (torchaudio.load needs torchcodec, absent here); resampling through torchaudio.functional.resample like the
-    reference (scipy polyphase only if torchaudio cannot be imported)."""
-    import io
-    f = io.BytesIO(source) if isinstance(source, (bytes, bytearray)) else str(source)
-    with wave.open(f, "rb") as w:
-        nch, sw, sr, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
-        raw = w.readframes(n)
-    if sw == 2:
-        a = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
-    elif sw == 4:
-        a = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
-    elif sw == 1:
-        a = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+    """Mono float32 in [-1,1] at `sampling_rate` (common/utilities.py:72-97: mean over channels, torchaudio sinc resampling,
+    clip).  RIFF/WAV — integer PCM and IEEE float — is decoded here (torchaudio.load needs a codec backend this image does
+    not ship); any other container goes through torchaudio.load when it can."""
+    from .output import _parse_riff_wav
+    if isinstance(source, (bytes, bytearray)):
+        blob = bytes(source)
     else:
-        raise ValueError(f"unsupported WAV sample width {sw}")
-    a = a.reshape(-1, nch).mean(axis=1)
+        with open(str(source), "rb") as f:
+            blob = f.read()
+    parsed = _parse_riff_wav(blob)
+    if parsed is None:
+        import io
+        import torchaudio
+        wav, sr = torchaudio.load(io.BytesIO(blob) if isinstance(source, (bytes, bytearray)) else str(source))
+        a = wav.mean(dim=0).numpy()
+    else:
+        frames, sr = parsed
+        a = frames.mean(axis=1)
     if sr != sampling_rate:
         a = _resample(np.ascontiguousarray(a, np.float32), int(sr), int(sampling_rate))     # torchaudio's sinc resampler, as the reference
     return np.clip(a, -1.0, 1.0).astype(np.float32)

@@ -16,6 +16,66 @@ from typing import List, Optional, Union
 import numpy as np
 
 
+def _riff_wav(x: np.ndarray, sample_rate: int, bits: int) -> bytes:
+    """Mono RIFF/WAVE: 32 bits -> IEEE float (format tag 3), 16 / 8 -> integer PCM (tag 1)."""
+    import struct
+    x = np.clip(x, -1.0, 1.0)
+    if bits == 32:
+        tag, payload = 3, x.astype("<f4").tobytes()
+    elif bits == 16:
+        tag, payload = 1, (x * 32767).astype("<i2").tobytes()
+    elif bits == 8:
+        tag, payload = 1, ((x * 127) + 128).astype(np.uint8).tobytes()
+    else:
+        raise ValueError(f"unsupported bit depth {bits}")
+    block = bits // 8
+    fmt = struct.pack("<HHIIHH", tag, 1, sample_rate, sample_rate * block, block, bits)
+    body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt
+    if tag == 3:
+        body += b"fact" + struct.pack("<II", 4, x.shape[0])
+    body += b"data" + struct.pack("<I", len(payload)) + payload
+    return b"RIFF" + struct.pack("<I", len(body)) + body
+
+
+def _parse_riff_wav(blob: bytes):
+    """-> (float32 [frames, channels], sample_rate) for integer-PCM (8/16/24/32 bit) and IEEE-float (32/64 bit) WAV, else None."""
+    import struct
+    if len(blob) < 12 or blob[:4] != b"RIFF" or blob[8:12] != b"WAVE":
+        return None
+    pos, fmt, data = 12, None, None
+    while pos + 8 <= len(blob):
+        cid, size = blob[pos:pos + 4], struct.unpack("<I", blob[pos + 4:pos + 8])[0]
+        chunk = blob[pos + 8:pos + 8 + size]
+        if cid == b"fmt ":
+            fmt = struct.unpack("<HHIIHH", chunk[:16])
+            if fmt[0] == 0xFFFE and len(chunk) >= 26:             # WAVE_FORMAT_EXTENSIBLE: the real tag is in the sub-format GUID
+                fmt = (struct.unpack("<H", chunk[24:26])[0],) + fmt[1:]
+        elif cid == b"data":
+            data = chunk
+        pos += 8 + size + (size & 1)
+    if fmt is None or data is None:
+        return None
+    tag, nch, sr, _, _, bits = fmt
+    if tag == 1 and bits == 16:
+        a = np.frombuffer(data, dtype="<i2").astype(np.float32) / 32768.0
+    elif tag == 1 and bits == 8:
+        a = (np.frombuffer(data, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+    elif tag == 1 and bits == 32:
+        a = np.frombuffer(data, dtype="<i4").astype(np.float32) / 2147483648.0
+    elif tag == 1 and bits == 24:
+        b = np.frombuffer(data[: len(data) // 3 * 3], dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+        a = (np.where(v >= 1 << 23, v - (1 << 24), v)).astype(np.float32) / 8388608.0
+    elif tag == 3 and bits == 32:
+        a = np.frombuffer(data, dtype="<f4").astype(np.float32)
+    elif tag == 3 and bits == 64:
+        a = np.frombuffer(data, dtype="<f8").astype(np.float32)
+    else:
+        return None
+    n = a.shape[0] // nch * nch
+    return a[:n].reshape(-1, nch), int(sr)
+
+
 @dataclass
 class TTSOutput:
     array: Union[np.ndarray, bytes]
@@ -111,10 +171,16 @@ class TTSOutput:
         raise ValueError(f"Unsupported format: {format}. Supported formats are: mp3, opus, aac, flac, wav, pcm")
 
     def save(self, filename: Union[str, Path], sample_rate: Optional[int] = None, format: Optional[str] = None) -> None:
+        """output.py:189-222: resample if asked, then write with `bits_per_sample = bit_depth` — 32 (the default) is an
+        IEEE-float WAV, which is what torchaudio writes for the reference; other containers go through `to_bytes`."""
         out = self if not sample_rate or sample_rate == self.sample_rate else self.resample(sample_rate)
         fmt = format or (Path(filename).suffix.lstrip(".") or "wav")
+        if fmt == "wav":
+            data = _riff_wav(np.asarray(out.array, np.float32), out.sample_rate, self.bit_depth)
+        else:
+            data = out.to_bytes(fmt)
         with open(filename, "wb") as f:
-            f.write(out.to_bytes(fmt))
+            f.write(data)
 
     def resample(self, new_sample_rate: int) -> "TTSOutput":
         """output.py:224-246: torchaudio's windowed-sinc resampler, like the reference; scipy's polyphase filter only when
@@ -161,24 +227,15 @@ class TTSOutput:
     def from_file(cls, filename: Union[str, Path]) -> "TTSOutput":
         """output.py:274-285.  RIFF/WAV through the standard library (the reference's torchaudio.load needs a codec
         backend that this image does not ship); other containers go through torchaudio when it can load them."""
-        try:
-            with wave.open(str(filename), "rb") as w:
-                nch, sw, sr, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
-                raw = w.readframes(n)
-        except wave.Error:
+        with open(str(filename), "rb") as f:
+            blob = f.read()
+        parsed = _parse_riff_wav(blob)
+        if parsed is None:                                   # not RIFF/WAVE (or an exotic encoding): torchaudio's loaders
             import torchaudio
             wav, sr = torchaudio.load(str(filename))
             return cls.from_tensor(wav, sr)
-        if sw == 2:
-            a = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
-        elif sw == 4:
-            a = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
-        elif sw == 1:
-            a = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
-        else:
-            raise ValueError(f"unsupported WAV sample width {sw}")
-        a = a.reshape(-1, nch)
-        return cls(array=(a[:, 0] if nch == 1 else a.T).copy(), sample_rate=sr)
+        a, sr = parsed
+        return cls(array=(a[:, 0] if a.shape[1] == 1 else a.T).copy(), sample_rate=sr)
 
     def play(self) -> None:
         """output.py:287-303 (needs the optional `sounddevice` package, like the reference)."""

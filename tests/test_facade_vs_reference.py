@@ -211,3 +211,7 @@ def test_load_audio_matches_the_reference_pipeline(tmp_path):
         f = tmp_path / f"a{sr}.wav"
         f.write_bytes(b)
         np.testing.assert_allclose(load_audio(str(f), 22050), want, atol=1e-6, rtol=0)
+    # IEEE-float WAV (what the reference's own TTSOutput.save writes) is accepted as a speaker reference too
+    x = (np.random.RandomState(5).rand(4000).astype(np.float32) * 1.2 - 0.6)
+    ours.TTSOutput(array=x, sample_rate=22050).save(tmp_path / "f32.wav")
+    np.testing.assert_array_equal(load_audio(str(tmp_path / "f32.wav"), 22050), x)

@@ -58,7 +58,14 @@ def test_output_file_and_tensor_round_trip(tmp_path):
     f = tmp_path / "a.wav"
     o.save(f)
     back = TTSOutput.from_file(f)
-    assert back.sample_rate == 24000 and back.array.shape == x.shape and np.abs(back.array - x).max() < 1e-4      # int16 quantisation
+    assert back.sample_rate == 24000 and np.array_equal(back.array, x)           # bit_depth 32 (default) = IEEE-float WAV, lossless
+    assert f.read_bytes()[20:22] == b"\x03\x00"                                 # format tag 3, what torchaudio writes for the reference
+    o16 = TTSOutput(array=x, bit_depth=16)
+    o16.save(tmp_path / "c.wav")
+    back16 = TTSOutput.from_file(tmp_path / "c.wav")
+    assert np.abs(back16.array - x).max() < 1e-4                                  # int16 quantisation
+    (tmp_path / "d.wav").write_bytes(o.to_bytes("wav"))                           # to_bytes('wav') stays 16-bit PCM (output.py:141-150)
+    assert np.abs(TTSOutput.from_file(tmp_path / "d.wav").array - x).max() < 1e-4
     o.save(tmp_path / "b.wav", sample_rate=12000)
     assert TTSOutput.from_file(tmp_path / "b.wav").get_info()[:2] == (240, 12000)
     t = TTSOutput.from_tensor(torch.from_numpy(x)[None], 16000)
