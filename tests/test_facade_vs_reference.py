@@ -215,3 +215,40 @@ def test_load_audio_matches_the_reference_pipeline(tmp_path):
     x = (np.random.RandomState(5).rand(4000).astype(np.float32) * 1.2 - 0.6)
     ours.TTSOutput(array=x, sample_rate=22050).save(tmp_path / "f32.wav")
     np.testing.assert_array_equal(load_audio(str(tmp_path / "f32.wav"), 22050), x)
+
+
+def test_randomised_requests_same_results(ref):
+    """30 random (length, stream, failing chunk, scheduler concurrency) cases: both façades return the same audio in the same
+    pieces, or fail with the same error."""
+    import importlib
+    from auralis_b200.base import ConditioningConfig as OursCC
+    RefCC = importlib.import_module("auralis.models.base").ConditioningConfig
+    rng = np.random.RandomState(2024)
+    for case in range(30):
+        n_chars = int(rng.randint(1, 140))
+        stream = bool(rng.randint(2))
+        n_chunks = max(1, n_chars // 10)
+        fail_at = int(rng.randint(n_chunks)) if rng.rand() < 0.25 else None
+        conc = int(rng.choice([1, 2, 5, 16]))
+        results = []
+        for side in ("ref", "ours"):
+            if side == "ref":
+                tts = ref.TTS(scheduler_max_concurrency=conc); tts._ensure_event_loop()
+                tts.tts_engine = make_engine(ref.TTSOutput, RefCC(speaker_embeddings=True, gpt_like_decoder_conditioning=True), fail_at=fail_at)
+                Req = ref.TTSRequest
+            else:
+                tts = ours.TTS(scheduler_max_concurrency=conc).from_engine(make_engine(ours.TTSOutput, OursCC(True, True), fail_at=fail_at))
+                Req = ours.TTSRequest
+            try:
+                out = tts.generate_speech(Req(text="r" * n_chars, speaker_files=["s.wav"], language="en", stream=stream))
+                if stream:
+                    got = ("ok", [np.asarray(c.array).tolist() for c in out])
+                else:
+                    got = ("ok", np.asarray(out.array).tolist())
+            except Exception as e:      # noqa: BLE001
+                got = ("err", type(e).__name__, str(e))
+            results.append(got)
+        if results[0][0] == "err" and stream:
+            assert results[1][0] == "err" and results[1][1:] == results[0][1:], (case, results)
+        else:
+            assert results[0] == results[1], (case, n_chars, stream, fail_at, conc)
