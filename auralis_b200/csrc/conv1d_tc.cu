@@ -24,6 +24,7 @@
 
 namespace xtts {
 int g_conv_epi_groups = 2;        // engine option "conv_epi_groups" (1 or 2 epilogue warpgroups per CTA)
+int g_voc_sm_cap = 0;             // > 0: persistent conv grids use at most this many CTAs (SM partition while the GPT decodes)
 namespace {
 
 // warps [0, 4*EG) epilogue (EG warpgroups share a tile's accumulator chunks), warp 4*EG producer, warp 4*EG+1 MMA issuer
@@ -96,7 +97,8 @@ struct ConvTcParams {
     int CK;         // input channels per chunk (<= 64, multiple of 16)
     int rows;       // time rows staged per chunk = 128*NACC + (K-1)*dil
     int cbias_bs;   // elements between the speaker-bias vectors of consecutive batch items
-    int tiles_t, tiles_n, batch;   // persistent-CTA tile space
+    int tile_rows, tiles_n, batch; // persistent-CTA tile space: per item ceil(rows_i / tile_rows) x tiles_n tiles
+    int item_L[kVocMaxItems];      // ragged batch: input time steps of each item (<= L; buffers are strided by L)
 };
 
 template <int NACC, int EG>
@@ -107,6 +109,7 @@ conv1d_tc_kernel(const ConvTcParams P) {
     __shared__ __align__(8) uint64_t a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float sbias[2][256];     // per-tile bias + speaker bias (double buffered across tiles)
+    __shared__ int s_cum[kVocMaxItems + 1], s_len[kVocMaxItems];   // ragged batch: first tile / input length of every item
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int halo = P.center * P.dil;
@@ -123,10 +126,17 @@ conv1d_tc_kernel(const ConvTcParams P) {
     const int nbuf = (2 * acc_cols <= 512) ? 2 : 1;
     uint32_t tm_cols = 32;
     while (tm_cols < (uint32_t)(nbuf * acc_cols)) tm_cols <<= 1;
-    const int tiles_t = P.tiles_t, tiles_n = P.tiles_n;
-    const int total_tiles = tiles_t * tiles_n * P.batch;
+    const int tiles_n = P.tiles_n;
+    const int extra_rows = P.up ? 1 : 0;             // a transposed conv also consumes the zero row x[L]
 
     if (threadIdx.x == 0) {
+        int c = 0;
+        for (int i = 0; i < P.batch; ++i) {
+            const int Li = P.item_L[i];
+            s_cum[i] = c; s_len[i] = Li;
+            c += (Li > 0 ? ceil_div(Li + extra_rows, P.tile_rows) : 0) * tiles_n;
+        }
+        s_cum[P.batch] = c;
         for (int i = 0; i < SA; ++i) { bar_init(&a_full[i], 1); bar_init(&a_empty[i], 1); }
         for (int i = 0; i < SB; ++i) { bar_init(&b_full[i], 1); bar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { bar_init(&tmem_full[i], 1); bar_init(&tmem_empty[i], 128 * EG); }
@@ -140,6 +150,16 @@ conv1d_tc_kernel(const ConvTcParams P) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    const int total_tiles = s_cum[P.batch];
+    // tile -> (batch item, C_out tile, time tile); every role walks the same compact tile list
+    auto decode_tile = [&](int tile, int& zi, int& tx, int& ty, int& Li) {
+        zi = 0;
+        while (zi + 1 < P.batch && tile >= s_cum[zi + 1]) ++zi;
+        Li = s_len[zi];
+        const int tt = ceil_div(Li + extra_rows, P.tile_rows);
+        const int local = tile - s_cum[zi];
+        tx = local % tt; ty = local / tt;
+    };
 
     if (warp < 4 * EG) {
         // ------------------------------------------------ epilogue: warp q owns TMEM lanes [32q, 32q+32) = time rows;
@@ -147,15 +167,16 @@ conv1d_tc_kernel(const ConvTcParams P) {
         // is staged once in shared memory; the residual of the NEXT chunk is requested before the current chunk is
         // stored (and the first chunk's before the tile's MMAs have finished), so its latency is off the critical path.
         const int q = warp & 3, grp = warp >> 2, etid = warp * 32 + lane;
-        const int row_limit = P.up ? P.L + 1 : P.L;      // a transposed conv also consumes the zero row x[L]
         const int ncn = P.N / 32, nitems = NACC * ncn;
         const bool has_res = P.resid != nullptr, accum = (P.mode == CONV_ACCUM);
         const size_t Ls = (size_t)P.Lout;
         float rs[32];
         int lt = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-            const int tx = tile % tiles_t, ty = (tile / tiles_t) % tiles_n;
-            const size_t zo = (size_t)(tile / (tiles_t * tiles_n));
+            int zi, tx, ty, Li;
+            decode_tile(tile, zi, tx, ty, Li);
+            const size_t zo = (size_t)zi;
+            const int row_limit = Li + extra_rows, Lout_i = P.up ? Li * P.up : Li;
             const int T0 = tx * (128 * NACC), n0 = ty * P.N;
             float* out32 = P.out32 ? P.out32 + zo * P.Cr * P.Lout : nullptr;
             const float* resid = has_res ? P.resid + zo * P.Cr * P.Lout : nullptr;
@@ -174,7 +195,7 @@ conv1d_tc_kernel(const ConvTcParams P) {
                 const int phase = P.up ? cbg / P.Cr : 0;
                 cb = cbg - phase * P.Cr;
                 t = P.up ? srow * P.up + phase - P.up / 2 : srow;
-                valid = srow < row_limit && t >= 0 && t < P.Lout;
+                valid = srow < row_limit && t >= 0 && t < Lout_i;
             };
             int a, nc, cb, t; bool valid;
             geom(grp, a, nc, cb, t, valid);
@@ -260,8 +281,9 @@ conv1d_tc_kernel(const ConvTcParams P) {
         if (lane == 0) {
             int ita = 0, itb = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int tx = tile % tiles_t, ty = (tile / tiles_t) % tiles_n;
-                const size_t zo = (size_t)(tile / (tiles_t * tiles_n));
+                int zi, tx, ty, Li;
+                decode_tile(tile, zi, tx, ty, Li);
+                const size_t zo = (size_t)zi;
                 const int T0 = tx * (128 * NACC);
                 const __half* wsrc = P.wblob + (size_t)ty * nch * P.K * (b_stage / 2);
                 const __half* asrc = P.a16 + zo * (size_t)(P.Cin / 8) * P.lpad * 8;
@@ -326,13 +348,17 @@ conv1d_tc_kernel(const ConvTcParams P) {
     }
 }
 
-// zero the head pad and everything from row PADL+L on, for every plane of every batch item
-__global__ void atoms_zero_pads_kernel(uint4* __restrict__ buf, int planes_total, int lpad, int L) {
+// zero the head pad and the rows behind the signal, for every plane of every batch item.  Ragged batches: item i's signal
+// ends at its own L_i; the rows a valid output can reach behind it (halo <= kAtomPadL) plus one tile of slack are cleared,
+// rows further out are only ever read by output rows that are never stored.
+struct ZeroPadLens { int planes_per_item; int len[kVocMaxItems]; };
+__global__ void atoms_zero_pads_kernel(uint4* __restrict__ buf, int planes_total, int lpad, const ZeroPadLens Z) {
     const int pl = blockIdx.y;
     if (pl >= planes_total) return;
     uint4* p = buf + (size_t)pl * lpad;
+    const int L = Z.len[pl / Z.planes_per_item];
     const int tail0 = kAtomPadL + L;
-    const int n = kAtomPadL + (lpad - tail0);
+    const int n = kAtomPadL + min(lpad - tail0, 640);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int row = (i < kAtomPadL) ? i : tail0 + (i - kAtomPadL);
         p[row] = make_uint4(0u, 0u, 0u, 0u);
@@ -382,8 +408,8 @@ static void launch_inst(const ConvTcParams& P, dim3 grid, size_t smem, cudaStrea
     conv1d_tc_kernel<NACC, EG><<<grid, threads_tc(EG), smem, st>>>(P);
 }
 
-static void launch_tc_common(ConvTcParams& P, const ConvTcPlan& pl, int rows_to_cover, int batch, double flops, double bytes,
-                             cudaStream_t st) {
+static void launch_tc_common(ConvTcParams& P, const ConvTcPlan& pl, int rows_to_cover, int batch, const int* item_len,
+                             double flops, double bytes, cudaStream_t st) {
     const int tile = 128 * pl.nacc;
     P.N = pl.N; P.CK = pl.CK;
     P.rows = tile + (P.K - 1) * P.dil;
@@ -393,11 +419,21 @@ static void launch_tc_common(ConvTcParams& P, const ConvTcPlan& pl, int rows_to_
     const size_t smem = ((SA * a_stage + 127) & ~(size_t)127) + SB * b_stage + 128;
     constexpr int kMaxDyn = kMaxDynTc;
     if (smem > (size_t)kMaxDyn) throw CudaError("conv1d_tc: shared memory budget exceeded");
-    P.tiles_t = ceil_div(rows_to_cover, tile); P.tiles_n = pl.n_tiles; P.batch = batch;
-    const int total_tiles = P.tiles_t * P.tiles_n * batch;
+    if (batch > kVocMaxItems) throw CudaError("conv1d_tc: batch exceeds kVocMaxItems");
+    P.tile_rows = tile; P.tiles_n = pl.n_tiles; P.batch = batch;
+    const int extra = P.up ? 1 : 0;
+    int total_tiles = 0;
+    for (int i = 0; i < batch; ++i) {
+        const int Li = item_len ? item_len[i] : P.L;
+        if (Li < 0 || Li > P.L) throw CudaError("conv1d_tc: item length out of range");
+        P.item_L[i] = Li;
+        total_tiles += (Li > 0 ? ceil_div(Li + extra, tile) : 0) * P.tiles_n;
+    }
+    if (total_tiles == 0) return;
     static int n_sm = 0;
     if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
-    dim3 grid(std::min(total_tiles, n_sm));          // one persistent CTA per SM
+    const int cap = (g_voc_sm_cap > 0 && g_voc_sm_cap < n_sm) ? g_voc_sm_cap : n_sm;
+    dim3 grid(std::min(total_tiles, cap));           // one persistent CTA per SM (of the SMs this launch may take)
     ProfScope ps(KF_CONV1D_TC, st, flops, bytes);
     const int eg = g_conv_epi_groups >= 2 ? 2 : 1;
     if (pl.nacc == 2) { if (eg == 2) launch_inst<2, 2>(P, grid, smem, st); else launch_inst<2, 1>(P, grid, smem, st); }
@@ -407,34 +443,39 @@ static void launch_tc_common(ConvTcParams& P, const ConvTcPlan& pl, int rows_to_
 
 void launch_conv1d_tc(const __half* a16, const __half* wblob, const ConvTcPlan& pl, const float* bias, const float* cbias,
                       const float* resid, float* out32, __half* out16, int Cin, int Cout, int L, int lpad, int K, int dil,
-                      float slope_out, float scale16, int mode, int batch, int cbias_batch_stride, cudaStream_t st) {
+                      float slope_out, float scale16, int mode, int batch, int cbias_batch_stride, cudaStream_t st,
+                      const int* item_len) {
     if (L <= 0 || batch <= 0) return;
     if (!pl.ok || K % 2 != 1) throw CudaError("conv1d_tc: unsupported geometry");
+    double Lsum = 0;                                  // time steps actually computed (ragged batch: sum of the item lengths)
+    for (int i = 0; i < batch; ++i) Lsum += item_len ? item_len[i] : L;
     ConvTcParams P{};
     P.a16 = a16; P.wblob = wblob; P.bias = bias; P.cbias = cbias; P.resid = resid; P.out32 = out32; P.out16 = out16;
     P.Cin = Cin; P.Cout = Cout; P.L = L; P.lpad = lpad; P.K = K; P.dil = dil; P.mode = mode; P.slope_out = slope_out;
     P.scale16 = scale16; P.center = (K - 1) / 2; P.up = 0; P.Cr = Cout; P.Lout = L; P.lpad_out = lpad;
     P.cbias_bs = cbias_batch_stride;
     // algorithmic traffic: fp16 atoms in, fp32 residual in, fp32 and/or fp16 out, weights once
-    const double by = batch * (double)L * (2.0 * Cin + (resid ? 4.0 * Cout : 0) + (out32 ? (mode == CONV_ACCUM ? 8.0 : 4.0) * Cout : 0) +
-                                           (out16 ? 2.0 * Cout : 0)) + 2.0 * Cin * Cout * K;
-    launch_tc_common(P, pl, L, batch, 2.0 * Cin * Cout * K * (double)L * batch, by, st);
+    const double by = Lsum * (2.0 * Cin + (resid ? 4.0 * Cout : 0) + (out32 ? (mode == CONV_ACCUM ? 8.0 : 4.0) * Cout : 0) +
+                              (out16 ? 2.0 * Cout : 0)) + 2.0 * Cin * Cout * K;
+    launch_tc_common(P, pl, L, batch, item_len, 2.0 * Cin * Cout * K * Lsum, by, st);
 }
 
 // ConvTranspose1d(Cin -> Cr, kernel 2u, stride u, padding u/2) on the same kernel: u phases x 2 taps.
 // `pl`/`wblob` come from conv1d_tc_plan(Cin, u*Cr, 2) / convT_tc_pack.
 void launch_convT_tc(const __half* a16, const __half* wblob, const ConvTcPlan& pl, const float* bias, const float* cbias,
                      float* out32, __half* out16, int Cin, int Cr, int Lin, int lpad_in, int lpad_out, int u, float slope_out,
-                     int batch, int cbias_batch_stride, cudaStream_t st) {
+                     int batch, int cbias_batch_stride, cudaStream_t st, const int* item_len) {
     if (Lin <= 0 || batch <= 0) return;
+    double Lsum = 0;
+    for (int i = 0; i < batch; ++i) Lsum += item_len ? item_len[i] : Lin;
     if (!pl.ok || (u & 1) || Cr % 32 != 0) throw CudaError("convT_tc: unsupported geometry");
     ConvTcParams P{};
     P.a16 = a16; P.wblob = wblob; P.bias = bias; P.cbias = cbias; P.resid = nullptr; P.out32 = out32; P.out16 = out16;
     P.Cin = Cin; P.Cout = u * Cr; P.L = Lin; P.lpad = lpad_in; P.K = 2; P.dil = 1; P.mode = CONV_STORE; P.slope_out = slope_out;
     P.scale16 = 1.0f; P.center = 1; P.up = u; P.Cr = Cr; P.Lout = Lin * u; P.lpad_out = lpad_out;
     P.cbias_bs = cbias_batch_stride;
-    const double by = batch * ((double)Lin * 2.0 * Cin + (double)Lin * u * Cr * ((out32 ? 4.0 : 0) + (out16 ? 2.0 : 0))) + 4.0 * Cin * Cr * u;
-    launch_tc_common(P, pl, Lin + 1, batch, 4.0 * Cin * Cr * (double)Lin * u * batch, by, st);
+    const double by = Lsum * 2.0 * Cin + Lsum * u * Cr * ((out32 ? 4.0 : 0) + (out16 ? 2.0 : 0)) + 4.0 * Cin * Cr * u;
+    launch_tc_common(P, pl, Lin + 1, batch, item_len, 4.0 * Cin * Cr * Lsum * u, by, st);
 }
 
 // ConvTranspose1d weight [Cin][Cr][2u] fp32 -> two-tap phase blob: W'[p*Cr+co][ci][0] = w[ci][co][p+u] (x[s-1]),
@@ -451,10 +492,14 @@ void convT_tc_pack(const float* w, int Cin, int Cr, int u, const ConvTcPlan& pl,
     conv1d_tc_pack(tmp.data(), Cin, u * Cr, 2, pl, blob);
 }
 
-void launch_atoms_zero_pads(__half* buf, int planes_total, int lpad, int L, cudaStream_t st) {
+void launch_atoms_zero_pads(__half* buf, int planes_total, int lpad, int L, cudaStream_t st, int batch, const int* item_len) {
     if (planes_total <= 0) return;
+    if (batch < 1 || batch > kVocMaxItems || planes_total % batch != 0) throw CudaError("atoms_zero_pads: bad batch");
+    ZeroPadLens Z{};
+    Z.planes_per_item = planes_total / batch;
+    for (int i = 0; i < batch; ++i) Z.len[i] = item_len ? item_len[i] : L;
     ProfScope ps(KF_MISC, st, 0, 16.0 * planes_total * (lpad - L));
-    atoms_zero_pads_kernel<<<dim3(2, planes_total), 256, 0, st>>>(reinterpret_cast<uint4*>(buf), planes_total, lpad, L);
+    atoms_zero_pads_kernel<<<dim3(2, planes_total), 256, 0, st>>>(reinterpret_cast<uint4*>(buf), planes_total, lpad, Z);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 

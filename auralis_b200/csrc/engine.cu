@@ -90,30 +90,53 @@ struct Sequence {
     xtts_sampling sp{};
     int slot = -1;
     int n_prompt = 0;
+    int max_tok = 0;              // min(sp.max_tokens, max_audio_tokens)
     int steps = 0;                // decode steps issued so far (host-side mirror of n_gen - 1)
     std::vector<int> pages;
     double t_submit = 0, t_first = 0, t_done = 0;
-    // results
-    int status = 0;
-    std::vector<int32_t> tokens;
-    int n_samples = 0;
-    float* wav_host = nullptr;    // pinned
+    bool cancelled = false;
+    // results: written on the vocoder stream, valid once the job that wrote them has completed
+    int n_tokens = 0;             // final token count (0 while decoding)
+    int32_t* tok_host = nullptr;  // pinned [max_tok]
+    size_t tok_cap = 0;
+    float* wav_host = nullptr;    // pinned, the whole chunk's samples (option d2h_wav = 1)
     size_t wav_cap = 0;
-    float* wav_dev = nullptr;     // kept when d2h_wav == 0 (pooled device buffer)
+    float* wav_dev = nullptr;     // pooled device buffer instead (d2h_wav = 0)
     size_t wav_dev_cap = 0;
-    float* lat_dev = nullptr;     // [n_tokens, H] copy so the slot can be reused (pooled device buffer)
+    float* lat_dev = nullptr;     // [n_tokens, H] snapshot of the latent ring (pooled device buffer)
     size_t lat_dev_cap = 0;
-    // first-audio early emit (xtts_sampling.early_tokens; 0 = off)
-    int early_tokens = 0;         // audio of this many leading tokens goes out as a partial result
-    bool early_done = false;
-    int early_samples = 0;        // samples already delivered by the partial result
+    // vocoder progress: the chunk's audio is produced window by window while it is still decoding
+    int next_boundary = 0;        // tokens: the next window is cut here (0 = no further cut, the rest goes out at the end)
+    int seg_next = 0;             // distance of the cuts after the first (0 = none)
+    bool stream_pieces = false;   // windows are handed to the completion queue as partial results (sp.early_tokens > 0)
+    int voc_z_done = 0;           // z-frames whose samples are produced or in flight
+    int tok_delivered = 0, samp_delivered = 0;   // covered by partial results already queued
 };
 
-// a partial (first-audio) piece lives in done_map under its sequence id with this bit set; user ids must not use it
-static constexpr uint64_t kPartialBit = 1ull << 63;
-// latent frames decoded beyond `early_tokens` before the prefix is vocoded: the vocoder's receptive field reaches
-// ~3 latent frames ahead (conv_pre + the k = 11, d = 5 resblock of the first stage; measured with the oracle), 6 leaves margin
-static constexpr int kEarlyLookahead = 6;
+// one entry of the completion queue: a partial piece of a chunk (status 1) or its final result (status <= 0)
+struct Piece {
+    std::shared_ptr<Sequence> s;
+    int status = 0;
+    int tok0 = 0, tok1 = 0;       // tokens [tok0, tok1) of s->tok_host
+    int samp0 = 0, nsamp = 0;     // samples [samp0, samp0 + nsamp) of the chunk's waveform buffer
+    double t_done = 0;
+    bool final = false;
+};
+
+// one window of one chunk on its way through the vocoder: z-frames [zw0, zw1) are computed, the samples of [zk0, zk1) kept
+// (the margins are the vocoder's receptive field, so kept samples equal those of the unsplit chunk)
+struct VocJob {
+    std::shared_ptr<Sequence> s;
+    int T_clamp = 0;              // latent frames the interpolation may touch
+    int zw0 = 0, zw1 = 0, zk0 = 0, zk1 = 0;
+    int tok_upto = 0;             // tokens [0, tok_upto) are final and copied out with this job
+    bool final = false;
+    int fail_status = 0;          // final job of a cancelled / failed chunk: no vocoder work, this status is delivered
+};
+struct VocBatch {
+    std::vector<VocJob> jobs;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
 
 class Engine {
 public:
@@ -126,6 +149,7 @@ public:
     void get_speaker(int slot, float* cond, float* g);
     void condition(int slot, const float* w22, int64_t n22, const float* w16, int64_t n16, int cond_len, int chunk_len);
     void submit(uint64_t id, const int32_t* text, int n_text, int speaker, const xtts_sampling& sp);
+    void cancel(uint64_t id);
     int poll(xtts_result* out, int timeout_ms);
     void fetch(uint64_t id, int32_t* tokens, float* wav, float* latents);
     void set_option(const std::string& k, int64_t v);
@@ -136,6 +160,7 @@ public:
 
     void vocode_sync(const float* latents, int T, int speaker, float* wav, int* n_out, const char* stage,
                      float* stage_out, int64_t stage_cap);
+    void vocode_window_sync(const float* latents, int T, int speaker, int z0, int nz, float* wav);
     void gpt_prefill_sync(const int32_t* text, int n_text, int speaker, const int32_t* audio, int n_audio,
                           float* hidden_out, float* logits_out, float* latents_out);
     void gpt_teacher_forced_sync(const int32_t* text, int n_text, int speaker, const int32_t* forced, int n,
@@ -152,11 +177,13 @@ private:
     int prefill_rows_cap;
     bool bf16;
     cudaStream_t st = nullptr;
+    cudaStream_t st_voc = nullptr;                       // the vocoder's own (low-priority) stream: runs beside the decode step
     static constexpr int kMaxMicro = 4;
     cudaStream_t st_mb[kMaxMicro] = {nullptr, nullptr, nullptr, nullptr};   // [0] == st; decode micro-batch branches
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;       // xtts_device_timer
     bool timer_armed = false;
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxMicro] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_vjoin = nullptr;
 
     // ---- weights
     std::map<std::string, HostTensor> raw;
@@ -203,12 +230,20 @@ private:
     DBuf<float> wXn32, wATT32, wFF32, wY32;
     DBuf<__nv_bfloat16> wXn16, wATT16, wFF16, wY16;
     // pinned staging
-    int* h_finished = nullptr;
-    // vocoder workspace
-    DBuf<float> vz, vpre, vb[5], vwav, vlat, vcb;
+    int* h_finished = nullptr;       // [2][NSLOT]: finished flags, then n_gen, read back after every step
+    SlotInit* h_slot_init = nullptr; // [B + 1] admission wave
+    int* h_slot_pages = nullptr;     // [B + 1][max_pages]
+    DBuf<SlotInit> d_slot_init;
+    DBuf<int> d_slot_pages;
+    // vocoder workspace (used on st_voc only)
+    DBuf<float> vz, vpre, vb[5], vwav, vcb;
     DBuf<__half> vz16, va16[5];   // fp16 operand atoms of the tensor-core vocoder path
     bool tc_vocoder_ready = false;
-    int voc_max_T = 0, VB = 1;
+    int voc_max_T = 0, voc_max_Tz = 0;
+    size_t voc_cap_z = 0;         // z-frames a batch may hold: items x longest window
+    size_t vz16_halves = 0, va16_halves = 0;
+    int voc_hz = 16;              // receptive field of the vocoder in z-frames (window margin), from the geometry
+    int voc_hop = 1;              // samples per z-frame
     std::vector<int> stage_ch;
 
     // ---- scheduler
@@ -222,8 +257,14 @@ private:
     std::deque<std::shared_ptr<Sequence>> waiting;      // scheduler thread only: accepted, not yet admitted
     std::vector<std::shared_ptr<Sequence>> running;     // index = position in active list
     std::vector<int> free_slots;
-    std::deque<std::shared_ptr<Sequence>> done_q;
-    std::unordered_map<uint64_t, std::shared_ptr<Sequence>> done_map;
+    std::deque<std::shared_ptr<Piece>> done_q;                                  // q_mu
+    std::unordered_map<uint64_t, std::deque<std::shared_ptr<Piece>>> done_map;  // q_mu: unfetched pieces per id, oldest first
+    std::vector<uint64_t> cancel_req;                                           // q_mu
+    std::deque<VocJob> voc_pending;          // scheduler thread only
+    std::deque<VocBatch> voc_inflight;       // scheduler thread only (stream order = queue order)
+    int voc_segment = 0;          // option "voc_segment": tokens per vocoder window while a chunk decodes (0 = whole chunks at the end)
+    int voc_sms = 0;              // option "voc_sms": SMs the conv kernels may take while a decode step is in flight (0 = all)
+    int voc_max_items = kVocMaxItems;   // option "voc_batch": windows per vocoder launch
     std::thread worker;
     std::atomic<bool> stop{false};
     int inflight = 0;
@@ -255,12 +296,15 @@ private:
     void up(DBuf<float>& d, const std::vector<float>& h) { d.alloc(h.size()); d.upload(h.data(), h.size(), st); weight_bytes += h.size() * 4; }
     void make_linear(Linear& lin, const std::string& wname, const std::string& bname, bool conv1d_layout, int pad_n = 0);
     void make_conv(ConvW& c, const std::string& prefix, bool transposed, bool has_bias);
-    void conv1d(const ConvW& c, const float* x, const float* cbias, const float* resid, float* out, int L, int dil,
-                float in_scale, float slope, int mode, int nb);
-    void conv1d_tc(const ConvW& c, const __half* a16, const float* cbias, const float* resid, float* out32, __half* out16,
-                   int L, int lpad, int dil, int mode, int nb, float scale16 = 1.0f);
-    void run_vocoder_tc(const float* lat_dev, int T, int nb, float* wav_dev_out, int* n_out, const char* stage,
-                        float* stage_out, int64_t stage_cap);
+    struct VocItem { const float* lat; int T; int z0, nz; int speaker; };
+    void run_vocoder_tc(const VocItem* it, int nb, int Lz, float* wav_dev_out, const char* stage, float* stage_out,
+                        int64_t stage_cap);
+    void run_vocoder_f32(const VocItem* it, int nb, int Lz, float* wav_dev_out, const char* stage, float* stage_out,
+                         int64_t stage_cap);
+    bool voc_fits(int nb, int Lz) const;
+    void compute_voc_margin(int pre_k);
+    int z_frames(int T) const;
+    int z_avail(int n) const;
     std::vector<float> folded(const std::string& prefix) const;
     GptTables tables() const {
         GptTables t; t.text_emb = text_emb.p; t.text_pos = text_pos.p; t.wte = wte.p; t.wpe = wpe.p;
@@ -274,19 +318,26 @@ private:
                          bool pdl_first = true);
     void decode_layers_rows(int r0, int Mi, cudaStream_t s, bool pdl_first, double ctx_sum);
     void decode_layers_chain(int M);
-    void init_slot(Sequence& s, const int32_t* forced, int n_forced);
+    void init_slots(const std::vector<Sequence*>& seqs, const int32_t* forced, int n_forced);
+    void release_pages(Sequence& s);
     void release_slot(Sequence& s);
+    void free_seq_buffers(Sequence& s);
+    void recycle_seq_buffers(Sequence& s);
     int build_prefill(const std::vector<Sequence*>& seqs, const std::vector<std::vector<int32_t>>& audio,
                       std::vector<int>& last_rows, int& max_nq);
     void prefill(const std::vector<Sequence*>& seqs);
     void decode_step(const std::vector<int>& active);
-    void run_vocoder(const float* lat_dev, int T, const int* speakers, int nb, float* wav_dev_out, int* n_out,
-                     const char* stage, float* stage_out, int64_t stage_cap);
-    void finish_group(std::vector<std::shared_ptr<Sequence>>& grp);
-    void emit_early(std::vector<std::shared_ptr<Sequence>>& grp);
+    void run_vocoder(const VocItem* it, int nb, float* wav_dev_out, const char* stage, float* stage_out, int64_t stage_cap);
     int samples_for(int T) const;
-    void finish_sequence(std::shared_ptr<Sequence> s);
-    void retire(std::shared_ptr<Sequence> s);
+    void on_finished(std::shared_ptr<Sequence> s, int n_tokens, int fail_status);
+    void maybe_cut_window(std::shared_ptr<Sequence>& s);
+    void dispatch_ready(bool decode_active);
+    void dispatch_batch(std::vector<VocJob>& jobs, bool decode_active);
+    void reap(bool block);
+    void complete_batch(VocBatch& b);
+    void deliver(std::shared_ptr<Piece> p, bool ends_sequence);
+    void fail_unadmitted(std::shared_ptr<Sequence> s, int code, const char* what);
+    void process_cancels(const std::vector<uint64_t>& ids);
     float* pinned_get(size_t n, size_t* cap);
     void pinned_put(float* p, size_t cap);
     float* dev_get(size_t n, size_t* cap);           // device buffer pool (no cudaMalloc/cudaFree per chunk)
@@ -327,9 +378,16 @@ Engine::Engine(const xtts_config& c) : cfg(c) {
     S = std::max(1, c.max_speakers);
     bf16 = c.precision == XTTS_PRECISION_BF16;
     if (bf16) { std::string err; if (!gemm_tc_init(&err)) throw std::runtime_error(err); }
-    CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    // the decode step is a chain of short dependent kernels: its streams get the highest priority, the vocoder (long
+    // throughput kernels on its own stream) the lowest, so a decode kernel never queues behind vocoder CTAs that have
+    // not started yet
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi));
     st_mb[0] = st;
-    for (int i = 1; i < kMaxMicro; ++i) CUDA_CHECK(cudaStreamCreateWithFlags(&st_mb[i], cudaStreamNonBlocking));
+    for (int i = 1; i < kMaxMicro; ++i) CUDA_CHECK(cudaStreamCreateWithPriority(&st_mb[i], cudaStreamNonBlocking, prio_hi));
+    CUDA_CHECK(cudaStreamCreateWithPriority(&st_voc, cudaStreamNonBlocking, prio_lo));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_vjoin, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     for (int i = 1; i < kMaxMicro; ++i) CUDA_CHECK(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
 
@@ -359,7 +417,11 @@ Engine::Engine(const xtts_config& c) : cfg(c) {
     d_active.alloc(NSLOT);
     d_latents.alloc((size_t)NSLOT * CAP * H);
     d_finished.zero(st); d_n_gen.zero(st); d_ctx_len.zero(st); d_last_tok.zero(st);
-    CUDA_CHECK(cudaMallocHost(&h_finished, NSLOT * sizeof(int)));
+    CUDA_CHECK(cudaMallocHost(&h_finished, 2 * NSLOT * sizeof(int)));
+    std::memset(h_finished, 0, 2 * NSLOT * sizeof(int));
+    CUDA_CHECK(cudaMallocHost(&h_slot_init, NSLOT * sizeof(SlotInit)));
+    CUDA_CHECK(cudaMallocHost(&h_slot_pages, (size_t)NSLOT * max_pages * sizeof(int)));
+    d_slot_init.alloc(NSLOT); d_slot_pages.alloc((size_t)NSLOT * max_pages);
 
     // prefill row budget: whole prompts of up to 8 sequences at the maximum prompt length, >= one debug pass
     prefill_rows_cap = std::max(8 * MAXP, MAXP + CAP);
@@ -388,24 +450,48 @@ Engine::Engine(const xtts_config& c) : cfg(c) {
     for (int p = total_pages - 1; p >= 0; --p) free_pages.push_back(p);
     for (int s = B - 1; s >= 0; --s) free_slots.push_back(s);
 
-    // vocoder workspace for the longest chunk
+    // vocoder workspace: a batch is up to kVocMaxItems windows, nb x (longest window) <= voc_cap_z z-frames
+    // (8 whole chunks of the maximum length, or more, shorter windows)
     voc_max_T = CAP;
     {
-        const int T1 = (int)std::floor((double)voc_max_T * ((double)c.code_stride / (double)c.output_hop_length));
-        const int Tz = (int)std::floor((double)T1 * ((double)c.output_sample_rate / (double)c.input_sample_rate));
-        VB = std::max(1, std::min(8, B));       // chunks vocoded per launch (fills the SMs at the short early stages)
-        vz.alloc((size_t)VB * c.voc_in_dim * Tz);
-        vpre.alloc((size_t)VB * c.voc_init_ch * Tz);
-        size_t mx = 0; int len = Tz;
-        for (int i = 0; i < c.voc_n_up; ++i) { len *= c.voc_up_rates[i]; mx = std::max(mx, (size_t)stage_ch[i] * len); }
-        for (auto& b : vb) b.alloc((size_t)VB * mx);
-        vwav.alloc((size_t)VB * len);
-        vlat.alloc((size_t)VB * voc_max_T * c.voc_in_dim);
-        vcb.alloc((size_t)VB * cbias_stride);
+        voc_hop = 1;
+        for (int i = 0; i < c.voc_n_up; ++i) voc_hop *= c.voc_up_rates[i];
+        voc_max_Tz = z_frames(voc_max_T);
+        const int nfull = std::max(1, std::min(8, B));
+        voc_cap_z = (size_t)nfull * voc_max_Tz;
+        vz.alloc(voc_cap_z * c.voc_in_dim);
+        vpre.alloc(voc_cap_z * c.voc_init_ch);
+        size_t mx = 0; size_t rate = 1;
+        for (int i = 0; i < c.voc_n_up; ++i) { rate *= c.voc_up_rates[i]; mx = std::max(mx, (size_t)stage_ch[i] * rate); }
+        for (auto& b : vb) b.alloc(voc_cap_z * mx);
+        vwav.alloc(voc_cap_z * voc_hop);
+        vcb.alloc((size_t)kVocMaxItems * cbias_stride);
+        compute_voc_margin(7);
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
     launch_base = g_launch_count;
     worker = std::thread([this] { this->loop(); });
+}
+
+// receptive field of the generator in z-frames: conv_pre, per stage the transposed conv (1.5 input frames) and the widest
+// resblock chain (sum over its dilations of the two convs' half-widths), conv_post (k = 7); + 2 frames of margin
+void Engine::compute_voc_margin(int pre_k) {
+    const auto& c = cfg;
+    double rf = (pre_k - 1) / 2, rt = 1.0;
+    for (int i = 0; i < c.voc_n_up; ++i) {
+        rf += 1.5 / rt;
+        rt *= c.voc_up_rates[i];
+        double widest = 0;
+        for (int j = 0; j < c.voc_n_rb; ++j) {
+            const int hk = (c.voc_rb_kernels[j] - 1) / 2;
+            double w = 0;
+            for (int t = 0; t < 3; ++t) w += hk * c.voc_rb_dilations[t] + hk;
+            widest = std::max(widest, w);
+        }
+        rf += widest / rt;
+    }
+    rf += 3.0 / rt;
+    voc_hz = (int)std::ceil(rf) + 2;
 }
 
 Engine::~Engine() {
@@ -417,19 +503,28 @@ Engine::~Engine() {
     if (worker.joinable()) worker.join();
     cudaSetDevice(cfg.device);
     cudaStreamSynchronize(st);
+    if (st_voc) cudaStreamSynchronize(st_voc);
     drop_graphs();
+    // buffers of every chunk still in the pipeline or never fetched
+    for (auto& s : running) free_seq_buffers(*s);
+    for (auto& j : voc_pending) free_seq_buffers(*j.s);
+    for (auto& b : voc_inflight) {
+        for (auto& j : b.jobs) free_seq_buffers(*j.s);
+        if (b.ev0) cudaEventDestroy(b.ev0);
+        if (b.ev1) cudaEventDestroy(b.ev1);
+    }
+    for (auto& kv : done_map) for (auto& pc : kv.second) if (pc->s) free_seq_buffers(*pc->s);
     for (auto& pr : pinned_pool) cudaFreeHost(pr.first);
     for (auto& pr : dev_pool) cudaFree(pr.first);
-    for (auto& kv : done_map) {                     // finished chunks nobody fetched
-        if (kv.second->wav_host) cudaFreeHost(kv.second->wav_host);
-        if (kv.second->wav_dev) cudaFree(kv.second->wav_dev);
-        if (kv.second->lat_dev) cudaFree(kv.second->lat_dev);
-    }
     if (h_finished) cudaFreeHost(h_finished);
+    if (h_slot_init) cudaFreeHost(h_slot_init);
+    if (h_slot_pages) cudaFreeHost(h_slot_pages);
     for (int i = 1; i < kMaxMicro; ++i) { if (st_mb[i]) cudaStreamDestroy(st_mb[i]); if (ev_join[i]) cudaEventDestroy(ev_join[i]); }
     if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_vjoin) cudaEventDestroy(ev_vjoin);
     if (ev_t0) cudaEventDestroy(ev_t0);
     if (ev_t1) cudaEventDestroy(ev_t1);
+    if (st_voc) cudaStreamDestroy(st_voc);
     if (st) cudaStreamDestroy(st);
 }
 
@@ -548,18 +643,6 @@ void Engine::make_conv(ConvW& c, const std::string& prefix, bool transposed, boo
     }
 }
 
-// Conv1d through whichever path the weights were prepared for
-void Engine::conv1d(const ConvW& c, const float* x, const float* cbias, const float* resid, float* out, int L, int dil,
-                    float in_scale, float slope, int mode, int nb) {
-    launch_conv1d(x, c.wt.p, c.b.p, cbias, resid, out, c.Cin, c.Cout, L, c.K, dil, in_scale, slope, mode, nb, cbias_stride, st);
-}
-
-void Engine::conv1d_tc(const ConvW& c, const __half* a16, const float* cbias, const float* resid, float* out32, __half* out16,
-                       int L, int lpad, int dil, int mode, int nb, float scale16) {
-    launch_conv1d_tc(a16, c.blob.p, c.plan, c.b.p, cbias, resid, out32, out16, c.Cin, c.Cout, L, lpad, c.K, dil, 0.1f, scale16,
-                     mode, nb, cbias_stride, st);
-}
-
 void Engine::finalize_weights() {
     std::lock_guard<std::mutex> lk(mu);
     if (finalized) return;
@@ -628,15 +711,23 @@ void Engine::finalize_weights() {
         for (auto& rb : rbs) for (int t = 0; t < 3; ++t) all_tc = all_tc && rb->c1[t]->tc && rb->c2[t]->tc;
         for (int ch : stage_ch) all_tc = all_tc && (ch % 16 == 0);
         if (all_tc) {
-            const int T1 = (int)std::floor((double)voc_max_T * ((double)c.code_stride / (double)c.output_hop_length));
-            const int Tz = (int)std::floor((double)T1 * ((double)c.output_sample_rate / (double)c.input_sample_rate));
-            vz16.alloc((size_t)VB * c.voc_in_dim * atoms_lpad(Tz));
-            size_t mx = (size_t)c.voc_init_ch * atoms_lpad(Tz); int len = Tz;
-            for (int i = 0; i < c.voc_n_up; ++i) { len *= c.voc_up_rates[i]; mx = std::max(mx, (size_t)stage_ch[i] * atoms_lpad(len)); }
-            for (auto& b : va16) b.alloc((size_t)VB * mx);
+            // atoms carry up to 640 pad rows per plane, which weighs more the shorter the windows: size the buffers for the
+            // three batch shapes the scheduler forms most (n whole chunks, 2n half-length, 4n quarter-length windows)
+            const int nfull = (int)(voc_cap_z / voc_max_Tz);
+            vz16_halves = va16_halves = 0;
+            for (int f = 1; f <= 4; f *= 2) {
+                const int nb = std::min(nfull * f, kVocMaxItems), Lz = ceil_div(voc_max_Tz, f);
+                vz16_halves = std::max(vz16_halves, (size_t)nb * c.voc_in_dim * atoms_lpad(Lz));
+                size_t mx = (size_t)c.voc_init_ch * atoms_lpad(Lz); int len = Lz;
+                for (int i = 0; i < c.voc_n_up; ++i) { len *= c.voc_up_rates[i]; mx = std::max(mx, (size_t)stage_ch[i] * atoms_lpad(len)); }
+                va16_halves = std::max(va16_halves, (size_t)nb * mx);
+            }
+            vz16.alloc(vz16_halves);
+            for (auto& b : va16) b.alloc(va16_halves);
             tc_vocoder_ready = true;
         }
     }
+    compute_voc_margin(conv_pre.K);
     CUDA_CHECK(cudaStreamSynchronize(st));
     // ---- speaker conditioning stack (optional in a checkpoint: without it only xtts_set_speaker works)
     if (raw.count("conditioning_encoder.init.weight") && raw.count("hifigan_decoder.speaker_encoder.conv1.weight")) {
@@ -785,40 +876,50 @@ void Engine::head_and_sample(int M, const int* row_index, const int* slots_dev, 
     if (do_sample) launch_sample(wLOG.p, Vpad, slots_dev, M, V, sample_state(), advance_ctx, st, pdl);
 }
 
-void Engine::init_slot(Sequence& s, const int32_t* forced, int n_forced) {
-    const int slot = s.slot;
-    const int n_text = (int)s.text_ids.size();
-    s.n_prompt = cfg.n_cond_latents + n_text + 1;
-    const int max_tok = std::min<int>(s.sp.max_tokens > 0 ? s.sp.max_tokens : CAP, CAP);
-    const int need_pages = ceil_div(s.n_prompt + max_tok, kPageTokens);
-    if ((int)free_pages.size() < need_pages) throw std::runtime_error("out of KV pages");
+// Slot state of an admission wave: KV pages are taken here, everything the device needs goes up in one staged copy and
+// one kernel (launch_init_slots).  `forced` (debug entry points, one sequence): teacher-forced token ids.
+void Engine::init_slots(const std::vector<Sequence*>& seqs, const int32_t* forced, int n_forced) {
+    const int n = (int)seqs.size();
+    if (n == 0) return;
+    if (n > NSLOT) throw std::runtime_error("init_slots: wave larger than the slot count");
+    for (int i = 0; i < n; ++i) {
+        Sequence& s = *seqs[i];
+        s.n_prompt = cfg.n_cond_latents + (int)s.text_ids.size() + 1;
+        s.max_tok = std::min<int>(s.sp.max_tokens > 0 ? s.sp.max_tokens : CAP, CAP);
+        const int need_pages = ceil_div(s.n_prompt + s.max_tok, kPageTokens);
+        if ((int)free_pages.size() < need_pages) throw std::runtime_error("out of KV pages");
+        s.pages.clear();
+        int* pg = h_slot_pages + (size_t)i * max_pages;
+        for (int k = 0; k < need_pages; ++k) { pg[k] = free_pages.back(); free_pages.pop_back(); s.pages.push_back(pg[k]); }
+        SlotInit& d = h_slot_init[i];
+        d.slot = s.slot; d.ctx_len = s.n_prompt; d.top_k = s.sp.top_k; d.max_tokens = s.max_tok; d.stop_token = s.sp.stop_token;
+        d.seq_seed = s.sp.seq_seed; d.start_token = cfg.start_audio_token; d.n_pages = need_pages;
+        d.temperature = s.sp.temperature; d.top_p = s.sp.top_p; d.penalty = s.sp.repetition_penalty; d.seed = s.sp.seed;
+    }
+    d_slot_init.upload(h_slot_init, n, st);
+    d_slot_pages.upload(h_slot_pages, (size_t)n * max_pages, st);
+    SlotArrays a{};
+    a.last_tok = d_last_tok.p; a.n_gen = d_n_gen.p; a.ctx_len = d_ctx_len.p; a.finished = d_finished.p; a.seen = d_seen.p;
+    a.temperature = d_temp.p; a.top_p = d_top_p.p; a.top_k = d_top_k.p; a.penalty = d_pen.p; a.max_tokens = d_max_tokens.p;
+    a.stop_token = d_stop.p; a.seed = d_seed.p; a.seq_seed = d_seq_seed.p; a.block_tables = d_block_tables.p;
+    a.seen_words = SEENW; a.max_pages = max_pages;
+    launch_init_slots(d_slot_init.p, d_slot_pages.p, n, a, st);
+    if (forced) {
+        std::vector<int> f(CAP, -1);
+        for (int i = 0; i < std::min(n_forced, CAP); ++i) f[i] = forced[i];
+        d_forced.upload(f.data(), CAP, st, (size_t)seqs[0]->slot * CAP);
+        CUDA_CHECK(cudaStreamSynchronize(st));     // `f` goes out of scope
+    }
+    // (the pinned staging is reused by the next wave: prefill() synchronizes the stream before the scheduler gets there)
+}
+
+void Engine::release_pages(Sequence& s) {
+    for (int p : s.pages) free_pages.push_back(p);
     s.pages.clear();
-    std::vector<int> bt(max_pages, 0);
-    for (int i = 0; i < need_pages; ++i) { bt[i] = free_pages.back(); free_pages.pop_back(); s.pages.push_back(bt[i]); }
-    d_block_tables.upload(bt.data(), max_pages, st, (size_t)slot * max_pages);
-    const int zero = 0, ctx = s.n_prompt;
-    d_n_gen.upload(&zero, 1, st, slot); d_finished.upload(&zero, 1, st, slot); d_ctx_len.upload(&ctx, 1, st, slot);
-    d_last_tok.upload(&cfg.start_audio_token, 1, st, slot);
-    const int tk = s.sp.top_k, stopt = s.sp.stop_token, ss = s.sp.seq_seed;
-    const float T = s.sp.temperature, tp = s.sp.top_p, pen = s.sp.repetition_penalty;
-    const unsigned long long seed = s.sp.seed;
-    d_top_k.upload(&tk, 1, st, slot); d_max_tokens.upload(&max_tok, 1, st, slot); d_stop.upload(&stopt, 1, st, slot);
-    d_seq_seed.upload(&ss, 1, st, slot); d_temp.upload(&T, 1, st, slot); d_top_p.upload(&tp, 1, st, slot);
-    d_pen.upload(&pen, 1, st, slot); d_seed.upload(&seed, 1, st, slot);
-    // penalty set seed: prompt ids are [1]*(32+Lt)+[start]  (vllm_mm_gpt.py:325, App. B.7)
-    std::vector<unsigned> seen(SEENW, 0u);
-    seen[1 >> 5] |= 1u << 1;
-    seen[cfg.start_audio_token >> 5] |= 1u << (cfg.start_audio_token & 31);
-    d_seen.upload(seen.data(), SEENW, st, (size_t)slot * SEENW);
-    std::vector<int> f(CAP, -1);
-    if (forced) for (int i = 0; i < std::min(n_forced, CAP); ++i) f[i] = forced[i];
-    d_forced.upload(f.data(), CAP, st, (size_t)slot * CAP);
-    CUDA_CHECK(cudaStreamSynchronize(st));     // host staging vectors go out of scope
 }
 
 void Engine::release_slot(Sequence& s) {
-    for (int p : s.pages) free_pages.push_back(p);
-    s.pages.clear();
+    release_pages(s);
     if (s.slot >= 0 && s.slot < B) free_slots.push_back(s.slot);
     s.slot = -1;
 }
@@ -1023,101 +1124,173 @@ void Engine::decode_step(const std::vector<int>& active) {
 // ================================================================================================
 // vocoder driver  (HifiDecoder.forward, hifigan_decoder.py:776-802 + HifiganGenerator.forward :228-260)
 // ================================================================================================
-// `nb` equal-length chunks at once: latents [nb][T][in_dim] (contiguous, device) -> wav_dev_out [nb][n_samples]
-void Engine::run_vocoder(const float* lat_dev, int T, const int* speakers, int nb, float* wav_dev_out, int* n_out,
-                         const char* stage, float* stage_out, int64_t stage_cap) {
-    const auto& c = cfg;
-    if (T <= 0 || T > voc_max_T) throw std::runtime_error("vocoder: latent count out of range");
-    if (nb < 1 || nb > VB) throw std::runtime_error("vocoder: batch out of range");
-    for (int i = 0; i < nb; ++i) {
-        const int sp = speakers[i];
-        if (sp < 0 || sp >= S || !spk_valid[sp]) throw std::runtime_error("vocoder: speaker slot not set");
-        CUDA_CHECK(cudaMemcpyAsync(vcb.p + (size_t)i * cbias_stride, spk_cbias.p + (size_t)sp * cbias_stride,
-                                   (size_t)cbias_stride * sizeof(float), cudaMemcpyDeviceToDevice, st));
+// A batch is `nb` WINDOWS: item i = z-frames [z0, z0 + nz) of a chunk whose latents start at `lat` (device).  A window that
+// starts at z-frame 0 / ends at the chunk's last z-frame sees the reference's zero padding there; inner window edges see
+// zero padding too, so the caller discards `voc_hz` z-frames of output next to them (receptive field).  Windows of one
+// batch may have different lengths: buffers are strided by the longest (Lz), kernels skip what lies beyond an item's end.
+// All vocoder work is issued on st_voc.  wav_dev_out: [nb][Lz * hop].
+int Engine::z_frames(int T) const {
+    const double s1 = (double)cfg.code_stride / (double)cfg.output_hop_length;
+    const double s2 = (double)cfg.output_sample_rate / (double)cfg.input_sample_rate;
+    const int T1 = (int)std::floor((double)T * s1);
+    return cfg.output_sample_rate != cfg.input_sample_rate ? (int)std::floor((double)T1 * s2) : T1;
+}
+
+// z-frames that can be interpolated from the first n latent frames of a chunk that is still growing, i.e. without touching
+// either interpolation's end clamp: z[j] reads y[a0], y[a0 + 1] with a0 = floor((j + .5) / s2 - .5) and y[a] reads
+// lat[b0], lat[b0 + 1] with b0 = floor((a + .5) / s1 - .5); one frame of slack on both levels (float rounding)
+int Engine::z_avail(int n) const {
+    const double s1 = (double)cfg.code_stride / (double)cfg.output_hop_length;
+    const bool resample = cfg.output_sample_rate != cfg.input_sample_rate;
+    const double s2 = resample ? (double)cfg.output_sample_rate / (double)cfg.input_sample_rate : 1.0;
+    const int A = (int)std::floor(((double)n - 1.5) * s1 - 0.5) - 1;        // largest y index whose sources are < n - 1
+    if (A < 1) return 0;
+    const int J = (int)std::floor(((double)A - 0.5) * s2 - 0.5) - 1;        // z indices < J read y indices <= A
+    return std::max(0, std::min(J, z_frames(n)));
+}
+
+int Engine::samples_for(int T) const { return z_frames(T) * voc_hop; }
+
+bool Engine::voc_fits(int nb, int Lz) const {
+    if (nb < 1 || nb > kVocMaxItems || Lz < 1 || Lz > voc_max_Tz) return false;
+    if ((size_t)nb * Lz > voc_cap_z) return false;
+    if (tc_vocoder_ready && use_tc_vocoder) {
+        if ((size_t)nb * cfg.voc_in_dim * atoms_lpad(Lz) > vz16_halves) return false;
+        size_t mx = (size_t)cfg.voc_init_ch * atoms_lpad(Lz); int len = Lz;
+        for (int i = 0; i < cfg.voc_n_up; ++i) { len *= cfg.voc_up_rates[i]; mx = std::max(mx, (size_t)stage_ch[i] * atoms_lpad(len)); }
+        if ((size_t)nb * mx > va16_halves) return false;
     }
-    if (tc_vocoder_ready && use_tc_vocoder) { run_vocoder_tc(lat_dev, T, nb, wav_dev_out, n_out, stage, stage_out, stage_cap); return; }
+    return true;
+}
+
+void Engine::run_vocoder(const VocItem* it, int nb, float* wav_dev_out, const char* stage, float* stage_out, int64_t stage_cap) {
+    if (nb < 1 || nb > kVocMaxItems) throw std::runtime_error("vocoder: batch out of range");
+    int Lz = 0, spk[kVocMaxItems];
+    for (int i = 0; i < nb; ++i) {
+        if (it[i].nz <= 0 || it[i].T <= 0 || it[i].T > voc_max_T) throw std::runtime_error("vocoder: window out of range");
+        const int sp = it[i].speaker;
+        if (sp < 0 || sp >= S || !spk_valid[sp]) throw std::runtime_error("vocoder: speaker slot not set");
+        spk[i] = sp;
+        Lz = std::max(Lz, it[i].nz);
+    }
+    if (!voc_fits(nb, Lz)) throw std::runtime_error("vocoder: batch exceeds the workspace");
+    launch_gather_rows(spk_cbias.p, spk, nb, cbias_stride, vcb.p, st_voc);
+    if (tc_vocoder_ready && use_tc_vocoder) run_vocoder_tc(it, nb, Lz, wav_dev_out, stage, stage_out, stage_cap);
+    else run_vocoder_f32(it, nb, Lz, wav_dev_out, stage, stage_out, stage_cap);
+}
+
+// fp32 CUDA-core path (parity mode).  Its kernels take equal-length batches: the items (sorted by length by the caller or
+// not) are processed in runs of equal window length, each run one batch through the whole generator.
+void Engine::run_vocoder_f32(const VocItem* it, int nb, int Lz, float* wav_dev_out, const char* stage, float* stage_out,
+                             int64_t stage_cap) {
+    const auto& c = cfg;
+    cudaStream_t sv = st_voc;
     const double s1 = (double)c.code_stride / (double)c.output_hop_length;
     const double s2 = (double)c.output_sample_rate / (double)c.input_sample_rate;
-    const int T1 = (int)std::floor((double)T * s1);
     const bool resample = c.output_sample_rate != c.input_sample_rate;
-    const int Tz = resample ? (int)std::floor((double)T1 * s2) : T1;
-    const float* cb = vcb.p;
-    auto dump = [&](const char* name, const float* p, size_t n) {           // first batch item only
-        if (stage && stage_out && std::strcmp(stage, name) == 0) {
-            const size_t m = std::min<size_t>(n, (size_t)stage_cap);
-            CUDA_CHECK(cudaMemcpyAsync(stage_out, p, m * sizeof(float), cudaMemcpyDeviceToHost, st));
-        }
-    };
-    launch_interp(lat_dev, vz.p, nullptr, 0, T, c.voc_in_dim, T1, Tz, s1, resample ? s2 : 1.0, nb, st);
-    dump("z", vz.p, (size_t)c.voc_in_dim * Tz);
-    conv1d(conv_pre, vz.p, cb + cbias_off[0], nullptr, vpre.p, Tz, 1, 1.0f, 1.0f, CONV_STORE, nb);
-    dump("pre", vpre.p, (size_t)c.voc_init_ch * Tz);
-    const float* cur = vpre.p;
-    float in_scale = 1.0f;
-    int len = Tz;
     const int nk = c.voc_n_rb;
-    float* X = vb[0].p; float* TMP = vb[1].p; float* R1 = vb[2].p; float* R2 = vb[3].p; float* ZS = vb[4].p;
-    for (int i = 0; i < c.voc_n_up; ++i) {
-        const ConvW& u = *ups[i];
-        launch_conv_transpose1d(cur, u.wt.p, u.b.p, cb + cbias_off[i + 1], X, nullptr, 0, 0.f, u.Cin, u.Cout, len, u.K,
-                                c.voc_up_rates[i], in_scale, 0.1f, nb, cbias_stride, st);
-        len *= c.voc_up_rates[i];
-        const int C = u.Cout;
-        { char nm[16]; snprintf(nm, sizeof(nm), "up%d", i); dump(nm, X, (size_t)C * len); }
-        for (int j = 0; j < nk; ++j) {
-            const RB& rb = *rbs[i * nk + j];
-            const float* r_in = X;
-            for (int t = 0; t < 3; ++t) {
-                const ConvW& a = *rb.c1[t];
-                const ConvW& b = *rb.c2[t];
-                conv1d(a, r_in, nullptr, nullptr, TMP, len, c.voc_rb_dilations[t], 1.0f, 0.1f, CONV_STORE, nb);
-                if (t < 2) {
-                    float* r_out = (t == 0) ? R1 : R2;
-                    conv1d(b, TMP, nullptr, r_in, r_out, len, 1, 1.0f, 0.1f, CONV_STORE, nb);
-                    r_in = r_out;
-                } else {
-                    conv1d(b, TMP, nullptr, r_in, ZS, len, 1, 1.0f, 0.1f, j == 0 ? CONV_STORE : CONV_ACCUM, nb);
+    const size_t wav_stride = (size_t)Lz * voc_hop;
+    for (int i0 = 0; i0 < nb;) {
+        int i1 = i0 + 1;
+        while (i1 < nb && it[i1].nz == it[i0].nz) ++i1;
+        const int rn = i1 - i0, Tz = it[i0].nz;
+        const float* cb = vcb.p + (size_t)i0 * cbias_stride;
+        const bool first = (i0 == 0);
+        auto dump = [&](const char* name, const float* p, size_t n) {           // first batch item only
+            if (first && stage && stage_out && std::strcmp(stage, name) == 0) {
+                const size_t m = std::min<size_t>(n, (size_t)stage_cap);
+                CUDA_CHECK(cudaMemcpyAsync(stage_out, p, m * sizeof(float), cudaMemcpyDeviceToHost, sv));
+            }
+        };
+        InterpItem ii[kVocMaxItems];
+        for (int k = 0; k < rn; ++k) {
+            const VocItem& v = it[i0 + k];
+            ii[k] = InterpItem{v.lat, v.T, (int)std::floor((double)v.T * s1), v.z0, v.nz};
+            if (!resample) ii[k].T1 = ii[k].T;
+        }
+        launch_interp(ii, rn, vz.p, nullptr, 0, c.voc_in_dim, Tz, s1, resample ? s2 : 1.0, sv);
+        dump("z", vz.p, (size_t)c.voc_in_dim * Tz);
+        launch_conv1d(vz.p, conv_pre.wt.p, conv_pre.b.p, cb + cbias_off[0], nullptr, vpre.p, conv_pre.Cin, conv_pre.Cout, Tz,
+                      conv_pre.K, 1, 1.0f, 1.0f, CONV_STORE, rn, cbias_stride, sv);
+        dump("pre", vpre.p, (size_t)c.voc_init_ch * Tz);
+        const float* cur = vpre.p;
+        float in_scale = 1.0f;
+        int len = Tz;
+        float* X = vb[0].p; float* TMP = vb[1].p; float* R1 = vb[2].p; float* R2 = vb[3].p; float* ZS = vb[4].p;
+        auto conv = [&](const ConvW& w, const float* x, const float* resid, float* out, int dil, int mode) {
+            launch_conv1d(x, w.wt.p, w.b.p, nullptr, resid, out, w.Cin, w.Cout, len, w.K, dil, 1.0f, 0.1f, mode, rn, cbias_stride, sv);
+        };
+        for (int i = 0; i < c.voc_n_up; ++i) {
+            const ConvW& u = *ups[i];
+            launch_conv_transpose1d(cur, u.wt.p, u.b.p, cb + cbias_off[i + 1], X, nullptr, 0, 0.f, u.Cin, u.Cout, len, u.K,
+                                    c.voc_up_rates[i], in_scale, 0.1f, rn, cbias_stride, sv);
+            len *= c.voc_up_rates[i];
+            const int C = u.Cout;
+            { char nm[16]; snprintf(nm, sizeof(nm), "up%d", i); dump(nm, X, (size_t)C * len); }
+            for (int j = 0; j < nk; ++j) {
+                const RB& rb = *rbs[i * nk + j];
+                const float* r_in = X;
+                for (int t = 0; t < 3; ++t) {
+                    conv(*rb.c1[t], r_in, nullptr, TMP, c.voc_rb_dilations[t], CONV_STORE);
+                    if (t < 2) {
+                        float* r_out = (t == 0) ? R1 : R2;
+                        conv(*rb.c2[t], TMP, r_in, r_out, 1, CONV_STORE);
+                        r_in = r_out;
+                    } else {
+                        conv(*rb.c2[t], TMP, r_in, ZS, 1, j == 0 ? CONV_STORE : CONV_ACCUM);
+                    }
                 }
             }
+            { char nm[16]; snprintf(nm, sizeof(nm), "mrf%d", i); dump(nm, ZS, (size_t)C * len); }   // un-normalised sum
+            // next stage reads the MRF sum scaled by 1/nk; its ConvT writes X (dead by now), and ZS is only
+            // overwritten after that ConvT has consumed it (stream order)
+            cur = ZS;
+            in_scale = 1.0f / (float)nk;
         }
-        { char nm[16]; snprintf(nm, sizeof(nm), "mrf%d", i); dump(nm, ZS, (size_t)C * len); }   // un-normalised sum
-        // next stage reads the MRF sum scaled by 1/nk; its ConvT writes X (dead by now), and ZS is only
-        // overwritten after that ConvT has consumed it (stream order)
-        cur = ZS;
-        in_scale = 1.0f / (float)nk;
+        launch_conv_post(cur, conv_post_w.p, wav_dev_out + (size_t)i0 * wav_stride, post_cin, len, 7, in_scale, 0.01f, rn, sv,
+                         nullptr, (int)wav_stride);
+        i0 = i1;
     }
-    launch_conv_post(cur, conv_post_w.p, wav_dev_out, post_cin, len, 7, in_scale, 0.01f, nb, st);
-    *n_out = len;
 }
 
 // Tensor-core vocoder: every Conv1d operand is kept as activated fp16 atoms written by its producer's epilogue
 // (ConvT / previous conv), so the conv kernels are pure bulk-copy + tcgen05; fp32 is kept for the residual stream
 // (x, r1, r2), the MRF sum and the final waveform.  (speaker biases were gathered into vcb by run_vocoder)
-void Engine::run_vocoder_tc(const float* lat_dev, int T, int nb, float* wav_dev_out, int* n_out, const char* stage,
-                            float* stage_out, int64_t stage_cap) {
+void Engine::run_vocoder_tc(const VocItem* it, int nb, int Lz, float* wav_dev_out, const char* stage, float* stage_out,
+                            int64_t stage_cap) {
     const auto& c = cfg;
+    cudaStream_t sv = st_voc;
     const double s1 = (double)c.code_stride / (double)c.output_hop_length;
     const double s2 = (double)c.output_sample_rate / (double)c.input_sample_rate;
-    const int T1 = (int)std::floor((double)T * s1);
     const bool resample = c.output_sample_rate != c.input_sample_rate;
-    const int Tz = resample ? (int)std::floor((double)T1 * s2) : T1;
     const float* cb = vcb.p;
     auto dump = [&](const char* name, const float* p, size_t n) {
         if (stage && stage_out && std::strcmp(stage, name) == 0) {
             const size_t m = std::min<size_t>(n, (size_t)stage_cap);
-            CUDA_CHECK(cudaMemcpyAsync(stage_out, p, m * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaMemcpyAsync(stage_out, p, m * sizeof(float), cudaMemcpyDeviceToHost, sv));
         }
     };
-    int lpad = atoms_lpad(Tz);
+    InterpItem ii[kVocMaxItems];
+    int lens[kVocMaxItems];                  // per-item signal length at the current stage
+    for (int k = 0; k < nb; ++k) {
+        ii[k] = InterpItem{it[k].lat, it[k].T, resample ? (int)std::floor((double)it[k].T * s1) : it[k].T, it[k].z0, it[k].nz};
+        lens[k] = it[k].nz;
+    }
+    auto conv_tc = [&](const ConvW& w, const __half* a16, const float* cbias, const float* resid, float* out32, __half* out16,
+                       int L, int lpad, int dil, int mode, float scale16) {
+        launch_conv1d_tc(a16, w.blob.p, w.plan, w.b.p, cbias, resid, out32, out16, w.Cin, w.Cout, L, lpad, w.K, dil, 0.1f, scale16,
+                         mode, nb, cbias_stride, sv, lens);
+    };
+    int lpad = atoms_lpad(Lz);
     __half* XA = va16[0].p; __half* TA = va16[1].p; __half* RA[2] = {va16[2].p, va16[3].p}; __half* PA = va16[4].p;
-    launch_atoms_zero_pads(vz16.p, nb * c.voc_in_dim / 8, lpad, Tz, st);
-    launch_atoms_zero_pads(PA, nb * c.voc_init_ch / 8, lpad, Tz, st);
-    launch_interp(lat_dev, stage ? vz.p : nullptr, vz16.p, lpad, T, c.voc_in_dim, T1, Tz, s1, resample ? s2 : 1.0, nb, st);
-    if (stage) dump("z", vz.p, (size_t)c.voc_in_dim * Tz);
+    launch_atoms_zero_pads(vz16.p, nb * c.voc_in_dim / 8, lpad, Lz, sv, nb, lens);
+    launch_atoms_zero_pads(PA, nb * c.voc_init_ch / 8, lpad, Lz, sv, nb, lens);
+    launch_interp(ii, nb, stage ? vz.p : nullptr, vz16.p, lpad, c.voc_in_dim, Lz, s1, resample ? s2 : 1.0, sv);
+    if (stage) dump("z", vz.p, (size_t)c.voc_in_dim * Lz);
     // conv_pre: fp32 copy only for the stage tap; its activated fp16 atoms feed the first transposed conv
-    conv1d_tc(conv_pre, vz16.p, cb + cbias_off[0], nullptr, stage ? vpre.p : nullptr, PA, Tz, lpad, 1, CONV_STORE, nb);
-    if (stage) dump("pre", vpre.p, (size_t)c.voc_init_ch * Tz);
-    int len = Tz;
+    conv_tc(conv_pre, vz16.p, cb + cbias_off[0], nullptr, stage ? vpre.p : nullptr, PA, Lz, lpad, 1, CONV_STORE, 1.0f);
+    if (stage) dump("pre", vpre.p, (size_t)c.voc_init_ch * Lz);
+    int len = Lz;
     const int nk = c.voc_n_rb;
     float* X = vb[0].p; float* R[2] = {vb[2].p, vb[3].p}; float* ZS = vb[4].p;
     for (int i = 0; i < c.voc_n_up; ++i) {
@@ -1127,36 +1300,36 @@ void Engine::run_vocoder_tc(const float* lat_dev, int T, int nb, float* wav_dev_
         const int lout = len * up;
         const int lpad_in = lpad;
         lpad = atoms_lpad(lout);
-        for (__half* b : {XA, TA, RA[0], RA[1]}) launch_atoms_zero_pads(b, nb * C / 8, lpad, lout, st);
+        int lens_out[kVocMaxItems];
+        for (int k = 0; k < nb; ++k) lens_out[k] = lens[k] * up;
+        for (__half* b : {XA, TA, RA[0], RA[1]}) launch_atoms_zero_pads(b, nb * C / 8, lpad, lout, sv, nb, lens_out);
         launch_convT_tc(PA, u.blob.p, u.plan, u.b.p, cb + cbias_off[i + 1], X, XA, u.Cin, C, len, lpad_in, lpad, up, 0.1f, nb,
-                        cbias_stride, st);
+                        cbias_stride, sv, lens);
         len = lout;
+        for (int k = 0; k < nb; ++k) lens[k] = lens_out[k];
         { char nm[16]; snprintf(nm, sizeof(nm), "up%d", i); dump(nm, X, (size_t)C * len); }
         const bool more = (i + 1 < c.voc_n_up);
-        if (more) launch_atoms_zero_pads(PA, nb * C / 8, lpad, len, st);     // PA is re-shaped for the next stage's input
+        if (more) launch_atoms_zero_pads(PA, nb * C / 8, lpad, len, sv, nb, lens);     // PA is re-shaped for the next stage's input
         for (int j = 0; j < nk; ++j) {
             const RB& rb = *rbs[i * nk + j];
             const __half* in16 = XA;
             const float* resid = X;
             for (int t = 0; t < 3; ++t) {
-                conv1d_tc(*rb.c1[t], in16, nullptr, nullptr, nullptr, TA, len, lpad, c.voc_rb_dilations[t], CONV_STORE, nb);
+                conv_tc(*rb.c1[t], in16, nullptr, nullptr, nullptr, TA, len, lpad, c.voc_rb_dilations[t], CONV_STORE, 1.0f);
                 if (t < 2) {
-                    conv1d_tc(*rb.c2[t], TA, nullptr, resid, R[t], RA[t], len, lpad, 1, CONV_STORE, nb);
+                    conv_tc(*rb.c2[t], TA, nullptr, resid, R[t], RA[t], len, lpad, 1, CONV_STORE, 1.0f);
                     in16 = RA[t]; resid = R[t];
                 } else {
                     // MRF sum; the last resblock also emits lrelu(sum / nk) as the next transposed conv's operand
                     const bool emit = more && (j == nk - 1);
-                    conv1d_tc(*rb.c2[t], TA, nullptr, resid, ZS, emit ? PA : nullptr, len, lpad, 1,
-                              j == 0 ? CONV_STORE : CONV_ACCUM, nb, 1.0f / (float)nk);
+                    conv_tc(*rb.c2[t], TA, nullptr, resid, ZS, emit ? PA : nullptr, len, lpad, 1,
+                            j == 0 ? CONV_STORE : CONV_ACCUM, 1.0f / (float)nk);
                 }
             }
         }
         { char nm[16]; snprintf(nm, sizeof(nm), "mrf%d", i); dump(nm, ZS, (size_t)C * len); }
     }
-    const float* cur = ZS;
-    const float in_scale = 1.0f / (float)nk;
-    launch_conv_post(cur, conv_post_w.p, wav_dev_out, post_cin, len, 7, in_scale, 0.01f, nb, st);
-    *n_out = len;
+    launch_conv_post(ZS, conv_post_w.p, wav_dev_out, post_cin, len, 7, 1.0f / (float)nk, 0.01f, nb, sv, lens);
 }
 
 // ================================================================================================
@@ -1164,12 +1337,14 @@ void Engine::run_vocoder_tc(const float* lat_dev, int T, int nb, float* wav_dev_
 // ================================================================================================
 float* Engine::pinned_get(size_t n, size_t* cap) {
     std::lock_guard<std::mutex> lk(pin_mu);
+    size_t best = pinned_pool.size();                  // best fit: token-sized requests must not eat waveform-sized buffers
     for (size_t i = 0; i < pinned_pool.size(); ++i)
-        if (pinned_pool[i].second >= n) {
-            float* p = pinned_pool[i].first; *cap = pinned_pool[i].second;
-            pinned_pool.erase(pinned_pool.begin() + i);
-            return p;
-        }
+        if (pinned_pool[i].second >= n && (best == pinned_pool.size() || pinned_pool[i].second < pinned_pool[best].second)) best = i;
+    if (best != pinned_pool.size() && pinned_pool[best].second <= 4 * n + 4096) {
+        float* p = pinned_pool[best].first; *cap = pinned_pool[best].second;
+        pinned_pool.erase(pinned_pool.begin() + best);
+        return p;
+    }
     float* p = nullptr;
     CUDA_CHECK(cudaMallocHost(&p, n * sizeof(float)));
     *cap = n;
@@ -1197,10 +1372,11 @@ void Engine::pinned_put(float* p, size_t cap) { std::lock_guard<std::mutex> lk(p
 void Engine::submit(uint64_t id, const int32_t* text, int n_text, int speaker, const xtts_sampling& sp) {
     if (n_text <= 0 || n_text > cfg.max_text_tokens + 2) throw std::runtime_error("n_text out of range (1..max_text_tokens+2)");
     if (speaker < 0 || speaker >= S) throw std::runtime_error("speaker slot out of range");
+    // ids are checked here so that a bad id fails this call alone, not the batched step it would have joined
+    for (int i = 0; i < n_text; ++i)
+        if (text[i] < 0 || text[i] >= cfg.n_text_tokens) throw std::runtime_error("text token id out of range");
     std::shared_ptr<Sequence> s(new Sequence());
     s->id = id; s->text_ids.assign(text, text + n_text); s->speaker = speaker; s->sp = sp; s->t_submit = now_s();
-    if (id & kPartialBit) throw std::runtime_error("seq_id must be < 2^63");
-    if (sp.early_tokens > 0 && sp.vocode) s->early_tokens = sp.early_tokens;
     require_finalized();
     if (!spk_valid[speaker]) throw std::runtime_error("speaker slot not set");
     {
@@ -1211,143 +1387,261 @@ void Engine::submit(uint64_t id, const int32_t* text, int n_text, int speaker, c
     cv_work.notify_all();
 }
 
-// tokens + latent snapshot of one finished sequence; frees its slot
-void Engine::finish_sequence(std::shared_ptr<Sequence> s) {
-    int n = 0;
-    d_n_gen.download(&n, 1, st, s->slot);
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    n = std::min(n, CAP);
-    s->tokens.resize(n);
-    d_tokens.download(s->tokens.data(), n, st, (size_t)s->slot * CAP);
-    // latents copy (device) so the slot can be recycled immediately
-    s->lat_dev = dev_get((size_t)std::max(1, n) * H, &s->lat_dev_cap);
-    CUDA_CHECK(cudaMemcpyAsync(s->lat_dev, d_latents.p + (size_t)s->slot * CAP * H, (size_t)n * H * sizeof(float),
-                               cudaMemcpyDeviceToDevice, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    st_tokens += n;
-    release_slot(*s);
-}
-
-// vocode a group of finished sequences that have the same token count, VB at a time, then retire them
-void Engine::finish_group(std::vector<std::shared_ptr<Sequence>>& grp) {
-    const double t0 = now_s();
-    for (size_t b0 = 0; b0 < grp.size(); b0 += VB) {
-        const int nb = (int)std::min<size_t>(VB, grp.size() - b0);
-        const int n = (int)grp[b0]->tokens.size();
-        std::vector<int> spk(nb);
-        for (int i = 0; i < nb; ++i) {
-            spk[i] = grp[b0 + i]->speaker;
-            CUDA_CHECK(cudaMemcpyAsync(vlat.p + (size_t)i * n * H, grp[b0 + i]->lat_dev, (size_t)n * H * sizeof(float),
-                                       cudaMemcpyDeviceToDevice, st));
-        }
-        int ns = 0;
-        run_vocoder(vlat.p, n, spk.data(), nb, vwav.p, &ns, nullptr, nullptr, 0);
-        for (int i = 0; i < nb; ++i) {
-            auto& s = grp[b0 + i];
-            const int skip = std::min(s->early_samples, ns);       // 0 unless a partial first-audio piece went out already
-            const int nrem = ns - skip;
-            const float* src = vwav.p + (size_t)i * ns + skip;
-            s->n_samples = nrem;
-            if (d2h_wav) {
-                s->wav_host = pinned_get(std::max(1, nrem), &s->wav_cap);
-                if (nrem > 0) CUDA_CHECK(cudaMemcpyAsync(s->wav_host, src, (size_t)nrem * sizeof(float), cudaMemcpyDeviceToHost, st));
-            } else {
-                s->wav_dev = dev_get(std::max(1, nrem), &s->wav_dev_cap);
-                if (nrem > 0) CUDA_CHECK(cudaMemcpyAsync(s->wav_dev, src, (size_t)nrem * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            }
-            st_samples += nrem;
-        }
-        CUDA_CHECK(cudaStreamSynchronize(st));
-        const double t = now_s();
-        for (int i = 0; i < nb; ++i) { grp[b0 + i]->t_done = t; retire(grp[b0 + i]); }
-    }
-    st_voc_ms += (now_s() - t0) * 1e3;
-}
-
-// samples the vocoder produces for T latent frames (the two interpolations of HifiDecoder.forward, then the upsampling)
-int Engine::samples_for(int T) const {
-    const double s1 = (double)cfg.code_stride / (double)cfg.output_hop_length;
-    const double s2 = (double)cfg.output_sample_rate / (double)cfg.input_sample_rate;
-    const int T1 = (int)std::floor((double)T * s1);
-    int len = cfg.output_sample_rate != cfg.input_sample_rate ? (int)std::floor((double)T1 * s2) : T1;
-    for (int i = 0; i < cfg.voc_n_up; ++i) len *= cfg.voc_up_rates[i];
-    return len;
-}
-
-// First audio early (xtts_sampling.early_tokens; not in the reference, which returns whole chunks):
-// every sequence of `grp` is still decoding and has early_tokens + kEarlyLookahead latent frames.  Vocode that prefix
-// straight from the latent ring and deliver the samples of the first early_tokens frames as a PARTIAL result (status 1);
-// the lookahead frames cover the vocoder's receptive field, so these samples equal the ones the whole chunk will give.
-void Engine::emit_early(std::vector<std::shared_ptr<Sequence>>& grp) {
-    const double t0 = now_s();
-    std::map<int, std::vector<std::shared_ptr<Sequence>>> by_len;
-    for (auto& s : grp) by_len[s->early_tokens].push_back(s);
-    for (auto& kv : by_len) {
-        const int n_early = kv.first, T = n_early + kEarlyLookahead;
-        const int keep = samples_for(n_early);
-        auto& v = kv.second;
-        for (size_t b0 = 0; b0 < v.size(); b0 += VB) {
-            const int nb = (int)std::min<size_t>(VB, v.size() - b0);
-            std::vector<int> spk(nb);
-            for (int i = 0; i < nb; ++i) {
-                spk[i] = v[b0 + i]->speaker;
-                CUDA_CHECK(cudaMemcpyAsync(vlat.p + (size_t)i * T * H, d_latents.p + (size_t)v[b0 + i]->slot * CAP * H,
-                                           (size_t)T * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            }
-            int ns = 0;
-            run_vocoder(vlat.p, T, spk.data(), nb, vwav.p, &ns, nullptr, nullptr, 0);
-            if (keep <= 0 || keep > ns) throw std::runtime_error("early emit: sample count out of range");
-            std::vector<std::shared_ptr<Sequence>> parts;
-            for (int i = 0; i < nb; ++i) {
-                auto& s = v[b0 + i];
-                std::shared_ptr<Sequence> p(new Sequence());
-                p->id = s->id; p->speaker = s->speaker; p->status = 1; p->n_prompt = s->n_prompt;
-                p->t_submit = s->t_submit; p->t_first = s->t_first;
-                p->tokens.resize(n_early);
-                d_tokens.download(p->tokens.data(), n_early, st, (size_t)s->slot * CAP);
-                p->n_samples = keep;
-                if (d2h_wav) {
-                    p->wav_host = pinned_get(keep, &p->wav_cap);
-                    CUDA_CHECK(cudaMemcpyAsync(p->wav_host, vwav.p + (size_t)i * ns, (size_t)keep * sizeof(float), cudaMemcpyDeviceToHost, st));
-                } else {
-                    p->wav_dev = dev_get(keep, &p->wav_dev_cap);
-                    CUDA_CHECK(cudaMemcpyAsync(p->wav_dev, vwav.p + (size_t)i * ns, (size_t)keep * sizeof(float), cudaMemcpyDeviceToDevice, st));
-                }
-                st_samples += keep;
-                parts.push_back(p);
-            }
-            CUDA_CHECK(cudaStreamSynchronize(st));
-            const double t = now_s();
-            for (int i = 0; i < nb; ++i) {
-                v[b0 + i]->early_done = true; v[b0 + i]->early_samples = keep;
-                parts[i]->t_done = t;
-                std::lock_guard<std::mutex> lk(q_mu);          // a partial piece does not end the sequence: inflight unchanged
-                done_q.push_back(parts[i]);
-                done_map[parts[i]->id | kPartialBit] = parts[i];
-            }
-            cv_done.notify_all();
-        }
-    }
-    st_voc_ms += (now_s() - t0) * 1e3;
-}
-
-void Engine::retire(std::shared_ptr<Sequence> s) {
+// xtts_cancel: the reference aborts the vLLM request when its generator is dropped.  Handled by the scheduler thread at
+// its next iteration: a queued chunk is dropped, a decoding one stops and gives its slot and KV pages back.
+void Engine::cancel(uint64_t id) {
     {
         std::lock_guard<std::mutex> lk(q_mu);
-        done_q.push_back(s);
-        done_map[s->id] = s;
-        --inflight;
+        cancel_req.push_back(id);
+    }
+    cv_work.notify_all();
+}
+
+void Engine::free_seq_buffers(Sequence& s) {
+    if (s.tok_host) { cudaFreeHost(s.tok_host); s.tok_host = nullptr; }
+    if (s.wav_host) { cudaFreeHost(s.wav_host); s.wav_host = nullptr; }
+    if (s.wav_dev) { cudaFree(s.wav_dev); s.wav_dev = nullptr; }
+    if (s.lat_dev) { cudaFree(s.lat_dev); s.lat_dev = nullptr; }
+}
+
+void Engine::recycle_seq_buffers(Sequence& s) {
+    if (s.tok_host) { pinned_put(reinterpret_cast<float*>(s.tok_host), s.tok_cap); s.tok_host = nullptr; }
+    if (s.wav_host) { pinned_put(s.wav_host, s.wav_cap); s.wav_host = nullptr; }
+    if (s.wav_dev) { dev_put(s.wav_dev, s.wav_dev_cap); s.wav_dev = nullptr; }
+    if (s.lat_dev) { dev_put(s.lat_dev, s.lat_dev_cap); s.lat_dev = nullptr; }
+}
+
+// hands a piece to the completion queue (xtts_poll / xtts_fetch)
+void Engine::deliver(std::shared_ptr<Piece> p, bool ends_sequence) {
+    {
+        std::lock_guard<std::mutex> lk(q_mu);
+        done_q.push_back(p);
+        done_map[p->s->id].push_back(p);
+        if (ends_sequence) --inflight;
     }
     cv_done.notify_all();
+}
+
+// a chunk that never reached a slot (queued, or its admission failed) ends with `code`
+void Engine::fail_unadmitted(std::shared_ptr<Sequence> s, int code, const char* what) {
+    if (code != XTTS_ERR_CANCELLED) set_error(what);
+    release_slot(*s);
+    std::shared_ptr<Piece> p(new Piece());
+    p->s = s; p->status = code; p->final = true; p->t_done = s->t_done = now_s();
+    deliver(p, true);
+}
+
+// The decode of `s` is over (stop token / max_tokens: fail_status 0; cancelled or failed: < 0).  Its KV pages go back now;
+// the slot — whose latent ring and token row the remaining vocoder work reads — when the final job has completed.
+void Engine::on_finished(std::shared_ptr<Sequence> s, int n_tokens, int fail_status) {
+    release_pages(*s);
+    s->n_tokens = std::max(0, std::min(n_tokens, CAP));
+    st_tokens += s->n_tokens;
+    VocJob j;
+    j.s = s; j.final = true; j.fail_status = fail_status; j.T_clamp = std::max(1, s->n_tokens); j.tok_upto = s->n_tokens;
+    if (fail_status == 0 && s->sp.vocode && s->n_tokens > 0) {
+        const int Tz = z_frames(s->n_tokens);
+        j.zk0 = std::min(s->voc_z_done, Tz); j.zk1 = Tz;
+        j.zw0 = std::max(0, j.zk0 - voc_hz); j.zw1 = Tz;
+    }
+    s->next_boundary = 0;
+    voc_pending.push_back(std::move(j));
+}
+
+// A chunk that is still decoding: once the frames behind its next cut (plus the vocoder's receptive field) exist, the
+// window up to the cut goes to the vocoder — audio is produced while the GPT is still busy with the rest of the chunk.
+void Engine::maybe_cut_window(std::shared_ptr<Sequence>& s) {
+    while (s->next_boundary > 0 && s->next_boundary < s->max_tok) {
+        const int b = s->next_boundary;
+        const int n_avail = s->steps + 1;                   // latent frames in the ring
+        const int zk1 = z_frames(b), zw1 = zk1 + voc_hz;
+        if (z_avail(n_avail) < zw1) return;
+        const int zk0 = s->voc_z_done;
+        const int zw0 = std::max(0, zk0 - voc_hz);
+        if (zw1 - zw0 > voc_max_Tz) { s->next_boundary = 0; return; }
+        if (zk1 > zk0) {
+            VocJob j;
+            j.s = s; j.T_clamp = n_avail; j.zw0 = zw0; j.zw1 = zw1; j.zk0 = zk0; j.zk1 = zk1; j.tok_upto = b;
+            voc_pending.push_back(std::move(j));
+            s->voc_z_done = zk1;
+        }
+        s->next_boundary = s->seg_next > 0 ? b + s->seg_next : 0;
+    }
+}
+
+// one vocoder launch sequence for `jobs` on st_voc: windows -> waveforms -> the kept samples into each chunk's own buffer,
+// token ids (and, for final jobs, the latent snapshot) next to them; completion is observed through b.ev1
+void Engine::dispatch_batch(std::vector<VocJob>& jobs, bool decode_active) {
+    VocBatch b;
+    CUDA_CHECK(cudaEventCreate(&b.ev0)); CUDA_CHECK(cudaEventCreate(&b.ev1));
+    cudaStream_t sv = st_voc;
+    try {
+        CUDA_CHECK(cudaEventRecord(b.ev0, sv));
+        std::vector<VocItem> items;
+        std::vector<int> job_of;
+        for (size_t k = 0; k < jobs.size(); ++k) {
+            VocJob& j = jobs[k];
+            Sequence& s = *j.s;
+            if (!s.tok_host) s.tok_host = reinterpret_cast<int32_t*>(pinned_get((size_t)std::max(1, s.max_tok), &s.tok_cap));
+            if (j.zk1 > j.zk0) {
+                const size_t need = (size_t)std::max(1, samples_for(s.max_tok));
+                if (d2h_wav) { if (!s.wav_host) s.wav_host = pinned_get(need, &s.wav_cap); }
+                else if (!s.wav_dev) s.wav_dev = dev_get(need, &s.wav_dev_cap);
+                items.push_back(VocItem{d_latents.p + (size_t)s.slot * CAP * H, j.T_clamp, j.zw0, j.zw1 - j.zw0, s.speaker});
+                job_of.push_back((int)k);
+            }
+        }
+        int Lz = 0;
+        for (auto& it : items) Lz = std::max(Lz, it.nz);
+        if (!items.empty()) {
+            g_voc_sm_cap = (decode_active && voc_sms > 0) ? voc_sms : 0;
+            run_vocoder(items.data(), (int)items.size(), vwav.p, nullptr, nullptr, 0);
+            g_voc_sm_cap = 0;
+        }
+        const size_t wstride = (size_t)Lz * voc_hop;
+        for (size_t i = 0; i < items.size(); ++i) {
+            VocJob& j = jobs[job_of[i]];
+            Sequence& s = *j.s;
+            const size_t n = (size_t)(j.zk1 - j.zk0) * voc_hop, dst_off = (size_t)j.zk0 * voc_hop;
+            const float* src = vwav.p + i * wstride + (size_t)(j.zk0 - j.zw0) * voc_hop;
+            if (d2h_wav) CUDA_CHECK(cudaMemcpyAsync(s.wav_host + dst_off, src, n * sizeof(float), cudaMemcpyDeviceToHost, sv));
+            else CUDA_CHECK(cudaMemcpyAsync(s.wav_dev + dst_off, src, n * sizeof(float), cudaMemcpyDeviceToDevice, sv));
+            st_samples += n;
+        }
+        for (auto& j : jobs) {
+            Sequence& s = *j.s;
+            if (j.tok_upto > 0 && s.slot >= 0)
+                CUDA_CHECK(cudaMemcpyAsync(s.tok_host, d_tokens.p + (size_t)s.slot * CAP, (size_t)j.tok_upto * sizeof(int32_t),
+                                           cudaMemcpyDeviceToHost, sv));
+            if (j.final && j.fail_status == 0 && s.n_tokens > 0 && s.slot >= 0) {
+                s.lat_dev = dev_get((size_t)s.n_tokens * H, &s.lat_dev_cap);
+                CUDA_CHECK(cudaMemcpyAsync(s.lat_dev, d_latents.p + (size_t)s.slot * CAP * H, (size_t)s.n_tokens * H * sizeof(float),
+                                           cudaMemcpyDeviceToDevice, sv));
+            }
+        }
+        CUDA_CHECK(cudaEventRecord(b.ev1, sv));
+    } catch (...) {
+        cudaEventDestroy(b.ev0); cudaEventDestroy(b.ev1);
+        throw;
+    }
+    b.jobs = std::move(jobs);
+    voc_inflight.push_back(std::move(b));
+}
+
+// Forms batches from the queued windows (oldest first): as many as the workspace holds, at most voc_max_items.  A full
+// batch always goes; a partial one only while fewer than two batches are in flight, so that windows arriving while the
+// vocoder is busy collect into larger launches instead of going out one by one.
+void Engine::dispatch_ready(bool decode_active) {
+    while (!voc_pending.empty()) {
+        if (voc_inflight.size() >= 2 && (int)voc_pending.size() < voc_max_items) break;
+        std::vector<VocJob> jobs;
+        int nb = 0, Lz = 0;
+        while (!voc_pending.empty()) {
+            VocJob& j = voc_pending.front();
+            const int w = j.zk1 > j.zk0 ? j.zw1 - j.zw0 : 0;
+            if (w > 0) {
+                if (nb + 1 > voc_max_items || !voc_fits(nb + 1, std::max(Lz, w))) break;
+                ++nb; Lz = std::max(Lz, w);
+            }
+            jobs.push_back(std::move(j));
+            voc_pending.pop_front();
+        }
+        if (jobs.empty()) throw std::runtime_error("vocoder: a window does not fit the workspace");
+        // longest first: equal lengths end up adjacent (the fp32 path batches runs of equal length)
+        std::stable_sort(jobs.begin(), jobs.end(), [](const VocJob& a, const VocJob& b) { return a.zw1 - a.zw0 > b.zw1 - b.zw0; });
+        std::vector<VocJob> keep = jobs;                    // (dispatch_batch consumes `jobs`)
+        try { dispatch_batch(jobs, decode_active); }
+        catch (const std::exception& ex) {
+            // the batch never reached the stream: its chunks fail, their slots are released
+            set_error(ex.what());
+            for (auto& j : keep) {
+                if (!j.final) { j.s->next_boundary = 0; continue; }      // the final job of that chunk will follow and deliver
+                std::shared_ptr<Piece> p(new Piece());
+                p->s = j.s; p->status = XTTS_ERR_CUDA; p->final = true; p->t_done = j.s->t_done = now_s();
+                release_slot(*j.s);
+                deliver(p, true);
+            }
+        }
+    }
+}
+
+void Engine::complete_batch(VocBatch& b) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, b.ev0, b.ev1) == cudaSuccess) st_voc_ms += ms;
+    const double t = now_s();
+    for (auto& j : b.jobs) {
+        Sequence& s = *j.s;
+        const int samp_end = j.zk1 > j.zk0 ? j.zk1 * voc_hop : s.samp_delivered;
+        if (!j.final) {
+            if (!s.stream_pieces) continue;                 // accumulated silently: everything goes out with the final result
+            std::shared_ptr<Piece> p(new Piece());
+            p->s = j.s; p->status = 1; p->tok0 = s.tok_delivered; p->tok1 = j.tok_upto;
+            p->samp0 = s.samp_delivered; p->nsamp = samp_end - s.samp_delivered; p->t_done = t;
+            s.tok_delivered = j.tok_upto; s.samp_delivered = samp_end;
+            deliver(p, false);
+            continue;
+        }
+        std::shared_ptr<Piece> p(new Piece());
+        p->s = j.s; p->final = true; p->status = j.fail_status; p->t_done = s.t_done = t;
+        if (j.fail_status == 0) {
+            const int total = s.sp.vocode ? samples_for(s.n_tokens) : 0;
+            p->tok0 = 0; p->tok1 = s.n_tokens;              // the final result lists every token; samples: what is left
+            p->samp0 = s.samp_delivered; p->nsamp = std::max(0, total - s.samp_delivered);
+        }
+        release_slot(s);
+        deliver(p, true);
+    }
+    cudaEventDestroy(b.ev0); cudaEventDestroy(b.ev1);
+    b.ev0 = b.ev1 = nullptr;
+}
+
+// completed vocoder batches -> completion queue.  block: wait for the oldest batch (nothing else to do meanwhile)
+void Engine::reap(bool block) {
+    while (!voc_inflight.empty()) {
+        VocBatch& b = voc_inflight.front();
+        cudaError_t e = block ? cudaEventSynchronize(b.ev1) : cudaEventQuery(b.ev1);
+        if (e == cudaErrorNotReady) { (void)cudaGetLastError(); return; }
+        if (e != cudaSuccess) {
+            // a failed batch fails its chunks (and, the context being what it is after a device fault, everything after it)
+            set_error(std::string("vocoder batch failed: ") + cudaGetErrorString(e));
+            for (auto& j : b.jobs) if (j.final && j.fail_status == 0) j.fail_status = XTTS_ERR_CUDA;
+        }
+        complete_batch(b);
+        voc_inflight.pop_front();
+        block = false;
+    }
+}
+
+void Engine::process_cancels(const std::vector<uint64_t>& ids) {
+    for (uint64_t id : ids) {
+        bool found = false;
+        for (auto it = waiting.begin(); it != waiting.end(); ++it)
+            if ((*it)->id == id) {
+                auto s = *it; waiting.erase(it);
+                fail_unadmitted(s, XTTS_ERR_CANCELLED, "cancelled");
+                found = true; break;
+            }
+        if (found) continue;
+        for (auto it = running.begin(); it != running.end(); ++it)
+            if ((*it)->id == id) {
+                auto s = *it; running.erase(it);
+                s->cancelled = true;
+                on_finished(s, 0, XTTS_ERR_CANCELLED);      // queued behind its in-flight windows: the slot is freed after them
+                break;
+            }
+        // (an id that is already finishing or finished: nothing to do, its result is on its way)
+    }
 }
 
 void Engine::loop() {
     cudaSetDevice(cfg.device);
     while (true) {
+        std::vector<uint64_t> cancels;
         {
             std::unique_lock<std::mutex> q(q_mu);
             cv_work.wait(q, [&] {
-                return stop.load() || !pending.empty() || (!waiting.empty() && !hold_admission.load()) || !running.empty();
+                return stop.load() || !pending.empty() || !cancel_req.empty() || (!waiting.empty() && !hold_admission.load()) ||
+                       !running.empty() || !voc_pending.empty() || !voc_inflight.empty();
             });
             if (stop.load()) break;
             while (!pending.empty()) {
@@ -1357,15 +1651,13 @@ void Engine::loop() {
                 while (it != waiting.begin() && (*(it - 1))->sp.priority > s->sp.priority) --it;
                 waiting.insert(it, s);
             }
+            cancels.swap(cancel_req);
         }
         std::lock_guard<std::mutex> lk(mu);
-        auto fail = [&](std::shared_ptr<Sequence>& s, int code, const char* what) {
-            s->status = code; set_error(what);
-            release_slot(*s); s->t_done = now_s();
-            retire(s);
-        };
         std::vector<std::shared_ptr<Sequence>> fresh_sp;      // admitted this iteration (outside the try: see the catch)
+        bool gpt_work = false;
         try {
+            process_cancels(cancels);
             // ---- admission (continuous batching): fill free slots, whole prompts, within the row budget
             std::vector<Sequence*> fresh;
             int rows = 0;
@@ -1373,25 +1665,29 @@ void Engine::loop() {
                 auto s = waiting.front();
                 const int p = cfg.n_cond_latents + (int)s->text_ids.size() + 1;
                 if (!fresh.empty() && rows + p > prefill_rows_cap) break;
-                waiting.pop_front();
+                waiting.pop_front();                          // (KV pages cannot run out: the pool holds max_pages per slot)
+                if (!spk_valid[s->speaker]) { fail_unadmitted(s, XTTS_ERR_STATE, "speaker slot not set"); continue; }
                 s->slot = free_slots.back(); free_slots.pop_back();
-                try {
-                    if (!spk_valid[s->speaker]) throw std::runtime_error("speaker slot not set");
-                    init_slot(*s, nullptr, 0);
-                } catch (const std::exception& ex) {
-                    fail(s, XTTS_ERR_STATE, ex.what());
-                    continue;
-                }
                 rows += p;
                 fresh.push_back(s.get()); fresh_sp.push_back(s);
             }
             const double t0 = now_s();
             if (!fresh.empty()) {
+                gpt_work = true;
+                init_slots(fresh, nullptr, 0);
+                for (auto& s : fresh_sp) {
+                    // vocoder windows: the first cut after early_tokens (streaming chunks) or voc_segment tokens, then every
+                    // voc_segment; 0 = the chunk is vocoded whole when it ends
+                    s->stream_pieces = s->sp.early_tokens > 0 && s->sp.vocode;
+                    s->seg_next = s->sp.vocode ? voc_segment : 0;
+                    s->next_boundary = s->stream_pieces ? s->sp.early_tokens : s->seg_next;
+                }
                 prefill(fresh);
                 for (auto& s : fresh_sp) running.push_back(s);
                 fresh_sp.clear();
                 // a sequence may already be finished after its first token (max_tokens == 1 / instant stop)
                 d_finished.download(h_finished, NSLOT, st);
+                d_n_gen.download(h_finished + NSLOT, NSLOT, st);
                 CUDA_CHECK(cudaStreamSynchronize(st));
             }
             if (!running.empty()) {
@@ -1399,85 +1695,80 @@ void Engine::loop() {
                 double ctx_sum = 0;
                 for (auto& s : running) if (!h_finished[s->slot]) { active.push_back(s->slot); ctx_sum += s->n_prompt + s->steps + 1; ++s->steps; }
                 if (!active.empty()) {
+                    gpt_work = true;
                     decode_ctx_sum = ctx_sum;
                     decode_step(active);
                     d_finished.download(h_finished, NSLOT, st);
+                    d_n_gen.download(h_finished + NSLOT, NSLOT, st);
                     CUDA_CHECK(cudaStreamSynchronize(st));
                     if (last_prof) { g_prof.collect_graph(*last_prof, decode_ctx_sum); last_prof = nullptr; }
                 }
             }
-            st_gpt_ms += (now_s() - t0) * 1e3;
-            // ---- first audio early (off unless a chunk asked for it): sequences that just reached their prefix length
-            {
-                std::vector<std::shared_ptr<Sequence>> early;
-                for (auto& s : running)
-                    if (s->early_tokens > 0 && !s->early_done && !h_finished[s->slot] &&
-                        s->steps + 1 >= s->early_tokens + kEarlyLookahead && s->early_tokens + kEarlyLookahead <= voc_max_T)
-                        early.push_back(s);
-                if (!early.empty()) emit_early(early);
+            if (gpt_work) st_gpt_ms += (now_s() - t0) * 1e3;
+            // ---- vocoder work: final windows of the chunks that just ended, cuts of the ones still decoding
+            std::vector<std::shared_ptr<Sequence>> keep;
+            for (auto& s : running) {
+                if (h_finished[s->slot]) on_finished(s, h_finished[NSLOT + s->slot], 0);
+                else { maybe_cut_window(s); keep.push_back(s); }
             }
-            // ---- retire finished sequences: vocode, D2H, completion queue
-            std::vector<std::shared_ptr<Sequence>> keep, fin;
-            for (auto& s : running) (h_finished[s->slot] ? fin : keep).push_back(s);
             running.swap(keep);
-            std::map<int, std::vector<std::shared_ptr<Sequence>>> groups;     // token count -> sequences to vocode
-            for (auto& s : fin) {
-                try {
-                    finish_sequence(s);
-                    if (s->sp.vocode) groups[(int)s->tokens.size()].push_back(s);
-                    else { s->t_done = now_s(); retire(s); }
-                } catch (const std::exception& ex) { fail(s, XTTS_ERR_CUDA, ex.what()); }
-            }
-            for (auto& kv : groups) {
-                try { finish_group(kv.second); }
-                catch (const std::exception& ex) {
-                    for (auto& s : kv.second) if (s->t_done == 0) fail(s, XTTS_ERR_CUDA, ex.what());
-                }
-            }
         } catch (const std::exception& ex) {
             // a failure inside a batched step fails every sequence that was part of it — including the ones admitted
             // in this iteration whose prefill threw before they reached `running`
-            for (auto& s : fresh_sp) fail(s, XTTS_ERR_CUDA, ex.what());
-            for (auto& s : running) fail(s, XTTS_ERR_CUDA, ex.what());
+            set_error(ex.what());
+            for (auto& s : fresh_sp) { release_pages(*s); on_finished(s, 0, XTTS_ERR_CUDA); }
+            for (auto& s : running) on_finished(s, 0, XTTS_ERR_CUDA);
             running.clear();
         }
+        try {
+            dispatch_ready(!running.empty());
+            // nothing for the GPT to do: wait for the oldest vocoder batch instead of spinning
+            reap(!gpt_work && running.empty() && !voc_inflight.empty());
+        } catch (const std::exception& ex) { set_error(ex.what()); }
     }
 }
 
 int Engine::poll(xtts_result* out, int timeout_ms) {
     std::unique_lock<std::mutex> lk(q_mu);
     if (!cv_done.wait_for(lk, std::chrono::milliseconds(std::max(0, timeout_ms)), [&] { return !done_q.empty(); })) return 0;
-    auto s = done_q.front(); done_q.pop_front();
-    out->seq_id = s->id; out->status = s->status; out->n_tokens = (int)s->tokens.size(); out->n_samples = s->n_samples;
-    out->n_prompt_rows = s->n_prompt; out->t_submit = s->t_submit; out->t_first_token = s->t_first; out->t_done = s->t_done;
+    auto p = done_q.front(); done_q.pop_front();
+    const Sequence& s = *p->s;
+    out->seq_id = s.id; out->status = p->status; out->n_tokens = p->tok1 - p->tok0; out->n_samples = p->nsamp;
+    out->n_prompt_rows = s.n_prompt; out->t_submit = s.t_submit; out->t_first_token = s.t_first; out->t_done = p->t_done;
     return 1;
 }
 
+// hands out the OLDEST unfetched piece of `id` (partial pieces before the final result)
 void Engine::fetch(uint64_t id, int32_t* tokens, float* wav, float* latents) {
-    std::shared_ptr<Sequence> s;
+    std::shared_ptr<Piece> p;
     {
         std::lock_guard<std::mutex> lk(q_mu);
-        auto it = done_map.find(id | kPartialBit);          // an unfetched first-audio piece of this id is older than its final
-        if (it == done_map.end()) it = done_map.find(id);
-        if (it == done_map.end()) throw std::runtime_error("fetch: unknown or unfinished sequence id");
-        s = it->second;
-        done_map.erase(it);
-        for (auto q = done_q.begin(); q != done_q.end(); ++q) if (*q == s) { done_q.erase(q); break; }
+        auto it = done_map.find(id);
+        if (it == done_map.end() || it->second.empty()) throw std::runtime_error("fetch: unknown or unfinished sequence id");
+        p = it->second.front();
+        it->second.pop_front();
+        if (it->second.empty()) done_map.erase(it);
+        for (auto q = done_q.begin(); q != done_q.end(); ++q) if (*q == p) { done_q.erase(q); break; }
     }
-    if (tokens) std::memcpy(tokens, s->tokens.data(), s->tokens.size() * sizeof(int32_t));
-    if (wav && s->n_samples > 0 && s->wav_host) std::memcpy(wav, s->wav_host, (size_t)s->n_samples * sizeof(float));
-    const bool dev_wav = wav && s->n_samples > 0 && !s->wav_host && s->wav_dev;
-    const bool dev_lat = latents && s->lat_dev;
+    Sequence& s = *p->s;
+    const int nt = p->tok1 - p->tok0;
+    if (tokens && nt > 0 && s.tok_host) std::memcpy(tokens, s.tok_host + p->tok0, (size_t)nt * sizeof(int32_t));
+    if (wav && p->nsamp > 0 && s.wav_host) std::memcpy(wav, s.wav_host + p->samp0, (size_t)p->nsamp * sizeof(float));
+    const bool dev_wav = wav && p->nsamp > 0 && !s.wav_host && s.wav_dev;
+    const bool dev_lat = latents && p->final && s.lat_dev && s.n_tokens > 0;
     if (dev_wav || dev_lat) {
-        std::lock_guard<std::mutex> lk(mu);          // device copies go through the engine stream
+        // device copies on a stream of their own: no need to wait behind the scheduler's iteration
         CUDA_CHECK(cudaSetDevice(cfg.device));
-        if (dev_wav) CUDA_CHECK(cudaMemcpyAsync(wav, s->wav_dev, (size_t)s->n_samples * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (dev_lat) CUDA_CHECK(cudaMemcpyAsync(latents, s->lat_dev, s->tokens.size() * (size_t)H * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaStream_t sc = nullptr;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
+        cudaError_t e = cudaSuccess;
+        if (dev_wav) e = cudaMemcpyAsync(wav, s.wav_dev + p->samp0, (size_t)p->nsamp * sizeof(float), cudaMemcpyDeviceToHost, sc);
+        if (e == cudaSuccess && dev_lat) e = cudaMemcpyAsync(latents, s.lat_dev, (size_t)s.n_tokens * H * sizeof(float), cudaMemcpyDeviceToHost, sc);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(sc);
+        cudaStreamDestroy(sc);
+        CUDA_CHECK(e);
     }
-    if (s->wav_host) { pinned_put(s->wav_host, s->wav_cap); s->wav_host = nullptr; }
-    if (s->wav_dev) { dev_put(s->wav_dev, s->wav_dev_cap); s->wav_dev = nullptr; }
-    if (s->lat_dev) { dev_put(s->lat_dev, s->lat_dev_cap); s->lat_dev = nullptr; }
+    if (p->final) recycle_seq_buffers(s);
 }
 
 void Engine::set_option(const std::string& k, int64_t v) {
@@ -1496,6 +1787,9 @@ void Engine::set_option(const std::string& k, int64_t v) {
         else g_attn_ctas_per_sm = (int)v;                        // < 0: absolute grid size (tests)
         drop_graphs();
     }
+    else if (k == "voc_segment") voc_segment = (int)std::max<int64_t>(0, v);
+    else if (k == "voc_sms") voc_sms = (int)std::max<int64_t>(0, v);
+    else if (k == "voc_batch") voc_max_items = (int)std::max<int64_t>(1, std::min<int64_t>(v, kVocMaxItems));
     else if (k == "cuda_graphs") use_graphs = v != 0;
     else if (k == "pdl") { use_pdl = v != 0; drop_graphs(); }
     else if (k == "splitk") { use_splitk = v != 0; drop_graphs(); }
@@ -1504,7 +1798,10 @@ void Engine::set_option(const std::string& k, int64_t v) {
         if (k == "microbatches") n_micro = std::max<int>(1, std::min<int64_t>(v, kMaxMicro)); else micro_min_rows = (int)std::max<int64_t>(2, v);
         drop_graphs();
     }
-    else if (k == "profile") { CUDA_CHECK(cudaSetDevice(cfg.device)); CUDA_CHECK(cudaStreamSynchronize(st)); g_prof.reset(); g_prof.enabled = v != 0; }
+    else if (k == "profile") {
+        CUDA_CHECK(cudaSetDevice(cfg.device)); CUDA_CHECK(cudaStreamSynchronize(st)); CUDA_CHECK(cudaStreamSynchronize(st_voc));
+        g_prof.reset(); g_prof.enabled = v != 0;
+    }
     else if (k == "reset_stats") {
         st_decode_steps = st_prefill_rows = st_tokens = st_samples = 0; st_gpt_ms = st_voc_ms = st_cond_ms = 0;
         launch_base = g_launch_count;
@@ -1522,6 +1819,7 @@ void Engine::kernel_profile(xtts_kernel_profile* out) {
     std::lock_guard<std::mutex> lk(mu);
     CUDA_CHECK(cudaSetDevice(cfg.device));
     CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(cudaStreamSynchronize(st_voc));
     g_prof.collect();
     std::memset(out, 0, sizeof(*out));
     out->n = KF_COUNT;
@@ -1532,8 +1830,8 @@ void Engine::kernel_profile(xtts_kernel_profile* out) {
     }
 }
 
-// Stopwatch on the engine stream.  Every other stream the engine uses (decode branches) forks from and joins back into
-// `st` inside a step, so an event recorded on `st` behind a step completes after all of that step's device work.
+// Stopwatch on the engine stream.  The decode branches fork from and join back into `st` inside a step; the vocoder stream
+// is joined into `st` explicitly before the stop event, so that event completes after all device work submitted so far.
 void Engine::device_timer(int op, double* ms) {
     std::lock_guard<std::mutex> lk(mu);
     CUDA_CHECK(cudaSetDevice(cfg.device));
@@ -1543,6 +1841,8 @@ void Engine::device_timer(int op, double* ms) {
         timer_armed = true;
     } else if (op == 1) {
         if (!timer_armed) throw std::runtime_error("device_timer: stop without start");
+        CUDA_CHECK(cudaEventRecord(ev_vjoin, st_voc));             // the vocoder runs on its own stream: join it
+        CUDA_CHECK(cudaStreamWaitEvent(st, ev_vjoin, 0));
         CUDA_CHECK(cudaEventRecord(ev_t1, st));
         CUDA_CHECK(cudaEventSynchronize(ev_t1));
         float t = 0.f;
@@ -1564,24 +1864,42 @@ void Engine::vocode_sync(const float* latents, int T, int speaker, float* wav, i
     std::lock_guard<std::mutex> lk(mu);
     require_finalized();
     CUDA_CHECK(cudaSetDevice(cfg.device));
+    if (T <= 0 || T > voc_max_T) throw std::runtime_error("vocoder: latent count out of range");
     DBuf<float> lat; lat.alloc((size_t)T * cfg.voc_in_dim);
-    lat.upload(latents, (size_t)T * cfg.voc_in_dim, st);
-    int ns = 0;
-    run_vocoder(lat.p, T, &speaker, 1, vwav.p, &ns, stage, stage_out, stage_cap);
-    if (wav) vwav.download(wav, ns, st);
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    lat.upload(latents, (size_t)T * cfg.voc_in_dim, st_voc);
+    const int Tz = z_frames(T), ns = Tz * voc_hop;
+    VocItem it{lat.p, T, 0, Tz, speaker};
+    run_vocoder(&it, 1, vwav.p, stage, stage_out, stage_cap);
+    if (wav) vwav.download(wav, ns, st_voc);
+    CUDA_CHECK(cudaStreamSynchronize(st_voc));
     if (n_out) *n_out = ns;
+}
+
+// z-frames [z0, z0 + nz) of the chunk `latents` [T] as a window of its own (what the scheduler does while a chunk decodes):
+// wav [nz * hop].  Samples further than the vocoder's receptive field from an inner window edge equal the whole chunk's.
+void Engine::vocode_window_sync(const float* latents, int T, int speaker, int z0, int nz, float* wav) {
+    std::lock_guard<std::mutex> lk(mu);
+    require_finalized();
+    CUDA_CHECK(cudaSetDevice(cfg.device));
+    if (T <= 0 || T > voc_max_T) throw std::runtime_error("vocoder: latent count out of range");
+    if (z0 < 0 || nz <= 0 || z0 + nz > z_frames(T)) throw std::runtime_error("vocoder: window outside the chunk");
+    DBuf<float> lat; lat.alloc((size_t)T * cfg.voc_in_dim);
+    lat.upload(latents, (size_t)T * cfg.voc_in_dim, st_voc);
+    VocItem it{lat.p, T, z0, nz, speaker};
+    run_vocoder(&it, 1, vwav.p, nullptr, nullptr, 0);
+    if (wav) vwav.download(wav, (size_t)nz * voc_hop, st_voc);
+    CUDA_CHECK(cudaStreamSynchronize(st_voc));
 }
 
 void Engine::gpt_prefill_sync(const int32_t* text, int n_text, int speaker, const int32_t* audio, int n_audio,
                               float* hidden_out, float* logits_out, float* latents_out) {
     std::lock_guard<std::mutex> lk(mu);
     require_finalized();
-    if (!running.empty() || !waiting.empty()) throw std::runtime_error("debug entry points need an idle engine");
+    if (!running.empty() || !waiting.empty() || !voc_pending.empty() || !voc_inflight.empty()) throw std::runtime_error("debug entry points need an idle engine");
     CUDA_CHECK(cudaSetDevice(cfg.device));
     Sequence s; s.text_ids.assign(text, text + n_text); s.speaker = speaker; s.slot = B;
     s.sp.max_tokens = CAP; s.sp.stop_token = cfg.stop_audio_token; s.sp.repetition_penalty = 1.f; s.sp.temperature = 0.f;
-    init_slot(s, nullptr, 0);
+    { std::vector<Sequence*> one{&s}; init_slots(one, nullptr, 0); }
     const int n = std::max(1, n_audio);
     std::vector<std::vector<int32_t>> aud(1);
     if (n_audio > 1) aud[0].assign(audio, audio + n_audio - 1);       // rows fed by t_1..t_{n-1}
@@ -1613,15 +1931,15 @@ void Engine::gpt_teacher_forced_sync(const int32_t* text, int n_text, int speake
                                      const xtts_sampling& sp, float* logits_out, float* latents_out, int32_t* sampled_out) {
     std::lock_guard<std::mutex> lk(mu);
     require_finalized();
-    if (!running.empty() || !waiting.empty()) throw std::runtime_error("debug entry points need an idle engine");
+    if (!running.empty() || !waiting.empty() || !voc_pending.empty() || !voc_inflight.empty()) throw std::runtime_error("debug entry points need an idle engine");
     if (n < 1 || n > CAP) throw std::runtime_error("teacher_forced: n out of range");
     CUDA_CHECK(cudaSetDevice(cfg.device));
     Sequence s; s.text_ids.assign(text, text + n_text); s.speaker = speaker; s.slot = B; s.sp = sp;
     s.sp.max_tokens = n;
     use_forced = forced != nullptr;
     try {
-        init_slot(s, forced, n);
         std::vector<Sequence*> seqs{&s};
+        init_slots(seqs, forced, n);
         prefill(seqs);                                   // samples token 1 (forced -> t_1)
         if (logits_out)
             CUDA_CHECK(cudaMemcpyAsync(logits_out, wLOG.p, (size_t)V * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -1683,7 +2001,7 @@ void Engine::debug_gemm(int mode, const float* A, const float* W, const float* b
 void Engine::debug_sample(const float* logits, const uint8_t* seen, int Bn, int Vn, const xtts_sampling& sp, int step,
                           int32_t* out) {
     std::lock_guard<std::mutex> lk(mu);
-    if (!running.empty() || !waiting.empty()) throw std::runtime_error("debug entry points need an idle engine");
+    if (!running.empty() || !waiting.empty() || !voc_pending.empty() || !voc_inflight.empty()) throw std::runtime_error("debug entry points need an idle engine");
     if (Bn < 1 || Bn > B || Vn != V) throw std::runtime_error("debug_sample: bad batch or vocabulary size");
     CUDA_CHECK(cudaSetDevice(cfg.device));
     std::vector<float> lg((size_t)Bn * Vpad, 0.f);
@@ -1756,6 +2074,7 @@ int xtts_submit(xtts_engine* e, uint64_t seq_id, const int32_t* text_ids, int32_
                 const xtts_sampling* sp) {
     XTTS_TRY(e->impl->submit(seq_id, text_ids, n_text, speaker_slot, *sp))
 }
+int xtts_cancel(xtts_engine* e, uint64_t seq_id) { XTTS_TRY(e->impl->cancel(seq_id)) }
 int xtts_poll(xtts_engine* e, xtts_result* out, int32_t timeout_ms) {
     try { return e->impl->poll(out, timeout_ms); }
     catch (const std::exception& ex) { xtts::set_error(ex.what()); return XTTS_ERR_INVALID; }
@@ -1771,6 +2090,9 @@ int xtts_device_timer(xtts_engine* e, int32_t op, double* ms) { XTTS_TRY(e->impl
 int xtts_vocode(xtts_engine* e, const float* latents, int32_t T, int32_t speaker_slot, float* wav, int32_t* n_out,
                 const char* stage, float* stage_out, int64_t stage_cap) {
     XTTS_TRY(e->impl->vocode_sync(latents, T, speaker_slot, wav, n_out, stage, stage_out, stage_cap))
+}
+int xtts_vocode_window(xtts_engine* e, const float* latents, int32_t T, int32_t speaker_slot, int32_t z0, int32_t nz, float* wav) {
+    XTTS_TRY(e->impl->vocode_window_sync(latents, T, speaker_slot, z0, nz, wav))
 }
 int xtts_gpt_prefill(xtts_engine* e, const int32_t* text_ids, int32_t n_text, int32_t speaker_slot,
                      const int32_t* audio_tokens, int32_t n_audio, float* hidden_out, float* logits_out, float* latents_out) {

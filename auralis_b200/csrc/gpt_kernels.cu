@@ -56,6 +56,37 @@ __global__ void build_decode_rows_kernel(const int* __restrict__ active, const i
 }
 
 // ------------------------------------------------------------------------------------------------
+// slot initialisation of an admission wave: one CTA per admitted sequence
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+init_slots_kernel(const SlotInit* __restrict__ init, const int* __restrict__ pages, SlotArrays a) {
+    const SlotInit d = init[blockIdx.x];
+    const int slot = d.slot;
+    if (threadIdx.x == 0) {
+        a.last_tok[slot] = d.start_token; a.n_gen[slot] = 0; a.ctx_len[slot] = d.ctx_len; a.finished[slot] = 0;
+        a.temperature[slot] = d.temperature; a.top_p[slot] = d.top_p; a.top_k[slot] = d.top_k; a.penalty[slot] = d.penalty;
+        a.max_tokens[slot] = d.max_tokens; a.stop_token[slot] = d.stop_token; a.seed[slot] = d.seed; a.seq_seed[slot] = d.seq_seed;
+    }
+    // penalty set seed: the prompt ids are [1]*(32+Lt)+[start]  (vllm_mm_gpt.py:325, App. B.7)
+    for (int w = threadIdx.x; w < a.seen_words; w += blockDim.x) {
+        unsigned v = 0u;
+        if (w == 0) v |= 1u << 1;
+        if (w == (d.start_token >> 5)) v |= 1u << (d.start_token & 31);
+        a.seen[(size_t)slot * a.seen_words + w] = v;
+    }
+    const int* pg = pages + (size_t)blockIdx.x * a.max_pages;
+    for (int i = threadIdx.x; i < a.max_pages; i += blockDim.x)
+        a.block_tables[(size_t)slot * a.max_pages + i] = i < d.n_pages ? pg[i] : 0;
+}
+
+struct GatherIdx { int idx[kVocMaxItems]; };
+__global__ void gather_rows_kernel(const float* __restrict__ src, const GatherIdx G, int width, float* __restrict__ dst) {
+    const float* s = src + (size_t)G.idx[blockIdx.x] * width;
+    float* d = dst + (size_t)blockIdx.x * width;
+    for (int i = threadIdx.x; i < width; i += blockDim.x) d[i] = s[i];
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm (fp32 statistics, two-pass), one CTA per row
 // ------------------------------------------------------------------------------------------------
 template <typename TOut>
@@ -744,6 +775,23 @@ sample_kernel(const float* __restrict__ logits, int ld, const int* __restrict__ 
 // ================================================================================================
 // launchers
 // ================================================================================================
+void launch_init_slots(const SlotInit* init, const int* pages, int n, SlotArrays a, cudaStream_t st) {
+    if (n <= 0) return;
+    ProfScope ps(KF_MISC, st, 0, (double)n * (sizeof(SlotInit) + 8.0 * a.max_pages + 4.0 * a.seen_words));
+    init_slots_kernel<<<n, 128, 0, st>>>(init, pages, a);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+
+void launch_gather_rows(const float* src, const int* idx_host, int n, int width, float* dst, cudaStream_t st) {
+    if (n <= 0) return;
+    if (n > kVocMaxItems) throw CudaError("gather_rows: too many rows");
+    GatherIdx G{};
+    for (int i = 0; i < n; ++i) G.idx[i] = idx_host[i];
+    ProfScope ps(KF_MISC, st, 0, 8.0 * n * width);
+    gather_rows_kernel<<<n, 128, 0, st>>>(src, G, width, dst);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+
 void launch_build_rows(const RowDesc* rows, int n_rows, GptTables t, float* X, cudaStream_t st) {
     if (n_rows <= 0) return;
     ProfScope ps(KF_EMBED, st, 0, 12.0 * n_rows * t.H);

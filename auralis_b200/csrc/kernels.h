@@ -129,10 +129,16 @@ void launch_sample(const float* logits, int ld_logits, const int* active, int M,
 // ------------------------------------------------------------------------------------------
 // Vocoder kernels (fp32, channel-major activations [C][L])
 // ------------------------------------------------------------------------------------------
-// every vocoder launcher takes `batch` equal-length items laid out back to back ([batch][C][L])
-// z32 (fp32 [C][Tz]) and/or z16 (fp16 atoms, lpad rows per plane) — either may be null
-void launch_interp(const float* latents, float* z32, __half* z16, int lpad, int T, int C, int T1, int Tz, double scale1,
-                   double scale2, int batch, cudaStream_t st);
+// every vocoder launcher takes `batch` items laid out back to back ([batch][C][L]); the tensor-core path also takes
+// ragged batches: `item_len[i] <= L` valid time steps per item (host array; nullptr = all L), buffers strided by L
+constexpr int kVocMaxItems = 32;
+// One item of an interpolation launch: z-frames [z0, z0 + nz) of a chunk whose latents start at `lat` ([T][C] fp32, device).
+// T / T1 are the clamp lengths of the two linear interpolations (HifiDecoder.forward): the chunk's real length once it is
+// known, otherwise any length the window does not reach (a window of a still-growing chunk never touches the clamp).
+struct InterpItem { const float* lat; int T, T1, z0, nz; };
+// z32 (fp32 [batch][C][Lz]) and/or z16 (fp16 atoms [batch][C/8][lpad][8]) — either may be null; Lz = row stride >= max nz
+void launch_interp(const InterpItem* items, int batch, float* z32, __half* z16, int lpad, int C, int Lz, double scale1,
+                   double scale2, cudaStream_t st);
 
 enum : int { CONV_STORE = 0, CONV_ACCUM = 1 };
 // out[co][t] (=|+=) bias[co] + cbias[co] + resid[co][t] + sum_{ci,j} w[ci][j][co] * act(in_scale*x[ci][t+(j-(K-1)/2)*dil])
@@ -152,23 +158,49 @@ void conv1d_tc_pack(const float* w /*[Cout][Cin][K]*/, int Cin, int Cout, int K,
 extern int g_attn_ctas_per_sm;  // 0 = uncapped decode-attention grid; > 0: at most this many CTAs per SM, each walking several (row, head) items
 extern int g_gemm_decode_bn;    // 0 = heuristic; 32/64/128 forces the tile width of decode-shaped (M <= 256) tcgen05 GEMMs
 extern int g_conv_epi_groups;   // 1 or 2 epilogue warpgroups in conv1d_tc_kernel (default 2)
+extern int g_voc_sm_cap;        // > 0: persistent tensor-core conv grids take at most this many SMs (set per vocoder batch)
 void launch_conv1d_tc(const __half* a16, const __half* wblob, const ConvTcPlan& pl, const float* bias, const float* cbias,
                       const float* resid, float* out32, __half* out16, int Cin, int Cout, int L, int lpad, int K, int dil,
-                      float slope_out, float scale16, int mode, int batch, int cbias_batch_stride, cudaStream_t st);
+                      float slope_out, float scale16, int mode, int batch, int cbias_batch_stride, cudaStream_t st,
+                      const int* item_len = nullptr);
 // ConvTranspose1d(kernel 2u, stride u, padding u/2) on the same kernel (u phases x 2 taps); plan = conv1d_tc_plan(Cin, u*Cr, 2)
 void convT_tc_pack(const float* w /*[Cin][Cr][2u]*/, int Cin, int Cr, int u, const ConvTcPlan& pl, __half* blob);
 void launch_convT_tc(const __half* a16, const __half* wblob, const ConvTcPlan& pl, const float* bias, const float* cbias,
                      float* out32, __half* out16, int Cin, int Cr, int Lin, int lpad_in, int lpad_out, int u, float slope_out,
-                     int batch, int cbias_batch_stride, cudaStream_t st);
-void launch_atoms_zero_pads(__half* buf, int planes_total, int lpad, int L, cudaStream_t st);
+                     int batch, int cbias_batch_stride, cudaStream_t st, const int* item_len = nullptr);
+// planes_total = batch * planes per item; item_len (host, optional): per-item signal length
+void launch_atoms_zero_pads(__half* buf, int planes_total, int lpad, int L, cudaStream_t st, int batch = 1,
+                            const int* item_len = nullptr);
 // transposed conv, stride u, kernel K = 2u, padding (K-u)/2;  w pre-transposed to [Cin][K][Cout]
 // out16 (optional): lrelu(out, slope16) as fp16 atoms with lpad16 rows per plane
 void launch_conv_transpose1d(const float* x, const float* w_t, const float* bias, const float* cbias, float* out,
                              __half* out16, int lpad16, float slope16, int Cin, int Cout, int Lin, int K, int u,
                              float in_scale, float slope, int batch, int cbias_batch_stride, cudaStream_t st);
-// wav[t] = tanh(sum w[ci][j] * lrelu(in_scale*x[ci][t+j-3], slope))
+// wav[t] = tanh(sum w[ci][j] * lrelu(in_scale*x[ci][t+j-3], slope));  x [batch][Cin][L], wav [batch][wav_stride (0 = L)];
+// item_len as above
 void launch_conv_post(const float* x, const float* w, float* wav, int Cin, int L, int K, float in_scale, float slope,
-                      int batch, cudaStream_t st);
+                      int batch, cudaStream_t st, const int* item_len = nullptr, int wav_stride = 0);
+
+// ------------------------------------------------------------------------------------------
+// slot bookkeeping
+// ------------------------------------------------------------------------------------------
+// Everything a freshly admitted sequence needs in its slot, written by ONE kernel from one staged upload (instead of a
+// dozen small copies per sequence).
+struct SlotInit {
+    int slot, ctx_len, top_k, max_tokens, stop_token, seq_seed, start_token, n_pages;
+    float temperature, top_p, penalty;
+    unsigned long long seed;
+};
+struct SlotArrays {       // per-slot device arrays (mutable view of SampleState + block tables)
+    int* last_tok; int* n_gen; int* ctx_len; int* finished; unsigned* seen;
+    float* temperature; float* top_p; int* top_k; float* penalty; int* max_tokens; int* stop_token;
+    unsigned long long* seed; int* seq_seed; int* block_tables;
+    int seen_words, max_pages;
+};
+// pages: [n][max_pages] page ids of each sequence (first n_pages valid)
+void launch_init_slots(const SlotInit* init, const int* pages, int n, SlotArrays a, cudaStream_t st);
+// dst[i][0..width) = src[idx[i]][0..width)   (i < n <= kVocMaxItems): speaker-bias rows of a vocoder batch
+void launch_gather_rows(const float* src, const int* idx_host, int n, int width, float* dst, cudaStream_t st);
 // y[c] = W[c,:] . g + b[c]   (speaker conditioning 1x1 convs)
 void launch_gemv(const float* W, const float* b, const float* g, float* y, int rows, int cols, cudaStream_t st);
 

@@ -11,6 +11,8 @@
 // Dense conv C->C with kernel k is a GEMM with K-dim = C*k; here it is register-tiled on the FP32 pipe:
 // a CTA computes 64 (or 32) output channels x 128 time steps, staging 8 input channels (+halo) and
 // the matching [8][k][64] weight slab in shared memory per iteration.
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace xtts {
@@ -31,19 +33,26 @@ __device__ __forceinline__ void lin_src(int dst, float rscale, int in_len, int& 
     l0 = 1.0f - l1;
 }
 
+struct PostLens { int len[kVocMaxItems]; };
+struct InterpBatch { InterpItem it[kVocMaxItems]; };
+
+// Block (x: 32 z-frames, y: 32 channels, z: batch item).  Output column j of item i is the chunk's z-frame it.z0 + j:
+// a window of a chunk gets the very values the whole chunk would (the source positions depend on the global index only).
 __global__ void __launch_bounds__(256)
-interp_kernel(const float* __restrict__ lat_, float* __restrict__ z_, uint4* __restrict__ z16_, int lpad, int T, int C,
-              int T1, int Tz, float r1, float r2) {
+interp_kernel(const InterpBatch B, float* __restrict__ z_, uint4* __restrict__ z16_, int lpad, int C, int Lz, float r1, float r2) {
     __shared__ float tile[32][33];
-    const float* lat = lat_ + (size_t)blockIdx.z * T * C;
+    const InterpItem it = B.it[blockIdx.z];
+    const float* __restrict__ lat = it.lat;
+    const int T = it.T, T1 = it.T1, nz = it.nz;
     const int c0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    if (j0 >= nz) return;
     const int tx = threadIdx.x, ty = threadIdx.y;       // (32, 8)
     for (int k = 0; k < 4; ++k) {
         const int j = j0 + ty + 8 * k, c = c0 + tx;
         float v = 0.f;
-        if (j < Tz && c < C) {
+        if (j < nz && c < C) {
             int a0, a1; float m0, m1;
-            lin_src(j, r2, T1, a0, a1, m0, m1);
+            lin_src(it.z0 + j, r2, T1, a0, a1, m0, m1);
             int b0, b1; float n0, n1;
             lin_src(a0, r1, T, b0, b1, n0, n1);
             const float za = n0 * lat[(size_t)b0 * C + c] + n1 * lat[(size_t)b1 * C + c];
@@ -55,15 +64,15 @@ interp_kernel(const float* __restrict__ lat_, float* __restrict__ z_, uint4* __r
     }
     __syncthreads();
     if (z_) {
-        float* z = z_ + (size_t)blockIdx.z * C * Tz;
+        float* z = z_ + (size_t)blockIdx.z * C * Lz;
         for (int k = 0; k < 4; ++k) {
             const int c = c0 + ty + 8 * k, j = j0 + tx;
-            if (c < C && j < Tz) z[(size_t)c * Tz + j] = tile[tx][ty + 8 * k];
+            if (c < C && j < nz) z[(size_t)c * Lz + j] = tile[tx][ty + 8 * k];
         }
     }
     if (z16_ && ty < 4) {                               // 32 time steps x 4 atoms of 8 channels
         const int j = j0 + tx, cg = c0 / 8 + ty;
-        if (j < Tz && c0 + ty * 8 < C) {
+        if (j < nz && c0 + ty * 8 < C) {
             const float* r = &tile[tx][ty * 8];
             __half2 h0 = __floats2half2_rn(r[0], r[1]), h1 = __floats2half2_rn(r[2], r[3]);
             __half2 h2 = __floats2half2_rn(r[4], r[5]), h3 = __floats2half2_rn(r[6], r[7]);
@@ -260,11 +269,13 @@ conv_transpose1d_kernel(const float* __restrict__ x_, const float* __restrict__ 
 // conv_post (C->1, k7, no bias) + tanh; HBM-bound (reads C*L floats, writes L)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-conv_post_kernel(const float* __restrict__ x_, const float* __restrict__ w, float* __restrict__ wav_, int Cin, int L,
-                 int K, float in_scale, float slope) {
+conv_post_kernel(const float* __restrict__ x_, const float* __restrict__ w, float* __restrict__ wav_, int Cin, int Ls,
+                 int wav_stride, int K, float in_scale, float slope, const PostLens PL) {
     extern __shared__ float wsm[];                 // [Cin*K]
-    const float* x = x_ + (size_t)blockIdx.y * Cin * L;
-    float* wav = wav_ + (size_t)blockIdx.y * L;
+    const int L = PL.len[blockIdx.y];              // this item's signal length; rows are strided by Ls
+    if ((int)(blockIdx.x * blockDim.x) >= L) return;
+    const float* x = x_ + (size_t)blockIdx.y * Cin * Ls;
+    float* wav = wav_ + (size_t)blockIdx.y * wav_stride;
     for (int e = threadIdx.x; e < Cin * K; e += blockDim.x) wsm[e] = w[e];
     __syncthreads();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -272,7 +283,7 @@ conv_post_kernel(const float* __restrict__ x_, const float* __restrict__ w, floa
     const int half = (K - 1) / 2;
     float acc = 0.f;
     for (int ci = 0; ci < Cin; ++ci) {
-        const float* xr = x + (size_t)ci * L;
+        const float* xr = x + (size_t)ci * Ls;
         for (int j = 0; j < K; ++j) {
             const int s = t + j - half;
             if (s >= 0 && s < L) acc = fmaf(wsm[ci * K + j], lrelu(in_scale * xr[s], slope), acc);
@@ -309,12 +320,21 @@ void conv1d_dispatch(const float* x, const float* w_t, const float* bias, const 
 
 }  // namespace
 
-void launch_interp(const float* latents, float* z32, __half* z16, int lpad, int T, int C, int T1, int Tz, double scale1,
-                   double scale2, int batch, cudaStream_t st) {
+void launch_interp(const InterpItem* items, int batch, float* z32, __half* z16, int lpad, int C, int Lz, double scale1,
+                   double scale2, cudaStream_t st) {
+    if (batch < 1 || batch > kVocMaxItems) throw CudaError("interp: batch out of range");
     const float r1 = (float)(1.0 / scale1), r2 = (float)(1.0 / scale2);
-    ProfScope ps(KF_INTERP, st, 0, C * (4.0 * T + (z32 ? 4.0 : 0.0) * Tz + (z16 ? 2.0 : 0.0) * Tz) * batch);
-    interp_kernel<<<dim3(ceil_div(Tz, 32), ceil_div(C, 32), batch), dim3(32, 8), 0, st>>>(
-        latents, z32, reinterpret_cast<uint4*>(z16), lpad, T, C, T1, Tz, r1, r2);
+    InterpBatch B{};
+    int nz_max = 0; double nz_sum = 0;
+    for (int i = 0; i < batch; ++i) {
+        B.it[i] = items[i];
+        if (items[i].nz > Lz) throw CudaError("interp: window longer than the row stride");
+        nz_max = std::max(nz_max, items[i].nz); nz_sum += items[i].nz;
+    }
+    if (nz_max <= 0) return;
+    ProfScope ps(KF_INTERP, st, 0, C * nz_sum * (4.0 / (scale1 * scale2) + (z32 ? 4.0 : 0.0) + (z16 ? 2.0 : 0.0)));
+    interp_kernel<<<dim3(ceil_div(nz_max, 32), ceil_div(C, 32), batch), dim3(32, 8), 0, st>>>(
+        B, z32, reinterpret_cast<uint4*>(z16), lpad, C, Lz, r1, r2);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 
@@ -345,9 +365,14 @@ void launch_conv_transpose1d(const float* x, const float* w_t, const float* bias
 }
 
 void launch_conv_post(const float* x, const float* w, float* wav, int Cin, int L, int K, float in_scale, float slope,
-                      int batch, cudaStream_t st) {
-    ProfScope ps(KF_CONV_POST, st, 2.0 * Cin * K * (double)L * batch, 4.0 * (double)L * (Cin + 1) * batch);
-    conv_post_kernel<<<dim3(ceil_div(L, 256), batch), 256, Cin * K * sizeof(float), st>>>(x, w, wav, Cin, L, K, in_scale, slope);
+                      int batch, cudaStream_t st, const int* item_len, int wav_stride) {
+    if (batch < 1 || batch > kVocMaxItems) throw CudaError("conv_post: batch out of range");
+    if (wav_stride <= 0) wav_stride = L;
+    PostLens PL{};
+    double Lsum = 0;
+    for (int i = 0; i < batch; ++i) { PL.len[i] = item_len ? item_len[i] : L; Lsum += PL.len[i]; }
+    ProfScope ps(KF_CONV_POST, st, 2.0 * Cin * K * Lsum, 4.0 * Lsum * (Cin + 1));
+    conv_post_kernel<<<dim3(ceil_div(L, 256), batch), 256, Cin * K * sizeof(float), st>>>(x, w, wav, Cin, L, wav_stride, K, in_scale, slope, PL);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 

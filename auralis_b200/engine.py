@@ -80,6 +80,7 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
         prec = {"fp32": native.PRECISION_FP32, "bf16": native.PRECISION_BF16}[precision]
         self.dims = dims
         self.precision = precision
+        self.device_index = int(device)
         self.max_concurrency = max_concurrency
         self.native = native.NativeEngine(dims, device=device, precision=prec, max_batch=max_concurrency,
                                           max_speakers=max_speakers)
@@ -119,6 +120,33 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
     @property
     def conditioning_config(self) -> ConditioningConfig:
         return ConditioningConfig(speaker_embeddings=True, gpt_like_decoder_conditioning=True)
+
+    @property
+    def device(self):
+        import torch
+        return torch.device("cuda", int(getattr(self, "device_index", 0)))
+
+    @property
+    def dtype(self):
+        import torch
+        return torch.bfloat16 if self.precision == "bf16" else torch.float32
+
+    def get_memory_usage_curve(self):
+        """XTTSv2.py:152-171 fits a polynomial to measured vLLM footprints; here the footprint is known exactly from the
+        geometry: weights + per-slot state (paged KV for a full-length sequence, latent ring, token rows) x max_concurrency
+        + the vocoder workspace.  Sets (and returns) `max_gb_for_vllm_model`, the attribute the reference's engine exposes."""
+        g, v = self.dims.gpt, self.dims.voc
+        kv_elem = 2 if self.precision == "bf16" else 4
+        w_elem = 2 if self.precision == "bf16" else 4
+        gpt_w = g.layers * (4 * g.hidden * g.hidden + 2 * g.hidden * g.ff) * w_elem
+        pages = -(-(g.max_prompt_rows + g.max_audio_tokens) // 32)
+        per_slot = pages * 32 * 2 * g.layers * g.hidden * kv_elem + g.max_audio_tokens * g.hidden * 4 + 3 * g.max_audio_tokens * 4
+        tz = v.z_frames(g.max_audio_tokens)
+        widest = max((v.init_ch >> (i + 1)) * int(np.prod(v.up_rates[: i + 1])) for i in range(len(v.up_rates)))
+        voc_ws = 8 * tz * (5 * widest * 4 + (5 * widest * 2 if self.precision == "bf16" else 0) + v.hop * 4)
+        total = gpt_w + per_slot * (self.max_concurrency + 1) + voc_ws
+        self.max_gb_for_vllm_model = total / 2 ** 30
+        return self.max_gb_for_vllm_model
 
     async def _acquire_speaker(self, key: str, timeout_s: float = 120.0):
         """SpeakerSlots.acquire, waiting (not failing) while every slot is pinned by chunks in flight."""
@@ -234,7 +262,7 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
                 request.speaker_files, request.max_ref_length, request.gpt_cond_len, request.gpt_cond_chunk_len)
         token_lists = self.prepare_text_tokens(request.text, request.language)
         generators, request_ids = [], []
-        base_seed = request.seed if request.seed is not None else int.from_bytes(hashlib.sha256(request.request_id.encode()).digest()[:6], "little")
+        base_seed = request.seed if getattr(request, "seed", None) is not None else int.from_bytes(hashlib.sha256(request.request_id.encode()).digest()[:6], "little")
         for seq_index, ids in enumerate(token_lists):
             sp = native.Sampling(temperature=request.temperature, top_p=request.top_p, top_k=request.top_k,
                                  repetition_penalty=request.repetition_penalty,
@@ -266,18 +294,31 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
             self._spk.unpin(slot)
             raise
         n_before = 0
-        while True:
-            payload, err = await box.get()
-            if err is not None:
-                raise err
-            result, toks, wav = payload
-            if result.status > 0:                       # first-audio piece: leading tokens only
-                n_before = len(toks)
-                yield ChunkOutput(rid, toks, wav, result, partial=True)
-                continue
-            # the final result lists every token; report only the ones whose audio this piece carries
-            yield ChunkOutput(rid, toks[n_before:], wav, result)
-            return
+        done = False
+        try:
+            while True:
+                payload, err = await box.get()
+                if err is not None:
+                    done = True
+                    raise err
+                result, toks, wav = payload
+                if result.status > 0:                   # partial piece: the tokens whose audio it carries
+                    n_before += len(toks)
+                    yield ChunkOutput(rid, toks, wav, result, partial=True)
+                    continue
+                # the final result lists every token; report only the ones whose audio this piece carries
+                done = True
+                yield ChunkOutput(rid, toks[n_before:], wav, result)
+                return
+        finally:
+            if not done:
+                # the consumer went away (cancelled coroutine, closed stream, failed sibling chunk): abort the native chunk so
+                # it gives its batch slot and KV pages back — the reference aborts the vLLM request the same way.  The
+                # poller still receives the (cancelled) final result and unpins the speaker slot.
+                try:
+                    self.native.cancel(sid)
+                except Exception:      # noqa: BLE001 — engine already shut down
+                    pass
 
     async def process_tokens_to_speech(self, generator, speaker_embeddings=None, multimodal_data=None,
                                        request: TTSRequest = None) -> AsyncGenerator[TTSOutput, None]:
@@ -331,8 +372,13 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
                 w = self._waiters.pop(r.seq_id, None) if final else self._waiters.get(r.seq_id)
             try:
                 if r.status < 0:
-                    raise native.NativeError(f"chunk {r.seq_id} failed ({r.status}): "
-                                             f"{self.native.lib.xtts_last_error().decode()}")
+                    msg = self.native.lib.xtts_last_error().decode()
+                    try:
+                        self.native.lib.xtts_fetch(self.native.h, r.seq_id, None, None, None)   # release its native buffers
+                    except Exception:      # noqa: BLE001
+                        pass
+                    raise native.NativeError(f"chunk {r.seq_id} " + ("was cancelled" if r.status == native.ERR_CANCELLED
+                                                                    else f"failed ({r.status}): {msg}"))
                 toks, wav, _ = self.native.fetch(r, want_wav=True)
                 payload, err = (r, toks, wav), None
             except Exception as e:      # noqa: BLE001 — forwarded to the awaiting coroutine

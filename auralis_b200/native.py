@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libxtts_b200.so")
 
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
+ERR_CANCELLED = -5
 
 
 class NativeError(RuntimeError):
@@ -72,8 +73,8 @@ class XttsKernelProfile(C.Structure):
 # every symbol include/xtts_b200.h declares (checked by tests/test_abi.py against the header text)
 ABI_SYMBOLS = [
     "xtts_last_error", "xtts_version", "xtts_create", "xtts_destroy", "xtts_load_weight", "xtts_finalize_weights",
-    "xtts_set_speaker", "xtts_get_speaker", "xtts_condition", "xtts_submit", "xtts_poll", "xtts_fetch",
-    "xtts_set_option", "xtts_get_stats", "xtts_sync", "xtts_get_kernel_profile", "xtts_device_timer", "xtts_vocode", "xtts_gpt_prefill", "xtts_gpt_teacher_forced",
+    "xtts_set_speaker", "xtts_get_speaker", "xtts_condition", "xtts_submit", "xtts_cancel", "xtts_poll", "xtts_fetch",
+    "xtts_set_option", "xtts_get_stats", "xtts_sync", "xtts_get_kernel_profile", "xtts_device_timer", "xtts_vocode", "xtts_vocode_window", "xtts_gpt_prefill", "xtts_gpt_teacher_forced",
     "xtts_debug_gemm", "xtts_debug_sample",
 ]
 
@@ -100,6 +101,7 @@ def load_library(path: Optional[str] = None):
     lib.xtts_get_speaker.argtypes = [vp, i32, f32p, f32p]
     lib.xtts_condition.argtypes = [vp, i32, f32p, i64, f32p, i64, i32, i32]
     lib.xtts_submit.argtypes = [vp, C.c_uint64, i32p, i32, i32, C.POINTER(XttsSampling)]
+    lib.xtts_cancel.argtypes = [vp, C.c_uint64]
     lib.xtts_poll.argtypes = [vp, C.POINTER(XttsResult), i32]
     lib.xtts_fetch.argtypes = [vp, C.c_uint64, i32p, f32p, f32p]
     lib.xtts_set_option.argtypes = [vp, C.c_char_p, i64]
@@ -108,6 +110,7 @@ def load_library(path: Optional[str] = None):
     lib.xtts_get_kernel_profile.argtypes = [vp, C.POINTER(XttsKernelProfile)]
     lib.xtts_device_timer.argtypes = [vp, i32, C.POINTER(C.c_double)]
     lib.xtts_vocode.argtypes = [vp, f32p, i32, i32, f32p, i32p, C.c_char_p, f32p, i64]
+    lib.xtts_vocode_window.argtypes = [vp, f32p, i32, i32, i32, i32, f32p]
     lib.xtts_gpt_prefill.argtypes = [vp, i32p, i32, i32, i32p, i32, f32p, f32p, f32p]
     lib.xtts_gpt_teacher_forced.argtypes = [vp, i32p, i32, i32, i32p, i32, C.POINTER(XttsSampling), f32p, f32p, i32p]
     lib.xtts_debug_gemm.argtypes = [vp, i32, f32p, f32p, f32p, f32p, f32p, i32, i32, i32, i32, i32, f32p]
@@ -176,7 +179,7 @@ class Sampling:
     seq_seed: int = 0
     vocode: bool = True
     priority: int = 0
-    early_tokens: int = 0          # > 0: deliver the audio of the first n tokens as a partial result (include/xtts_b200.h)
+    early_tokens: int = 0          # > 0: stream the chunk's audio as partial results, first piece after n tokens (include/xtts_b200.h)
 
     def c(self) -> XttsSampling:
         s = XttsSampling()
@@ -253,6 +256,9 @@ class NativeEngine:
         cs = sp.c()
         self._chk(self.lib.xtts_submit(self.h, seq_id, _ip(t), t.size, speaker_slot, C.byref(cs)), "submit")
 
+    def cancel(self, seq_id: int):
+        self._chk(self.lib.xtts_cancel(self.h, seq_id), "cancel")
+
     def poll(self, timeout_ms: int = 1000) -> Optional[XttsResult]:
         r = XttsResult()
         rc = self.lib.xtts_poll(self.h, C.byref(r), timeout_ms)
@@ -321,14 +327,15 @@ class NativeEngine:
                     raise NativeError("run_batch timed out")
                 continue
             if r.status < 0:
+                self.lib.xtts_fetch(self.h, r.seq_id, None, None, None)      # releases the failed chunk's native buffers
                 raise NativeError(f"sequence {r.seq_id} failed ({r.status}): {self.lib.xtts_last_error().decode()}")
-            if r.status > 0:                 # partial first-audio piece (Sampling.early_tokens): kept next to the final result
+            if r.status > 0:                 # partial piece (Sampling.early_tokens): kept, in order, next to the final result
                 ptoks, pwav, _ = self.fetch(r, want_wav, False)
-                partials[r.seq_id] = (r, ptoks, pwav)
+                partials.setdefault(r.seq_id, []).append((r, ptoks, pwav))
                 continue
             toks, wav, lat = self.fetch(r, want_wav, want_latents)
             out[r.seq_id] = (r, toks, wav, lat)
-        self.last_partials = partials        # {seq_id: (result, tokens, wav)} of the batch just run
+        self.last_partials = partials        # {seq_id: [(result, tokens, wav), ...]} of the batch just run, oldest first
         return out
 
 
@@ -344,6 +351,13 @@ class NativeEngine:
                                        stage.encode() if stage else None, _fp(st_arr), st_arr.size if stage else 0), "vocode")
         assert n_out.value == ns, (n_out.value, ns)
         return (wav, st_arr) if stage else wav
+
+    def vocode_window(self, latents, speaker_slot: int, z0: int, nz: int) -> np.ndarray:
+        """z-frames [z0, z0 + nz) of the chunk as a window of its own -> nz * hop samples (include/xtts_b200.h)."""
+        lat = _f32(latents)
+        wav = np.empty((nz * self.dims.voc.hop,), np.float32)
+        self._chk(self.lib.xtts_vocode_window(self.h, _fp(lat), lat.shape[0], speaker_slot, z0, nz, _fp(wav)), "vocode_window")
+        return wav
 
     def gpt_prefill(self, text_ids, speaker_slot: int, audio_tokens=(), want_hidden: bool = False):
         g = self.dims.gpt

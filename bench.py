@@ -319,11 +319,14 @@ def main():
     # The profile step also runs the decode rows as ONE branch: concurrent micro-batch branches overlap kernels of
     # different families, which would smear each family's own duration.
     ne.set_option("microbatches", 1)
+    ne.set_option("voc_segment", 0)          # the vocoder after the decode, not beside it: each family's own duration
     ne.set_option("profile", 1)
     device_step(args.warmup + args.steps)
     prof = ne.kernel_profile()
     ne.set_option("profile", 0)
     ne.set_option("microbatches", args.microbatches)
+    for kv in args.engine_opt:
+        ne.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     eng.park_poller(False)
     log("profile step done")
 

@@ -25,6 +25,7 @@ extern "C" {
 #define XTTS_ERR_CUDA -2
 #define XTTS_ERR_STATE -3
 #define XTTS_ERR_TIMEOUT -4
+#define XTTS_ERR_CANCELLED -5 /* the chunk was cancelled with xtts_cancel before it finished */
 
 #define XTTS_PRECISION_FP32 0 /* parity mode: fp32 CUDA-core GEMMs, fp32 KV cache            */
 #define XTTS_PRECISION_BF16 1 /* fast mode: bf16 tcgen05 GEMMs (fp32 accumulate), bf16 KV    */
@@ -65,19 +66,21 @@ typedef struct xtts_sampling {
     int32_t priority;          /* admission order: lower first (the engine passes the chunk index,
                                   so every request's first chunk is decoded before any second chunk) */
     int32_t early_tokens;      /* 0 (default): one result per chunk, as the reference (FINAL_ONLY, XTTSv2.py:738).
-                                  n > 0: "first audio early" — as soon as n + 6 tokens are decoded the engine vocodes that
-                                  prefix and delivers the samples of the first n tokens as a PARTIAL result (status 1);
-                                  the final result then carries all tokens and only the remaining samples.  The 6-token
-                                  lookahead covers the vocoder's receptive field (~3 latent frames), so partial + final
-                                  concatenate to exactly the waveform of the unsplit chunk.  SURVEY.md §8f-3.            */
+                                  n > 0: streaming — the chunk's audio is delivered while it is still decoding: the samples
+                                  of the first n tokens as soon as n + ~7 tokens exist, then (engine option "voc_segment" = m > 0)
+                                  of every further m tokens, each as a PARTIAL result (status 1); the final result carries all
+                                  tokens and the remaining samples.  Each piece is vocoded as a window with the vocoder's
+                                  receptive field as margin, so the pieces concatenate to exactly the waveform of the
+                                  unsplit chunk.  SURVEY.md §8f-3.                                                        */
 } xtts_sampling;
 
 typedef struct xtts_result {
     uint64_t seq_id;
-    int32_t status;            /* 0 ok (final result), <0 failed, 1 = partial first-audio piece (see early_tokens):
-                                  fetch it before polling further; xtts_fetch(seq_id) hands out the partial piece of an
-                                  id before its final one                                        */
-    int32_t n_tokens;          /* = TTSOutput.token_length (XTTSv2.py:813); stop token included */
+    int32_t status;            /* 0 ok (final result), <0 failed / cancelled, 1 = partial piece (see early_tokens).
+                                  xtts_fetch(seq_id) hands out the pieces of an id oldest first: fetch each result
+                                  before polling further                                          */
+    int32_t n_tokens;          /* final: = TTSOutput.token_length (XTTSv2.py:813), stop token included;
+                                  partial: the tokens whose audio this piece carries               */
     int32_t n_samples;         /* 24 kHz samples                                               */
     int32_t n_prompt_rows;
     double t_submit, t_first_token, t_done;   /* seconds, engine clock                         */
@@ -125,11 +128,15 @@ int xtts_condition(xtts_engine* e, int32_t slot, const float* wav22k, int64_t n2
  * Asynchronous: the scheduler thread admits, prefills, decodes (continuous batching), vocodes. */
 int xtts_submit(xtts_engine* e, uint64_t seq_id, const int32_t* text_ids, int32_t n_text, int32_t speaker_slot,
                 const xtts_sampling* sp);
+/* Aborts a chunk (the reference aborts the vLLM request when its generator is dropped).  A queued chunk is dropped, a
+ * decoding one stops at the scheduler's next iteration and returns its batch slot and KV pages; either way exactly one
+ * final result with status XTTS_ERR_CANCELLED is delivered.  Unknown / already finished ids are ignored. */
+int xtts_cancel(xtts_engine* e, uint64_t seq_id);
 /* completion queue (replaces `async for output in generator` + get_model_logits + hifigan_decoder,
  * XTTSv2.py:785-814).  Returns 1 and fills *out when a chunk finished, 0 on timeout. */
 int xtts_poll(xtts_engine* e, xtts_result* out, int32_t timeout_ms);
-/* copies out and releases a finished chunk (or its partial first-audio piece, whichever is older); any of tokens / wav /
- * latents may be NULL (a partial piece has no latents).  seq_id must be < 2^63. */
+/* copies out and releases the OLDEST unfetched result of a chunk (its partial pieces, then the final one); any of tokens /
+ * wav / latents may be NULL (a partial piece has no latents; a failed result has no data and is only released). */
 int xtts_fetch(xtts_engine* e, uint64_t seq_id, int32_t* tokens, float* wav, float* latents);
 /* engine knobs (key, value):
  *   "d2h_wav"             0 = leave waveforms in HBM (kernel-only timing), 1 = D2H into pinned memory (default)
@@ -140,6 +147,10 @@ int xtts_fetch(xtts_engine* e, uint64_t seq_id, int32_t* tokens, float* wav, flo
  *                         GEMM / LayerNorm with "microbatches" concurrent row branches (default: measured faster)
  *   "microbatches"        1..4 concurrent branches the decode step's rows are split into (default 2)
  *   "microbatch_min_rows" steps with fewer active rows stay single-branch (default 48)
+ *   "voc_segment"         m > 0: a chunk is vocoded in windows of m tokens WHILE it decodes (the vocoder runs on its own
+ *                         stream beside the decode step), 0 = one window per chunk when it ends.  Same samples either way.
+ *   "voc_sms"             SMs the vocoder's persistent conv kernels may occupy while a decode step is in flight (0 = all)
+ *   "voc_batch"           windows per vocoder launch (1..32, default 32; ragged lengths are batched together)
  *   "profile"             1 = CUDA events around every launch (xtts_get_kernel_profile), "reset_stats" = zero the counters */
 int xtts_set_option(xtts_engine* e, const char* key, int64_t value);
 int xtts_get_stats(xtts_engine* e, xtts_stats* out);
@@ -155,6 +166,10 @@ int xtts_device_timer(xtts_engine* e, int32_t op, double* ms);
  * in *n_out; `stage` (may be NULL) names an intermediate to copy to stage_out ("z","pre","up0","mrf0",...). */
 int xtts_vocode(xtts_engine* e, const float* latents, int32_t T, int32_t speaker_slot, float* wav, int32_t* n_out,
                 const char* stage, float* stage_out, int64_t stage_cap);
+/* The vocoder on z-frames [z0, z0 + nz) of the chunk `latents` [T, in_dim] as a window of its own: wav [nz * 256].
+ * Samples further than the generator's receptive field (~14 z-frames) from an inner window edge equal the whole chunk's —
+ * the property "voc_segment" / early_tokens rest on (tests/test_gpu_vocoder.py). */
+int xtts_vocode_window(xtts_engine* e, const float* latents, int32_t T, int32_t speaker_slot, int32_t z0, int32_t nz, float* wav);
 /* one prefill over [prompt ; forced audio tokens] (the reference's 2nd pass, XTTSv2.py:617-687):
  * outputs ln_f hidden of every row, raw logits + latents of the last n_audio rows */
 int xtts_gpt_prefill(xtts_engine* e, const int32_t* text_ids, int32_t n_text, int32_t speaker_slot,

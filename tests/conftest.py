@@ -29,6 +29,17 @@ def has_gpu() -> bool:
     return torch.cuda.is_available()
 
 
+def pytest_collection_modifyitems(config, items):
+    """A box with the library built but no B200: GPU tests are skipped, not errored (the library has no CPU fallback)."""
+    ok = has_gpu() and torch.cuda.get_device_capability(0)[0] == 10
+    if ok:
+        return
+    skip = pytest.mark.skip(reason="needs an sm_100 GPU (libxtts_b200 has no CPU fallback)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def dims_small():
     return XTTSDims.small()

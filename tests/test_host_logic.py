@@ -99,6 +99,9 @@ class FakeEngine(BaseAsyncTTSEngine):
     def __init__(self, fail_at=None, delay=0.02):
         self.fail_at, self.delay, self.started = fail_at, delay, []
 
+    def get_memory_usage_curve(self):
+        return None
+
     @property
     def conditioning_config(self):
         return ConditioningConfig(True, True)
@@ -327,6 +330,9 @@ class _FakeNativeEngine:
     def submit(self, sid, ids, slot, sp):
         self.q.put((sid, list(ids), slot, int(getattr(sp, "early_tokens", 0))))
 
+    def cancel(self, sid):
+        self.cancelled = getattr(self, "cancelled", []) + [sid]
+
     def poll(self, timeout_ms=50):
         try:
             return self.done.get(timeout=timeout_ms / 1000.0)
@@ -440,3 +446,31 @@ def test_engine_early_first_audio_piece():
     np.testing.assert_array_equal(whole.array, np.concatenate([c.array for c in plain]))
     assert not eng._waiters and all(eng._spk.pinned(s) == 0 for s in range(2))
     tts.loop.run_until_complete(tts.shutdown())
+
+
+def test_abandoned_chunk_is_cancelled_natively():
+    """a chunk whose consumer goes away (closed generator / cancelled coroutine) must not keep decoding:
+    engine.py calls xtts_cancel for it; a chunk consumed to its final result is not cancelled."""
+    import asyncio
+    from auralis_b200 import native
+    eng = _host_engine(delay=0.05)
+    loop = asyncio.new_event_loop()
+
+    async def go():
+        cond, g = await eng.get_audio_conditioning(_wav(0.2), 30, 6, 6)
+        sp = native.Sampling()
+        gen = eng._chunk_generator("r_0", [0, 5, 6, 1], cond, g, sp)
+        task = asyncio.ensure_future(gen.__anext__())
+        await asyncio.sleep(0.01)                      # submitted, not finished
+        task.cancel()
+        try:
+            await task
+        except asyncio.CancelledError:
+            pass
+        await gen.aclose()
+        assert getattr(eng.native, "cancelled", []) == [1]
+        gen2 = eng._chunk_generator("r_1", [0, 5, 6, 1], cond, g, sp)
+        out = [o async for o in gen2]
+        assert len(out) == 1 and getattr(eng.native, "cancelled", []) == [1]     # consumed to the end: no cancel
+    loop.run_until_complete(go())
+    loop.run_until_complete(eng.shutdown())
