@@ -25,9 +25,16 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 #define CUDA_CHECK(x) ::xtts::cuda_check((x), #x, __FILE__, __LINE__)
 #define KERNEL_CHECK() ::xtts::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
 
+// Per-engine launcher state.  Several engines (one per GPU) may live in one process, each with its own scheduler thread:
+// what used to be process globals is a KernelCtx owned by the engine and bound to whichever thread issues that engine's
+// work (the scheduler thread, or an API thread inside a synchronous entry point).  Unbound threads see a default context.
+struct KernelCtx;
+extern thread_local KernelCtx* t_kctx;
+KernelCtx& kctx_default();
+inline KernelCtx& kctx() { return t_kctx ? *t_kctx : kctx_default(); }
 // Every kernel launch of this library goes through this counter (bench.py "gpu_launches").
-extern unsigned long long g_launch_count;
-#define COUNT_LAUNCH() (++::xtts::g_launch_count)
+#define g_launch_count (::xtts::kctx().launch_count)
+#define COUNT_LAUNCH() (++::xtts::kctx().launch_count)
 
 // Optional per-kernel-family timing with CUDA events on the launching stream (bench.py "roofline").
 // Off by default; when on, every launcher records an event pair and its algorithmic FLOPs / bytes.
@@ -80,7 +87,31 @@ struct KernelProfiler {
     }
     void reset() { collect(); for (int i = 0; i < KF_COUNT; ++i) { ms[i] = flops[i] = bytes[i] = 0; launches[i] = 0; } }
 };
-extern KernelProfiler g_prof;
+struct KernelCtx {
+    unsigned long long launch_count = 0;
+    KernelProfiler prof;
+    bool use_pdl = true;
+    int voc_sm_cap = 0;           // > 0: persistent tensor-core conv grids take at most this many SMs (set per vocoder batch)
+    int attn_ctas_per_sm = 0;     // 0 = uncapped decode-attention grid; > 0: at most this many CTAs per SM
+    int gemm_decode_bn = 0;       // 0 = heuristic; 32/64/128 forces the tile width of decode-shaped tcgen05 GEMMs
+    int conv_epi_groups = 2;      // 1 or 2 epilogue warpgroups in conv1d_tc_kernel
+};
+#define g_prof (::xtts::kctx().prof)
+#define g_use_pdl (::xtts::kctx().use_pdl)
+#define g_voc_sm_cap (::xtts::kctx().voc_sm_cap)
+#define g_attn_ctas_per_sm (::xtts::kctx().attn_ctas_per_sm)
+#define g_gemm_decode_bn (::xtts::kctx().gemm_decode_bn)
+#define g_conv_epi_groups (::xtts::kctx().conv_epi_groups)
+
+// true the first time it is called with the current CUDA device for this flag set (function attributes are per device)
+inline bool first_on_device(bool (&done)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || done[dev]) return false;
+    done[dev] = true;
+    return true;
+}
+
 struct ProfScope {
     cudaStream_t st; cudaEvent_t b; bool on; bool ext;
     ProfScope(int fam, cudaStream_t s, double fl = 0, double by = 0) : st(s), b(nullptr), on(g_prof.enabled), ext(false) {
@@ -113,7 +144,6 @@ inline const char* kernel_family_name(int f) {
 // ---- programmatic dependent launch (PDL): the decode step is a chain of ~200 short dependent kernels; with the
 // programmatic-serialization attribute kernel N+1 is launched while kernel N still runs, does its prologue (barrier
 // init, TMEM alloc, weight-tile prefetch) and only blocks at griddepcontrol.wait before touching N's outputs.
-extern bool g_use_pdl;
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

@@ -23,8 +23,6 @@
 #include "kernels.h"
 
 namespace xtts {
-int g_conv_epi_groups = 2;        // engine option "conv_epi_groups" (1 or 2 epilogue warpgroups per CTA)
-int g_voc_sm_cap = 0;             // > 0: persistent conv grids use at most this many CTAs (SM partition while the GPT decodes)
 namespace {
 
 // warps [0, 4*EG) epilogue (EG warpgroups share a tile's accumulator chunks), warp 4*EG producer, warp 4*EG+1 MMA issuer
@@ -403,8 +401,8 @@ int atoms_lpad(int L) { return kAtomPadL + ceil_div(L + 1, 512) * 512 + kAtomPad
 constexpr int kMaxDynTc = 227 * 1024 - 4096;      // opt-in limit minus the kernel's static shared memory
 template <int NACC, int EG>
 static void launch_inst(const ConvTcParams& P, dim3 grid, size_t smem, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(conv1d_tc_kernel<NACC, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynTc)); attr = true; }
+    static bool attr[64] = {};
+    if (first_on_device(attr)) CUDA_CHECK(cudaFuncSetAttribute(conv1d_tc_kernel<NACC, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynTc));
     conv1d_tc_kernel<NACC, EG><<<grid, threads_tc(EG), smem, st>>>(P);
 }
 

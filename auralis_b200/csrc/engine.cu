@@ -142,6 +142,12 @@ class Engine {
 public:
     explicit Engine(const xtts_config& c);
     ~Engine();
+    // binds this engine's launcher state (launch counter, profiler, knobs) to the calling thread for one API call
+    struct Bind {
+        KernelCtx* prev;
+        explicit Bind(Engine* e) : prev(t_kctx) { t_kctx = &e->kctx_; }
+        ~Bind() { t_kctx = prev; }
+    };
 
     void load_weight(const char* name, const float* data, const int64_t* shape, int ndim);
     void finalize_weights();
@@ -171,6 +177,7 @@ public:
                       int32_t* out);
 
 private:
+    KernelCtx kctx_;
     // ---- geometry
     xtts_config cfg;
     int H, L, NH, FF, V, Vpad, B, NSLOT, CAP, MAXP, max_pages, SEENW, S;
@@ -351,6 +358,7 @@ private:
 // construction
 // ================================================================================================
 Engine::Engine(const xtts_config& c) : cfg(c) {
+    Bind bind_ctx(this);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -1634,6 +1642,7 @@ void Engine::process_cancels(const std::vector<uint64_t>& ids) {
 }
 
 void Engine::loop() {
+    t_kctx = &kctx_;                                   // this thread issues this engine's work, and only this engine's
     cudaSetDevice(cfg.device);
     while (true) {
         std::vector<uint64_t> cancels;
@@ -2037,7 +2046,7 @@ using xtts::Engine;
 struct xtts_engine { Engine* impl; };
 
 #define XTTS_TRY(body)                                                  \
-    try { body; return XTTS_OK; }                                       \
+    try { Engine::Bind bind_ctx_(e->impl); body; return XTTS_OK; }      \
     catch (const xtts::CudaError& ex) { xtts::set_error(ex.what()); return XTTS_ERR_CUDA; } \
     catch (const std::exception& ex) { xtts::set_error(ex.what()); return XTTS_ERR_INVALID; } \
     catch (...) { xtts::set_error("unknown error"); return XTTS_ERR_INVALID; }
@@ -2052,13 +2061,19 @@ const char* xtts_last_error(void) {
 }
 const char* xtts_version(void) { return "libxtts_b200 0.1 (sm_100a)"; }
 
+#define XTTS_TRY_UNBOUND(body)                                          \
+    try { body; return XTTS_OK; }                                       \
+    catch (const xtts::CudaError& ex) { xtts::set_error(ex.what()); return XTTS_ERR_CUDA; } \
+    catch (const std::exception& ex) { xtts::set_error(ex.what()); return XTTS_ERR_INVALID; } \
+    catch (...) { xtts::set_error("unknown error"); return XTTS_ERR_INVALID; }
+
 int xtts_create(const xtts_config* cfg, xtts_engine** out) {
     if (!cfg || !out) { xtts::set_error("null argument"); return XTTS_ERR_INVALID; }
-    XTTS_TRY({ Engine* e = new Engine(*cfg); *out = new xtts_engine{e}; })
+    XTTS_TRY_UNBOUND({ Engine* eng = new Engine(*cfg); *out = new xtts_engine{eng}; })
 }
 int xtts_destroy(xtts_engine* e) {
     if (!e) return XTTS_OK;
-    XTTS_TRY({ delete e->impl; delete e; })
+    XTTS_TRY_UNBOUND({ delete e->impl; delete e; })
 }
 int xtts_load_weight(xtts_engine* e, const char* name, const float* data, const int64_t* shape, int32_t ndim) {
     XTTS_TRY(e->impl->load_weight(name, data, shape, ndim))
@@ -2076,7 +2091,7 @@ int xtts_submit(xtts_engine* e, uint64_t seq_id, const int32_t* text_ids, int32_
 }
 int xtts_cancel(xtts_engine* e, uint64_t seq_id) { XTTS_TRY(e->impl->cancel(seq_id)) }
 int xtts_poll(xtts_engine* e, xtts_result* out, int32_t timeout_ms) {
-    try { return e->impl->poll(out, timeout_ms); }
+    try { return e->impl->poll(out, timeout_ms); }       // (no device work: nothing to bind)
     catch (const std::exception& ex) { xtts::set_error(ex.what()); return XTTS_ERR_INVALID; }
 }
 int xtts_fetch(xtts_engine* e, uint64_t seq_id, int32_t* tokens, float* wav, float* latents) {

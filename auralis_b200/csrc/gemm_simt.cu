@@ -6,9 +6,8 @@
 
 namespace xtts {
 
-unsigned long long g_launch_count = 0;
-KernelProfiler g_prof;
-bool g_use_pdl = true;
+thread_local KernelCtx* t_kctx = nullptr;
+KernelCtx& kctx_default() { static KernelCtx c; return c; }
 
 namespace {
 

@@ -10,7 +10,6 @@
 #include "kernels.h"
 
 namespace xtts {
-int g_gemm_decode_bn = 0;
 namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
@@ -273,11 +272,9 @@ void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias
                int N, int K, int flags, cudaStream_t st, int splits, int a_box_rows, bool pdl) {
     constexpr int STAGES = stages_for(BN);
     constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (first_on_device(attr_set))
         CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
     ProfScope ps(KF_GEMM_TC, st, 2.0 * M * N * K,
                  2.0 * ((double)M * K + (double)N * K) + ((flags & GEMM_OUT_BF16) ? 2.0 : 4.0) * M * N);
@@ -582,7 +579,17 @@ decode_chain_kernel(const __grid_constant__ CUtensorMap tmATT, const __grid_cons
 }  // namespace
 
 bool gemm_tc_init(std::string* err) {
-    if (g_encode) return true;
+    static bool dev_done[64] = {};
+    auto per_device = [&] {
+        // opt every instantiation into its dynamic shared memory now (never inside a stream capture); per device
+        if (!first_on_device(dev_done)) return;
+        auto smem_of = [](int bn) { return (int)(stages_for(bn) * (BM * BK * 2 + bn * BK * 2) + 1024); };
+        cudaFuncSetAttribute(gemm_bf16_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(128));
+        cudaFuncSetAttribute(gemm_bf16_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(64));
+        cudaFuncSetAttribute(gemm_bf16_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(32));
+        (void)cudaGetLastError();
+    };
+    if (g_encode) { per_device(); return true; }
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -592,12 +599,7 @@ bool gemm_tc_init(std::string* err) {
         return false;
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-    // opt every instantiation into its dynamic shared memory now (never inside a stream capture)
-    auto smem_of = [](int bn) { return (int)(stages_for(bn) * (BM * BK * 2 + bn * BK * 2) + 1024); };
-    cudaFuncSetAttribute(gemm_bf16_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(128));
-    cudaFuncSetAttribute(gemm_bf16_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(64));
-    cudaFuncSetAttribute(gemm_bf16_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(32));
-    (void)cudaGetLastError();
+    per_device();
     return true;
 }
 
@@ -657,13 +659,11 @@ void launch_decode_chain(const DecodeChainArgs& a, cudaStream_t st, bool pdl) {
     if (!decode_chain_supported(a.M, a.H, a.FF)) throw CudaError("decode_chain: unsupported geometry");
     if (!g_encode) { std::string err; if (!gemm_tc_init(&err)) throw CudaError(err); }
     static int n_sm = 0;
-    static bool attr_set = false;
+    static bool attr_set[64] = {};
     constexpr size_t smem = CH_STAGES * (BM * BK * 2 + CH_BN * BK * 2) + 1024;
     if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
-    if (!attr_set) {
+    if (first_on_device(attr_set))
         CUDA_CHECK(cudaFuncSetAttribute(decode_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     const int abox = a_box_rows_for(a.M);
     const int H = a.H, FF = a.FF;
     CUtensorMap tATT, tWo, tXn, tWfc, tFF, tWproj, tWqkv;

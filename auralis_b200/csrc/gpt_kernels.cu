@@ -12,7 +12,6 @@
 #include "kernels.h"
 
 namespace xtts {
-int g_attn_ctas_per_sm = 0;       // engine option "attn_ctas_per_sm": 0 = one CTA per (row, head); > 0 caps the decode-attention grid
 namespace {
 
 // ------------------------------------------------------------------------------------------------

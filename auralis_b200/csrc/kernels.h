@@ -155,10 +155,8 @@ ConvTcPlan conv1d_tc_plan(int Cin, int Cout, int K);
 void conv1d_tc_pack(const float* w /*[Cout][Cin][K]*/, int Cin, int Cout, int K, const ConvTcPlan& pl, __half* blob);
 // y = bias + cbias + resid + conv(a16);  out32 (fp32 [C][L], store/accumulate) and/or out16 (lrelu(y, slope_out) atoms)
 // out16 = lrelu(y * scale16, slope_out)
-extern int g_attn_ctas_per_sm;  // 0 = uncapped decode-attention grid; > 0: at most this many CTAs per SM, each walking several (row, head) items
-extern int g_gemm_decode_bn;    // 0 = heuristic; 32/64/128 forces the tile width of decode-shaped (M <= 256) tcgen05 GEMMs
-extern int g_conv_epi_groups;   // 1 or 2 epilogue warpgroups in conv1d_tc_kernel (default 2)
-extern int g_voc_sm_cap;        // > 0: persistent tensor-core conv grids take at most this many SMs (set per vocoder batch)
+// (engine knobs of the launchers — attention grid cap, decode GEMM tile, conv epilogue groups, vocoder SM cap — live in
+//  the calling engine's KernelCtx, common.cuh)
 void launch_conv1d_tc(const __half* a16, const __half* wblob, const ConvTcPlan& pl, const float* bias, const float* cbias,
                       const float* resid, float* out32, __half* out16, int Cin, int Cout, int L, int lpad, int K, int dil,
                       float slope_out, float scale16, int mode, int batch, int cbias_batch_stride, cudaStream_t st,

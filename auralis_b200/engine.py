@@ -74,17 +74,42 @@ def load_audio(source: Union[str, Path, bytes], sampling_rate: int) -> np.ndarra
 class XTTSv2Engine(BaseAsyncTTSEngine):
     model_type = "xtts"
 
-    def __init__(self, dims: XTTSDims, gpt_state, core_state, *, device: int = 0, precision: str = "bf16",
-                 max_concurrency: int = 64, max_speakers: int = 32, tokenizer_file: Optional[str] = None,
-                 early_emit_tokens: int = 0, **_):
+    def __init__(self, dims: XTTSDims, gpt_state, core_state, *, device: int = 0, devices: Optional[List[int]] = None,
+                 precision: str = "bf16", max_concurrency: int = 64, max_speakers: int = 32,
+                 tokenizer_file: Optional[str] = None, early_emit_tokens: int = 0, voc_segment: Optional[int] = None, **_):
+        """`devices=[0, 1, ...]`: data parallelism inside the product (north_star: "requests shard data-parallel across the
+        8xB200 box") — one native engine (full weight replica, own scheduler thread, own streams) per listed GPU in THIS
+        process; every text chunk goes to the engine with the least work in flight, results are re-assembled in request
+        order by the façade as before.  `max_concurrency` is per GPU.  Default: the single GPU `device`."""
         prec = {"fp32": native.PRECISION_FP32, "bf16": native.PRECISION_BF16}[precision]
         self.dims = dims
         self.precision = precision
-        self.device_index = int(device)
+        self.devices = [int(d) for d in devices] if devices else [int(device)]
+        if len(set(self.devices)) != len(self.devices):
+            raise ValueError("devices must be distinct CUDA ordinals")
+        self.device_index = self.devices[0]
         self.max_concurrency = max_concurrency
-        self.native = native.NativeEngine(dims, device=device, precision=prec, max_batch=max_concurrency,
-                                          max_speakers=max_speakers)
-        self.native.load_state(gpt_state, core_state)
+        self.natives = [native.NativeEngine(dims, device=d, precision=prec, max_batch=max_concurrency, max_speakers=max_speakers)
+                        for d in self.devices]
+        self.native = self.natives[0]
+        if len(self.natives) == 1:
+            self.native.load_state(gpt_state, core_state)
+        else:                                               # replicas load side by side (the C calls release the GIL)
+            errs: list = []
+
+            def _load(ne):
+                try:
+                    ne.load_state(gpt_state, core_state)
+                except BaseException as e:      # noqa: BLE001 — re-raised below
+                    errs.append(e)
+            ts = [threading.Thread(target=_load, args=(ne,)) for ne in self.natives]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+            if errs:
+                raise errs[0]
+        if voc_segment is not None:
+            for ne in self.natives:
+                ne.set_option("voc_segment", int(voc_segment))
         self.tokenizer = XTTSTokenizer(dims.gpt.n_text_tokens, dims.gpt.max_text_tokens, tokenizer_file)
         self.mel_bos_token_id = dims.gpt.start_audio_token
         self.mel_eos_token_id = dims.gpt.stop_audio_token
@@ -92,17 +117,20 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
         # > 0: streaming requests get the audio of their first chunk's leading tokens as soon as those are decoded
         # (time-to-first-audio); 0 = one TTSOutput per chunk, exactly like the reference
         self.early_emit_tokens = int(early_emit_tokens)
-        self._spk = SpeakerSlots(max_speakers)        # key -> native slot; pins slots referenced by chunks in flight
+        self._spks = [SpeakerSlots(max_speakers) for _ in self.natives]     # per GPU: key -> native slot, pins
+        self._spk = self._spks[0]
         self._spk_arrays: Dict[str, Tuple["_SpeakerArray", "_SpeakerArray"]] = {}    # reference key -> host (cond, g) pair
         self._next_id = 1
         self._id_lock = threading.Lock()
-        self._waiters: Dict[int, Tuple[asyncio.AbstractEventLoop, asyncio.Queue, int]] = {}
+        self._waiters: Dict[int, tuple] = {}            # sid -> (loop, box, slot, device index, work units)
         self._wlock = threading.Lock()
+        self._load = [0] * len(self.natives)            # text ids of the chunks in flight per GPU (under _wlock)
         self._stop = False
-        self._parked = False
+        self._parked = 0
         self._paused = False       # set while a caller drives the native completion queue itself (bench device arm)
-        self._poller = threading.Thread(target=self._poll_loop, name="xtts-poll", daemon=True)
-        self._poller.start()
+        self._pollers = [threading.Thread(target=self._poll_loop, args=(i,), name=f"xtts-poll-{i}", daemon=True)
+                         for i in range(len(self.natives))]
+        [t.start() for t in self._pollers]
 
     # ---- plugin API -------------------------------------------------------------------------
     @classmethod
@@ -218,34 +246,38 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
         self._spk_arrays[key] = pair
         return pair
 
-    def register_speaker(self, cond_latents: np.ndarray, d_vector: np.ndarray) -> Tuple["_SpeakerArray", "_SpeakerArray"]:
-        """Pre-computed conditioning (the pair `prepare_for_streaming_generation` hands back, tts.py:91-105).
-        Raises SpeakerSlotsFull when every slot is pinned by chunks in flight."""
+    def register_speaker(self, cond_latents: np.ndarray, d_vector: np.ndarray, dev: int = 0) -> Tuple["_SpeakerArray", "_SpeakerArray"]:
+        """Pre-computed conditioning (the pair `prepare_for_streaming_generation` hands back, tts.py:91-105) uploaded to
+        GPU `dev` (index into `devices`).  Raises SpeakerSlotsFull when every slot is pinned by chunks in flight."""
+        natives = getattr(self, "natives", None) or [self.native]
+        spks = getattr(self, "_spks", None) or [self._spk]
         c = np.ascontiguousarray(cond_latents, np.float32).reshape(self.dims.gpt.n_cond_latents, self.dims.gpt.hidden)
         g = np.ascontiguousarray(d_vector, np.float32).reshape(-1)
         key = hashlib.sha256(c.tobytes() + g.tobytes()).hexdigest()
-        slot, pending, owner = self._spk.acquire(key)
+        slot, pending, owner = spks[dev].acquire(key)
         if owner:
             try:
-                self.native.set_speaker(slot, c, g)
+                natives[dev].set_speaker(slot, c, g)
             except BaseException as e:
-                self._spk.failed(key, e if isinstance(e, Exception) else RuntimeError("set_speaker interrupted"))
+                spks[dev].failed(key, e if isinstance(e, Exception) else RuntimeError("set_speaker interrupted"))
                 raise
-            self._spk.ready(key)
+            spks[dev].ready(key)
         elif pending is not None:
             pending.result(timeout=120)
-        return _SpeakerArray(c[None], slot, key), _SpeakerArray(g.reshape(1, -1, 1), slot, key)
+        return _SpeakerArray(c[None], slot, key, dev), _SpeakerArray(g.reshape(1, -1, 1), slot, key, dev)
 
-    async def _pin_speaker(self, cond, g, timeout_s: float = 120.0) -> int:
-        """Slot holding this conditioning pair, pinned for one chunk.  A pair whose slot was recycled since it was
-        handed out (LRU eviction) is uploaded again from the arrays instead of selecting another speaker's voice."""
+    async def _pin_speaker(self, cond, g, timeout_s: float = 120.0, dev: int = 0) -> int:
+        """Slot of GPU `dev` holding this conditioning pair, pinned for one chunk.  A pair whose slot was recycled since it
+        was handed out (LRU eviction), or that was computed on another GPU, is uploaded (again) from the host arrays
+        instead of selecting another speaker's voice."""
+        spks = getattr(self, "_spks", None) or [self._spk]
         t0 = time.monotonic()
         while True:
             key, slot = getattr(cond, "key", None), getattr(cond, "slot", None)
-            if key is not None and slot is not None and self._spk.pin(key, slot):
+            if key is not None and slot is not None and (getattr(cond, "dev", 0) or 0) == dev and spks[dev].pin(key, slot):
                 return slot
             try:
-                cond, g = self.register_speaker(np.asarray(cond), np.asarray(g))
+                cond, g = self.register_speaker(np.asarray(cond), np.asarray(g), dev)
             except SpeakerSlotsFull:
                 if time.monotonic() - t0 > timeout_s:
                     raise
@@ -279,19 +311,34 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
         pinned from submission until the native completion arrives (released by the poller thread), so it cannot be
         recycled under a queued or running chunk even if the awaiting coroutine is cancelled."""
         loop = asyncio.get_running_loop()
-        box: asyncio.Queue = asyncio.Queue()            # completions of this chunk: an optional partial piece, then the final one
-        slot = await self._pin_speaker(cond, g)
+        box: asyncio.Queue = asyncio.Queue()            # completions of this chunk: partial pieces, then the final one
+        natives = getattr(self, "natives", None) or [self.native]
+        spks = getattr(self, "_spks", None) or [self._spk]
+        work = len(ids)
+        with self._wlock:                               # data parallelism: the GPU with the least work in flight takes it
+            load = getattr(self, "_load", None)
+            if load is None:
+                load = self._load = [0] * len(natives)
+            dev = min(range(len(natives)), key=lambda d: (load[d], d))
+            load[dev] += work
+        try:
+            slot = await self._pin_speaker(cond, g, dev=dev)
+        except BaseException:
+            with self._wlock:
+                self._load[dev] -= work
+            raise
         with self._id_lock:
             sid = self._next_id
             self._next_id += 1
         with self._wlock:
-            self._waiters[sid] = (loop, box, slot)
+            self._waiters[sid] = (loop, box, slot, dev, work)
         try:
-            self.native.submit(sid, ids, slot, sp)
+            natives[dev].submit(sid, ids, slot, sp)
         except BaseException:
             with self._wlock:
                 self._waiters.pop(sid, None)
-            self._spk.unpin(slot)
+                self._load[dev] -= work
+            spks[dev].unpin(slot)
             raise
         n_before = 0
         done = False
@@ -316,7 +363,7 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
                 # it gives its batch slot and KV pages back — the reference aborts the vLLM request the same way.  The
                 # poller still receives the (cancelled) final result and unpins the speaker slot.
                 try:
-                    self.native.cancel(sid)
+                    natives[dev].cancel(sid)
                 except Exception:      # noqa: BLE001 — engine already shut down
                     pass
 
@@ -330,13 +377,14 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
                                 token_length=len(output.token_ids))
 
     def park_poller(self, parked: bool = True):
-        """Park / resume the completion poller (a caller that drives `native.run_batch` itself must own the queue)."""
+        """Park / resume the completion pollers (a caller that drives `native.run_batch` itself must own the queue)."""
         self._paused = parked
-        while parked and not self._parked:    # acknowledged between two poll() calls (<= 50 ms)
+        n = len(getattr(self, "_pollers", [None]))
+        while parked and self._parked < n:    # acknowledged between two poll() calls (<= 50 ms)
             time.sleep(0.002)
 
     def run_batch_direct(self, jobs, **kw):
-        """Drive the native engine synchronously (no asyncio): the poller thread is parked for the duration."""
+        """Drive the (first) native engine synchronously (no asyncio): the poller threads are parked for the duration."""
         was = self._paused
         self.park_poller(True)
         try:
@@ -345,21 +393,41 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
             if not was:
                 self.park_poller(False)
 
+    def stats(self) -> dict:
+        """Native counters summed over the GPUs (the numbers the reference's TTSMetricsTracker derives,
+        common/metrics/performance.py:105-151): tokens, samples, decode steps, kernel launches, device time."""
+        tot: Dict[str, float] = {}
+        for ne in (getattr(self, "natives", None) or [self.native]):
+            st = ne.stats()
+            for k, _ in st._fields_:
+                tot[k] = tot.get(k, 0) + getattr(st, k)
+        return tot
+
     async def shutdown(self):
         self._stop = True
-        self._poller.join(timeout=5)
-        self.native.close()
+        for t in getattr(self, "_pollers", []):
+            t.join(timeout=5)
+        for ne in (getattr(self, "natives", None) or [self.native]):
+            ne.close()
 
     # ---- completion dispatch ----------------------------------------------------------------
-    def _poll_loop(self):
+    def _poll_loop(self, dev: int = 0):
+        natives = getattr(self, "natives", None) or [self.native]
+        spks = getattr(self, "_spks", None) or [self._spk]
+        ne = natives[dev]
+        parked = False
         while not self._stop:
             if self._paused:
-                self._parked = True
+                if not parked:
+                    parked = True
+                    self._parked += 1
                 time.sleep(0.002)
                 continue
-            self._parked = False
+            if parked:
+                parked = False
+                self._parked -= 1
             try:
-                r = self.native.poll(50)
+                r = ne.poll(50)
             except Exception:
                 if self._stop:
                     return
@@ -370,24 +438,26 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
             final = r.status <= 0
             with self._wlock:
                 w = self._waiters.pop(r.seq_id, None) if final else self._waiters.get(r.seq_id)
+                if final and w is not None and len(w) > 4 and getattr(self, "_load", None) is not None:
+                    self._load[w[3]] -= w[4]
             try:
                 if r.status < 0:
-                    msg = self.native.lib.xtts_last_error().decode()
+                    msg = ne.lib.xtts_last_error().decode()
                     try:
-                        self.native.lib.xtts_fetch(self.native.h, r.seq_id, None, None, None)   # release its native buffers
+                        ne.lib.xtts_fetch(ne.h, r.seq_id, None, None, None)   # release its native buffers
                     except Exception:      # noqa: BLE001
                         pass
                     raise native.NativeError(f"chunk {r.seq_id} " + ("was cancelled" if r.status == native.ERR_CANCELLED
                                                                     else f"failed ({r.status}): {msg}"))
-                toks, wav, _ = self.native.fetch(r, want_wav=True)
+                toks, wav, _ = ne.fetch(r, want_wav=True)
                 payload, err = (r, toks, wav), None
             except Exception as e:      # noqa: BLE001 — forwarded to the awaiting coroutine
                 payload, err = None, e
             if w is None:
                 continue
-            loop, box, slot = w
+            loop, box, slot = w[0], w[1], w[2]
             if final:
-                self._spk.unpin(slot)               # the native engine is done with this chunk's speaker slot
+                spks[dev].unpin(slot)               # the native engine is done with this chunk's speaker slot
             loop.call_soon_threadsafe(box.put_nowait, (payload, err))
 
 
@@ -395,15 +465,17 @@ class _SpeakerArray(np.ndarray):
     """numpy array that remembers which native speaker slot it was uploaded to and under which cache key (the pair is
     re-validated before every use: a recycled slot is detected and the array uploaded again)."""
 
-    def __new__(cls, arr, slot, key=None):
+    def __new__(cls, arr, slot, key=None, dev=0):
         obj = np.asarray(arr).view(cls)
         obj.slot = slot
         obj.key = key
+        obj.dev = dev               # index into the engine's `devices` the slot number refers to
         return obj
 
     def __array_finalize__(self, obj):
         self.slot = getattr(obj, "slot", None)
         self.key = getattr(obj, "key", None)
+        self.dev = getattr(obj, "dev", 0)
 
 
 def _resample(a: np.ndarray, sr: int, new_sr: int) -> np.ndarray:

@@ -169,6 +169,88 @@ class GPTOracle:
         return out
 
     @torch.no_grad()
+    def generate_batched(self, cond_latents: Sequence[torch.Tensor], text_ids: Sequence[Sequence[int]], sp: SamplingParams,
+                         fast_rng: bool = False, return_logits: bool = False):
+        """The same decode for B chunks AT ONCE — what a CPU deployment of the reference would do (vLLM batches the
+        decode; a B = 1 loop streams the 1.5 GB of fp32 weights once per token instead of once per B tokens).  Prompts are
+        prefilled one by one (`forward_rows`), their K/V copied into a left-aligned padded cache [B, heads, L, 64]; every
+        decode step is one pass over all still-running rows.  Arithmetic per row == `generate` (tests/test_oracle_gpt.py).
+        fast_rng: Exp(1) noise from torch's generator instead of the Philox stream shared with the CUDA sampler (the
+        reference itself is unseeded) — used by bench.py's CPU arm so the timing is not dominated by a Python RNG."""
+        g, w = self.g, self.w
+        B, H, nh, hd, L = len(text_ids), self.g.hidden, self.g.heads, self.g.head_dim, self.g.layers
+        lens, h_last = [], []
+        P = [g.n_cond_latents + len(t) + 1 for t in text_ids]
+        cap = max(P) + sp.max_tokens
+        K = [torch.zeros(B, nh, cap, hd) for _ in range(L)]
+        V = [torch.zeros(B, nh, cap, hd) for _ in range(L)]
+        for b in range(B):
+            h, cache = self.forward_rows(self.prompt_rows(cond_latents[b], text_ids[b]))
+            for i in range(L):
+                K[i][b, :, :P[b]] = cache[i][0]
+                V[i][b, :, :P[b]] = cache[i][1]
+            h_last.append(h[-1])
+        x_lnf = torch.stack(h_last)                                    # [B,H] ln_f output of the last prompt row
+        ctx = torch.tensor(P)                                          # cached positions per row
+        seen = [prompt_seen_set(g) for _ in range(B)]
+        toks: List[List[int]] = [[] for _ in range(B)]
+        lats: List[List[torch.Tensor]] = [[] for _ in range(B)]
+        all_logits: List[List[torch.Tensor]] = [[] for _ in range(B)]
+        alive = list(range(B))
+        gen = torch.Generator().manual_seed(sp.seed) if fast_rng else None
+        wte, wpe = w["gpt.wte.weight"], w["gpt.wpe.emb.weight"]
+        for k in range(1, sp.max_tokens + 1):
+            logits, lat = self.head(x_lnf)
+            nxt, keep = [], []
+            for j, b in enumerate(alive):
+                lats[b].append(lat[j])
+                z = logits[j].clone()
+                if return_logits:
+                    all_logits[b].append(z.clone())
+                if fast_rng and sp.temperature >= _SAMPLING_EPS:
+                    z = apply_repetition_penalty(z.float(), seen[b], sp.repetition_penalty) / sp.temperature
+                    p = torch.softmax(topk_topp_mask(z, sp.top_k, sp.top_p), dim=-1)
+                    tok = int(torch.argmax(p / torch.empty_like(p).exponential_(generator=gen)))
+                else:
+                    tok = sample_token(z, seen[b], sp, b, k - 1)
+                toks[b].append(tok)
+                seen[b].add(tok)
+                if not (tok == sp.stop_token or k == sp.max_tokens):
+                    nxt.append(tok); keep.append(j)
+            if not keep:
+                break
+            alive = [alive[j] for j in keep]
+            rows = torch.tensor(alive)
+            x = wte[torch.tensor(nxt)] + wpe[k]                        # [M,H] decode inputs of the running rows
+            pos = ctx[rows]                                            # where this step's K/V go
+            M = len(alive)
+            ar = torch.arange(M)
+            Lmax = int(pos.max()) + 1
+            mask = torch.arange(Lmax)[None, :] > pos[:, None]          # [M,Lmax] True = not visible
+            for i in range(L):
+                pfx = f"gpt.h.{i}."
+                hN = layer_norm(x, w[pfx + "ln_1.weight"], w[pfx + "ln_1.bias"], g.ln_eps)
+                qkv = hN @ w[pfx + "attn.c_attn.weight"] + w[pfx + "attn.c_attn.bias"]
+                q, kk, vv = qkv.split(H, dim=-1)
+                K[i][rows, :, pos] = kk.view(M, nh, hd)
+                V[i][rows, :, pos] = vv.view(M, nh, hd)
+                Kr, Vr = K[i][rows, :, :Lmax], V[i][rows, :, :Lmax]    # [M,nh,Lmax,hd]
+                sc = torch.einsum("mhd,mhld->mhl", q.view(M, nh, hd), Kr) * (hd ** -0.5)
+                sc = sc.masked_fill(mask[:, None, :], float("-inf"))
+                a = torch.einsum("mhl,mhld->mhd", torch.softmax(sc, dim=-1), Vr).reshape(M, H)
+                x = x + a @ w[pfx + "attn.c_proj.weight"] + w[pfx + "attn.c_proj.bias"]
+                hN = layer_norm(x, w[pfx + "ln_2.weight"], w[pfx + "ln_2.bias"], g.ln_eps)
+                hN = gelu_new(hN @ w[pfx + "mlp.c_fc.weight"] + w[pfx + "mlp.c_fc.bias"])
+                x = x + hN @ w[pfx + "mlp.c_proj.weight"] + w[pfx + "mlp.c_proj.bias"]
+            ctx[rows] = pos + 1
+            x_lnf = layer_norm(x, w["gpt.ln_f.weight"], w["gpt.ln_f.bias"], g.ln_eps)
+            del ar
+        out = (toks, [torch.stack(l) for l in lats])
+        if return_logits:
+            out = out + ([torch.stack(l) for l in all_logits],)
+        return out
+
+    @torch.no_grad()
     def teacher_forced(self, cond_latents, text_ids, tokens: Sequence[int]):
         """The reference's 2nd pass (XTTSv2.py:617-687) without the 4 causally-irrelevant EOS rows:
         one prefill over [prefix ; bos ; t_1..t_{n-1}] -> (raw logits [n,V], latents [n,H])."""

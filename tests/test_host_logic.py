@@ -347,8 +347,8 @@ class _FakeNativeEngine:
         self.closed = True
 
 
-def _host_engine(max_speakers=2, **kw):
-    """The real XTTSv2Engine host code (engine.py) over the fake native layer."""
+def _host_engine(max_speakers=2, n_devices=1, **kw):
+    """The real XTTSv2Engine host code (engine.py) over the fake native layer (`n_devices` fake GPUs)."""
     import threading
     from auralis_b200.config import XTTSDims
     from auralis_b200.engine import XTTSv2Engine
@@ -356,16 +356,21 @@ def _host_engine(max_speakers=2, **kw):
     dims = XTTSDims.small()
     eng = object.__new__(XTTSv2Engine)
     eng.dims, eng.precision, eng.max_concurrency, eng.max_speakers = dims, "fp32", 8, max_speakers
-    eng.native = _FakeNativeEngine(dims, max_speakers, **kw)
+    eng.natives = [_FakeNativeEngine(dims, max_speakers, **kw) for _ in range(n_devices)]
+    eng.native = eng.natives[0]
+    eng.devices, eng.device_index = list(range(n_devices)), 0
     eng.tokenizer = XTTSTokenizer(dims.gpt.n_text_tokens, dims.gpt.max_text_tokens)
     eng.mel_bos_token_id, eng.mel_eos_token_id = dims.gpt.start_audio_token, dims.gpt.stop_audio_token
-    eng._spk = SpeakerSlots(max_speakers)
+    eng._spks = [SpeakerSlots(max_speakers) for _ in range(n_devices)]
+    eng._spk = eng._spks[0]
     eng._spk_arrays = {}
     eng.early_emit_tokens = 0
     eng._next_id, eng._id_lock, eng._waiters, eng._wlock = 1, threading.Lock(), {}, threading.Lock()
-    eng._stop = eng._parked = eng._paused = False
-    eng._poller = threading.Thread(target=eng._poll_loop, daemon=True)
-    eng._poller.start()
+    eng._load = [0] * n_devices
+    eng._stop = eng._paused = False
+    eng._parked = 0
+    eng._pollers = [threading.Thread(target=eng._poll_loop, args=(i,), daemon=True) for i in range(n_devices)]
+    [t.start() for t in eng._pollers]
     return eng
 
 
@@ -474,3 +479,31 @@ def test_abandoned_chunk_is_cancelled_natively():
         assert len(out) == 1 and getattr(eng.native, "cancelled", []) == [1]     # consumed to the end: no cancel
     loop.run_until_complete(go())
     loop.run_until_complete(eng.shutdown())
+
+
+def test_in_process_data_parallel_engines():
+    """`XTTSv2Engine(devices=[...])`: chunks are spread over the engines by work in flight, the speaker computed on GPU 0
+    is uploaded to the other GPU from the host arrays on first use (no voice swap), the request comes back in order, and
+    the per-GPU load counters return to zero."""
+    from auralis_b200 import TTS, TTSRequest
+    eng = _host_engine(max_speakers=2, n_devices=2, delay=0.01)
+    tts = TTS(scheduler_max_concurrency=64).from_engine(eng)
+    text = " ".join(f"Sentence number {i} talks about nothing in particular, at some length, to fill a chunk." for i in range(14))
+    n_chunks = len(eng.prepare_text_tokens(text, "en"))
+    assert n_chunks >= 6
+    seen = [[], []]
+    for d, ne in enumerate(eng.natives):
+        orig = ne.submit
+
+        def rec(sid, ids, slot, sp, _o=orig, _d=d):
+            seen[_d].append(sid)
+            return _o(sid, ids, slot, sp)
+        ne.submit = rec
+    out = tts.generate_speech(TTSRequest(text=text, speaker_files=_wav(0.2), language="en"))
+    assert out.array.shape[0] == 8 * n_chunks
+    assert len(seen[0]) + len(seen[1]) == n_chunks and min(len(seen[0]), len(seen[1])) >= n_chunks // 2 - 1
+    v = float(np.round(0.2 * 32767) / 32767 * 1000 // 1)                    # the fake's voice value for this reference
+    assert np.allclose(np.round(out.array.reshape(n_chunks, 8)[:, 0]), np.round(out.array[0]))      # one voice on both GPUs
+    assert eng.natives[0].cond_calls == 1 and eng.natives[1].cond_calls == 0  # conditioned once, uploaded to the 2nd GPU
+    assert eng._load == [0, 0] and not eng._waiters
+    tts.loop.run_until_complete(tts.shutdown())

@@ -170,3 +170,33 @@ def test_repetition_penalty_matches_the_reference_class(dims_small):
         seen = O.prompt_seen_set(g) | set(gen)
         got = O.apply_repetition_penalty(z.clone(), seen, p)
         assert torch.equal(got, want), (trial, p)
+
+
+def test_batched_decode_equals_per_sequence_decode():
+    """oracle.generate_batched (the CPU arm of bench.py decodes B chunks per step, like a batched deployment of the reference
+    would) against the per-sequence `generate`: same greedy tokens, latents and logits to fp32 rounding, for prompts of
+    different lengths and chunks that stop at different steps."""
+    import numpy as np
+    import torch
+    from auralis_b200.config import XTTSDims
+    from auralis_b200.weights import synth_state
+    from oracle import xtts_oracle as O
+    dims = XTTSDims.small()
+    gs, cs = synth_state(dims, 1234)
+    orc = O.GPTOracle(gs, cs, dims)
+    g = torch.Generator().manual_seed(3)
+    conds = [torch.randn(dims.gpt.n_cond_latents, dims.gpt.hidden, generator=g) for _ in range(4)]
+    ids = [[0] + list(range(5, 5 + n)) + [1] for n in (6, 19, 11, 3)]
+    sp = O.SamplingParams(temperature=0.0, repetition_penalty=5.0, max_tokens=14, stop_token=dims.gpt.stop_audio_token)
+    toks, lats, lgs = orc.generate_batched(conds, ids, sp, return_logits=True)
+    for b in range(4):
+        et, el, elg = orc.generate(conds[b], ids[b], sp, return_logits=True)
+        assert toks[b] == et
+        np.testing.assert_allclose(lats[b].numpy(), el.numpy(), atol=2e-4)
+        np.testing.assert_allclose(lgs[b].numpy(), elg.numpy(), atol=2e-4)
+    # seeded sampling through the shared Philox stream: token-for-token (seq_seed = row index)
+    sp2 = O.SamplingParams(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, max_tokens=10,
+                           stop_token=dims.gpt.stop_audio_token, seed=5)
+    toks2, _ = orc.generate_batched(conds, ids, sp2)
+    for b in range(4):
+        assert toks2[b] == orc.generate(conds[b], ids[b], sp2, seq_seed=b)[0]
