@@ -141,6 +141,30 @@ inline const char* kernel_family_name(int f) {
     return (f >= 0 && f < KF_COUNT) ? n[f] : "?";
 }
 
+// ---- device-side timeline (debug, option "trace"): the first and the last CTA of a traced kernel stamp %globaltimer at
+// entry, after the dependency wait and at exit.  Unlike event brackets this does not serialise anything, so it shows the
+// decode step as it really runs (PDL overlap, concurrent branches).  One buffer per translation unit (no -rdc).
+struct TraceBuf { unsigned long long* rec; unsigned* n; unsigned cap; };
+static __device__ TraceBuf g_trace_tu = {nullptr, nullptr, 0};
+enum { TR_GEMM = 1, TR_ATTN = 2, TR_REDUCE_LN = 3, TR_LN = 4, TR_HEAD = 5, TR_SAMPLE = 6, TR_ROWS = 7, TR_CONV = 8 };
+__device__ __forceinline__ void trace_pt(int id, int phase) {
+    if (threadIdx.x != 0 || threadIdx.y != 0) return;
+    const bool first = (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
+    const bool last = blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1;
+    if (!first && !last) return;
+    const TraceBuf tb = g_trace_tu;
+    if (tb.rec == nullptr) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned i = atomicAdd(tb.n, 1u);
+    if (i < tb.cap) {
+        tb.rec[2 * i] = t;
+        tb.rec[2 * i + 1] = ((unsigned long long)id << 32) | ((unsigned long long)(first ? 0 : 1) << 8) | (unsigned long long)phase |
+                            ((unsigned long long)(gridDim.x * gridDim.y * gridDim.z) << 40);
+    }
+}
+#define XTTS_TRACE_SETTER(name) void name(TraceBuf b) { cudaMemcpyToSymbol(g_trace_tu, &b, sizeof(b)); }
+
 // ---- programmatic dependent launch (PDL): the decode step is a chain of ~200 short dependent kernels; with the
 // programmatic-serialization attribute kernel N+1 is launched while kernel N still runs, does its prologue (barrier
 // init, TMEM alloc, weight-tile prefetch) and only blocks at griddepcontrol.wait before touching N's outputs.

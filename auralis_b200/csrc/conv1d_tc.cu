@@ -109,6 +109,7 @@ conv1d_tc_kernel(const ConvTcParams P) {
     __shared__ __align__(16) float sbias[2][256];     // per-tile bias + speaker bias (double buffered across tiles)
     __shared__ int s_cum[kVocMaxItems + 1], s_len[kVocMaxItems];   // ragged batch: first tile / input length of every item
 
+    trace_pt(TR_CONV, 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int halo = P.center * P.dil;
     const int planes = P.CK / 8, ksteps = P.CK / 16, nch = P.Cin / P.CK;
@@ -341,6 +342,7 @@ conv1d_tc_kernel(const ConvTcParams P) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    trace_pt(TR_CONV, 2);
     if (warp == kMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tm_cols) : "memory");
     }
@@ -368,6 +370,8 @@ __global__ void atoms_zero_pads_kernel(uint4* __restrict__ buf, int planes_total
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+XTTS_TRACE_SETTER(trace_set_conv)
+
 ConvTcPlan conv1d_tc_plan(int Cin, int Cout, int K) {
     ConvTcPlan pl{};
     pl.N = Cout > 256 ? 256 : Cout;

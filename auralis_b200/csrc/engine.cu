@@ -163,6 +163,7 @@ public:
     void sync_idle();
     void kernel_profile(xtts_kernel_profile* out);
     void device_timer(int op, double* ms);
+    int trace(int op, uint64_t* out, int cap);
 
     void vocode_sync(const float* latents, int T, int speaker, float* wav, int* n_out, const char* stage,
                      float* stage_out, int64_t stage_cap);
@@ -285,6 +286,7 @@ private:
     void drop_graphs();
     bool use_chain = false;       // option "decode_chain": fused persistent per-layer GEMM/LayerNorm chain kernel (measured slower)
     DBuf<unsigned> d_chain_sync;  // device-wide barrier words of the chain kernel
+    DBuf<unsigned long long> d_trace; DBuf<unsigned> d_trace_n;      // debug timeline (xtts_debug_trace)
     int n_micro = 2;              // option "microbatches": decode rows are split into this many concurrent branches
     int micro_min_rows = 48;      // option "microbatch_min_rows": below this many active rows the step stays single-branch
     int eager_steps_done = 0;
@@ -1860,6 +1862,35 @@ void Engine::device_timer(int op, double* ms) {
     } else throw std::runtime_error("device_timer: op must be 0 (start) or 1 (stop)");
 }
 
+// debug timeline: op 1 arms the trace points of the decode / vocoder kernels (common.cuh), op 0 disarms and copies the
+// records out: [n][2] u64 = (globaltimer ns, id << 32 | grid << 40 | last-CTA flag << 8 | phase).  Returns the record count.
+int Engine::trace(int op, uint64_t* out, int cap) {
+    std::lock_guard<std::mutex> lk(mu);
+    CUDA_CHECK(cudaSetDevice(cfg.device));
+    CUDA_CHECK(cudaStreamSynchronize(st)); CUDA_CHECK(cudaStreamSynchronize(st_voc));
+    if (op == 1) {
+        const unsigned n = 1u << 20;
+        if (!d_trace.p) { d_trace.alloc((size_t)2 * n); d_trace_n.alloc(1); }
+        d_trace_n.zero(st);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        TraceBuf tb{d_trace.p, d_trace_n.p, n};
+        trace_set_gemm(tb); trace_set_gpt(tb); trace_set_conv(tb);
+        CUDA_CHECK(cudaDeviceSynchronize());
+        return 0;
+    }
+    TraceBuf off{nullptr, nullptr, 0};
+    trace_set_gemm(off); trace_set_gpt(off); trace_set_conv(off);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    if (!d_trace.p) return 0;
+    unsigned n = 0;
+    d_trace_n.download(&n, 1, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    n = std::min<unsigned>(n, 1u << 20);
+    const int m = std::min<int>((int)n, cap);
+    if (out && m > 0) { d_trace.download(reinterpret_cast<unsigned long long*>(out), (size_t)2 * m, st); CUDA_CHECK(cudaStreamSynchronize(st)); }
+    return m;
+}
+
 void Engine::sync_idle() {
     std::unique_lock<std::mutex> lk(q_mu);
     cv_done.wait(lk, [&] { return inflight == 0; });
@@ -2102,6 +2133,10 @@ int xtts_get_stats(xtts_engine* e, xtts_stats* out) { XTTS_TRY(e->impl->get_stat
 int xtts_sync(xtts_engine* e) { XTTS_TRY(e->impl->sync_idle()) }
 int xtts_get_kernel_profile(xtts_engine* e, xtts_kernel_profile* out) { XTTS_TRY(e->impl->kernel_profile(out)) }
 int xtts_device_timer(xtts_engine* e, int32_t op, double* ms) { XTTS_TRY(e->impl->device_timer(op, ms)) }
+int xtts_debug_trace(xtts_engine* e, int32_t op, uint64_t* out, int32_t cap) {
+    try { Engine::Bind b(e->impl); return e->impl->trace(op, out, cap); }
+    catch (const std::exception& ex) { xtts::set_error(ex.what()); return XTTS_ERR_INVALID; }
+}
 int xtts_vocode(xtts_engine* e, const float* latents, int32_t T, int32_t speaker_slot, float* wav, int32_t* n_out,
                 const char* stage, float* stage_out, int64_t stage_cap) {
     XTTS_TRY(e->impl->vocode_sync(latents, T, speaker_slot, wav, n_out, stage, stage_out, stage_cap))

@@ -109,6 +109,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
 
+    trace_pt(TR_GEMM, 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
     // split-K: gridDim.z CTAs share one output tile, each owning a contiguous range of k-blocks and writing its raw
@@ -150,6 +151,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tma_load_2d(sB + kb * B_BYTES, &tmB, &full_bar[kb], (kb_begin + kb) * BK, n0);
             }
             pdl_wait();
+            trace_pt(TR_GEMM, 1);
             for (int kb = 0; kb < pre; ++kb)
                 tma_load_2d(sA + kb * A_BYTES, &tmA, &full_bar[kb], (kb_begin + kb) * BK, m0);
             for (int kb = pre; kb < num_kb; ++kb) {
@@ -242,6 +244,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    trace_pt(TR_GEMM, 2);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
@@ -577,6 +580,8 @@ decode_chain_kernel(const __grid_constant__ CUtensorMap tmATT, const __grid_cons
 }
 
 }  // namespace
+
+XTTS_TRACE_SETTER(trace_set_gemm)
 
 bool gemm_tc_init(std::string* err) {
     static bool dev_done[64] = {};

@@ -41,7 +41,7 @@ __global__ void build_rows_kernel(const RowDesc* __restrict__ rows, GptTables t,
 
 __global__ void build_decode_rows_kernel(const int* __restrict__ active, const int* __restrict__ last_tok,
                                          const int* __restrict__ n_gen, GptTables t, float* __restrict__ X) {
-    pdl_trigger(); pdl_wait();
+    trace_pt(TR_ROWS, 0); pdl_trigger(); pdl_wait(); trace_pt(TR_ROWS, 1);
     const int slot = active[blockIdx.x];
     const int H = t.H;
     const float4* a = reinterpret_cast<const float4*>(t.wte + (size_t)last_tok[slot] * H);
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ X, const float* __restrict__ w, const float* __restrict__ b,
                  TOut* __restrict__ Y, int H, float eps) {
     __shared__ float red[32];
-    pdl_trigger(); pdl_wait();
+    trace_pt(TR_LN, 0); pdl_trigger(); pdl_wait(); trace_pt(TR_LN, 1);
     const float* x = X + (size_t)blockIdx.x * H;
     float s = 0.f;
     for (int i = threadIdx.x; i < H; i += blockDim.x) s += x[i];
@@ -126,7 +126,7 @@ residual_reduce_ln_kernel(float* __restrict__ X, const float* __restrict__ P, in
                           TOut* __restrict__ Y, int H, float eps) {
     extern __shared__ float buf[];
     __shared__ float red[32];
-    pdl_trigger(); pdl_wait();
+    trace_pt(TR_REDUCE_LN, 0); pdl_trigger(); pdl_wait(); trace_pt(TR_REDUCE_LN, 1);
     float* x = X + (size_t)blockIdx.x * H;
     const float* p = P + (size_t)blockIdx.x * H;
     // 16-byte lanes: with H = 1024 every thread owns one float4, so the residual, the bias and all split partials of the
@@ -149,6 +149,7 @@ residual_reduce_ln_kernel(float* __restrict__ X, const float* __restrict__ P, in
     smem_layernorm(buf, w, b, H, eps, red);
     TOut* y = Y + (size_t)blockIdx.x * H;
     for (int c = threadIdx.x; c < H; c += blockDim.x) y[c] = from_f32<TOut>(buf[c]);
+    trace_pt(TR_REDUCE_LN, 2);
 }
 
 template <typename TOut>
@@ -160,7 +161,7 @@ head_norms_kernel(const float* __restrict__ X, const int* __restrict__ row_index
                   float eps) {
     extern __shared__ float buf[];
     __shared__ float red[32];
-    pdl_trigger(); pdl_wait();
+    trace_pt(TR_HEAD, 0); pdl_trigger(); pdl_wait(); trace_pt(TR_HEAD, 1);
     const int i = blockIdx.x;
     const int r = row_index ? row_index[i] : i;
     const float* x = X + (size_t)r * H;
@@ -254,7 +255,7 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
     __shared__ __align__(16) float qs[kHeadDim], ks[kHeadDim], vs[kHeadDim];
     __shared__ float pm[4], pl[4];
     __shared__ float pacc[4][kHeadDim];
-    pdl_trigger(); pdl_wait();
+    trace_pt(TR_ATTN, 0); pdl_trigger(); pdl_wait(); trace_pt(TR_ATTN, 1);
     const int H = heads * kHeadDim;
     // work items = (active row, head); the grid may be capped below M*heads (engine option "attn_ctas_per_sm") so that the
     // kernel leaves registers free for GEMM CTAs of a concurrent decode branch: then each CTA walks several items
@@ -366,6 +367,7 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
     }
     __syncthreads();                                  // qs/ks/vs/pacc are reused by the next item
     }
+    trace_pt(TR_ATTN, 2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -494,7 +496,7 @@ sample_kernel(const float* __restrict__ logits, int ld, const int* __restrict__ 
     __shared__ float red[32];
     __shared__ int redi[32];
     __shared__ float scan_part[256];
-    pdl_trigger(); pdl_wait();
+    trace_pt(TR_SAMPLE, 0); pdl_trigger(); pdl_wait(); trace_pt(TR_SAMPLE, 1);
     const int tid = threadIdx.x;
     const int slot = active[blockIdx.x];
     const int n = S.n_gen[slot];
@@ -774,6 +776,8 @@ sample_kernel(const float* __restrict__ logits, int ld, const int* __restrict__ 
 // ================================================================================================
 // launchers
 // ================================================================================================
+XTTS_TRACE_SETTER(trace_set_gpt)
+
 void launch_init_slots(const SlotInit* init, const int* pages, int n, SlotArrays a, cudaStream_t st) {
     if (n <= 0) return;
     ProfScope ps(KF_MISC, st, 0, (double)n * (sizeof(SlotInit) + 8.0 * a.max_pages + 4.0 * a.seen_words));

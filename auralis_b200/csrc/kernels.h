@@ -42,6 +42,10 @@ bool decode_chain_supported(int M, int H, int FF);
 void launch_decode_chain(const DecodeChainArgs& a, cudaStream_t st, bool pdl);
 bool gemm_tc_init(std::string* err);   // resolves cuTensorMapEncodeTiled; false -> err filled
 
+void trace_set_gemm(TraceBuf b);     // per-translation-unit setters of the debug timeline buffer (common.cuh)
+void trace_set_gpt(TraceBuf b);
+void trace_set_conv(TraceBuf b);
+
 void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------

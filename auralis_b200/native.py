@@ -75,7 +75,7 @@ ABI_SYMBOLS = [
     "xtts_last_error", "xtts_version", "xtts_create", "xtts_destroy", "xtts_load_weight", "xtts_finalize_weights",
     "xtts_set_speaker", "xtts_get_speaker", "xtts_condition", "xtts_submit", "xtts_cancel", "xtts_poll", "xtts_fetch",
     "xtts_set_option", "xtts_get_stats", "xtts_sync", "xtts_get_kernel_profile", "xtts_device_timer", "xtts_vocode", "xtts_vocode_window", "xtts_gpt_prefill", "xtts_gpt_teacher_forced",
-    "xtts_debug_gemm", "xtts_debug_sample",
+    "xtts_debug_gemm", "xtts_debug_sample", "xtts_debug_trace",
 ]
 
 _lib = None
@@ -115,6 +115,7 @@ def load_library(path: Optional[str] = None):
     lib.xtts_gpt_teacher_forced.argtypes = [vp, i32p, i32, i32, i32p, i32, C.POINTER(XttsSampling), f32p, f32p, i32p]
     lib.xtts_debug_gemm.argtypes = [vp, i32, f32p, f32p, f32p, f32p, f32p, i32, i32, i32, i32, i32, f32p]
     lib.xtts_debug_sample.argtypes = [vp, f32p, C.POINTER(C.c_uint8), i32, i32, C.POINTER(XttsSampling), i32, i32p]
+    lib.xtts_debug_trace.argtypes = [vp, i32, C.POINTER(C.c_uint64), i32]
     for s in ABI_SYMBOLS:
         if s not in ("xtts_last_error", "xtts_version"):
             getattr(lib, s).restype = C.c_int
@@ -293,6 +294,23 @@ class NativeEngine:
         ms = C.c_double(0.0)
         self._chk(self.lib.xtts_device_timer(self.h, 1, C.byref(ms)), "device_timer(stop)")
         return float(ms.value)
+
+    def trace_start(self):
+        rc = self.lib.xtts_debug_trace(self.h, 1, None, 0)
+        if rc < 0:
+            self._chk(rc, "debug_trace(start)")
+
+    def trace_stop(self, cap: int = 1 << 20) -> np.ndarray:
+        """-> [n, 4] int64: (ns, kernel id, phase, last-CTA flag) sorted by time; grid size in column 4 of the raw word"""
+        buf = np.zeros((cap, 2), np.uint64)
+        n = self.lib.xtts_debug_trace(self.h, 0, buf.ctypes.data_as(C.POINTER(C.c_uint64)), cap)
+        if n < 0:
+            self._chk(n, "debug_trace(stop)")
+        b = buf[:n]
+        out = np.stack([b[:, 0].astype(np.int64), (b[:, 1] >> np.uint64(32) & np.uint64(0xFF)).astype(np.int64),
+                        (b[:, 1] & np.uint64(0xFF)).astype(np.int64), (b[:, 1] >> np.uint64(8) & np.uint64(1)).astype(np.int64),
+                        (b[:, 1] >> np.uint64(40)).astype(np.int64)], axis=1)
+        return out[np.argsort(out[:, 0], kind="stable")]
 
     def kernel_profile(self) -> Dict[str, dict]:
         """{family: {ms, flops, bytes, launches}} accumulated since option "profile" was switched on."""

@@ -182,6 +182,10 @@ int xtts_gpt_teacher_forced(xtts_engine* e, const int32_t* text_ids, int32_t n_t
 /* GEMM under test: mode 0 = fp32 CUDA-core, 1 = bf16 tcgen05.  A [M,K], W [N,K], bias [N] or NULL, resid [M,N] or NULL */
 int xtts_debug_gemm(xtts_engine* e, int32_t mode, const float* A, const float* W, const float* bias, const float* resid,
                     float* out, int32_t M, int32_t N, int32_t K, int32_t gelu, int32_t iters, float* ms_per_iter);
+/* debug timeline: op 1 arms %globaltimer stamps in the decode / vocoder kernels (first and last CTA: entry, dependency
+ * resolved, exit), op 0 disarms and copies up to `cap` records [n][2] u64 = (ns, id<<32 | grid<<40 | last<<8 | phase) into
+ * `out`; returns the count (>= 0) or a negative error.  Nothing is serialised: shows the step as it really runs. */
+int xtts_debug_trace(xtts_engine* e, int32_t op, uint64_t* out, int32_t cap);
 /* sampler under test: logits [B,V]; seen [B,V] (0/1) ; out tokens [B] */
 int xtts_debug_sample(xtts_engine* e, const float* logits, const uint8_t* seen, int32_t B, int32_t V,
                       const xtts_sampling* sp, int32_t step, int32_t* out_tokens);

@@ -14,10 +14,13 @@ from conftest import text_ids, _make_engine
 pytestmark = pytest.mark.gpu
 
 
+NO_STOP = 4095          # an id outside the audio vocabulary: the chunk runs to max_tokens (random-init weights stop at random)
+
+
 def _greedy_replay(orc, dims, cond, ids, toks, penalty=5.0):
     """oracle logits [n,V] for the prefix `toks` (one prefill) -> the oracle's greedy pick at every position + latents"""
     lg, lat = orc.teacher_forced(cond, ids, list(toks))
-    sp = O.SamplingParams(temperature=0.0, repetition_penalty=penalty, max_tokens=len(toks), stop_token=dims.gpt.stop_audio_token)
+    sp = O.SamplingParams(temperature=0.0, repetition_penalty=penalty, max_tokens=len(toks), stop_token=NO_STOP)
     seen = O.prompt_seen_set(dims.gpt)
     picks = []
     for k in range(len(toks)):
@@ -26,15 +29,19 @@ def _greedy_replay(orc, dims, cond, ids, toks, penalty=5.0):
     return np.array(picks), lg.numpy(), lat.numpy()
 
 
-def test_cfg1_full_chunk_fp32_greedy_bit_exact(engine_full, dims_full, state_full, speakers_full):
-    """BASELINE cfg1 at its real size: one 64-char-like request, greedy, fp32 parity mode, the full 605-token chunk.
+@pytest.mark.parametrize("stop", ["model", "never"])
+def test_cfg1_full_chunk_fp32_greedy_bit_exact(engine_full, dims_full, state_full, speakers_full, stop):
+    """BASELINE cfg1 at its real size: one 64-char-like request, greedy, fp32 parity mode, a complete chunk — once ending
+    where the (random-init) model emits the stop token, once with the stop token disabled so that all 605 tokens are decoded.
     Token ids bit-exact against the oracle, latents 1e-3, waveform within the fp32 tolerance (2e-4)."""
     orc = O.GPTOracle(state_full[0], state_full[1], dims_full)
     g = dims_full.gpt
     ids = text_ids(dims_full, 22, 64)                       # ~64 characters of BPE ids
-    sp = Sampling(temperature=0.0, repetition_penalty=5.0, max_tokens=g.max_audio_tokens, stop_token=g.stop_audio_token)
+    sp = Sampling(temperature=0.0, repetition_penalty=5.0, max_tokens=g.max_audio_tokens,
+                  stop_token=g.stop_audio_token if stop == "model" else NO_STOP)
     r, toks, wav, lat = engine_full.run_batch([(1, ids, 0, sp)], timeout_s=600, want_latents=True)[1]
     assert r.n_tokens == len(toks) and 1 <= len(toks) <= g.max_audio_tokens
+    assert stop == "model" or len(toks) == g.max_audio_tokens
     picks, lg, olat = _greedy_replay(orc, dims_full, speakers_full[0][0], ids, toks)
     bad = [(k, int(a), int(b), float(lg[k][b] - lg[k][a])) for k, (a, b) in enumerate(zip(toks, picks)) if a != b]
     print("cfg1 full chunk:", len(toks), "tokens, disagreements", bad[:4], "latent max err", float(np.abs(lat - olat).max()))
@@ -64,7 +71,7 @@ def test_decode_at_bench_batch_rows_in_both_m_tiles(engine_wide_bf16, dims_full,
     n_seq, n_tok = 168, 12
     jobs = []
     for i in range(n_seq):
-        sp = Sampling(temperature=0.0, repetition_penalty=5.0, max_tokens=n_tok, stop_token=g.stop_audio_token)
+        sp = Sampling(temperature=0.0, repetition_penalty=5.0, max_tokens=n_tok, stop_token=NO_STOP)
         jobs.append((i, text_ids(dims_full, 10 + (7 * i) % 70, 1000 + i), i % 3, sp))
     res = eng.run_batch(jobs, timeout_s=300, want_latents=True)
     assert eng.stats().decode_steps >= n_tok - 1
@@ -92,7 +99,7 @@ def test_batched_full_length_tc_vocoder_vs_oracle(engine_wide_bf16, dims_full, s
     jobs = []
     for i in range(8):
         sp = Sampling(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, max_tokens=g.max_audio_tokens,
-                      stop_token=g.stop_audio_token, seed=11, seq_seed=i)
+                      stop_token=NO_STOP, seed=11, seq_seed=i)
         jobs.append((i, text_ids(dims_full, 30 + i, 50 + i), i % 3, sp))
     res = eng.run_batch(jobs, timeout_s=300, want_latents=True)
     for i in range(8):
@@ -117,7 +124,7 @@ def test_mixed_length_batch_tc_vocoder_vs_oracle(engine_wide_bf16, dims_full, st
     lens = rng.randint(150, 606, size=24).tolist()
     jobs = []
     for i, n in enumerate(lens):
-        sp = Sampling(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, max_tokens=n, stop_token=g.stop_audio_token,
+        sp = Sampling(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, max_tokens=n, stop_token=NO_STOP,
                       seed=12, seq_seed=i)
         jobs.append((i, text_ids(dims_full, 20 + i, 80 + i), i % 3, sp))
     res = eng.run_batch(jobs, timeout_s=300, want_latents=True)
