@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libxtts_b200.so")
-SOURCES = ["engine.cu", "gpt_kernels.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "vocoder.cu", "conv1d_tc.cu", "cond.cu"]
+SOURCES = ["engine.cu", "gpt_kernels.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2cta.cu", "vocoder.cu", "conv1d_tc.cu", "cond.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
 

@@ -95,6 +95,7 @@ struct KernelCtx {
     int attn_ctas_per_sm = 0;     // 0 = uncapped decode-attention grid; > 0: at most this many CTAs per SM
     int gemm_decode_bn = 0;       // 0 = heuristic; 32/64/128 forces the tile width of decode-shaped tcgen05 GEMMs
     int conv_epi_groups = 2;      // 1 or 2 epilogue warpgroups in conv1d_tc_kernel
+    int gemm_2cta = 1;            // large shapes (M >= 256) go to the persistent CTA-pair kernel (gemm_tcgen05_2cta.cu)
 };
 #define g_prof (::xtts::kctx().prof)
 #define g_use_pdl (::xtts::kctx().use_pdl)
@@ -102,6 +103,7 @@ struct KernelCtx {
 #define g_attn_ctas_per_sm (::xtts::kctx().attn_ctas_per_sm)
 #define g_gemm_decode_bn (::xtts::kctx().gemm_decode_bn)
 #define g_conv_epi_groups (::xtts::kctx().conv_epi_groups)
+#define g_gemm_2cta (::xtts::kctx().gemm_2cta)
 
 // true the first time it is called with the current CUDA device for this flag set (function attributes are per device)
 inline bool first_on_device(bool (&done)[64]) {

@@ -79,6 +79,63 @@ __device__ __forceinline__ void mma_commit(uint64_t* b) {
 }
 __device__ __forceinline__ float lrelu_s(float v, float slope) { return v > 0.f ? v : v * slope; }
 
+// Transposed-conv epilogue of one 32-column chunk (co-major GEMM columns: 32/U channels x U phases).  r[c*U + p] is channel
+// co0 + c at output step tb + p.  All register indices are compile-time (no local-memory array).
+template <int U>
+__device__ __forceinline__ void convT_store(const uint32_t (&r)[32], const float* __restrict__ sbc, float* __restrict__ out32,
+                                            uint4* __restrict__ out16, int co0, int tb, int Lout, size_t Ls, int lpad_out,
+                                            float scale16, float slope) {
+    constexpr int CPC = 32 / U;
+    const bool inner = tb >= 0 && tb + U <= Lout;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + sbc[i];
+    if (out32) {
+        if (inner) {
+#pragma unroll
+            for (int c = 0; c < CPC; ++c) {
+                float* op = out32 + (size_t)(co0 + c) * Ls + tb;
+                if constexpr (U == 8) {
+                    reinterpret_cast<float4*>(op)[0] = make_float4(v[8 * c], v[8 * c + 1], v[8 * c + 2], v[8 * c + 3]);
+                    reinterpret_cast<float4*>(op)[1] = make_float4(v[8 * c + 4], v[8 * c + 5], v[8 * c + 6], v[8 * c + 7]);
+                } else if constexpr (U == 4) {
+                    reinterpret_cast<float2*>(op)[0] = make_float2(v[4 * c], v[4 * c + 1]);
+                    reinterpret_cast<float2*>(op)[1] = make_float2(v[4 * c + 2], v[4 * c + 3]);
+                } else {
+#pragma unroll
+                    for (int p = 0; p < U; ++p) op[p] = v[U * c + p];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPC; ++c)
+#pragma unroll
+                for (int p = 0; p < U; ++p) {
+                    const int tt = tb + p;
+                    if (tt >= 0 && tt < Lout) out32[(size_t)(co0 + c) * Ls + tt] = v[U * c + p];
+                }
+        }
+    }
+    if (out16) {
+        // atoms [C/8][t][8]: per output step the lane owns CPC consecutive channels; groups of 4 -> 8-byte stores
+        __half* ah = reinterpret_cast<__half*>(out16);
+#pragma unroll
+        for (int p = 0; p < U; ++p) {
+            const int tt = tb + p;
+            if (tt < 0 || tt >= Lout) continue;
+#pragma unroll
+            for (int c4 = 0; c4 < CPC; c4 += 4) {
+                const int co = co0 + c4;
+                __half2 h0 = __floats2half2_rn(lrelu_s(v[(c4 + 0) * U + p] * scale16, slope), lrelu_s(v[(c4 + 1) * U + p] * scale16, slope));
+                __half2 h1 = __floats2half2_rn(lrelu_s(v[(c4 + 2) * U + p] * scale16, slope), lrelu_s(v[(c4 + 3) * U + p] * scale16, slope));
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(ah + (((size_t)(co / 8) * lpad_out + (tt + kAtomPadL)) * 8 + (co % 8))) = pk;
+            }
+        }
+    }
+}
+
 struct ConvTcParams {
     const __half* a16;       // input atoms  [batch][Cin/8][lpad][8]
     const __half* wblob;
@@ -183,21 +240,57 @@ conv1d_tc_kernel(const ConvTcParams P) {
             uint4* out16 = P.out16 ? reinterpret_cast<uint4*>(P.out16) + zo * (size_t)(P.Cr / 8) * P.lpad_out : nullptr;
             float* sb = sbias[lt & 1];
             for (int j = etid; j < P.N; j += EG * 128) {
-                const int co = (n0 + j) % P.Cr;          // GEMM channel -> real output channel (phases of a transposed conv)
+                const int co = P.up ? (n0 + j) / P.up : n0 + j;      // GEMM column -> output channel (transposed conv: co * u + phase)
                 sb[j] = (P.bias ? __ldg(P.bias + co) : 0.f) + (cbias ? __ldg(cbias + co) : 0.f);
             }
-            // geometry of a 32-column chunk: all its GEMM channels belong to one phase (Cr % 32 == 0)
+            // geometry of a 32-column chunk (Conv1d: 32 output channels at the lane's time step)
             auto geom = [&](int item, int& a, int& nc, int& cb, int& t, bool& valid) {
                 a = item / ncn; nc = item - a * ncn;
                 const int srow = T0 + a * 128 + q * 32 + lane;
-                const int cbg = n0 + nc * 32;
-                const int phase = P.up ? cbg / P.Cr : 0;
-                cb = cbg - phase * P.Cr;
-                t = P.up ? srow * P.up + phase - P.up / 2 : srow;
-                valid = srow < row_limit && t >= 0 && t < Lout_i;
+                cb = n0 + nc * 32;
+                t = srow;
+                valid = srow < row_limit && t < Lout_i;
             };
             int a, nc, cb, t; bool valid;
             geom(grp, a, nc, cb, t, valid);
+            if (P.up) {
+                // ---- ConvTranspose1d: GEMM column n' = co * u + phase (co-major), GEMM row s -> output steps
+                // s*u - u/2 + [0, u).  A 32-column chunk is 32/u channels x all u phases: per channel the lane holds u
+                // CONSECUTIVE output steps, stored as whole vectors (whole 32-byte sectors once a warp's neighbouring lanes
+                // have written theirs) instead of one float per phase pass.
+                asm volatile("bar.sync 1, %0;" ::"r"(EG * 128) : "memory");
+                const int ab_ = lt % nbuf;
+                bar_wait(&tmem_full[ab_], (uint32_t)((lt / nbuf) & 1), 4);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int u = P.up;
+#pragma unroll 1
+                for (int item = grp; item < nitems; item += EG) {
+                    const int a2 = item / ncn, nc2 = item - a2 * ncn;
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab_ * acc_cols + a2 * P.N + nc2 * 32);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const int srow = T0 + a2 * 128 + q * 32 + lane;
+                    if (srow >= row_limit) continue;
+                    const float* sbc = sb + nc2 * 32;
+                    const int co0 = (n0 + nc2 * 32) / u;
+                    const int tb = srow * u - u / 2;                     // first output step of this lane
+                    if (u == 8) convT_store<8>(r, sbc, out32, out16, co0, tb, Lout_i, Ls, P.lpad_out, P.scale16, P.slope_out);
+                    else if (u == 4) convT_store<4>(r, sbc, out32, out16, co0, tb, Lout_i, Ls, P.lpad_out, P.scale16, P.slope_out);
+                    else convT_store<2>(r, sbc, out32, out16, co0, tb, Lout_i, Ls, P.lpad_out, P.scale16, P.slope_out);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                bar_arrive(&tmem_empty[ab_]);
+                continue;
+            }
             if (has_res && valid) {
                 const float* rp = resid + (size_t)cb * Ls + t;
 #pragma unroll
@@ -470,7 +563,7 @@ void launch_convT_tc(const __half* a16, const __half* wblob, const ConvTcPlan& p
     if (Lin <= 0 || batch <= 0) return;
     double Lsum = 0;
     for (int i = 0; i < batch; ++i) Lsum += item_len ? item_len[i] : Lin;
-    if (!pl.ok || (u & 1) || Cr % 32 != 0) throw CudaError("convT_tc: unsupported geometry");
+    if (!pl.ok || (u != 2 && u != 4 && u != 8) || Cr % 32 != 0) throw CudaError("convT_tc: unsupported geometry");
     ConvTcParams P{};
     P.a16 = a16; P.wblob = wblob; P.bias = bias; P.cbias = cbias; P.resid = nullptr; P.out32 = out32; P.out16 = out16;
     P.Cin = Cin; P.Cout = u * Cr; P.L = Lin; P.lpad = lpad_in; P.K = 2; P.dil = 1; P.mode = CONV_STORE; P.slope_out = slope_out;
@@ -480,14 +573,15 @@ void launch_convT_tc(const __half* a16, const __half* wblob, const ConvTcPlan& p
     launch_tc_common(P, pl, Lin + 1, batch, item_len, 4.0 * Cin * Cr * Lsum * u, by, st);
 }
 
-// ConvTranspose1d weight [Cin][Cr][2u] fp32 -> two-tap phase blob: W'[p*Cr+co][ci][0] = w[ci][co][p+u] (x[s-1]),
-//                                                                     W'[p*Cr+co][ci][1] = w[ci][co][p]   (x[s])
+// ConvTranspose1d weight [Cin][Cr][2u] fp32 -> two-tap phase blob, GEMM column n' = co*u + p (co-major: the u phases of a
+// channel are adjacent columns, so an epilogue lane holds u consecutive output steps of it):
+//   W'[co*u+p][ci][0] = w[ci][co][p+u] (x[s-1]),   W'[co*u+p][ci][1] = w[ci][co][p] (x[s])
 void convT_tc_pack(const float* w, int Cin, int Cr, int u, const ConvTcPlan& pl, __half* blob) {
     std::vector<float> tmp((size_t)u * Cr * Cin * 2);
     for (int p = 0; p < u; ++p)
         for (int co = 0; co < Cr; ++co)
             for (int ci = 0; ci < Cin; ++ci) {
-                const size_t o = (((size_t)p * Cr + co) * Cin + ci) * 2;
+                const size_t o = (((size_t)co * u + p) * Cin + ci) * 2;
                 tmp[o + 0] = w[((size_t)ci * Cr + co) * (2 * u) + p + u];
                 tmp[o + 1] = w[((size_t)ci * Cr + co) * (2 * u) + p];
             }

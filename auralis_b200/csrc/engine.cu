@@ -260,6 +260,14 @@ private:
     //   mu     — all GPU state and work issue: held by the scheduler thread for one iteration at a time and by
     //            the synchronous entry points (weights, speakers, debug calls)
     std::mutex mu, q_mu, pin_mu;
+    // std::mutex is not fair: the scheduler thread re-takes `mu` a few hundred nanoseconds after releasing it and would
+    // starve a synchronous API call (stats, set_speaker, options) for as long as the engine stays busy.  API calls
+    // announce themselves; the scheduler waits for them between two iterations.
+    std::atomic<int> api_waiting{0};
+    struct ApiLock {
+        Engine* e; std::unique_lock<std::mutex> lk;
+        explicit ApiLock(Engine* en) : e(en) { e->api_waiting.fetch_add(1); lk = std::unique_lock<std::mutex>(e->mu); e->api_waiting.fetch_sub(1); }
+    };
     std::condition_variable cv_work, cv_done;
     std::deque<std::shared_ptr<Sequence>> pending;      // q_mu
     std::deque<std::shared_ptr<Sequence>> waiting;      // scheduler thread only: accepted, not yet admitted
@@ -289,6 +297,7 @@ private:
     DBuf<unsigned long long> d_trace; DBuf<unsigned> d_trace_n;      // debug timeline (xtts_debug_trace)
     int n_micro = 2;              // option "microbatches": decode rows are split into this many concurrent branches
     int micro_min_rows = 48;      // option "microbatch_min_rows": below this many active rows the step stays single-branch
+    int stagger_us = 0;           // option "branch_stagger_us": branch i starts i * this many microseconds late
     int eager_steps_done = 0;
     std::map<int, cudaGraphExec_t> decode_graphs;
     std::map<int, unsigned long long> graph_kernels;
@@ -542,7 +551,7 @@ Engine::~Engine() {
 // weights
 // ================================================================================================
 void Engine::load_weight(const char* name, const float* data, const int64_t* shape, int ndim) {
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     if (finalized) throw std::runtime_error("weights already finalized");
     HostTensor t;
     t.shape.assign(shape, shape + ndim);
@@ -654,7 +663,7 @@ void Engine::make_conv(ConvW& c, const std::string& prefix, bool transposed, boo
 }
 
 void Engine::finalize_weights() {
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     if (finalized) return;
     CUDA_CHECK(cudaSetDevice(cfg.device));
     const auto& c = cfg;
@@ -755,7 +764,7 @@ void Engine::finalize_weights() {
 // speakers
 // ================================================================================================
 void Engine::set_speaker(int slot, const float* cond, const float* g) {
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     require_finalized();
     if (slot < 0 || slot >= S) throw std::runtime_error("speaker slot out of range");
     CUDA_CHECK(cudaSetDevice(cfg.device));
@@ -778,7 +787,7 @@ void Engine::finish_speaker(int slot) {
 
 // get_conditioning_latents (XTTSv2.py:409-468) on the GPU
 void Engine::condition(int slot, const float* w22, int64_t n22, const float* w16, int64_t n16, int cond_len, int chunk_len) {
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     require_finalized();
     if (!conditioner) throw std::runtime_error("checkpoint has no conditioning encoder / speaker encoder weights");
     if (slot < 0 || slot >= S) throw std::runtime_error("speaker slot out of range");
@@ -792,7 +801,7 @@ void Engine::condition(int slot, const float* w22, int64_t n22, const float* w16
 }
 
 void Engine::get_speaker(int slot, float* cond, float* g) {
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     if (slot < 0 || slot >= S || !spk_valid[slot]) throw std::runtime_error("speaker slot not set");
     CUDA_CHECK(cudaSetDevice(cfg.device));
     const size_t nc = (size_t)cfg.n_cond_latents * H;
@@ -1065,6 +1074,7 @@ void Engine::decode_step(const std::vector<int>& active) {
             for (int i = 1; i < nmb; ++i) CUDA_CHECK(cudaStreamWaitEvent(st_mb[i], ev_fork, 0));
             for (int i = 0, r0 = 0; i < nmb; ++i) {
                 const int Mi = M / nmb + (i < M % nmb ? 1 : 0);
+                if (i > 0 && stagger_us > 0) launch_stream_delay((unsigned)(i * stagger_us) * 1000u, st_mb[i], false);
                 decode_layers_rows(r0, Mi, st_mb[i], i == 0, decode_ctx_sum * (double)Mi / (double)M);
                 r0 += Mi;
             }
@@ -1647,6 +1657,7 @@ void Engine::loop() {
     t_kctx = &kctx_;                                   // this thread issues this engine's work, and only this engine's
     cudaSetDevice(cfg.device);
     while (true) {
+        for (int spin = 0; api_waiting.load() > 0 && spin < 20000; ++spin) std::this_thread::yield();   // API calls go first
         std::vector<uint64_t> cancels;
         {
             std::unique_lock<std::mutex> q(q_mu);
@@ -1789,7 +1800,7 @@ void Engine::set_option(const std::string& k, int64_t v) {
         cv_work.notify_all();
         return;
     }
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     if (k == "d2h_wav") d2h_wav = v != 0;
     else if (k == "tc_vocoder") use_tc_vocoder = v != 0;
     else if (k == "conv_epi_groups") g_conv_epi_groups = v >= 2 ? 2 : 1;
@@ -1801,10 +1812,12 @@ void Engine::set_option(const std::string& k, int64_t v) {
     else if (k == "voc_segment") voc_segment = (int)std::max<int64_t>(0, v);
     else if (k == "voc_sms") voc_sms = (int)std::max<int64_t>(0, v);
     else if (k == "voc_batch") voc_max_items = (int)std::max<int64_t>(1, std::min<int64_t>(v, kVocMaxItems));
+    else if (k == "gemm_2cta") g_gemm_2cta = v != 0;
     else if (k == "cuda_graphs") use_graphs = v != 0;
     else if (k == "pdl") { use_pdl = v != 0; drop_graphs(); }
     else if (k == "splitk") { use_splitk = v != 0; drop_graphs(); }
     else if (k == "decode_chain") { use_chain = v != 0; drop_graphs(); }
+    else if (k == "branch_stagger_us") { stagger_us = (int)std::max<int64_t>(0, std::min<int64_t>(v, 1000)); drop_graphs(); }
     else if (k == "microbatches" || k == "microbatch_min_rows") {
         if (k == "microbatches") n_micro = std::max<int>(1, std::min<int64_t>(v, kMaxMicro)); else micro_min_rows = (int)std::max<int64_t>(2, v);
         drop_graphs();
@@ -1820,14 +1833,14 @@ void Engine::set_option(const std::string& k, int64_t v) {
 }
 
 void Engine::get_stats(xtts_stats* s) {
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     s->kernel_launches = g_launch_count - launch_base; s->decode_steps = st_decode_steps; s->prefill_rows = st_prefill_rows;
     s->tokens_generated = st_tokens; s->samples_generated = st_samples; s->gpt_ms = st_gpt_ms; s->vocoder_ms = st_voc_ms;
     s->cond_ms = st_cond_ms; s->hbm_bytes_weights = weight_bytes;
 }
 
 void Engine::kernel_profile(xtts_kernel_profile* out) {
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     CUDA_CHECK(cudaSetDevice(cfg.device));
     CUDA_CHECK(cudaStreamSynchronize(st));
     CUDA_CHECK(cudaStreamSynchronize(st_voc));
@@ -1844,7 +1857,7 @@ void Engine::kernel_profile(xtts_kernel_profile* out) {
 // Stopwatch on the engine stream.  The decode branches fork from and join back into `st` inside a step; the vocoder stream
 // is joined into `st` explicitly before the stop event, so that event completes after all device work submitted so far.
 void Engine::device_timer(int op, double* ms) {
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     CUDA_CHECK(cudaSetDevice(cfg.device));
     if (!ev_t0) { CUDA_CHECK(cudaEventCreate(&ev_t0)); CUDA_CHECK(cudaEventCreate(&ev_t1)); }
     if (op == 0) {
@@ -1865,7 +1878,7 @@ void Engine::device_timer(int op, double* ms) {
 // debug timeline: op 1 arms the trace points of the decode / vocoder kernels (common.cuh), op 0 disarms and copies the
 // records out: [n][2] u64 = (globaltimer ns, id << 32 | grid << 40 | last-CTA flag << 8 | phase).  Returns the record count.
 int Engine::trace(int op, uint64_t* out, int cap) {
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     CUDA_CHECK(cudaSetDevice(cfg.device));
     CUDA_CHECK(cudaStreamSynchronize(st)); CUDA_CHECK(cudaStreamSynchronize(st_voc));
     if (op == 1) {
@@ -1901,7 +1914,7 @@ void Engine::sync_idle() {
 // ================================================================================================
 void Engine::vocode_sync(const float* latents, int T, int speaker, float* wav, int* n_out, const char* stage,
                          float* stage_out, int64_t stage_cap) {
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     require_finalized();
     CUDA_CHECK(cudaSetDevice(cfg.device));
     if (T <= 0 || T > voc_max_T) throw std::runtime_error("vocoder: latent count out of range");
@@ -1918,7 +1931,7 @@ void Engine::vocode_sync(const float* latents, int T, int speaker, float* wav, i
 // z-frames [z0, z0 + nz) of the chunk `latents` [T] as a window of its own (what the scheduler does while a chunk decodes):
 // wav [nz * hop].  Samples further than the vocoder's receptive field from an inner window edge equal the whole chunk's.
 void Engine::vocode_window_sync(const float* latents, int T, int speaker, int z0, int nz, float* wav) {
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     require_finalized();
     CUDA_CHECK(cudaSetDevice(cfg.device));
     if (T <= 0 || T > voc_max_T) throw std::runtime_error("vocoder: latent count out of range");
@@ -1933,7 +1946,7 @@ void Engine::vocode_window_sync(const float* latents, int T, int speaker, int z0
 
 void Engine::gpt_prefill_sync(const int32_t* text, int n_text, int speaker, const int32_t* audio, int n_audio,
                               float* hidden_out, float* logits_out, float* latents_out) {
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     require_finalized();
     if (!running.empty() || !waiting.empty() || !voc_pending.empty() || !voc_inflight.empty()) throw std::runtime_error("debug entry points need an idle engine");
     CUDA_CHECK(cudaSetDevice(cfg.device));
@@ -1969,7 +1982,7 @@ void Engine::gpt_prefill_sync(const int32_t* text, int n_text, int speaker, cons
 
 void Engine::gpt_teacher_forced_sync(const int32_t* text, int n_text, int speaker, const int32_t* forced, int n,
                                      const xtts_sampling& sp, float* logits_out, float* latents_out, int32_t* sampled_out) {
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     require_finalized();
     if (!running.empty() || !waiting.empty() || !voc_pending.empty() || !voc_inflight.empty()) throw std::runtime_error("debug entry points need an idle engine");
     if (n < 1 || n > CAP) throw std::runtime_error("teacher_forced: n out of range");
@@ -2002,7 +2015,7 @@ void Engine::gpt_teacher_forced_sync(const int32_t* text, int n_text, int speake
 
 void Engine::debug_gemm(int mode, const float* A, const float* W, const float* bias, const float* resid, float* out, int M,
                         int N, int K, int gelu, int iters, float* ms) {
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     CUDA_CHECK(cudaSetDevice(cfg.device));
     DBuf<float> dA, dW, db, dr, dout;
     dA.alloc((size_t)M * K); dW.alloc((size_t)N * K); dout.alloc((size_t)M * N);
@@ -2040,7 +2053,7 @@ void Engine::debug_gemm(int mode, const float* A, const float* W, const float* b
 
 void Engine::debug_sample(const float* logits, const uint8_t* seen, int Bn, int Vn, const xtts_sampling& sp, int step,
                           int32_t* out) {
-    std::lock_guard<std::mutex> lk(mu);
+    ApiLock lk(this);
     if (!running.empty() || !waiting.empty() || !voc_pending.empty() || !voc_inflight.empty()) throw std::runtime_error("debug entry points need an idle engine");
     if (Bn < 1 || Bn > B || Vn != V) throw std::runtime_error("debug_sample: bad batch or vocabulary size");
     CUDA_CHECK(cudaSetDevice(cfg.device));

@@ -612,6 +612,10 @@ void launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const f
                          void* out, int M, int N, int K, int flags, cudaStream_t st, bool pdl) {
     if (M <= 0 || N <= 0) return;
     if (K % BK != 0 || N % 32 != 0) throw CudaError("gemm_bf16_tc: need K % 64 == 0 and N % 32 == 0");
+    if (g_gemm_2cta && !pdl && gemm_2cta_supported(M, N, K)) {       // prefill-shaped: persistent CTA pairs
+        launch_gemm_bf16_2cta(A, W, bias, resid, out, M, N, K, flags, st);
+        return;
+    }
     if (!g_encode) {
         std::string err;
         if (!gemm_tc_init(&err)) throw CudaError(err);

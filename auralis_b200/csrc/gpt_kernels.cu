@@ -78,6 +78,20 @@ init_slots_kernel(const SlotInit* __restrict__ init, const int* __restrict__ pag
         a.block_tables[(size_t)slot * a.max_pages + i] = i < d.n_pages ? pg[i] : 0;
 }
 
+// Holds its stream for `ns` nanoseconds (one thread).  Used once per decode step to start the second row branch half a layer
+// late: two identical branches otherwise run in lock-step — both in the HBM-bound attention at the same time (each at half
+// the bandwidth), then both in the latency-bound GEMM chain (contending for SMs) — instead of one's attention under the
+// other's GEMMs.
+__global__ void stream_delay_kernel(unsigned ns) {
+    pdl_trigger(); pdl_wait();
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while (t - t0 < (unsigned long long)ns && t - t0 < 2000000ull);
+}
+
 struct GatherIdx { int idx[kVocMaxItems]; };
 __global__ void gather_rows_kernel(const float* __restrict__ src, const GatherIdx G, int width, float* __restrict__ dst) {
     const float* s = src + (size_t)G.idx[blockIdx.x] * width;
@@ -782,6 +796,12 @@ void launch_init_slots(const SlotInit* init, const int* pages, int n, SlotArrays
     if (n <= 0) return;
     ProfScope ps(KF_MISC, st, 0, (double)n * (sizeof(SlotInit) + 8.0 * a.max_pages + 4.0 * a.seen_words));
     init_slots_kernel<<<n, 128, 0, st>>>(init, pages, a);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+
+void launch_stream_delay(unsigned ns, cudaStream_t st, bool pdl) {
+    if (ns == 0) return;
+    launch_k(stream_delay_kernel, dim3(1), dim3(32), 0, st, pdl, ns);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 

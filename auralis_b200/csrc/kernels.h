@@ -22,6 +22,10 @@ void launch_gemm_f32(const float* A, const float* W, const float* bias, const fl
 // that way executes griddepcontrol.wait before touching its predecessor's outputs
 void launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const float* resid,
                          void* out, int M, int N, int K, int flags, cudaStream_t st, bool pdl = false);
+// large-shape path (gemm_tcgen05_2cta.cu): persistent CTA pairs (cta_group::2), 256 x 256 tiles, double-buffered TMEM
+bool gemm_2cta_supported(int M, int N, int K);
+void launch_gemm_bf16_2cta(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const float* resid,
+                           void* out, int M, int N, int K, int flags, cudaStream_t st);
 void launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, float* partials, int M, int N, int K,
                                 int splits, cudaStream_t st, bool pdl = false);
 
@@ -201,6 +205,8 @@ struct SlotArrays {       // per-slot device arrays (mutable view of SampleState
 };
 // pages: [n][max_pages] page ids of each sequence (first n_pages valid)
 void launch_init_slots(const SlotInit* init, const int* pages, int n, SlotArrays a, cudaStream_t st);
+// occupies `st` for ns nanoseconds (branch stagger of the decode step, see gpt_kernels.cu)
+void launch_stream_delay(unsigned ns, cudaStream_t st, bool pdl = false);
 // dst[i][0..width) = src[idx[i]][0..width)   (i < n <= kVocMaxItems): speaker-bias rows of a vocoder batch
 void launch_gather_rows(const float* src, const int* idx_host, int n, int width, float* dst, cudaStream_t st);
 // y[c] = W[c,:] . g + b[c]   (speaker conditioning 1x1 convs)

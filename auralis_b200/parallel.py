@@ -61,13 +61,14 @@ def _host_buffer(tag: str, n: int, pinned: bool) -> torch.Tensor:
 
 
 def gather_waveforms(local: Dict[int, np.ndarray], n_items: int, device: torch.device | None = None,
-                     group=None, dst: int | None = None) -> List[np.ndarray] | None:
+                     group=None, dst: int | None = None, tag: str = "") -> List[np.ndarray] | None:
     """All-gather {item index -> waveform} from every rank; returns the list in item order on every rank.
 
     Wire format: int64 [2*k] (index, length) table, then one flat fp32 payload per rank, both max-padded so a
     single `all_gather_into_tensor` moves each.  With NCCL the payload lives in HBM (`device`), so the
     transfer is GPU->NVSwitch->GPU; with gloo (CPU tests) it stays on the host.
-    `dst`: only that rank copies the gathered payload back to the host and returns the list (others return None)."""
+    `dst`: only that rank copies the gathered payload back to the host and returns the list (others return None).
+    `tag`: names the cached staging buffers — callers that overlap consecutive gathers alternate two tags."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return [local[i] for i in range(n_items)]
@@ -85,7 +86,7 @@ def gather_waveforms(local: Dict[int, np.ndarray], n_items: int, device: torch.d
     dist.all_gather_into_tensor(tables, tpad, group=group)
     on_gpu = dev.type == "cuda"
     # stage this rank's audio in one (cached, pinned) host buffer -> a single H2D copy
-    stage = _host_buffer("send", max(1, max_n), on_gpu)
+    stage = _host_buffer("send" + tag, max(1, max_n), on_gpu)
     off = 0
     for i in idx:
         n = int(local[i].shape[0])
@@ -98,7 +99,7 @@ def gather_waveforms(local: Dict[int, np.ndarray], n_items: int, device: torch.d
         return None
     tables = tables.cpu().view(world, -1)
     if on_gpu:                                    # one D2H into a cached pinned buffer; the results are views into it
-        recv = _host_buffer("recv", allp.numel(), True)
+        recv = _host_buffer("recv" + tag, allp.numel(), True)
         recv.copy_(allp, non_blocking=False)
         allp_h = recv.view(world, -1).numpy()
     else:

@@ -48,18 +48,13 @@ def find_best_split_point(text: str, target_pos: int, window_size: int = 30) -> 
     return best_pos
 
 
-_SENT_END = re.compile(r"([.!?。！？؟…]+[\"'”’)\]]*)(\s+|$)")
+from .sentencizer import sentencize as _sentencize      # spaCy's sentencizer + blank-language tokenizer rules, restated
 
 
-def sentencize(text: str) -> List[str]:
-    """Rule-based sentence boundaries (what spaCy's `sentencizer` pipe does: split after . ! ? and CJK stops)."""
-    out, last = [], 0
-    for m in _SENT_END.finditer(text):
-        out.append(text[last:m.end(1)])
-        last = m.end()
-    if last < len(text):
-        out.append(text[last:])
-    return [s for s in (x.strip() for x in out) if s]
+def sentencize(text: str, lang: str = "en") -> List[str]:
+    """Sentences as spaCy's rule-based `sentencizer` yields them for the language object the reference picks
+    (`config/tokenizer.py:25-48`); see sentencizer.py."""
+    return _sentencize(text, lang)
 
 
 def split_sentence(text: str, lang: str, text_split_length: int = 250) -> List[str]:
@@ -69,7 +64,7 @@ def split_sentence(text: str, lang: str, text_split_length: int = 250) -> List[s
     if len(text) <= text_split_length:
         return [text]
     splits, current, current_length = [], [], 0
-    for sentence_text in sentencize(text):
+    for sentence_text in sentencize(text, lang):
         n = len(sentence_text)
         if current_length + n <= text_split_length:
             current.append(sentence_text)

@@ -171,6 +171,8 @@ def main():
     ap.add_argument("--microbatches", type=int, default=2, help="concurrent decode branches per step (engine option; unfused decode only)")
     ap.add_argument("--engine-opt", action="append", default=[], help="extra engine option key=value (repeatable)")
     ap.add_argument("--decode-chain", type=int, default=0, help="1 = fused persistent per-layer chain kernel in the decode step")
+    ap.add_argument("--voc-segment", type=int, default=96, help="tokens per vocoder window while a chunk decodes (engine option voc_segment; 0 = whole chunks at the end)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra arms (ragged lengths, cfg3 time-to-first-audio, fp32 parity mode, strong scaling)")
     ap.add_argument("--sweep", action="store_true", help="option sweeps only: skip the e2e arm and the CPU baseline (the line says so; not a headline run)")
     ap.add_argument("--small", action="store_true", help="tiny geometry (plumbing check only; not a valid bench number)")
     args = ap.parse_args()
@@ -245,11 +247,13 @@ def main():
     n_chunks = sum(len(c) for c in reqs_chunks)
     max_tok = min(args.max_tokens, dims.gpt.max_audio_tokens)
 
-    def device_step(step_idx: int):
+    def device_step(step_idx: int, lengths=None, chunk_lists=None):
+        """lengths: per-chunk max_tokens (the ragged arm); chunk_lists: another request set (the strong-scaling arm)"""
         jobs, sid = [], 0
-        for ri, chunks in enumerate(reqs_chunks):
+        for ri, chunks in enumerate(chunk_lists if chunk_lists is not None else reqs_chunks):
             for ci, ids in enumerate(chunks):
-                sp = native.Sampling(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, max_tokens=max_tok,
+                sp = native.Sampling(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0,
+                                     max_tokens=max_tok if lengths is None else int(lengths[sid]),
                                      stop_token=dims.gpt.stop_audio_token, seed=SEED + step_idx, seq_seed=sid, vocode=True)
                 jobs.append((sid, ids, spk_slots[ri % 4], sp))
                 sid += 1
@@ -262,11 +266,30 @@ def main():
         if max_tok != dims.gpt.max_audio_tokens:
             eng.dims.gpt.max_audio_tokens = max_tok          # reduced runs only (flagged in config)
         outs = tts.generate_speech_batch(reqs)
-        # DP epilogue: gather every rank's waveforms on all ranks (rank 0 is the consumer) over NCCL
+        # DP epilogue: every rank's waveforms go to rank 0 (the consumer) over NCCL.  Like the output shipping of a serving
+        # system it runs BESIDE the next step: a worker thread issues the gather on its own CUDA stream while this thread
+        # already generates step i + 1; the timed region ends only when the last gather has landed (gather_pool.join).
         if world > 1:
             local_w = {rank * len(outs) + i: o.array for i, o in enumerate(outs)}
-            parallel.gather_waveforms(local_w, world * len(outs), torch.device("cuda", local), dst=0)
+            gather_jobs.append(gather_pool.submit(_gather, local_w, world * len(outs), step_idx))
         return sum(o.array.shape[0] for o in outs), sum(len(t) for t in texts)
+
+    import concurrent.futures
+    gather_pool = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+    gather_jobs = []
+    gather_stream = torch.cuda.Stream(device=local) if world > 1 else None
+
+    def _gather(local_w, n_items, step_idx):
+        torch.cuda.set_device(local)
+        with torch.cuda.stream(gather_stream):
+            out = parallel.gather_waveforms(local_w, n_items, torch.device("cuda", local), dst=0, tag=f"s{step_idx % 2}")
+            gather_stream.synchronize()
+        return 0 if out is None else sum(int(w.shape[0]) for w in out)
+
+    def gather_join():
+        for f in gather_jobs:
+            f.result(timeout=600)
+        gather_jobs.clear()
 
     def log(msg):
         if rank == 0:
@@ -283,11 +306,13 @@ def main():
         barrier + synchronize), the second behind the last step's work."""
         for i in range(warm):
             fn(i)
+        gather_join()
         barrier()
         t0w = time.time(); t0 = time.perf_counter()
         ne.timer_start()
         acc = [fn(warm + i) for i in range(steps)]
         dt_ev = ne.timer_stop_ms() * 1e-3
+        gather_join()                      # (e2e arm, N > 1) the last step's waveform gather is inside the timed region
         barrier()
         dt = time.perf_counter() - t0
         return dt_ev, dt, acc, (t0w, time.time())
@@ -297,6 +322,7 @@ def main():
     ne.set_option("d2h_wav", 0)
     ne.set_option("microbatches", args.microbatches)
     ne.set_option("decode_chain", args.decode_chain)
+    ne.set_option("voc_segment", args.voc_segment)
     for kv in args.engine_opt:
         ne.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     eng.park_poller(True)                 # the device arm drives the native completion queue directly
@@ -327,8 +353,38 @@ def main():
     prof = ne.kernel_profile()
     ne.set_option("profile", 0)
     ne.set_option("microbatches", args.microbatches)
+    ne.set_option("voc_segment", args.voc_segment)
     for kv in args.engine_opt:
         ne.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+
+    extras = {}
+    do_extras = not (args.sweep or args.no_extras or args.small)
+    # ---- extra arm 1: LENGTH-DISTRIBUTED chunks (per-chunk max_tokens ~ U(150, 605)): what real weights produce — the stop
+    # token lands at a different step per chunk, so chunks finish (and reach the vocoder) at different times and in ragged
+    # batches.  Device-resident like `value`.
+    if do_extras:
+        rng_len = np.random.RandomState(SEED + 17)
+        lens = rng_len.randint(150, max_tok + 1, size=n_chunks)
+        device_step(900, lens)
+        barrier()
+        ne.timer_start()
+        acc_r = [device_step(901 + i, lens) for i in range(2)]
+        dt_r = ne.timer_stop_ms() * 1e-3
+        extras["ragged"] = {"value": sum(a[0] for a in acc_r) / 24000.0 / dt_r, "unit": "audio-s/s", "steps": 2,
+                            "ms_per_step": 1e3 * dt_r / 2, "tokens_per_s": sum(a[1] for a in acc_r) / dt_r,
+                            "workload": f"same {n_chunks} chunks per GPU, per-chunk max_tokens ~ U(150, {max_tok}) (mean {float(lens.mean()):.0f}); "
+                                        "chunks finish at different steps, the vocoder batches ragged windows"}
+        log(f"ragged arm: {extras['ragged']['value']:.1f} audio-s/s")
+    # ---- extra arm 2 (N > 1): STRONG scaling — the north-star headline shape, 64 x 1k-char requests in TOTAL
+    if do_extras and world > 1:
+        per_rank = max(1, 64 // world)
+        strong_chunks = reqs_chunks[:per_rank]
+        device_step(950, None, strong_chunks)
+        barrier()
+        ne.timer_start()
+        acc_s = [device_step(951 + i, None, strong_chunks) for i in range(2)]
+        dt_s = ne.timer_stop_ms() * 1e-3
+        extras["_strong_local"] = (sum(a[0] for a in acc_s) / 24000.0, dt_s, per_rank)
     eng.park_poller(False)
     log("profile step done")
 
@@ -343,6 +399,37 @@ def main():
     h2d = sum(len(ids) * 4 for chunks in reqs_chunks for ids in chunks)
     d2h = samples_e2e // max(1, args.steps) * 4 + n_chunks * max_tok * 4
 
+    # ---- extra arm 3 (N = 1): cfg3 time-to-first-audio — 64 mixed-length requests streamed at t = 0 through the public async
+    # API, without and with streaming pieces (first piece after 58 tokens = 2.7 s of audio)
+    if do_extras and world == 1:
+        import asyncio
+        rng3 = np.random.RandomState(11)
+        lens3 = rng3.randint(128, 4097, size=64)
+        texts3 = [make_text(int(n), 5000 + i) for i, n in enumerate(lens3)]
+
+        async def one(i, t0):
+            req = TTSRequest(text=texts3[i], speaker_files=spk_bytes[i % 4], language="en", stream=True, seed=SEED + i)
+            gen = await tts.generate_speech_async(req)
+            first = None
+            async for chunk in gen:
+                if first is None:
+                    first = time.perf_counter() - t0
+            return first
+
+        async def run3():
+            t0 = time.perf_counter()
+            return await asyncio.gather(*[one(i, t0) for i in range(len(texts3))])
+        ttfa = {}
+        for early in (0, 58):
+            eng.early_emit_tokens = early
+            tt = np.array(loop.run_until_complete(run3()))
+            ttfa[f"early_{early}"] = {"p50_s": float(np.percentile(tt, 50)), "p99_s": float(np.percentile(tt, 99))}
+        eng.early_emit_tokens = 0
+        extras["cfg3_ttfa"] = {"requests": 64, "chars": "128..4096", "speakers": 4, **ttfa,
+                               "note": "early_58: streaming pieces (xtts_sampling.early_tokens = 58): the first 2.7 s of a request's audio "
+                                       "leave the engine ~65 decode steps after admission instead of after the whole 605-token chunk"}
+        log(f"cfg3 time-to-first-audio: {ttfa}")
+
     # ---- max over ranks, aggregate over ranks
     if world > 1:
         t = torch.tensor([dt_dev, dt_e2e, wall_dev], dtype=torch.float64, device="cuda")
@@ -351,6 +438,15 @@ def main():
         s = torch.tensor([samples_dev, tokens_dev, samples_e2e], dtype=torch.float64, device="cuda")
         torch.distributed.all_reduce(s, op=torch.distributed.ReduceOp.SUM)
         samples_dev, tokens_dev, samples_e2e = float(s[0]), float(s[1]), float(s[2])
+    if "_strong_local" in extras:
+        a_s, dt_s, per_rank = extras.pop("_strong_local")
+        t = torch.tensor([dt_s], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        a = torch.tensor([a_s], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(a, op=torch.distributed.ReduceOp.SUM)
+        extras["strong"] = {"value": float(a[0]) / float(t[0]), "unit": "audio-s/s", "requests_total": per_rank * world,
+                            "requests_per_gpu": per_rank, "steps": 2, "ms_per_step": 1e3 * float(t[0]) / 2,
+                            "workload": "north-star headline shape: 64 x 1k-char requests in total, split over the GPUs (strong scaling)"}
     if rank != 0:
         loop.run_until_complete(tts.shutdown())
         if world > 1:
@@ -425,6 +521,8 @@ def main():
                              "behind the last step's work); max over ranks; e2e: host wall clock around the public API calls",
                    "host_wall_ms_per_step": 1e3 * wall_dev / args.steps,
                    "engine_opts": args.engine_opt,
+                   "vocoder": (f"windows of {args.voc_segment} tokens vocoded on a second stream while the chunk decodes (ragged batches of up to 32 windows)"
+                               if args.voc_segment else "whole chunks, vocoded when they end (ragged batches)"),
                    "decode_step": ("per layer: paged attention + one persistent chain kernel (out-proj, LN2, fc+gelu, down-proj, LN1, next QKV)"
                                    if args.decode_chain else f"one launch per GEMM/LayerNorm, {args.microbatches} concurrent row branches"),
                    "roofline_timing": "CUDA events around every launch on the engine stream, in one extra identical step right after the timed ones (decode step: event-record nodes inside the replayed graph, single row branch, no PDL overlap; prefill/vocoder: eager)",
@@ -436,12 +534,43 @@ def main():
         "gpu_launches": int(st.kernel_launches),
         "clocks": clocks, "roofline": roof,
     }
+    # ---- extra arm 4 (N = 1): the PARITY mode — fp32 CUDA-core GEMMs / convs, fp32 KV (greedy token ids bit-exact against
+    # the oracle in tests/test_gpu_gpt.py, tests/test_gpu_bench_regime.py) on the same workload, one timed step
+    if do_extras and world == 1:
+        loop.run_until_complete(tts.shutdown())
+        eng32 = XTTSv2Engine(dims, state[0], state[1], device=local, precision="fp32",
+                             max_concurrency=min(256, max(8, n_chunks_est)), max_speakers=8)
+        ne32 = eng32.native
+        spk32 = [tts.loop.run_until_complete(eng32.get_audio_conditioning(b, 60, 30, 4))[0].slot for b in spk_bytes]
+        ne32.set_option("d2h_wav", 0)
+
+        def step32(i):
+            jobs, sid = [], 0
+            for ri, chunks in enumerate(reqs_chunks):
+                for ids in chunks:
+                    jobs.append((sid, ids, spk32[ri % 4], native.Sampling(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0,
+                                 max_tokens=max_tok, stop_token=dims.gpt.stop_audio_token, seed=SEED + i, seq_seed=sid, vocode=True)))
+                    sid += 1
+            res = eng32.run_batch_direct(jobs, timeout_s=900, want_wav=False)
+            return sum(r.n_samples for (r, _, _, _) in res.values())
+        step32(0)
+        torch.cuda.synchronize()
+        ne32.timer_start()
+        n32 = step32(1)
+        dt32 = ne32.timer_stop_ms() * 1e-3
+        extras["fp32_value"] = n32 / 24000.0 / dt32
+        extras["fp32"] = {"value": n32 / 24000.0 / dt32, "unit": "audio-s/s", "steps": 1, "ms_per_step": 1e3 * dt32,
+                          "mode": "precision=fp32: CUDA-core fp32 GEMMs and convs, fp32 KV — the mode whose greedy token ids are bit-exact vs the oracle"}
+        log(f"fp32 parity mode: {extras['fp32_value']:.1f} audio-s/s")
+        tts.loop.run_until_complete(eng32.shutdown())
+    line.update(extras)
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if args.sweep:
         line["sweep"] = "option sweep: e2e arm and CPU baseline skipped — not a headline run"
     print(json.dumps(line), flush=True)
-    loop.run_until_complete(tts.shutdown())
+    if not (do_extras and world == 1):
+        loop.run_until_complete(tts.shutdown())
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -147,6 +147,8 @@ int xtts_fetch(xtts_engine* e, uint64_t seq_id, int32_t* tokens, float* wav, flo
  *                         GEMM / LayerNorm with "microbatches" concurrent row branches (default: measured faster)
  *   "microbatches"        1..4 concurrent branches the decode step's rows are split into (default 2)
  *   "microbatch_min_rows" steps with fewer active rows stay single-branch (default 48)
+ *   "gemm_2cta"           1 (default) = GEMMs with M >= 256 rows (prefill, conditioning) run on the persistent CTA-pair kernel
+ *                         (cta_group::2, 256x256 tiles, double-buffered TMEM), 0 = the one-tile-per-CTA kernel
  *   "voc_segment"         m > 0: a chunk is vocoded in windows of m tokens WHILE it decodes (the vocoder runs on its own
  *                         stream beside the decode step), 0 = one window per chunk when it ends.  Same samples either way.
  *   "voc_sms"             SMs the vocoder's persistent conv kernels may occupy while a decode step is in flight (0 = all)

@@ -78,6 +78,7 @@ class _Doc:
 
 class _Lang:
     """Minimal `spacy.lang.xx.Xx()` look-alike: add_pipe("sentencizer") + __call__ -> doc.sents."""
+    lang = "en"
 
     def __init__(self):
         self.pipe_names = []
@@ -88,8 +89,8 @@ class _Lang:
         self.pipe_names.append(name)
 
     def __call__(self, text):
-        from auralis_b200.text import sentencize          # the restated punctuation rule (see module docstring)
-        return _Doc(sentencize(text))
+        from auralis_b200.text import sentencize          # the restated spaCy rules (see module docstring)
+        return _Doc(sentencize(text, self.lang))
 
 
 def _raising(name):
@@ -124,7 +125,7 @@ def load():
         put("spacy", sp); put("spacy.lang", spl)
         for code, cls in (("ar", "Arabic"), ("en", "English"), ("es", "Spanish"), ("ja", "Japanese"), ("zh", "Chinese")):
             m = types.ModuleType(f"spacy.lang.{code}")
-            setattr(m, cls, _Lang)
+            setattr(m, cls, type(cls, (_Lang,), {"lang": code}))       # the language object decides the tokenizer rules
             put(f"spacy.lang.{code}", m)
     try:
         mod = importlib.import_module("auralis.models.xttsv2.config.tokenizer")

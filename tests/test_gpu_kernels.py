@@ -40,9 +40,12 @@ def _bf16(x):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1, 384, 128), (7, 128, 512), (150, 3072, 1024), (300, 1024, 4096),
-                                   (33, 1056, 1024), (257, 4096, 1024)])
+                                   (33, 1056, 1024), (257, 4096, 1024), (256, 256, 64), (1000, 3072, 1024), (513, 288, 192),
+                                   (2304, 1056, 1024)])
 def test_gemm_bf16_tcgen05(engine_small, M, N, K):
-    """tcgen05 path vs an fp64 product of the bf16-rounded operands (isolates layout/descriptor bugs from rounding)."""
+    """tcgen05 path vs an fp64 product of the bf16-rounded operands (isolates layout/descriptor bugs from rounding).
+    M >= 256 and N >= 256 shapes run on the persistent CTA-pair kernel (cta_group::2): full and ragged 256 x 256 tiles, more
+    tiles than clusters (the double-buffered accumulators and the stage ring wrap), N tails that are not a multiple of 256."""
     rng = np.random.RandomState(M * 13 + N)
     A = rng.randn(M, K).astype(np.float32)
     W = (rng.randn(N, K) * 0.05).astype(np.float32)
@@ -66,6 +69,11 @@ def test_gemm_tcgen05_speed_report(engine_small):
         for mode in (0, 1):
             _, ms = engine_small.debug_gemm(mode, A, W, None, None, False, iters=20)
             print(f"gemm mode={mode} M={M} N={N} K={K}: {ms * 1e3:.1f} us  {2.0 * M * N * K / ms / 1e9:.2f} TFLOP/s")
+        if M >= 256:
+            engine_small.set_option("gemm_2cta", 0)
+            _, ms = engine_small.debug_gemm(1, A, W, None, None, False, iters=20)
+            engine_small.set_option("gemm_2cta", 1)
+            print(f"gemm one-tile-per-CTA kernel M={M} N={N} K={K}: {ms * 1e3:.1f} us  {2.0 * M * N * K / ms / 1e9:.2f} TFLOP/s")
 
 
 def _oracle_tokens(logits, seen, sp, step):
