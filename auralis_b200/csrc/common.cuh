@@ -173,6 +173,39 @@ __device__ __forceinline__ void trace_pt(int id, int phase) {
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---- fine-grained dependencies along the decode chain.  `griddepcontrol.wait` resolves only when the whole prerequisite
+// grid has drained and flushed (measured: 1.2-5 us after its last CTA's exit, tools/trace_step.py).  With a DepFlag the
+// consumer instead polls a counter that every producer CTA bumps (release) right after its own stores: ~1 us.  The consumer
+// kernel is still launched with the PDL attribute (so it is resident early) but never executes griddepcontrol.wait; ordering
+// with everything older follows transitively, because its producer waited on ITS producer's flag before finishing.
+// wait == nullptr: fall back to griddepcontrol.wait.  One thread of the CTA calls dep_wait, then the CTA synchronises.
+struct DepFlag {
+    const unsigned* wait = nullptr;     // counter of the producer kernel (device)
+    unsigned target = 0;                // its value once every producer CTA has arrived
+    unsigned* arrive = nullptr;         // this kernel's own counter (nullptr: nobody polls it)
+};
+__device__ __forceinline__ void dep_wait(const DepFlag& d, int tag) {
+    if (d.wait == nullptr) { pdl_wait(); return; }
+    const long long t0 = clock64();
+    int polls = 0;
+    unsigned v;
+    while (true) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(d.wait) : "memory");
+        if (v >= d.target) break;
+        if ((++polls & 255) == 0 && clock64() - t0 > 4000000000LL) {
+            printf("dep_wait watchdog (tag %d, block %d, have %u want %u)\n", tag, blockIdx.x, v, d.target);
+            __trap();
+        }
+    }
+}
+// every thread that stored results calls this; `leader` (one thread, after a CTA barrier) publishes the CTA's arrival
+__device__ __forceinline__ void dep_arrive(const DepFlag& d, bool leader) {
+    if (d.arrive == nullptr) return;
+    __threadfence();
+    __syncthreads();
+    if (leader) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(d.arrive) : "memory");
+}
+
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
     cudaLaunchConfig_t cfg{};

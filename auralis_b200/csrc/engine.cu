@@ -298,6 +298,8 @@ private:
     int n_micro = 2;              // option "microbatches": decode rows are split into this many concurrent branches
     int micro_min_rows = 48;      // option "microbatch_min_rows": below this many active rows the step stays single-branch
     int stagger_us = 0;           // option "branch_stagger_us": branch i starts i * this many microseconds late
+    bool use_dep_flags = true;    // option "dep_flags": counter dependencies along the decode chain instead of grid-wide waits
+    DBuf<unsigned> d_dep;         // [kMaxMicro][layers][7] dependency counters (zeroed by the first kernel of every step)
     int eager_steps_done = 0;
     std::map<int, cudaGraphExec_t> decode_graphs;
     std::map<int, unsigned long long> graph_kernels;
@@ -334,7 +336,7 @@ private:
     void layers_forward(int M, bool prefill, int nseq, int max_nq);
     void head_and_sample(int M, const int* row_index, const int* slots_dev, const int* lat_pos, int advance_ctx, bool do_sample,
                          bool pdl_first = true);
-    void decode_layers_rows(int r0, int Mi, cudaStream_t s, bool pdl_first, double ctx_sum);
+    void decode_layers_rows(int r0, int Mi, cudaStream_t s, bool pdl_first, double ctx_sum, int branch);
     void decode_layers_chain(int M);
     void init_slots(const std::vector<Sequence*>& seqs, const int32_t* forced, int n_forced);
     void release_pages(Sequence& s);
@@ -451,6 +453,7 @@ Engine::Engine(const xtts_config& c) : cfg(c) {
     wX.alloc(Mmax * H); wQKV.alloc(Mmax * 3 * H); wLOG.alloc((size_t)std::max(NSLOT, CAP + 1) * Vpad);
     if (bf16) wPART.alloc((size_t)8 * NSLOT * H);
     d_chain_sync.alloc(64); d_chain_sync.zero(st);
+    d_dep.alloc((size_t)kMaxMicro * L * 7); d_dep.zero(st);
     if (bf16) { wXn16.alloc(Mmax * H); wATT16.alloc(Mmax * H); wFF16.alloc(Mmax * FF); wY16.alloc((size_t)std::max(NSLOT, CAP + 1) * H); }
     else { wXn32.alloc(Mmax * H); wATT32.alloc(Mmax * H); wFF32.alloc(Mmax * FF); wY32.alloc((size_t)std::max(NSLOT, CAP + 1) * H); }
 
@@ -1000,7 +1003,7 @@ void Engine::prefill(const std::vector<Sequence*>& seqs) {
 // Fast-mode decode layers for rows [r0, r0 + Mi) of the step on stream `s`.  Every work buffer is row-major and the
 // KV cache is per slot, so disjoint row ranges are independent: decode_step runs several of these as concurrent
 // branches (micro-batches), which lets one branch's HBM-bound attention overlap another's latency-bound GEMM chain.
-void Engine::decode_layers_rows(int r0, int Mi, cudaStream_t s, bool pdl_first, double ctx_sum) {
+void Engine::decode_layers_rows(int r0, int Mi, cudaStream_t s, bool pdl_first, double ctx_sum, int branch) {
     float* X = wX.p + (size_t)r0 * H;
     __nv_bfloat16* Xn = wXn16.p + (size_t)r0 * H;
     float* QKV = wQKV.p + (size_t)r0 * 3 * H;
@@ -1009,20 +1012,40 @@ void Engine::decode_layers_rows(int r0, int Mi, cudaStream_t s, bool pdl_first, 
     float* PART = wPART.p + (size_t)r0 * 8 * H;          // [splits <= 8][Mi][H] inside this branch's own region
     const int* act = d_active.p + r0;
     const bool pdl = use_pdl;
-    launch_layernorm<__nv_bfloat16>(X, layers[0]->ln1w.p, layers[0]->ln1b.p, Xn, Mi, H, cfg.ln_eps, s, pdl && pdl_first);
+    // Dependency counters of this branch (option "dep_flags"): 7 per layer — ln1, qkv, attn, o-proj, ln2, fc, down-proj done.
+    // Every kernel polls its producer's counter instead of waiting for that whole grid to drain (common.cuh: DepFlag);
+    // build_decode_rows zeroed them at the start of the step.
+    const bool flags = use_dep_flags && d_dep.p != nullptr;
+    unsigned* F = flags ? d_dep.p + (size_t)branch * L * 7 : nullptr;
+    auto dep = [&](int l_wait, int e_wait, unsigned target, int l_arr, int e_arr) {
+        DepFlag d;
+        if (flags) { d.wait = F + l_wait * 7 + e_wait; d.target = target; d.arrive = F + l_arr * 7 + e_arr; }
+        return d;
+    };
+    DepFlag d0;
+    if (flags) d0.arrive = F + 0;                        // the step's first LayerNorm: full wait (the row build), then counts in
+    launch_layernorm<__nv_bfloat16>(X, layers[0]->ln1w.p, layers[0]->ln1b.p, Xn, Mi, H, cfg.ln_eps, s, pdl && pdl_first, d0);
+    unsigned n_ln1 = (unsigned)Mi;
     for (int l = 0; l < L; ++l) {
         Layer& ly = *layers[l];
-        launch_gemm_bf16_tc(Xn, ly.qkv.w16.p, ly.qkv.b.p, nullptr, QKV, Mi, ly.qkv.N, ly.qkv.K, 0, s, pdl);
-        launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(QKV, act, Mi, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p,
-                                                         ATT, NH, s, ctx_sum, pdl);
-        launch_gemm_bf16_tc_splitk(ATT, ly.o.w16.p, PART, Mi, H, H, 4, s, pdl);
-        launch_residual_reduce_layernorm<__nv_bfloat16>(X, PART, 4, ly.o.b.p, ly.ln2w.p, ly.ln2b.p, Xn, Mi, H, cfg.ln_eps, s, pdl);
-        launch_gemm_bf16_tc(Xn, ly.fc.w16.p, ly.fc.b.p, nullptr, FFb, Mi, ly.fc.N, ly.fc.K, GEMM_GELU | GEMM_OUT_BF16, s, pdl);
-        launch_gemm_bf16_tc_splitk(FFb, ly.proj.w16.p, PART, Mi, H, FF, 8, s, pdl);
+        const unsigned n_qkv = (unsigned)launch_gemm_bf16_tc(Xn, ly.qkv.w16.p, ly.qkv.b.p, nullptr, QKV, Mi, ly.qkv.N, ly.qkv.K, 0, s, pdl,
+                                                             dep(l, 0, n_ln1, l, 1));
+        const unsigned n_att = (unsigned)launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(QKV, act, Mi, d_ctx_len.p, d_block_tables.p, max_pages,
+                                                                                       k16[l]->p, v16[l]->p, ATT, NH, s, ctx_sum, pdl,
+                                                                                       dep(l, 1, n_qkv, l, 2));
+        const unsigned n_o = (unsigned)launch_gemm_bf16_tc_splitk(ATT, ly.o.w16.p, PART, Mi, H, H, 4, s, pdl, dep(l, 2, n_att, l, 3));
+        launch_residual_reduce_layernorm<__nv_bfloat16>(X, PART, 4, ly.o.b.p, ly.ln2w.p, ly.ln2b.p, Xn, Mi, H, cfg.ln_eps, s, pdl,
+                                                        dep(l, 3, n_o, l, 4));
+        const unsigned n_fc = (unsigned)launch_gemm_bf16_tc(Xn, ly.fc.w16.p, ly.fc.b.p, nullptr, FFb, Mi, ly.fc.N, ly.fc.K,
+                                                            GEMM_GELU | GEMM_OUT_BF16, s, pdl, dep(l, 4, (unsigned)Mi, l, 5));
+        const unsigned n_pr = (unsigned)launch_gemm_bf16_tc_splitk(FFb, ly.proj.w16.p, PART, Mi, H, FF, 8, s, pdl, dep(l, 5, n_fc, l, 6));
         const bool last = (l + 1 == L);
+        DepFlag dl = dep(l, 6, n_pr, last ? l : l + 1, 0);
+        if (last) dl.arrive = nullptr;                   // the head kernel behind it takes a full dependency
         launch_residual_reduce_layernorm<__nv_bfloat16>(X, PART, 8, ly.proj.b.p, last ? nullptr : layers[l + 1]->ln1w.p,
                                                         last ? nullptr : layers[l + 1]->ln1b.p, last ? nullptr : Xn, Mi, H,
-                                                        cfg.ln_eps, s, pdl);
+                                                        cfg.ln_eps, s, pdl, dl);
+        n_ln1 = (unsigned)Mi;
     }
 }
 
@@ -1067,7 +1090,8 @@ void Engine::decode_step(const std::vector<int>& active) {
     const bool chain = fast && use_chain && decode_chain_supported(M, H, FF);
     const int nmb = (fast && !chain && n_micro > 1 && M >= micro_min_rows) ? std::min(n_micro, (int)kMaxMicro) : 1;
     auto enqueue = [&] {
-        launch_build_decode_rows(d_active.p, M, d_last_tok.p, d_n_gen.p, tables(), wX.p, st, use_pdl);
+        launch_build_decode_rows(d_active.p, M, d_last_tok.p, d_n_gen.p, tables(), wX.p, st, use_pdl,
+                                 (fast && use_dep_flags) ? d_dep.p : nullptr, kMaxMicro * L * 7);
         if (nmb > 1) {
             // fork: every branch starts after the row build; join: head + sampler run once over all rows
             CUDA_CHECK(cudaEventRecord(ev_fork, st));
@@ -1075,7 +1099,7 @@ void Engine::decode_step(const std::vector<int>& active) {
             for (int i = 0, r0 = 0; i < nmb; ++i) {
                 const int Mi = M / nmb + (i < M % nmb ? 1 : 0);
                 if (i > 0 && stagger_us > 0) launch_stream_delay((unsigned)(i * stagger_us) * 1000u, st_mb[i], false);
-                decode_layers_rows(r0, Mi, st_mb[i], i == 0, decode_ctx_sum * (double)Mi / (double)M);
+                decode_layers_rows(r0, Mi, st_mb[i], i == 0, decode_ctx_sum * (double)Mi / (double)M, i);
                 r0 += Mi;
             }
             for (int i = 1; i < nmb; ++i) {
@@ -1084,7 +1108,9 @@ void Engine::decode_step(const std::vector<int>& active) {
             }
             head_and_sample(M, nullptr, d_active.p, nullptr, 1, true, false);
         } else {
-            if (chain) decode_layers_chain(M); else layers_forward(M, false, 0, 0);
+            if (chain) decode_layers_chain(M);
+            else if (fast) decode_layers_rows(0, M, st, true, decode_ctx_sum, 0);
+            else layers_forward(M, false, 0, 0);
             head_and_sample(M, nullptr, d_active.p, nullptr, 1, true);
         }
     };
@@ -1817,6 +1843,7 @@ void Engine::set_option(const std::string& k, int64_t v) {
     else if (k == "pdl") { use_pdl = v != 0; drop_graphs(); }
     else if (k == "splitk") { use_splitk = v != 0; drop_graphs(); }
     else if (k == "decode_chain") { use_chain = v != 0; drop_graphs(); }
+    else if (k == "dep_flags") { use_dep_flags = v != 0; drop_graphs(); }
     else if (k == "branch_stagger_us") { stagger_us = (int)std::max<int64_t>(0, std::min<int64_t>(v, 1000)); drop_graphs(); }
     else if (k == "microbatches" || k == "microbatch_min_rows") {
         if (k == "microbatches") n_micro = std::max<int>(1, std::min<int64_t>(v, kMaxMicro)); else micro_min_rows = (int)std::max<int64_t>(2, v);

@@ -94,7 +94,7 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const float* __restrict__ bias, const float* resid, void* out, int M, int N, int K, int flags,
-                    int a_box_rows) {
+                    int a_box_rows, const DepFlag dep) {
     // (bias / out / flags are re-pointed below for split-K launches)
     constexpr int STAGES = stages_for(BN);
     constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
@@ -150,7 +150,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_expect_tx(&full_bar[kb], (uint32_t)a_box_rows * BK * 2 + B_BYTES);
                 tma_load_2d(sB + kb * B_BYTES, &tmB, &full_bar[kb], (kb_begin + kb) * BK, n0);
             }
-            pdl_wait();
+            dep_wait(dep, 21);                       // the activations exist (whole predecessor grid, or its counter)
+            if (dep.wait) asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores -> TMA (async proxy) reads
             trace_pt(TR_GEMM, 1);
             for (int kb = 0; kb < pre; ++kb)
                 tma_load_2d(sA + kb * A_BYTES, &tmA, &full_bar[kb], (kb_begin + kb) * BK, m0);
@@ -185,7 +186,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else {
         // ---------------- epilogue: warp (2..5) owns TMEM lanes [32*(warp%4), +32) = tile rows
         const int q = warp & 3;
-        pdl_wait();                                  // this warp reads `resid` and overwrites `out`
+        if (dep.wait == nullptr) pdl_wait();         // this warp reads `resid` and overwrites `out` (with a counter: ordered behind
+                                                     // the producer's wait through tmem_full_bar; such launches carry no resid)
         mbar_wait(&tmem_full_bar, 0, 3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = m0 + q * 32 + lane;
@@ -243,6 +245,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    dep_arrive(dep, threadIdx.x == 0);               // (fence + CTA barrier inside) this CTA's tile is in global memory
     __syncthreads();
     trace_pt(TR_GEMM, 2);
     if (warp == 1) {
@@ -271,8 +274,8 @@ void encode_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, u
 }
 
 template <int BN>
-void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, const float* resid, void* out, int M,
-               int N, int K, int flags, cudaStream_t st, int splits, int a_box_rows, bool pdl) {
+int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, const float* resid, void* out, int M,
+              int N, int K, int flags, cudaStream_t st, int splits, int a_box_rows, bool pdl, const DepFlag& dep) {
     constexpr int STAGES = stages_for(BN);
     constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
     static bool attr_set[64] = {};
@@ -281,8 +284,10 @@ void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
     ProfScope ps(KF_GEMM_TC, st, 2.0 * M * N * K,
                  2.0 * ((double)M * K + (double)N * K) + ((flags & GEMM_OUT_BF16) ? 2.0 : 4.0) * M * N);
-    launch_k(gemm_bf16_tc_kernel<BN>, grid, dim3(kThreads), smem, st, pdl, tmA, tmB, bias, resid, out, M, N, K, flags, a_box_rows);
+    if (dep.wait && (flags & GEMM_RESID)) throw CudaError("gemm_bf16_tc: a counter dependency cannot order a residual read");
+    launch_k(gemm_bf16_tc_kernel<BN>, grid, dim3(kThreads), smem, st, pdl, tmA, tmB, bias, resid, out, M, N, K, flags, a_box_rows, dep);
     COUNT_LAUNCH(); KERNEL_CHECK();
+    return (int)(grid.x * grid.y * grid.z);
 }
 
 
@@ -608,13 +613,13 @@ bool gemm_tc_init(std::string* err) {
     return true;
 }
 
-void launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const float* resid,
-                         void* out, int M, int N, int K, int flags, cudaStream_t st, bool pdl) {
-    if (M <= 0 || N <= 0) return;
+int launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const float* resid,
+                        void* out, int M, int N, int K, int flags, cudaStream_t st, bool pdl, DepFlag dep) {
+    if (M <= 0 || N <= 0) return 0;
     if (K % BK != 0 || N % 32 != 0) throw CudaError("gemm_bf16_tc: need K % 64 == 0 and N % 32 == 0");
-    if (g_gemm_2cta && !pdl && gemm_2cta_supported(M, N, K)) {       // prefill-shaped: persistent CTA pairs
+    if (g_gemm_2cta && !pdl && !dep.wait && !dep.arrive && gemm_2cta_supported(M, N, K)) {       // prefill-shaped: persistent CTA pairs
         launch_gemm_bf16_2cta(A, W, bias, resid, out, M, N, K, flags, st);
-        return;
+        return 0;
     }
     if (!g_encode) {
         std::string err;
@@ -631,16 +636,16 @@ void launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const f
     const int abox = a_box_rows_for(M);
     encode_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint32_t)abox);
     encode_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint32_t)bn);
-    if (bn == 128) launch_bn<128>(tmA, tmB, bias, resid, out, M, N, K, flags, st, 1, abox, pdl);
-    else if (bn == 64) launch_bn<64>(tmA, tmB, bias, resid, out, M, N, K, flags, st, 1, abox, pdl);
-    else launch_bn<32>(tmA, tmB, bias, resid, out, M, N, K, flags, st, 1, abox, pdl);
+    if (bn == 128) return launch_bn<128>(tmA, tmB, bias, resid, out, M, N, K, flags, st, 1, abox, pdl, dep);
+    if (bn == 64) return launch_bn<64>(tmA, tmB, bias, resid, out, M, N, K, flags, st, 1, abox, pdl, dep);
+    return launch_bn<32>(tmA, tmB, bias, resid, out, M, N, K, flags, st, 1, abox, pdl, dep);
 }
 
 
 // split-K variant for the skinny decode GEMMs (N = hidden): partials[z][M][N] = A[:, kz] . W[:, kz]^T, fp32, no epilogue
-void launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, float* partials, int M, int N, int K,
-                                int splits, cudaStream_t st, bool pdl) {
-    if (M <= 0 || N <= 0) return;
+int launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, float* partials, int M, int N, int K,
+                               int splits, cudaStream_t st, bool pdl, DepFlag dep) {
+    if (M <= 0 || N <= 0) return 0;
     if (K % BK != 0 || N % 32 != 0 || splits < 1 || (K / BK) % splits != 0) throw CudaError("gemm_bf16_tc_splitk: bad shape");
     if (!g_encode) { std::string err; if (!gemm_tc_init(&err)) throw CudaError(err); }
     const int mt = ceil_div(M, BM);
@@ -652,9 +657,9 @@ void launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, 
     const int abox = a_box_rows_for(M);
     encode_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint32_t)abox);
     encode_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint32_t)bn);
-    if (bn == 128) launch_bn<128>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox, pdl);
-    else if (bn == 64) launch_bn<64>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox, pdl);
-    else launch_bn<32>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox, pdl);
+    if (bn == 128) return launch_bn<128>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox, pdl, dep);
+    if (bn == 64) return launch_bn<64>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox, pdl, dep);
+    return launch_bn<32>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox, pdl, dep);
 }
 
 

@@ -21,7 +21,7 @@ namespace {
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 6;
 constexpr int kThreads = 192;
 constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2;      // per CTA and stage: 16 KB + 16 KB
-constexpr size_t kSmem = (size_t)STAGES * (A_BYTES + B_BYTES) + 1024;
+constexpr size_t kSmem = (size_t)STAGES * (A_BYTES + B_BYTES) + 4 * 32 * 33 * sizeof(float) + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -106,6 +106,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
+    float* stage = reinterpret_cast<float*>(smem + STAGES * (A_BYTES + B_BYTES));     // 4 epilogue warps x [32][33] fp32
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
@@ -176,7 +177,6 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&tmem_full[ab], (uint32_t)((lt >> 1) & 1), 4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int row = m0 + q * 32 + lane;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t r[32];
@@ -197,43 +197,31 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(&tmem_empty[ab], 0);
                 }
+                // ---- store through a per-warp 32 x 33 transpose in shared memory: TMEM hands every lane one ROW (32 consecutive
+                // columns); written as it comes, one store instruction would touch 32 different 128-byte lines (16 B each).
+                // After the transpose a lane owns one COLUMN, so each instruction writes one row's 128 contiguous bytes
+                // (one transaction instead of 32) and the residual / bias reads are coalesced the same way.
                 const int nb = n0 + c * 32;
-                if (row < M && nb < N) {
-                    float v[32];
+                float* stg = stage + (warp - 2) * (32 * 33);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float x = __uint_as_float(r[i]);
-                        if (bias) x += __ldg(bias + nb + i);
+                for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(r[i]);
+                __syncwarp();
+                if (nb < N) {
+                    const int col = nb + lane;
+                    const float bv = bias ? __ldg(bias + col) : 0.f;
+                    const int row0 = m0 + q * 32;
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int grow = row0 + rr;
+                        if (grow >= M) break;
+                        float x = stg[rr * 33 + lane] + bv;
                         if (flags & GEMM_GELU) x = gelu_new(x);
-                        v[i] = x;
-                    }
-                    if (flags & GEMM_RESID) {
-                        const float4* rp = reinterpret_cast<const float4*>(resid + (size_t)row * N + nb);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 t = rp[i];
-                            v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-                        }
-                    }
-                    if (flags & GEMM_OUT_BF16) {
-                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)row * N + nb;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            uint4 pk;
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
-                            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-                            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                            reinterpret_cast<uint4*>(op)[i] = pk;
-                        }
-                    } else {
-                        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)row * N + nb);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        if (flags & GEMM_RESID) x += resid[(size_t)grow * N + col];
+                        if (flags & GEMM_OUT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[(size_t)grow * N + col] = __float2bfloat16_rn(x);
+                        else reinterpret_cast<float*>(out)[(size_t)grow * N + col] = x;
                     }
                 }
+                __syncwarp();
             }
         }
     }

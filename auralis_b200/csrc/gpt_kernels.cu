@@ -40,8 +40,11 @@ __global__ void build_rows_kernel(const RowDesc* __restrict__ rows, GptTables t,
 }
 
 __global__ void build_decode_rows_kernel(const int* __restrict__ active, const int* __restrict__ last_tok,
-                                         const int* __restrict__ n_gen, GptTables t, float* __restrict__ X) {
+                                         const int* __restrict__ n_gen, GptTables t, float* __restrict__ X,
+                                         unsigned* __restrict__ dep_flags, int n_flags) {
     trace_pt(TR_ROWS, 0); pdl_trigger(); pdl_wait(); trace_pt(TR_ROWS, 1);
+    // first kernel of the step, behind a full dependency wait: the step's dependency counters start from zero
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_flags; i += blockDim.x) dep_flags[i] = 0u;
     const int slot = active[blockIdx.x];
     const int H = t.H;
     const float4* a = reinterpret_cast<const float4*>(t.wte + (size_t)last_tok[slot] * H);
@@ -105,9 +108,12 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const GatherId
 template <typename TOut>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ X, const float* __restrict__ w, const float* __restrict__ b,
-                 TOut* __restrict__ Y, int H, float eps) {
+                 TOut* __restrict__ Y, int H, float eps, const DepFlag dep) {
     __shared__ float red[32];
-    trace_pt(TR_LN, 0); pdl_trigger(); pdl_wait(); trace_pt(TR_LN, 1);
+    trace_pt(TR_LN, 0); pdl_trigger();
+    if (threadIdx.x == 0) dep_wait(dep, 31);
+    __syncthreads();
+    trace_pt(TR_LN, 1);
     const float* x = X + (size_t)blockIdx.x * H;
     float s = 0.f;
     for (int i = threadIdx.x; i < H; i += blockDim.x) s += x[i];
@@ -118,6 +124,7 @@ layernorm_kernel(const float* __restrict__ X, const float* __restrict__ w, const
     const float rstd = 1.0f / sqrtf(var + eps);
     TOut* y = Y + (size_t)blockIdx.x * H;
     for (int i = threadIdx.x; i < H; i += blockDim.x) y[i] = from_f32<TOut>((x[i] - mean) * rstd * w[i] + b[i]);
+    dep_arrive(dep, threadIdx.x == 0);
 }
 
 __device__ __forceinline__ void smem_layernorm(float* buf, const float* __restrict__ w, const float* __restrict__ b,
@@ -137,10 +144,13 @@ template <typename TOut>
 __global__ void __launch_bounds__(256)
 residual_reduce_ln_kernel(float* __restrict__ X, const float* __restrict__ P, int splits, size_t split_stride,
                           const float* __restrict__ bias, const float* __restrict__ w, const float* __restrict__ b,
-                          TOut* __restrict__ Y, int H, float eps) {
+                          TOut* __restrict__ Y, int H, float eps, const DepFlag dep) {
     extern __shared__ float buf[];
     __shared__ float red[32];
-    trace_pt(TR_REDUCE_LN, 0); pdl_trigger(); pdl_wait(); trace_pt(TR_REDUCE_LN, 1);
+    trace_pt(TR_REDUCE_LN, 0); pdl_trigger();
+    if (threadIdx.x == 0) dep_wait(dep, 32);
+    __syncthreads();
+    trace_pt(TR_REDUCE_LN, 1);
     float* x = X + (size_t)blockIdx.x * H;
     const float* p = P + (size_t)blockIdx.x * H;
     // 16-byte lanes: with H = 1024 every thread owns one float4, so the residual, the bias and all split partials of the
@@ -159,10 +169,11 @@ residual_reduce_ln_kernel(float* __restrict__ X, const float* __restrict__ P, in
         *reinterpret_cast<float4*>(buf + c) = v;
     }
     __syncthreads();
-    if (Y == nullptr) return;
+    if (Y == nullptr) { dep_arrive(dep, threadIdx.x == 0); return; }
     smem_layernorm(buf, w, b, H, eps, red);
     TOut* y = Y + (size_t)blockIdx.x * H;
     for (int c = threadIdx.x; c < H; c += blockDim.x) y[c] = from_f32<TOut>(buf[c]);
+    dep_arrive(dep, threadIdx.x == 0);
     trace_pt(TR_REDUCE_LN, 2);
 }
 
@@ -261,7 +272,7 @@ template <typename TKV, typename TOut>
 __global__ void __launch_bounds__(128)
 attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active, const int* __restrict__ ctx_len,
                    const int* __restrict__ block_tables, int max_pages, TKV* __restrict__ kpool, TKV* __restrict__ vpool,
-                   TOut* __restrict__ out, int heads, int n_items) {
+                   TOut* __restrict__ out, int heads, int n_items, const DepFlag dep) {
     constexpr int X = KVec<TKV>::X;
     constexpr int NCH = kHeadDim / X;                 // 16-byte atoms per token row (8 bf16 / 16 fp32)
     constexpr int TPI = 32 / NCH;                     // tokens covered by one warp-wide V load (4 / 2)
@@ -269,7 +280,10 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
     __shared__ __align__(16) float qs[kHeadDim], ks[kHeadDim], vs[kHeadDim];
     __shared__ float pm[4], pl[4];
     __shared__ float pacc[4][kHeadDim];
-    trace_pt(TR_ATTN, 0); pdl_trigger(); pdl_wait(); trace_pt(TR_ATTN, 1);
+    trace_pt(TR_ATTN, 0); pdl_trigger();
+    if (threadIdx.x == 0) dep_wait(dep, 33);
+    __syncthreads();
+    trace_pt(TR_ATTN, 1);
     const int H = heads * kHeadDim;
     // work items = (active row, head); the grid may be capped below M*heads (engine option "attn_ctas_per_sm") so that the
     // kernel leaves registers free for GEMM CTAs of a concurrent decode branch: then each CTA walks several items
@@ -381,6 +395,7 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
     }
     __syncthreads();                                  // qs/ks/vs/pacc are reused by the next item
     }
+    dep_arrive(dep, threadIdx.x == 0);
     trace_pt(TR_ATTN, 2);
 }
 
@@ -823,34 +838,34 @@ void launch_build_rows(const RowDesc* rows, int n_rows, GptTables t, float* X, c
 }
 
 void launch_build_decode_rows(const int* active, int M, const int* last_tok, const int* n_gen, GptTables t,
-                              float* X, cudaStream_t st, bool pdl) {
+                              float* X, cudaStream_t st, bool pdl, unsigned* flags, int n_flags) {
     if (M <= 0) return;
     ProfScope ps(KF_EMBED, st, 0, 12.0 * M * t.H);
-    launch_k(build_decode_rows_kernel, dim3(M), dim3(256), 0, st, pdl, active, last_tok, n_gen, t, X);
+    launch_k(build_decode_rows_kernel, dim3(M), dim3(256), 0, st, pdl, active, last_tok, n_gen, t, X, flags, flags ? n_flags : 0);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 
 template <typename TOut>
 void launch_layernorm(const float* X, const float* w, const float* b, TOut* Y, int M, int H, float eps,
-                      cudaStream_t st, bool pdl) {
+                      cudaStream_t st, bool pdl, DepFlag dep) {
     if (M <= 0) return;
     ProfScope ps(KF_NORM, st, 0, (4.0 + sizeof(TOut)) * M * H);
-    launch_k(layernorm_kernel<TOut>, dim3(M), dim3(256), 0, st, pdl, X, w, b, Y, H, eps);
+    launch_k(layernorm_kernel<TOut>, dim3(M), dim3(256), 0, st, pdl, X, w, b, Y, H, eps, dep);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
-template void launch_layernorm<float>(const float*, const float*, const float*, float*, int, int, float, cudaStream_t, bool);
-template void launch_layernorm<__nv_bfloat16>(const float*, const float*, const float*, __nv_bfloat16*, int, int, float, cudaStream_t, bool);
+template void launch_layernorm<float>(const float*, const float*, const float*, float*, int, int, float, cudaStream_t, bool, DepFlag);
+template void launch_layernorm<__nv_bfloat16>(const float*, const float*, const float*, __nv_bfloat16*, int, int, float, cudaStream_t, bool, DepFlag);
 
 template <typename TOut>
 void launch_residual_reduce_layernorm(float* X, const float* partials, int splits, const float* bias, const float* w,
-                                      const float* b, TOut* Y, int M, int H, float eps, cudaStream_t st, bool pdl) {
+                                      const float* b, TOut* Y, int M, int H, float eps, cudaStream_t st, bool pdl, DepFlag dep) {
     if (M <= 0) return;
     ProfScope ps(KF_NORM, st, 0, (8.0 + 4.0 * splits + sizeof(TOut)) * M * H);
-    launch_k(residual_reduce_ln_kernel<TOut>, dim3(M), dim3(256), H * sizeof(float), st, pdl, X, partials, splits, (size_t)M * H, bias, w, b, Y, H, eps);
+    launch_k(residual_reduce_ln_kernel<TOut>, dim3(M), dim3(256), H * sizeof(float), st, pdl, X, partials, splits, (size_t)M * H, bias, w, b, Y, H, eps, dep);
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
-template void launch_residual_reduce_layernorm<float>(float*, const float*, int, const float*, const float*, const float*, float*, int, int, float, cudaStream_t, bool);
-template void launch_residual_reduce_layernorm<__nv_bfloat16>(float*, const float*, int, const float*, const float*, const float*, __nv_bfloat16*, int, int, float, cudaStream_t, bool);
+template void launch_residual_reduce_layernorm<float>(float*, const float*, int, const float*, const float*, const float*, float*, int, int, float, cudaStream_t, bool, DepFlag);
+template void launch_residual_reduce_layernorm<__nv_bfloat16>(float*, const float*, int, const float*, const float*, const float*, __nv_bfloat16*, int, int, float, cudaStream_t, bool, DepFlag);
 
 template <typename TOut>
 void launch_head_norms(const float* X, const int* row_index, const float* lnf_w, const float* lnf_b,
@@ -879,10 +894,10 @@ template void launch_kv_write<float>(const float*, int, const int*, const int*, 
 template void launch_kv_write<__nv_bfloat16>(const float*, int, const int*, const int*, const int*, const int*, int, __nv_bfloat16*, __nv_bfloat16*, int, cudaStream_t);
 
 template <typename TKV, typename TOut>
-void launch_attn_decode(const float* QKV, const int* active, int M, const int* ctx_len, const int* block_tables,
+int launch_attn_decode(const float* QKV, const int* active, int M, const int* ctx_len, const int* block_tables,
                         int max_pages, TKV* kpool, TKV* vpool, TOut* out, int heads, cudaStream_t st,
-                        double ctx_sum_hint, bool pdl) {
-    if (M <= 0) return;
+                        double ctx_sum_hint, bool pdl, DepFlag dep) {
+    if (M <= 0) return 0;
     // algorithmic bytes: K and V of every cached token of every sequence, once
     ProfScope ps(KF_ATTN_DECODE, st, 4.0 * ctx_sum_hint * heads * kHeadDim,
                  2.0 * ctx_sum_hint * heads * kHeadDim * sizeof(TKV));
@@ -896,11 +911,12 @@ void launch_attn_decode(const float* QKV, const int* active, int M, const int* c
         grid = std::min(n_items, -g_attn_ctas_per_sm);          // test hook: an absolute grid size
     }
     launch_k(attn_decode_kernel<TKV, TOut>, dim3(grid), dim3(128), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
-             kpool, vpool, out, heads, n_items);
+             kpool, vpool, out, heads, n_items, dep);
     COUNT_LAUNCH(); KERNEL_CHECK();
+    return grid;
 }
-template void launch_attn_decode<float, float>(const float*, const int*, int, const int*, const int*, int, float*, float*, float*, int, cudaStream_t, double, bool);
-template void launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(const float*, const int*, int, const int*, const int*, int, __nv_bfloat16*, __nv_bfloat16*, __nv_bfloat16*, int, cudaStream_t, double, bool);
+template int launch_attn_decode<float, float>(const float*, const int*, int, const int*, const int*, int, float*, float*, float*, int, cudaStream_t, double, bool, DepFlag);
+template int launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(const float*, const int*, int, const int*, const int*, int, __nv_bfloat16*, __nv_bfloat16*, __nv_bfloat16*, int, cudaStream_t, double, bool, DepFlag);
 
 template <typename TOut>
 void launch_attn_generic(AttnLayout L, const AttnSeq* seqs, int nseq, int max_nq, TOut* out, int out_row_stride,

@@ -20,14 +20,16 @@ void launch_gemm_f32(const float* A, const float* W, const float* bias, const fl
 // out is fp32 unless GEMM_OUT_BF16.  K % 64 == 0, N % 16 == 0 required.
 // `pdl`: launch with the programmatic-dependent-launch attribute (decode chain); every kernel that can be launched
 // that way executes griddepcontrol.wait before touching its predecessor's outputs
-void launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const float* resid,
-                         void* out, int M, int N, int K, int flags, cudaStream_t st, bool pdl = false);
+// `dep` (decode chain): wait / arrive counters instead of griddepcontrol.wait (common.cuh).  Returns the number of CTAs
+// launched = the value the kernel's arrive counter reaches (0 when the launch went to the CTA-pair kernel).
+int launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const float* resid,
+                        void* out, int M, int N, int K, int flags, cudaStream_t st, bool pdl = false, DepFlag dep = DepFlag());
 // large-shape path (gemm_tcgen05_2cta.cu): persistent CTA pairs (cta_group::2), 256 x 256 tiles, double-buffered TMEM
 bool gemm_2cta_supported(int M, int N, int K);
 void launch_gemm_bf16_2cta(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const float* resid,
                            void* out, int M, int N, int K, int flags, cudaStream_t st);
-void launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, float* partials, int M, int N, int K,
-                                int splits, cudaStream_t st, bool pdl = false);
+int launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, float* partials, int M, int N, int K,
+                               int splits, cudaStream_t st, bool pdl = false, DepFlag dep = DepFlag());
 
 // Fused decode chain (gemm_tcgen05.cu): one persistent launch runs, for one layer boundary of the decode step,
 //   proj (split-K) -> residual+LN2 -> fc+gelu -> fc2 (split-K) -> residual+LN1(next layer) -> qkv(next layer)
@@ -72,18 +74,20 @@ struct GptTables {        // embedding tables (device, fp32)
 
 void launch_build_rows(const RowDesc* rows, int n_rows, GptTables t, float* X, cudaStream_t st);
 // decode input rows: X[i] = wte[last_tok[slot]] + wpe[n_gen[slot]],  slot = active[i]
+// (also zeroes `n_flags` dependency counters at `flags`: the step's first kernel, behind a full dependency wait)
 void launch_build_decode_rows(const int* active, int M, const int* last_tok, const int* n_gen, GptTables t,
-                              float* X, cudaStream_t st, bool pdl = false);
+                              float* X, cudaStream_t st, bool pdl = false, unsigned* flags = nullptr, int n_flags = 0);
 
 template <typename TOut>
 void launch_layernorm(const float* X, const float* w, const float* b, TOut* Y, int M, int H, float eps,
-                      cudaStream_t st, bool pdl = false);
+                      cudaStream_t st, bool pdl = false, DepFlag dep = DepFlag());
 
 // X[m] += bias + sum_z partials[z][m]  (deterministic split-K reduction fused with the residual add), then
 // Y[m] = LN(X[m]) when Y != nullptr  (the following block's LayerNorm)
 template <typename TOut>
 void launch_residual_reduce_layernorm(float* X, const float* partials, int splits, const float* bias, const float* w,
-                                      const float* b, TOut* Y, int M, int H, float eps, cudaStream_t st, bool pdl = false);
+                                      const float* b, TOut* Y, int M, int H, float eps, cudaStream_t st, bool pdl = false,
+                                      DepFlag dep = DepFlag());
 
 // y = LN_fn(LN_lnf(X[row_index[i]]));  Y[i] = y (GEMM operand);
 // latents[slots[i]][lat_pos ? lat_pos[i] : n_gen[slots[i]]] = LN_fn(y)
@@ -102,10 +106,11 @@ void launch_kv_write(const float* QKV, int M, const int* row_slot, const int* ro
 
 // decode attention over the paged cache, ctx = ctx_len[slot] + 1.  The kernel also appends the new token's K/V
 // (read from the QKV row) to the cache — the reshape_and_cache step — so no separate kv_write launch is needed.
+// returns the number of CTAs launched
 template <typename TKV, typename TOut>
-void launch_attn_decode(const float* QKV, const int* active, int M, const int* ctx_len,
-                        const int* block_tables, int max_pages, TKV* kpool, TKV* vpool,
-                        TOut* out, int heads, cudaStream_t st, double ctx_sum_hint = 0, bool pdl = false);
+int launch_attn_decode(const float* QKV, const int* active, int M, const int* ctx_len,
+                       const int* block_tables, int max_pages, TKV* kpool, TKV* vpool,
+                       TOut* out, int heads, cudaStream_t st, double ctx_sum_hint = 0, bool pdl = false, DepFlag dep = DepFlag());
 
 struct AttnSeq { int q_start, nq, kv_start, nk; };
 struct AttnLayout {

@@ -82,10 +82,12 @@ class TTS:
         return {"parallel_inputs": parallel_inputs, "request": input_request}
 
     async def _second_phase_fn(self, gen_input: Dict):
-        """tts.py:160-194 (phase 2)."""
+        """tts.py:160-194 (phase 2), wrapped by the reference in `track_generation` (performance.py:105-151)."""
+        from .metrics import track
         async for chunk in self.tts_engine.process_tokens_to_speech(
                 generator=gen_input["generator"], speaker_embeddings=gen_input["speaker_embedding"],
                 multimodal_data=gen_input["multimodal_data"], request=gen_input["request"]):
+            track(chunk, self.tts_engine)
             yield chunk
 
     async def generate_speech_async(self, request: TTSRequest) -> Union[AsyncGenerator[TTSOutput, None], TTSOutput]:

@@ -507,3 +507,27 @@ def test_in_process_data_parallel_engines():
     assert eng.natives[0].cond_calls == 1 and eng.natives[1].cond_calls == 0  # conditioned once, uploaded to the 2nd GPU
     assert eng._load == [0, 0] and not eng._waiters
     tts.loop.run_until_complete(tts.shutdown())
+
+
+def test_generation_metrics_tracker_matches_the_reference_rule():
+    """metrics.py restates performance.py:12-151: one update per chunk that has a start_time, a log line (and a window reset)
+    once log_interval has passed, the three rates from the window totals; native counters are appended when available."""
+    from auralis_b200.metrics import TTSMetricsTracker, track
+    from auralis_b200 import TTSOutput
+    t = TTSMetricsTracker(log_interval=0.0)
+    t.window_start -= 2.0
+
+    class Eng:
+        def stats(self):
+            return {"decode_steps": 7, "kernel_launches": 1500, "gpt_ms": 12.0, "vocoder_ms": 3.0}
+    out = TTSOutput(array=np.zeros(24000, np.float32), token_length=21, start_time=time.time())
+    assert t.update_metrics(21, 1.0) is True and t.window_requests == 1 and t.window_tokens == 21
+    assert 9 < t.tokens_per_second < 11 and 0.4 < t.requests_per_second < 0.6 and 1900 < t.ms_per_second_of_audio < 2200
+    line = t.line(Eng())
+    assert line.startswith("Generation metrics | Throughput: ") and "tokens/s" in line and "7 decode steps" in line
+    t.reset_window()
+    assert t.window_requests == 0 and t.window_tokens == 0
+    track(out, Eng(), t)                                    # logs + resets (interval 0)
+    assert t.window_requests == 0
+    track(TTSOutput(array=np.zeros(10, np.float32), token_length=1, start_time=None), None, t)   # no start_time: not counted
+    assert t.window_requests == 0
