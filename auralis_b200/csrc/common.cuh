@@ -95,6 +95,7 @@ struct KernelCtx {
     int attn_ctas_per_sm = 0;     // 0 = uncapped decode-attention grid; > 0: at most this many CTAs per SM
     int gemm_decode_bn = 0;       // 0 = heuristic; 32/64/128 forces the tile width of decode-shaped tcgen05 GEMMs
     int conv_epi_groups = 2;      // 1 or 2 epilogue warpgroups in conv1d_tc_kernel
+    int attn_warps = 4;           // warps per (row, head) item of the bf16 decode attention (4, or 8: measured slower, run 7)
     int gemm_2cta = 1;            // large shapes (M >= 256) go to the persistent CTA-pair kernel (gemm_tcgen05_2cta.cu)
 };
 #define g_prof (::xtts::kctx().prof)
@@ -104,6 +105,7 @@ struct KernelCtx {
 #define g_gemm_decode_bn (::xtts::kctx().gemm_decode_bn)
 #define g_conv_epi_groups (::xtts::kctx().conv_epi_groups)
 #define g_gemm_2cta (::xtts::kctx().gemm_2cta)
+#define g_attn_warps (::xtts::kctx().attn_warps)
 
 // true the first time it is called with the current CUDA device for this flag set (function attributes are per device)
 inline bool first_on_device(bool (&done)[64]) {
@@ -192,6 +194,7 @@ __device__ __forceinline__ void dep_wait(const DepFlag& d, int tag) {
     while (true) {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(d.wait) : "memory");
         if (v >= d.target) break;
+        __nanosleep(polls < 8 ? 100 : 400);          // hundreds of CTAs poll one line that the producers are also adding to
         if ((++polls & 255) == 0 && clock64() - t0 > 4000000000LL) {
             printf("dep_wait watchdog (tag %d, block %d, have %u want %u)\n", tag, blockIdx.x, v, d.target);
             __trap();

@@ -298,7 +298,8 @@ private:
     int n_micro = 2;              // option "microbatches": decode rows are split into this many concurrent branches
     int micro_min_rows = 48;      // option "microbatch_min_rows": below this many active rows the step stays single-branch
     int stagger_us = 0;           // option "branch_stagger_us": branch i starts i * this many microseconds late
-    bool use_dep_flags = true;    // option "dep_flags": counter dependencies along the decode chain instead of grid-wide waits
+    bool use_dep_flags = false;   // option "dep_flags": counter dependencies along the decode chain instead of grid-wide waits
+                                  // (parity-tested; measured SLOWER than griddepcontrol.wait, runs 6-7: kept as an experiment)
     DBuf<unsigned> d_dep;         // [kMaxMicro][layers][7] dependency counters (zeroed by the first kernel of every step)
     int eager_steps_done = 0;
     std::map<int, cudaGraphExec_t> decode_graphs;
@@ -1838,7 +1839,8 @@ void Engine::set_option(const std::string& k, int64_t v) {
     else if (k == "voc_segment") voc_segment = (int)std::max<int64_t>(0, v);
     else if (k == "voc_sms") voc_sms = (int)std::max<int64_t>(0, v);
     else if (k == "voc_batch") voc_max_items = (int)std::max<int64_t>(1, std::min<int64_t>(v, kVocMaxItems));
-    else if (k == "gemm_2cta") g_gemm_2cta = v != 0;
+    else if (k == "gemm_2cta") g_gemm_2cta = (int)std::max<int64_t>(0, std::min<int64_t>(v, 4));      // 0 off, 1 default ring, 2-4 ring variants
+    else if (k == "attn_warps") { g_attn_warps = v >= 8 ? 8 : 4; drop_graphs(); }
     else if (k == "cuda_graphs") use_graphs = v != 0;
     else if (k == "pdl") { use_pdl = v != 0; drop_graphs(); }
     else if (k == "splitk") { use_splitk = v != 0; drop_graphs(); }

@@ -9,8 +9,9 @@
 //   * PERSISTENT: one cluster per SM pair walks the tile list; barriers, the 6-stage TMA ring and TMEM live across tiles;
 //   * DOUBLE-BUFFERED ACCUMULATORS: two 256-column TMEM buffers (all 512 columns): the epilogue of tile i drains one
 //     while the MMAs of tile i + 1 fill the other.
-// Roles per CTA (192 threads): warp 0 TMA producer (both CTAs load; transaction bytes land on the LEADER's barrier),
-// warp 1 TMEM allocation + (leader CTA only) MMA issue, warps 2..5 epilogue (TMEM lane quarter = warp % 4).
+// Roles per CTA (320 threads): warp 0 TMA producer (both CTAs load; transaction bytes land on the LEADER's barrier),
+// warp 1 TMEM allocation + (leader CTA only) MMA issue, warps 2..9 epilogue (TMEM lane quarter = warp % 4, two warpgroups
+// on alternate column chunks: four warps alone could not drain a 128 x 256 fp32 tile in the time its MMAs take).
 // Same watchdog discipline as the other tcgen05 kernels: every mbarrier wait traps instead of hanging the GPU.
 #include <cuda.h>
 #include "kernels.h"
@@ -18,10 +19,12 @@
 namespace xtts {
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 6;
-constexpr int kThreads = 192;
-constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2;      // per CTA and stage: 16 KB + 16 KB
-constexpr size_t kSmem = (size_t)STAGES * (A_BYTES + B_BYTES) + 4 * 32 * 33 * sizeof(float) + 1024;
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
+constexpr int kEpiWarps = 8;                                  // two warpgroups: (w, w + 4) share a TMEM lane quarter
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2;      // per CTA and 64-wide k-block: 16 KB + 16 KB
+// a ring stage holds KPS k-blocks (KPS = 2: half the barrier round trips per byte)
+__host__ __device__ constexpr size_t smem_for(int stages, int kps) { return (size_t)stages * kps * (A_BYTES + B_BYTES) + 1024; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -93,6 +96,7 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                  ::"r"(smem_u32(bar)), "h"((uint16_t)0b11) : "memory");
 }
 
+template <int STAGES, int KPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const float* __restrict__ bias, const float* resid, void* out, int M, int N, int K, int flags) {
@@ -105,8 +109,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * A_BYTES;
-    float* stage = reinterpret_cast<float*>(smem + STAGES * (A_BYTES + B_BYTES));     // 4 epilogue warps x [32][33] fp32
+    uint8_t* sB = smem + STAGES * KPS * A_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
@@ -115,7 +118,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {        // the same warp of both CTAs allocates all 512 columns for the pair
@@ -130,7 +133,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
     const int tiles_m = (M + 2 * BM - 1) / (2 * BM), tiles_n = (N + BN - 1) / BN;
     const int total = tiles_m * tiles_n, n_clusters = gridDim.x / 2, cid = blockIdx.x / 2;
-    const int num_kb = K / BK;
+    const int num_kb = (K / BK + KPS - 1) / KPS;      // ring stages per tile (the last may be half filled)
+    const int kb_total = K / BK;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -140,9 +144,14 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&empty_bar[s], (uint32_t)(((it / STAGES) & 1) ^ 1), 1);
-                    if (leader) mbar_expect_tx(&full_bar[s], 2u * (A_BYTES + B_BYTES));
-                    tma_load_2d_2sm(sA + s * A_BYTES, &tmA, &full_bar[s], kb * BK, m0);
-                    tma_load_2d_2sm(sB + s * B_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+                    const int nk = min(KPS, kb_total - kb * KPS);
+                    if (leader) mbar_expect_tx(&full_bar[s], 2u * (uint32_t)nk * (A_BYTES + B_BYTES));
+#pragma unroll
+                    for (int j = 0; j < KPS; ++j)
+                        if (j < nk) {
+                            tma_load_2d_2sm(sA + (s * KPS + j) * A_BYTES, &tmA, &full_bar[s], (kb * KPS + j) * BK, m0);
+                            tma_load_2d_2sm(sB + (s * KPS + j) * B_BYTES, &tmB, &full_bar[s], (kb * KPS + j) * BK, n0);
+                        }
                 }
             }
         }
@@ -158,27 +167,34 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     const int s = it % STAGES;
                     mbar_wait(&full_bar[s], (uint32_t)((it / STAGES) & 1), 3);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = smem_u32(sA + s * A_BYTES), b_addr = smem_u32(sB + s * B_BYTES);
+                    const int nk = min(KPS, kb_total - kb * KPS);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)
-                        umma_bf16_2cta(acc, make_sw128_desc(a_addr + k * UMMA_K * 2), make_sw128_desc(b_addr + k * UMMA_K * 2),
-                                       (kb | k) != 0 ? 1u : 0u);
+                    for (int j = 0; j < KPS; ++j) {
+                        if (j >= nk) break;
+                        const uint32_t a_addr = smem_u32(sA + (s * KPS + j) * A_BYTES), b_addr = smem_u32(sB + (s * KPS + j) * B_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16_2cta(acc, make_sw128_desc(a_addr + k * UMMA_K * 2), make_sw128_desc(b_addr + k * UMMA_K * 2),
+                                           (kb | j | k) != 0 ? 1u : 0u);
+                    }
                     umma_commit_pair(&empty_bar[s]);        // the slot is free in both CTAs once these MMAs have read it
                 }
                 umma_commit_pair(&tmem_full[ab]);           // accumulators of both CTAs complete
             }
         }
     } else {
-        // ---------------- epilogue: warp (2..5) owns TMEM lanes [32*(warp%4), +32) = this CTA's tile rows
-        const int q = warp & 3;
+        // ---------------- epilogue: warp w owns TMEM lanes [32*(w%4), +32) = this CTA's tile rows; the two warpgroups take
+        // alternate 32-column chunks of the 256-column accumulator
+        const int q = warp & 3, grp = (warp - 2) >> 2;
         int lt = 0;
         for (int tile = cid; tile < total; tile += n_clusters, ++lt) {
             const int ab = lt & 1;
             const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&tmem_full[ab], (uint32_t)((lt >> 1) & 1), 4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + q * 32 + lane;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = grp; c < BN / 32; c += kEpiWarps / 4) {
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c * 32);
                 asm volatile(
@@ -191,37 +207,49 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr) : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c == BN / 32 - 1) {
+                if (c + kEpiWarps / 4 >= BN / 32) {
                     // this warp has read the last of the buffer: hand it back to the (leader's) MMA thread before the stores
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(&tmem_empty[ab], 0);
                 }
-                // ---- store through a per-warp 32 x 33 transpose in shared memory: TMEM hands every lane one ROW (32 consecutive
-                // columns); written as it comes, one store instruction would touch 32 different 128-byte lines (16 B each).
-                // After the transpose a lane owns one COLUMN, so each instruction writes one row's 128 contiguous bytes
-                // (one transaction instead of 32) and the residual / bias reads are coalesced the same way.
                 const int nb = n0 + c * 32;
-                float* stg = stage + (warp - 2) * (32 * 33);
+                if (row < M && nb < N) {
+                    float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(r[i]);
-                __syncwarp();
-                if (nb < N) {
-                    const int col = nb + lane;
-                    const float bv = bias ? __ldg(bias + col) : 0.f;
-                    const int row0 = m0 + q * 32;
-#pragma unroll 4
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int grow = row0 + rr;
-                        if (grow >= M) break;
-                        float x = stg[rr * 33 + lane] + bv;
+                    for (int i = 0; i < 32; ++i) {
+                        float x = __uint_as_float(r[i]);
+                        if (bias) x += __ldg(bias + nb + i);
                         if (flags & GEMM_GELU) x = gelu_new(x);
-                        if (flags & GEMM_RESID) x += resid[(size_t)grow * N + col];
-                        if (flags & GEMM_OUT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[(size_t)grow * N + col] = __float2bfloat16_rn(x);
-                        else reinterpret_cast<float*>(out)[(size_t)grow * N + col] = x;
+                        v[i] = x;
+                    }
+                    if (flags & GEMM_RESID) {
+                        const float4* rp = reinterpret_cast<const float4*>(resid + (size_t)row * N + nb);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 t = rp[i];
+                            v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+                        }
+                    }
+                    if (flags & GEMM_OUT_BF16) {
+                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)row * N + nb;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            uint4 pk;
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
+                            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
+                            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            reinterpret_cast<uint4*>(op)[i] = pk;
+                        }
+                    } else {
+                        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)row * N + nb);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     }
                 }
-                __syncwarp();
             }
         }
     }
@@ -265,8 +293,12 @@ void launch_gemm_bf16_2cta(const __nv_bfloat16* A, const __nv_bfloat16* W, const
         g_encode2 = reinterpret_cast<EncodeTiledFn>(fn);
     }
     static bool attr[64] = {};
-    if (first_on_device(attr))
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    if (first_on_device(attr)) {
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(6, 1)));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(4, 1)));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(7, 1)));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(3, 2)));
+    }
     static int n_sm = 0;
     if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
     CUtensorMap tmA, tmB;
@@ -276,7 +308,14 @@ void launch_gemm_bf16_2cta(const __nv_bfloat16* A, const __nv_bfloat16* W, const
     const int clusters = std::min(total, n_sm / 2);
     ProfScope ps(KF_GEMM_TC, st, 2.0 * M * N * K,
                  2.0 * ((double)M * K + (double)N * K) + ((flags & GEMM_OUT_BF16) ? 2.0 : 4.0) * M * N);
-    gemm_bf16_2cta_kernel<<<dim3(2 * clusters), dim3(kThreads), kSmem, st>>>(tmA, tmB, bias, resid, out, M, N, K, flags);
+    // g_gemm_2cta selects the ring shape (1 = default): 6 x 1 k-block, 2: 4 x 1, 3: 7 x 1, 4: 3 stages x 2 k-blocks
+    const dim3 grid(2 * clusters), block(kThreads);
+    switch (g_gemm_2cta) {
+        case 2: gemm_bf16_2cta_kernel<4, 1><<<grid, block, smem_for(4, 1), st>>>(tmA, tmB, bias, resid, out, M, N, K, flags); break;
+        case 3: gemm_bf16_2cta_kernel<7, 1><<<grid, block, smem_for(7, 1), st>>>(tmA, tmB, bias, resid, out, M, N, K, flags); break;
+        case 4: gemm_bf16_2cta_kernel<3, 2><<<grid, block, smem_for(3, 2), st>>>(tmA, tmB, bias, resid, out, M, N, K, flags); break;
+        default: gemm_bf16_2cta_kernel<6, 1><<<grid, block, smem_for(6, 1), st>>>(tmA, tmB, bias, resid, out, M, N, K, flags); break;
+    }
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 

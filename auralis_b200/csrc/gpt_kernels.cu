@@ -268,8 +268,8 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {          // streami
 // reshape_and_cache does in vLLM) and attended to straight from shared memory, rounded to the cache type first so the
 // result is identical to reading it back.
 // HBM-bound: algorithmic bytes = 2 * ctx * 64 * sizeof(TKV) per (sequence, head).
-template <typename TKV, typename TOut>
-__global__ void __launch_bounds__(128)
+template <typename TKV, typename TOut, int NW>
+__global__ void __launch_bounds__(32 * NW)
 attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active, const int* __restrict__ ctx_len,
                    const int* __restrict__ block_tables, int max_pages, TKV* __restrict__ kpool, TKV* __restrict__ vpool,
                    TOut* __restrict__ out, int heads, int n_items, const DepFlag dep) {
@@ -278,8 +278,8 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
     constexpr int TPI = 32 / NCH;                     // tokens covered by one warp-wide V load (4 / 2)
     constexpr int VIT = kPageTokens / TPI;            // V loads per page (8 / 16)
     __shared__ __align__(16) float qs[kHeadDim], ks[kHeadDim], vs[kHeadDim];
-    __shared__ float pm[4], pl[4];
-    __shared__ float pacc[4][kHeadDim];
+    __shared__ float pm[NW], pl[NW];
+    __shared__ float pacc[NW][kHeadDim];
     trace_pt(TR_ATTN, 0); pdl_trigger();
     if (threadIdx.x == 0) dep_wait(dep, 33);
     __syncthreads();
@@ -303,7 +303,7 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
             const TKV k = from_f32<TKV>(row[H + d]);
             ks[d] = to_f32<TKV>(k);
             kpool[pbase + ((size_t)(d / X) * kPageTokens + tk) * X + (d % X)] = k;
-        } else {
+        } else if (tid < 128) {
             const TKV v = from_f32<TKV>(row[2 * H + d]);
             vs[d] = to_f32<TKV>(v);
             vpool[pbase + (size_t)tk * kHeadDim + d] = v;
@@ -316,7 +316,7 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
 #pragma unroll
     for (int e = 0; e < X; ++e) acc[e] = 0.f;
     const int npages = (past + kPageTokens - 1) / kPageTokens;
-    for (int pg = w; pg < npages; pg += 4) {
+    for (int pg = w; pg < npages; pg += NW) {
         const int page = bt[pg];
         const size_t pbase = ((size_t)page * heads + h) * (kPageTokens * kHeadDim);
         const int nvalid = min(kPageTokens, past - pg * kPageTokens);
@@ -383,10 +383,12 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
     }
     __syncthreads();
     if (tid < kHeadDim) {
-        const float M = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
+        float M = pm[0];
+#pragma unroll
+        for (int k = 1; k < NW; ++k) M = fmaxf(M, pm[k]);
         float L = 0.f, o = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < NW; ++k) {
             const float e = (pm[k] == -INFINITY) ? 0.f : expf(pm[k] - M);
             L = fmaf(pl[k], e, L);
             o = fmaf(pacc[k][tid], e, o);
@@ -910,8 +912,15 @@ int launch_attn_decode(const float* QKV, const int* active, int M, const int* ct
     } else if (g_attn_ctas_per_sm < 0) {
         grid = std::min(n_items, -g_attn_ctas_per_sm);          // test hook: an absolute grid size
     }
-    launch_k(attn_decode_kernel<TKV, TOut>, dim3(grid), dim3(128), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
-             kpool, vpool, out, heads, n_items, dep);
+    // warps per (row, head) item: the cache pages of an item are dealt round-robin to its warps.  4 is the default; 8 (engine
+    // option "attn_warps", bf16 only) halves an item's latency and was meant to shorten the under-filled tail of the kernel —
+    // measured 18 % SLOWER per decode step (run 7: 256-thread CTAs, three per SM), kept as an option.
+    if (sizeof(TKV) == 2 && g_attn_warps == 8)
+        launch_k(attn_decode_kernel<TKV, TOut, 8>, dim3(grid), dim3(256), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
+                 kpool, vpool, out, heads, n_items, dep);
+    else
+        launch_k(attn_decode_kernel<TKV, TOut, 4>, dim3(grid), dim3(128), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
+                 kpool, vpool, out, heads, n_items, dep);
     COUNT_LAUNCH(); KERNEL_CHECK();
     return grid;
 }

@@ -196,8 +196,16 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
         paths = audio_reference if isinstance(audio_reference, list) else [audio_reference]
         hk = hashlib.sha256()
         for p in paths:
-            hk.update(p if isinstance(p, (bytes, bytearray)) else str(p).encode())
-        hk.update(f"{max_ref_length}|{gpt_cond_len}|{gpt_cond_chunk_len}|{sound_norm_refs}".encode())
+            if isinstance(p, (bytes, bytearray)):
+                hk.update(p)
+            else:                           # a file: its identity is path + size + mtime (a replaced file is a new speaker)
+                import os
+                try:
+                    stt = os.stat(str(p))
+                    hk.update(f"{p}|{stt.st_size}|{stt.st_mtime_ns}".encode())
+                except OSError:
+                    hk.update(str(p).encode())
+        hk.update(f"{max_ref_length}|{gpt_cond_len}|{gpt_cond_chunk_len}|{sound_norm_refs}|{load_sr}".encode())
         key = hk.hexdigest()
         cached = self._spk_arrays.get(key)
         if cached is not None:
@@ -229,10 +237,16 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
                     self.native.condition(slot, full, _resample(audios22[0], load_sr, 16000), gpt_cond_len, gpt_cond_chunk_len)
                     c, _ = self.native.get_speaker(slot)
                     self.native.set_speaker(slot, c, np.mean(np.stack(gs), axis=0))
+                fut = asyncio.ensure_future(asyncio.to_thread(work))
                 try:
-                    await asyncio.to_thread(work)
+                    await asyncio.shield(fut)
+                except asyncio.CancelledError:
+                    # the worker thread is still writing into `slot`: the entry stays "being computed" (never evicted, never
+                    # a hit) until the thread has really finished, and only then is it dropped
+                    fut.add_done_callback(lambda f, k=key: (f.exception(), self._spk.failed(k, RuntimeError("conditioning cancelled"))))
+                    raise
                 except BaseException as e:
-                    self._spk.failed(key, e if isinstance(e, Exception) else RuntimeError("conditioning cancelled"))
+                    self._spk.failed(key, e if isinstance(e, Exception) else RuntimeError("conditioning failed"))
                     raise
                 self._spk.ready(key)
             elif pending is not None:                      # another request is computing this speaker right now

@@ -151,13 +151,16 @@ class TTSOutput:
                 return (wav * np.float32(2147483647)).astype(np.int32).tobytes()
             return (wav * 127).astype(np.int8).tobytes()
         if format == "wav":
-            buf = io.BytesIO()
-            with wave.open(buf, "wb") as w:
-                w.setnchannels(1)
-                w.setsampwidth(2)
-                w.setframerate(self.sample_rate)
-                w.writeframes((wav * 32767).astype(np.int16).tobytes())
-            return buf.getvalue()
+            # output.py:141-149: encoding PCM_S at sample_width 2, PCM_F (IEEE float) otherwise, bits = 8 * sample_width
+            if sample_width == 2:
+                buf = io.BytesIO()
+                with wave.open(buf, "wb") as w:
+                    w.setnchannels(1)
+                    w.setsampwidth(2)
+                    w.setframerate(self.sample_rate)
+                    w.writeframes((wav * 32767).astype(np.int16).tobytes())
+                return buf.getvalue()
+            return _riff_wav(wav, self.sample_rate, 8 * sample_width)
         if format in ("flac", "mp3", "opus", "aac"):
             try:
                 import torch

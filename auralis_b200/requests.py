@@ -3,7 +3,8 @@
 
 Differences, all outside the hot path: language auto-detection uses ``langid`` when it is installed and
 otherwise falls back to "en" with a warning (the reference hard-requires langid); ``enhance_speech``
-(off by default, requests.py:171; CPU DSP on the reference wav) raises if requested.
+(off by default, requests.py:171; CPU DSP on the reference wav) is not provided: when requested, the original speaker
+files are used and a warning is issued — the reference's own behaviour when its enhancer fails.
 """
 from __future__ import annotations
 

@@ -32,7 +32,8 @@ def run(label, **opts):
 for extra in sys.argv[2:]:
     eng.set_option(extra.split("=")[0], int(extra.split("=")[1]))
 run("warm", microbatches=2)
-for flags in (1, 0):
-    for mb, stg in ((2, 0), (2, 30), (1, 0), (3, 0), (3, 20)):
-        run(f"dep_flags {flags}, {mb} branches, stagger {stg} us", dep_flags=flags, microbatches=mb, branch_stagger_us=stg)
+for aw in (8, 4):
+    for flags in (0, 1):
+        for mb in (2, 1):
+            run(f"attn_warps {aw}, dep_flags {flags}, {mb} branches", attn_warps=aw, dep_flags=flags, microbatches=mb, branch_stagger_us=0)
 eng.close()
