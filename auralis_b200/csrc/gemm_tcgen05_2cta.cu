@@ -24,7 +24,9 @@ constexpr int kEpiWarps = 8;                                  // two warpgroups:
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2;      // per CTA and 64-wide k-block: 16 KB + 16 KB
 // a ring stage holds KPS k-blocks (KPS = 2: half the barrier round trips per byte)
-__host__ __device__ constexpr size_t smem_for(int stages, int kps) { return (size_t)stages * kps * (A_BYTES + B_BYTES) + 1024; }
+__host__ __device__ constexpr size_t smem_for(int stages, int kps) {
+    return (size_t)stages * kps * (A_BYTES + B_BYTES) + (size_t)kEpiWarps * 4096 + 1024;     // ring + epilogue boxes + alignment
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -99,7 +101,8 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 template <int STAGES, int KPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const float* __restrict__ bias, const float* resid, void* out, int M, int N, int K, int flags) {
+                      const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* resid, int M, int N,
+                      int K, int flags) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];       // leader's copy is the live one (both CTAs' bytes land there)
     __shared__ __align__(8) uint64_t empty_bar[STAGES];      // one per CTA: the MMA commit is multicast to the pair
@@ -110,6 +113,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * KPS * A_BYTES;
+    uint8_t* sC = smem + STAGES * KPS * (A_BYTES + B_BYTES);          // kEpiWarps x 4 KB: one 32 x 32 output box per warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
@@ -117,6 +121,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -213,45 +218,61 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(&tmem_empty[ab], 0);
                 }
+                // ---- the chunk leaves through shared memory and a TMA store: a lane holds 32 consecutive columns of ONE row,
+                // so written directly every store instruction touches 32 different 128-byte lines (16 B each) and the LSU —
+                // not HBM — bounds the epilogue (measured: 12 us per 128 x 256 fp32 tile, twice the tile's MMA time at
+                // K = 1024).  Staged as a 128B-swizzled 32 x 32 box (conflict-free 16-byte shared stores), one
+                // cp.async.bulk.tensor store writes whole rows and clips the tile tails itself.
                 const int nb = n0 + c * 32;
-                if (row < M && nb < N) {
-                    float v[32];
+                float v[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float x = __uint_as_float(r[i]);
-                        if (bias) x += __ldg(bias + nb + i);
-                        if (flags & GEMM_GELU) x = gelu_new(x);
-                        v[i] = x;
+                for (int i = 0; i < 32; ++i) {
+                    float x = __uint_as_float(r[i]);
+                    if (bias && nb + i < N) x += __ldg(bias + nb + i);
+                    if (flags & GEMM_GELU) x = gelu_new(x);
+                    v[i] = x;
+                }
+                if ((flags & GEMM_RESID) && row < M && nb < N) {
+                    const float4* rp = reinterpret_cast<const float4*>(resid + (size_t)row * N + nb);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 t = rp[i];
+                        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
                     }
-                    if (flags & GEMM_RESID) {
-                        const float4* rp = reinterpret_cast<const float4*>(resid + (size_t)row * N + nb);
+                }
+                uint8_t* box = sC + (warp - 2) * 4096;
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the box
+                __syncwarp();
+                if (flags & GEMM_OUT_BF16) {
+                    // 32 rows x 64 B, SWIZZLE_64B: 16-byte chunk j of row r sits at chunk j ^ ((r >> 1) & 3)
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 t = rp[i];
-                            v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 pk;
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+                        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+                        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(box + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
                     }
-                    if (flags & GEMM_OUT_BF16) {
-                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)row * N + nb;
+                } else {
+                    // 32 rows x 128 B, SWIZZLE_128B: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            uint4 pk;
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
-                            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-                            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                            reinterpret_cast<uint4*>(op)[i] = pk;
-                        }
-                    } else {
-                        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)row * N + nb);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> the TMA engine's reads
+                __syncwarp();
+                if (lane == 0 && nb < N && m0 + q * 32 < M) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(&tmC), "r"(smem_u32(box)), "r"(nb), "r"(m0 + q * 32) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every store of this warp has landed
     }
     // nobody leaves (or frees TMEM) while the peer may still read this CTA's shared memory or signal its barriers
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -294,27 +315,38 @@ void launch_gemm_bf16_2cta(const __nv_bfloat16* A, const __nv_bfloat16* W, const
     }
     static bool attr[64] = {};
     if (first_on_device(attr)) {
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(6, 1)));
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(4, 1)));
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(7, 1)));
         CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(3, 2)));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(4, 1)));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(6, 1)));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(2, 2)));
     }
     static int n_sm = 0;
     if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;
     encode_2d(&tmA, A, (uint64_t)M, (uint64_t)K, BM);
     encode_2d(&tmB, W, (uint64_t)N, (uint64_t)K, BN / 2);
+    {   // output [M, N] row-major, 32 x 32 boxes; the swizzle spans one box row (128 B fp32, 64 B bf16)
+        const bool h = (flags & GEMM_OUT_BF16) != 0;
+        const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+        const cuuint64_t strides[1] = {(cuuint64_t)N * (h ? 2 : 4)};
+        const cuuint32_t box[2] = {32, 32};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = g_encode2(&tmC, h ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides,
+                                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, h ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) throw CudaError("gemm_2cta: cuTensorMapEncodeTiled (output) failed");
+    }
     const int total = ceil_div(M, 2 * BM) * ceil_div(N, BN);
     const int clusters = std::min(total, n_sm / 2);
     ProfScope ps(KF_GEMM_TC, st, 2.0 * M * N * K,
                  2.0 * ((double)M * K + (double)N * K) + ((flags & GEMM_OUT_BF16) ? 2.0 : 4.0) * M * N);
-    // g_gemm_2cta selects the ring shape (1 = default): 6 x 1 k-block, 2: 4 x 1, 3: 7 x 1, 4: 3 stages x 2 k-blocks
+    // g_gemm_2cta selects the ring shape: 1 (default) = 3 stages x 2 k-blocks (best measured, run 8), 2: 4 x 1, 3: 6 x 1, 4: 2 x 2
     const dim3 grid(2 * clusters), block(kThreads);
     switch (g_gemm_2cta) {
-        case 2: gemm_bf16_2cta_kernel<4, 1><<<grid, block, smem_for(4, 1), st>>>(tmA, tmB, bias, resid, out, M, N, K, flags); break;
-        case 3: gemm_bf16_2cta_kernel<7, 1><<<grid, block, smem_for(7, 1), st>>>(tmA, tmB, bias, resid, out, M, N, K, flags); break;
-        case 4: gemm_bf16_2cta_kernel<3, 2><<<grid, block, smem_for(3, 2), st>>>(tmA, tmB, bias, resid, out, M, N, K, flags); break;
-        default: gemm_bf16_2cta_kernel<6, 1><<<grid, block, smem_for(6, 1), st>>>(tmA, tmB, bias, resid, out, M, N, K, flags); break;
+        case 2: gemm_bf16_2cta_kernel<4, 1><<<grid, block, smem_for(4, 1), st>>>(tmA, tmB, tmC, bias, resid, M, N, K, flags); break;
+        case 3: gemm_bf16_2cta_kernel<6, 1><<<grid, block, smem_for(6, 1), st>>>(tmA, tmB, tmC, bias, resid, M, N, K, flags); break;
+        case 4: gemm_bf16_2cta_kernel<2, 2><<<grid, block, smem_for(2, 2), st>>>(tmA, tmB, tmC, bias, resid, M, N, K, flags); break;
+        default: gemm_bf16_2cta_kernel<3, 2><<<grid, block, smem_for(3, 2), st>>>(tmA, tmB, tmC, bias, resid, M, N, K, flags); break;
     }
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
