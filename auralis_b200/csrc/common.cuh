@@ -270,6 +270,13 @@ template <> __device__ __forceinline__ float from_f32<float>(float v) { return v
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 
+// two fp32 -> one 32-bit word of 16-bit values: IEEE fp16 when f16, bf16 otherwise (the GEMMs' 16-bit epilogue)
+__device__ __forceinline__ uint32_t pack16(float a, float b, bool f16) {
+    if (f16) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
 // tanh-GELU ("gelu_new", checkpoint_converter.py:197)
 __device__ __forceinline__ float gelu_new(float x) {
     const float k = 0.7978845608028654f;   // sqrt(2/pi)

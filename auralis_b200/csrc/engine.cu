@@ -183,7 +183,9 @@ private:
     xtts_config cfg;
     int H, L, NH, FF, V, Vpad, B, NSLOT, CAP, MAXP, max_pages, SEENW, S;
     int prefill_rows_cap;
-    bool bf16;
+    bool bf16;                    // 16-bit fast mode (tcgen05 GEMMs, 16-bit KV): bf16 operands, or IEEE fp16 when `f16`
+    bool f16 = false;             // precision fp16: same kernels, fp16 operands (3 more mantissa bits than bf16, range is ample here)
+    int gflag = 0;                // GEMM_F16 in fp16 mode
     cudaStream_t st = nullptr;
     cudaStream_t st_voc = nullptr;                       // the vocoder's own (low-priority) stream: runs beside the decode step
     static constexpr int kMaxMicro = 4;
@@ -338,6 +340,12 @@ private:
     void head_and_sample(int M, const int* row_index, const int* slots_dev, const int* lat_pos, int advance_ctx, bool do_sample,
                          bool pdl_first = true);
     void decode_layers_rows(int r0, int Mi, cudaStream_t s, bool pdl_first, double ctx_sum, int branch);
+    // split-K reduction + bias + residual + LayerNorm into the 16-bit operand buffer, in the engine's 16-bit format
+    void reduce_ln16(float* X, const float* part, int splits, const float* bias, const float* w, const float* b, __nv_bfloat16* Y, int M,
+                     cudaStream_t s, bool pdl, DepFlag dep) {
+        if (f16) launch_residual_reduce_layernorm<__half>(X, part, splits, bias, w, b, reinterpret_cast<__half*>(Y), M, H, cfg.ln_eps, s, pdl, dep);
+        else launch_residual_reduce_layernorm<__nv_bfloat16>(X, part, splits, bias, w, b, Y, M, H, cfg.ln_eps, s, pdl, dep);
+    }
     void decode_layers_chain(int M);
     void init_slots(const std::vector<Sequence*>& seqs, const int32_t* forced, int n_forced);
     void release_pages(Sequence& s);
@@ -398,7 +406,10 @@ Engine::Engine(const xtts_config& c) : cfg(c) {
     max_pages = ceil_div(MAXP + CAP, kPageTokens);
     SEENW = ceil_div(V, 32);
     S = std::max(1, c.max_speakers);
-    bf16 = c.precision == XTTS_PRECISION_BF16;
+    bf16 = c.precision == XTTS_PRECISION_BF16 || c.precision == XTTS_PRECISION_FP16;
+    f16 = c.precision == XTTS_PRECISION_FP16;
+    gflag = f16 ? GEMM_F16 : 0;
+    if (c.precision != XTTS_PRECISION_FP32 && !bf16) throw std::runtime_error("unknown precision");
     if (bf16) { std::string err; if (!gemm_tc_init(&err)) throw std::runtime_error(err); }
     // the decode step is a chain of short dependent kernels: its streams get the highest priority, the vocoder (long
     // throughput kernels on its own stream) the lowest, so a decode kernel never queues behind vocoder CTAs that have
@@ -594,7 +605,8 @@ void Engine::make_linear(Linear& lin, const std::string& wname, const std::strin
     lin.w32.alloc(t.size()); lin.w32.upload(t.data(), t.size(), st);
     if (bf16) {
         lin.w16.alloc(t.size());
-        launch_f32_to_bf16(lin.w32.p, lin.w16.p, t.size(), st);
+        if (f16) launch_f32_to_f16(lin.w32.p, reinterpret_cast<__half*>(lin.w16.p), t.size(), st);
+        else launch_f32_to_bf16(lin.w32.p, lin.w16.p, t.size(), st);
         CUDA_CHECK(cudaStreamSynchronize(st));
         lin.w32.release();
         weight_bytes += t.size() * 2;
@@ -829,7 +841,7 @@ SampleState Engine::sample_state() const {
 
 void Engine::gemm(const void* A, const Linear& lin, const float* resid, void* out, int M, int flags, bool pdl) {
     if (bf16)
-        launch_gemm_bf16_tc(reinterpret_cast<const __nv_bfloat16*>(A), lin.w16.p, lin.b.p, resid, out, M, lin.N, lin.K, flags, st, pdl);
+        launch_gemm_bf16_tc(reinterpret_cast<const __nv_bfloat16*>(A), lin.w16.p, lin.b.p, resid, out, M, lin.N, lin.K, flags | gflag, st, pdl);
     else
         launch_gemm_f32(reinterpret_cast<const float*>(A), lin.w32.p, lin.b.p, resid, reinterpret_cast<float*>(out), M, lin.N, lin.K,
                         flags & ~GEMM_OUT_BF16, st);
@@ -848,7 +860,8 @@ void Engine::layers_forward(int M, bool prefill, int nseq, int max_nq) {
     const bool splitk = bf16 && !prefill && use_splitk && M <= NSLOT && (H / 64) % 4 == 0 && (FF / 64) % 8 == 0;
     const bool pdl = !prefill && use_pdl;            // decode chain: programmatic dependent launch
     auto ln = [&](const float* w, const float* b) {
-        if (bf16) launch_layernorm<__nv_bfloat16>(wX.p, w, b, wXn16.p, M, H, cfg.ln_eps, st, pdl);
+        if (f16) launch_layernorm<__half>(wX.p, w, b, reinterpret_cast<__half*>(wXn16.p), M, H, cfg.ln_eps, st, pdl);
+        else if (bf16) launch_layernorm<__nv_bfloat16>(wX.p, w, b, wXn16.p, M, H, cfg.ln_eps, st, pdl);
         else launch_layernorm<float>(wX.p, w, b, wXn32.p, M, H, cfg.ln_eps, st, pdl);
     };
     if (splitk) ln(layers[0]->ln1w.p, layers[0]->ln1b.p);
@@ -857,28 +870,30 @@ void Engine::layers_forward(int M, bool prefill, int nseq, int max_nq) {
         if (!splitk) ln(ly.ln1w.p, ly.ln1b.p);
         gemm(Xn, ly.qkv, nullptr, wQKV.p, M, 0, pdl);
         if (prefill) {
-            if (bf16) launch_kv_write<__nv_bfloat16>(wQKV.p, M, d_row_slot.p, d_row_pos.p, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p, NH, st);
+            if (f16) launch_kv_write<__half>(wQKV.p, M, d_row_slot.p, d_row_pos.p, d_ctx_len.p, d_block_tables.p, max_pages, reinterpret_cast<__half*>(k16[l]->p), reinterpret_cast<__half*>(v16[l]->p), NH, st);
+            else if (bf16) launch_kv_write<__nv_bfloat16>(wQKV.p, M, d_row_slot.p, d_row_pos.p, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p, NH, st);
             else launch_kv_write<float>(wQKV.p, M, d_row_slot.p, d_row_pos.p, d_ctx_len.p, d_block_tables.p, max_pages, k32[l]->p, v32[l]->p, NH, st);
             AttnLayout A;
             A.q = wQKV.p; A.k = wQKV.p + H; A.v = wQKV.p + 2 * H;
             A.q_row_stride = 3 * H; A.kv_row_stride = 3 * H; A.q_head_stride = kHeadDim; A.kv_head_stride = kHeadDim;
             A.heads = NH; A.scale = 0.125f; A.causal = 1;
-            if (bf16) launch_attn_generic<__nv_bfloat16>(A, d_attnseq.p, nseq, max_nq, wATT16.p, H, st);
+            if (f16) launch_attn_generic<__half>(A, d_attnseq.p, nseq, max_nq, reinterpret_cast<__half*>(wATT16.p), H, st);
+            else if (bf16) launch_attn_generic<__nv_bfloat16>(A, d_attnseq.p, nseq, max_nq, wATT16.p, H, st);
             else launch_attn_generic<float>(A, d_attnseq.p, nseq, max_nq, wATT32.p, H, st);
         } else {
             // (the attention kernel appends this step's K/V to the cache itself)
-            if (bf16) launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p, wATT16.p, NH, st, decode_ctx_sum, pdl);
+            if (f16) launch_attn_decode<__half, __half>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, reinterpret_cast<__half*>(k16[l]->p), reinterpret_cast<__half*>(v16[l]->p), reinterpret_cast<__half*>(wATT16.p), NH, st, decode_ctx_sum, pdl);
+            else if (bf16) launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p, wATT16.p, NH, st, decode_ctx_sum, pdl);
             else launch_attn_decode<float, float>(wQKV.p, d_active.p, M, d_ctx_len.p, d_block_tables.p, max_pages, k32[l]->p, v32[l]->p, wATT32.p, NH, st, decode_ctx_sum, pdl);
         }
         if (splitk) {
-            launch_gemm_bf16_tc_splitk(wATT16.p, ly.o.w16.p, wPART.p, M, H, H, 4, st, pdl);
-            launch_residual_reduce_layernorm<__nv_bfloat16>(wX.p, wPART.p, 4, ly.o.b.p, ly.ln2w.p, ly.ln2b.p, wXn16.p, M, H, cfg.ln_eps, st, pdl);
+            launch_gemm_bf16_tc_splitk(wATT16.p, ly.o.w16.p, wPART.p, M, H, H, 4, st, pdl, DepFlag(), gflag);
+            reduce_ln16(wX.p, wPART.p, 4, ly.o.b.p, ly.ln2w.p, ly.ln2b.p, wXn16.p, M, st, pdl, DepFlag());
             gemm(Xn, ly.fc, nullptr, FFb, M, GEMM_GELU | oflag, pdl);
-            launch_gemm_bf16_tc_splitk(wFF16.p, ly.proj.w16.p, wPART.p, M, H, FF, 8, st, pdl);
+            launch_gemm_bf16_tc_splitk(wFF16.p, ly.proj.w16.p, wPART.p, M, H, FF, 8, st, pdl, DepFlag(), gflag);
             const bool last = (l + 1 == L);
-            launch_residual_reduce_layernorm<__nv_bfloat16>(wX.p, wPART.p, 8, ly.proj.b.p, last ? nullptr : layers[l + 1]->ln1w.p,
-                                                            last ? nullptr : layers[l + 1]->ln1b.p, last ? nullptr : wXn16.p, M, H,
-                                                            cfg.ln_eps, st, pdl);
+            reduce_ln16(wX.p, wPART.p, 8, ly.proj.b.p, last ? nullptr : layers[l + 1]->ln1w.p,
+                        last ? nullptr : layers[l + 1]->ln1b.p, last ? nullptr : wXn16.p, M, st, pdl, DepFlag());
         } else {
             gemm(ATT, ly.o, wX.p, wX.p, M, GEMM_RESID, pdl);
             ln(ly.ln2w.p, ly.ln2b.p);
@@ -893,7 +908,8 @@ void Engine::head_and_sample(int M, const int* row_index, const int* slots_dev, 
                              bool pdl_first) {
     const bool pdl = advance_ctx && use_pdl;         // decode step only
     const bool pdl0 = pdl && pdl_first;              // (the first kernel after a stream join takes a full dependency)
-    if (bf16) launch_head_norms<__nv_bfloat16>(wX.p, row_index, lnfw.p, lnfb.p, fnw.p, fnb.p, wY16.p, d_latents.p, slots_dev, lat_pos, d_n_gen.p, CAP, M, H, cfg.ln_eps, st, pdl0);
+    if (f16) launch_head_norms<__half>(wX.p, row_index, lnfw.p, lnfb.p, fnw.p, fnb.p, reinterpret_cast<__half*>(wY16.p), d_latents.p, slots_dev, lat_pos, d_n_gen.p, CAP, M, H, cfg.ln_eps, st, pdl0);
+    else if (bf16) launch_head_norms<__nv_bfloat16>(wX.p, row_index, lnfw.p, lnfb.p, fnw.p, fnb.p, wY16.p, d_latents.p, slots_dev, lat_pos, d_n_gen.p, CAP, M, H, cfg.ln_eps, st, pdl0);
     else launch_head_norms<float>(wX.p, row_index, lnfw.p, lnfb.p, fnw.p, fnb.p, wY32.p, d_latents.p, slots_dev, lat_pos, d_n_gen.p, CAP, M, H, cfg.ln_eps, st, pdl0);
     gemm(bf16 ? (void*)wY16.p : (void*)wY32.p, mel_head, nullptr, wLOG.p, M, 0, pdl);
     if (do_sample) launch_sample(wLOG.p, Vpad, slots_dev, M, V, sample_state(), advance_ctx, st, pdl);
@@ -1025,27 +1041,29 @@ void Engine::decode_layers_rows(int r0, int Mi, cudaStream_t s, bool pdl_first, 
     };
     DepFlag d0;
     if (flags) d0.arrive = F + 0;                        // the step's first LayerNorm: full wait (the row build), then counts in
-    launch_layernorm<__nv_bfloat16>(X, layers[0]->ln1w.p, layers[0]->ln1b.p, Xn, Mi, H, cfg.ln_eps, s, pdl && pdl_first, d0);
+    if (f16) launch_layernorm<__half>(X, layers[0]->ln1w.p, layers[0]->ln1b.p, reinterpret_cast<__half*>(Xn), Mi, H, cfg.ln_eps, s, pdl && pdl_first, d0);
+    else launch_layernorm<__nv_bfloat16>(X, layers[0]->ln1w.p, layers[0]->ln1b.p, Xn, Mi, H, cfg.ln_eps, s, pdl && pdl_first, d0);
     unsigned n_ln1 = (unsigned)Mi;
     for (int l = 0; l < L; ++l) {
         Layer& ly = *layers[l];
-        const unsigned n_qkv = (unsigned)launch_gemm_bf16_tc(Xn, ly.qkv.w16.p, ly.qkv.b.p, nullptr, QKV, Mi, ly.qkv.N, ly.qkv.K, 0, s, pdl,
+        const unsigned n_qkv = (unsigned)launch_gemm_bf16_tc(Xn, ly.qkv.w16.p, ly.qkv.b.p, nullptr, QKV, Mi, ly.qkv.N, ly.qkv.K, gflag, s, pdl,
                                                              dep(l, 0, n_ln1, l, 1));
-        const unsigned n_att = (unsigned)launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(QKV, act, Mi, d_ctx_len.p, d_block_tables.p, max_pages,
-                                                                                       k16[l]->p, v16[l]->p, ATT, NH, s, ctx_sum, pdl,
-                                                                                       dep(l, 1, n_qkv, l, 2));
-        const unsigned n_o = (unsigned)launch_gemm_bf16_tc_splitk(ATT, ly.o.w16.p, PART, Mi, H, H, 4, s, pdl, dep(l, 2, n_att, l, 3));
-        launch_residual_reduce_layernorm<__nv_bfloat16>(X, PART, 4, ly.o.b.p, ly.ln2w.p, ly.ln2b.p, Xn, Mi, H, cfg.ln_eps, s, pdl,
-                                                        dep(l, 3, n_o, l, 4));
+        const unsigned n_att = f16
+            ? (unsigned)launch_attn_decode<__half, __half>(QKV, act, Mi, d_ctx_len.p, d_block_tables.p, max_pages, reinterpret_cast<__half*>(k16[l]->p),
+                                                           reinterpret_cast<__half*>(v16[l]->p), reinterpret_cast<__half*>(ATT), NH, s, ctx_sum, pdl,
+                                                           dep(l, 1, n_qkv, l, 2))
+            : (unsigned)launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(QKV, act, Mi, d_ctx_len.p, d_block_tables.p, max_pages, k16[l]->p, v16[l]->p,
+                                                                         ATT, NH, s, ctx_sum, pdl, dep(l, 1, n_qkv, l, 2));
+        const unsigned n_o = (unsigned)launch_gemm_bf16_tc_splitk(ATT, ly.o.w16.p, PART, Mi, H, H, 4, s, pdl, dep(l, 2, n_att, l, 3), gflag);
+        reduce_ln16(X, PART, 4, ly.o.b.p, ly.ln2w.p, ly.ln2b.p, Xn, Mi, s, pdl, dep(l, 3, n_o, l, 4));
         const unsigned n_fc = (unsigned)launch_gemm_bf16_tc(Xn, ly.fc.w16.p, ly.fc.b.p, nullptr, FFb, Mi, ly.fc.N, ly.fc.K,
-                                                            GEMM_GELU | GEMM_OUT_BF16, s, pdl, dep(l, 4, (unsigned)Mi, l, 5));
-        const unsigned n_pr = (unsigned)launch_gemm_bf16_tc_splitk(FFb, ly.proj.w16.p, PART, Mi, H, FF, 8, s, pdl, dep(l, 5, n_fc, l, 6));
+                                                            GEMM_GELU | GEMM_OUT_BF16 | gflag, s, pdl, dep(l, 4, (unsigned)Mi, l, 5));
+        const unsigned n_pr = (unsigned)launch_gemm_bf16_tc_splitk(FFb, ly.proj.w16.p, PART, Mi, H, FF, 8, s, pdl, dep(l, 5, n_fc, l, 6), gflag);
         const bool last = (l + 1 == L);
         DepFlag dl = dep(l, 6, n_pr, last ? l : l + 1, 0);
         if (last) dl.arrive = nullptr;                   // the head kernel behind it takes a full dependency
-        launch_residual_reduce_layernorm<__nv_bfloat16>(X, PART, 8, ly.proj.b.p, last ? nullptr : layers[l + 1]->ln1w.p,
-                                                        last ? nullptr : layers[l + 1]->ln1b.p, last ? nullptr : Xn, Mi, H,
-                                                        cfg.ln_eps, s, pdl, dl);
+        reduce_ln16(X, PART, 8, ly.proj.b.p, last ? nullptr : layers[l + 1]->ln1w.p, last ? nullptr : layers[l + 1]->ln1b.p,
+                    last ? nullptr : Xn, Mi, s, pdl, dl);
         n_ln1 = (unsigned)Mi;
     }
 }
@@ -1088,7 +1106,7 @@ void Engine::decode_step(const std::vector<int>& active) {
     const int M = (int)active.size();
     d_active.upload(active.data(), M, st);
     const bool fast = bf16 && use_splitk && M <= NSLOT && (H / 64) % 4 == 0 && (FF / 64) % 8 == 0;
-    const bool chain = fast && use_chain && decode_chain_supported(M, H, FF);
+    const bool chain = fast && use_chain && !f16 && decode_chain_supported(M, H, FF);
     const int nmb = (fast && !chain && n_micro > 1 && M >= micro_min_rows) ? std::min(n_micro, (int)kMaxMicro) : 1;
     auto enqueue = [&] {
         launch_build_decode_rows(d_active.p, M, d_last_tok.p, d_n_gen.p, tables(), wX.p, st, use_pdl,

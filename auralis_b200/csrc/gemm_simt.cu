@@ -120,6 +120,16 @@ void launch_gemm_f32(const float* A, const float* W, const float* bias, const fl
     KERNEL_CHECK();
 }
 
+__global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = __float2half_rn(in[i]);
+}
+void launch_f32_to_f16(const float* in, __half* out, size_t n, cudaStream_t st) {
+    if (n == 0) return;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
+    f32_to_f16_kernel<<<blocks, 256, 0, st>>>(in, out, n);
+    COUNT_LAUNCH(); KERNEL_CHECK();
+}
+
 void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st) {
     if (n == 0) return;
     int blocks = (int)((n + 255) / 256);

@@ -118,6 +118,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int kb_per = (total_kb + gridDim.z - 1) / gridDim.z;
     const int kb_begin = blockIdx.z * kb_per;
     const int num_kb = max(0, min(total_kb, kb_begin + kb_per) - kb_begin);
+    const int flags_in = flags;
     if (gridDim.z > 1) {
         out = reinterpret_cast<float*>(out) + (size_t)blockIdx.z * M * N;
         bias = nullptr; flags = 0;
@@ -166,7 +167,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN);
+            // operand format bits of the instruction descriptor: bf16 (1) by default, IEEE fp16 (0) with GEMM_F16
+            const uint32_t idesc = (flags_in & GEMM_F16) ? (make_idesc(BN) & ~((1u << 7) | (1u << 10))) : make_idesc(BN);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
@@ -225,15 +227,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 if (flags & GEMM_OUT_BF16) {
                     __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)row * N + nb;
+                    const bool f16 = (flags & GEMM_F16) != 0;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         uint4 pk;
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
-                        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-                        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-                        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                        pk.x = pack16(v[8 * i], v[8 * i + 1], f16); pk.y = pack16(v[8 * i + 2], v[8 * i + 3], f16);
+                        pk.z = pack16(v[8 * i + 4], v[8 * i + 5], f16); pk.w = pack16(v[8 * i + 6], v[8 * i + 7], f16);
                         reinterpret_cast<uint4*>(op)[i] = pk;
                     }
                 } else {
@@ -644,7 +643,8 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const fl
 
 // split-K variant for the skinny decode GEMMs (N = hidden): partials[z][M][N] = A[:, kz] . W[:, kz]^T, fp32, no epilogue
 int launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, float* partials, int M, int N, int K,
-                               int splits, cudaStream_t st, bool pdl, DepFlag dep) {
+                               int splits, cudaStream_t st, bool pdl, DepFlag dep, int flags) {
+    flags &= GEMM_F16;
     if (M <= 0 || N <= 0) return 0;
     if (K % BK != 0 || N % 32 != 0 || splits < 1 || (K / BK) % splits != 0) throw CudaError("gemm_bf16_tc_splitk: bad shape");
     if (!g_encode) { std::string err; if (!gemm_tc_init(&err)) throw CudaError(err); }
@@ -657,9 +657,9 @@ int launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, f
     const int abox = a_box_rows_for(M);
     encode_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint32_t)abox);
     encode_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint32_t)bn);
-    if (bn == 128) return launch_bn<128>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox, pdl, dep);
-    if (bn == 64) return launch_bn<64>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox, pdl, dep);
-    return launch_bn<32>(tmA, tmB, nullptr, nullptr, partials, M, N, K, 0, st, splits, abox, pdl, dep);
+    if (bn == 128) return launch_bn<128>(tmA, tmB, nullptr, nullptr, partials, M, N, K, flags, st, splits, abox, pdl, dep);
+    if (bn == 64) return launch_bn<64>(tmA, tmB, nullptr, nullptr, partials, M, N, K, flags, st, splits, abox, pdl, dep);
+    return launch_bn<32>(tmA, tmB, nullptr, nullptr, partials, M, N, K, flags, st, splits, abox, pdl, dep);
 }
 
 

@@ -87,10 +87,10 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // D = f32, A = B = bf16, both K-major, M = 256 (the pair), N = BN
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
-__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t acc) {
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(acc) : "memory");
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 // completion of every MMA issued so far -> arrive on `bar` in both CTAs of the pair
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
@@ -163,6 +163,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     } else if (warp == 1) {
         if (leader && lane == 0) {
             int it = 0, lt = 0;
+            const uint32_t idesc = (flags & GEMM_F16) ? (kIdesc & ~((1u << 7) | (1u << 10))) : kIdesc;      // fp16 / bf16 operands
             for (int tile = cid; tile < total; tile += n_clusters, ++lt) {
                 const int ab = lt & 1;
                 mbar_wait(&tmem_empty[ab], (uint32_t)(((lt >> 1) & 1) ^ 1), 2);
@@ -180,7 +181,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k)
                             umma_bf16_2cta(acc, make_sw128_desc(a_addr + k * UMMA_K * 2), make_sw128_desc(b_addr + k * UMMA_K * 2),
-                                           (kb | j | k) != 0 ? 1u : 0u);
+                                           idesc, (kb | j | k) != 0 ? 1u : 0u);
                     }
                     umma_commit_pair(&empty_bar[s]);        // the slot is free in both CTAs once these MMAs have read it
                 }
@@ -245,15 +246,12 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 __syncwarp();
                 if (flags & GEMM_OUT_BF16) {
                     // 32 rows x 64 B, SWIZZLE_64B: 16-byte chunk j of row r sits at chunk j ^ ((r >> 1) & 3)
+                    const bool f16 = (flags & GEMM_F16) != 0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint4 pk;
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
-                        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-                        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-                        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                        pk.x = pack16(v[8 * j], v[8 * j + 1], f16); pk.y = pack16(v[8 * j + 2], v[8 * j + 3], f16);
+                        pk.z = pack16(v[8 * j + 4], v[8 * j + 5], f16); pk.w = pack16(v[8 * j + 6], v[8 * j + 7], f16);
                         *reinterpret_cast<uint4*>(box + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
                     }
                 } else {

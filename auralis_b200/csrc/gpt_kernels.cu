@@ -254,6 +254,14 @@ template <> struct KVec<__nv_bfloat16> {
         for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(b[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
     }
 };
+template <> struct KVec<__half> {
+    static constexpr int X = 8;
+    static __device__ __forceinline__ void unpack(const uint4& raw, float* f) {
+        const __half2* b = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(b[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    }
+};
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {          // streaming 16-byte load: KV is read once per step
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -857,6 +865,7 @@ void launch_layernorm(const float* X, const float* w, const float* b, TOut* Y, i
 }
 template void launch_layernorm<float>(const float*, const float*, const float*, float*, int, int, float, cudaStream_t, bool, DepFlag);
 template void launch_layernorm<__nv_bfloat16>(const float*, const float*, const float*, __nv_bfloat16*, int, int, float, cudaStream_t, bool, DepFlag);
+template void launch_layernorm<__half>(const float*, const float*, const float*, __half*, int, int, float, cudaStream_t, bool, DepFlag);
 
 template <typename TOut>
 void launch_residual_reduce_layernorm(float* X, const float* partials, int splits, const float* bias, const float* w,
@@ -868,6 +877,7 @@ void launch_residual_reduce_layernorm(float* X, const float* partials, int split
 }
 template void launch_residual_reduce_layernorm<float>(float*, const float*, int, const float*, const float*, const float*, float*, int, int, float, cudaStream_t, bool, DepFlag);
 template void launch_residual_reduce_layernorm<__nv_bfloat16>(float*, const float*, int, const float*, const float*, const float*, __nv_bfloat16*, int, int, float, cudaStream_t, bool, DepFlag);
+template void launch_residual_reduce_layernorm<__half>(float*, const float*, int, const float*, const float*, const float*, __half*, int, int, float, cudaStream_t, bool, DepFlag);
 
 template <typename TOut>
 void launch_head_norms(const float* X, const int* row_index, const float* lnf_w, const float* lnf_b,
@@ -882,6 +892,7 @@ void launch_head_norms(const float* X, const int* row_index, const float* lnf_w,
 }
 template void launch_head_norms<float>(const float*, const int*, const float*, const float*, const float*, const float*, float*, float*, const int*, const int*, const int*, int, int, int, float, cudaStream_t, bool);
 template void launch_head_norms<__nv_bfloat16>(const float*, const int*, const float*, const float*, const float*, const float*, __nv_bfloat16*, float*, const int*, const int*, const int*, int, int, int, float, cudaStream_t, bool);
+template void launch_head_norms<__half>(const float*, const int*, const float*, const float*, const float*, const float*, __half*, float*, const int*, const int*, const int*, int, int, int, float, cudaStream_t, bool);
 
 template <typename TKV>
 void launch_kv_write(const float* QKV, int M, const int* row_slot, const int* row_pos, const int* ctx_len,
@@ -894,6 +905,7 @@ void launch_kv_write(const float* QKV, int M, const int* row_slot, const int* ro
 }
 template void launch_kv_write<float>(const float*, int, const int*, const int*, const int*, const int*, int, float*, float*, int, cudaStream_t);
 template void launch_kv_write<__nv_bfloat16>(const float*, int, const int*, const int*, const int*, const int*, int, __nv_bfloat16*, __nv_bfloat16*, int, cudaStream_t);
+template void launch_kv_write<__half>(const float*, int, const int*, const int*, const int*, const int*, int, __half*, __half*, int, cudaStream_t);
 
 template <typename TKV, typename TOut>
 int launch_attn_decode(const float* QKV, const int* active, int M, const int* ctx_len, const int* block_tables,
@@ -926,6 +938,7 @@ int launch_attn_decode(const float* QKV, const int* active, int M, const int* ct
 }
 template int launch_attn_decode<float, float>(const float*, const int*, int, const int*, const int*, int, float*, float*, float*, int, cudaStream_t, double, bool, DepFlag);
 template int launch_attn_decode<__nv_bfloat16, __nv_bfloat16>(const float*, const int*, int, const int*, const int*, int, __nv_bfloat16*, __nv_bfloat16*, __nv_bfloat16*, int, cudaStream_t, double, bool, DepFlag);
+template int launch_attn_decode<__half, __half>(const float*, const int*, int, const int*, const int*, int, __half*, __half*, __half*, int, cudaStream_t, double, bool, DepFlag);
 
 template <typename TOut>
 void launch_attn_generic(AttnLayout L, const AttnSeq* seqs, int nseq, int max_nq, TOut* out, int out_row_stride,
@@ -937,6 +950,7 @@ void launch_attn_generic(AttnLayout L, const AttnSeq* seqs, int nseq, int max_nq
 }
 template void launch_attn_generic<float>(AttnLayout, const AttnSeq*, int, int, float*, int, cudaStream_t);
 template void launch_attn_generic<__nv_bfloat16>(AttnLayout, const AttnSeq*, int, int, __nv_bfloat16*, int, cudaStream_t);
+template void launch_attn_generic<__half>(AttnLayout, const AttnSeq*, int, int, __half*, int, cudaStream_t);
 
 void launch_sample(const float* logits, int ld_logits, const int* active, int M, int V, SampleState s,
                    int advance_ctx, cudaStream_t st, bool pdl) {

@@ -10,7 +10,8 @@ namespace xtts {
 //   flags: GEMM_GELU  -> gelu_new after bias
 //          GEMM_RESID -> out = resid + (...)   (resid may alias out)
 // ------------------------------------------------------------------------------------------
-enum : int { GEMM_GELU = 1, GEMM_RESID = 2, GEMM_OUT_BF16 = 4 };
+// GEMM_OUT_BF16: 16-bit output in the operand format;  GEMM_F16: the 16-bit operands (and that output) are IEEE fp16, not bf16
+enum : int { GEMM_GELU = 1, GEMM_RESID = 2, GEMM_OUT_BF16 = 4, GEMM_F16 = 8 };
 
 // fp32 CUDA-core path (parity mode; also the GPU-side reference for the tcgen05 path)
 void launch_gemm_f32(const float* A, const float* W, const float* bias, const float* resid, float* out,
@@ -29,7 +30,7 @@ bool gemm_2cta_supported(int M, int N, int K);
 void launch_gemm_bf16_2cta(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, const float* resid,
                            void* out, int M, int N, int K, int flags, cudaStream_t st);
 int launch_gemm_bf16_tc_splitk(const __nv_bfloat16* A, const __nv_bfloat16* W, float* partials, int M, int N, int K,
-                               int splits, cudaStream_t st, bool pdl = false, DepFlag dep = DepFlag());
+                               int splits, cudaStream_t st, bool pdl = false, DepFlag dep = DepFlag(), int flags = 0);
 
 // Fused decode chain (gemm_tcgen05.cu): one persistent launch runs, for one layer boundary of the decode step,
 //   proj (split-K) -> residual+LN2 -> fc+gelu -> fc2 (split-K) -> residual+LN1(next layer) -> qkv(next layer)
@@ -53,6 +54,7 @@ void trace_set_gpt(TraceBuf b);
 void trace_set_conv(TraceBuf b);
 
 void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st);
+void launch_f32_to_f16(const float* in, __half* out, size_t n, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------
 // GPT glue kernels

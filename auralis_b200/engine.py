@@ -81,7 +81,7 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
         8xB200 box") — one native engine (full weight replica, own scheduler thread, own streams) per listed GPU in THIS
         process; every text chunk goes to the engine with the least work in flight, results are re-assembled in request
         order by the façade as before.  `max_concurrency` is per GPU.  Default: the single GPU `device`."""
-        prec = {"fp32": native.PRECISION_FP32, "bf16": native.PRECISION_BF16}[precision]
+        prec = {"fp32": native.PRECISION_FP32, "bf16": native.PRECISION_BF16, "fp16": native.PRECISION_FP16}[precision]
         self.dims = dims
         self.precision = precision
         self.devices = [int(d) for d in devices] if devices else [int(device)]
@@ -157,21 +157,21 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
     @property
     def dtype(self):
         import torch
-        return torch.bfloat16 if self.precision == "bf16" else torch.float32
+        return {"bf16": torch.bfloat16, "fp16": torch.float16}.get(self.precision, torch.float32)
 
     def get_memory_usage_curve(self):
         """XTTSv2.py:152-171 fits a polynomial to measured vLLM footprints; here the footprint is known exactly from the
         geometry: weights + per-slot state (paged KV for a full-length sequence, latent ring, token rows) x max_concurrency
         + the vocoder workspace.  Sets (and returns) `max_gb_for_vllm_model`, the attribute the reference's engine exposes."""
         g, v = self.dims.gpt, self.dims.voc
-        kv_elem = 2 if self.precision == "bf16" else 4
-        w_elem = 2 if self.precision == "bf16" else 4
+        kv_elem = 2 if self.precision in ("bf16", "fp16") else 4
+        w_elem = 2 if self.precision in ("bf16", "fp16") else 4
         gpt_w = g.layers * (4 * g.hidden * g.hidden + 2 * g.hidden * g.ff) * w_elem
         pages = -(-(g.max_prompt_rows + g.max_audio_tokens) // 32)
         per_slot = pages * 32 * 2 * g.layers * g.hidden * kv_elem + g.max_audio_tokens * g.hidden * 4 + 3 * g.max_audio_tokens * 4
         tz = v.z_frames(g.max_audio_tokens)
         widest = max((v.init_ch >> (i + 1)) * int(np.prod(v.up_rates[: i + 1])) for i in range(len(v.up_rates)))
-        voc_ws = 8 * tz * (5 * widest * 4 + (5 * widest * 2 if self.precision == "bf16" else 0) + v.hop * 4)
+        voc_ws = 8 * tz * (5 * widest * 4 + (5 * widest * 2 if self.precision in ("bf16", "fp16") else 0) + v.hop * 4)
         total = gpt_w + per_slot * (self.max_concurrency + 1) + voc_ws
         self.max_gb_for_vllm_model = total / 2 ** 30
         return self.max_gb_for_vllm_model

@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libxtts_b200.so")
 
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
+PRECISION_FP16 = 2
 ERR_CANCELLED = -5
 
 

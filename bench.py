@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--requests", type=int, default=32, help="requests per GPU")
     ap.add_argument("--chars", type=int, default=1000)
     ap.add_argument("--max-tokens", type=int, default=605)
@@ -510,12 +510,13 @@ def main():
         "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "dtype": {"bf16": "bf16", "fp16": "f16"}.get(args.precision, "f32"), "data": "synthetic",
         "config": {"workload": workload, "chunks_per_gpu": n_chunks, "tokens_per_chunk": max_tok,
                    "audio_s_per_step": audio_s_dev / args.steps, "geometry": "small (INVALID as a bench number)" if args.small else "XTTSv2 full: GPT-2 30x1024x16h, HiFi-GAN 512ch, random-init",
                    "parallelism": f"dp{args.gpus} (requests sharded, waveform all-gather only)",
-                   "gpt_compute": "bf16 tcgen05 GEMM operands + bf16 KV, fp32 accumulate/residual/LN/softmax" if args.precision == "bf16" else "fp32",
-                   "vocoder_compute": "fp16 tcgen05 implicit-GEMM convs (fp32 accumulate, fp32 residual stream)" if args.precision == "bf16" else "fp32",
+                   "gpt_compute": (f"{args.precision} tcgen05 GEMM operands + {args.precision} KV, fp32 accumulate/residual/LN/softmax"
+                                   if args.precision != "fp32" else "fp32"),
+                   "vocoder_compute": "fp16 tcgen05 implicit-GEMM convs (fp32 accumulate, fp32 residual stream)" if args.precision != "fp32" else "fp32",
                    "l2": "no explicit flush: per-step working set (0.76 GB weights + >5 GB KV + 0.4 GB vocoder activations) >> 126 MB L2",
                    "timing": "CUDA events on the engine stream (first recorded with the device idle after barrier + synchronize, second "
                              "behind the last step's work); max over ranks; e2e: host wall clock around the public API calls",

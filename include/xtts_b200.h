@@ -29,6 +29,8 @@ extern "C" {
 
 #define XTTS_PRECISION_FP32 0 /* parity mode: fp32 CUDA-core GEMMs, fp32 KV cache            */
 #define XTTS_PRECISION_BF16 1 /* fast mode: bf16 tcgen05 GEMMs (fp32 accumulate), bf16 KV    */
+#define XTTS_PRECISION_FP16 2 /* fast mode with IEEE fp16 operands and KV: the same kernels at the same rate, 11 significand
+                                 bits instead of 8 — closer to the fp32 parity mode (the reference's GPU vocoder is fp16 too) */
 
 typedef struct xtts_engine xtts_engine;
 

@@ -118,6 +118,20 @@ def engine_full_bf16(dims_full, state_full, speakers_full):
     eng.close()
 
 
+@pytest.fixture(scope="module")
+def engine_small_fp16(dims_small, state_small, speakers_small):
+    eng = _make_engine(dims_small, state_small, speakers_small, 2)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def engine_full_fp16(dims_full, state_full, speakers_full):
+    eng = _make_engine(dims_full, state_full, speakers_full, 2, max_batch=4)
+    yield eng
+    eng.close()
+
+
 def text_ids(dims, n, seed):
     """[bos] + n synthetic BPE ids + [eos] (XTTSv2.py:519-522); ids 0/1 stand in for [START]/[STOP]."""
     rng = np.random.RandomState(seed)

@@ -360,3 +360,52 @@ def test_device_timer_brackets_a_batch(engine_small, dims_small):
     ms = engine_small.timer_stop_ms()
     wall_ms = (time.perf_counter() - t0) * 1e3
     assert 0.0 < ms <= wall_ms + 5.0, (ms, wall_ms)
+
+
+# ------------------------------------------------------------------------------------------------
+# precision "fp16": the tcgen05 fast path with IEEE fp16 operands / KV instead of bf16 (a tensor-core mode
+# closer to the parity mode — kind::f16 takes fp16 at the same rate, 11 significand bits instead of 8)
+# ------------------------------------------------------------------------------------------------
+def test_fp16_operand_mode_small(engine_small_fp16, dims_small, state_small, speakers_small):
+    orc = _orc(dims_small, state_small)
+    g = dims_small.gpt
+    ids = text_ids(dims_small, 17, 4)
+    osp = O.SamplingParams(temperature=0.0, repetition_penalty=5.0, max_tokens=40, stop_token=g.stop_audio_token)
+    toks, lats, lg = orc.generate(speakers_small[0][0], ids, osp, return_logits=True)
+    sp = Sampling(temperature=0.0, repetition_penalty=5.0, max_tokens=40, stop_token=g.stop_audio_token)
+    logits, lat, sampled = engine_small_fp16.gpt_teacher_forced(ids, 0, toks, sp)
+    err = np.abs(logits - lg.numpy()).max()
+    print("fp16 decode logits max err", err, "greedy agreement", int((sampled == np.array(toks)).sum()), "/", len(toks))
+    assert err < 0.01 * max(1.0, float(lg.abs().max()))                     # bf16 mode: 0.05
+    for k, a, b, margin in _margin_report(lg.numpy(), sampled, toks):
+        assert margin < 0.02, (k, a, b, margin)
+    res = engine_small_fp16.run_batch([(1, ids, 0, sp)], timeout_s=60, want_latents=True)
+    r, got, wav, glat = res[1]
+    assert np.isfinite(wav).all() and r.n_tokens >= 1
+    if list(got) == toks:                                   # same tokens (no near-tie flipped): the captured latents agree too
+        assert np.abs(glat - lats.numpy()).max() < 0.02
+
+
+def test_fp16_operand_mode_full_size_vs_bf16(engine_full_fp16, engine_full_bf16, dims_full, state_full, speakers_full):
+    """full geometry, 24 greedy tokens teacher-forced: the fp16-operand mode's logits are several times closer to the fp32
+    oracle than the bf16 mode's, through the same kernels (split-K GEMMs, paged attention, graph replay in run_batch)."""
+    orc = _orc(dims_full, state_full)
+    g = dims_full.gpt
+    ids = text_ids(dims_full, 14, 9)
+    osp = O.SamplingParams(temperature=0.0, repetition_penalty=5.0, max_tokens=24, stop_token=g.stop_audio_token)
+    toks, lats, lg = orc.generate(speakers_full[1][0], ids, osp, return_logits=True)
+    sp = Sampling(temperature=0.0, repetition_penalty=5.0, max_tokens=24, stop_token=g.stop_audio_token)
+    l16, lat16, s16 = engine_full_fp16.gpt_teacher_forced(ids, 1, toks, sp)
+    lbf, latbf, sbf = engine_full_bf16.gpt_teacher_forced(ids, 1, toks, sp)
+    e16, ebf = float(np.abs(l16 - lg.numpy()).max()), float(np.abs(lbf - lg.numpy()).max())
+    a16, abf = int((s16 == np.array(toks)).sum()), int((sbf == np.array(toks)).sum())
+    print(f"full geometry logits max err: fp16 operands {e16:.4f}, bf16 operands {ebf:.4f} (|logit| max {float(lg.abs().max()):.2f}); "
+          f"greedy agreement {a16} / {abf} of {len(toks)}; latents {float(np.abs(lat16 - lats.numpy()).max()):.4f} / {float(np.abs(latbf - lats.numpy()).max()):.4f}")
+    assert e16 < 0.5 * ebf and e16 < 0.01 * max(1.0, float(lg.abs().max()))
+    assert a16 >= abf
+    for k, a, b, margin in _margin_report(lg.numpy(), s16, toks):
+        assert margin < 0.03, (k, a, b, margin)
+    res = engine_full_fp16.run_batch([(i, ids, 1, sp) for i in range(3)], timeout_s=120)
+    for i in range(3):
+        assert res[i][0].n_tokens == 24 and np.isfinite(res[i][2]).all()
+        np.testing.assert_array_equal(res[i][1], res[0][1])
