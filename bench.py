@@ -393,7 +393,8 @@ def main():
     if args.sweep:
         ev_e2e, dt_e2e, acc_e2e, samples_e2e = 0.0, float("nan"), [], 0
     else:
-        ev_e2e, dt_e2e, acc_e2e, _ = timed(e2e_step, 1, args.steps)      # e2e = host wall clock: tokenisation and the host copies count
+        # two warm-up steps: the waveform gather alternates two sets of pinned staging buffers, both must exist before the clock
+        ev_e2e, dt_e2e, acc_e2e, _ = timed(e2e_step, 2, args.steps)      # e2e = host wall clock: tokenisation and the host copies count
         samples_e2e = sum(a[0] for a in acc_e2e)
         log(f"e2e arm: {dt_e2e:.2f}s for {args.steps} step(s)")
     h2d = sum(len(ids) * 4 for chunks in reqs_chunks for ids in chunks)
