@@ -303,18 +303,20 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
     const int* bt = block_tables + (size_t)slot * max_pages;
     {
         const float* row = QKV + (size_t)i * 3 * H + h * kHeadDim;
-        const int d = tid & 63;
         const int page = bt[past / kPageTokens], tk = past % kPageTokens;
         const size_t pbase = ((size_t)page * heads + h) * (kPageTokens * kHeadDim);
-        if (tid < 64) {
-            qs[d] = row[d] * 0.125f;                                                 // 64^-0.5
-            const TKV k = from_f32<TKV>(row[H + d]);
-            ks[d] = to_f32<TKV>(k);
-            kpool[pbase + ((size_t)(d / X) * kPageTokens + tk) * X + (d % X)] = k;
-        } else if (tid < 128) {
-            const TKV v = from_f32<TKV>(row[2 * H + d]);
-            vs[d] = to_f32<TKV>(v);
-            vpool[pbase + (size_t)tk * kHeadDim + d] = v;
+        for (int t = tid; t < 2 * kHeadDim; t += 32 * NW) {              // (NW < 4: fewer than 128 threads stage the row)
+            const int dd = t & 63;
+            if (t < 64) {
+                qs[dd] = row[dd] * 0.125f;                                           // 64^-0.5
+                const TKV k = from_f32<TKV>(row[H + dd]);
+                ks[dd] = to_f32<TKV>(k);
+                kpool[pbase + ((size_t)(dd / X) * kPageTokens + tk) * X + (dd % X)] = k;
+            } else {
+                const TKV v = from_f32<TKV>(row[2 * H + dd]);
+                vs[dd] = to_f32<TKV>(v);
+                vpool[pbase + (size_t)tk * kHeadDim + dd] = v;
+            }
         }
     }
     __syncthreads();
@@ -390,7 +392,7 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
         for (int e = 0; e < X; ++e) pacc[w][dc * X + e] = acc[e];
     }
     __syncthreads();
-    if (tid < kHeadDim) {
+    for (int t = tid; t < kHeadDim; t += 32 * NW) {
         float M = pm[0];
 #pragma unroll
         for (int k = 1; k < NW; ++k) M = fmaxf(M, pm[k]);
@@ -399,9 +401,9 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
         for (int k = 0; k < NW; ++k) {
             const float e = (pm[k] == -INFINITY) ? 0.f : expf(pm[k] - M);
             L = fmaf(pl[k], e, L);
-            o = fmaf(pacc[k][tid], e, o);
+            o = fmaf(pacc[k][t], e, o);
         }
-        out[(size_t)i * H + h * kHeadDim + tid] = from_f32<TOut>(o / L);
+        out[(size_t)i * H + h * kHeadDim + t] = from_f32<TOut>(o / L);
     }
     __syncthreads();                                  // qs/ks/vs/pacc are reused by the next item
     }
@@ -929,6 +931,12 @@ int launch_attn_decode(const float* QKV, const int* active, int M, const int* ct
     // measured 18 % SLOWER per decode step (run 7: 256-thread CTAs, three per SM), kept as an option.
     if (sizeof(TKV) == 2 && g_attn_warps == 8)
         launch_k(attn_decode_kernel<TKV, TOut, 8>, dim3(grid), dim3(256), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
+                 kpool, vpool, out, heads, n_items, dep);
+    else if (sizeof(TKV) == 2 && g_attn_warps == 2)
+        launch_k(attn_decode_kernel<TKV, TOut, 2>, dim3(grid), dim3(64), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
+                 kpool, vpool, out, heads, n_items, dep);
+    else if (sizeof(TKV) == 2 && g_attn_warps == 1)
+        launch_k(attn_decode_kernel<TKV, TOut, 1>, dim3(grid), dim3(32), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
                  kpool, vpool, out, heads, n_items, dep);
     else
         launch_k(attn_decode_kernel<TKV, TOut, 4>, dim3(grid), dim3(128), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,

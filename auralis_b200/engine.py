@@ -33,6 +33,22 @@ from .text import XTTSTokenizer
 from .weights import load_model_dir
 
 
+def tune_host_allocator() -> bool:
+    """Keeps large host buffers on the malloc heap instead of fresh `mmap` regions.  Every finished chunk arrives as a new
+    2.7 MB float32 array (and is copied once more into its request's buffer); glibc serves allocations that large with `mmap`
+    and returns them with `munmap`, so each one is page-faulted in again — 0.3-1 s per 4 600 audio-seconds of output on the
+    hosts measured, serialised across threads by the process's mm lock.  `mallopt(M_MMAP_THRESHOLD, 1 GiB)` +
+    `mallopt(M_TRIM_THRESHOLD, max)` makes the heap keep and reuse those pages.  Process-wide, so it is the APPLICATION's call
+    (bench.py makes it; `XTTSv2Engine(tune_malloc=True)` does too).  Returns False where glibc's mallopt is unavailable."""
+    import ctypes
+    try:
+        libc = ctypes.CDLL("libc.so.6")
+        ok = libc.mallopt(-3, 1 << 30) == 1            # M_MMAP_THRESHOLD
+        return (libc.mallopt(-1, 2 ** 31 - 1) == 1) and ok      # M_TRIM_THRESHOLD
+    except Exception:      # noqa: BLE001 — not glibc
+        return False
+
+
 class ChunkOutput:
     """What the reference reads off vLLM's RequestOutput (XTTSv2.py:785-799): finished flag + token ids.
     `partial`: a first-audio piece (engine option `early_emit_tokens`) — the audio of the chunk's leading tokens, delivered
@@ -76,12 +92,15 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
 
     def __init__(self, dims: XTTSDims, gpt_state, core_state, *, device: int = 0, devices: Optional[List[int]] = None,
                  precision: str = "bf16", max_concurrency: int = 64, max_speakers: int = 32,
-                 tokenizer_file: Optional[str] = None, early_emit_tokens: int = 0, voc_segment: Optional[int] = None, **_):
+                 tokenizer_file: Optional[str] = None, early_emit_tokens: int = 0, voc_segment: Optional[int] = None,
+                 tune_malloc: bool = False, **_):
         """`devices=[0, 1, ...]`: data parallelism inside the product (north_star: "requests shard data-parallel across the
         8xB200 box") — one native engine (full weight replica, own scheduler thread, own streams) per listed GPU in THIS
         process; every text chunk goes to the engine with the least work in flight, results are re-assembled in request
         order by the façade as before.  `max_concurrency` is per GPU.  Default: the single GPU `device`."""
         prec = {"fp32": native.PRECISION_FP32, "bf16": native.PRECISION_BF16, "fp16": native.PRECISION_FP16}[precision]
+        if tune_malloc:
+            tune_host_allocator()
         self.dims = dims
         self.precision = precision
         self.devices = [int(d) for d in devices] if devices else [int(device)]

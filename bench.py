@@ -227,7 +227,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference)")
     from auralis_b200 import TTS, TTSRequest, native
-    from auralis_b200.engine import XTTSv2Engine
+    from auralis_b200.engine import XTTSv2Engine, tune_host_allocator
+    malloc_tuned = tune_host_allocator()      # output buffers stay on the heap (no page-fault storm per step), see engine.py
     torch.cuda.set_device(local)
     state = synth_state(dims, SEED)
     n_chunks_est = args.requests * (args.chars // 200 + 2)
@@ -523,6 +524,7 @@ def main():
                              "behind the last step's work); max over ranks; e2e: host wall clock around the public API calls",
                    "host_wall_ms_per_step": 1e3 * wall_dev / args.steps,
                    "engine_opts": args.engine_opt,
+                   "host_allocator": "glibc mallopt(M_MMAP_THRESHOLD = 1 GiB, M_TRIM_THRESHOLD = max): output arrays reuse heap pages" if malloc_tuned else "default",
                    "vocoder": (f"windows of {args.voc_segment} tokens vocoded on a second stream while the chunk decodes (ragged batches of up to 32 windows)"
                                if args.voc_segment else "whole chunks, vocoded when they end (ragged batches)"),
                    "decode_step": ("per layer: paged attention + one persistent chain kernel (out-proj, LN2, fc+gelu, down-proj, LN1, next QKV)"

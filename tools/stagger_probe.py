@@ -32,8 +32,20 @@ def run(label, **opts):
 for extra in sys.argv[2:]:
     eng.set_option(extra.split("=")[0], int(extra.split("=")[1]))
 run("warm", microbatches=2)
-for aw in (8, 4):
-    for flags in (0, 1):
-        for mb in (2, 1):
-            run(f"attn_warps {aw}, dep_flags {flags}, {mb} branches", attn_warps=aw, dep_flags=flags, microbatches=mb, branch_stagger_us=0)
+import itertools
+cfgs = [(aw, mb) for aw in (4, 2, 1) for mb in (2, 1)]
+best = {}
+def measure(**opts):
+    for k, v in opts.items(): eng.set_option(k, v)
+    eng.run_batch(jobs(12), timeout_s=600, want_wav=False)
+    t = []
+    for nt in (300, 400):
+        t0 = time.time(); eng.run_batch(jobs(nt), timeout_s=600, want_wav=False); t.append(time.time() - t0)
+    return 1e3 * (t[1] - t[0]) / 100
+for rep in range(3):                                         # interleaved repeats: clock / thermal drift hits every config alike
+    for (aw, mb) in (cfgs if rep % 2 == 0 else cfgs[::-1]):
+        v = measure(attn_warps=aw, microbatches=mb, dep_flags=0, branch_stagger_us=0)
+        best.setdefault((aw, mb), []).append(v)
+for k, v in best.items():
+    print(f"attn_warps {k[0]}, {k[1]} branch(es): " + " ".join(f"{x:6.3f}" for x in v) + f"   min {min(v):6.3f} ms/decode-step", flush=True)
 eng.close()
