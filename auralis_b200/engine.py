@@ -91,7 +91,7 @@ class XTTSv2Engine(BaseAsyncTTSEngine):
     model_type = "xtts"
 
     def __init__(self, dims: XTTSDims, gpt_state, core_state, *, device: int = 0, devices: Optional[List[int]] = None,
-                 precision: str = "bf16", max_concurrency: int = 64, max_speakers: int = 32,
+                 precision: str = "fp16", max_concurrency: int = 64, max_speakers: int = 32,
                  tokenizer_file: Optional[str] = None, early_emit_tokens: int = 0, voc_segment: Optional[int] = None,
                  tune_malloc: bool = False, **_):
         """`devices=[0, 1, ...]`: data parallelism inside the product (north_star: "requests shard data-parallel across the

@@ -47,7 +47,7 @@ def test_window_interior_equals_whole_chunk(request, which, dims_name, T):
         np.testing.assert_array_equal(w[a * hop: b * hop], full[(z0 + a) * hop: (z0 + b) * hop])
 
 
-@pytest.mark.parametrize("which", ["engine_small", "engine_small_bf16"])
+@pytest.mark.parametrize("which", ["engine_small", "engine_small_bf16", "engine_small_fp16"])
 def test_ragged_batch_equals_single_chunks(request, dims_small, which):
     """chunks of different lengths finish at different steps and share vocoder launches (per-item lengths): tokens and
     waveform of each equal what the same chunk gives alone; the waveform also equals xtts_vocode of its own latents."""
@@ -64,7 +64,7 @@ def test_ragged_batch_equals_single_chunks(request, dims_small, which):
         np.testing.assert_array_equal(wav, eng.vocode(lat, spk))
 
 
-@pytest.mark.parametrize("which", ["engine_small", "engine_small_bf16", "engine_full_bf16"])
+@pytest.mark.parametrize("which", ["engine_small", "engine_small_bf16", "engine_full_bf16", "engine_full_fp16"])
 def test_segmented_vocoding_equals_whole(request, which):
     """option voc_segment: windows cut while the chunk decodes (the vocoder overlapping the decode step on its own stream,
     with and without an SM cap) give the same result as one window at the end."""
