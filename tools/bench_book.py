@@ -23,7 +23,7 @@ per_req = int(sys.argv[2]) if len(sys.argv) > 2 else 5_000
 rank, world, local = parallel.init_from_env()
 dims = XTTSDims.full()
 state = synth_state(dims, SEED)
-eng = XTTSv2Engine(dims, state[0], state[1], device=local, precision="bf16", max_concurrency=256, max_speakers=4)
+eng = XTTSv2Engine(dims, state[0], state[1], device=local, precision="fp16", max_concurrency=256, max_speakers=4)
 tts = TTS(scheduler_max_concurrency=100000).from_engine(eng)
 spk = synthetic_wav_bytes(6.0, 120.0, 7)
 tts.loop.run_until_complete(eng.get_audio_conditioning(spk, 60, 30, 4))

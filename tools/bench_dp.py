@@ -23,7 +23,7 @@ modes = sys.argv[2:] or ["weak", "strong", "book"]
 dims = XTTSDims.full()
 state = synth_state(dims, SEED)
 t0 = time.perf_counter()
-eng = XTTSv2Engine(dims, state[0], state[1], devices=list(range(n_gpus)), precision="bf16", max_concurrency=256,
+eng = XTTSv2Engine(dims, state[0], state[1], devices=list(range(n_gpus)), precision="fp16", max_concurrency=256,
                    max_speakers=8, voc_segment=96, tune_malloc=True)
 print(f"[bench_dp] {n_gpus} engines up in {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
 tts = TTS(scheduler_max_concurrency=100000).from_engine(eng)

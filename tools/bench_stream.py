@@ -19,7 +19,7 @@ conc = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 early = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 dims = XTTSDims.full()
 state = synth_state(dims, SEED)
-eng = XTTSv2Engine(dims, state[0], state[1], device=0, precision="bf16", max_concurrency=conc, max_speakers=8,
+eng = XTTSv2Engine(dims, state[0], state[1], device=0, precision="fp16", max_concurrency=conc, max_speakers=8,
                    early_emit_tokens=early)
 tts = TTS(scheduler_max_concurrency=100000).from_engine(eng)
 spk = [synthetic_wav_bytes(6.0, 100.0 + 25.0 * i, 7 + i) for i in range(4)]

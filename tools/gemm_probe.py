@@ -6,7 +6,7 @@ from auralis_b200 import native
 from auralis_b200.config import XTTSDims
 eng = native.NativeEngine(XTTSDims.small(), precision=1, max_batch=4, max_speakers=2)
 rng = np.random.RandomState(1)
-names = {0: "one tile per CTA", 1: "pair 6x1", 2: "pair 4x1", 3: "pair 7x1", 4: "pair 3x2"}
+names = {0: "one tile per CTA", 1: "pair 3x2 (default)", 2: "pair 4x1", 3: "pair 6x1", 4: "pair 2x2"}   # stages x k-blocks per stage
 for (M, N, K) in ((4096, 4096, 1024), (4096, 4096, 4096), (2304, 3072, 1024), (2304, 4096, 1024), (2304, 1024, 4096), (8192, 8192, 1024)):
     A = rng.randn(M, K).astype(np.float32); W = (rng.randn(N, K) * 0.05).astype(np.float32)
     for v in (1, 2, 3, 4, 0):
