@@ -96,6 +96,9 @@ struct KernelCtx {
     int gemm_decode_bn = 0;       // 0 = heuristic; 32/64/128 forces the tile width of decode-shaped tcgen05 GEMMs
     int conv_epi_groups = 2;      // 1 or 2 epilogue warpgroups in conv1d_tc_kernel
     int attn_warps = 4;           // warps per (row, head) item of the bf16 decode attention (4, or 8: measured slower, run 7)
+    int attn_bulk = 0;            // > 0: 16-bit decode attention streams cache pages with cp.async.bulk, this many CTAs per SM
+    int attn_stages = 8;          // ring depth of that kernel (8 KB per stage)
+    int attn_l2_ahead = 1;        // that kernel prefetches the next item's pages into L2 (cp.async.bulk.prefetch.L2)
     int gemm_2cta = 1;            // large shapes (M >= 256) go to the persistent CTA-pair kernel (gemm_tcgen05_2cta.cu)
 };
 #define g_prof (::xtts::kctx().prof)
@@ -106,6 +109,9 @@ struct KernelCtx {
 #define g_conv_epi_groups (::xtts::kctx().conv_epi_groups)
 #define g_gemm_2cta (::xtts::kctx().gemm_2cta)
 #define g_attn_warps (::xtts::kctx().attn_warps)
+#define g_attn_bulk (::xtts::kctx().attn_bulk)
+#define g_attn_stages (::xtts::kctx().attn_stages)
+#define g_attn_l2_ahead (::xtts::kctx().attn_l2_ahead)
 
 // true the first time it is called with the current CUDA device for this flag set (function attributes are per device)
 inline bool first_on_device(bool (&done)[64]) {

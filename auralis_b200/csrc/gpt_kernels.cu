@@ -412,6 +412,269 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
 }
 
 // ------------------------------------------------------------------------------------------------
+// Decode attention, bulk-copy form (16-bit caches): the cache pages of a (row, head) item are contiguous 4 KB blocks (K atoms,
+// V rows), so one producer thread streams them into a shared-memory ring with cp.async.bulk + mbarriers and four consumer warps
+// do the arithmetic of attn_decode_kernel<.., 4> out of shared memory (same page -> warp assignment, same operation order:
+// results are bit-identical).  Why:
+//   * bytes in flight no longer depend on resident warps: ONE 160-thread CTA per SM with an 8-stage ring keeps 64 KB per SM
+//     outstanding, so the kernel leaves registers, thread slots and ~160 KB of shared memory to the GEMM CTAs of the other
+//     decode branch (the load-into-registers kernel needs ~9 CTAs per SM to reach the same bandwidth and starves them);
+//   * the cached pages, block tables and context lengths of this step were written by EARLIER graph launches, so the producer
+//     starts streaming BEFORE griddepcontrol.wait — the ring is full when the QKV GEMM retires; only q and the step's own
+//     k/v (read from the QKV row) wait for the predecessor;
+//   * the producer walks straight from one item's pages into the next item's: no per-item ramp.
+// CTA c handles items c, c + grid, ... (at most kBulkMaxItems of them; the host sizes the grid accordingly).
+// ------------------------------------------------------------------------------------------------
+constexpr int kBulkMaxItems = 32;
+constexpr int kBulkStageBytes = 2 * kPageTokens * kHeadDim * 2;       // K page + V page, 16-bit: 8 KB
+
+__device__ __forceinline__ uint32_t ab_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ab_bar_init(uint64_t* b, uint32_t c) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ab_s32(b)), "r"(c) : "memory");
+}
+__device__ __forceinline__ void ab_bar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ab_s32(b)) : "memory");
+}
+__device__ __forceinline__ void ab_bar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ab_s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ab_bar_wait(uint64_t* b, uint32_t parity, int tag) {
+    const long long t0 = clock64();
+    int polls = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(ab_s32(b)), "r"(parity) : "memory");
+        if (ok) return;
+        if ((++polls & 1023) == 0 && clock64() - t0 > 4000000000LL) {
+            printf("attn_decode_bulk: mbarrier watchdog (tag %d, block %d, thread %d)\n", tag, blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void ab_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ab_s32(dst)), "l"(src), "r"(bytes), "r"(ab_s32(bar)) : "memory");
+}
+__device__ __forceinline__ void ab_consumer_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <typename TKV, typename TOut>
+__global__ void __launch_bounds__(160)
+attn_decode_bulk_kernel(const float* __restrict__ QKV, const int* __restrict__ active, const int* __restrict__ ctx_len,
+                        const int* __restrict__ block_tables, int max_pages, TKV* __restrict__ kpool, TKV* __restrict__ vpool,
+                        TOut* __restrict__ out, int heads, int n_items, int stages, int l2_ahead) {
+    static_assert(sizeof(TKV) == 2, "bulk attention: 16-bit caches only");
+    constexpr int X = 8, NCH = 8, TPI = 4, VIT = 8;
+    extern __shared__ __align__(128) uint8_t ring[];                  // stages x (K page | V page)
+    __shared__ __align__(8) uint64_t full_bar[16], empty_bar[16];
+    __shared__ int s_slot[kBulkMaxItems], s_past[kBulkMaxItems];
+    __shared__ __align__(16) float qs[2][kHeadDim], ks[2][kHeadDim], vs[2][kHeadDim];
+    __shared__ float pm[4], pl[4];
+    __shared__ float pacc[4][kHeadDim];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    trace_pt(TR_ATTN, 0); pdl_trigger();
+    const int my_items = (blockIdx.x < n_items) ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (tid < kBulkMaxItems && tid < my_items) {                      // written by earlier graph launches: safe before the wait
+        const int item = blockIdx.x + tid * gridDim.x;
+        const int slot = active[item / heads];
+        s_slot[tid] = slot; s_past[tid] = ctx_len[slot];
+    }
+    if (tid == 0)
+        for (int s = 0; s < stages; ++s) { ab_bar_init(&full_bar[s], 1); ab_bar_init(&empty_bar[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int H = heads * kHeadDim;
+
+    const int D = stages >> 2;                                        // ring depth per consumer warp
+    if (w == 4) {
+        // ------------------------------------------------------------ producer warp: one bulk copy per K page, one per V page.
+        // Page pg of an item belongs to consumer warp pg % 4 and goes to that warp's own D-deep sub-ring, so every stage is
+        // always drained by the same warp, in order (an mbarrier parity wait can only tell the current phase from the previous
+        // one).  A single thread issues ~one 4 KB copy per 270 cycles (29 GB/s per SM, tools/probes/bulk_probe.cu), so up to
+        // `stages` lanes issue at once, each for the page whose id it read from the block table; rounds of `stages` pages keep
+        // every empty-barrier wait at most one phase ahead.
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;                      // pages handed to each consumer warp so far
+        // HBM latency under load is ~1.6 us: 64 KB per SM in flight reach only ~39 GB/s per SM.  The ring therefore only covers
+        // the L2 -> shared latency; HBM -> L2 runs one item ahead on cp.async.bulk.prefetch.L2 (no SM resources held).
+        auto prefetch_item = [&](int k) {
+            const int item = blockIdx.x + k * gridDim.x;
+            const int h = item % heads;
+            const int past = s_past[k];
+            const int npages = (past + kPageTokens - 1) / kPageTokens;
+            const int* bt = block_tables + (size_t)s_slot[k] * max_pages;
+            for (int pg = lane; pg < npages; pg += 32) {
+                const size_t pbase = ((size_t)bt[pg] * heads + h) * (kPageTokens * kHeadDim);
+                const int nvalid = min(kPageTokens, past - pg * kPageTokens);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kpool + pbase), "r"(kPageTokens * kHeadDim * 2) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vpool + pbase), "r"(nvalid * kHeadDim * 2) : "memory");
+            }
+        };
+        if (l2_ahead && my_items > 0) prefetch_item(0);
+        for (int k = 0; k < my_items; ++k) {
+            const int item = blockIdx.x + k * gridDim.x;
+            const int h = item % heads;
+            const int slot = s_slot[k], past = s_past[k];
+            const int npages = (past + kPageTokens - 1) / kPageTokens;
+            const int* bt = block_tables + (size_t)slot * max_pages;
+            if (l2_ahead && k + 1 < my_items) prefetch_item(k + 1);
+            for (int pg0 = 0; pg0 < npages; pg0 += 32) {
+                const int n = min(32, npages - pg0);
+                const int page = (lane < n) ? bt[pg0 + lane] : 0;     // one coalesced read per 32 pages
+                const int wt = lane & 3;
+                const uint32_t pos = (wt == 0 ? c0 : wt == 1 ? c1 : wt == 2 ? c2 : c3) + (uint32_t)(lane >> 2);
+                for (int r = 0; r * stages < n; ++r) {
+                    if (lane < n && lane / stages == r) {
+                        const int s = wt * D + (int)(pos % D);
+                        ab_bar_wait(&empty_bar[s], ((pos / D) & 1) ^ 1, 1);
+                        const int nvalid = min(kPageTokens, past - (pg0 + lane) * kPageTokens);
+                        const size_t pbase = ((size_t)page * heads + h) * (kPageTokens * kHeadDim);
+                        uint8_t* dst = ring + (size_t)s * kBulkStageBytes;
+                        ab_bar_expect_tx(&full_bar[s], (uint32_t)(kPageTokens * kHeadDim * 2 + nvalid * kHeadDim * 2));
+                        ab_bulk_g2s(dst, kpool + pbase, kPageTokens * kHeadDim * 2, &full_bar[s]);
+                        ab_bulk_g2s(dst + kPageTokens * kHeadDim * 2, vpool + pbase, (uint32_t)(nvalid * kHeadDim * 2), &full_bar[s]);
+                    }
+                    __syncwarp();
+                }
+                c0 += (uint32_t)((n + 3) >> 2); c1 += (uint32_t)((n + 2) >> 2); c2 += (uint32_t)((n + 1) >> 2); c3 += (uint32_t)(n >> 2);
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumers: 4 warps, pages round-robin inside an item
+    pdl_wait();                                                       // QKV of this step; `out` may still be read upstream
+    trace_pt(TR_ATTN, 1);
+    // stage item k's row (q scaled, k / v rounded to the cache type) and append k / v to the cache: thread t < 64 owns q[t]
+    // and v[t], thread t >= 64 owns k[t - 64]
+    auto load_row = [&](int k, float& a, float& b) {
+        const int item = blockIdx.x + k * gridDim.x;
+        const int i = item / heads, h = item - i * heads;
+        const float* row = QKV + (size_t)i * 3 * H + h * kHeadDim;
+        if (tid < 64) { a = row[tid]; b = row[2 * H + tid]; } else { a = row[H + tid - 64]; b = 0.f; }
+    };
+    auto stage_row = [&](int k, int buf, float a, float b, int page_new) {
+        const int item = blockIdx.x + k * gridDim.x;
+        const int h = item % heads;
+        const int tk = s_past[k] % kPageTokens;
+        const size_t pbase = ((size_t)page_new * heads + h) * (kPageTokens * kHeadDim);
+        if (tid < 64) {
+            qs[buf][tid] = a * 0.125f;                                               // 64^-0.5
+            const TKV v = from_f32<TKV>(b);
+            vs[buf][tid] = to_f32<TKV>(v);
+            vpool[pbase + (size_t)tk * kHeadDim + tid] = v;
+        } else {
+            const int dd = tid - 64;
+            const TKV kk = from_f32<TKV>(a);
+            ks[buf][dd] = to_f32<TKV>(kk);
+            kpool[pbase + ((size_t)(dd / X) * kPageTokens + tk) * X + (dd % X)] = kk;
+        }
+    };
+    float ra = 0.f, rb = 0.f; int rpage = 0;
+    if (my_items > 0) {
+        load_row(0, ra, rb);
+        rpage = block_tables[(size_t)s_slot[0] * max_pages + s_past[0] / kPageTokens];
+        stage_row(0, 0, ra, rb, rpage);
+    }
+    ab_consumer_sync();
+    uint32_t mypos = 0;                                               // pages this warp has drained (its sub-ring position)
+    const int tg = lane / NCH, dc = lane % NCH;                       // PV role of this lane: token group, dim chunk
+    for (int k = 0; k < my_items; ++k) {
+        const int buf = k & 1;
+        const int item = blockIdx.x + k * gridDim.x;
+        const int i = item / heads, h = item - i * heads;
+        const int past = s_past[k];
+        const int npages = (past + kPageTokens - 1) / kPageTokens;
+        if (k + 1 < my_items) {                                       // next item's row + page id: in flight during this item
+            load_row(k + 1, ra, rb);
+            rpage = block_tables[(size_t)s_slot[k + 1] * max_pages + s_past[k + 1] / kPageTokens];
+        }
+        float m = -INFINITY, l = 0.f;
+        float acc[X];
+#pragma unroll
+        for (int e = 0; e < X; ++e) acc[e] = 0.f;
+        for (int pg = w; pg < npages; pg += 4, ++mypos) {
+            const int s = w * D + (int)(mypos % D);
+            ab_bar_wait(&full_bar[s], (mypos / D) & 1, 2);
+            const uint8_t* st = ring + (size_t)s * kBulkStageBytes;
+            const int nvalid = min(kPageTokens, past - pg * kPageTokens);
+            uint4 kraw[NCH], vraw[VIT];
+#pragma unroll
+            for (int cc = 0; cc < NCH; ++cc) kraw[cc] = *reinterpret_cast<const uint4*>(st + ((size_t)cc * kPageTokens + lane) * 16);
+#pragma unroll
+            for (int it = 0; it < VIT; ++it)                          // rows >= nvalid were not copied: never multiplied in
+                vraw[it] = *reinterpret_cast<const uint4*>(st + kPageTokens * kHeadDim * 2 + ((size_t)(it * TPI + tg) * kHeadDim + dc * X) * 2);
+            __syncwarp();
+            if (lane == 0) ab_bar_arrive(&empty_bar[s]);              // the page is in registers: hand the slot back
+            float sc = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < NCH; ++cc) {
+                float kf[X];
+                KVec<TKV>::unpack(kraw[cc], kf);
+#pragma unroll
+                for (int e = 0; e < X; ++e) sc = fmaf(kf[e], qs[buf][cc * X + e], sc);
+            }
+            const bool valid = lane < nvalid;
+            sc = valid ? sc : -INFINITY;
+            const float mnew = fmaxf(m, warp_max(sc));
+            const float p = valid ? expf(sc - mnew) : 0.f;
+            const float corr = (m == -INFINITY) ? 0.f : expf(m - mnew);
+            l = l * corr + warp_sum(p);
+#pragma unroll
+            for (int e = 0; e < X; ++e) acc[e] *= corr;
+#pragma unroll
+            for (int it = 0; it < VIT; ++it) {
+                const int j = it * TPI + tg;
+                const float pj = __shfl_sync(0xffffffffu, p, j);
+                if (j < nvalid) {
+                    float vf[X];
+                    KVec<TKV>::unpack(vraw[it], vf);
+#pragma unroll
+                    for (int e = 0; e < X; ++e) acc[e] = fmaf(pj, vf[e], acc[e]);
+                }
+            }
+            m = mnew;
+        }
+        if (w == 0) {                                                 // the step's own token, from shared memory
+            float sc = qs[buf][lane] * ks[buf][lane] + qs[buf][lane + 32] * ks[buf][lane + 32];
+            sc = warp_sum(sc);
+            const float mnew = fmaxf(m, sc);
+            const float p = expf(sc - mnew);
+            const float corr = (m == -INFINITY) ? 0.f : expf(m - mnew);
+            l = l * corr + p;
+#pragma unroll
+            for (int e = 0; e < X; ++e) acc[e] = acc[e] * corr + ((tg == 0) ? p * vs[buf][dc * X + e] : 0.f);
+            m = mnew;
+        }
+#pragma unroll
+        for (int o = NCH; o < 32; o <<= 1)
+#pragma unroll
+            for (int e = 0; e < X; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+        if (lane == 0) { pm[w] = m; pl[w] = l; }
+        if (lane < NCH) {
+#pragma unroll
+            for (int e = 0; e < X; ++e) pacc[w][dc * X + e] = acc[e];
+        }
+        ab_consumer_sync();
+        if (tid < kHeadDim) {
+            float M = pm[0];
+#pragma unroll
+            for (int q = 1; q < 4; ++q) M = fmaxf(M, pm[q]);
+            float L = 0.f, o = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float e = (pm[q] == -INFINITY) ? 0.f : expf(pm[q] - M);
+                L = fmaf(pl[q], e, L);
+                o = fmaf(pacc[q][tid], e, o);
+            }
+            out[(size_t)i * H + h * kHeadDim + tid] = from_f32<TOut>(o / L);
+        }
+        if (k + 1 < my_items) stage_row(k + 1, buf ^ 1, ra, rb, rpage);
+        ab_consumer_sync();                                           // next row staged; pm / pl / pacc free again
+    }
+    trace_pt(TR_ATTN, 2);
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic fp32 attention for prefill-style work (GPT prompt, conditioning encoder, perceiver).
 // CTA = 16 queries of one (sequence, head); K/V tiles of 32 keys staged in shared memory;
 // each warp owns 4 queries; lane = key for QK^T, lane = dims {lane, lane+32} for PV.
@@ -925,6 +1188,25 @@ int launch_attn_decode(const float* QKV, const int* active, int M, const int* ct
         grid = std::min(n_items, n_sm * g_attn_ctas_per_sm);
     } else if (g_attn_ctas_per_sm < 0) {
         grid = std::min(n_items, -g_attn_ctas_per_sm);          // test hook: an absolute grid size
+    }
+    if constexpr (sizeof(TKV) == 2) {
+        if (g_attn_bulk > 0 && dep.wait == nullptr && dep.arrive == nullptr) {
+            // bulk-copy form: `attn_bulk` persistent CTAs per SM, each with an `attn_stages`-deep ring of 8 KB pages
+            static int n_sm = 0;
+            if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+            int g = std::min(n_items, n_sm * g_attn_bulk);
+            if (g_attn_ctas_per_sm < 0) g = std::min(n_items, -g_attn_ctas_per_sm);          // test hook: an absolute grid size
+            g = std::max(g, ceil_div(n_items, kBulkMaxItems));
+            const int stages = std::max(4, std::min(g_attn_stages & ~3, 16));   // one sub-ring per consumer warp
+            const size_t smem = (size_t)stages * kBulkStageBytes;
+            static bool attr[64] = {};
+            if (first_on_device(attr))
+                CUDA_CHECK(cudaFuncSetAttribute(attn_decode_bulk_kernel<TKV, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * kBulkStageBytes));
+            launch_k(attn_decode_bulk_kernel<TKV, TOut>, dim3(g), dim3(160), smem, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
+                     kpool, vpool, out, heads, n_items, stages, g_attn_l2_ahead);
+            COUNT_LAUNCH(); KERNEL_CHECK();
+            return g;
+        }
     }
     // warps per (row, head) item: the cache pages of an item are dealt round-robin to its warps.  4 is the default; 8 (engine
     // option "attn_warps", bf16 only) halves an item's latency and was meant to shorten the under-filled tail of the kernel —

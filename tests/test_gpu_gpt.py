@@ -324,6 +324,30 @@ def test_capped_attention_grid_and_forced_gemm_tile(engine_small, engine_full_bf
                     assert list(got[sid][1]) == list(ref[sid][1]), (key, sid)     # K order per output is unchanged
 
 
+def test_bulk_copy_attention_matches_register_attention(engine_small_bf16, engine_full_bf16, engine_full_fp16, dims_small, dims_full):
+    """Engine option "attn_bulk": the decode attention streams cache pages with cp.async.bulk into a shared-memory ring (one
+    producer thread, mbarriers, persistent CTAs that walk several (row, head) items, prefetch before griddepcontrol.wait)
+    instead of loading them into registers.  Same page -> warp assignment and operation order: tokens AND latents must be
+    bit-identical, for every grid size / ring depth, across page boundaries (>= 3 pages of context) and in both 16-bit modes."""
+    for eng, dims, n_tok in ((engine_small_bf16, dims_small, 40), (engine_full_bf16, dims_full, 70), (engine_full_fp16, dims_full, 70)):
+        g = dims.gpt
+        jobs = [(i, text_ids(dims, 6 + 4 * i, 120 + i), i % 3,
+                 Sampling(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, max_tokens=n_tok, seed=11, seq_seed=i,
+                          stop_token=4095, vocode=False)) for i in range(7)]
+        ref = eng.run_batch(jobs, timeout_s=180, want_wav=False, want_latents=True)
+        try:
+            for bulk, stages, grid in ((1, 8, 0), (2, 4, 0), (1, 4, -3), (1, 16, -5), (1, 12, -1000), (1, 8, -7)):
+                eng.set_option("attn_bulk", bulk); eng.set_option("attn_stages", stages); eng.set_option("attn_ctas_per_sm", grid)
+                eng.set_option("attn_l2_ahead", 0 if grid == -7 else 1)
+                got = eng.run_batch(jobs, timeout_s=180, want_wav=False, want_latents=True)
+                for sid in ref:
+                    assert list(got[sid][1]) == list(ref[sid][1]), (bulk, stages, grid, sid)
+                    assert len(got[sid][1]) == n_tok
+                    np.testing.assert_array_equal(got[sid][3], ref[sid][3])
+        finally:
+            eng.set_option("attn_bulk", 0); eng.set_option("attn_stages", 8); eng.set_option("attn_ctas_per_sm", 0); eng.set_option("attn_l2_ahead", 1)
+
+
 def test_kernel_profile_graph_events(engine_small_bf16, dims_small):
     """Option "profile": the decode step is replayed from a graph that carries an event-record node on either side of
     every kernel; the family table must account for every decode launch and the tokens must not change."""
