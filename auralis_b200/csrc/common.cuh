@@ -98,7 +98,9 @@ struct KernelCtx {
     int attn_warps = 4;           // warps per (row, head) item of the bf16 decode attention (4, or 8: measured slower, run 7)
     int attn_bulk = 0;            // > 0: 16-bit decode attention streams cache pages with cp.async.bulk, this many CTAs per SM
     int attn_stages = 8;          // ring depth of that kernel (8 KB per stage)
+    int attn_l2_pages = 0;        // register-load decode attention: every warp prefetches the page this many of its pages ahead into L2
     int attn_l2_ahead = 1;        // that kernel prefetches the next item's pages into L2 (cp.async.bulk.prefetch.L2)
+    int gemm_l2_prefetch = 0;     // one-tile tcgen05 GEMM: weight tiles beyond the first ring pass are prefetched into L2 before the dependency wait
     int gemm_2cta = 1;            // large shapes (M >= 256) go to the persistent CTA-pair kernel (gemm_tcgen05_2cta.cu)
 };
 #define g_prof (::xtts::kctx().prof)
@@ -109,9 +111,11 @@ struct KernelCtx {
 #define g_conv_epi_groups (::xtts::kctx().conv_epi_groups)
 #define g_gemm_2cta (::xtts::kctx().gemm_2cta)
 #define g_attn_warps (::xtts::kctx().attn_warps)
+#define g_gemm_l2_prefetch (::xtts::kctx().gemm_l2_prefetch)
 #define g_attn_bulk (::xtts::kctx().attn_bulk)
 #define g_attn_stages (::xtts::kctx().attn_stages)
 #define g_attn_l2_ahead (::xtts::kctx().attn_l2_ahead)
+#define g_attn_l2_pages (::xtts::kctx().attn_l2_pages)
 
 // true the first time it is called with the current CUDA device for this flag set (function attributes are per device)
 inline bool first_on_device(bool (&done)[64]) {

@@ -1859,9 +1859,11 @@ void Engine::set_option(const std::string& k, int64_t v) {
     else if (k == "voc_batch") voc_max_items = (int)std::max<int64_t>(1, std::min<int64_t>(v, kVocMaxItems));
     else if (k == "gemm_2cta") g_gemm_2cta = (int)std::max<int64_t>(0, std::min<int64_t>(v, 4));      // 0 off, 1 default ring, 2-4 ring variants
     else if (k == "attn_bulk") { g_attn_bulk = (int)std::max<int64_t>(0, std::min<int64_t>(v, 4)); drop_graphs(); }
+    else if (k == "gemm_l2_prefetch") { g_gemm_l2_prefetch = v ? 1 : 0; drop_graphs(); }
+    else if (k == "attn_l2_pages") { g_attn_l2_pages = (int)std::max<int64_t>(0, std::min<int64_t>(v, 8)); drop_graphs(); }
     else if (k == "attn_l2_ahead") { g_attn_l2_ahead = v ? 1 : 0; drop_graphs(); }
-    else if (k == "attn_stages") { g_attn_stages = (int)std::max<int64_t>(2, std::min<int64_t>(v, 16)); drop_graphs(); }
-    else if (k == "attn_warps") { g_attn_warps = (v == 1 || v == 2 || v == 8) ? (int)v : 4; drop_graphs(); }
+    else if (k == "attn_stages") { g_attn_stages = (int)std::max<int64_t>(4, std::min<int64_t>(v, 24)); drop_graphs(); }
+    else if (k == "attn_warps") { g_attn_warps = (v == 1 || v == 2 || v == 8 || v == 16) ? (int)v : 4; drop_graphs(); }
     else if (k == "cuda_graphs") use_graphs = v != 0;
     else if (k == "pdl") { use_pdl = v != 0; drop_graphs(); }
     else if (k == "splitk") { use_splitk = v != 0; drop_graphs(); }

@@ -151,6 +151,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_expect_tx(&full_bar[kb], (uint32_t)a_box_rows * BK * 2 + B_BYTES);
                 tma_load_2d(sB + kb * B_BYTES, &tmB, &full_bar[kb], (kb_begin + kb) * BK, n0);
             }
+            // ... and the weight tiles of the later passes are pulled into L2 meanwhile: a decode-shaped GEMM is a chain of
+            // ring passes each paying the full HBM latency (~1.6 us under load); from L2 a pass costs ~0.7 us
+            if (!(flags_in & GEMM_NO_L2PF))
+            for (int kb = pre; kb < num_kb; ++kb)
+                asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                             ::"l"(&tmB), "r"((kb_begin + kb) * BK), "r"(n0) : "memory");
             dep_wait(dep, 21);                       // the activations exist (whole predecessor grid, or its counter)
             if (dep.wait) asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores -> TMA (async proxy) reads
             trace_pt(TR_GEMM, 1);
@@ -284,7 +290,8 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias,
     ProfScope ps(KF_GEMM_TC, st, 2.0 * M * N * K,
                  2.0 * ((double)M * K + (double)N * K) + ((flags & GEMM_OUT_BF16) ? 2.0 : 4.0) * M * N);
     if (dep.wait && (flags & GEMM_RESID)) throw CudaError("gemm_bf16_tc: a counter dependency cannot order a residual read");
-    launch_k(gemm_bf16_tc_kernel<BN>, grid, dim3(kThreads), smem, st, pdl, tmA, tmB, bias, resid, out, M, N, K, flags, a_box_rows, dep);
+    launch_k(gemm_bf16_tc_kernel<BN>, grid, dim3(kThreads), smem, st, pdl, tmA, tmB, bias, resid, out, M, N, K,
+             flags | (g_gemm_l2_prefetch ? 0 : GEMM_NO_L2PF), a_box_rows, dep);
     COUNT_LAUNCH(); KERNEL_CHECK();
     return (int)(grid.x * grid.y * grid.z);
 }

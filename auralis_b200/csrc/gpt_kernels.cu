@@ -280,7 +280,7 @@ template <typename TKV, typename TOut, int NW>
 __global__ void __launch_bounds__(32 * NW)
 attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active, const int* __restrict__ ctx_len,
                    const int* __restrict__ block_tables, int max_pages, TKV* __restrict__ kpool, TKV* __restrict__ vpool,
-                   TOut* __restrict__ out, int heads, int n_items, const DepFlag dep) {
+                   TOut* __restrict__ out, int heads, int n_items, const DepFlag dep, int l2_pages) {
     constexpr int X = KVec<TKV>::X;
     constexpr int NCH = kHeadDim / X;                 // 16-byte atoms per token row (8 bf16 / 16 fp32)
     constexpr int TPI = 32 / NCH;                     // tokens covered by one warp-wide V load (4 / 2)
@@ -289,6 +289,8 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
     __shared__ float pm[NW], pl[NW];
     __shared__ float pacc[NW][kHeadDim];
     trace_pt(TR_ATTN, 0); pdl_trigger();
+    // ncu: 24 resident warps per SM, long-scoreboard stalls dominate: the kernel is bound by the bytes its warps keep in
+    // flight against ~1.6 us of HBM latency under load.  Option "attn_l2_pages": cp.async.bulk.prefetch.L2 holds no registers.
     if (threadIdx.x == 0) dep_wait(dep, 33);
     __syncthreads();
     trace_pt(TR_ATTN, 1);
@@ -301,6 +303,18 @@ attn_decode_kernel(const float* __restrict__ QKV, const int* __restrict__ active
     const int past = ctx_len[slot];                   // tokens already cached; the new one goes to position `past`
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int* bt = block_tables + (size_t)slot * max_pages;
+    if (l2_pages > 0 && lane == 0) {
+        // ask L2 for this warp's pages 2 .. 1 + l2_pages now (its first page is loaded right away): kept out of the page
+        // loop, where the address arithmetic of a prefetch costs the 16 in-flight loads per lane their registers (69 -> 96)
+        const int np = (past + kPageTokens - 1) / kPageTokens;
+        for (int j = 1; j <= l2_pages; ++j) {
+            const int pf = w + j * NW;
+            if (pf >= np) break;
+            const size_t pb = ((size_t)bt[pf] * heads + h) * (kPageTokens * kHeadDim);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kpool + pb), "r"((int)(kPageTokens * kHeadDim * sizeof(TKV))));
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vpool + pb), "r"((int)(min(kPageTokens, past - pf * kPageTokens) * kHeadDim * sizeof(TKV))));
+        }
+    }
     {
         const float* row = QKV + (size_t)i * 3 * H + h * kHeadDim;
         const int page = bt[past / kPageTokens], tk = past % kPageTokens;
@@ -456,21 +470,22 @@ __device__ __forceinline__ void ab_bulk_g2s(void* dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(ab_s32(dst)), "l"(src), "r"(bytes), "r"(ab_s32(bar)) : "memory");
 }
-__device__ __forceinline__ void ab_consumer_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int NW> __device__ __forceinline__ void ab_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NW) : "memory"); }
 
-template <typename TKV, typename TOut>
-__global__ void __launch_bounds__(160)
+template <typename TKV, typename TOut, int NW>
+__global__ void __launch_bounds__(32 * NW + 32)
 attn_decode_bulk_kernel(const float* __restrict__ QKV, const int* __restrict__ active, const int* __restrict__ ctx_len,
                         const int* __restrict__ block_tables, int max_pages, TKV* __restrict__ kpool, TKV* __restrict__ vpool,
                         TOut* __restrict__ out, int heads, int n_items, int stages, int l2_ahead) {
     static_assert(sizeof(TKV) == 2, "bulk attention: 16-bit caches only");
     constexpr int X = 8, NCH = 8, TPI = 4, VIT = 8;
     extern __shared__ __align__(128) uint8_t ring[];                  // stages x (K page | V page)
-    __shared__ __align__(8) uint64_t full_bar[16], empty_bar[16];
+    __shared__ __align__(8) uint64_t full_bar[24], empty_bar[24];
     __shared__ int s_slot[kBulkMaxItems], s_past[kBulkMaxItems];
     __shared__ __align__(16) float qs[2][kHeadDim], ks[2][kHeadDim], vs[2][kHeadDim];
-    __shared__ float pm[4], pl[4];
-    __shared__ float pacc[4][kHeadDim];
+    static_assert(NW == 4 || NW == 8 || NW == 16, "consumer warps: 4, 8 or 16");
+    __shared__ float pm[NW], pl[NW];
+    __shared__ float pacc[NW][kHeadDim];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     trace_pt(TR_ATTN, 0); pdl_trigger();
     const int my_items = (blockIdx.x < n_items) ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -485,15 +500,15 @@ attn_decode_bulk_kernel(const float* __restrict__ QKV, const int* __restrict__ a
     __syncthreads();
     const int H = heads * kHeadDim;
 
-    const int D = stages >> 2;                                        // ring depth per consumer warp
-    if (w == 4) {
+    const int D = stages / NW;                                        // ring depth per consumer warp
+    if (w == NW) {
         // ------------------------------------------------------------ producer warp: one bulk copy per K page, one per V page.
         // Page pg of an item belongs to consumer warp pg % 4 and goes to that warp's own D-deep sub-ring, so every stage is
         // always drained by the same warp, in order (an mbarrier parity wait can only tell the current phase from the previous
         // one).  A single thread issues ~one 4 KB copy per 270 cycles (29 GB/s per SM, tools/probes/bulk_probe.cu), so up to
         // `stages` lanes issue at once, each for the page whose id it read from the block table; rounds of `stages` pages keep
         // every empty-barrier wait at most one phase ahead.
-        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;                      // pages handed to each consumer warp so far
+        uint32_t handed = 0;                                          // lane w < NW: pages handed to consumer warp w so far
         // HBM latency under load is ~1.6 us: 64 KB per SM in flight reach only ~39 GB/s per SM.  The ring therefore only covers
         // the L2 -> shared latency; HBM -> L2 runs one item ahead on cp.async.bulk.prefetch.L2 (no SM resources held).
         auto prefetch_item = [&](int k) {
@@ -520,8 +535,8 @@ attn_decode_bulk_kernel(const float* __restrict__ QKV, const int* __restrict__ a
             for (int pg0 = 0; pg0 < npages; pg0 += 32) {
                 const int n = min(32, npages - pg0);
                 const int page = (lane < n) ? bt[pg0 + lane] : 0;     // one coalesced read per 32 pages
-                const int wt = lane & 3;
-                const uint32_t pos = (wt == 0 ? c0 : wt == 1 ? c1 : wt == 2 ? c2 : c3) + (uint32_t)(lane >> 2);
+                const int wt = lane % NW;                             // (pg0 is a multiple of 32, 32 % NW == 0)
+                const uint32_t pos = __shfl_sync(0xffffffffu, handed, wt) + (uint32_t)(lane / NW);
                 for (int r = 0; r * stages < n; ++r) {
                     if (lane < n && lane / stages == r) {
                         const int s = wt * D + (int)(pos % D);
@@ -535,7 +550,7 @@ attn_decode_bulk_kernel(const float* __restrict__ QKV, const int* __restrict__ a
                     }
                     __syncwarp();
                 }
-                c0 += (uint32_t)((n + 3) >> 2); c1 += (uint32_t)((n + 2) >> 2); c2 += (uint32_t)((n + 1) >> 2); c3 += (uint32_t)(n >> 2);
+                if (lane < NW) handed += (uint32_t)((n + NW - 1 - lane) / NW);
             }
         }
         return;
@@ -550,7 +565,7 @@ attn_decode_bulk_kernel(const float* __restrict__ QKV, const int* __restrict__ a
         const int item = blockIdx.x + k * gridDim.x;
         const int i = item / heads, h = item - i * heads;
         const float* row = QKV + (size_t)i * 3 * H + h * kHeadDim;
-        if (tid < 64) { a = row[tid]; b = row[2 * H + tid]; } else { a = row[H + tid - 64]; b = 0.f; }
+        if (tid < 64) { a = row[tid]; b = row[2 * H + tid]; } else if (tid < 128) { a = row[H + tid - 64]; b = 0.f; }
     };
     auto stage_row = [&](int k, int buf, float a, float b, int page_new) {
         const int item = blockIdx.x + k * gridDim.x;
@@ -562,7 +577,7 @@ attn_decode_bulk_kernel(const float* __restrict__ QKV, const int* __restrict__ a
             const TKV v = from_f32<TKV>(b);
             vs[buf][tid] = to_f32<TKV>(v);
             vpool[pbase + (size_t)tk * kHeadDim + tid] = v;
-        } else {
+        } else if (tid < 128) {
             const int dd = tid - 64;
             const TKV kk = from_f32<TKV>(a);
             ks[buf][dd] = to_f32<TKV>(kk);
@@ -575,7 +590,7 @@ attn_decode_bulk_kernel(const float* __restrict__ QKV, const int* __restrict__ a
         rpage = block_tables[(size_t)s_slot[0] * max_pages + s_past[0] / kPageTokens];
         stage_row(0, 0, ra, rb, rpage);
     }
-    ab_consumer_sync();
+    ab_consumer_sync<NW>();
     uint32_t mypos = 0;                                               // pages this warp has drained (its sub-ring position)
     const int tg = lane / NCH, dc = lane % NCH;                       // PV role of this lane: token group, dim chunk
     for (int k = 0; k < my_items; ++k) {
@@ -592,7 +607,7 @@ attn_decode_bulk_kernel(const float* __restrict__ QKV, const int* __restrict__ a
         float acc[X];
 #pragma unroll
         for (int e = 0; e < X; ++e) acc[e] = 0.f;
-        for (int pg = w; pg < npages; pg += 4, ++mypos) {
+        for (int pg = w; pg < npages; pg += NW, ++mypos) {
             const int s = w * D + (int)(mypos % D);
             ab_bar_wait(&full_bar[s], (mypos / D) & 1, 2);
             const uint8_t* st = ring + (size_t)s * kBulkStageBytes;
@@ -654,14 +669,14 @@ attn_decode_bulk_kernel(const float* __restrict__ QKV, const int* __restrict__ a
 #pragma unroll
             for (int e = 0; e < X; ++e) pacc[w][dc * X + e] = acc[e];
         }
-        ab_consumer_sync();
+        ab_consumer_sync<NW>();
         if (tid < kHeadDim) {
             float M = pm[0];
 #pragma unroll
-            for (int q = 1; q < 4; ++q) M = fmaxf(M, pm[q]);
+            for (int q = 1; q < NW; ++q) M = fmaxf(M, pm[q]);
             float L = 0.f, o = 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < NW; ++q) {
                 const float e = (pm[q] == -INFINITY) ? 0.f : expf(pm[q] - M);
                 L = fmaf(pl[q], e, L);
                 o = fmaf(pacc[q][tid], e, o);
@@ -669,7 +684,7 @@ attn_decode_bulk_kernel(const float* __restrict__ QKV, const int* __restrict__ a
             out[(size_t)i * H + h * kHeadDim + tid] = from_f32<TOut>(o / L);
         }
         if (k + 1 < my_items) stage_row(k + 1, buf ^ 1, ra, rb, rpage);
-        ab_consumer_sync();                                           // next row staged; pm / pl / pacc free again
+        ab_consumer_sync<NW>();                                           // next row staged; pm / pl / pacc free again
     }
     trace_pt(TR_ATTN, 2);
 }
@@ -1197,13 +1212,25 @@ int launch_attn_decode(const float* QKV, const int* active, int M, const int* ct
             int g = std::min(n_items, n_sm * g_attn_bulk);
             if (g_attn_ctas_per_sm < 0) g = std::min(n_items, -g_attn_ctas_per_sm);          // test hook: an absolute grid size
             g = std::max(g, ceil_div(n_items, kBulkMaxItems));
-            const int stages = std::max(4, std::min(g_attn_stages & ~3, 16));   // one sub-ring per consumer warp
+            // consumer warps per CTA = option "attn_warps" (4 / 8 / 16; same page -> warp assignment and combination order as
+            // attn_decode_kernel<.., NW>); ring = one sub-ring of attn_stages / NW pages per consumer warp
+            const int nw = (g_attn_warps == 8 || g_attn_warps == 16) ? g_attn_warps : 4;
+            const int depth = std::max(1, std::min(g_attn_stages / nw, 24 / nw));
+            const int stages = nw * depth;
             const size_t smem = (size_t)stages * kBulkStageBytes;
             static bool attr[64] = {};
-            if (first_on_device(attr))
-                CUDA_CHECK(cudaFuncSetAttribute(attn_decode_bulk_kernel<TKV, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * kBulkStageBytes));
-            launch_k(attn_decode_bulk_kernel<TKV, TOut>, dim3(g), dim3(160), smem, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
-                     kpool, vpool, out, heads, n_items, stages, g_attn_l2_ahead);
+            if (first_on_device(attr)) {
+                CUDA_CHECK(cudaFuncSetAttribute(attn_decode_bulk_kernel<TKV, TOut, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * kBulkStageBytes));
+                CUDA_CHECK(cudaFuncSetAttribute(attn_decode_bulk_kernel<TKV, TOut, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * kBulkStageBytes));
+                CUDA_CHECK(cudaFuncSetAttribute(attn_decode_bulk_kernel<TKV, TOut, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * kBulkStageBytes));
+            }
+            auto go = [&](auto kern) {
+                launch_k(kern, dim3(g), dim3(32 * nw + 32), smem, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
+                         kpool, vpool, out, heads, n_items, stages, g_attn_l2_ahead);
+            };
+            if (nw == 16) go(attn_decode_bulk_kernel<TKV, TOut, 16>);
+            else if (nw == 8) go(attn_decode_bulk_kernel<TKV, TOut, 8>);
+            else go(attn_decode_bulk_kernel<TKV, TOut, 4>);
             COUNT_LAUNCH(); KERNEL_CHECK();
             return g;
         }
@@ -1211,18 +1238,22 @@ int launch_attn_decode(const float* QKV, const int* active, int M, const int* ct
     // warps per (row, head) item: the cache pages of an item are dealt round-robin to its warps.  4 is the default; 8 (engine
     // option "attn_warps", bf16 only) halves an item's latency and was meant to shorten the under-filled tail of the kernel —
     // measured 18 % SLOWER per decode step (run 7: 256-thread CTAs, three per SM), kept as an option.
-    if (sizeof(TKV) == 2 && g_attn_warps == 8)
+    const int l2_pages = (sizeof(TKV) == 2) ? g_attn_l2_pages : 0;
+    if (sizeof(TKV) == 2 && g_attn_warps == 16)
+        launch_k(attn_decode_kernel<TKV, TOut, 16>, dim3(grid), dim3(512), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
+                 kpool, vpool, out, heads, n_items, dep, l2_pages);
+    else if (sizeof(TKV) == 2 && g_attn_warps == 8)
         launch_k(attn_decode_kernel<TKV, TOut, 8>, dim3(grid), dim3(256), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
-                 kpool, vpool, out, heads, n_items, dep);
+                 kpool, vpool, out, heads, n_items, dep, l2_pages);
     else if (sizeof(TKV) == 2 && g_attn_warps == 2)
         launch_k(attn_decode_kernel<TKV, TOut, 2>, dim3(grid), dim3(64), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
-                 kpool, vpool, out, heads, n_items, dep);
+                 kpool, vpool, out, heads, n_items, dep, l2_pages);
     else if (sizeof(TKV) == 2 && g_attn_warps == 1)
         launch_k(attn_decode_kernel<TKV, TOut, 1>, dim3(grid), dim3(32), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
-                 kpool, vpool, out, heads, n_items, dep);
+                 kpool, vpool, out, heads, n_items, dep, l2_pages);
     else
         launch_k(attn_decode_kernel<TKV, TOut, 4>, dim3(grid), dim3(128), 0, st, pdl, QKV, active, ctx_len, block_tables, max_pages,
-                 kpool, vpool, out, heads, n_items, dep);
+                 kpool, vpool, out, heads, n_items, dep, l2_pages);
     COUNT_LAUNCH(); KERNEL_CHECK();
     return grid;
 }

@@ -11,7 +11,7 @@ namespace xtts {
 //          GEMM_RESID -> out = resid + (...)   (resid may alias out)
 // ------------------------------------------------------------------------------------------
 // GEMM_OUT_BF16: 16-bit output in the operand format;  GEMM_F16: the 16-bit operands (and that output) are IEEE fp16, not bf16
-enum : int { GEMM_GELU = 1, GEMM_RESID = 2, GEMM_OUT_BF16 = 4, GEMM_F16 = 8 };
+enum : int { GEMM_GELU = 1, GEMM_RESID = 2, GEMM_OUT_BF16 = 4, GEMM_F16 = 8, GEMM_NO_L2PF = 16 /* internal: engine option gemm_l2_prefetch = 0 */ };
 
 // fp32 CUDA-core path (parity mode; also the GPU-side reference for the tcgen05 path)
 void launch_gemm_f32(const float* A, const float* W, const float* bias, const float* resid, float* out,

@@ -325,27 +325,37 @@ def test_capped_attention_grid_and_forced_gemm_tile(engine_small, engine_full_bf
 
 
 def test_bulk_copy_attention_matches_register_attention(engine_small_bf16, engine_full_bf16, engine_full_fp16, dims_small, dims_full):
-    """Engine option "attn_bulk": the decode attention streams cache pages with cp.async.bulk into a shared-memory ring (one
-    producer thread, mbarriers, persistent CTAs that walk several (row, head) items, prefetch before griddepcontrol.wait)
-    instead of loading them into registers.  Same page -> warp assignment and operation order: tokens AND latents must be
+    """Engine option "attn_bulk": the decode attention streams cache pages with cp.async.bulk into shared-memory sub-rings (one
+    per consumer warp; a producer warp, mbarriers, L2 prefetch one item ahead, persistent CTAs that walk several (row, head)
+    items, streaming starts before griddepcontrol.wait) instead of loading them into registers.  Same page -> warp assignment
+    and operation order as the register kernel with as many warps ("attn_warps" = 4 / 8 / 16): tokens AND latents must be
     bit-identical, for every grid size / ring depth, across page boundaries (>= 3 pages of context) and in both 16-bit modes."""
     for eng, dims, n_tok in ((engine_small_bf16, dims_small, 40), (engine_full_bf16, dims_full, 70), (engine_full_fp16, dims_full, 70)):
-        g = dims.gpt
         jobs = [(i, text_ids(dims, 6 + 4 * i, 120 + i), i % 3,
                  Sampling(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, max_tokens=n_tok, seed=11, seq_seed=i,
                           stop_token=4095, vocode=False)) for i in range(7)]
-        ref = eng.run_batch(jobs, timeout_s=180, want_wav=False, want_latents=True)
         try:
-            for bulk, stages, grid in ((1, 8, 0), (2, 4, 0), (1, 4, -3), (1, 16, -5), (1, 12, -1000), (1, 8, -7)):
-                eng.set_option("attn_bulk", bulk); eng.set_option("attn_stages", stages); eng.set_option("attn_ctas_per_sm", grid)
-                eng.set_option("attn_l2_ahead", 0 if grid == -7 else 1)
-                got = eng.run_batch(jobs, timeout_s=180, want_wav=False, want_latents=True)
-                for sid in ref:
-                    assert list(got[sid][1]) == list(ref[sid][1]), (bulk, stages, grid, sid)
-                    assert len(got[sid][1]) == n_tok
-                    np.testing.assert_array_equal(got[sid][3], ref[sid][3])
+            for nw in (4, 8, 16):
+                eng.set_option("attn_warps", nw); eng.set_option("attn_bulk", 0); eng.set_option("attn_ctas_per_sm", 0)
+                ref = eng.run_batch(jobs, timeout_s=180, want_wav=False, want_latents=True)
+                for l2_pages in (1, 3):                  # register kernel + cp.async.bulk.prefetch.L2 of later pages: a hint only
+                    eng.set_option("attn_l2_pages", l2_pages)
+                    got = eng.run_batch(jobs, timeout_s=180, want_wav=False, want_latents=True)
+                    eng.set_option("attn_l2_pages", 0)
+                    for sid in ref:
+                        assert list(got[sid][1]) == list(ref[sid][1]), (nw, l2_pages, sid)
+                        np.testing.assert_array_equal(got[sid][3], ref[sid][3])
+                for bulk, stages, grid, l2 in ((1, 8, 0, 1), (2, 16, 0, 1), (1, 4, -3, 1), (1, 16, -5, 1), (1, 24, -1000, 1), (1, 16, 0, 0)):
+                    eng.set_option("attn_bulk", bulk); eng.set_option("attn_stages", stages); eng.set_option("attn_ctas_per_sm", grid)
+                    eng.set_option("attn_l2_ahead", l2)
+                    got = eng.run_batch(jobs, timeout_s=180, want_wav=False, want_latents=True)
+                    for sid in ref:
+                        assert list(got[sid][1]) == list(ref[sid][1]), (nw, bulk, stages, grid, sid)
+                        assert len(got[sid][1]) == n_tok
+                        np.testing.assert_array_equal(got[sid][3], ref[sid][3])
         finally:
-            eng.set_option("attn_bulk", 0); eng.set_option("attn_stages", 8); eng.set_option("attn_ctas_per_sm", 0); eng.set_option("attn_l2_ahead", 1)
+            for k, v in (("attn_bulk", 0), ("attn_stages", 8), ("attn_ctas_per_sm", 0), ("attn_l2_ahead", 1), ("attn_warps", 4), ("attn_l2_pages", 0)):
+                eng.set_option(k, v)
 
 
 def test_kernel_profile_graph_events(engine_small_bf16, dims_small):

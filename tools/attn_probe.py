@@ -29,16 +29,16 @@ def measure(**opts):
     for nt in (300, 400):
         t0 = time.time(); eng.run_batch(jobs(nt), timeout_s=600, want_wav=False); t.append(time.time() - t0)
     return 1e3 * (t[1] - t[0]) / 100
-cfgs = [dict(attn_bulk=b, attn_stages=st, attn_l2_ahead=l2, microbatches=mb)
-        for mb in (1, 2) for (b, st, l2) in ((0, 8, 1), (1, 8, 1), (1, 8, 0), (1, 12, 1), (1, 16, 1), (2, 8, 1), (2, 4, 1), (3, 4, 1))]
+cfgs = [dict(attn_bulk=b, attn_warps=nw, attn_stages=st, attn_l2_pages=lp, microbatches=mb)
+        for mb in (1, 2) for (b, nw, st, lp) in ((0, 4, 8, 0), (0, 4, 8, 1), (0, 4, 8, 2), (0, 4, 8, 3), (0, 4, 8, 5))]
 for extra in sys.argv[3:]:
     eng.set_option(extra.split("=")[0], int(extra.split("=")[1]))
 measure(**cfgs[0])
 res = {}
-for rep in range(2):
+for rep in range(3):
     for i in (range(len(cfgs)) if rep % 2 == 0 else reversed(range(len(cfgs)))):
         res.setdefault(i, []).append(measure(**cfgs[i]))
 for i, c in enumerate(cfgs):
     v = res[i]
-    print(f"bulk {c['attn_bulk']} stages {c['attn_stages']:2d} l2-ahead {c['attn_l2_ahead']} branches {c['microbatches']}: " + " ".join(f"{x:6.3f}" for x in v) + f"   min {min(v):6.3f} ms/decode-step", flush=True)
+    print(f"bulk {c['attn_bulk']} warps {c['attn_warps']:2d} stages {c['attn_stages']:2d} l2-pages {c['attn_l2_pages']} branches {c['microbatches']}: " + " ".join(f"{x:6.3f}" for x in v) + f"   min {min(v):6.3f} ms/decode-step", flush=True)
 eng.close()

@@ -23,7 +23,7 @@ for kv in os.environ.get("XTTS_OPTS", "").split(","):      # e.g. XTTS_OPTS=deco
           # ncu attributes kernels per launch either way; eager keeps names simple
 rng = np.random.RandomState(1)
 jobs = [(i, [0] + rng.randint(2, 6000, size=78).tolist() + [1], 0,
-         native.Sampling(temperature=0.75, top_p=0.85, top_k=50, max_tokens=nt, seed=1, seq_seed=i, vocode=False)) for i in range(nb)]
+         native.Sampling(temperature=0.75, top_p=0.85, top_k=50, max_tokens=nt, seed=1, seq_seed=i, vocode=False, stop_token=4095)) for i in range(nb)]
 eng.run_batch(jobs, timeout_s=600, want_wav=False)
 lat = rng.randn(voc_T, 1024).astype(np.float32)
 eng.vocode(lat, 0)
