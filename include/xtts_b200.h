@@ -155,6 +155,16 @@ int xtts_fetch(xtts_engine* e, uint64_t seq_id, int32_t* tokens, float* wav, flo
  *                         stream beside the decode step), 0 = one window per chunk when it ends.  Same samples either way.
  *   "voc_sms"             SMs the vocoder's persistent conv kernels may occupy while a decode step is in flight (0 = all)
  *   "voc_batch"           windows per vocoder launch (1..32, default 32; ragged lengths are batched together)
+ *   "attn_warps"          warps per (row, head) item of the 16-bit decode attention: 4 (default), 1 / 2 / 8 / 16 measured slower
+ *   "attn_ctas_per_sm"    > 0 caps the decode-attention grid (each CTA walks several items); < 0: absolute grid size (tests)
+ *   "attn_l2_pages"       n > 0: each warp of the decode attention asks L2 for n of its later pages per item
+ *                         (cp.async.bulk.prefetch.L2); default 0 (measured slower: the kernel is throughput-, not latency-bound)
+ *   "attn_bulk"           c > 0: decode attention in bulk-copy form (c persistent CTAs per SM stream cache pages with
+ *                         cp.async.bulk into "attn_stages" x 8 KB of shared-memory sub-rings, "attn_l2_ahead" = L2 prefetch
+ *                         one item ahead); bit-identical to the default register-load kernel, measured slower; default 0
+ *   "gemm_l2_prefetch"    1 = decode GEMMs prefetch the weight tiles of their later ring passes into L2 before the
+ *                         dependency wait; default 0 (no measurable effect)
+ *   "dep_flags" / "branch_stagger_us"   counter dependencies / delayed second branch in the decode step (default off)
  *   "profile"             1 = CUDA events around every launch (xtts_get_kernel_profile), "reset_stats" = zero the counters */
 int xtts_set_option(xtts_engine* e, const char* key, int64_t value);
 int xtts_get_stats(xtts_engine* e, xtts_stats* out);
