@@ -20,12 +20,16 @@ namespace xtts {
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
-constexpr int kEpiWarps = 8;                                  // two warpgroups: (w, w + 4) share a TMEM lane quarter
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+// epilogue warps EW = 8 or 16 (two or four warpgroups; warps w, w + 4, ... share a TMEM lane quarter and take alternate
+// 32-column chunks).  A warp's chunk is a dependent chain (tcgen05.ld -> wait for its previous TMA store to have read the box ->
+// shared stores -> fence -> TMA store) of ~2 us; with 8 warps a 128 x 256 fp32 tile takes ~8.7 us to drain — longer than its
+// MMAs at K = 1024 (5.8 us), so short-K shapes were epilogue-bound (run 9: 8.7 us per tile at K = 1024, 22.9 us = the MMA
+// time at K = 4096).  16 warps halve the chain per tile.
+constexpr int threads_for(int ew) { return 64 + 32 * ew; }
 constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2;      // per CTA and 64-wide k-block: 16 KB + 16 KB
 // a ring stage holds KPS k-blocks (KPS = 2: half the barrier round trips per byte)
-__host__ __device__ constexpr size_t smem_for(int stages, int kps) {
-    return (size_t)stages * kps * (A_BYTES + B_BYTES) + (size_t)kEpiWarps * 4096 + 1024;     // ring + epilogue boxes + alignment
+__host__ __device__ constexpr size_t smem_for(int stages, int kps, int ew) {
+    return (size_t)stages * kps * (A_BYTES + B_BYTES) + (size_t)ew * 4096 + 1024;     // ring + epilogue boxes + alignment
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -98,8 +102,8 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                  ::"r"(smem_u32(bar)), "h"((uint16_t)0b11) : "memory");
 }
 
-template <int STAGES, int KPS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+template <int STAGES, int KPS, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads_for(EW), 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* resid, int M, int N,
                       int K, int flags) {
@@ -113,7 +117,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * KPS * A_BYTES;
-    uint8_t* sC = smem + STAGES * KPS * (A_BYTES + B_BYTES);          // kEpiWarps x 4 KB: one 32 x 32 output box per warp
+    uint8_t* sC = smem + STAGES * KPS * (A_BYTES + B_BYTES);          // EW x 4 KB: one 32 x 32 output box per warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
@@ -123,7 +127,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kEpiWarps); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {        // the same warp of both CTAs allocates all 512 columns for the pair
@@ -200,7 +204,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = m0 + q * 32 + lane;
 #pragma unroll 1
-            for (int c = grp; c < BN / 32; c += kEpiWarps / 4) {
+            for (int c = grp; c < BN / 32; c += EW / 4) {
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c * 32);
                 asm volatile(
@@ -213,7 +217,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr) : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c + kEpiWarps / 4 >= BN / 32) {
+                if (c + EW / 4 >= BN / 32) {
                     // this warp has read the last of the buffer: hand it back to the (leader's) MMA thread before the stores
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
@@ -313,10 +317,12 @@ void launch_gemm_bf16_2cta(const __nv_bfloat16* A, const __nv_bfloat16* W, const
     }
     static bool attr[64] = {};
     if (first_on_device(attr)) {
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(3, 2)));
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(4, 1)));
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(6, 1)));
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(2, 2)));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<3, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(3, 2, 8)));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<4, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(4, 1, 8)));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<6, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(6, 1, 8)));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<2, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(2, 2, 8)));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<2, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(2, 2, 16)));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<5, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(5, 1, 16)));
     }
     static int n_sm = 0;
     if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
@@ -338,14 +344,22 @@ void launch_gemm_bf16_2cta(const __nv_bfloat16* A, const __nv_bfloat16* W, const
     const int clusters = std::min(total, n_sm / 2);
     ProfScope ps(KF_GEMM_TC, st, 2.0 * M * N * K,
                  2.0 * ((double)M * K + (double)N * K) + ((flags & GEMM_OUT_BF16) ? 2.0 : 4.0) * M * N);
-    // g_gemm_2cta selects the ring shape: 1 (default) = 3 stages x 2 k-blocks (best measured, run 8), 2: 4 x 1, 3: 6 x 1, 4: 2 x 2
-    const dim3 grid(2 * clusters), block(kThreads);
-    switch (g_gemm_2cta) {
-        case 2: gemm_bf16_2cta_kernel<4, 1><<<grid, block, smem_for(4, 1), st>>>(tmA, tmB, tmC, bias, resid, M, N, K, flags); break;
-        case 3: gemm_bf16_2cta_kernel<6, 1><<<grid, block, smem_for(6, 1), st>>>(tmA, tmB, tmC, bias, resid, M, N, K, flags); break;
-        case 4: gemm_bf16_2cta_kernel<2, 2><<<grid, block, smem_for(2, 2), st>>>(tmA, tmB, tmC, bias, resid, M, N, K, flags); break;
-        default: gemm_bf16_2cta_kernel<3, 2><<<grid, block, smem_for(3, 2), st>>>(tmA, tmB, tmC, bias, resid, M, N, K, flags); break;
+    // g_gemm_2cta selects the variant (ring stages x k-blocks per stage, epilogue warps):
+    //   1 (default): K < 2048 -> 5 x 1 ring, 16 epilogue warps (short K is epilogue-bound); else 3 x 2 ring, 8 warps (run 8)
+    //   2: 4 x 1, 8    3: 6 x 1, 8    4: 2 x 2, 8    5: 3 x 2, 8 for every K    6: 2 x 2, 16    7: 5 x 1, 16 for every K
+    const dim3 grid(2 * clusters);
+    int v = g_gemm_2cta;
+    if (v == 1) v = (K < 2048) ? 7 : 5;
+#define XTTS_2CTA(ST, KP, E) gemm_bf16_2cta_kernel<ST, KP, E><<<grid, dim3(threads_for(E)), smem_for(ST, KP, E), st>>>(tmA, tmB, tmC, bias, resid, M, N, K, flags)
+    switch (v) {
+        case 2: XTTS_2CTA(4, 1, 8); break;
+        case 3: XTTS_2CTA(6, 1, 8); break;
+        case 4: XTTS_2CTA(2, 2, 8); break;
+        case 6: XTTS_2CTA(2, 2, 16); break;
+        case 7: XTTS_2CTA(5, 1, 16); break;
+        default: XTTS_2CTA(3, 2, 8); break;
     }
+#undef XTTS_2CTA
     COUNT_LAUNCH(); KERNEL_CHECK();
 }
 

@@ -60,6 +60,30 @@ def test_gemm_bf16_tcgen05(engine_small, M, N, K):
                                                           np.unravel_index(np.abs(out - ref).argmax(), out.shape))
 
 
+@pytest.mark.parametrize("variant", [2, 3, 4, 5, 6, 7])
+def test_gemm_2cta_ring_and_epilogue_variants(engine_small, variant):
+    """Engine option "gemm_2cta" = 2..7: ring shapes (stages x k-blocks per stage) and 8 / 16 epilogue warps of the CTA-pair kernel.
+    Every variant, on ragged tiles with more tiles than clusters and on a 16-bit-output... (fp32 here) path, must give the
+    default's result bit for bit (same MMA order per output element)."""
+    outs = {}
+    for (M, N, K) in ((1000, 3072, 1024), (513, 288, 192), (2304, 1056, 1024)):
+        rng = np.random.RandomState(M + N)
+        A = rng.randn(M, K).astype(np.float32)
+        W = (rng.randn(N, K) * 0.05).astype(np.float32)
+        b = rng.randn(N).astype(np.float32)
+        r = rng.randn(M, N).astype(np.float32)
+        try:
+            engine_small.set_option("gemm_2cta", variant)
+            got, _ = engine_small.debug_gemm(1, A, W, b, r, True)
+        finally:
+            engine_small.set_option("gemm_2cta", 1)
+        ref = _ref_gemm(_bf16(A), _bf16(W), b, r, True)
+        assert np.isfinite(got).all()
+        assert np.abs(got - ref).max() < 2e-3 * max(1.0, np.abs(ref).max()), (variant, M, N, K)
+        base, _ = engine_small.debug_gemm(1, A, W, b, r, True)
+        np.testing.assert_array_equal(got, base)
+
+
 def test_gemm_tcgen05_speed_report(engine_small):
     """Not a pass/fail perf gate: prints achieved TFLOP/s of both GEMM paths at a prefill-like and a decode-like shape."""
     for (M, N, K) in ((4096, 4096, 1024), (160, 3072, 1024)):

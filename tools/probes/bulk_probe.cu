@@ -17,7 +17,7 @@ __device__ __forceinline__ void bulk(void* dst, const void* src, uint32_t n, uin
 // each CTA streams `per_cta` bytes: stage = `copies` bulk copies of `csize` bytes (scattered `stride` apart), `depth` stages.
 // `np` producer lanes each own stages s % np == lane (np = 1: one thread issues everything).  mode 1: consumers also read the
 // stage into registers (LDS.128) before handing it back.
-__global__ void __launch_bounds__(160) probe(const uint8_t* src, size_t per_cta, int csize, int copies, int depth, int np, int mode, size_t stride, float* sink) {
+__global__ void __launch_bounds__(160) probe(const uint8_t* src, size_t per_cta, int csize, int copies, int depth, int np, int mode, size_t stride, float* sink, unsigned long long nblocks) {
     extern __shared__ __align__(128) uint8_t ring[];
     __shared__ __align__(8) uint64_t full[32], empty[32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -34,7 +34,12 @@ __global__ void __launch_bounds__(160) probe(const uint8_t* src, size_t per_cta,
                 bar_wait(&empty[s], ((c / depth) & 1) ^ 1);
                 bar_expect(&full[s], (uint32_t)stage_bytes);
                 for (int k = 0; k < copies; ++k)
-                    bulk(ring + (size_t)s * stage_bytes + (size_t)k * csize, base + ((size_t)c * copies + k) * stride, csize, &full[s]);
+                    if (stride != 0) bulk(ring + (size_t)s * stage_bytes + (size_t)k * csize, base + ((size_t)c * copies + k) * stride, csize, &full[s]);
+                    else {          // scattered: every copy reads a pseudo-randomly placed csize-aligned block of the whole buffer
+                        const unsigned long long i = ((unsigned long long)blockIdx.x * n + c) * copies + k;
+                        const unsigned long long blk = (i * 0x9E3779B1ull + 12345ull) % nblocks;
+                        bulk(ring + (size_t)s * stage_bytes + (size_t)k * csize, src + blk * (size_t)csize, csize, &full[s]);
+                    }
             }
         return;
     }
@@ -58,11 +63,10 @@ int main() {
     float* sink; cudaMalloc(&sink, 4);
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    struct Cfg { int csize, copies, depth, np, mode, ctas_per_sm; };
-    const Cfg cfgs[] = {{4096, 2, 8, 1, 0, 1}, {4096, 2, 8, 1, 1, 1}, {4096, 2, 16, 1, 0, 1}, {4096, 2, 8, 2, 0, 1}, {4096, 2, 8, 4, 0, 1}, {4096, 2, 16, 8, 0, 1},
-                         {8192, 1, 8, 1, 0, 1}, {8192, 2, 8, 1, 0, 1}, {16384, 1, 8, 1, 0, 1}, {16384, 1, 4, 1, 0, 1}, {32768, 1, 4, 1, 0, 1}, {32768, 1, 6, 1, 1, 1},
-                         {2048, 4, 8, 1, 0, 1}, {4096, 2, 8, 1, 0, 2}, {4096, 2, 8, 1, 1, 2}, {4096, 2, 8, 4, 1, 2}, {4096, 2, 4, 1, 0, 4}, {16384, 1, 4, 1, 1, 2},
-                         {4096, 4, 8, 1, 0, 1}, {4096, 8, 4, 1, 0, 1}, {4096, 8, 4, 1, 1, 1}};
+    struct Cfg { int csize, copies, depth, np, mode, ctas_per_sm, scatter; };
+    const Cfg cfgs[] = {{4096, 2, 16, 8, 0, 1, 0}, {4096, 2, 16, 8, 0, 1, 1}, {4096, 2, 8, 8, 0, 2, 0}, {4096, 2, 8, 8, 0, 2, 1},
+                         {4096, 2, 8, 8, 0, 1, 1}, {16384, 1, 8, 2, 0, 1, 0}, {16384, 1, 8, 2, 0, 1, 1}, {65536, 1, 2, 1, 0, 1, 0}, {65536, 1, 2, 1, 0, 1, 1},
+                         {1024, 8, 16, 8, 0, 1, 1}, {512, 16, 16, 8, 0, 1, 1}, {4096, 2, 8, 8, 0, 3, 1}};
     for (const Cfg& c : cfgs) {
         const int grid = nsm * c.ctas_per_sm;
         const size_t stage = (size_t)c.csize * c.copies;
@@ -72,14 +76,14 @@ int main() {
         float best = 1e9f;
         for (int rep = 0; rep < 3; ++rep) {
             cudaEventRecord(a);
-            probe<<<grid, 160, smem>>>(src, per_cta, c.csize, c.copies, c.depth, c.np, c.mode, (size_t)c.csize, sink);
+            probe<<<grid, 160, smem>>>(src, per_cta, c.csize, c.copies, c.depth, c.np, c.mode, c.scatter ? 0 : (size_t)c.csize, sink, (unsigned long long)(total / c.csize));
             cudaEventRecord(b); cudaEventSynchronize(b);
             float ms; cudaEventElapsedTime(&ms, a, b); best = ms < best ? ms : best;
         }
         cudaError_t e = cudaGetLastError();
         const double gbs = (double)per_cta * grid / best / 1e6;
-        printf("copy %6d B x %d per stage, depth %2d (%3zu KB in flight/CTA), %d issuing lane(s), %d CTA/SM, consumers %s: %8.1f GB/s total, %6.1f GB/s per SM  %s\n",
-               c.csize, c.copies, c.depth, smem >> 10, c.np, c.ctas_per_sm, c.mode ? "read stage" : "idle", gbs, gbs / nsm, e == cudaSuccess ? "" : cudaGetErrorString(e));
+        printf("%s copy %6d B x %d per stage, depth %2d (%3zu KB in flight/CTA), %d issuing lane(s), %d CTA/SM, consumers %s: %8.1f GB/s total, %6.1f GB/s per SM  %s\n",
+               c.scatter ? "scattered " : "sequential", c.csize, c.copies, c.depth, smem >> 10, c.np, c.ctas_per_sm, c.mode ? "read stage" : "idle", gbs, gbs / nsm, e == cudaSuccess ? "" : cudaGetErrorString(e));
     }
     return 0;
 }
