@@ -100,6 +100,7 @@ struct KernelCtx {
     int attn_stages = 8;          // ring depth of that kernel (8 KB per stage)
     int attn_l2_pages = 0;        // register-load decode attention: every warp prefetches the page this many of its pages ahead into L2
     int attn_l2_ahead = 1;        // that kernel prefetches the next item's pages into L2 (cp.async.bulk.prefetch.L2)
+    int gemm_deep_ring = 0;       // decode-shaped unsplit GEMMs use a ring that fills the SM (BN 32: 10 stages, BN 64: 8) instead of 5 / 4
     int gemm_l2_prefetch = 0;     // one-tile tcgen05 GEMM: weight tiles beyond the first ring pass are prefetched into L2 before the dependency wait
     int gemm_2cta = 1;            // large shapes (M >= 256) go to the persistent CTA-pair kernel (gemm_tcgen05_2cta.cu)
 };
@@ -112,6 +113,7 @@ struct KernelCtx {
 #define g_gemm_2cta (::xtts::kctx().gemm_2cta)
 #define g_attn_warps (::xtts::kctx().attn_warps)
 #define g_gemm_l2_prefetch (::xtts::kctx().gemm_l2_prefetch)
+#define g_gemm_deep_ring (::xtts::kctx().gemm_deep_ring)
 #define g_attn_bulk (::xtts::kctx().attn_bulk)
 #define g_attn_stages (::xtts::kctx().attn_stages)
 #define g_attn_l2_ahead (::xtts::kctx().attn_l2_ahead)

@@ -1859,6 +1859,7 @@ void Engine::set_option(const std::string& k, int64_t v) {
     else if (k == "voc_batch") voc_max_items = (int)std::max<int64_t>(1, std::min<int64_t>(v, kVocMaxItems));
     else if (k == "gemm_2cta") g_gemm_2cta = (int)std::max<int64_t>(0, std::min<int64_t>(v, 7));      // 0 off, 1 default, 2-7 ring / epilogue variants
     else if (k == "attn_bulk") { g_attn_bulk = (int)std::max<int64_t>(0, std::min<int64_t>(v, 4)); drop_graphs(); }
+    else if (k == "gemm_deep_ring") { g_gemm_deep_ring = v ? 1 : 0; drop_graphs(); }
     else if (k == "gemm_l2_prefetch") { g_gemm_l2_prefetch = v ? 1 : 0; drop_graphs(); }
     else if (k == "attn_l2_pages") { g_attn_l2_pages = (int)std::max<int64_t>(0, std::min<int64_t>(v, 8)); drop_graphs(); }
     else if (k == "attn_l2_ahead") { g_attn_l2_ahead = v ? 1 : 0; drop_graphs(); }

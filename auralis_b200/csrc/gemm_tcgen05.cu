@@ -90,13 +90,16 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
-template <int BN>
+// STAGES = 0: the default ring (stages_for(BN), two CTAs of the narrow tiles fit on an SM); otherwise an explicit depth — the
+// "deep" instantiations (engine option "gemm_deep_ring") fill the SM's shared memory with ONE CTA's ring: a decode-shaped GEMM
+// is a chain of ring passes that each pay the load latency, and its 16 k-blocks then need 1.6 passes instead of 3.2
+template <int BN, int STAGES_ = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const float* __restrict__ bias, const float* resid, void* out, int M, int N, int K, int flags,
                     int a_box_rows, const DepFlag dep) {
     // (bias / out / flags are re-pointed below for split-K launches)
-    constexpr int STAGES = stages_for(BN);
+    constexpr int STAGES = STAGES_ > 0 ? STAGES_ : stages_for(BN);
     constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ uint8_t smem_raw[];
@@ -278,22 +281,32 @@ void encode_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, u
     }
 }
 
-template <int BN>
-int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, const float* resid, void* out, int M,
-              int N, int K, int flags, cudaStream_t st, int splits, int a_box_rows, bool pdl, const DepFlag& dep) {
-    constexpr int STAGES = stages_for(BN);
+constexpr int deep_stages_for(int bn) { return bn >= 128 ? 6 : (bn >= 64 ? 8 : 10); }
+
+template <int BN, int STAGES_>
+int launch_bn_st(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, const float* resid, void* out, int M,
+                 int N, int K, int flags, cudaStream_t st, int splits, int a_box_rows, bool pdl, const DepFlag& dep) {
+    constexpr int STAGES = STAGES_ > 0 ? STAGES_ : stages_for(BN);
     constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
     static bool attr_set[64] = {};
     if (first_on_device(attr_set))
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, STAGES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
     ProfScope ps(KF_GEMM_TC, st, 2.0 * M * N * K,
                  2.0 * ((double)M * K + (double)N * K) + ((flags & GEMM_OUT_BF16) ? 2.0 : 4.0) * M * N);
     if (dep.wait && (flags & GEMM_RESID)) throw CudaError("gemm_bf16_tc: a counter dependency cannot order a residual read");
-    launch_k(gemm_bf16_tc_kernel<BN>, grid, dim3(kThreads), smem, st, pdl, tmA, tmB, bias, resid, out, M, N, K,
+    launch_k(gemm_bf16_tc_kernel<BN, STAGES_>, grid, dim3(kThreads), smem, st, pdl, tmA, tmB, bias, resid, out, M, N, K,
              flags | (g_gemm_l2_prefetch ? 0 : GEMM_NO_L2PF), a_box_rows, dep);
     COUNT_LAUNCH(); KERNEL_CHECK();
     return (int)(grid.x * grid.y * grid.z);
+}
+template <int BN>
+int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, const float* resid, void* out, int M,
+              int N, int K, int flags, cudaStream_t st, int splits, int a_box_rows, bool pdl, const DepFlag& dep) {
+    // deep ring: only where the whole K range is one CTA's (no split-K: those CTAs have 2-4 k-blocks) and the shape is decode's
+    if (g_gemm_deep_ring && BN < 128 && M <= 256 && splits == 1 && K / BK > stages_for(BN))
+        return launch_bn_st<BN, deep_stages_for(BN)>(tmA, tmB, bias, resid, out, M, N, K, flags, st, splits, a_box_rows, pdl, dep);
+    return launch_bn_st<BN, 0>(tmA, tmB, bias, resid, out, M, N, K, flags, st, splits, a_box_rows, pdl, dep);
 }
 
 
@@ -603,6 +616,9 @@ bool gemm_tc_init(std::string* err) {
         cudaFuncSetAttribute(gemm_bf16_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(128));
         cudaFuncSetAttribute(gemm_bf16_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(64));
         cudaFuncSetAttribute(gemm_bf16_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(32));
+        auto deep_of = [](int bn) { return (int)(deep_stages_for(bn) * (BM * BK * 2 + bn * BK * 2) + 1024); };
+        cudaFuncSetAttribute(gemm_bf16_tc_kernel<64, deep_stages_for(64)>, cudaFuncAttributeMaxDynamicSharedMemorySize, deep_of(64));
+        cudaFuncSetAttribute(gemm_bf16_tc_kernel<32, deep_stages_for(32)>, cudaFuncAttributeMaxDynamicSharedMemorySize, deep_of(32));
         (void)cudaGetLastError();
     };
     if (g_encode) { per_device(); return true; }

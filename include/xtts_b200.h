@@ -162,6 +162,7 @@ int xtts_fetch(xtts_engine* e, uint64_t seq_id, int32_t* tokens, float* wav, flo
  *   "attn_bulk"           c > 0: decode attention in bulk-copy form (c persistent CTAs per SM stream cache pages with
  *                         cp.async.bulk into "attn_stages" x 8 KB of shared-memory sub-rings, "attn_l2_ahead" = L2 prefetch
  *                         one item ahead); bit-identical to the default register-load kernel, measured slower; default 0
+ *   "gemm_deep_ring"      1 = unsplit decode GEMMs use a ring that fills the SM (one CTA per SM); default 0 (measured slower)
  *   "gemm_l2_prefetch"    1 = decode GEMMs prefetch the weight tiles of their later ring passes into L2 before the
  *                         dependency wait; default 0 (no measurable effect)
  *   "dep_flags" / "branch_stagger_us"   counter dependencies / delayed second branch in the decode step (default off)

@@ -304,7 +304,7 @@ def test_capped_attention_grid_and_forced_gemm_tile(engine_small, engine_full_bf
     """Engine options "attn_ctas_per_sm" (decode attention walks several (row, head) items per CTA) and "gemm_bn" (tile
     width of the decode GEMMs) change scheduling only: tokens and waveforms must be unchanged."""
     for eng, dims, opts in ((engine_small, dims_small, [("attn_ctas_per_sm", -3)]),
-                            (engine_full_bf16, dims_full, [("attn_ctas_per_sm", -5), ("gemm_bn", 64)])):
+                            (engine_full_bf16, dims_full, [("attn_ctas_per_sm", -5), ("gemm_bn", 64), ("gemm_deep_ring", 1), ("gemm_l2_prefetch", 1)])):
         g = dims.gpt
         jobs = [(i, text_ids(dims, 6 + 4 * i, 90 + i), i % 3,
                  Sampling(temperature=0.75, top_p=0.85, top_k=50, repetition_penalty=5.0, max_tokens=10, seed=3, seq_seed=i,

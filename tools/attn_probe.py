@@ -29,8 +29,11 @@ def measure(**opts):
     for nt in (300, 400):
         t0 = time.time(); eng.run_batch(jobs(nt), timeout_s=600, want_wav=False); t.append(time.time() - t0)
     return 1e3 * (t[1] - t[0]) / 100
+import json
 cfgs = [dict(attn_bulk=b, attn_warps=nw, attn_stages=st, attn_l2_pages=lp, microbatches=mb)
         for mb in (1, 2) for (b, nw, st, lp) in ((0, 4, 8, 0), (0, 4, 8, 1), (0, 4, 8, 2), (0, 4, 8, 3), (0, 4, 8, 5))]
+if os.environ.get("STEP_CFGS"):          # any list of option dicts, e.g. STEP_CFGS='[{"gemm_deep_ring":0},{"gemm_deep_ring":1}]'
+    cfgs = json.loads(os.environ["STEP_CFGS"])
 for extra in sys.argv[3:]:
     eng.set_option(extra.split("=")[0], int(extra.split("=")[1]))
 measure(**cfgs[0])
@@ -40,5 +43,5 @@ for rep in range(3):
         res.setdefault(i, []).append(measure(**cfgs[i]))
 for i, c in enumerate(cfgs):
     v = res[i]
-    print(f"bulk {c['attn_bulk']} warps {c['attn_warps']:2d} stages {c['attn_stages']:2d} l2-pages {c['attn_l2_pages']} branches {c['microbatches']}: " + " ".join(f"{x:6.3f}" for x in v) + f"   min {min(v):6.3f} ms/decode-step", flush=True)
+    print(" ".join(f"{k}={val}" for k, val in c.items()) + ": " + " ".join(f"{x:6.3f}" for x in v) + f"   min {min(v):6.3f} ms/decode-step", flush=True)
 eng.close()
