@@ -11,8 +11,9 @@ What is pinned and how (tests/test_text_golden.py, vectors in tests/golden/text_
     with the reference's own functions, imported unmodified, with `num2words` replaced by a marker function on both sides;
   * the number WORDS come from the third-party `num2words` package (not installed here, not vendored by the
     reference).  `verbalise()` restates its conventions for en / es / fr / de / it / pt (the languages of
-    BASELINE.json's multilingual config that use digits); there is no copy of num2words to check against, so the
-    word lists are "parity unpinned" (DESIGN.md §7).  For ar / cs / hu / ko / nl / pl / ru / tr digits are kept.
+    BASELINE.json's multilingual config that use digits) and, in `numwords_more.py`, for nl / tr / hu / ru / pl / cs (cardinals,
+    fractions, Dutch and Turkish ordinals); there is no copy of num2words to check against, so the word lists are "parity
+    unpinned" (DESIGN.md §7).  For ar / ko digits are kept.
   * zh number normalisation is the reference's own `zh_num2words.TextNorm`: restated in `zh_textnorm.py` and pinned against
     that module (golden records + live fuzz, tests/test_zh_textnorm.py).  The zh / ja / ko romanisation is
     third-party (pypinyin, cutlet, hangul_romanize): it is called exactly as the reference calls it when the package is
@@ -22,6 +23,8 @@ from __future__ import annotations
 
 import re
 from typing import Callable, Dict, List, Optional, Tuple
+
+from . import numwords_more as _MORE
 
 # ---------------------------------------------------------------------------------------------------------------
 # tables (tokenizer.py:241-398 abbreviations, :407-594 symbols, :603-618 ordinal suffixes, :650-665 unit separators)
@@ -530,6 +533,12 @@ def verbalise(number, ordinal: bool = False, lang: str = "en", to: str = "cardin
     (for an ordinal or an amount: the digits of the number alone)."""
     if lang == "cz":
         lang = "cs"
+    if lang in _MORE.CARDINAL:                 # nl, tr, hu, ru, pl, cs: numwords_more.py (cardinals, fractions, some ordinals)
+        if to == "currency":
+            return repr(float(number)) if not float(number).is_integer() else str(int(number))
+        if ordinal or to == "ordinal":
+            return _MORE.ORDINAL[lang](int(number)) if lang in _MORE.ORDINAL else str(number)
+        return _MORE.decimal_words(number, lang) if isinstance(number, float) else _MORE.CARDINAL[lang](int(number))
     if lang not in VERBALISED_LANGS:
         if to == "currency":
             return repr(float(number)) if not float(number).is_integer() else str(int(number))

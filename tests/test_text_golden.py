@@ -114,8 +114,31 @@ def test_number_words_follow_num2words_conventions():
         "mil duzentos e trinta e quatro", "dois mil", "um milhão", "dois milhões"]
     assert v(1.5, lang="pt") == "um vírgula cinco" and v(11, ordinal=True, lang="pt") == "décimo primeiro"
     assert v(5.5, to="currency", currency="EUR", lang="pt") == "cinco euros e cinquenta cêntimos"
-    # languages without a restatement keep their digits
-    assert v(12, lang="pl") == "12" and v(7, ordinal=True, lang="cz") == "7"
+    # Dutch, Turkish, Hungarian, Russian, Polish, Czech (numwords_more.py)
+    assert [v(n, lang="nl") for n in (0, 21, 22, 23, 100, 101, 1000, 1234, 2000, 21000, 1000000, 2500000)] == [
+        "nul", "eenentwintig", "tweeëntwintig", "drieëntwintig", "honderd", "honderdeen", "duizend", "duizendtweehonderdvierendertig",
+        "tweeduizend", "eenentwintigduizend", "een miljoen", "twee miljoen vijfhonderdduizend"]
+    assert [v(n, ordinal=True, lang="nl") for n in (1, 3, 8, 13, 20, 100, 101)] == [
+        "eerste", "derde", "achtste", "dertiende", "twintigste", "honderdste", "honderdeerste"]
+    assert v(3.25, lang="nl") == "drie komma twee vijf"
+    assert [v(n, lang="tr") for n in (0, 11, 100, 101, 1000, 2345, 1000000)] == [
+        "sıfır", "onbir", "yüz", "yüzbir", "bin", "ikibinüçyüzkırkbeş", "birmilyon"]
+    assert [v(n, ordinal=True, lang="tr") for n in (1, 4, 6, 9, 20, 34, 100)] == [
+        "birinci", "dördüncü", "altıncı", "dokuzuncu", "yirminci", "otuzdördüncü", "yüzüncü"]
+    assert [v(n, lang="hu") for n in (0, 2, 12, 21, 200, 1000, 1999, 2000, 2001, 22000, 2500000)] == [
+        "nulla", "kettő", "tizenkettő", "huszonegy", "kétszáz", "ezer", "ezerkilencszázkilencvenkilenc", "kétezer", "kétezer-egy",
+        "huszonkétezer", "kétmillió-ötszázezer"]
+    assert v(3.5, lang="hu") == "három egész öt tized"
+    assert [v(n, lang="ru") for n in (0, 21, 101, 1000, 2000, 5000, 11000, 21000, 1000000, 2000000, 5000000)] == [
+        "ноль", "двадцать один", "сто один", "одна тысяча", "две тысячи", "пять тысяч", "одиннадцать тысяч", "двадцать одна тысяча",
+        "один миллион", "два миллиона", "пять миллионов"]
+    assert v(3.05, lang="ru") == "три запятая ноль пять"
+    assert [v(n, lang="pl") for n in (0, 21, 1000, 2000, 5000, 12000, 22000, 1000000)] == [
+        "zero", "dwadzieścia jeden", "tysiąc", "dwa tysiące", "pięć tysięcy", "dwanaście tysięcy", "dwadzieścia dwa tysiące", "milion"]
+    assert v(3.25, lang="pl") == "trzy przecinek dwadzieścia pięć"
+    assert [v(n, lang="cz") for n in (0, 21, 200, 1000, 2000, 5000)] == ["nula", "dvacet jedna", "dvě stě", "tisíc", "dva tisíce", "pět tisíc"]
+    # what is not restated keeps its digits: Arabic and Korean altogether, ordinals and amounts of the six languages above
+    assert v(12, lang="ar") == "12" and v(7, ordinal=True, lang="cz") == "7" and v(5.5, to="currency", currency="EUR", lang="pl") == "5.5"
 
 
 def test_cleaners_end_to_end_with_number_words():
@@ -126,7 +149,10 @@ def test_cleaners_end_to_end_with_number_words():
     assert T.preprocess_text("El Sr. García pagó 20€ el 1º", "es") == "el señor garcía pagó veinte euros el primero"
     assert T.preprocess_text("Mme. Dupont a 71 ans & 2,5 chats", "fr") == "madame dupont a soixante et onze ans et deux virgule cinq chats"
     assert T.preprocess_text("ÇOK  İYİ", "tr") == "çok iyi"                                    # dotted capital İ mapped before lower()
-    assert T.preprocess_text("To jest 12 & 3", "pl") == "to jest 12 i 3"                       # digits kept (no Polish number words)
+    assert T.preprocess_text("To jest 12 & 3", "pl") == "to jest dwanaście i trzy"
+    assert T.preprocess_text("Ik heb 21 appels en 3,5 liter op de 3de dag", "nl") == "ik heb eenentwintig appels en drie komma vijf liter op de derde dag"
+    assert T.preprocess_text("У меня 21000 рублей", "ru") == "у меня двадцать одна тысяча рублей"
+    assert T.preprocess_text("هذا 12", "ar") == "هذا 12"                                        # digits kept (no Arabic number words)
     assert T.format_for_bpe("Hello there", "en") == "[en]hello[SPACE]there"
     assert T.format_for_bpe("你好", "zh-cn").startswith("[zh-cn]")
     assert T.preprocess_text("MiXed   Case", "xx") == "mixed case"
