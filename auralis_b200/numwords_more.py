@@ -6,7 +6,7 @@ against; they restate the library's published conventions (word lists, plural ru
 read) from the languages' grammar.  What IS pinned is everything around them (which spans are numbers, ordinals, amounts, in which
 order they are expanded): `tests/test_text_golden.py` runs our cleaners and the reference's with the same marker verbaliser.
 
-Cardinals for all six; ordinals for Dutch and Turkish; fractions: Dutch digit by digit after "komma" (the base class's reading),
+Cardinals for all six; ordinals for Dutch, Turkish and Hungarian; fractions: Dutch digit by digit after "komma" (the base class's reading),
 Russian / Polish / Czech as an integer after "запятая" / "przecinek" / "celá" with leading zeros spoken (those three modules
 share that code), Hungarian "egész ... tized / század / ezred".  Amounts of money and the other ordinals keep their digits."""
 from typing import Callable, Dict, List, Tuple
@@ -159,6 +159,25 @@ def cardinal_hu(n: int) -> str:
 
 
 _HU_FRACTION = {1: "tized", 2: "század", 3: "ezred"}
+# the last component of the cardinal takes its ordinal form (longest match first); 1 and 2 alone are suppletive
+_HU_ORD_LAST = [("milliárd", "milliárdodik"), ("millió", "milliomodik"), ("billió", "billiomodik"), ("kilencven", "kilencvenedik"),
+                ("nyolcvan", "nyolcvanadik"), ("hetven", "hetvenedik"), ("hatvan", "hatvanadik"), ("ötven", "ötvenedik"),
+                ("negyven", "negyvenedik"), ("harminc", "harmincadik"), ("húsz", "huszadik"), ("tíz", "tizedik"), ("száz", "századik"),
+                ("ezer", "ezredik"), ("kilenc", "kilencedik"), ("nyolc", "nyolcadik"), ("három", "harmadik"), ("kettő", "kettedik"),
+                ("négy", "negyedik"), ("egy", "egyedik"), ("hét", "hetedik"), ("hat", "hatodik"), ("öt", "ötödik")]
+
+
+def ordinal_hu(n: int) -> str:
+    """1 -> 'első', 2 -> 'második', 21 -> 'huszonegyedik', 100 -> 'századik', 2001 -> 'kétezer-egyedik'."""
+    if n == 1:
+        return "első"
+    if n == 2:
+        return "második"
+    word = cardinal_hu(n)
+    for tail, repl in _HU_ORD_LAST:
+        if word.endswith(tail):
+            return word[: len(word) - len(tail)] + repl
+    return word
 
 
 # --------------------------------------------------------------------------------------------------- Russian / Polish / Czech
@@ -261,7 +280,7 @@ def cardinal_cs(n: int) -> str:
 # --------------------------------------------------------------------------------------------------- tables for textnorm.verbalise
 CARDINAL: Dict[str, Callable[[int], str]] = {"nl": cardinal_nl, "tr": cardinal_tr, "hu": cardinal_hu, "ru": cardinal_ru,
                                              "pl": cardinal_pl, "cs": cardinal_cs}
-ORDINAL: Dict[str, Callable[[int], str]] = {"nl": ordinal_nl, "tr": ordinal_tr}
+ORDINAL: Dict[str, Callable[[int], str]] = {"nl": ordinal_nl, "tr": ordinal_tr, "hu": ordinal_hu}
 
 
 def _split_float(value: float) -> Tuple[str, str]:

@@ -129,6 +129,9 @@ def test_number_words_follow_num2words_conventions():
         "nulla", "kettő", "tizenkettő", "huszonegy", "kétszáz", "ezer", "ezerkilencszázkilencvenkilenc", "kétezer", "kétezer-egy",
         "huszonkétezer", "kétmillió-ötszázezer"]
     assert v(3.5, lang="hu") == "három egész öt tized"
+    assert [v(n, ordinal=True, lang="hu") for n in (1, 2, 3, 5, 10, 11, 12, 20, 21, 36, 100, 101, 1000, 2001)] == [
+        "első", "második", "harmadik", "ötödik", "tizedik", "tizenegyedik", "tizenkettedik", "huszadik", "huszonegyedik",
+        "harminchatodik", "századik", "százegyedik", "ezredik", "kétezer-egyedik"]
     assert [v(n, lang="ru") for n in (0, 21, 101, 1000, 2000, 5000, 11000, 21000, 1000000, 2000000, 5000000)] == [
         "ноль", "двадцать один", "сто один", "одна тысяча", "две тысячи", "пять тысяч", "одиннадцать тысяч", "двадцать одна тысяча",
         "один миллион", "два миллиона", "пять миллионов"]
