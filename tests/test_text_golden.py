@@ -144,6 +144,20 @@ def test_number_words_follow_num2words_conventions():
     assert v(12, lang="ar") == "12" and v(7, ordinal=True, lang="cz") == "7" and v(5.5, to="currency", currency="EUR", lang="pl") == "5.5"
 
 
+def test_number_words_are_injective_and_clean():
+    """A table typo shows up as two numbers with one reading, an empty group or a stray digit: every restated language must
+    give 30 000 consecutive integers (and a few large ones) distinct, trimmed, digit-free readings."""
+    v = T.verbalise
+    probe = list(range(0, 30001, 1)) + [10 ** 6, 10 ** 6 + 1, 2 * 10 ** 6 + 345678, 10 ** 9, 123456789012]
+    for lang in ("en", "es", "fr", "de", "it", "pt", "nl", "tr", "hu", "ru", "pl", "cs"):
+        seen = {}
+        for n in probe:
+            w = v(n, lang=lang)
+            assert w and w == w.strip() and "  " not in w and not any(ch.isdigit() for ch in w), (lang, n, w)
+            assert w not in seen, (lang, n, seen[w], w)
+            seen[w] = n
+
+
 def test_cleaners_end_to_end_with_number_words():
     c = T.preprocess_text('Dr. Smith paid $5.50 for the 21st "copy", 1,234 in all & 3.5% more.', "en")
     assert c == ("doctor smith paid five dollars, fifty cents for the twenty-first copy, one thousand, two hundred and "
