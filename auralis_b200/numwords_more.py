@@ -8,7 +8,8 @@ order they are expanded): `tests/test_text_golden.py` runs our cleaners and the 
 
 Cardinals for all six; ordinals for Dutch, Turkish and Hungarian; fractions: Dutch digit by digit after "komma" (the base class's reading),
 Russian / Polish / Czech as an integer after "запятая" / "przecinek" / "celá" with leading zeros spoken (those three modules
-share that code), Hungarian "egész ... tized / század / ezred".  Amounts of money and the other ordinals keep their digits."""
+share that code), Hungarian "egész ... tized / század / ezred"; amounts of money as "<amount> <unit>, <cents> <sub-unit>".  The other
+ordinals (ru / pl / cs) keep their digits."""
 from typing import Callable, Dict, List, Tuple
 
 
@@ -281,6 +282,39 @@ def cardinal_cs(n: int) -> str:
 CARDINAL: Dict[str, Callable[[int], str]] = {"nl": cardinal_nl, "tr": cardinal_tr, "hu": cardinal_hu, "ru": cardinal_ru,
                                              "pl": cardinal_pl, "cs": cardinal_cs}
 ORDINAL: Dict[str, Callable[[int], str]] = {"nl": ordinal_nl, "tr": ordinal_tr, "hu": ordinal_hu}
+
+
+# (unit forms, sub-unit forms): two forms (one / many) for nl, hu, tr; three (1 / 2-4 / 5+, picked by the language's plural rule)
+# for ru, pl, cs.  Read as "<amount> <unit>, <cents> <sub-unit>": ", " is the separator the reference trims integer amounts at
+# (tokenizer.py:651-673, `and_equivalents` of these six languages)
+_CURRENCY: Dict[str, Dict[str, Tuple[Tuple[str, ...], Tuple[str, ...]]]] = {
+    "nl": {"EUR": (("euro", "euro"), ("cent", "cent")), "USD": (("dollar", "dollar"), ("cent", "cent")),
+           "GBP": (("pond", "pond"), ("penny", "pence"))},
+    "hu": {"EUR": (("euró", "euró"), ("cent", "cent")), "USD": (("dollár", "dollár"), ("cent", "cent")),
+           "GBP": (("font", "font"), ("penny", "penny"))},
+    "tr": {"EUR": (("euro", "euro"), ("sent", "sent")), "USD": (("dolar", "dolar"), ("sent", "sent")),
+           "GBP": (("sterlin", "sterlin"), ("peni", "peni"))},
+    "ru": {"EUR": (("евро", "евро", "евро"), ("цент", "цента", "центов")), "USD": (("доллар", "доллара", "долларов"), ("цент", "цента", "центов")),
+           "GBP": (("фунт", "фунта", "фунтов"), ("пенс", "пенса", "пенсов"))},
+    "pl": {"EUR": (("euro", "euro", "euro"), ("cent", "centy", "centów")), "USD": (("dolar", "dolary", "dolarów"), ("cent", "centy", "centów")),
+           "GBP": (("funt", "funty", "funtów"), ("pens", "pensy", "pensów"))},
+    "cs": {"EUR": (("euro", "euro", "euro"), ("cent", "centy", "centů")), "USD": (("dolar", "dolary", "dolarů"), ("cent", "centy", "centů")),
+           "GBP": (("libra", "libry", "liber"), ("pence", "pence", "pencí"))},
+}
+
+
+def currency_words(amount: float, code: str, lang: str) -> str:
+    """5.5 EUR -> 'vijf euro, vijftig cent' / 'пять евро, пятьдесят центов' — always both parts; the caller trims whole amounts."""
+    unit, sub = _CURRENCY[lang][code]
+    whole = int(amount)
+    cents = int(round((amount - whole) * 100))
+    card = CARDINAL[lang]
+
+    def form(n: int, forms: Tuple[str, ...]) -> str:
+        if len(forms) == 3:
+            return forms[_SLAVIC[lang]["plural"](n)]
+        return forms[0] if n == 1 else forms[1]
+    return f"{card(whole)} {form(whole, unit)}, {card(cents)} {form(cents, sub)}"
 
 
 def _split_float(value: float) -> Tuple[str, str]:

@@ -535,7 +535,7 @@ def verbalise(number, ordinal: bool = False, lang: str = "en", to: str = "cardin
         lang = "cs"
     if lang in _MORE.CARDINAL:                 # nl, tr, hu, ru, pl, cs: numwords_more.py (cardinals, fractions, some ordinals)
         if to == "currency":
-            return repr(float(number)) if not float(number).is_integer() else str(int(number))
+            return _MORE.currency_words(float(number), kwargs.get("currency", "EUR"), lang)
         if ordinal or to == "ordinal":
             return _MORE.ORDINAL[lang](int(number)) if lang in _MORE.ORDINAL else str(number)
         return _MORE.decimal_words(number, lang) if isinstance(number, float) else _MORE.CARDINAL[lang](int(number))

@@ -140,8 +140,12 @@ def test_number_words_follow_num2words_conventions():
         "zero", "dwadzieścia jeden", "tysiąc", "dwa tysiące", "pięć tysięcy", "dwanaście tysięcy", "dwadzieścia dwa tysiące", "milion"]
     assert v(3.25, lang="pl") == "trzy przecinek dwadzieścia pięć"
     assert [v(n, lang="cz") for n in (0, 21, 200, 1000, 2000, 5000)] == ["nula", "dvacet jedna", "dvě stě", "tisíc", "dva tisíce", "pět tisíc"]
-    # what is not restated keeps its digits: Arabic and Korean altogether, ordinals and amounts of the six languages above
-    assert v(12, lang="ar") == "12" and v(7, ordinal=True, lang="cz") == "7" and v(5.5, to="currency", currency="EUR", lang="pl") == "5.5"
+    assert v(5.5, to="currency", currency="EUR", lang="nl") == "vijf euro, vijftig cent"
+    assert v(21.05, to="currency", currency="USD", lang="ru") == "двадцать один доллар, пять центов"
+    assert v(2.5, to="currency", currency="EUR", lang="pl") == "dwa euro, pięćdziesiąt centów"
+    assert v(5.22, to="currency", currency="USD", lang="cz") == "pět dolarů, dvacet dva centy"
+    # what is not restated keeps its digits: Arabic and Korean altogether, ordinals of ru / pl / cs
+    assert v(12, lang="ar") == "12" and v(7, ordinal=True, lang="cz") == "7"
 
 
 def test_number_words_are_injective_and_clean():
@@ -169,6 +173,8 @@ def test_cleaners_end_to_end_with_number_words():
     assert T.preprocess_text("To jest 12 & 3", "pl") == "to jest dwanaście i trzy"
     assert T.preprocess_text("Ik heb 21 appels en 3,5 liter op de 3de dag", "nl") == "ik heb eenentwintig appels en drie komma vijf liter op de derde dag"
     assert T.preprocess_text("У меня 21000 рублей", "ru") == "у меня двадцать одна тысяча рублей"
+    assert T.preprocess_text("Het kost 20€ of $5,50.", "nl") == "het kost twintig euro of vijf dollar, vijftig cent."
+    assert T.preprocess_text("Ez 20€ meg 1$.", "hu") == "ez húsz euró meg egy dollár."
     assert T.preprocess_text("هذا 12", "ar") == "هذا 12"                                        # digits kept (no Arabic number words)
     assert T.format_for_bpe("Hello there", "en") == "[en]hello[SPACE]there"
     assert T.format_for_bpe("你好", "zh-cn").startswith("[zh-cn]")
