@@ -6,10 +6,10 @@ against; they restate the library's published conventions (word lists, plural ru
 read) from the languages' grammar.  What IS pinned is everything around them (which spans are numbers, ordinals, amounts, in which
 order they are expanded): `tests/test_text_golden.py` runs our cleaners and the reference's with the same marker verbaliser.
 
-Cardinals for all six; ordinals for Dutch, Turkish and Hungarian; fractions: Dutch digit by digit after "komma" (the base class's reading),
+Cardinals for all six; ordinals for Dutch, Turkish, Hungarian and (masculine nominative) Russian; fractions: Dutch digit by digit after "komma" (the base class's reading),
 Russian / Polish / Czech as an integer after "запятая" / "przecinek" / "celá" with leading zeros spoken (those three modules
-share that code), Hungarian "egész ... tized / század / ezred"; amounts of money as "<amount> <unit>, <cents> <sub-unit>".  The other
-ordinals (ru / pl / cs) keep their digits."""
+share that code), Hungarian "egész ... tized / század / ezred"; amounts of money as "<amount> <unit>, <cents> <sub-unit>".  Polish and
+Czech ordinals keep their digits (and are then read as cardinals)."""
 from typing import Callable, Dict, List, Tuple
 
 
@@ -268,6 +268,29 @@ def cardinal_ru(n: int) -> str:
     return _slavic_cardinal(n, "ru")
 
 
+_RU_ORD_WORD = {"один": "первый", "одна": "первый", "два": "второй", "две": "второй", "три": "третий", "четыре": "четвертый", "пять": "пятый",
+                "шесть": "шестой", "семь": "седьмой", "восемь": "восьмой", "девять": "девятый", "десять": "десятый",
+                "одиннадцать": "одиннадцатый", "двенадцать": "двенадцатый", "тринадцать": "тринадцатый", "четырнадцать": "четырнадцатый",
+                "пятнадцать": "пятнадцатый", "шестнадцать": "шестнадцатый", "семнадцать": "семнадцатый", "восемнадцать": "восемнадцатый",
+                "девятнадцать": "девятнадцатый", "двадцать": "двадцатый", "тридцать": "тридцатый", "сорок": "сороковой",
+                "пятьдесят": "пятидесятый", "шестьдесят": "шестидесятый", "семьдесят": "семидесятый", "восемьдесят": "восьмидесятый",
+                "девяносто": "девяностый", "сто": "сотый", "двести": "двухсотый", "триста": "трехсотый", "четыреста": "четырехсотый",
+                "пятьсот": "пятисотый", "шестьсот": "шестисотый", "семьсот": "семисотый", "восемьсот": "восьмисотый",
+                "девятьсот": "девятисотый", "ноль": "нулевой"}
+_RU_THOUSANDS_PREFIX = {1: "", 2: "двух", 3: "трех", 4: "четырех", 5: "пяти", 6: "шести", 7: "семи", 8: "восьми", 9: "девяти", 10: "десяти"}
+
+
+def ordinal_ru(n: int) -> str:
+    """Masculine nominative: 21 -> 'двадцать первый', 100 -> 'сотый', 2000 -> 'двухтысячный'.  Only the last word of the cardinal
+    changes; round thousands above ten thousand and round millions keep their digits (the caller then reads them as cardinals)."""
+    if n % 1000 == 0 and n > 0:
+        k = n // 1000
+        return _RU_THOUSANDS_PREFIX[k] + "тысячный" if k in _RU_THOUSANDS_PREFIX else str(n)
+    words = cardinal_ru(n).split(" ")
+    words[-1] = _RU_ORD_WORD.get(words[-1], words[-1])
+    return " ".join(words)
+
+
 def cardinal_pl(n: int) -> str:
     """1000 -> 'tysiąc', 2000 -> 'dwa tysiące', 5000 -> 'pięć tysięcy'."""
     return _slavic_cardinal(n, "pl")
@@ -281,7 +304,7 @@ def cardinal_cs(n: int) -> str:
 # --------------------------------------------------------------------------------------------------- tables for textnorm.verbalise
 CARDINAL: Dict[str, Callable[[int], str]] = {"nl": cardinal_nl, "tr": cardinal_tr, "hu": cardinal_hu, "ru": cardinal_ru,
                                              "pl": cardinal_pl, "cs": cardinal_cs}
-ORDINAL: Dict[str, Callable[[int], str]] = {"nl": ordinal_nl, "tr": ordinal_tr, "hu": ordinal_hu}
+ORDINAL: Dict[str, Callable[[int], str]] = {"nl": ordinal_nl, "tr": ordinal_tr, "hu": ordinal_hu, "ru": ordinal_ru}
 
 
 # (unit forms, sub-unit forms): two forms (one / many) for nl, hu, tr; three (1 / 2-4 / 5+, picked by the language's plural rule)

@@ -12,7 +12,7 @@ What is pinned and how (tests/test_text_golden.py, vectors in tests/golden/text_
   * the number WORDS come from the third-party `num2words` package (not installed here, not vendored by the
     reference).  `verbalise()` restates its conventions for en / es / fr / de / it / pt (the languages of
     BASELINE.json's multilingual config that use digits) and, in `numwords_more.py`, for nl / tr / hu / ru / pl / cs (cardinals,
-    fractions, amounts of money, Dutch / Turkish / Hungarian ordinals); there is no copy of num2words to check against, so the word lists are "parity
+    fractions, amounts of money, Dutch / Turkish / Hungarian / Russian ordinals); there is no copy of num2words to check against, so the word lists are "parity
     unpinned" (DESIGN.md §7).  For ar / ko digits are kept.
   * zh number normalisation is the reference's own `zh_num2words.TextNorm`: restated in `zh_textnorm.py` and pinned against
     that module (golden records + live fuzz, tests/test_zh_textnorm.py).  The zh / ja / ko romanisation is

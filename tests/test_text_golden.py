@@ -136,6 +136,8 @@ def test_number_words_follow_num2words_conventions():
         "ноль", "двадцать один", "сто один", "одна тысяча", "две тысячи", "пять тысяч", "одиннадцать тысяч", "двадцать одна тысяча",
         "один миллион", "два миллиона", "пять миллионов"]
     assert v(3.05, lang="ru") == "три запятая ноль пять"
+    assert [v(n, ordinal=True, lang="ru") for n in (1, 3, 11, 21, 40, 100, 121, 1000, 2000)] == [
+        "первый", "третий", "одиннадцатый", "двадцать первый", "сороковой", "сотый", "сто двадцать первый", "тысячный", "двухтысячный"]
     assert [v(n, lang="pl") for n in (0, 21, 1000, 2000, 5000, 12000, 22000, 1000000)] == [
         "zero", "dwadzieścia jeden", "tysiąc", "dwa tysiące", "pięć tysięcy", "dwanaście tysięcy", "dwadzieścia dwa tysiące", "milion"]
     assert v(3.25, lang="pl") == "trzy przecinek dwadzieścia pięć"
@@ -144,7 +146,7 @@ def test_number_words_follow_num2words_conventions():
     assert v(21.05, to="currency", currency="USD", lang="ru") == "двадцать один доллар, пять центов"
     assert v(2.5, to="currency", currency="EUR", lang="pl") == "dwa euro, pięćdziesiąt centów"
     assert v(5.22, to="currency", currency="USD", lang="cz") == "pět dolarů, dvacet dva centy"
-    # what is not restated keeps its digits: Arabic and Korean altogether, ordinals of ru / pl / cs
+    # what is not restated keeps its digits: Arabic and Korean altogether, ordinals of pl / cs
     assert v(12, lang="ar") == "12" and v(7, ordinal=True, lang="cz") == "7"
 
 
