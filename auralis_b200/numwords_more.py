@@ -302,9 +302,22 @@ def cardinal_cs(n: int) -> str:
 
 
 # --------------------------------------------------------------------------------------------------- tables for textnorm.verbalise
-CARDINAL: Dict[str, Callable[[int], str]] = {"nl": cardinal_nl, "tr": cardinal_tr, "hu": cardinal_hu, "ru": cardinal_ru,
-                                             "pl": cardinal_pl, "cs": cardinal_cs}
-ORDINAL: Dict[str, Callable[[int], str]] = {"nl": ordinal_nl, "tr": ordinal_tr, "hu": ordinal_hu, "ru": ordinal_ru}
+_LIMIT = 10 ** 15           # the scale tables end at 10^12 (x 999): longer digit strings (ids, phone numbers) are read digit by digit
+
+
+def _bounded(card: Callable[[int], str]) -> Callable[[int], str]:
+    def f(n: int) -> str:
+        if abs(n) >= _LIMIT:
+            return " ".join(card(int(d)) for d in str(abs(n)))
+        return card(n)
+    f.__doc__ = card.__doc__
+    return f
+
+
+CARDINAL: Dict[str, Callable[[int], str]] = {k: _bounded(c) for k, c in (("nl", cardinal_nl), ("tr", cardinal_tr), ("hu", cardinal_hu),
+                                                                          ("ru", cardinal_ru), ("pl", cardinal_pl), ("cs", cardinal_cs))}
+ORDINAL: Dict[str, Callable[[int], str]] = {k: (lambda n, o=o, k=k: o(n) if abs(n) < _LIMIT else CARDINAL[k](n))
+                                            for k, o in (("nl", ordinal_nl), ("tr", ordinal_tr), ("hu", ordinal_hu), ("ru", ordinal_ru))}
 
 
 # (unit forms, sub-unit forms): two forms (one / many) for nl, hu, tr; three (1 / 2-4 / 5+, picked by the language's plural rule)

@@ -164,6 +164,19 @@ def test_number_words_are_injective_and_clean():
             seen[w] = n
 
 
+def test_long_digit_strings_never_raise():
+    """Ids and phone numbers are digit strings too: every cleaned language must read them somehow (beyond their scale tables
+    the six languages of numwords_more.py go digit by digit), never raise."""
+    for lang in ("en", "es", "fr", "de", "it", "pt", "nl", "tr", "hu", "ru", "pl", "cs", "ar", "ko"):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = T.preprocess_text("id 123456789012345678901234567890, 999999999999999 and 1000000000000000.", lang)
+        assert out and "  " not in out
+    assert T.verbalise(10 ** 15, lang="ru") == "один ноль ноль ноль ноль ноль ноль ноль ноль ноль ноль ноль ноль ноль ноль ноль"
+    assert T.verbalise(10 ** 15 - 1, lang="pl").startswith("dziewięćset dziewięćdziesiąt dziewięć bilionów")
+
+
 def test_cleaners_end_to_end_with_number_words():
     c = T.preprocess_text('Dr. Smith paid $5.50 for the 21st "copy", 1,234 in all & 3.5% more.', "en")
     assert c == ("doctor smith paid five dollars, fifty cents for the twenty-first copy, one thousand, two hundred and "
